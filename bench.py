@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py -- queries/sec of the FSPANN query hot path (TokenGen -> Route -> Refine) on B200.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one process per GPU under torchrun)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm (oracle port) on host cores
+
+A "step" = one pass of the hot path over one batch of synthetic queries (BASELINE.json configs[1]: SIFT1M-shape
+1M x 128, L=8 tables, D=8, m=24, lambda=2, B=1024, k=10, 10k-query batch).  For N>1 every rank holds a replica of the
+routing index and the record store and searches its own 10k batch per step (weak scaling, no data-path collective).
+`value`  = queries/sec with the query batches already resident in HBM (CUDA events on the library's stream).
+`e2e`    = the same through the host-buffer C-ABI call (pinned host queries -> H2D -> search -> D2H of results).
+The oracle (oracle/) is used ONLY for the cpu_baseline / --impl reference legs, as the thing being timed there.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from fspann_query_system_b200 import hostsetup as HS  # noqa: E402
+from fspann_query_system_b200 import workloads as WL  # noqa: E402
+
+
+def log(*a):
+    if int(os.environ.get("RANK", "0")) == 0:
+        print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def build_world(cfg: WL.Config, gpu, n_batches: int, rank: int):
+    """Setup (host side, untimed): synthetic base set, GFunctions, encrypted store, greedy partitions; upload to HBM."""
+    t0 = time.time()
+    base = WL.base_vectors(cfg)
+    alpha, r, omega = HS.build_gfunctions(base[:HS.MIN_SAMPLE_SIZE], cfg.m, cfg.lam, cfg.seed, cfg.T, cfg.D)
+    log(f"base {base.shape} + GFunctions in {time.time() - t0:.1f}s")
+    t0 = time.time()
+    gpu.gfunctions_upload(cfg.dim, cfg.T, cfg.D, cfg.m, cfg.lam, alpha, r, omega)
+    codes = np.empty((cfg.N, cfg.T * cfg.D, cfg.W), dtype=np.uint64)
+    for s in range(0, cfg.N, 131072):
+        e = min(cfg.N, s + 131072)
+        codes[s:e] = gpu.tokengen_batch(base[s:e])        # Setup-side bulk coding reuses the TokenGen kernel
+    log(f"base codes (GPU TokenGen) in {time.time() - t0:.1f}s")
+    t0 = time.time()
+    mn, mx, rep, ids = HS.build_partitions(codes, HS.staged_order(cfg.N))
+    gpu.routing_upload(cfg.dim, cfg.T, cfg.D, cfg.m, cfg.lam, alpha, r, omega, mn, mx, rep, ids)
+    log(f"greedy partitions ({cfg.T * cfg.D} x {mn.shape[1]}) in {time.time() - t0:.1f}s")
+    t0 = time.time()
+    km = HS.KeyManager(WL.MASTER_KEY)
+    iv = WL.record_ivs(cfg.N, cfg.base_seed + 5)
+    ct = HS.encrypt_store(base, np.arange(cfg.N, dtype=np.int32), 1, km.derive(1), iv)
+    ver = np.ones(cfg.N, dtype=np.int32)
+    gpu.keys_set(1, km.derive(1))
+    gpu.store_upload(cfg.dim, iv, ct, ver)
+    log(f"encrypted store ({ct.nbytes / 1e9:.2f} GB) in {time.time() - t0:.1f}s")
+    batches = []
+    for b in range(n_batches):
+        qcfg = cfg.scaled(name=cfg.name)
+        object.__setattr__(qcfg, "query_seed", cfg.query_seed + 7919 * b + 104729 * rank)
+        batches.append(WL.query_vectors(qcfg))
+    world = dict(alpha=alpha, r=r, omega=omega, mn=mn, mx=mx, rep=rep, ids=ids, iv=iv, ct=ct, ver=ver, keys={1: km.derive(1)}, base=base)
+    return world, batches
+
+
+def oracle_objects(cfg, world):
+    from oracle import oracle as O
+    g = O.GFunctions(cfg.dim, cfg.T, cfg.D, cfg.m, cfg.lam, world["alpha"], world["r"], world["omega"])
+    ix = O.Index(g, cfg.N, world["mn"].shape[1], world["mn"], world["mx"], world["rep"], world["ids"])
+    st = O.Store(cfg.dim, world["iv"], world["ct"], world["ver"], dict(world["keys"]))
+    return O, ix, st
+
+
+def cpu_run(cfg, O, ix, st, queries, threads: int):
+    """The reference algorithm (oracle port) over `queries`, statically partitioned over `threads` host threads."""
+    Q = queries.shape[0]
+    out = dict(top_ids=np.full((Q, cfg.k), -1, dtype=np.int32), top_dist=np.full((Q, cfg.k), np.nan), n_ret=np.zeros(Q, dtype=np.int32),
+               counters=np.zeros((Q, 6), dtype=np.int64))
+    bounds = np.linspace(0, Q, threads + 1).astype(int)
+    ts = [threading.Thread(target=O.search_batch, args=(ix, st, queries, cfg.k, cfg.probes, cfg.hard_cap, cfg.B, 0, int(bounds[i]), int(bounds[i + 1]), out))
+          for i in range(threads) if bounds[i + 1] > bounds[i]]
+    t0 = time.perf_counter()
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    return time.perf_counter() - t0, out
+
+
+def world_cpu_only(cfg):
+    """--impl reference needs the same world without touching our CUDA library: the base codes come from the oracle."""
+    from oracle import oracle as O
+    base = WL.base_vectors(cfg)
+    alpha, r, omega = HS.build_gfunctions(base[:HS.MIN_SAMPLE_SIZE], cfg.m, cfg.lam, cfg.seed, cfg.T, cfg.D)
+    g = O.GFunctions(cfg.dim, cfg.T, cfg.D, cfg.m, cfg.lam, alpha, r, omega)
+    threads = os.cpu_count() or 1
+    codes = np.zeros((cfg.N, cfg.T * cfg.D, cfg.W), dtype=np.uint64)
+    bounds = np.linspace(0, cfg.N, threads * 4 + 1).astype(int)
+
+    def work(i):
+        codes[bounds[i]:bounds[i + 1]] = O.tokengen_batch(base[bounds[i]:bounds[i + 1]], g)
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(threads * 4)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    mn, mx, rep, ids = HS.build_partitions(codes, HS.staged_order(cfg.N))
+    km = HS.KeyManager(WL.MASTER_KEY)
+    iv = WL.record_ivs(cfg.N, cfg.base_seed + 5)
+    ct = O.encrypt_store(base, 1, km.derive(1), iv)
+    return dict(alpha=alpha, r=r, omega=omega, mn=mn, mx=mx, rep=rep, ids=ids, iv=iv, ct=ct, ver=np.ones(cfg.N, dtype=np.int32), keys={1: km.derive(1)})
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default=os.environ.get("FSPANN_BENCH_CONFIG", "C2"))
+    ap.add_argument("--n", type=int, default=0, help="override N (debug)")
+    ap.add_argument("--q", type=int, default=0, help="override batch size (debug)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    cfg = WL.CONFIGS[args.config]
+    if args.n or args.q:
+        cfg = cfg.scaled(N=args.n or None, Q=args.q or None)
+    metric = "queries/sec at recall@10 (fixed budget B)"
+    config = {"workload": f"{cfg.name}: N={cfg.N} d={cfg.dim} T={cfg.T} D={cfg.D} m={cfg.m} lambda={cfg.lam} probes={cfg.probes} "
+                          f"B={cfg.B} k={cfg.k} maxGlobalCandidates={cfg.max_global} Q={cfg.Q}/step/GPU",
+              "parallelism": f"query batch per GPU x{max(args.gpus, 1)}, routing index + store replicated, no collective",
+              "l2": "inputs larger than L2 (store 1.06 GB + routing ids 0.26 GB vs 126 MB L2); a different query batch every step"}
+
+    # ------------------------------------------------------------------ reference arm: oracle port on the host cores
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        from oracle import oracle as O
+        threads = os.cpu_count() or 1
+        world = world_cpu_only(cfg)
+        O, ix, st = oracle_objects(cfg, world)
+        per_step = max(threads * 48, 64)
+        times = []
+        for s in range(args.warmup + args.steps):
+            qcfg = cfg.scaled(name=cfg.name)
+            object.__setattr__(qcfg, "query_seed", cfg.query_seed + 7919 * s)
+            qs = WL.query_vectors(qcfg, per_step)
+            dt, _ = cpu_run(cfg, O, ix, st, qs, threads)
+            if s >= args.warmup:
+                times.append(dt)
+        total = sum(times)
+        val = per_step * args.steps / total
+        sample = f"{per_step} queries/step of the {cfg.Q}-query workload, all {threads} host threads, in-memory store, OpenSSL AES-NI GCM"
+        print(json.dumps({"impl": "reference", "metric": metric, "value": val, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                          "cpu_baseline": {"value": val, "unit": "queries/s", "cores": threads, "kind": "port", "sample": sample},
+                          "e2e": {"value": val, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "note": "reference is pure Java and no JVM exists in this image: this is the C restatement of its algorithm (oracle/), optimistic for the CPU"}))
+        return
+
+    # ------------------------------------------------------------------ our arm
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the FSPANN hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world_size > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from fspann_query_system_b200.gpu import GpuContext
+    gpu = GpuContext(local_rank)
+    K, Wm = args.steps, args.warmup
+    n_batches = min(K + Wm, 6)
+    world, batches = build_world(cfg, gpu, n_batches, rank)
+    Q, k, dim = cfg.Q, cfg.k, cfg.dim
+
+    stream = torch.cuda.ExternalStream(gpu.stream(), device=torch.device("cuda", local_rank))
+    d_batches = [torch.from_numpy(b).cuda() for b in batches]
+    d_ids = torch.empty((Q, k), dtype=torch.int32, device="cuda")
+    d_dist = torch.empty((Q, k), dtype=torch.float64, device="cuda")
+    d_nret = torch.empty((Q,), dtype=torch.int32, device="cuda")
+    d_cnt = torch.empty((Q, 6), dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+
+    def step_dev(i):
+        gpu.search_batch_dev(Q, d_batches[i % n_batches].data_ptr(), k, cfg.probes, cfg.hard_cap, cfg.B, 0, 1, d_ids.data_ptr(), d_dist.data_ptr(),
+                             d_nret.data_ptr(), d_cnt.data_ptr())
+
+    def barrier():
+        if world_size > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        gpu.sync()
+
+    # ---- value: inputs resident in HBM
+    for i in range(Wm):
+        step_dev(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = gpu.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(K):
+        step_dev(Wm + i)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = gpu.launch_count() - l0
+    clocks = sampler.stop()
+
+    # ---- roofline of the dominant kernel (refine decrypt+distance), measured live with CUDA events on the launching stream
+    stage = dict(tokengen=0.0, route=0.0, group=0.0, decrypt=0.0, topk=0.0)
+    pairs = 0
+    for i in range(K):
+        step_dev(Wm + i)
+        sm = gpu.stage_ms()
+        for key in stage:
+            stage[key] += sm[key]
+        pairs += int(d_cnt[:, 5].sum().item())
+    dec_ms = stage["decrypt"] / K
+    alg_bytes = pairs / K * (8 * dim + 36) + Q * (8 * dim + 12 * k)       # per pair 8d+36 B, per query 8d+12k B
+    peak, peak_src = load_peaks()
+    achieved = alg_bytes / (dec_ms * 1e-3) / 1e9 if dec_ms > 0 else 0.0
+
+    # ---- e2e: host buffers through the public C-ABI call (pinned queries -> H2D -> search -> D2H results)
+    h_q = [torch.from_numpy(b).pin_memory() for b in batches]
+    h_ids = torch.empty((Q, k), dtype=torch.int32).pin_memory()
+    h_dist = torch.empty((Q, k), dtype=torch.float64).pin_memory()
+    h_nret = torch.empty((Q,), dtype=torch.int32).pin_memory()
+    h_cnt = torch.empty((Q, 6), dtype=torch.int64).pin_memory()
+
+    def step_host(i):
+        gpu.search_batch_raw(Q, h_q[i % n_batches].data_ptr(), k, cfg.probes, cfg.hard_cap, cfg.B, 0, h_ids.data_ptr(), h_dist.data_ptr(),
+                             h_nret.data_ptr(), h_cnt.data_ptr())
+    for i in range(Wm):
+        step_host(i)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall = time.perf_counter()
+    f0.record(stream)
+    for i in range(K):
+        step_host(Wm + i)
+    f1.record(stream)
+    barrier()
+    e2e_ms = max(f0.elapsed_time(f1), (time.perf_counter() - t_wall) * 1e3 * 0.0)
+    e2e_wall_ms = (time.perf_counter() - t_wall) * 1e3
+    checksum = int(h_ids.to(torch.int64).sum().item())
+
+    if world_size > 1:
+        t = torch.tensor([ms, e2e_ms, e2e_wall_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms, e2e_wall_ms = (float(x) for x in t.tolist())
+        ln = torch.tensor([launches], dtype=torch.int64, device="cuda")
+        dist.all_reduce(ln)
+        launches = int(ln.item())
+    total_q = Q * K * world_size
+    value = total_q / (ms * 1e-3)
+    e2e_val = total_q / (e2e_ms * 1e-3)
+
+    # ---- CPU baseline beside it: the oracle port on this box's host cores (rank 0, N=1 only; bounded sample)
+    cpu_baseline = None
+    if rank == 0 and world_size == 1 and not args.no_cpu_baseline:
+        O, ix, st = oracle_objects(cfg, world)
+        threads = os.cpu_count() or 1
+        nq = min(Q, max(64, threads * 96))
+        dt, ref = cpu_run(cfg, O, ix, st, batches[0][:nq], threads)
+        dt1, _ = cpu_run(cfg, O, ix, st, batches[0][:min(nq, 96)], 1)
+        # the GPU result for the same queries must be identical (ids exact, FP64 distances bit-exact)
+        got = gpu.search_batch(batches[0][:nq], k, cfg.probes, cfg.hard_cap, cfg.B)
+        same = bool(np.array_equal(got["top_ids"], ref["top_ids"]) and np.array_equal(got["top_dist"].view(np.uint64), ref["top_dist"].view(np.uint64)))
+        cpu_baseline = {"value": nq / dt, "unit": "queries/s", "cores": threads, "kind": "port",
+                        "sample": f"first {nq} queries of batch 0, {threads} threads; single-thread: {min(nq, 96) / dt1:.1f} queries/s on {min(nq, 96)} queries",
+                        "single_thread_value": min(nq, 96) / dt1, "gpu_matches_oracle_on_sample": same}
+
+    if rank == 0:
+        out = {"metric": metric, "value": value, "unit": "queries/s", "n_gpus": world_size, "steps": K, "warmup": Wm, "ms_per_step": ms / K,
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+               "clocks": clocks, "gpu_launches": launches,
+               "e2e": {"value": e2e_val, "unit": "queries/s", "h2d_bytes_per_step": Q * dim * 8, "d2h_bytes_per_step": Q * k * 12 + Q * 4 + Q * 48,
+                       "ms_per_step": e2e_ms / K, "wall_ms_per_step": e2e_wall_ms / K, "result_checksum": checksum},
+               "roofline": {"bound": "hbm", "kernel": "refine_decrypt_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                            "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src,
+                            "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": dec_ms, "pairs_per_launch": pairs / K},
+               "stage_ms_per_step": {s: v / K for s, v in stage.items()},
+               "cpu_baseline": cpu_baseline}
+        print(json.dumps(out))
+    gpu.close()
+    if world_size > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,655 @@
+// abi.cu -- the C ABI of libfspann_gpu.so (include/fspann_gpu.h): context, uploads, batched entry points.
+// Host-side orchestration only; all arithmetic of the hot path runs in the kernels of tokengen.cu / route.cu /
+// refine.cu.  There is no CPU fallback: every compute entry point fails with FSPANN_E_CUDA if the device path fails.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+
+#include "fspann_internal.cuh"
+
+using namespace fsp;
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace
+
+struct fspann_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+
+    // routing state
+    bool routing_ready = false;
+    RoutingView rv{};
+    DevBuf d_alpha, d_r, d_omega, d_keys, d_rep, d_ids, d_deleted;
+
+    // store
+    bool store_ready = false;
+    StoreView sv{};
+    DevBuf d_rec, d_keyring, d_hpow, d_te0, d_touched;
+    std::map<int32_t, std::vector<uint8_t>> keys;  // live versions -> raw key
+
+    // scratch (grow only)
+    DevBuf s_queries, s_codes, s_cand_ids, s_cand_sc, s_ncand, s_raw, s_uniq_cnt, s_route_scratch, s_overflow;
+    DevBuf s_cnt, s_flag, s_fill, s_uniq, s_pairs, s_bsums, s_totals, s_dist, s_verdict;
+    DevBuf s_topk_ids, s_topk_dist, s_nret, s_ndec, s_counters;
+    DevBuf s_stage_a, s_stage_b, s_stage_c;  // upload staging
+    DevBuf r_rows, r_queries, r_codes, r_topk_ids, r_topk_dist, r_nret, r_counters;  // retry subset
+    DevBuf t_cand_ids, t_cand_sc, t_ncand, t_raw, t_uniq_cnt, t_ndec;               // retry subset route outputs
+
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool ev_valid = false;
+    int64_t last_call_launches = 0;
+};
+
+namespace {
+
+int fail(fspann_ctx *c, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e__ = (call);                                                                         \
+        if (e__ != cudaSuccess) return fail(ctx, e__ == cudaErrorMemoryAllocation ? FSPANN_E_NOMEM : FSPANN_E_CUDA, \
+                                            "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+#define LAUNCHED(expr)                                                                              \
+    do {                                                                                            \
+        int n__ = (expr);                                                                           \
+        if (n__ < 0) return fail(ctx, FSPANN_E_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(cudaGetLastError()), __FILE__, __LINE__); \
+        ctx->launches += n__;                                                                       \
+    } while (0)
+
+int ensure(fspann_ctx *ctx, DevBuf &b, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    if (b.bytes >= bytes) return 0;
+    if (b.p) { cudaFree(b.p); b.p = nullptr; b.bytes = 0; }
+    size_t want = bytes + (bytes >> 3);
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) { want = bytes; e = cudaMalloc(&b.p, want); }
+    if (e != cudaSuccess) { b.p = nullptr; return fail(ctx, FSPANN_E_NOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e)); }
+    b.bytes = want;
+    return 0;
+}
+#define ENSURE(buf, bytes) do { int rc__ = ensure(ctx, buf, bytes); if (rc__) return rc__; } while (0)
+
+void release(DevBuf &b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.bytes = 0; }
+
+uint32_t table_size_for(int64_t cap) {  // java.util.HashMap.tableSizeFor
+    if (cap <= 1) return 1;
+    uint32_t n = 1;
+    while ((int64_t)n < cap && n < (1u << 30)) n <<= 1;
+    return n;
+}
+
+struct TeHost { const uint32_t *t; uint32_t operator()(uint32_t x) const { return t[x]; } };
+struct RkHost { const uint32_t *r; uint32_t operator()(int i) const { return r[i]; } };
+
+// Rebuilds the device key ring (round keys) and GHASH key-power tables from ctx->keys.
+int rebuild_keys(fspann_ctx *ctx) {
+    static uint32_t te0[256];
+    static bool te_init = false;
+    if (!te_init) { aes_make_te0(te0); te_init = true; }
+    DevKeyRing ring;
+    memset(&ring, 0, sizeof ring);
+    const int dim = ctx->sv.dim > 0 ? ctx->sv.dim : 0;
+    const int c = (8 * dim + 15) / 16;
+    const int npow = c + 4;
+    std::vector<u128> hp((size_t)kMaxKeys * (npow + 1));
+    int n = 0;
+    for (auto &kv : ctx->keys) {
+        ring.version[n] = kv.first;
+        aes256_expand_key(kv.second.data(), ring.rk[n]);
+        uint32_t h[4];
+        aes256_encrypt(TeHost{te0}, RkHost{ring.rk[n]}, 0u, 0u, 0u, 0u, h);   // H = E_K(0^128)
+        u128 H{((uint64_t)h[0] << 32) | h[1], ((uint64_t)h[2] << 32) | h[3]};
+        u128 *row = hp.data() + (size_t)n * (npow + 1);
+        row[0] = u128{0, 0};
+        row[1] = H;
+        for (int p = 2; p <= npow; p++) row[p] = gf128_mul_ref(row[p - 1], H);
+        n++;
+    }
+    ring.n = n;
+    ENSURE(ctx->d_keyring, sizeof ring);
+    ENSURE(ctx->d_hpow, sizeof(u128) * hp.size());
+    CK(cudaMemcpyAsync(ctx->d_keyring.p, &ring, sizeof ring, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_hpow.p, hp.data(), sizeof(u128) * hp.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));   // host vectors go out of scope
+    ctx->sv.keys = (const DevKeyRing *)ctx->d_keyring.p;
+    ctx->sv.hpow = (const u128 *)ctx->d_hpow.p;
+    ctx->sv.npow = npow;
+    return 0;
+}
+
+int check_routing(fspann_ctx *ctx) {
+    if (!ctx->routing_ready) return fail(ctx, FSPANN_E_STATE, "Index not finalized: no routing state uploaded (PIS:594)");
+    return 0;
+}
+int check_store(fspann_ctx *ctx) {
+    if (!ctx->store_ready) return fail(ctx, FSPANN_E_STATE, "record store not uploaded");
+    if (ctx->routing_ready && ctx->rv.dim != ctx->sv.dim) return fail(ctx, FSPANN_E_STATE, "dimension mismatch: routing dim=%d store dim=%d", ctx->rv.dim, ctx->sv.dim);
+    return 0;
+}
+
+int record_ev(fspann_ctx *ctx, int i) {
+    CK(cudaEventRecord(ctx->ev[i], ctx->stream));
+    return 0;
+}
+
+// Route for Q queries whose codes are on the device.
+int do_route(fspann_ctx *ctx, int64_t Q, const uint64_t *d_codes, int probes, int64_t hard_cap, int B, int32_t *d_cand_ids,
+             int32_t *d_cand_sc, int32_t *d_ncand, int32_t *d_raw, int32_t *d_uniq) {
+    const RoutingView &rv = ctx->rv;
+    if (probes < 0) probes = 0;
+    if ((int64_t)rv.TD * std::max(probes, 1) >= 262144) return fail(ctx, FSPANN_E_ARG, "T*D*probes too large (%d*%d)", rv.TD, probes);
+    RouteParams p{};
+    p.Q = Q; p.codes = d_codes; p.probes = probes; p.hard_cap = hard_cap; p.B = B;
+    p.cand_ids = d_cand_ids; p.cand_scores = d_cand_sc; p.n_cand = d_ncand; p.raw_seen = d_raw; p.unique = d_uniq;
+    p.cap0 = (int32_t)table_size_for(std::min<int64_t>(hard_cap, 65536));           // PIS:619
+    int64_t max_nodes = (int64_t)rv.TD * probes * kBlock;
+    if (max_nodes > hard_cap + kBlock) max_nodes = hard_cap + kBlock;
+    if (max_nodes < kBlock) max_nodes = kBlock;
+    p.max_nodes = (int32_t)max_nodes;
+    p.scratch_ints = route_scratch_ints(p.cap0, p.max_nodes);
+    const int grid = route_grid(Q, ctx->sm_count);
+    ENSURE(ctx->s_route_scratch, sizeof(int32_t) * (size_t)p.scratch_ints * grid);
+    ENSURE(ctx->s_overflow, sizeof(int32_t));
+    p.scratch = (int32_t *)ctx->s_route_scratch.p;
+    p.chain_overflow = (int32_t *)ctx->s_overflow.p;
+    CK(cudaMemsetAsync(d_cand_ids, 0xff, sizeof(int32_t) * (size_t)Q * B, ctx->stream));
+    CK(cudaMemsetAsync(d_cand_sc, 0xff, sizeof(int32_t) * (size_t)Q * B, ctx->stream));
+    LAUNCHED(launch_route(ctx->stream, rv, p, grid));
+    return 0;
+}
+
+// Refine for Q queries; everything on the device.
+int do_refine(fspann_ctx *ctx, int64_t Q, const double *d_queries, const int32_t *d_cand_ids, const int32_t *d_ncand, int stride, int k,
+              int32_t *d_topk_ids, double *d_topk_dist, int32_t *d_nret, int32_t *d_ndec, bool stage_events) {
+    const StoreView &sv = ctx->sv;
+    const int64_t total = Q * (int64_t)stride;
+    if (total >= (1LL << 31)) return fail(ctx, FSPANN_E_ARG, "Q*B too large for one batch (%lld)", (long long)total);
+    const int64_t n1 = sv.N + 1;
+    const int nblocks = (int)((n1 + 2047) / 2048);
+    ENSURE(ctx->s_cnt, sizeof(int32_t) * (size_t)n1);
+    ENSURE(ctx->s_fill, sizeof(int32_t) * (size_t)n1);
+    ENSURE(ctx->s_uniq, sizeof(int32_t) * (size_t)std::min<int64_t>(n1, total + 1));
+    ENSURE(ctx->s_pairs, sizeof(uint32_t) * (size_t)(total + 1));
+    ENSURE(ctx->s_bsums, sizeof(int32_t) * 2 * (size_t)(nblocks + 1));
+    ENSURE(ctx->s_totals, sizeof(int32_t) * 4);
+    ENSURE(ctx->s_dist, sizeof(double) * (size_t)(total + 1));
+    ENSURE(ctx->s_verdict, (size_t)(total + 1));
+    RefineParams p{};
+    p.Q = Q; p.queries = d_queries; p.cand_ids = d_cand_ids; p.n_cand = d_ncand; p.stride = stride; p.k = k;
+    p.cnt = (int32_t *)ctx->s_cnt.p; p.fill = (int32_t *)ctx->s_fill.p; p.uniq = (int32_t *)ctx->s_uniq.p;
+    p.pairs = (uint32_t *)ctx->s_pairs.p; p.block_sums = (int32_t *)ctx->s_bsums.p; p.totals = (int32_t *)ctx->s_totals.p;
+    p.dist = (double *)ctx->s_dist.p; p.verdict = (uint8_t *)ctx->s_verdict.p; p.touched = (uint32_t *)ctx->d_touched.p;
+    p.topk_ids = d_topk_ids; p.topk_dist = d_topk_dist; p.n_ret = d_nret; p.n_dec = d_ndec;
+    LAUNCHED(launch_refine_group(ctx->stream, sv, p));
+    if (stage_events) { int rc = record_ev(ctx, 3); if (rc) return rc; }
+    LAUNCHED(launch_refine_decrypt(ctx->stream, sv, p, ctx->sm_count));
+    if (stage_events) { int rc = record_ev(ctx, 4); if (rc) return rc; }
+    LAUNCHED(launch_refine_topk(ctx->stream, p));
+    if (stage_events) { int rc = record_ev(ctx, 5); if (rc) return rc; }
+    return 0;
+}
+
+bool all_finite(const double *v, int64_t n) {
+    for (int64_t i = 0; i < n; i++) if (!std::isfinite(v[i])) return false;
+    return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fspann_ctx_create(int device, fspann_ctx **out) {
+    if (!out) return FSPANN_E_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return FSPANN_E_CUDA;   // no GPU, no service: there is no CPU path
+    if (device < 0 || device >= ndev) return FSPANN_E_ARG;
+    fspann_ctx *ctx = new fspann_ctx();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return FSPANN_E_CUDA; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return FSPANN_E_CUDA; }
+    for (int i = 0; i < 6; i++) cudaEventCreate(&ctx->ev[i]);
+    uint32_t te0[256];
+    aes_make_te0(te0);
+    if (ensure(ctx, ctx->d_te0, sizeof te0) || cudaMemcpy(ctx->d_te0.p, te0, sizeof te0, cudaMemcpyHostToDevice) != cudaSuccess) {
+        fspann_ctx_destroy(ctx);
+        return FSPANN_E_CUDA;
+    }
+    ctx->sv.te0 = (const uint32_t *)ctx->d_te0.p;
+    if (rebuild_keys(ctx)) { fspann_ctx_destroy(ctx); return FSPANN_E_CUDA; }
+    *out = ctx;
+    return FSPANN_OK;
+}
+
+void fspann_ctx_destroy(fspann_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    DevBuf *bufs[] = {&ctx->d_alpha, &ctx->d_r, &ctx->d_omega, &ctx->d_keys, &ctx->d_rep, &ctx->d_ids, &ctx->d_deleted, &ctx->d_rec,
+                      &ctx->d_keyring, &ctx->d_hpow, &ctx->d_te0, &ctx->d_touched, &ctx->s_queries, &ctx->s_codes, &ctx->s_cand_ids,
+                      &ctx->s_cand_sc, &ctx->s_ncand, &ctx->s_raw, &ctx->s_uniq_cnt, &ctx->s_route_scratch, &ctx->s_overflow, &ctx->s_cnt,
+                      &ctx->s_flag, &ctx->s_fill, &ctx->s_uniq, &ctx->s_pairs, &ctx->s_bsums, &ctx->s_totals, &ctx->s_dist, &ctx->s_verdict,
+                      &ctx->s_topk_ids, &ctx->s_topk_dist, &ctx->s_nret, &ctx->s_ndec, &ctx->s_counters, &ctx->s_stage_a, &ctx->s_stage_b,
+                      &ctx->s_stage_c, &ctx->r_rows, &ctx->r_queries, &ctx->r_codes, &ctx->r_topk_ids, &ctx->r_topk_dist, &ctx->r_nret,
+                      &ctx->r_counters, &ctx->t_cand_ids, &ctx->t_cand_sc, &ctx->t_ncand, &ctx->t_raw, &ctx->t_uniq_cnt, &ctx->t_ndec};
+    for (DevBuf *b : bufs) release(*b);
+    for (int i = 0; i < 6; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *fspann_last_error(const fspann_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+void *fspann_ctx_stream(fspann_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+int fspann_ctx_sync(fspann_ctx *ctx) {
+    if (!ctx) return FSPANN_E_ARG;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FSPANN_OK;
+}
+int64_t fspann_ctx_launch_count(const fspann_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int fspann_routing_upload(fspann_ctx *ctx, int32_t dim, int32_t T, int32_t D, int32_t m, int32_t lambda, const double *alpha,
+                          const double *r, const double *omega, int64_t n_ids, const int64_t *min_key, const int64_t *max_key,
+                          const uint64_t *rep_code, const int32_t *ids) {
+    if (!ctx) return FSPANN_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (!alpha || !r || !omega || !min_key || !max_key || !rep_code || !ids) return fail(ctx, FSPANN_E_ARG, "null array");
+    if (dim <= 0 || T <= 0 || D <= 0 || m <= 0 || lambda <= 0 || n_ids <= 0) return fail(ctx, FSPANN_E_ARG, "non-positive parameter");
+    if (lambda > 32) return fail(ctx, FSPANN_E_ARG, "lambda > 32");
+    if ((int64_t)m * lambda > 255) return fail(ctx, FSPANN_E_ARG, "m*lambda = %d > 255 code bits not supported", m * lambda);
+    const int W = (m * lambda + 63) / 64, TD = T * D;
+    const size_t tg_smem = sizeof(double) * ((size_t)64 * (dim | 1) + (size_t)m * dim + 2 * (size_t)m) + 4 * (size_t)64 * 2 * W;
+    if (tg_smem > 227 * 1024) return fail(ctx, FSPANN_E_ARG, "dim=%d, m=%d need %zu B of shared memory for TokenGen (> 227 KB)", dim, m, tg_smem);
+    for (int64_t i = 0; i < (int64_t)TD * m; i++)
+        if (!(omega[i] > 0.0)) return fail(ctx, FSPANN_E_ARG, "omega_j <= 0 (Coding:85-87)");
+    const int64_t P = (n_ids + kBlock - 1) / kBlock;
+    ctx->routing_ready = false;
+    ENSURE(ctx->d_alpha, sizeof(double) * (size_t)TD * m * dim);
+    ENSURE(ctx->d_r, sizeof(double) * (size_t)TD * m);
+    ENSURE(ctx->d_omega, sizeof(double) * (size_t)TD * m);
+    ENSURE(ctx->d_keys, sizeof(int64_t) * 2 * (size_t)TD * P);
+    ENSURE(ctx->d_rep, sizeof(uint64_t) * (size_t)TD * P * W);
+    ENSURE(ctx->d_ids, sizeof(int32_t) * (size_t)TD * n_ids);
+    std::vector<int64_t> inter(2 * (size_t)TD * P);
+    for (size_t i = 0; i < (size_t)TD * P; i++) { inter[2 * i] = min_key[i]; inter[2 * i + 1] = max_key[i]; }
+    CK(cudaMemcpy(ctx->d_alpha.p, alpha, sizeof(double) * (size_t)TD * m * dim, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_r.p, r, sizeof(double) * (size_t)TD * m, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_omega.p, omega, sizeof(double) * (size_t)TD * m, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_keys.p, inter.data(), sizeof(int64_t) * inter.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_rep.p, rep_code, sizeof(uint64_t) * (size_t)TD * P * W, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_ids.p, ids, sizeof(int32_t) * (size_t)TD * n_ids, cudaMemcpyHostToDevice));
+    RoutingView &rv = ctx->rv;
+    rv.dim = dim; rv.T = T; rv.D = D; rv.m = m; rv.lambda = lambda; rv.W = W; rv.TD = TD; rv.n_ids = n_ids; rv.P = P;
+    rv.alpha = (const double *)ctx->d_alpha.p; rv.r = (const double *)ctx->d_r.p; rv.omega = (const double *)ctx->d_omega.p;
+    rv.keys = (const int64_t *)ctx->d_keys.p; rv.rep = (const uint64_t *)ctx->d_rep.p; rv.ids = (const int32_t *)ctx->d_ids.p;
+    ctx->routing_ready = true;
+    return FSPANN_OK;
+}
+
+// GFunctions only (Setup-side bulk coding of the base set runs TokenGen before any partition exists).
+int fspann_gfunctions_upload(fspann_ctx *ctx, int32_t dim, int32_t T, int32_t D, int32_t m, int32_t lambda, const double *alpha,
+                             const double *r, const double *omega) {
+    const int64_t one_min = 0, one_max = 0; const uint64_t rep[4] = {0, 0, 0, 0}; const int32_t id0 = 0;
+    if (!ctx) return FSPANN_E_ARG;
+    // a single dummy partition per (t,d) keeps the routing view well-formed; Route on it is meaningless and rejected below
+    std::vector<int64_t> mn((size_t)T * D, one_min), mx((size_t)T * D, one_max);
+    std::vector<uint64_t> rp((size_t)T * D * 4, rep[0]);
+    std::vector<int32_t> ii((size_t)T * D, id0);
+    int rc = fspann_routing_upload(ctx, dim, T, D, m, lambda, alpha, r, omega, 1, mn.data(), mx.data(), rp.data(), ii.data());
+    return rc;
+}
+
+int fspann_deleted_set(fspann_ctx *ctx, const uint8_t *flags, int64_t n) {
+    if (!ctx) return FSPANN_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (!flags || n <= 0) {
+        ctx->rv.deleted = nullptr; ctx->rv.n_deleted = 0; ctx->sv.deleted = nullptr; ctx->sv.n_deleted = 0;
+        return FSPANN_OK;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    ENSURE(ctx->d_deleted, (size_t)n);
+    CK(cudaMemcpy(ctx->d_deleted.p, flags, (size_t)n, cudaMemcpyHostToDevice));
+    ctx->rv.deleted = (const uint8_t *)ctx->d_deleted.p; ctx->rv.n_deleted = n;
+    ctx->sv.deleted = (const uint8_t *)ctx->d_deleted.p; ctx->sv.n_deleted = n;
+    return FSPANN_OK;
+}
+
+static int store_write(fspann_ctx *ctx, int64_t n, const int32_t *ids, const uint8_t *iv, const uint8_t *ct, const int32_t *ver) {
+    const int dim = ctx->sv.dim;
+    const size_t ct_row = 8 * (size_t)dim + 16;
+    const int64_t chunk = 65536;
+    ENSURE(ctx->s_stage_a, (size_t)chunk * 12);
+    ENSURE(ctx->s_stage_b, (size_t)chunk * ct_row);
+    ENSURE(ctx->s_stage_c, (size_t)chunk * 8);
+    for (int64_t s = 0; s < n; s += chunk) {
+        const int64_t c = std::min(chunk, n - s);
+        CK(cudaMemcpyAsync(ctx->s_stage_a.p, iv + (size_t)s * 12, (size_t)c * 12, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->s_stage_b.p, ct + (size_t)s * ct_row, (size_t)c * ct_row, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->s_stage_c.p, ver + s, (size_t)c * 4, cudaMemcpyHostToDevice, ctx->stream));
+        int32_t *d_ids = nullptr;
+        if (ids) {
+            d_ids = (int32_t *)ctx->s_stage_c.p + chunk;
+            CK(cudaMemcpyAsync(d_ids, ids + s, (size_t)c * 4, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        uint8_t *base = (uint8_t *)ctx->d_rec.p + (ids ? 0 : (size_t)s * ctx->sv.rec_stride);
+        LAUNCHED(launch_store_pack(ctx->stream, base, ctx->sv.rec_stride, dim, c, d_ids, (const uint8_t *)ctx->s_stage_a.p,
+                                   (const uint8_t *)ctx->s_stage_b.p, (const int32_t *)ctx->s_stage_c.p));
+        CK(cudaStreamSynchronize(ctx->stream));   // staging buffers are reused
+    }
+    return 0;
+}
+
+int fspann_store_upload(fspann_ctx *ctx, int64_t N, int32_t dim, const uint8_t *iv, const uint8_t *ct, const int32_t *key_version) {
+    if (!ctx) return FSPANN_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (!iv || !ct || !key_version) return fail(ctx, FSPANN_E_ARG, "null array");
+    if (N <= 0 || dim <= 0) return fail(ctx, FSPANN_E_ARG, "non-positive N/dim");
+    if (N >= (1LL << 31) - 1) return fail(ctx, FSPANN_E_ARG, "N too large for int32 ids");
+    ctx->store_ready = false;
+    const int64_t stride = ((32 + 8LL * dim) + 15) / 16 * 16;
+    ENSURE(ctx->d_rec, (size_t)N * stride + 64);
+    ENSURE(ctx->d_touched, sizeof(uint32_t) * (size_t)((N + 31) / 32 + 1));
+    CK(cudaMemsetAsync(ctx->d_rec.p, 0, (size_t)N * stride + 64, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_touched.p, 0, sizeof(uint32_t) * (size_t)((N + 31) / 32 + 1), ctx->stream));
+    const bool dim_changed = ctx->sv.dim != dim;
+    ctx->sv.N = N; ctx->sv.dim = dim; ctx->sv.rec_stride = stride; ctx->sv.rec = (const uint8_t *)ctx->d_rec.p;
+    if (dim_changed || !ctx->sv.hpow) { int rc = rebuild_keys(ctx); if (rc) return rc; }
+    int rc = store_write(ctx, N, nullptr, iv, ct, key_version);
+    if (rc) return rc;
+    ctx->store_ready = true;
+    return FSPANN_OK;
+}
+
+int fspann_store_update(fspann_ctx *ctx, int64_t n, const int32_t *ids, const uint8_t *iv, const uint8_t *ct, const int32_t *key_version) {
+    if (!ctx) return FSPANN_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->store_ready) return fail(ctx, FSPANN_E_STATE, "record store not uploaded");
+    if (n == 0) return FSPANN_OK;
+    if (!ids || !iv || !ct || !key_version || n < 0) return fail(ctx, FSPANN_E_ARG, "null array");
+    for (int64_t i = 0; i < n; i++)
+        if (ids[i] < 0 || ids[i] >= ctx->sv.N) return fail(ctx, FSPANN_E_ARG, "id %d out of range", ids[i]);
+    return store_write(ctx, n, ids, iv, ct, key_version);
+}
+
+int fspann_keys_set(fspann_ctx *ctx, int32_t version, const uint8_t key[32]) {
+    if (!ctx) return FSPANN_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (!key) return fail(ctx, FSPANN_E_ARG, "null key");
+    if (!ctx->keys.count(version) && (int)ctx->keys.size() >= kMaxKeys) return fail(ctx, FSPANN_E_STATE, "more than %d live key versions", kMaxKeys);
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->keys[version] = std::vector<uint8_t>(key, key + 32);
+    return rebuild_keys(ctx);
+}
+int fspann_keys_retire(fspann_ctx *ctx, int32_t version) {
+    if (!ctx) return FSPANN_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    auto it = ctx->keys.find(version);
+    if (it == ctx->keys.end()) return FSPANN_OK;
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::fill(it->second.begin(), it->second.end(), 0);   // SecureKeyDeletion analogue: wipe before dropping
+    ctx->keys.erase(it);
+    return rebuild_keys(ctx);
+}
+
+int fspann_tokengen_batch(fspann_ctx *ctx, int64_t Q, const double *queries, uint64_t *codes_out) {
+    if (!ctx) return FSPANN_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    int rc = check_routing(ctx); if (rc) return rc;
+    if (Q == 0) return FSPANN_OK;
+    if (Q < 0 || !queries || !codes_out) return fail(ctx, FSPANN_E_ARG, "null array");
+    const RoutingView &rv = ctx->rv;
+    if (!all_finite(queries, Q * rv.dim)) return fail(ctx, FSPANN_E_ARG, "Vector contains NaN/Inf (Coding:357-359)");
+    const size_t cb = sizeof(uint64_t) * (size_t)Q * rv.TD * rv.W;
+    ENSURE(ctx->s_queries, sizeof(double) * (size_t)Q * rv.dim);
+    ENSURE(ctx->s_codes, cb);
+    CK(cudaMemcpyAsync(ctx->s_queries.p, queries, sizeof(double) * (size_t)Q * rv.dim, cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCHED(launch_tokengen(ctx->stream, rv, Q, (const double *)ctx->s_queries.p, (uint64_t *)ctx->s_codes.p));
+    CK(cudaMemcpyAsync(codes_out, ctx->s_codes.p, cb, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FSPANN_OK;
+}
+
+int fspann_route_batch(fspann_ctx *ctx, int64_t Q, const uint64_t *codes, int32_t probes, int64_t hard_cap, int32_t ham_threshold,
+                       int32_t B, int32_t *cand_ids_out, int32_t *cand_scores_out, int32_t *n_cand_out, int32_t *raw_seen_out,
+                       int32_t *unique_out) {
+    (void)ham_threshold;  // the list is score-sorted, so QSI:176-199's two passes select exactly the first B entries
+    if (!ctx) return FSPANN_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    int rc = check_routing(ctx); if (rc) return rc;
+    if (ctx->rv.n_ids <= 1 && ctx->rv.P <= 1) return fail(ctx, FSPANN_E_STATE, "Index not finalized: only GFunctions uploaded");
+    if (Q == 0) return FSPANN_OK;
+    if (Q < 0 || !codes || !cand_ids_out || !n_cand_out) return fail(ctx, FSPANN_E_ARG, "null array");
+    if (B <= 0) return fail(ctx, FSPANN_E_ARG, "refinementLimit must be > 0");
+    const RoutingView &rv = ctx->rv;
+    const size_t cb = sizeof(uint64_t) * (size_t)Q * rv.TD * rv.W, ib = sizeof(int32_t) * (size_t)Q * B;
+    ENSURE(ctx->s_codes, cb); ENSURE(ctx->s_cand_ids, ib); ENSURE(ctx->s_cand_sc, ib);
+    ENSURE(ctx->s_ncand, sizeof(int32_t) * (size_t)Q); ENSURE(ctx->s_raw, sizeof(int32_t) * (size_t)Q); ENSURE(ctx->s_uniq_cnt, sizeof(int32_t) * (size_t)Q);
+    CK(cudaMemcpyAsync(ctx->s_codes.p, codes, cb, cudaMemcpyHostToDevice, ctx->stream));
+    rc = do_route(ctx, Q, (const uint64_t *)ctx->s_codes.p, probes, hard_cap, B, (int32_t *)ctx->s_cand_ids.p, (int32_t *)ctx->s_cand_sc.p,
+                  (int32_t *)ctx->s_ncand.p, (int32_t *)ctx->s_raw.p, (int32_t *)ctx->s_uniq_cnt.p);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(cand_ids_out, ctx->s_cand_ids.p, ib, cudaMemcpyDeviceToHost, ctx->stream));
+    if (cand_scores_out) CK(cudaMemcpyAsync(cand_scores_out, ctx->s_cand_sc.p, ib, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(n_cand_out, ctx->s_ncand.p, sizeof(int32_t) * (size_t)Q, cudaMemcpyDeviceToHost, ctx->stream));
+    if (raw_seen_out) CK(cudaMemcpyAsync(raw_seen_out, ctx->s_raw.p, sizeof(int32_t) * (size_t)Q, cudaMemcpyDeviceToHost, ctx->stream));
+    if (unique_out) CK(cudaMemcpyAsync(unique_out, ctx->s_uniq_cnt.p, sizeof(int32_t) * (size_t)Q, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FSPANN_OK;
+}
+
+int fspann_refine_batch(fspann_ctx *ctx, int64_t Q, const double *queries, const int32_t *cand_ids, const int32_t *n_cand,
+                        int32_t cand_stride, int32_t k, int32_t *topk_ids_out, double *topk_dist_out, int32_t *n_ret_out,
+                        uint8_t *verdict_out, int32_t *n_decrypted_out) {
+    if (!ctx) return FSPANN_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    int rc = check_store(ctx); if (rc) return rc;
+    if (Q == 0) return FSPANN_OK;
+    if (Q < 0 || !queries || !cand_ids || !n_cand || !topk_ids_out || !topk_dist_out || !n_ret_out) return fail(ctx, FSPANN_E_ARG, "null array");
+    if (k <= 0 || cand_stride <= 0) return fail(ctx, FSPANN_E_ARG, "topK and cand_stride must be > 0");
+    for (int64_t q = 0; q < Q; q++)
+        if (n_cand[q] < 0 || n_cand[q] > cand_stride) return fail(ctx, FSPANN_E_ARG, "n_cand[%lld] out of range", (long long)q);
+    const int dim = ctx->sv.dim;
+    const size_t ib = sizeof(int32_t) * (size_t)Q * cand_stride;
+    ENSURE(ctx->s_queries, sizeof(double) * (size_t)Q * dim); ENSURE(ctx->s_cand_ids, ib); ENSURE(ctx->s_ncand, sizeof(int32_t) * (size_t)Q);
+    ENSURE(ctx->s_topk_ids, sizeof(int32_t) * (size_t)Q * k); ENSURE(ctx->s_topk_dist, sizeof(double) * (size_t)Q * k);
+    ENSURE(ctx->s_nret, sizeof(int32_t) * (size_t)Q); ENSURE(ctx->s_ndec, sizeof(int32_t) * (size_t)Q);
+    CK(cudaMemcpyAsync(ctx->s_queries.p, queries, sizeof(double) * (size_t)Q * dim, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->s_cand_ids.p, cand_ids, ib, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->s_ncand.p, n_cand, sizeof(int32_t) * (size_t)Q, cudaMemcpyHostToDevice, ctx->stream));
+    const int64_t l0 = ctx->launches;
+    rc = record_ev(ctx, 0); if (rc) return rc;
+    rc = record_ev(ctx, 1); if (rc) return rc;
+    rc = record_ev(ctx, 2); if (rc) return rc;
+    rc = do_refine(ctx, Q, (const double *)ctx->s_queries.p, (const int32_t *)ctx->s_cand_ids.p, (const int32_t *)ctx->s_ncand.p, cand_stride, k,
+                   (int32_t *)ctx->s_topk_ids.p, (double *)ctx->s_topk_dist.p, (int32_t *)ctx->s_nret.p, (int32_t *)ctx->s_ndec.p, true);
+    if (rc) return rc;
+    ctx->ev_valid = true; ctx->last_call_launches = ctx->launches - l0;
+    CK(cudaMemcpyAsync(topk_ids_out, ctx->s_topk_ids.p, sizeof(int32_t) * (size_t)Q * k, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(topk_dist_out, ctx->s_topk_dist.p, sizeof(double) * (size_t)Q * k, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(n_ret_out, ctx->s_nret.p, sizeof(int32_t) * (size_t)Q, cudaMemcpyDeviceToHost, ctx->stream));
+    if (verdict_out) CK(cudaMemcpyAsync(verdict_out, ctx->s_verdict.p, (size_t)Q * cand_stride, cudaMemcpyDeviceToHost, ctx->stream));
+    if (n_decrypted_out) CK(cudaMemcpyAsync(n_decrypted_out, ctx->s_ndec.p, sizeof(int32_t) * (size_t)Q, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FSPANN_OK;
+}
+
+// One full pass (tokengen -> route -> refine -> counters) over device-resident queries.
+static int search_pass(fspann_ctx *ctx, int64_t Q, const double *d_queries, int k, int probes, int64_t hard_cap, int B, int retried,
+                       int32_t *d_topk_ids, double *d_topk_dist, int32_t *d_nret, int64_t *d_counters, bool main_pass) {
+    const RoutingView &rv = ctx->rv;
+    DevBuf &b_codes = main_pass ? ctx->s_codes : ctx->r_codes;
+    DevBuf &b_cid = main_pass ? ctx->s_cand_ids : ctx->t_cand_ids;
+    DevBuf &b_csc = main_pass ? ctx->s_cand_sc : ctx->t_cand_sc;
+    DevBuf &b_nc = main_pass ? ctx->s_ncand : ctx->t_ncand;
+    DevBuf &b_raw = main_pass ? ctx->s_raw : ctx->t_raw;
+    DevBuf &b_un = main_pass ? ctx->s_uniq_cnt : ctx->t_uniq_cnt;
+    DevBuf &b_nd = main_pass ? ctx->s_ndec : ctx->t_ndec;
+    ENSURE(b_codes, sizeof(uint64_t) * (size_t)Q * rv.TD * rv.W);
+    ENSURE(b_cid, sizeof(int32_t) * (size_t)Q * B); ENSURE(b_csc, sizeof(int32_t) * (size_t)Q * B);
+    ENSURE(b_nc, sizeof(int32_t) * (size_t)Q); ENSURE(b_raw, sizeof(int32_t) * (size_t)Q); ENSURE(b_un, sizeof(int32_t) * (size_t)Q);
+    ENSURE(b_nd, sizeof(int32_t) * (size_t)Q);
+    int rc;
+    if (main_pass) { rc = record_ev(ctx, 0); if (rc) return rc; }
+    LAUNCHED(launch_tokengen(ctx->stream, rv, Q, d_queries, (uint64_t *)b_codes.p));
+    if (main_pass) { rc = record_ev(ctx, 1); if (rc) return rc; }
+    rc = do_route(ctx, Q, (const uint64_t *)b_codes.p, probes, hard_cap, B, (int32_t *)b_cid.p, (int32_t *)b_csc.p, (int32_t *)b_nc.p,
+                  (int32_t *)b_raw.p, (int32_t *)b_un.p);
+    if (rc) return rc;
+    if (main_pass) { rc = record_ev(ctx, 2); if (rc) return rc; }
+    rc = do_refine(ctx, Q, d_queries, (const int32_t *)b_cid.p, (const int32_t *)b_nc.p, B, k, d_topk_ids, d_topk_dist, d_nret, (int32_t *)b_nd.p, main_pass);
+    if (rc) return rc;
+    if (d_counters)
+        LAUNCHED(launch_counters(ctx->stream, Q, (const int32_t *)b_raw.p, (const int32_t *)b_un.p, (const int32_t *)b_nd.p, d_nret,
+                                 (const int32_t *)b_nc.p, retried, d_counters));
+    return 0;
+}
+
+int fspann_search_batch_dev(fspann_ctx *ctx, int64_t Q, const double *d_queries, int32_t k, int32_t probes, int64_t hard_cap, int32_t B,
+                            int32_t ham_threshold, int32_t allow_retry, int32_t *d_topk_ids, double *d_topk_dist, int32_t *d_n_ret,
+                            int64_t *d_counters) {
+    (void)ham_threshold;
+    if (!ctx) return FSPANN_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    int rc = check_routing(ctx); if (rc) return rc;
+    rc = check_store(ctx); if (rc) return rc;
+    if (ctx->rv.n_ids <= 1 && ctx->rv.P <= 1) return fail(ctx, FSPANN_E_STATE, "Index not finalized: only GFunctions uploaded");
+    if (Q == 0) return FSPANN_OK;
+    if (Q < 0 || !d_queries || !d_topk_ids || !d_topk_dist || !d_n_ret) return fail(ctx, FSPANN_E_ARG, "null array");
+    if (k <= 0) return fail(ctx, FSPANN_E_ARG, "topK must be > 0 (QTF:65)");
+    if (B <= 0) return fail(ctx, FSPANN_E_ARG, "refinementLimit must be > 0");
+    if (probes <= 0) probes = 5;   // DEFAULT_MAX_PROBES (PIS:93) when no override is configured (PIS:880-888)
+    const int64_t l0 = ctx->launches;
+    rc = search_pass(ctx, Q, d_queries, k, probes, hard_cap, B, 0, d_topk_ids, d_topk_dist, d_n_ret, d_counters, true);
+    if (rc) return rc;
+    ctx->ev_valid = true;
+    if (allow_retry) {
+        // QSI:327-337 + 444-447: once per query, if returned < K or decrypted < 10*K, redo with 10 probes.
+        std::vector<int32_t> nret((size_t)Q), ndec((size_t)Q);
+        CK(cudaMemcpyAsync(nret.data(), d_n_ret, sizeof(int32_t) * (size_t)Q, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ndec.data(), ctx->s_ndec.p, sizeof(int32_t) * (size_t)Q, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        std::vector<int32_t> rows;
+        // a first pass with no decrypted candidate returns immediately (QSI:293: scored.isEmpty() -> return), no retry
+        for (int64_t q = 0; q < Q; q++)
+            if (ndec[q] > 0 && (nret[q] < k || ndec[q] < 10 * k)) rows.push_back((int32_t)q);
+        const int64_t R = (int64_t)rows.size();
+        if (R > 0) {
+            const int dim = ctx->rv.dim;
+            ENSURE(ctx->r_rows, sizeof(int32_t) * (size_t)R); ENSURE(ctx->r_queries, sizeof(double) * (size_t)R * dim);
+            ENSURE(ctx->r_topk_ids, sizeof(int32_t) * (size_t)R * k); ENSURE(ctx->r_topk_dist, sizeof(double) * (size_t)R * k);
+            ENSURE(ctx->r_nret, sizeof(int32_t) * (size_t)R); ENSURE(ctx->r_counters, sizeof(int64_t) * FSPANN_COUNTERS * (size_t)R);
+            CK(cudaMemcpyAsync(ctx->r_rows.p, rows.data(), sizeof(int32_t) * (size_t)R, cudaMemcpyHostToDevice, ctx->stream));
+            LAUNCHED(launch_gather_rows(ctx->stream, d_queries, ctx->r_queries.p, (const int32_t *)ctx->r_rows.p, R, sizeof(double) * dim, false));
+            rc = search_pass(ctx, R, (const double *)ctx->r_queries.p, k, 10, hard_cap, B, 1, (int32_t *)ctx->r_topk_ids.p,
+                             (double *)ctx->r_topk_dist.p, (int32_t *)ctx->r_nret.p, d_counters ? (int64_t *)ctx->r_counters.p : nullptr, false);
+            if (rc) return rc;
+            LAUNCHED(launch_gather_rows(ctx->stream, ctx->r_topk_ids.p, d_topk_ids, (const int32_t *)ctx->r_rows.p, R, sizeof(int32_t) * k, true));
+            LAUNCHED(launch_gather_rows(ctx->stream, ctx->r_topk_dist.p, d_topk_dist, (const int32_t *)ctx->r_rows.p, R, sizeof(double) * k, true));
+            LAUNCHED(launch_gather_rows(ctx->stream, ctx->r_nret.p, d_n_ret, (const int32_t *)ctx->r_rows.p, R, sizeof(int32_t), true));
+            if (d_counters)
+                LAUNCHED(launch_gather_rows(ctx->stream, ctx->r_counters.p, d_counters, (const int32_t *)ctx->r_rows.p, R, sizeof(int64_t) * FSPANN_COUNTERS, true));
+            CK(cudaStreamSynchronize(ctx->stream));   // rows vector is read by the H2D copy above
+        }
+    }
+    ctx->last_call_launches = ctx->launches - l0;
+    return FSPANN_OK;
+}
+
+int fspann_search_batch(fspann_ctx *ctx, int64_t Q, const double *queries, int32_t k, int32_t probes, int64_t hard_cap, int32_t B,
+                        int32_t ham_threshold, int32_t *topk_ids_out, double *topk_dist_out, int32_t *n_ret_out, int64_t *counters_out) {
+    if (!ctx) return FSPANN_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    int rc = check_routing(ctx); if (rc) return rc;
+    rc = check_store(ctx); if (rc) return rc;
+    if (Q == 0) return FSPANN_OK;
+    if (Q < 0 || !queries || !topk_ids_out || !topk_dist_out || !n_ret_out) return fail(ctx, FSPANN_E_ARG, "null array");
+    if (k <= 0) return fail(ctx, FSPANN_E_ARG, "topK must be > 0 (QTF:65)");
+    const int dim = ctx->rv.dim;
+    // QSI:137: a query that is not all-finite returns an empty list; createToken would already have thrown
+    // (Coding:357-359), so the batch is rejected like the reference rejects the token.
+    if (!all_finite(queries, Q * dim)) return fail(ctx, FSPANN_E_ARG, "Vector contains NaN/Inf (Coding:357-359)");
+    ENSURE(ctx->s_queries, sizeof(double) * (size_t)Q * dim);
+    ENSURE(ctx->s_topk_ids, sizeof(int32_t) * (size_t)Q * k); ENSURE(ctx->s_topk_dist, sizeof(double) * (size_t)Q * k);
+    ENSURE(ctx->s_nret, sizeof(int32_t) * (size_t)Q); ENSURE(ctx->s_counters, sizeof(int64_t) * FSPANN_COUNTERS * (size_t)Q);
+    CK(cudaMemcpyAsync(ctx->s_queries.p, queries, sizeof(double) * (size_t)Q * dim, cudaMemcpyHostToDevice, ctx->stream));
+    rc = fspann_search_batch_dev(ctx, Q, (const double *)ctx->s_queries.p, k, probes, hard_cap, B, ham_threshold, 1, (int32_t *)ctx->s_topk_ids.p,
+                                 (double *)ctx->s_topk_dist.p, (int32_t *)ctx->s_nret.p, (int64_t *)ctx->s_counters.p);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(topk_ids_out, ctx->s_topk_ids.p, sizeof(int32_t) * (size_t)Q * k, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(topk_dist_out, ctx->s_topk_dist.p, sizeof(double) * (size_t)Q * k, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(n_ret_out, ctx->s_nret.p, sizeof(int32_t) * (size_t)Q, cudaMemcpyDeviceToHost, ctx->stream));
+    if (counters_out) CK(cudaMemcpyAsync(counters_out, ctx->s_counters.p, sizeof(int64_t) * FSPANN_COUNTERS * (size_t)Q, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FSPANN_OK;
+}
+
+int fspann_touched_fetch(fspann_ctx *ctx, uint32_t *bitmap_out, int64_t n_words, int32_t clear) {
+    if (!ctx) return FSPANN_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->store_ready) return fail(ctx, FSPANN_E_STATE, "record store not uploaded");
+    const int64_t have = (ctx->sv.N + 31) / 32;
+    if (n_words > have) n_words = have;
+    if (bitmap_out && n_words > 0) CK(cudaMemcpyAsync(bitmap_out, ctx->d_touched.p, sizeof(uint32_t) * (size_t)n_words, cudaMemcpyDeviceToHost, ctx->stream));
+    if (clear) CK(cudaMemsetAsync(ctx->d_touched.p, 0, sizeof(uint32_t) * (size_t)have, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FSPANN_OK;
+}
+
+int64_t fspann_last_stage_ms(fspann_ctx *ctx, float out[5]) {
+    if (!ctx || !out) return -1;
+    for (int i = 0; i < 5; i++) out[i] = 0.f;
+    if (!ctx->ev_valid) return 0;
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return -1;
+    for (int i = 0; i < 5; i++) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->ev[i], ctx->ev[i + 1]) == cudaSuccess) out[i] = ms;
+    }
+    return ctx->last_call_launches;
+}
+
+int fspann_debug_decrypt(fspann_ctx *ctx, int64_t n, const int32_t *ids, double *plaintext_out, uint8_t *verdict_out) {
+    if (!ctx) return FSPANN_E_ARG;
+#ifndef FSPANN_DEBUG_TAP
+    (void)n; (void)ids; (void)plaintext_out; (void)verdict_out;
+    return fail(ctx, FSPANN_E_STATE, "production build: plaintext never leaves the SM (rebuild with -DFSPANN_DEBUG_TAP for parity tests)");
+#else
+    CK(cudaSetDevice(ctx->device));
+    int rc = check_store(ctx); if (rc) return rc;
+    if (n <= 0) return FSPANN_OK;
+    if (!ids || !plaintext_out || !verdict_out) return fail(ctx, FSPANN_E_ARG, "null array");
+    const int dim = ctx->sv.dim;
+    ENSURE(ctx->s_cand_ids, sizeof(int32_t) * (size_t)n); ENSURE(ctx->s_dist, sizeof(double) * (size_t)n * dim); ENSURE(ctx->s_verdict, (size_t)n);
+    CK(cudaMemcpyAsync(ctx->s_cand_ids.p, ids, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCHED(launch_debug_decrypt(ctx->stream, ctx->sv, n, (const int32_t *)ctx->s_cand_ids.p, (double *)ctx->s_dist.p, (uint8_t *)ctx->s_verdict.p));
+    CK(cudaMemcpyAsync(plaintext_out, ctx->s_dist.p, sizeof(double) * (size_t)n * dim, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(verdict_out, ctx->s_verdict.p, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FSPANN_OK;
+#endif
+}
+
+}  // extern "C"

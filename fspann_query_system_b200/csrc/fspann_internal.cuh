@@ -1,0 +1,104 @@
+// fspann_internal.cuh -- context layout and kernel launcher declarations shared by the .cu files.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/fspann_gpu.h"
+#include "aes_gcm.cuh"
+
+namespace fsp {
+
+constexpr int kMaxKeys = FSPANN_MAX_KEYS;
+constexpr int kBlock = FSPANN_BLOCK;  // ids per partition (PIS:92)
+
+// Device-visible key ring: AES-256 round keys per live version (KRS:82-88 getVersion -> key).
+struct DevKeyRing {
+    int32_t n;
+    int32_t version[kMaxKeys];
+    uint32_t rk[kMaxKeys][60];
+};
+
+// Routing index as the kernels see it.
+struct RoutingView {
+    int32_t dim, T, D, m, lambda, W, TD;
+    int64_t n_ids, P;
+    const double *alpha, *r, *omega;  // [TD][m][dim], [TD][m], [TD][m]
+    const int64_t *keys;              // [TD][P][2] interleaved (minKey, maxKey)
+    const uint64_t *rep;              // [TD][P][W]
+    const int32_t *ids;               // [TD][n_ids]
+    const uint8_t *deleted;           // [n_deleted] or nullptr
+    int64_t n_deleted;
+};
+
+// Record store as the kernels see it.  One record = [iv 12 B | key_version 4 B | ciphertext 8*dim B | tag 16 B | pad],
+// rec_stride a multiple of 16 so every record starts 128-bit aligned.
+struct StoreView {
+    int64_t N;
+    int32_t dim;
+    int64_t rec_stride;
+    const uint8_t *rec;
+    const DevKeyRing *keys;
+    const u128 *hpow;     // [kMaxKeys][npow+1] GHASH key powers H^1..H^npow (index 0 unused)
+    int32_t npow;         // c + 4, c = ceil(8*dim/16)
+    const uint32_t *te0;  // [256]
+    const uint8_t *deleted;
+    int64_t n_deleted;
+};
+
+struct RouteParams {
+    int64_t Q;
+    const uint64_t *codes;  // [Q][TD][W]
+    int32_t probes;
+    int64_t hard_cap;
+    int32_t B;
+    int32_t *cand_ids, *cand_scores;  // [Q][B]
+    int32_t *n_cand, *raw_seen, *unique;
+    // per-CTA scratch
+    int32_t cap0;        // Java initial table size = tableSizeFor(min(hard_cap, 65536)) (PIS:619)
+    int32_t max_nodes;   // upper bound on distinct candidates of one query
+    int32_t *scratch;    // [grid][scratch_ints]
+    int64_t scratch_ints;
+    int32_t *chain_overflow;  // set when a bucket chain reached 9 (Java would treeify; order then unspecified)
+};
+
+struct RefineParams {
+    int64_t Q;
+    const double *queries;    // [Q][dim]
+    const int32_t *cand_ids;  // [Q][stride]
+    const int32_t *n_cand;    // [Q]
+    int32_t stride, k;
+    // grouping scratch
+    int32_t *cnt;       // [N+1]  pairs per record -> exclusive offsets after the scan
+    int32_t *flag_pref; // [N+1]  exclusive prefix of (cnt>0)
+    int32_t *fill;      // [N]
+    int32_t *uniq;      // [<= min(N, Q*stride)]
+    uint32_t *pairs;    // [Q*stride]
+    int32_t *block_sums;  // scan scratch
+    int32_t *totals;    // [4]: n_pairs, n_uniq, work counter, spare
+    double *dist;       // [Q*stride]
+    uint8_t *verdict;   // [Q*stride]
+    uint32_t *touched;  // [ceil(N/32)]
+    // outputs
+    int32_t *topk_ids;  // [Q][k]
+    double *topk_dist;  // [Q][k]
+    int32_t *n_ret, *n_dec;
+};
+
+// launchers (each returns the number of kernels it launched, or -1 after setting a CUDA error)
+int launch_tokengen(cudaStream_t s, const RoutingView &rv, int64_t Q, const double *queries, uint64_t *codes);
+int launch_route(cudaStream_t s, const RoutingView &rv, const RouteParams &p, int grid);
+int route_grid(int64_t Q, int sm_count);
+int64_t route_scratch_ints(int32_t cap0, int32_t max_nodes);
+int launch_refine_group(cudaStream_t s, const StoreView &sv, const RefineParams &p);
+int launch_refine_decrypt(cudaStream_t s, const StoreView &sv, const RefineParams &p, int sm_count);
+int launch_refine_topk(cudaStream_t s, const RefineParams &p);
+int launch_counters(cudaStream_t s, int64_t Q, const int32_t *raw, const int32_t *uniq, const int32_t *n_dec,
+                    const int32_t *n_ret, const int32_t *n_cand, int32_t retried, int64_t *counters);
+int launch_gather_rows(cudaStream_t s, const void *src, void *dst, const int32_t *rows, int64_t n_rows, int64_t row_bytes, bool scatter);
+int launch_store_pack(cudaStream_t s, uint8_t *rec, int64_t rec_stride, int32_t dim, int64_t n, const int32_t *ids /* or null */,
+                      const uint8_t *iv, const uint8_t *ct, const int32_t *ver);
+int launch_debug_decrypt(cudaStream_t s, const StoreView &sv, int64_t n, const int32_t *ids, double *pt, uint8_t *verdict);
+
+}  // namespace fsp

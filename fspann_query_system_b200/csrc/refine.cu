@@ -1,0 +1,499 @@
+// refine.cu -- stage 3: bounded trusted refinement.
+//
+// Replaces QueryServiceImpl.search stage B + C (query/.../service/QueryServiceImpl.java:238-322):
+//   loadPointIfActive (PIS:717-724) -> keyService.getVersion(ep.keyVersion) (KRS:82-88) ->
+//   AesGcmCryptoService.decryptFromPoint (crypto/.../AesGcmCryptoService.java:126-166, AAD EP:80-83) ->
+//   isValid (QSI:407-413) -> l2 (QSI:364-372) -> stable sort by distance, first K (QSI:298-316).
+//
+// B200 design: the batch is processed RECORD-major.  A 10k-query batch at B=1024 names ~10M (query, candidate)
+// pairs but at most N distinct records, and AES-256-GCM on the SM (no AES/CLMUL instructions) is ALU/LDS bound,
+// far below the HBM rate.  So pairs are grouped by record id (count -> scan -> fill), each distinct record is
+// authenticated and decrypted ONCE, its plaintext lives only in shared memory, and every pair that selected it is
+// scored from there (exact sequential FP64, bit-identical to the Java loop).  Per-query top-k runs afterwards on
+// the scalar distances.  Plaintext never reaches global memory.
+#include "fspann_internal.cuh"
+
+namespace fsp {
+
+// ------------------------------------------------------------------------------------------------------------------
+// grouping: pairs (q, rank) -> per-record lists
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool is_deleted(const StoreView &sv, int32_t id) {
+    return sv.deleted && id < sv.n_deleted && sv.deleted[id];
+}
+
+__global__ void refine_count_kernel(StoreView sv, RefineParams p) {
+    const int64_t total = p.Q * (int64_t)p.stride;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t q = i / p.stride;
+        const int r = (int)(i - q * p.stride);
+        uint8_t v = 0xff;                               // 0xff = slot not part of the candidate list
+        if (r < p.n_cand[q]) {
+            const int32_t id = p.cand_ids[i];
+            if (id < 0 || id >= sv.N || is_deleted(sv, id)) v = FSPANN_V_NOT_FOUND;     // PIS:717-724
+            else { atomicAdd(&p.cnt[id], 1); v = 0xfe; }                                 // 0xfe = pending
+        }
+        p.verdict[i] = v;
+    }
+}
+
+// Two-level exclusive scan of (cnt, cnt>0) over N+1 entries.  SCAN_ITEMS per block.
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_PER_THREAD = 8;
+constexpr int SCAN_ITEMS = SCAN_THREADS * SCAN_PER_THREAD;
+
+__device__ __forceinline__ int2 block_excl_scan2(int2 v, int2 *total) {
+    __shared__ int2 s_w[SCAN_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int2 x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int ya = __shfl_up_sync(0xffffffffu, x.x, o), yb = __shfl_up_sync(0xffffffffu, x.y, o);
+        if (lane >= o) { x.x += ya; x.y += yb; }
+    }
+    if (lane == 31) s_w[warp] = x;
+    __syncthreads();
+    int2 base = make_int2(0, 0), tot = make_int2(0, 0);
+    for (int w = 0; w < SCAN_THREADS / 32; w++) { if (w < warp) { base.x += s_w[w].x; base.y += s_w[w].y; } tot.x += s_w[w].x; tot.y += s_w[w].y; }
+    __syncthreads();
+    *total = tot;
+    return make_int2(base.x + x.x - v.x, base.y + x.y - v.y);
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_partial_kernel(const int32_t *__restrict__ cnt, int64_t n, int32_t *__restrict__ block_sums) {
+    const int64_t b0 = (int64_t)blockIdx.x * SCAN_ITEMS;
+    int2 acc = make_int2(0, 0);
+    for (int k = 0; k < SCAN_PER_THREAD; k++) {
+        const int64_t i = b0 + (int64_t)k * SCAN_THREADS + threadIdx.x;
+        if (i < n) { const int c = cnt[i]; acc.x += c; acc.y += c > 0; }
+    }
+    int2 tot;
+    block_excl_scan2(acc, &tot);
+    if (threadIdx.x == 0) { block_sums[2 * blockIdx.x] = tot.x; block_sums[2 * blockIdx.x + 1] = tot.y; }
+}
+__global__ void __launch_bounds__(SCAN_THREADS) scan_sums_kernel(int32_t *block_sums, int nblocks, int32_t *totals) {
+    __shared__ int2 carry;
+    if (threadIdx.x == 0) carry = make_int2(0, 0);
+    __syncthreads();
+    for (int b0 = 0; b0 < nblocks; b0 += SCAN_THREADS) {
+        const int i = b0 + threadIdx.x;
+        int2 v = i < nblocks ? make_int2(block_sums[2 * i], block_sums[2 * i + 1]) : make_int2(0, 0);
+        int2 tot;
+        int2 ex = block_excl_scan2(v, &tot);
+        const int2 c = carry;
+        if (i < nblocks) { block_sums[2 * i] = ex.x + c.x; block_sums[2 * i + 1] = ex.y + c.y; }
+        __syncthreads();
+        if (threadIdx.x == 0) { carry.x = c.x + tot.x; carry.y = c.y + tot.y; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { totals[0] = carry.x; totals[1] = carry.y; totals[2] = 0; totals[3] = 0; }
+}
+// Rewrites cnt[] in place to exclusive offsets, writes flag prefix, the unique-id list and zeroes fill[].
+__global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(int32_t *__restrict__ cnt, int64_t n, const int32_t *__restrict__ block_sums,
+                                                                  int32_t *__restrict__ uniq, int32_t *__restrict__ fill) {
+    const int64_t b0 = (int64_t)blockIdx.x * SCAN_ITEMS;
+    // thread owns SCAN_PER_THREAD consecutive items so the in-block order is the id order
+    int c[SCAN_PER_THREAD];
+    int2 acc = make_int2(0, 0);
+    const int64_t t0 = b0 + (int64_t)threadIdx.x * SCAN_PER_THREAD;
+#pragma unroll
+    for (int k = 0; k < SCAN_PER_THREAD; k++) { const int64_t i = t0 + k; c[k] = i < n ? cnt[i] : 0; acc.x += c[k]; acc.y += c[k] > 0; }
+    int2 tot;
+    int2 ex = block_excl_scan2(acc, &tot);
+    ex.x += block_sums[2 * blockIdx.x]; ex.y += block_sums[2 * blockIdx.x + 1];
+#pragma unroll
+    for (int k = 0; k < SCAN_PER_THREAD; k++) {
+        const int64_t i = t0 + k;
+        if (i < n) {
+            cnt[i] = ex.x;
+            fill[i] = 0;
+            if (c[k] > 0) uniq[ex.y] = (int32_t)i;
+            ex.x += c[k]; ex.y += c[k] > 0;
+        }
+    }
+}
+__global__ void refine_fill_kernel(StoreView sv, RefineParams p) {
+    const int64_t total = p.Q * (int64_t)p.stride;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        if (p.verdict[i] != 0xfe) continue;
+        const int32_t id = p.cand_ids[i];
+        const int pos = p.cnt[id] + atomicAdd(&p.fill[id], 1);
+        p.pairs[pos] = (uint32_t)i;
+    }
+}
+
+int launch_refine_group(cudaStream_t s, const StoreView &sv, const RefineParams &p) {
+    const int64_t n = sv.N + 1;  // one extra slot so cnt[N] = total after the scan
+    if (cudaMemsetAsync(p.cnt, 0, sizeof(int32_t) * (size_t)n, s) != cudaSuccess) return -1;
+    const int64_t total = p.Q * (int64_t)p.stride;
+    int grid = (int)((total + 255) / 256); if (grid > 148 * 16) grid = 148 * 16; if (grid < 1) grid = 1;
+    refine_count_kernel<<<grid, 256, 0, s>>>(sv, p);
+    const int nblocks = (int)((n + SCAN_ITEMS - 1) / SCAN_ITEMS);
+    scan_partial_kernel<<<nblocks, SCAN_THREADS, 0, s>>>(p.cnt, n, p.block_sums);
+    scan_sums_kernel<<<1, SCAN_THREADS, 0, s>>>(p.block_sums, nblocks, p.totals);
+    scan_apply_kernel<<<nblocks, SCAN_THREADS, 0, s>>>(p.cnt, n, p.block_sums, p.uniq, p.fill);
+    refine_fill_kernel<<<grid, 256, 0, s>>>(sv, p);
+    return cudaGetLastError() == cudaSuccess ? 5 : -1;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// decrypt + verify + distance.  One warp owns up to 32 consecutive distinct records at a time:
+//   round 0   : lane l computes E_K(J0) of record l (the tag mask) -- 32 blocks, all lanes busy;
+//   per record: lanes split the ciphertext blocks (coalesced 128-bit loads), each lane runs AES-CTR on its blocks,
+//               multiplies them by the matching GHASH key power H^p (aggregated GHASH: sum_i X_i * H^(n-i)) and the
+//               warp XOR-reduces; plaintext goes to the warp's shared-memory row; then lanes take the (query, rank)
+//               pairs of the record and accumulate the exact FP64 distance from shared memory.
+// AES uses one T-table (Te0) replicated for the 32 banks so every lookup is conflict free; Te1..3 are rotations.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int RF_THREADS = 256;
+constexpr int RF_WARPS = RF_THREADS / 32;
+
+struct TeSmem {
+    const uint32_t *t;  // te_s + lane
+    __device__ __forceinline__ uint32_t operator()(uint32_t x) const { return t[x << 5]; }
+};
+struct RkSmem {
+    const uint32_t *r;
+    __device__ __forceinline__ uint32_t operator()(int i) const { return r[i]; }
+};
+
+__device__ __forceinline__ int find_key_slot(const int32_t *s_ver, int nkeys, int32_t version) {
+    int slot = -1;
+    for (int i = 0; i < nkeys; i++) if (s_ver[i] == version) slot = i;
+    return slot;
+}
+
+// Decrypts record `id` with the whole warp.  Plaintext doubles -> pt_row[0..dim).  Returns the verdict (warp-uniform).
+// hdr = first 16 bytes of the record (iv | key_version), slot = key slot (>= 0), ej0 = E_K(J0) words.
+__device__ __forceinline__ int warp_decrypt_record(const StoreView &sv, const uint8_t *rec, int32_t id, uint4 hdr, int slot,
+                                                   const uint32_t ej0[4], const TeSmem &te, const uint32_t *s_rk, double *pt_row, int lane) {
+    const int dim = sv.dim;
+    const int nbytes = 8 * dim;
+    const int c = (nbytes + 15) >> 4;                     // ciphertext blocks (the last may hold only 8 bytes)
+    const uint32_t iv0 = bswap32(hdr.x), iv1 = bswap32(hdr.y), iv2 = bswap32(hdr.z);
+    const int32_t version = (int32_t)hdr.w;
+    const RkSmem rk{s_rk + slot * 60};
+    const u128 *hp = sv.hpow + (size_t)slot * (sv.npow + 1);
+    const uint4 *ctv = reinterpret_cast<const uint4 *>(rec + 16);
+
+    u128 gh = {0, 0};
+    bool finite = true;
+    for (int blk = lane; blk < c; blk += 32) {
+        uint4 w = __ldg(ctv + blk);
+        uint32_t x0 = bswap32(w.x), x1 = bswap32(w.y), x2 = bswap32(w.z), x3 = bswap32(w.w);
+        const bool half = (blk == c - 1) && (nbytes & 15);  // odd dim: 8 ciphertext bytes, the rest is tag
+        if (half) { x2 = 0; x3 = 0; }
+        u128 X; X.hi = ((uint64_t)x0 << 32) | x1; X.lo = ((uint64_t)x2 << 32) | x3;
+        const u128 z = gf128_mul(X, hp[c + 1 - blk]);
+        gh.hi ^= z.hi; gh.lo ^= z.lo;
+        uint32_t ks[4];
+        aes256_encrypt(te, rk, iv0, iv1, iv2, (uint32_t)(blk + 2), ks);
+        const uint32_t p0 = x0 ^ ks[0], p1 = x1 ^ ks[1], p2 = x2 ^ ks[2], p3 = x3 ^ ks[3];
+        // big-endian FP64 (AGC:261-277): first word is the high half
+        pt_row[2 * blk] = __hiloint2double((int)p0, (int)p1);
+        finite &= ((p0 >> 20) & 0x7ffu) != 0x7ffu;
+        if (!half) {
+            pt_row[2 * blk + 1] = __hiloint2double((int)p2, (int)p3);
+            finite &= ((p2 >> 20) & 0x7ffu) != 0x7ffu;
+        }
+    }
+    // AAD blocks and the length block (every lane builds the <= 48-byte AAD string; lanes 0..a-1 and lane 31 use it)
+    uint8_t aad[FSP_AAD_MAX];
+    const int alen = build_aad((int64_t)id, version, dim, aad);
+    const int a = (alen + 15) >> 4;
+    if (lane < a) {
+        u128 X; X.hi = load_be64(aad + 16 * lane); X.lo = load_be64(aad + 16 * lane + 8);
+        const u128 z = gf128_mul(X, hp[c + 1 + a - lane]);
+        gh.hi ^= z.hi; gh.lo ^= z.lo;
+    }
+    if (lane == 31) {
+        u128 X; X.hi = (uint64_t)alen * 8u; X.lo = (uint64_t)nbytes * 8u;
+        const u128 z = gf128_mul(X, hp[1]);
+        gh.hi ^= z.hi; gh.lo ^= z.lo;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        gh.hi ^= __shfl_xor_sync(0xffffffffu, gh.hi, o);
+        gh.lo ^= __shfl_xor_sync(0xffffffffu, gh.lo, o);
+    }
+    // tag = GHASH ^ E_K(J0); stored tag sits right after the ciphertext (8-byte aligned for every dim)
+    const uint2 *tagp = reinterpret_cast<const uint2 *>(rec + 16 + nbytes);
+    const uint2 t0 = __ldg(tagp), t1 = __ldg(tagp + 1);
+    const uint64_t tag_hi = ((uint64_t)bswap32(t0.x) << 32) | bswap32(t0.y), tag_lo = ((uint64_t)bswap32(t1.x) << 32) | bswap32(t1.y);
+    const uint64_t my_hi = gh.hi ^ (((uint64_t)ej0[0] << 32) | ej0[1]), my_lo = gh.lo ^ (((uint64_t)ej0[2] << 32) | ej0[3]);
+    const bool all_finite = __all_sync(0xffffffffu, finite);
+    if (my_hi != tag_hi || my_lo != tag_lo) return FSPANN_V_TAG_FAIL;     // AGC:159-165
+    if (!all_finite) return FSPANN_V_NON_FINITE;                           // QSI:253
+    return FSPANN_V_OK;
+}
+
+__global__ void __launch_bounds__(RF_THREADS) refine_decrypt_kernel(StoreView sv, RefineParams p) {
+    extern __shared__ __align__(16) unsigned char rf_smem[];
+    uint32_t *te_s = reinterpret_cast<uint32_t *>(rf_smem);                 // [256][32] lane-replicated Te0
+    uint32_t *s_rk = te_s + 256 * 32;                                       // [kMaxKeys][60]
+    int32_t *s_ver = reinterpret_cast<int32_t *>(s_rk + kMaxKeys * 60);     // [kMaxKeys]
+    double *pt_all = reinterpret_cast<double *>(s_ver + kMaxKeys);          // [RF_WARPS][dim_pad]
+    const int dim = sv.dim, dim_pad = (dim + 1) & ~1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    for (int i = tid; i < 256 * 32; i += RF_THREADS) te_s[i] = sv.te0[i >> 5];
+    const int nkeys = sv.keys->n;
+    for (int i = tid; i < nkeys * 60; i += RF_THREADS) s_rk[i] = sv.keys->rk[i / 60][i % 60];
+    for (int i = tid; i < kMaxKeys; i += RF_THREADS) s_ver[i] = i < nkeys ? sv.keys->version[i] : INT32_MIN;
+    __syncthreads();
+
+    const TeSmem te{te_s + lane};
+    double *pt_row = pt_all + (size_t)warp * dim_pad;
+    const int n_uniq = p.totals[1];
+    const int n_chunks = (n_uniq + 31) >> 5;
+
+    for (;;) {
+        int chunk = 0;
+        if (lane == 0) chunk = atomicAdd(&p.totals[2], 1);
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+        if (chunk >= n_chunks) break;
+        const int base = chunk << 5;
+        const int nrec = min(32, n_uniq - base);
+
+        // round 0: lane l prepares record l (header, key slot, E_K(J0))
+        int32_t my_id = -1; int my_slot = -1; uint4 my_hdr = make_uint4(0, 0, 0, 0); uint32_t my_ej0[4] = {0, 0, 0, 0};
+        if (lane < nrec) {
+            my_id = p.uniq[base + lane];
+            my_hdr = __ldg(reinterpret_cast<const uint4 *>(sv.rec + (size_t)my_id * sv.rec_stride));
+            my_slot = find_key_slot(s_ver, nkeys, (int32_t)my_hdr.w);
+        }
+        {
+            const int sl = my_slot < 0 ? 0 : my_slot;   // lanes without a key still run the rounds (uniform control flow)
+            const RkSmem rk{s_rk + sl * 60};
+            aes256_encrypt(te, rk, bswap32(my_hdr.x), bswap32(my_hdr.y), bswap32(my_hdr.z), 1u, my_ej0);
+        }
+
+        for (int r = 0; r < nrec; r++) {
+            const int32_t id = __shfl_sync(0xffffffffu, my_id, r);
+            const int slot = __shfl_sync(0xffffffffu, my_slot, r);
+            uint4 hdr;
+            hdr.x = __shfl_sync(0xffffffffu, my_hdr.x, r); hdr.y = __shfl_sync(0xffffffffu, my_hdr.y, r);
+            hdr.z = __shfl_sync(0xffffffffu, my_hdr.z, r); hdr.w = __shfl_sync(0xffffffffu, my_hdr.w, r);
+            uint32_t ej0[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) ej0[k] = __shfl_sync(0xffffffffu, my_ej0[k], r);
+
+            int verdict;
+            if (slot < 0) verdict = FSPANN_V_NO_KEY;                         // KRS:82-88 -> QSI:265-270
+            else verdict = warp_decrypt_record(sv, sv.rec + (size_t)id * sv.rec_stride, id, hdr, slot, ej0, te, s_rk, pt_row, lane);
+            __syncwarp();
+
+            // the (query, rank) pairs that selected this record
+            const int off = p.cnt[id], n_pairs = p.cnt[id + 1] - off;
+            for (int j = lane; j < n_pairs; j += 32) {
+                const uint32_t pair = p.pairs[off + j];
+                if (verdict == FSPANN_V_OK) {
+                    const double *qv = p.queries + (size_t)(pair / (uint32_t)p.stride) * dim;
+                    double s = 0.0;
+                    for (int i = 0; i < dim; i++) {                           // QSI:364-372, strict FP64, index order
+                        const double d = __dsub_rn(__ldg(qv + i), pt_row[i]);
+                        s = __dadd_rn(s, __dmul_rn(d, d));
+                    }
+                    p.dist[pair] = __dsqrt_rn(s);
+                }
+                p.verdict[pair] = (uint8_t)verdict;
+            }
+            if (verdict == FSPANN_V_OK && lane == 0) atomicOr(&p.touched[id >> 5], 1u << (id & 31));   // QSI:262
+            __syncwarp();
+        }
+    }
+}
+
+int launch_refine_decrypt(cudaStream_t s, const StoreView &sv, const RefineParams &p, int sm_count) {
+    const int dim_pad = (sv.dim + 1) & ~1;
+    const size_t smem = sizeof(uint32_t) * (256 * 32 + kMaxKeys * 60) + sizeof(int32_t) * kMaxKeys + sizeof(double) * (size_t)RF_WARPS * dim_pad;
+    static size_t configured = 0;
+    if (smem > configured) {
+        if (cudaFuncSetAttribute(refine_decrypt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+        configured = smem;
+    }
+    int per_sm = 2;
+    refine_decrypt_kernel<<<sm_count * per_sm, RF_THREADS, smem, s>>>(sv, p);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// per-query stable top-k (QSI:298-316): order by (Double.compare(dist), candidate order); distances are >= +0.0 so
+// the IEEE bit pattern orders like the value.  One CTA per query, k rounds of block-wide arg-min.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int TK_THREADS = 128;
+
+__global__ void __launch_bounds__(TK_THREADS) refine_topk_kernel(RefineParams p) {
+    __shared__ unsigned long long s_key[TK_THREADS / 32];
+    __shared__ int s_rank[TK_THREADS / 32];
+    __shared__ unsigned long long s_last_key;
+    __shared__ int s_last_rank, s_ndec;
+    const int64_t q = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = p.n_cand[q];
+    const double *dist = p.dist + (size_t)q * p.stride;
+    const uint8_t *ver = p.verdict + (size_t)q * p.stride;
+
+    int ndec = 0;
+    for (int r = tid; r < n; r += TK_THREADS) ndec += ver[r] == FSPANN_V_OK;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) ndec += __shfl_xor_sync(0xffffffffu, ndec, o);
+    if (tid == 0) { s_ndec = 0; s_last_rank = -1; s_last_key = 0ull; }
+    __syncthreads();
+    if (lane == 0) atomicAdd(&s_ndec, ndec);
+    __syncthreads();
+    const int total_ok = s_ndec;
+    const int eff = min(p.k, total_ok);
+
+    for (int round = 0; round < eff; round++) {
+        const unsigned long long lk = s_last_key; const int lr = s_last_rank;
+        unsigned long long best = ~0ull; int best_r = 0x7fffffff;
+        for (int r = tid; r < n; r += TK_THREADS) {
+            if (ver[r] != FSPANN_V_OK) continue;
+            const unsigned long long key = (unsigned long long)__double_as_longlong(dist[r]);
+            // strictly after the previously selected (key, rank)
+            const bool after = round == 0 || key > lk || (key == lk && r > lr);
+            if (after && (key < best || (key == best && r < best_r))) { best = key; best_r = r; }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const unsigned long long ok = __shfl_xor_sync(0xffffffffu, best, o);
+            const int orr = __shfl_xor_sync(0xffffffffu, best_r, o);
+            if (ok < best || (ok == best && orr < best_r)) { best = ok; best_r = orr; }
+        }
+        if (lane == 0) { s_key[warp] = best; s_rank[warp] = best_r; }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long b = s_key[0]; int br = s_rank[0];
+            for (int w = 1; w < TK_THREADS / 32; w++) if (s_key[w] < b || (s_key[w] == b && s_rank[w] < br)) { b = s_key[w]; br = s_rank[w]; }
+            s_last_key = b; s_last_rank = br;
+            p.topk_ids[(size_t)q * p.k + round] = p.cand_ids[(size_t)q * p.stride + br];
+            p.topk_dist[(size_t)q * p.k + round] = __longlong_as_double((long long)b);
+        }
+        __syncthreads();
+    }
+    for (int i = eff + tid; i < p.k; i += TK_THREADS) {
+        p.topk_ids[(size_t)q * p.k + i] = -1;
+        p.topk_dist[(size_t)q * p.k + i] = __longlong_as_double(0x7ff8000000000000ll);
+    }
+    if (tid == 0) { p.n_ret[q] = eff; if (p.n_dec) p.n_dec[q] = total_ok; }
+}
+
+int launch_refine_topk(cudaStream_t s, const RefineParams &p) {
+    if (p.Q <= 0) return 0;
+    refine_topk_kernel<<<(unsigned)p.Q, TK_THREADS, 0, s>>>(p);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void counters_kernel(int64_t Q, const int32_t *raw, const int32_t *uniq, const int32_t *n_dec, const int32_t *n_ret,
+                                const int32_t *n_cand, int32_t retried, int64_t *counters) {
+    const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (q >= Q) return;
+    int64_t *c = counters + q * FSPANN_COUNTERS;
+    c[0] = raw ? raw[q] : 0; c[1] = uniq ? uniq[q] : 0; c[2] = n_dec[q]; c[3] = n_ret[q]; c[4] = retried; c[5] = n_cand[q];
+}
+int launch_counters(cudaStream_t s, int64_t Q, const int32_t *raw, const int32_t *uniq, const int32_t *n_dec, const int32_t *n_ret,
+                    const int32_t *n_cand, int32_t retried, int64_t *counters) {
+    if (Q <= 0) return 0;
+    counters_kernel<<<(unsigned)((Q + 255) / 256), 256, 0, s>>>(Q, raw, uniq, n_dec, n_ret, n_cand, retried, counters);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// dst[i] = src[rows[i]] (gather) or dst[rows[i]] = src[i] (scatter); rows of row_bytes (multiple of 4)
+__global__ void gather_rows_kernel(const uint32_t *src, uint32_t *dst, const int32_t *rows, int64_t n_rows, int64_t row_words, int scatter) {
+    const int64_t total = n_rows * row_words;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / row_words, w = i - r * row_words;
+        if (scatter) dst[(int64_t)rows[r] * row_words + w] = src[i];
+        else dst[i] = src[(int64_t)rows[r] * row_words + w];
+    }
+}
+int launch_gather_rows(cudaStream_t s, const void *src, void *dst, const int32_t *rows, int64_t n_rows, int64_t row_bytes, bool scatter) {
+    if (n_rows <= 0) return 0;
+    const int64_t words = row_bytes / 4, total = n_rows * words;
+    int grid = (int)((total + 255) / 256); if (grid > 148 * 8) grid = 148 * 8;
+    gather_rows_kernel<<<grid, 256, 0, s>>>((const uint32_t *)src, (uint32_t *)dst, rows, n_rows, words, scatter ? 1 : 0);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// Packs host-layout arrays (iv[n][12], ct[n][8*dim+16], ver[n]) staged on the device into the record layout.
+__global__ void store_pack_kernel(uint8_t *rec, int64_t rec_stride, int32_t dim, int64_t n, const int32_t *ids, const uint8_t *iv,
+                                  const uint8_t *ct, const int32_t *ver) {
+    const int64_t ct_bytes = 8LL * dim + 16, words = (16 + ct_bytes) / 4;   // 8*dim+32 is a multiple of 8
+    const int64_t total = n * words;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / words, w = i - r * words;
+        const int64_t dst_row = ids ? ids[r] : r;
+        uint32_t v;
+        if (w < 3) v = reinterpret_cast<const uint32_t *>(iv)[r * 3 + w];
+        else if (w == 3) v = (uint32_t)ver[r];
+        else v = reinterpret_cast<const uint32_t *>(ct)[r * (ct_bytes / 4) + (w - 4)];
+        reinterpret_cast<uint32_t *>(rec + dst_row * rec_stride)[w] = v;
+    }
+}
+int launch_store_pack(cudaStream_t s, uint8_t *rec, int64_t rec_stride, int32_t dim, int64_t n, const int32_t *ids, const uint8_t *iv,
+                      const uint8_t *ct, const int32_t *ver) {
+    if (n <= 0) return 0;
+    const int64_t total = n * ((32 + 8LL * dim) / 4);
+    int grid = (int)((total + 255) / 256); if (grid > 148 * 16) grid = 148 * 16;
+    store_pack_kernel<<<grid, 256, 0, s>>>(rec, rec_stride, dim, n, ids, iv, ct, ver);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// debug tap (only with -DFSPANN_DEBUG_TAP): plaintext of listed records to global memory, for the parity test that
+// "decrypted plaintexts are bit-exact".  Not compiled into the production library.
+// ------------------------------------------------------------------------------------------------------------------
+#ifdef FSPANN_DEBUG_TAP
+__global__ void __launch_bounds__(RF_THREADS) debug_decrypt_kernel(StoreView sv, int64_t n, const int32_t *ids, double *pt, uint8_t *verdict) {
+    extern __shared__ __align__(16) unsigned char rf_smem[];
+    uint32_t *te_s = reinterpret_cast<uint32_t *>(rf_smem);
+    uint32_t *s_rk = te_s + 256 * 32;
+    int32_t *s_ver = reinterpret_cast<int32_t *>(s_rk + kMaxKeys * 60);
+    double *pt_all = reinterpret_cast<double *>(s_ver + kMaxKeys);
+    const int dim = sv.dim, dim_pad = (dim + 1) & ~1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < 256 * 32; i += RF_THREADS) te_s[i] = sv.te0[i >> 5];
+    const int nkeys = sv.keys->n;
+    for (int i = tid; i < nkeys * 60; i += RF_THREADS) s_rk[i] = sv.keys->rk[i / 60][i % 60];
+    for (int i = tid; i < kMaxKeys; i += RF_THREADS) s_ver[i] = i < nkeys ? sv.keys->version[i] : INT32_MIN;
+    __syncthreads();
+    const TeSmem te{te_s + lane};
+    double *pt_row = pt_all + (size_t)warp * dim_pad;
+    for (int64_t j = (int64_t)blockIdx.x * RF_WARPS + warp; j < n; j += (int64_t)gridDim.x * RF_WARPS) {
+        const int32_t id = ids[j];
+        int v;
+        if (id < 0 || id >= sv.N || is_deleted(sv, id)) v = FSPANN_V_NOT_FOUND;
+        else {
+            const uint8_t *rec = sv.rec + (size_t)id * sv.rec_stride;
+            const uint4 hdr = __ldg(reinterpret_cast<const uint4 *>(rec));
+            const int slot = find_key_slot(s_ver, nkeys, (int32_t)hdr.w);
+            if (slot < 0) v = FSPANN_V_NO_KEY;
+            else {
+                uint32_t ej0[4];
+                aes256_encrypt(te, RkSmem{s_rk + slot * 60}, bswap32(hdr.x), bswap32(hdr.y), bswap32(hdr.z), 1u, ej0);
+                v = warp_decrypt_record(sv, rec, id, hdr, slot, ej0, te, s_rk, pt_row, lane);
+            }
+        }
+        __syncwarp();
+        for (int i = lane; i < dim; i += 32) pt[j * dim + i] = (v == FSPANN_V_OK || v == FSPANN_V_NON_FINITE) ? pt_row[i] : __longlong_as_double(0x7ff8000000000000ll);
+        if (lane == 0) verdict[j] = (uint8_t)v;
+        __syncwarp();
+    }
+}
+int launch_debug_decrypt(cudaStream_t s, const StoreView &sv, int64_t n, const int32_t *ids, double *pt, uint8_t *verdict) {
+    const int dim_pad = (sv.dim + 1) & ~1;
+    const size_t smem = sizeof(uint32_t) * (256 * 32 + kMaxKeys * 60) + sizeof(int32_t) * kMaxKeys + sizeof(double) * (size_t)RF_WARPS * dim_pad;
+    if (cudaFuncSetAttribute(debug_decrypt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    int grid = (int)((n + RF_WARPS - 1) / RF_WARPS); if (grid > 148 * 2) grid = 148 * 2; if (grid < 1) grid = 1;
+    debug_decrypt_kernel<<<grid, RF_THREADS, smem, s>>>(sv, n, ids, pt, verdict);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+#else
+int launch_debug_decrypt(cudaStream_t, const StoreView &, int64_t, const int32_t *, double *, uint8_t *) { return -2; }
+#endif
+
+}  // namespace fsp

@@ -1,0 +1,176 @@
+"""Thin object wrapper over the C ABI: one GpuContext per GPU (include/fspann_gpu.h)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+
+
+class GpuContext:
+    def __init__(self, device: int = 0, debug: bool = False):
+        self.lib = N.load(debug)
+        self.ctx = C.c_void_p()
+        rc = self.lib.fspann_ctx_create(C.c_int(device), C.byref(self.ctx))
+        if rc != N.OK:
+            self.ctx = None
+            N.check(self.lib, None, rc)
+        self.device = device
+        self.dim = self.T = self.D = self.m = self.lam = self.W = 0
+        self.N = 0
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.fspann_ctx_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        N.check(self.lib, self.ctx, rc)
+
+    # ---- uploads
+    def gfunctions_upload(self, dim, T, D, m, lam, alpha, r, omega):
+        alpha, r, omega = (np.ascontiguousarray(x, dtype=np.float64) for x in (alpha, r, omega))
+        self._ck(self.lib.fspann_gfunctions_upload(self.ctx, dim, T, D, m, lam, N.ptr(alpha), N.ptr(r), N.ptr(omega)))
+        self.dim, self.T, self.D, self.m, self.lam, self.W = dim, T, D, m, lam, (m * lam + 63) // 64
+
+    def routing_upload(self, dim, T, D, m, lam, alpha, r, omega, min_key, max_key, rep, ids):
+        alpha, r, omega = (np.ascontiguousarray(x, dtype=np.float64) for x in (alpha, r, omega))
+        min_key = np.ascontiguousarray(min_key, dtype=np.int64)
+        max_key = np.ascontiguousarray(max_key, dtype=np.int64)
+        rep = np.ascontiguousarray(rep, dtype=np.uint64)
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        n_ids = ids.shape[-1]
+        self._ck(self.lib.fspann_routing_upload(self.ctx, dim, T, D, m, lam, N.ptr(alpha), N.ptr(r), N.ptr(omega), C.c_int64(n_ids),
+                                                N.ptr(min_key), N.ptr(max_key), N.ptr(rep), N.ptr(ids)))
+        self.dim, self.T, self.D, self.m, self.lam, self.W = dim, T, D, m, lam, (m * lam + 63) // 64
+
+    def deleted_set(self, flags):
+        if flags is None:
+            self._ck(self.lib.fspann_deleted_set(self.ctx, None, C.c_int64(0)))
+        else:
+            flags = np.ascontiguousarray(flags, dtype=np.uint8)
+            self._ck(self.lib.fspann_deleted_set(self.ctx, N.ptr(flags), C.c_int64(flags.shape[0])))
+
+    def store_upload(self, dim, iv, ct, key_version):
+        iv = np.ascontiguousarray(iv, dtype=np.uint8)
+        ct = np.ascontiguousarray(ct, dtype=np.uint8)
+        key_version = np.ascontiguousarray(key_version, dtype=np.int32)
+        n = iv.shape[0]
+        assert iv.shape == (n, 12) and ct.shape == (n, 8 * dim + 16) and key_version.shape == (n,)
+        self._ck(self.lib.fspann_store_upload(self.ctx, C.c_int64(n), dim, N.ptr(iv), N.ptr(ct), N.ptr(key_version)))
+        self.N = n
+        self.store_dim = dim
+
+    def store_update(self, ids, iv, ct, key_version):
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        iv = np.ascontiguousarray(iv, dtype=np.uint8)
+        ct = np.ascontiguousarray(ct, dtype=np.uint8)
+        key_version = np.ascontiguousarray(key_version, dtype=np.int32)
+        self._ck(self.lib.fspann_store_update(self.ctx, C.c_int64(ids.shape[0]), N.ptr(ids), N.ptr(iv), N.ptr(ct), N.ptr(key_version)))
+
+    def keys_set(self, version: int, key: bytes):
+        assert len(key) == 32
+        self._ck(self.lib.fspann_keys_set(self.ctx, C.c_int32(version), C.c_char_p(key)))
+
+    def keys_retire(self, version: int):
+        self._ck(self.lib.fspann_keys_retire(self.ctx, C.c_int32(version)))
+
+    # ---- hot path, host buffers
+    def tokengen_batch(self, queries):
+        queries = np.ascontiguousarray(queries, dtype=np.float64)
+        if queries.ndim != 2 or queries.shape[1] != self.dim:
+            raise N.IllegalArgumentError(f"Expected vector length {self.dim}")
+        Q = queries.shape[0]
+        codes = np.zeros((Q, self.T * self.D, self.W), dtype=np.uint64)
+        self._ck(self.lib.fspann_tokengen_batch(self.ctx, C.c_int64(Q), N.ptr(queries), N.ptr(codes)))
+        return codes
+
+    def route_batch(self, codes, probes, hard_cap, B, ham_threshold=0):
+        codes = np.ascontiguousarray(codes, dtype=np.uint64)
+        Q = codes.shape[0]
+        cid = np.full((Q, B), -1, dtype=np.int32)
+        csc = np.full((Q, B), -1, dtype=np.int32)
+        nc = np.zeros(Q, dtype=np.int32)
+        raw = np.zeros(Q, dtype=np.int32)
+        uq = np.zeros(Q, dtype=np.int32)
+        self._ck(self.lib.fspann_route_batch(self.ctx, C.c_int64(Q), N.ptr(codes), C.c_int32(probes), C.c_int64(hard_cap),
+                                             C.c_int32(ham_threshold), C.c_int32(B), N.ptr(cid), N.ptr(csc), N.ptr(nc), N.ptr(raw), N.ptr(uq)))
+        return dict(cand_ids=cid, cand_scores=csc, n_cand=nc, raw_seen=raw, unique=uq)
+
+    def refine_batch(self, queries, cand_ids, n_cand, k):
+        queries = np.ascontiguousarray(queries, dtype=np.float64)
+        cand_ids = np.ascontiguousarray(cand_ids, dtype=np.int32)
+        n_cand = np.ascontiguousarray(n_cand, dtype=np.int32)
+        Q, stride = cand_ids.shape
+        tid = np.full((Q, k), -1, dtype=np.int32)
+        td = np.full((Q, k), np.nan, dtype=np.float64)
+        nret = np.zeros(Q, dtype=np.int32)
+        ver = np.full((Q, stride), 255, dtype=np.uint8)
+        ndec = np.zeros(Q, dtype=np.int32)
+        self._ck(self.lib.fspann_refine_batch(self.ctx, C.c_int64(Q), N.ptr(queries), N.ptr(cand_ids), N.ptr(n_cand), C.c_int32(stride),
+                                              C.c_int32(k), N.ptr(tid), N.ptr(td), N.ptr(nret), N.ptr(ver), N.ptr(ndec)))
+        return dict(top_ids=tid, top_dist=td, n_ret=nret, verdict=ver, n_decrypted=ndec)
+
+    def search_batch(self, queries, k, probes, hard_cap, B, ham_threshold=0, out=None):
+        """Host buffers in, host buffers out.  `queries` may be a numpy array or (address, Q) of pinned memory via out=."""
+        queries = np.ascontiguousarray(queries, dtype=np.float64)
+        if queries.ndim != 2 or queries.shape[1] != self.dim:
+            raise N.IllegalArgumentError(f"Query dimension mismatch: expected={self.dim} got={queries.shape[-1]}")
+        Q = queries.shape[0]
+        if out is None:
+            out = dict(top_ids=np.full((Q, k), -1, dtype=np.int32), top_dist=np.full((Q, k), np.nan, dtype=np.float64),
+                       n_ret=np.zeros(Q, dtype=np.int32), counters=np.zeros((Q, N.COUNTERS), dtype=np.int64))
+        self._ck(self.lib.fspann_search_batch(self.ctx, C.c_int64(Q), N.ptr(queries), C.c_int32(k), C.c_int32(probes), C.c_int64(hard_cap),
+                                              C.c_int32(B), C.c_int32(ham_threshold), N.ptr(out["top_ids"]), N.ptr(out["top_dist"]),
+                                              N.ptr(out["n_ret"]), N.ptr(out["counters"])))
+        return out
+
+    def search_batch_raw(self, Q, queries_addr, k, probes, hard_cap, B, ham_threshold, ids_addr, dist_addr, nret_addr, counters_addr):
+        """Host-pointer call with caller-provided (e.g. pinned) buffers given as raw addresses."""
+        self._ck(self.lib.fspann_search_batch(self.ctx, C.c_int64(Q), C.c_void_p(queries_addr), C.c_int32(k), C.c_int32(probes),
+                                              C.c_int64(hard_cap), C.c_int32(B), C.c_int32(ham_threshold), C.c_void_p(ids_addr),
+                                              C.c_void_p(dist_addr), C.c_void_p(nret_addr),
+                                              C.c_void_p(counters_addr) if counters_addr else None))
+
+    def search_batch_dev(self, Q, d_queries, k, probes, hard_cap, B, ham_threshold, allow_retry, d_ids, d_dist, d_nret, d_counters=None):
+        """Device pointers (ints); enqueues on the context stream, no synchronisation unless allow_retry."""
+        self._ck(self.lib.fspann_search_batch_dev(self.ctx, C.c_int64(Q), C.c_void_p(d_queries), C.c_int32(k), C.c_int32(probes),
+                                                  C.c_int64(hard_cap), C.c_int32(B), C.c_int32(ham_threshold), C.c_int32(allow_retry),
+                                                  C.c_void_p(d_ids), C.c_void_p(d_dist), C.c_void_p(d_nret),
+                                                  C.c_void_p(d_counters) if d_counters else None))
+
+    def touched(self, clear: bool = False) -> np.ndarray:
+        words = (self.N + 31) // 32
+        bm = np.zeros(words, dtype=np.uint32)
+        self._ck(self.lib.fspann_touched_fetch(self.ctx, N.ptr(bm), C.c_int64(words), C.c_int32(1 if clear else 0)))
+        bits = np.unpackbits(bm.view(np.uint8), bitorder="little")[: self.N]
+        return np.nonzero(bits)[0].astype(np.int32)
+
+    def stage_ms(self):
+        out = (C.c_float * 5)()
+        n = self.lib.fspann_last_stage_ms(self.ctx, out)
+        return dict(tokengen=out[0], route=out[1], group=out[2], decrypt=out[3], topk=out[4], launches=int(n))
+
+    def stream(self) -> int:
+        return int(self.lib.fspann_ctx_stream(self.ctx) or 0)
+
+    def sync(self):
+        self._ck(self.lib.fspann_ctx_sync(self.ctx))
+
+    def launch_count(self) -> int:
+        return int(self.lib.fspann_ctx_launch_count(self.ctx))
+
+    def debug_decrypt(self, ids):
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        n = ids.shape[0]
+        pt = np.zeros((n, self.store_dim), dtype=np.float64)
+        ver = np.zeros(n, dtype=np.uint8)
+        self._ck(self.lib.fspann_debug_decrypt(self.ctx, C.c_int64(n), N.ptr(ids), N.ptr(pt), N.ptr(ver)))
+        return pt, ver

@@ -1,0 +1,161 @@
+/*
+ * fspann_gpu.h -- C ABI of libfspann_gpu.so: the B200 (sm_100a) implementation of FSPANN's query hot path
+ * (TokenGen -> Route -> Refine).
+ *
+ * The reference (pure Java, /root/reference/fsp-anns-parent) has no FFI for this path; its seam is
+ *   QueryService.search(QueryToken)                       query/src/main/java/com/fspann/query/service/QueryService.java:10-12
+ *   QueryTokenFactory.create(double[], int)               query/src/main/java/com/fspann/query/core/QueryTokenFactory.java:63
+ *   PartitionedIndexService.lookupCandidatesWithScores    index/src/main/java/com/fspann/index/paper/PartitionedIndexService.java:592
+ *   PartitionedIndexService.loadPointIfActive             .../PartitionedIndexService.java:717
+ *   CryptoService.decryptFromPoint                        crypto/src/main/java/com/fspann/crypto/AesGcmCryptoService.java:126
+ *   KeyLifeCycleService.getVersion                        keymanagement/src/main/java/com/fspann/key/KeyRotationServiceImpl.java:82
+ * Each entry point below names the Java member it replaces.  A JNI / Panama binding that a maintainer would
+ * add on the Java side is shown in INTEGRATION.md.
+ *
+ * Conventions (mirroring the reference's):
+ *  - plain C, no torch / CUDA types in signatures; every array is caller-owned and copied (the reference clones
+ *    every byte[] at its getters, common/.../QueryToken.java:76-93), so no host pointer is retained;
+ *  - one context per GPU; calls on one context are serialised on its stream; distinct contexts are independent;
+ *  - return 0 on success, negative on error; fspann_last_error(ctx) gives the text:
+ *        FSPANN_E_ARG    <-> IllegalArgumentException / NullPointerException (bad argument, dimension mismatch)
+ *        FSPANN_E_STATE  <-> IllegalStateException (index not finalized / registry mismatch, PIS:594, QTF:67-88)
+ *        FSPANN_E_CUDA   <-> a CUDA runtime failure (there is NO CPU fallback)
+ *        FSPANN_E_NOMEM  <-> device allocation failure
+ *  - per-candidate failures never fail a call: they are reported as verdict codes and counted (QSI:242-270);
+ *  - ids are the non-negative 32-bit integers whose decimal strings the reference's facade uses as point ids
+ *    (api/.../ForwardSecureANNSystem.java:501,515).  Routing order depends on java.lang.String.hashCode of that
+ *    string, which the kernels recompute.
+ *  - "_dev" variants take DEVICE pointers (inputs already resident in HBM) and enqueue on the context stream
+ *    without synchronising; everything else takes HOST pointers and returns after the results are on the host.
+ */
+#ifndef FSPANN_GPU_H
+#define FSPANN_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FSPANN_OK 0
+#define FSPANN_E_ARG (-1)
+#define FSPANN_E_STATE (-2)
+#define FSPANN_E_CUDA (-3)
+#define FSPANN_E_NOMEM (-4)
+
+/* verdict codes per refined candidate (QSI:242-270 counters notFound / decryptError / invalidVector) */
+#define FSPANN_V_OK 0         /* decrypted, tag verified, finite: distance evaluated, id is "touched" (QSI:262) */
+#define FSPANN_V_NOT_FOUND 1  /* loadPointIfActive returned null: deleted / unknown id (PIS:717-724)           */
+#define FSPANN_V_NO_KEY 2     /* keyService.getVersion threw: version unknown or retired (KRS:82-88)           */
+#define FSPANN_V_TAG_FAIL 3   /* AES-GCM tag mismatch (AGC:159-165)                                            */
+#define FSPANN_V_NON_FINITE 4 /* plaintext holds NaN/Inf (QSI:253, QSI:407-413)                                */
+
+#define FSPANN_BLOCK 64       /* DEFAULT_GREEDY_BLOCK_SIZE (PIS:92) */
+#define FSPANN_MAX_KEYS 16    /* live key versions held on the device */
+#define FSPANN_COUNTERS 6     /* per query: candTotal(raw), candKept(unique), candDecrypted, returned, retried, refined */
+
+typedef struct fspann_ctx fspann_ctx;
+
+/* ---- context ------------------------------------------------------------------------------------------ */
+int fspann_ctx_create(int device, fspann_ctx **out);
+void fspann_ctx_destroy(fspann_ctx *ctx);
+const char *fspann_last_error(const fspann_ctx *ctx);
+/* cudaStream_t of the context (as void*), so a harness can record CUDA events around "_dev" calls. */
+void *fspann_ctx_stream(fspann_ctx *ctx);
+int fspann_ctx_sync(fspann_ctx *ctx);
+/* number of kernels this library has launched on the context since creation (bench.py's gpu_launches). */
+int64_t fspann_ctx_launch_count(const fspann_ctx *ctx);
+
+/* ---- Setup state crossing the boundary ----------------------------------------------------------------- */
+/* Routing state I = GFunctions + frozen partitions: GFunctionRegistry contents (GFR:63-147; Coding.GFunction
+ * alpha/r/omega, Coding:52-97) and every DivisionState.partitions after finalizeForSearch (PIS:789-845, GP:13-32).
+ *   alpha[T*D][m][dim], r[T*D][m], omega[T*D][m] FP64;   n_ids = points per (table,division);
+ *   P = ceil(n_ids/64) partitions per (t,d);  min_key/max_key int64 [T*D][P];  rep_code uint64 [T*D][P][W],
+ *   W = ceil(m*lambda/64), bit p of a code = BitSet bit p (word p>>6, bit p&63);  ids int32 [T*D][n_ids] in
+ *   partition order (partition i owns slots [64i, min(64i+64, n_ids))).
+ * Immutable until the next upload (the reference freezes the index, PIS:842). */
+int fspann_routing_upload(fspann_ctx *ctx, int32_t dim, int32_t T, int32_t D, int32_t m, int32_t lambda,
+                          const double *alpha, const double *r, const double *omega, int64_t n_ids,
+                          const int64_t *min_key, const int64_t *max_key, const uint64_t *rep_code,
+                          const int32_t *ids);
+
+/* GFunctions only: lets TokenGen run before any partition exists (Setup-side bulk coding of the base set,
+ * PIS:331-346).  Route / search on such a context fail with FSPANN_E_STATE ("Index not finalized"). */
+int fspann_gfunctions_upload(fspann_ctx *ctx, int32_t dim, int32_t T, int32_t D, int32_t m, int32_t lambda,
+                             const double *alpha, const double *r, const double *omega);
+
+/* metadata.isDeleted(id) (common/.../RocksDBMetadataManager.java:203-224): flags[id] != 0 => deleted.
+ * n may be 0 / flags NULL to clear.  Consulted by Route (PIS:739) and Refine (PIS:718). */
+int fspann_deleted_set(fspann_ctx *ctx, const uint8_t *flags, int64_t n);
+
+/* Record store Store_t: EncryptedPoint fields (EP:18-26) for ids 0..N-1, packed:
+ *   iv uint8 [N][12], ct uint8 [N][8*dim+16] (ciphertext || 128-bit tag, Java doFinal layout),
+ *   key_version int32 [N].  Replaces RocksDBMetadataManager.loadEncryptedPoint (RDB:530-544) on the hot path. */
+int fspann_store_upload(fspann_ctx *ctx, int64_t N, int32_t dim, const uint8_t *iv, const uint8_t *ct,
+                        const int32_t *key_version);
+/* In-place replacement of n records: the result of Migrate = reencryptTouched (KRS:250-266).  Atomic with
+ * respect to later batches (stream ordered). */
+int fspann_store_update(fspann_ctx *ctx, int64_t n, const int32_t *ids, const uint8_t *iv, const uint8_t *ct,
+                        const int32_t *key_version);
+
+/* Key ring K_t: KeyLifeCycleService.getVersion(v) -> 32-byte AES key (KRS:82-88, KM:221-237).
+ * set = Rotate made version v available; retire = Retire deleted it (KM:274-317): records still bound to a
+ * retired version then yield FSPANN_V_NO_KEY, exactly as the Java path counts a decryptError. */
+int fspann_keys_set(fspann_ctx *ctx, int32_t version, const uint8_t key[32]);
+int fspann_keys_retire(fspann_ctx *ctx, int32_t version);
+
+/* ---- TokenGen (a2-a3): Coding.C for every (table, division) of every query (QTF:98-131, Coding:250-301) ---
+ * queries FP64 [Q][dim] -> codes uint64 [Q][T*D][W].  A query holding NaN/Inf fails the whole call with
+ * FSPANN_E_ARG (Coding:355-360 requireVector). */
+int fspann_tokengen_batch(fspann_ctx *ctx, int64_t Q, const double *queries, uint64_t *codes_out);
+
+/* ---- Route (a6-a12): lookupCandidatesWithScores + the first-B cut of QueryServiceImpl stage A.5 ------------
+ * (PIS:592-753, QSI:153-214).  probes = effectiveMaxProbes() (PIS:880-888), hard_cap = max(maxGlobalCandidates,
+ * refinementLimit) (PIS:612-615), B = effective refinementLimit (> 0), ham_threshold = hammingPrefilterThreshold.
+ * Outputs per query q: cand_ids/cand_scores [Q][B] (first n_cand[q] valid, in the reference's order),
+ * raw_seen[q] = getLastRawCandidateCount(), unique[q] = number of distinct candidates (lastCandKept). */
+int fspann_route_batch(fspann_ctx *ctx, int64_t Q, const uint64_t *codes, int32_t probes, int64_t hard_cap,
+                       int32_t ham_threshold, int32_t B, int32_t *cand_ids_out, int32_t *cand_scores_out,
+                       int32_t *n_cand_out, int32_t *raw_seen_out, int32_t *unique_out);
+
+/* ---- Refine (a13-a17): stage B + C of QueryServiceImpl.search (QSI:238-322) ---------------------------------
+ * For each query: candidates cand_ids[q][0..n_cand[q]) in order -> load, key lookup, AES-256-GCM verify+decrypt
+ * under the record's stored key version, finite check, exact sequential FP64 L2, stable top-k.
+ * cand_stride = row stride of cand_ids / verdict_out (>= max n_cand).  Outputs: topk_ids/topk_dist [Q][k]
+ * (first n_ret[q] valid), verdict_out uint8 [Q][cand_stride] (may be NULL), n_decrypted_out[q] (may be NULL).
+ * Plaintext vectors exist only in registers / shared memory and are never written to global memory. */
+int fspann_refine_batch(fspann_ctx *ctx, int64_t Q, const double *queries, const int32_t *cand_ids,
+                        const int32_t *n_cand, int32_t cand_stride, int32_t k, int32_t *topk_ids_out,
+                        double *topk_dist_out, int32_t *n_ret_out, uint8_t *verdict_out, int32_t *n_decrypted_out);
+
+/* ---- search (a4-a18): createToken + QueryServiceImpl.search for a batch, incl. the adaptive retry (QSI:327-337):
+ * a query whose first pass returned < k results or decrypted < 10*k candidates is re-run once with 10 probes and
+ * the second result is returned.  counters int64 [Q][FSPANN_COUNTERS] (may be NULL). */
+int fspann_search_batch(fspann_ctx *ctx, int64_t Q, const double *queries, int32_t k, int32_t probes,
+                        int64_t hard_cap, int32_t B, int32_t ham_threshold, int32_t *topk_ids_out,
+                        double *topk_dist_out, int32_t *n_ret_out, int64_t *counters_out);
+
+/* Device-resident variant: d_queries, d_topk_ids, d_topk_dist, d_n_ret, d_counters are DEVICE pointers; work is
+ * enqueued on the context stream and the call returns without synchronising.  The adaptive retry needs the
+ * per-query first-pass counters on the host, so it is applied only when allow_retry != 0 (which synchronises). */
+int fspann_search_batch_dev(fspann_ctx *ctx, int64_t Q, const double *d_queries, int32_t k, int32_t probes,
+                            int64_t hard_cap, int32_t B, int32_t ham_threshold, int32_t allow_retry,
+                            int32_t *d_topk_ids, double *d_topk_dist, int32_t *d_n_ret, int64_t *d_counters);
+
+/* Touched set (QSI:262, QSI:348-350 reencTracker.record): bitmap over ids (bit id&31 of word id>>5, N bits) of
+ * every record that reached verdict OK since the last clear.  Feeds the host's selective re-encryption. */
+int fspann_touched_fetch(fspann_ctx *ctx, uint32_t *bitmap_out, int64_t n_words, int32_t clear);
+
+/* Per-stage device time in milliseconds of the last search/refine call (CUDA events on the context stream):
+ * out[0]=tokengen, out[1]=route, out[2]=refine-group(count/scan/fill), out[3]=refine-decrypt+distance,
+ * out[4]=top-k.  Returns the number of kernel launches of that call. */
+int64_t fspann_last_stage_ms(fspann_ctx *ctx, float out[5]);
+
+/* ---- debug build only (compiled with -DFSPANN_DEBUG_TAP): decrypted plaintext for parity tests -------------
+ * Returns FSPANN_E_STATE in production builds, where plaintext never reaches global memory. */
+int fspann_debug_decrypt(fspann_ctx *ctx, int64_t n, const int32_t *ids, double *plaintext_out, uint8_t *verdict_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FSPANN_GPU_H */
