@@ -20,7 +20,7 @@ EXPORTS = [
     "fspann_ctx_launch_count", "fspann_routing_upload", "fspann_gfunctions_upload", "fspann_deleted_set",
     "fspann_store_upload", "fspann_store_update", "fspann_keys_set", "fspann_keys_retire", "fspann_tokengen_batch",
     "fspann_route_batch", "fspann_refine_batch", "fspann_search_batch", "fspann_search_batch_dev", "fspann_touched_fetch",
-    "fspann_last_stage_ms", "fspann_debug_decrypt",
+    "fspann_last_stage_ms", "fspann_debug_decrypt", "fspann_set_option", "fspann_get_info",
 ]
 
 _libs = {}
@@ -38,6 +38,7 @@ def load(debug: bool = False):
     lib.fspann_ctx_stream.restype = C.c_void_p
     lib.fspann_ctx_launch_count.restype = C.c_int64
     lib.fspann_last_stage_ms.restype = C.c_int64
+    lib.fspann_get_info.restype = C.c_int64
     _libs[path] = lib
     return lib
 

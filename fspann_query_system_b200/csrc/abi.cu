@@ -41,6 +41,9 @@ struct fspann_ctx {
     std::map<int32_t, std::vector<uint8_t>> keys;  // live versions -> raw key
 
     // scratch (grow only)
+    DevBuf s_vis_part, s_vis_score, s_vis_n;
+    int opt_route_general = 0;   // force the general (sequential, cap-exact) Route kernel
+    int last_route_path = 0;     // 1 = shared-memory fast path, 2 = general path
     DevBuf s_queries, s_codes, s_cand_ids, s_cand_sc, s_ncand, s_raw, s_uniq_cnt, s_route_scratch, s_overflow;
     DevBuf s_cnt, s_flag, s_fill, s_uniq, s_pairs, s_bsums, s_totals, s_dist, s_verdict;
     DevBuf s_topk_ids, s_topk_dist, s_nret, s_ndec, s_counters;
@@ -169,15 +172,27 @@ int do_route(fspann_ctx *ctx, int64_t Q, const uint64_t *d_codes, int probes, in
     if (max_nodes > hard_cap + kBlock) max_nodes = hard_cap + kBlock;
     if (max_nodes < kBlock) max_nodes = kBlock;
     p.max_nodes = (int32_t)max_nodes;
+    CK(cudaMemsetAsync(d_cand_ids, 0xff, sizeof(int32_t) * (size_t)Q * B, ctx->stream));
+    CK(cudaMemsetAsync(d_cand_sc, 0xff, sizeof(int32_t) * (size_t)Q * B, ctx->stream));
+    RouteFastExtra fx{};
+    size_t fsmem = 0;
+    if (!ctx->opt_route_general && route_fast_eligible(rv, probes, hard_cap, B, fx, fsmem)) {
+        ENSURE(ctx->s_vis_part, sizeof(int32_t) * (size_t)Q * rv.TD * probes);
+        ENSURE(ctx->s_vis_score, (size_t)Q * rv.TD * probes);
+        ENSURE(ctx->s_vis_n, (size_t)Q * rv.TD);
+        LAUNCHED(launch_route_fast(ctx->stream, rv, p, fx, fsmem, ctx->sm_count, (int32_t *)ctx->s_vis_part.p, (uint8_t *)ctx->s_vis_score.p,
+                                   (uint8_t *)ctx->s_vis_n.p));
+        ctx->last_route_path = 1;
+        return 0;
+    }
     p.scratch_ints = route_scratch_ints(p.cap0, p.max_nodes);
     const int grid = route_grid(Q, ctx->sm_count);
     ENSURE(ctx->s_route_scratch, sizeof(int32_t) * (size_t)p.scratch_ints * grid);
     ENSURE(ctx->s_overflow, sizeof(int32_t));
     p.scratch = (int32_t *)ctx->s_route_scratch.p;
     p.chain_overflow = (int32_t *)ctx->s_overflow.p;
-    CK(cudaMemsetAsync(d_cand_ids, 0xff, sizeof(int32_t) * (size_t)Q * B, ctx->stream));
-    CK(cudaMemsetAsync(d_cand_sc, 0xff, sizeof(int32_t) * (size_t)Q * B, ctx->stream));
     LAUNCHED(launch_route(ctx->stream, rv, p, grid));
+    ctx->last_route_path = 2;
     return 0;
 }
 
@@ -255,7 +270,7 @@ void fspann_ctx_destroy(fspann_ctx *ctx) {
                       &ctx->s_cand_sc, &ctx->s_ncand, &ctx->s_raw, &ctx->s_uniq_cnt, &ctx->s_route_scratch, &ctx->s_overflow, &ctx->s_cnt,
                       &ctx->s_flag, &ctx->s_fill, &ctx->s_uniq, &ctx->s_pairs, &ctx->s_bsums, &ctx->s_totals, &ctx->s_dist, &ctx->s_verdict,
                       &ctx->s_topk_ids, &ctx->s_topk_dist, &ctx->s_nret, &ctx->s_ndec, &ctx->s_counters, &ctx->s_stage_a, &ctx->s_stage_b,
-                      &ctx->s_stage_c, &ctx->r_rows, &ctx->r_queries, &ctx->r_codes, &ctx->r_topk_ids, &ctx->r_topk_dist, &ctx->r_nret,
+                      &ctx->s_stage_c, &ctx->s_vis_part, &ctx->s_vis_score, &ctx->s_vis_n, &ctx->r_rows, &ctx->r_queries, &ctx->r_codes, &ctx->r_topk_ids, &ctx->r_topk_dist, &ctx->r_nret,
                       &ctx->r_counters, &ctx->t_cand_ids, &ctx->t_cand_sc, &ctx->t_ncand, &ctx->t_raw, &ctx->t_uniq_cnt, &ctx->t_ndec};
     for (DevBuf *b : bufs) release(*b);
     for (int i = 0; i < 6; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -271,6 +286,18 @@ int fspann_ctx_sync(fspann_ctx *ctx) {
     return FSPANN_OK;
 }
 int64_t fspann_ctx_launch_count(const fspann_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int fspann_set_option(fspann_ctx *ctx, const char *name, int64_t value) {
+    if (!ctx || !name) return FSPANN_E_ARG;
+    if (!strcmp(name, "route_general")) { ctx->opt_route_general = value != 0; return FSPANN_OK; }
+    return fail(ctx, FSPANN_E_ARG, "unknown option %s", name);
+}
+int64_t fspann_get_info(fspann_ctx *ctx, const char *name) {
+    if (!ctx || !name) return -1;
+    if (!strcmp(name, "last_route_path")) return ctx->last_route_path;
+    if (!strcmp(name, "sm_count")) return ctx->sm_count;
+    return -1;
+}
 
 int fspann_routing_upload(fspann_ctx *ctx, int32_t dim, int32_t T, int32_t D, int32_t m, int32_t lambda, const double *alpha,
                           const double *r, const double *omega, int64_t n_ids, const int64_t *min_key, const int64_t *max_key,

@@ -220,12 +220,14 @@ FSP_HD uint64_t load_be64(const uint8_t *b) {
 // java.lang.String.hashCode of the decimal string of a non-negative id, spread like java.util.HashMap.hash
 // (h ^ (h >>> 16)).  Drives the reference's candidate ordering (PIS:619,690-696).
 FSP_HD uint32_t java_hash_decimal(int32_t id) {
-    uint32_t digits[10];
-    int n = 0;
-    uint32_t u = (uint32_t)id;
-    do { digits[n++] = u % 10u; u /= 10u; } while (u);
-    uint32_t h = 0;
-    while (n) h = 31u * h + (48u + digits[--n]);
+    // h = sum_i c_i * 31^(n-1-i): peel digits from the right, the power of 31 grows with the position
+    uint32_t u = (uint32_t)id, h = 0, p = 1;
+    do {
+        const uint32_t q = u / 10u;
+        h += (48u + (u - q * 10u)) * p;
+        p *= 31u;
+        u = q;
+    } while (u);
     return h ^ (h >> 16);
 }
 

@@ -63,6 +63,15 @@ struct RouteParams {
     int32_t *chain_overflow;  // set when a bucket chain reached 9 (Java would treeify; order then unspecified)
 };
 
+struct RouteFastExtra {
+    const int32_t *vis_part;
+    const uint8_t *vis_score;
+    const uint8_t *vis_n;
+    int n_raw;    // T*D*probes*64
+    int tbl;      // open-addressing slots (power of two)
+    int sort_n;   // bitonic sort width (power of two >= B + slack)
+};
+
 struct RefineParams {
     int64_t Q;
     const double *queries;    // [Q][dim]
@@ -90,6 +99,9 @@ struct RefineParams {
 int launch_tokengen(cudaStream_t s, const RoutingView &rv, int64_t Q, const double *queries, uint64_t *codes);
 int launch_route(cudaStream_t s, const RoutingView &rv, const RouteParams &p, int grid);
 int route_grid(int64_t Q, int sm_count);
+bool route_fast_eligible(const RoutingView &rv, int probes, int64_t hard_cap, int B, RouteFastExtra &x, size_t &smem);
+int launch_route_fast(cudaStream_t s, const RoutingView &rv, const RouteParams &p, RouteFastExtra x, size_t smem, int sm_count,
+                      int32_t *vis_part, uint8_t *vis_score, uint8_t *vis_n);
 int64_t route_scratch_ints(int32_t cap0, int32_t max_nodes);
 int launch_refine_group(cudaStream_t s, const StoreView &sv, const RefineParams &p);
 int launch_refine_decrypt(cudaStream_t s, const StoreView &sv, const RefineParams &p, int sm_count);

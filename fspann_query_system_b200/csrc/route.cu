@@ -18,6 +18,8 @@
 // Java map (at its initial capacity) in an L2-resident scratch area: heads[cap0] + a node pool.  The T*D groups are
 // processed in order (the algorithm is sequential across groups through the cap and the improvement counter), the
 // <= probes*64 ids of one group in parallel (they are distinct, so no two threads touch the same map entry).
+#include <algorithm>
+
 #include "fspann_internal.cuh"
 
 namespace fsp {
@@ -331,6 +333,321 @@ int launch_route(cudaStream_t s, const RoutingView &rv, const RouteParams &p, in
     const size_t smem = sizeof(int32_t) * ((size_t)2 * rv.TD * p.probes + rv.TD);
     route_kernel<<<grid, RT_THREADS, smem, s>>>(rv, p);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// =====================================================================================================================
+// Fast path.  Used when (a) the HARD_CAP can never bind (T*D*probes*64 - 64 < hard_cap, so every poll of PIS:657-659
+// proceeds) and (b) the per-query working set fits in shared memory.  Then nothing in the algorithm is sequential any
+// more except the per-id improvement count, which is resolved per id from its (short) occurrence chain:
+//   kernel 1 (route_probe_kernel): one thread per (query, table, division): centre partition + probe order + scores;
+//   kernel 2 (route_fast_kernel) : one 1024-thread CTA per query, everything in shared memory:
+//        gather the <= T*D*probes*64 ids (coalesced 256-byte partition rows), insert them into an open-addressing table
+//        of 16-bit positions (all occurrences of an id are chained through next_s), finalise per id (first position =
+//        Java insertion order, min score, #strict improvements in visit order), radix-select the B smallest
+//        (score, Java bucket, insertion order) keys and bitonic-sort just those.
+// =====================================================================================================================
+constexpr int RQ_THREADS = 1024;
+constexpr uint32_t RQ_EMPTY = 0xffffu;
+
+__global__ void route_probe_kernel(RoutingView rv, int64_t Q, const uint64_t *__restrict__ codes, int probes, int32_t *__restrict__ vis_part,
+                                   uint8_t *__restrict__ vis_score, uint8_t *__restrict__ vis_n) {
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= Q * rv.TD) return;
+    const int g = (int)(idx % rv.TD);
+    const int W = rv.W;
+    const int64_t P = rv.P;
+    int nv = 0;
+    if (P > 0 && probes > 0) {
+        uint64_t qc[4];
+        for (int w = 0; w < W; w++) qc[w] = codes[idx * W + w];
+        const int64_t *keys = rv.keys + (size_t)g * P * 2;
+        const uint64_t *rep = rv.rep + (size_t)g * P * W;
+        const int64_t center = find_nearest(keys, P, code_key(qc, W));
+        int64_t lo = center, hi = center;
+        bool lv = false, rvd = false; int ldist = 0, rdist = 0, lseq = 0, rseq = 0, seq = 0;
+        int64_t cur = center; int curd = hamming_w(qc, rep + (size_t)center * W, W);
+        for (;;) {
+            vis_part[idx * probes + nv] = (int32_t)cur;
+            vis_score[idx * probes + nv] = (uint8_t)curd;
+            nv++;
+            if (cur == lo && lo - 1 >= 0 && !lv) { lv = true; ldist = hamming_w(qc, rep + (size_t)(lo - 1) * W, W); lseq = seq++; }
+            if (cur == hi && hi + 1 < P && !rvd) { rvd = true; rdist = hamming_w(qc, rep + (size_t)(hi + 1) * W, W); rseq = seq++; }
+            if (nv >= probes) break;
+            if (!lv && !rvd) break;
+            bool take_left;
+            if (lv && rvd) take_left = (ldist < rdist) || (ldist == rdist && lseq < rseq);
+            else take_left = lv;
+            if (take_left) { lo -= 1; cur = lo; curd = ldist; lv = false; }
+            else { hi += 1; cur = hi; curd = rdist; rvd = false; }
+        }
+    }
+    vis_n[idx] = (uint8_t)nv;
+}
+
+__device__ __forceinline__ uint32_t cas16(uint16_t *addr, uint32_t expect, uint32_t val) {
+    uint32_t *w = reinterpret_cast<uint32_t *>(reinterpret_cast<uintptr_t>(addr) & ~(uintptr_t)3);
+    const int shift = (reinterpret_cast<uintptr_t>(addr) & 2) ? 16 : 0;
+    uint32_t old = *reinterpret_cast<volatile uint32_t *>(w);
+    for (;;) {
+        const uint32_t cur = (old >> shift) & 0xffffu;
+        if (cur != expect) return cur;
+        const uint32_t neu = (old & ~(0xffffu << shift)) | (val << shift);
+        const uint32_t prev = atomicCAS(w, old, neu);
+        if (prev == old) return expect;
+        old = prev;
+    }
+}
+
+size_t route_fast_smem(int TD, int probes, int n_raw, int tbl, int sort_n) {
+    size_t s = 0;
+    s += sizeof(uint64_t) * sort_n;            // skey
+    s += sizeof(int32_t) * n_raw;              // ids_s
+    s += sizeof(int32_t) * sort_n;             // sid
+    s += sizeof(int32_t) * TD * probes;        // vp_s
+    s += sizeof(uint16_t) * tbl;               // table
+    s += sizeof(uint16_t) * n_raw;             // next_s
+    s += ((size_t)TD * probes + 15) / 16 * 16; // vs_s
+    return s + 64;
+}
+
+__global__ void __launch_bounds__(RQ_THREADS, 1) route_fast_kernel(RoutingView rv, RouteParams p, RouteFastExtra x) {
+    extern __shared__ __align__(16) unsigned char rq_smem[];
+    const int TD = rv.TD, probes = p.probes, n_raw = x.n_raw, tbl = x.tbl, sort_n = x.sort_n;
+    uint64_t *skey = reinterpret_cast<uint64_t *>(rq_smem);
+    int32_t *ids_s = reinterpret_cast<int32_t *>(skey + sort_n);
+    int32_t *sid = ids_s + n_raw;
+    int32_t *vp_s = sid + sort_n;
+    uint16_t *table = reinterpret_cast<uint16_t *>(vp_s + TD * probes);
+    uint16_t *next_s = table + tbl;
+    uint8_t *vs_s = reinterpret_cast<uint8_t *>(next_s + n_raw);
+    __shared__ int32_t s_hist[256];
+    __shared__ int32_t s_raw, s_uniq, s_m, s_digit, s_cum, s_bin;
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int64_t n_ids = rv.n_ids;
+    const uint32_t tmask = (uint32_t)tbl - 1u;
+    int tshift = 32; while ((1u << (32 - tshift)) < (uint32_t)tbl) tshift--;
+
+    for (int64_t q = blockIdx.x; q < p.Q; q += gridDim.x) {
+        __syncthreads();
+        // ---- 1. stage visits, reset table ----
+        for (int v = tid; v < TD * probes; v += RQ_THREADS) {
+            const int g = v / probes, j = v - g * probes;
+            const int64_t vi = (q * TD + g) * probes + j;
+            const bool valid = j < (int)x.vis_n[q * TD + g];
+            vp_s[v] = valid ? x.vis_part[vi] : -1;
+            vs_s[v] = valid ? x.vis_score[vi] : 255;
+        }
+        for (int i = tid; i < tbl / 2; i += RQ_THREADS) reinterpret_cast<uint32_t *>(table)[i] = 0xffffffffu;
+        if (tid < 256) s_hist[tid] = 0;
+        if (tid == 0) { s_raw = 0; s_uniq = 0; s_m = 0; }
+        __syncthreads();
+        // ---- 2. gather ids (each partition row is 256 contiguous bytes) ----
+        for (int e = tid; e < n_raw; e += RQ_THREADS) {
+            const int v = e >> 6, pos = e & 63;
+            const int32_t part = vp_s[v];
+            int32_t id = -1;
+            if (part >= 0) {
+                const int64_t slot = (int64_t)part * kBlock + pos;
+                if (slot < n_ids) {
+                    id = __ldg(rv.ids + (size_t)(v / probes) * n_ids + slot);
+                    if (rv.deleted && id >= 0 && id < rv.n_deleted && rv.deleted[id]) id = -1;     // PIS:739
+                }
+            }
+            ids_s[e] = id;
+        }
+        __syncthreads();
+        // ---- 3. insert: table[slot] = head of the chain of all positions holding one id ----
+        for (int e = tid; e < n_raw; e += RQ_THREADS) {
+            const int32_t id = ids_s[e];
+            if (id < 0) continue;
+            next_s[e] = (uint16_t)RQ_EMPTY;
+            uint32_t slot = ((uint32_t)id * 0x9E3779B1u) >> tshift;    // any hash works here; Java's is only needed for the order
+            for (;;) {
+                uint32_t cur = *reinterpret_cast<volatile uint16_t *>(&table[slot]);
+                if (cur == RQ_EMPTY) {
+                    cur = cas16(&table[slot], RQ_EMPTY, (uint32_t)e);
+                    if (cur == RQ_EMPTY) break;                       // claimed an empty slot
+                }
+                if (ids_s[cur] == id) {                               // same id: push this occurrence onto its chain
+                    for (;;) {
+                        next_s[e] = (uint16_t)cur;
+                        const uint32_t prev = cas16(&table[slot], cur, (uint32_t)e);
+                        if (prev == cur) break;
+                        cur = prev;                                   // still the same id (slots never change owner)
+                    }
+                    break;
+                }
+                slot = (slot + 1) & tmask;
+            }
+        }
+        __syncthreads();
+        // ---- 4. finalise per id: first position (insertion order), min score, improvements in visit order ----
+        int my_raw = 0, my_uniq = 0;
+        for (int slot = tid; slot < tbl; slot += RQ_THREADS) {
+            const uint32_t head = table[slot];
+            if (head == RQ_EMPTY) continue;
+            uint32_t first = head, best = 255;
+            int n = 0;
+            for (uint32_t e = head; e != RQ_EMPTY; e = next_s[e]) { const uint32_t sc = vs_s[e >> 6]; first = min(first, e); best = min(best, sc); n++; }
+            int cnt = 1;
+            if (n > 1) {
+                cnt = 0;
+                for (uint32_t e = head; e != RQ_EMPTY; e = next_s[e]) {
+                    const uint32_t sc = vs_s[e >> 6];
+                    bool low = true;                                  // strictly below every earlier visit of this id (PIS:747)
+                    for (uint32_t e2 = head; e2 != RQ_EMPTY; e2 = next_s[e2]) if (e2 < e && vs_s[e2 >> 6] <= sc) low = false;
+                    cnt += low;
+                }
+            }
+            my_raw += cnt; my_uniq++;
+            table[slot] = (uint16_t)first;
+            next_s[first] = (uint16_t)best;                            // chain consumed: reuse the link as the id's best score
+            atomicAdd(&s_hist[best], 1);
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) { my_raw += __shfl_xor_sync(0xffffffffu, my_raw, o); my_uniq += __shfl_xor_sync(0xffffffffu, my_uniq, o); }
+        if (lane == 0) { atomicAdd(&s_raw, my_raw); atomicAdd(&s_uniq, my_uniq); }
+        __syncthreads();
+        const int n_unique = s_uniq;
+        const int want = min(p.B, n_unique);
+        // Java's final table size for this many entries (HashMap.resize doubles while size > 0.75*cap)
+        uint32_t capF = (uint32_t)p.cap0;
+        while ((double)n_unique > 0.75 * (double)capF && capF < (1u << 30)) capF <<= 1;
+        int cb = 0; while ((1u << cb) < capF) cb++;
+        const int total_bits = 8 + cb + 16;
+        auto make_key = [&](uint32_t rep) -> uint64_t {
+            const uint32_t bucket = java_hash_decimal(ids_s[rep]) & (capF - 1u);
+            return ((uint64_t)next_s[rep] << (cb + 16)) | ((uint64_t)bucket << 16) | (uint64_t)rep;
+        };
+        // ---- 5. exact radix select of the `want` smallest keys, 8 key bits per level.  Level 0 is the score histogram
+        //         from step 4; deeper levels only look at entries of the cut score class, so Java's string hash is
+        //         evaluated for that class (and later for the selected entries) only.
+        uint64_t prefix = 0;       // chosen digits so far (top `used` bits of the key)
+        int used = 0;              // number of key bits fixed
+        int cum = 0;               // entries strictly below the chosen prefix
+        uint32_t sstar = 0;
+        for (int level = 0;; level++) {
+            const int take = min(8, total_bits - used);
+            const int shift = total_bits - used - take;
+            if (level > 0) {
+                if (tid < 256) s_hist[tid] = 0;
+                __syncthreads();
+                for (int slot = tid; slot < tbl; slot += RQ_THREADS) {
+                    const uint32_t rep = table[slot];
+                    if (rep == RQ_EMPTY || next_s[rep] != sstar) continue;
+                    const uint64_t key = make_key(rep);
+                    if ((key >> (shift + take)) == prefix) atomicAdd(&s_hist[(int)((key >> shift) & ((1u << take) - 1u))], 1);
+                }
+                __syncthreads();
+            }
+            if (tid == 0) {
+                int c = cum, d = 0;
+                const int nd = 1 << take;
+                for (d = 0; d < nd; d++) { if (c + s_hist[d] >= want) break; c += s_hist[d]; }
+                if (d == nd) d = nd - 1;
+                s_digit = d; s_cum = c; s_bin = s_hist[d];
+            }
+            __syncthreads();
+            if (level == 0) sstar = (uint32_t)s_digit;
+            prefix = (prefix << take) | (uint64_t)s_digit;
+            used += take;
+            cum = s_cum;
+            const int bin = s_bin;
+            __syncthreads();
+            if (cum + bin == want || used >= total_bits) break;
+        }
+        const int sel_shift = total_bits - used;
+        // ---- 6. compact the selected entries (exactly `want`), pad, bitonic sort ----
+        for (int slot = tid; slot < tbl; slot += RQ_THREADS) {
+            const uint32_t rep = table[slot];
+            if (rep == RQ_EMPTY) continue;
+            const uint32_t sc = next_s[rep];
+            if (sc > sstar) continue;
+            const uint64_t key = make_key(rep);
+            if (sc < sstar || (key >> sel_shift) <= prefix) {
+                const int i = atomicAdd(&s_m, 1);
+                if (i < sort_n) { skey[i] = key; sid[i] = ids_s[rep]; }
+            }
+        }
+        __syncthreads();
+        const int m = min(s_m, sort_n);
+        for (int i = m + tid; i < sort_n; i += RQ_THREADS) { skey[i] = ~0ull; sid[i] = -1; }
+        __syncthreads();
+        // bitonic sort: element i lives in thread i % 1024 (registers), strides < 32 are exchanged with warp shuffles,
+        // larger strides through shared memory
+        if (sort_n <= RQ_THREADS) {
+            const int i = tid;
+            uint64_t a = i < sort_n ? skey[i] : ~0ull;
+            int32_t av = i < sort_n ? sid[i] : -1;
+            for (int k = 2; k <= sort_n; k <<= 1) {
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    const bool asc = (i & k) == 0;
+                    uint64_t b; int32_t bv;
+                    if (j >= 32) {
+                        __syncthreads();
+                        if (i < sort_n) { skey[i] = a; sid[i] = av; }
+                        __syncthreads();
+                        b = i < sort_n ? skey[i ^ j] : ~0ull; bv = i < sort_n ? sid[i ^ j] : -1;
+                    } else {
+                        b = __shfl_xor_sync(0xffffffffu, a, j); bv = __shfl_xor_sync(0xffffffffu, av, j);
+                    }
+                    const bool lower = (i & j) == 0;                // this thread keeps the smaller of the pair when ascending
+                    const bool take_b = (lower == asc) ? (b < a) : (b > a);
+                    if (take_b) { a = b; av = bv; }
+                }
+            }
+            __syncthreads();
+            if (i < sort_n) { skey[i] = a; sid[i] = av; }
+            __syncthreads();
+        } else {
+            for (int k = 2; k <= sort_n; k <<= 1) {
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    for (int i = tid; i < sort_n; i += RQ_THREADS) {
+                        const int ixj = i ^ j;
+                        if (ixj > i) {
+                            const uint64_t a = skey[i], b = skey[ixj];
+                            const bool asc = (i & k) == 0;
+                            if ((a > b) == asc) { skey[i] = b; skey[ixj] = a; const int32_t t = sid[i]; sid[i] = sid[ixj]; sid[ixj] = t; }
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+        }
+        int32_t *out_id = p.cand_ids + (size_t)q * p.B, *out_sc = p.cand_scores + (size_t)q * p.B;
+        for (int i = tid; i < want; i += RQ_THREADS) { out_id[i] = sid[i]; out_sc[i] = (int32_t)(skey[i] >> (cb + 16)); }
+        if (tid == 0) { p.n_cand[q] = want; p.unique[q] = n_unique; p.raw_seen[q] = s_raw; }
+    }
+}
+
+bool route_fast_eligible(const RoutingView &rv, int probes, int64_t hard_cap, int B, RouteFastExtra &x, size_t &smem) {
+    if (probes < 1) return false;
+    const int64_t n_raw = (int64_t)rv.TD * probes * kBlock;
+    if (n_raw > 65000) return false;
+    if (n_raw - kBlock >= hard_cap) return false;          // the cap could bind: needs the sequential path
+    int sort_n = 64; while (sort_n < B) sort_n <<= 1;
+    int tbl = 1024; while (tbl < n_raw + n_raw / 4) tbl <<= 1;
+    smem = route_fast_smem(rv.TD, probes, (int)n_raw, tbl, sort_n);
+    if (smem > 227 * 1024 - 2048) return false;
+    x.n_raw = (int)n_raw; x.tbl = tbl; x.sort_n = sort_n;
+    return true;
+}
+
+int launch_route_fast(cudaStream_t s, const RoutingView &rv, const RouteParams &p, RouteFastExtra x, size_t smem, int sm_count,
+                      int32_t *vis_part, uint8_t *vis_score, uint8_t *vis_n) {
+    if (p.Q <= 0) return 0;
+    static size_t configured = 0;
+    if (smem > configured) {
+        if (cudaFuncSetAttribute(route_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+        configured = smem;
+    }
+    const int64_t nthreads = p.Q * rv.TD;
+    route_probe_kernel<<<(unsigned)((nthreads + 127) / 128), 128, 0, s>>>(rv, p.Q, p.codes, p.probes, vis_part, vis_score, vis_n);
+    x.vis_part = vis_part; x.vis_score = vis_score; x.vis_n = vis_n;
+    int grid = (int)std::min<int64_t>(p.Q, sm_count);
+    route_fast_kernel<<<grid, RQ_THREADS, smem, s>>>(rv, p, x);
+    return cudaGetLastError() == cudaSuccess ? 2 : -1;
 }
 
 }  // namespace fsp

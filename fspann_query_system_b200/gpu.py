@@ -158,6 +158,12 @@ class GpuContext:
         n = self.lib.fspann_last_stage_ms(self.ctx, out)
         return dict(tokengen=out[0], route=out[1], group=out[2], decrypt=out[3], topk=out[4], launches=int(n))
 
+    def set_option(self, name: str, value: int):
+        self._ck(self.lib.fspann_set_option(self.ctx, C.c_char_p(name.encode()), C.c_int64(value)))
+
+    def get_info(self, name: str) -> int:
+        return int(self.lib.fspann_get_info(self.ctx, C.c_char_p(name.encode())))
+
     def stream(self) -> int:
         return int(self.lib.fspann_ctx_stream(self.ctx) or 0)
 

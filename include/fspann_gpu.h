@@ -66,6 +66,12 @@ int fspann_ctx_sync(fspann_ctx *ctx);
 /* number of kernels this library has launched on the context since creation (bench.py's gpu_launches). */
 int64_t fspann_ctx_launch_count(const fspann_ctx *ctx);
 
+/* Tuning / test switches: "route_general" = 1 forces the general Route kernel (sequential groups, exact HARD_CAP
+ * semantics) even where the shared-memory fast path applies.  fspann_get_info: "last_route_path" (1 fast, 2 general),
+ * "sm_count". */
+int fspann_set_option(fspann_ctx *ctx, const char *name, int64_t value);
+int64_t fspann_get_info(fspann_ctx *ctx, const char *name);
+
 /* ---- Setup state crossing the boundary ----------------------------------------------------------------- */
 /* Routing state I = GFunctions + frozen partitions: GFunctionRegistry contents (GFR:63-147; Coding.GFunction
  * alpha/r/omega, Coding:52-97) and every DivisionState.partitions after finalizeForSearch (PIS:789-845, GP:13-32).

@@ -36,13 +36,23 @@ def test_tokengen_codes_bit_exact(wg):
     assert np.array_equal(ctx.tokengen_batch(w.base[:777]), w.codes[:777])
 
 
-@pytest.mark.parametrize("probes,hard_cap,B", [(5, 20000, 64), (5, 20000, 100000), (3, 700, 256), (10, 2000, 1500), (1, 50, 40), (5, 1 << 20, 300)])
-def test_route_candidates_ordered_bit_exact(wg, probes, hard_cap, B):
+@pytest.mark.parametrize("general", [0, 1], ids=["fast-path", "general-path"])
+@pytest.mark.parametrize("probes,hard_cap,B", [(5, 20000, 64), (5, 20000, 100000), (3, 700, 256), (10, 2000, 1500), (1, 50, 40), (5, 1 << 20, 300),
+                                               (5, 24000, 1024), (2, 20000, 1)])
+def test_route_candidates_ordered_bit_exact(wg, probes, hard_cap, B, general):
+    """Both Route kernels: the shared-memory fast path (when the HARD_CAP cannot bind and the query fits in smem) and the
+    general path (sequential groups, exact cap semantics) must give the reference's ordered candidate list."""
     w, ctx = wg
     codes = O.tokengen_batch(w.queries, w.g)
     hard_cap = max(hard_cap, min(B, 5000)) if hard_cap < B and B < 100000 else hard_cap
     B = min(B, 8192)
-    out = ctx.route_batch(codes, probes, hard_cap, B)
+    ctx.set_option("route_general", general)
+    try:
+        out = ctx.route_batch(codes, probes, hard_cap, B)
+    finally:
+        ctx.set_option("route_general", 0)
+    if general:
+        assert ctx.get_info("last_route_path") == 2
     for q in range(codes.shape[0]):
         ids, sc, raw, mc = O.route(w.ix, codes[q], probes, hard_cap)
         n = min(B, len(ids))
