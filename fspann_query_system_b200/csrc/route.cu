@@ -384,9 +384,10 @@ __global__ void route_probe_kernel(RoutingView rv, int64_t Q, const uint64_t *__
     vis_n[idx] = (uint8_t)nv;
 }
 
-__device__ __forceinline__ uint32_t cas16(uint16_t *addr, uint32_t expect, uint32_t val) {
-    uint32_t *w = reinterpret_cast<uint32_t *>(reinterpret_cast<uintptr_t>(addr) & ~(uintptr_t)3);
-    const int shift = (reinterpret_cast<uintptr_t>(addr) & 2) ? 16 : 0;
+// 16-bit compare-and-swap on a shared-memory table of uint16 (tw = the table viewed as 32-bit words).
+__device__ __forceinline__ uint32_t cas16(uint32_t *tw, uint32_t slot, uint32_t expect, uint32_t val) {
+    uint32_t *w = tw + (slot >> 1);
+    const int shift = (slot & 1u) ? 16 : 0;
     uint32_t old = *reinterpret_cast<volatile uint32_t *>(w);
     for (;;) {
         const uint32_t cur = (old >> shift) & 0xffffu;
@@ -400,28 +401,62 @@ __device__ __forceinline__ uint32_t cas16(uint16_t *addr, uint32_t expect, uint3
 
 size_t route_fast_smem(int TD, int probes, int n_raw, int tbl, int sort_n) {
     size_t s = 0;
-    s += sizeof(uint64_t) * sort_n;            // skey
-    s += sizeof(int32_t) * n_raw;              // ids_s
-    s += sizeof(int32_t) * sort_n;             // sid
-    s += sizeof(int32_t) * TD * probes;        // vp_s
-    s += sizeof(uint16_t) * tbl;               // table
-    s += sizeof(uint16_t) * n_raw;             // next_s
-    s += ((size_t)TD * probes + 15) / 16 * 16; // vs_s
+    s += sizeof(uint64_t) * sort_n;                 // skey
+    s += sizeof(int64_t) * TD * probes;             // vbase_s
+    s += sizeof(int32_t) * n_raw;                   // ids_s
+    s += sizeof(int32_t) * sort_n;                  // sid
+    s += sizeof(uint16_t) * tbl;                    // table (later: dense list of the cut score class)
+    s += sizeof(uint16_t) * n_raw;                  // next_s (later: low 16 bits of the Java hash)
+    s += (size_t)n_raw;                             // best_s
+    s += 2 * (((size_t)TD * probes + 15) / 16 * 16); // vs_s, vlen_s
     return s + 64;
+}
+
+// Finds the first bin d (of nd <= 256) with base + sum(hist[0..d]) >= want; warp 0 only.  Writes s_out = {d, cum_before_d, hist[d]}.
+__device__ __forceinline__ void warp_pick_digit(const int32_t *hist, int nd, int base, int want, int lane, int32_t *s_out) {
+    int loc[8], sum = 0;
+#pragma unroll
+    for (int u = 0; u < 8; u++) { const int d = lane * 8 + u; loc[u] = d < nd ? hist[d] : 0; sum += loc[u]; }
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+    const int excl = base + incl - sum;
+    const unsigned hit = __ballot_sync(0xffffffffu, excl + sum >= want);
+    const int owner = hit ? __ffs(hit) - 1 : 31;
+    if (lane == owner) {
+        int c = excl, d = lane * 8, u = 0;
+        for (u = 0; u < 8; u++) { if (c + loc[u] >= want) break; c += loc[u]; }
+        if (u == 8) { u = 7; c -= loc[7]; }
+        d += u;
+        if (d >= nd) { d = nd - 1; }
+        s_out[0] = d; s_out[1] = c; s_out[2] = hist[d];
+    }
+}
+
+// warp-aggregated histogram increment: one shared atomic per distinct bin per warp
+__device__ __forceinline__ void hist_add(int32_t *hist, bool active, int bin, int lane) {
+    const unsigned act = __ballot_sync(0xffffffffu, active);
+    if (!active) return;
+    const unsigned peers = __match_any_sync(act, bin);
+    if (lane == __ffs(peers) - 1) atomicAdd(&hist[bin], __popc(peers));
 }
 
 __global__ void __launch_bounds__(RQ_THREADS, 1) route_fast_kernel(RoutingView rv, RouteParams p, RouteFastExtra x) {
     extern __shared__ __align__(16) unsigned char rq_smem[];
-    const int TD = rv.TD, probes = p.probes, n_raw = x.n_raw, tbl = x.tbl, sort_n = x.sort_n;
+    const int TD = rv.TD, probes = p.probes, n_raw = x.n_raw, tbl = x.tbl, sort_n = x.sort_n, nvis = TD * probes;
     uint64_t *skey = reinterpret_cast<uint64_t *>(rq_smem);
-    int32_t *ids_s = reinterpret_cast<int32_t *>(skey + sort_n);
+    int64_t *vbase_s = reinterpret_cast<int64_t *>(skey + sort_n);          // per visit: offset of its partition row in rv.ids, or -1
+    int32_t *ids_s = reinterpret_cast<int32_t *>(vbase_s + nvis);
     int32_t *sid = ids_s + n_raw;
-    int32_t *vp_s = sid + sort_n;
-    uint16_t *table = reinterpret_cast<uint16_t *>(vp_s + TD * probes);
+    uint32_t *table_w = reinterpret_cast<uint32_t *>(sid + sort_n);
+    uint16_t *table = reinterpret_cast<uint16_t *>(table_w);
     uint16_t *next_s = table + tbl;
-    uint8_t *vs_s = reinterpret_cast<uint8_t *>(next_s + n_raw);
+    uint8_t *best_s = reinterpret_cast<uint8_t *>(next_s + n_raw);           // rep positions: the id's best score; others: 255
+    uint8_t *vs_s = best_s + n_raw;
+    uint8_t *vlen_s = vs_s + (nvis + 15) / 16 * 16;                           // valid ids in the visited partition row
+    uint16_t *cls = table;                                                   // after step 4 the table is dead: dense class list
     __shared__ int32_t s_hist[256];
-    __shared__ int32_t s_raw, s_uniq, s_m, s_digit, s_cum, s_bin;
+    __shared__ int32_t s_raw, s_uniq, s_m, s_ncls, s_pick[3];
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int64_t n_ids = rv.n_ids;
@@ -431,79 +466,92 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) route_fast_kernel(RoutingView r
     for (int64_t q = blockIdx.x; q < p.Q; q += gridDim.x) {
         __syncthreads();
         // ---- 1. stage visits, reset table ----
-        for (int v = tid; v < TD * probes; v += RQ_THREADS) {
+        for (int v = tid; v < nvis; v += RQ_THREADS) {
             const int g = v / probes, j = v - g * probes;
             const int64_t vi = (q * TD + g) * probes + j;
             const bool valid = j < (int)x.vis_n[q * TD + g];
-            vp_s[v] = valid ? x.vis_part[vi] : -1;
+            const int64_t row = valid ? (int64_t)x.vis_part[vi] * kBlock : 0;
+            vbase_s[v] = (int64_t)g * n_ids + row;
+            vlen_s[v] = valid ? (uint8_t)min((int64_t)kBlock, n_ids - row) : 0;
             vs_s[v] = valid ? x.vis_score[vi] : 255;
         }
-        for (int i = tid; i < tbl / 2; i += RQ_THREADS) reinterpret_cast<uint32_t *>(table)[i] = 0xffffffffu;
+        for (int i = tid; i < tbl / 2; i += RQ_THREADS) table_w[i] = 0xffffffffu;
         if (tid < 256) s_hist[tid] = 0;
-        if (tid == 0) { s_raw = 0; s_uniq = 0; s_m = 0; }
+        if (tid == 0) { s_raw = 0; s_uniq = 0; s_m = 0; s_ncls = 0; }
         __syncthreads();
         // ---- 2. gather ids (each partition row is 256 contiguous bytes) ----
         for (int e = tid; e < n_raw; e += RQ_THREADS) {
             const int v = e >> 6, pos = e & 63;
-            const int32_t part = vp_s[v];
             int32_t id = -1;
-            if (part >= 0) {
-                const int64_t slot = (int64_t)part * kBlock + pos;
-                if (slot < n_ids) {
-                    id = __ldg(rv.ids + (size_t)(v / probes) * n_ids + slot);
-                    if (rv.deleted && id >= 0 && id < rv.n_deleted && rv.deleted[id]) id = -1;     // PIS:739
-                }
+            if (pos < (int)vlen_s[v]) {
+                id = __ldg(rv.ids + vbase_s[v] + pos);
+                if (rv.deleted && id >= 0 && id < rv.n_deleted && rv.deleted[id]) id = -1;     // PIS:739
             }
             ids_s[e] = id;
+            next_s[e] = (uint16_t)RQ_EMPTY;
+            best_s[e] = 255;
         }
         __syncthreads();
-        // ---- 3. insert: table[slot] = head of the chain of all positions holding one id ----
+        // ---- 3. insert (open addressing, double hashing): table[slot] = newest position holding that id; each position links
+        //         to the previous newest one; the FIRST arrival's link is the terminator 0x8000|slot, so later phases find the
+        //         slot of any position by following its (short) chain instead of probing again ----
         for (int e = tid; e < n_raw; e += RQ_THREADS) {
             const int32_t id = ids_s[e];
             if (id < 0) continue;
-            next_s[e] = (uint16_t)RQ_EMPTY;
-            uint32_t slot = ((uint32_t)id * 0x9E3779B1u) >> tshift;    // any hash works here; Java's is only needed for the order
+            const uint32_t h = (uint32_t)id * 0x9E3779B1u;
+            uint32_t slot = h >> tshift;
+            const uint32_t step = ((h >> 7) | 1u) & tmask;             // odd => visits every slot of the power-of-two table
             for (;;) {
                 uint32_t cur = *reinterpret_cast<volatile uint16_t *>(&table[slot]);
                 if (cur == RQ_EMPTY) {
-                    cur = cas16(&table[slot], RQ_EMPTY, (uint32_t)e);
-                    if (cur == RQ_EMPTY) break;                       // claimed an empty slot
+                    next_s[e] = (uint16_t)(0x8000u | slot);
+                    cur = cas16(table_w, slot, RQ_EMPTY, (uint32_t)e);
+                    if (cur == RQ_EMPTY) break;                       // claimed an empty slot: first arrival
                 }
-                if (ids_s[cur] == id) {                               // same id: push this occurrence onto its chain
+                if (ids_s[cur] == id) {                               // same id: become the newest element of its chain
                     for (;;) {
                         next_s[e] = (uint16_t)cur;
-                        const uint32_t prev = cas16(&table[slot], cur, (uint32_t)e);
+                        const uint32_t prev = cas16(table_w, slot, cur, (uint32_t)e);
                         if (prev == cur) break;
                         cur = prev;                                   // still the same id (slots never change owner)
                     }
                     break;
                 }
-                slot = (slot + 1) & tmask;
+                slot = (slot + step) & tmask;
             }
         }
         __syncthreads();
-        // ---- 4. finalise per id: first position (insertion order), min score, improvements in visit order ----
+        // ---- 4. finalise, one thread per POSITION (dense): every occurrence walks its id's (short) chain once and decides
+        //         (a) whether it strictly improved on all earlier visits of the id (PIS:747 -> lastRawVisited) and
+        //         (b) whether it is the first occurrence (= HashMap insertion order); the first one records the min score.
         int my_raw = 0, my_uniq = 0;
-        for (int slot = tid; slot < tbl; slot += RQ_THREADS) {
-            const uint32_t head = table[slot];
-            if (head == RQ_EMPTY) continue;
-            uint32_t first = head, best = 255;
-            int n = 0;
-            for (uint32_t e = head; e != RQ_EMPTY; e = next_s[e]) { const uint32_t sc = vs_s[e >> 6]; first = min(first, e); best = min(best, sc); n++; }
-            int cnt = 1;
-            if (n > 1) {
-                cnt = 0;
-                for (uint32_t e = head; e != RQ_EMPTY; e = next_s[e]) {
-                    const uint32_t sc = vs_s[e >> 6];
-                    bool low = true;                                  // strictly below every earlier visit of this id (PIS:747)
-                    for (uint32_t e2 = head; e2 != RQ_EMPTY; e2 = next_s[e2]) if (e2 < e && vs_s[e2 >> 6] <= sc) low = false;
-                    cnt += low;
+        for (int e0 = 0; e0 < n_raw; e0 += RQ_THREADS) {
+            const int e = e0 + tid;
+            const int32_t id = e < n_raw ? ids_s[e] : -1;
+            bool is_rep = false; uint32_t best = 255;
+            if (id >= 0) {
+                const uint32_t sc = vs_s[e >> 6];
+                uint32_t lk = next_s[e];
+                while (!(lk & 0x8000u)) lk = next_s[lk];               // terminator carries the slot
+                const uint32_t head = table[lk & 0x7fffu];
+                if (head == (uint32_t)e && (next_s[e] & 0x8000u)) {    // the only occurrence of this id (the common case)
+                    my_raw++; is_rep = true; best = sc;
+                } else {
+                    uint32_t first = head; bool low = true;
+                    for (uint32_t y = head;;) {
+                        const uint32_t sy = vs_s[y >> 6];
+                        first = min(first, y); best = min(best, sy);
+                        if (y < (uint32_t)e && sy <= sc) low = false;
+                        const uint32_t ny = next_s[y];
+                        if (ny & 0x8000u) break;
+                        y = ny;
+                    }
+                    my_raw += low;
+                    is_rep = first == (uint32_t)e;
                 }
+                if (is_rep) { my_uniq++; best_s[e] = (uint8_t)best; }
             }
-            my_raw += cnt; my_uniq++;
-            table[slot] = (uint16_t)first;
-            next_s[first] = (uint16_t)best;                            // chain consumed: reuse the link as the id's best score
-            atomicAdd(&s_hist[best], 1);
+            hist_add(s_hist, is_rep, (int)best, lane);
         }
 #pragma unroll
         for (int o = 16; o; o >>= 1) { my_raw += __shfl_xor_sync(0xffffffffu, my_raw, o); my_uniq += __shfl_xor_sync(0xffffffffu, my_uniq, o); }
@@ -511,71 +559,100 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) route_fast_kernel(RoutingView r
         __syncthreads();
         const int n_unique = s_uniq;
         const int want = min(p.B, n_unique);
-        // Java's final table size for this many entries (HashMap.resize doubles while size > 0.75*cap)
+        // Java's final table size for this many entries (HashMap.resize doubles while size > 0.75*cap); <= 65536 here
         uint32_t capF = (uint32_t)p.cap0;
         while ((double)n_unique > 0.75 * (double)capF && capF < (1u << 30)) capF <<= 1;
         int cb = 0; while ((1u << cb) < capF) cb++;
-        const int total_bits = 8 + cb + 16;
-        auto make_key = [&](uint32_t rep) -> uint64_t {
-            const uint32_t bucket = java_hash_decimal(ids_s[rep]) & (capF - 1u);
-            return ((uint64_t)next_s[rep] << (cb + 16)) | ((uint64_t)bucket << 16) | (uint64_t)rep;
-        };
-        // ---- 5. exact radix select of the `want` smallest keys, 8 key bits per level.  Level 0 is the score histogram
-        //         from step 4; deeper levels only look at entries of the cut score class, so Java's string hash is
-        //         evaluated for that class (and later for the selected entries) only.
-        uint64_t prefix = 0;       // chosen digits so far (top `used` bits of the key)
-        int used = 0;              // number of key bits fixed
-        int cum = 0;               // entries strictly below the chosen prefix
-        uint32_t sstar = 0;
-        for (int level = 0;; level++) {
-            const int take = min(8, total_bits - used);
-            const int shift = total_bits - used - take;
-            if (level > 0) {
+        // ---- 5. level 0 of the radix select = score histogram from step 4 ----
+        if (tid < 32) warp_pick_digit(s_hist, 256, 0, want, lane, s_pick);
+        __syncthreads();
+        const uint32_t sstar = (uint32_t)s_pick[0];    // cut score class
+        int cum = s_pick[1];                           // entries with score < sstar (all selected)
+        const int cls_n_expected = s_pick[2];
+        __syncthreads();
+        // ---- 6. dense list of the cut class; Java hash only for its members; exact select inside the class on
+        //         key2 = (Java bucket << 16) | first position, 8 bits per level ----
+        const int bits2 = cb + 16;
+        uint32_t prefix = 0; int used = 0;
+        const bool need_levels = cum + cls_n_expected != want;
+        if (need_levels) {
+            for (int e0 = 0; e0 < n_raw; e0 += RQ_THREADS) {
+                const int e = e0 + tid;
+                const bool in = e < n_raw && best_s[e] == sstar && sstar != 255;
+                const unsigned bal = __ballot_sync(0xffffffffu, in);
+                int base = 0;
+                if (lane == 0 && bal) base = atomicAdd(&s_ncls, __popc(bal));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (in) cls[base + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)e;
+            }
+            __syncthreads();
+            const int ncls = s_ncls;
+            for (int i = tid; i < ncls; i += RQ_THREADS) { const uint32_t e = cls[i]; next_s[e] = (uint16_t)(java_hash_decimal(ids_s[e]) & 0xffffu); }
+            __syncthreads();
+            for (;;) {
+                const int take = min(8, bits2 - used);
+                const int shift = bits2 - used - take;
                 if (tid < 256) s_hist[tid] = 0;
                 __syncthreads();
-                for (int slot = tid; slot < tbl; slot += RQ_THREADS) {
-                    const uint32_t rep = table[slot];
-                    if (rep == RQ_EMPTY || next_s[rep] != sstar) continue;
-                    const uint64_t key = make_key(rep);
-                    if ((key >> (shift + take)) == prefix) atomicAdd(&s_hist[(int)((key >> shift) & ((1u << take) - 1u))], 1);
+                for (int i0 = 0; i0 < ncls; i0 += RQ_THREADS) {
+                    const int i = i0 + tid;
+                    bool in = false; int bin = 0;
+                    if (i < ncls) {
+                        const uint32_t e = cls[i];
+                        const uint32_t key2 = (((uint32_t)next_s[e] & (capF - 1u)) << 16) | e;
+                        in = used == 0 || (key2 >> (shift + take)) == prefix;
+                        bin = (int)((key2 >> shift) & ((1u << take) - 1u));
+                    }
+                    hist_add(s_hist, in, bin, lane);
                 }
                 __syncthreads();
+                if (tid < 32) warp_pick_digit(s_hist, 1 << take, cum, want, lane, s_pick);
+                __syncthreads();
+                prefix = (prefix << take) | (uint32_t)s_pick[0];
+                used += take;
+                cum = s_pick[1];
+                const int bin = s_pick[2];
+                __syncthreads();
+                if (cum + bin == want || used >= bits2) break;
             }
-            if (tid == 0) {
-                int c = cum, d = 0;
-                const int nd = 1 << take;
-                for (d = 0; d < nd; d++) { if (c + s_hist[d] >= want) break; c += s_hist[d]; }
-                if (d == nd) d = nd - 1;
-                s_digit = d; s_cum = c; s_bin = s_hist[d];
-            }
-            __syncthreads();
-            if (level == 0) sstar = (uint32_t)s_digit;
-            prefix = (prefix << take) | (uint64_t)s_digit;
-            used += take;
-            cum = s_cum;
-            const int bin = s_bin;
-            __syncthreads();
-            if (cum + bin == want || used >= total_bits) break;
         }
-        const int sel_shift = total_bits - used;
-        // ---- 6. compact the selected entries (exactly `want`), pad, bitonic sort ----
-        for (int slot = tid; slot < tbl; slot += RQ_THREADS) {
-            const uint32_t rep = table[slot];
-            if (rep == RQ_EMPTY) continue;
-            const uint32_t sc = next_s[rep];
-            if (sc > sstar) continue;
-            const uint64_t key = make_key(rep);
-            if (sc < sstar || (key >> sel_shift) <= prefix) {
-                const int i = atomicAdd(&s_m, 1);
-                if (i < sort_n) { skey[i] = key; sid[i] = ids_s[rep]; }
+        const int sel_shift = bits2 - used;
+        // ---- 7. compact the selected positions (exactly `want`): everything below the cut class, plus the chosen part of it ----
+        for (int e0 = 0; e0 < n_raw; e0 += RQ_THREADS) {
+            const int e = e0 + tid;
+            bool sel = false;
+            if (e < n_raw) {
+                const uint32_t sc = best_s[e];
+                if (sc < sstar) sel = true;
+                else if (sc == sstar && sc != 255) {
+                    if (!need_levels) sel = true;
+                    else { const uint32_t key2 = (((uint32_t)next_s[e] & (capF - 1u)) << 16) | (uint32_t)e; sel = (key2 >> sel_shift) <= prefix; }
+                }
             }
+            const unsigned bal = __ballot_sync(0xffffffffu, sel);
+            int base = 0;
+            if (lane == 0 && bal) base = atomicAdd(&s_m, __popc(bal));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (sel) { const int i = base + __popc(bal & ((1u << lane) - 1u)); if (i < sort_n) sid[i] = e; }
         }
         __syncthreads();
         const int m = min(s_m, sort_n);
-        for (int i = m + tid; i < sort_n; i += RQ_THREADS) { skey[i] = ~0ull; sid[i] = -1; }
+        // one selected entry per thread: full key (score | Java bucket | first position), Java hash evaluated densely here
+        for (int i = tid; i < sort_n; i += RQ_THREADS) {
+            uint64_t key = ~0ull; int32_t idv = -1;
+            if (i < m) {
+                const int e = sid[i];
+                idv = ids_s[e];
+                const uint32_t bucket = java_hash_decimal(idv) & (capF - 1u);
+                key = ((uint64_t)best_s[e] << (cb + 16)) | ((uint64_t)bucket << 16) | (uint64_t)e;
+            }
+            skey[i] = key;
+        }
         __syncthreads();
-        // bitonic sort: element i lives in thread i % 1024 (registers), strides < 32 are exchanged with warp shuffles,
-        // larger strides through shared memory
+        for (int i = tid; i < sort_n; i += RQ_THREADS) sid[i] = i < m ? ids_s[sid[i]] : -1;
+        __syncthreads();
+        // ---- 8. bitonic sort: element i lives in thread i (registers), strides < 32 are exchanged with warp shuffles,
+        //         larger strides through shared memory ----
         if (sort_n <= RQ_THREADS) {
             const int i = tid;
             uint64_t a = i < sort_n ? skey[i] : ~0ull;
@@ -624,10 +701,12 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) route_fast_kernel(RoutingView r
 bool route_fast_eligible(const RoutingView &rv, int probes, int64_t hard_cap, int B, RouteFastExtra &x, size_t &smem) {
     if (probes < 1) return false;
     const int64_t n_raw = (int64_t)rv.TD * probes * kBlock;
-    if (n_raw > 65000) return false;
+    if (n_raw > 32000) return false;                         // positions and slots carry a 1-bit tag in 16 bits
     if (n_raw - kBlock >= hard_cap) return false;          // the cap could bind: needs the sequential path
+    if (rv.m * rv.lambda > 254) return false;               // score 255 marks non-representative positions
     int sort_n = 64; while (sort_n < B) sort_n <<= 1;
     int tbl = 1024; while (tbl < n_raw + n_raw / 4) tbl <<= 1;
+    if (tbl > 32768) return false;
     smem = route_fast_smem(rv.TD, probes, (int)n_raw, tbl, sort_n);
     if (smem > 227 * 1024 - 2048) return false;
     x.n_raw = (int)n_raw; x.tbl = tbl; x.sort_n = sort_n;
