@@ -267,7 +267,7 @@ def main():
     clocks = sampler.stop()
 
     # ---- roofline of the dominant kernel (refine decrypt+distance), measured live with CUDA events on the launching stream
-    stage = dict(tokengen=0.0, route=0.0, group=0.0, decrypt=0.0, topk=0.0)
+    stage = dict(tokengen=0.0, route=0.0, group=0.0, verify=0.0, decrypt=0.0, topk=0.0)
     pairs = 0
     for i in range(K):
         step_dev(Wm + i)

@@ -37,7 +37,7 @@ struct fspann_ctx {
     // store
     bool store_ready = false;
     StoreView sv{};
-    DevBuf d_rec, d_keyring, d_hpow, d_te0, d_touched;
+    DevBuf d_rec, d_keyring, d_hpow, d_shoup, d_te0, d_touched;
     std::map<int32_t, std::vector<uint8_t>> keys;  // live versions -> raw key
 
     // scratch (grow only)
@@ -45,13 +45,14 @@ struct fspann_ctx {
     int opt_route_general = 0;   // force the general (sequential, cap-exact) Route kernel
     int last_route_path = 0;     // 1 = shared-memory fast path, 2 = general path
     DevBuf s_queries, s_codes, s_cand_ids, s_cand_sc, s_ncand, s_raw, s_uniq_cnt, s_route_scratch, s_overflow;
+    DevBuf s_rec_verdict;
     DevBuf s_cnt, s_flag, s_fill, s_uniq, s_pairs, s_bsums, s_totals, s_dist, s_verdict;
     DevBuf s_topk_ids, s_topk_dist, s_nret, s_ndec, s_counters;
     DevBuf s_stage_a, s_stage_b, s_stage_c;  // upload staging
     DevBuf r_rows, r_queries, r_codes, r_topk_ids, r_topk_dist, r_nret, r_counters;  // retry subset
     DevBuf t_cand_ids, t_cand_sc, t_ncand, t_raw, t_uniq_cnt, t_ndec;               // retry subset route outputs
 
-    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool ev_valid = false;
     int64_t last_call_launches = 0;
 };
@@ -118,6 +119,7 @@ int rebuild_keys(fspann_ctx *ctx) {
     const int c = (8 * dim + 15) / 16;
     const int npow = c + 4;
     std::vector<u128> hp((size_t)kMaxKeys * (npow + 1));
+    std::vector<uint32_t> shoup((size_t)std::max<size_t>(ctx->keys.size(), 1) * 4096 * 4);
     int n = 0;
     for (auto &kv : ctx->keys) {
         ring.version[n] = kv.first;
@@ -129,17 +131,21 @@ int rebuild_keys(fspann_ctx *ctx) {
         row[0] = u128{0, 0};
         row[1] = H;
         for (int p = 2; p <= npow; p++) row[p] = gf128_mul_ref(row[p - 1], H);
+        ghash_make_shoup8(H, shoup.data() + (size_t)n * 4096 * 4);
         n++;
     }
     ring.n = n;
     ENSURE(ctx->d_keyring, sizeof ring);
     ENSURE(ctx->d_hpow, sizeof(u128) * hp.size());
+    ENSURE(ctx->d_shoup, sizeof(uint32_t) * shoup.size());
+    CK(cudaMemcpyAsync(ctx->d_shoup.p, shoup.data(), sizeof(uint32_t) * shoup.size(), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_keyring.p, &ring, sizeof ring, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_hpow.p, hp.data(), sizeof(u128) * hp.size(), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));   // host vectors go out of scope
     ctx->sv.keys = (const DevKeyRing *)ctx->d_keyring.p;
     ctx->sv.hpow = (const u128 *)ctx->d_hpow.p;
     ctx->sv.npow = npow;
+    ctx->sv.shoup = (const uint4 *)ctx->d_shoup.p;
     return 0;
 }
 
@@ -212,18 +218,24 @@ int do_refine(fspann_ctx *ctx, int64_t Q, const double *d_queries, const int32_t
     ENSURE(ctx->s_totals, sizeof(int32_t) * 4);
     ENSURE(ctx->s_dist, sizeof(double) * (size_t)(total + 1));
     ENSURE(ctx->s_verdict, (size_t)(total + 1));
+    ENSURE(ctx->s_rec_verdict, (size_t)std::min<int64_t>(n1, total + 1) + 64);
     RefineParams p{};
     p.Q = Q; p.queries = d_queries; p.cand_ids = d_cand_ids; p.n_cand = d_ncand; p.stride = stride; p.k = k;
     p.cnt = (int32_t *)ctx->s_cnt.p; p.fill = (int32_t *)ctx->s_fill.p; p.uniq = (int32_t *)ctx->s_uniq.p;
     p.pairs = (uint32_t *)ctx->s_pairs.p; p.block_sums = (int32_t *)ctx->s_bsums.p; p.totals = (int32_t *)ctx->s_totals.p;
     p.dist = (double *)ctx->s_dist.p; p.verdict = (uint8_t *)ctx->s_verdict.p; p.touched = (uint32_t *)ctx->d_touched.p;
+    p.rec_verdict = (uint8_t *)ctx->s_rec_verdict.p;
     p.topk_ids = d_topk_ids; p.topk_dist = d_topk_dist; p.n_ret = d_nret; p.n_dec = d_ndec;
+    // unknown / retired key version is the default verdict (KRS:82-88); the verify kernel overwrites it per live version
+    CK(cudaMemsetAsync(p.rec_verdict, FSPANN_V_NO_KEY, (size_t)std::min<int64_t>(n1, total + 1), ctx->stream));
     LAUNCHED(launch_refine_group(ctx->stream, sv, p));
     if (stage_events) { int rc = record_ev(ctx, 3); if (rc) return rc; }
-    LAUNCHED(launch_refine_decrypt(ctx->stream, sv, p, ctx->sm_count));
+    LAUNCHED(launch_refine_verify(ctx->stream, sv, p, ctx->sm_count));
     if (stage_events) { int rc = record_ev(ctx, 4); if (rc) return rc; }
-    LAUNCHED(launch_refine_topk(ctx->stream, p));
+    LAUNCHED(launch_refine_decrypt(ctx->stream, sv, p, ctx->sm_count));
     if (stage_events) { int rc = record_ev(ctx, 5); if (rc) return rc; }
+    LAUNCHED(launch_refine_topk(ctx->stream, p));
+    if (stage_events) { int rc = record_ev(ctx, 6); if (rc) return rc; }
     return 0;
 }
 
@@ -248,7 +260,7 @@ int fspann_ctx_create(int device, fspann_ctx **out) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return FSPANN_E_CUDA; }
-    for (int i = 0; i < 6; i++) cudaEventCreate(&ctx->ev[i]);
+    for (int i = 0; i < 7; i++) cudaEventCreate(&ctx->ev[i]);
     uint32_t te0[256];
     aes_make_te0(te0);
     if (ensure(ctx, ctx->d_te0, sizeof te0) || cudaMemcpy(ctx->d_te0.p, te0, sizeof te0, cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -266,14 +278,14 @@ void fspann_ctx_destroy(fspann_ctx *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->d_alpha, &ctx->d_r, &ctx->d_omega, &ctx->d_keys, &ctx->d_rep, &ctx->d_ids, &ctx->d_deleted, &ctx->d_rec,
-                      &ctx->d_keyring, &ctx->d_hpow, &ctx->d_te0, &ctx->d_touched, &ctx->s_queries, &ctx->s_codes, &ctx->s_cand_ids,
+                      &ctx->d_keyring, &ctx->d_hpow, &ctx->d_shoup, &ctx->s_rec_verdict, &ctx->d_te0, &ctx->d_touched, &ctx->s_queries, &ctx->s_codes, &ctx->s_cand_ids,
                       &ctx->s_cand_sc, &ctx->s_ncand, &ctx->s_raw, &ctx->s_uniq_cnt, &ctx->s_route_scratch, &ctx->s_overflow, &ctx->s_cnt,
                       &ctx->s_flag, &ctx->s_fill, &ctx->s_uniq, &ctx->s_pairs, &ctx->s_bsums, &ctx->s_totals, &ctx->s_dist, &ctx->s_verdict,
                       &ctx->s_topk_ids, &ctx->s_topk_dist, &ctx->s_nret, &ctx->s_ndec, &ctx->s_counters, &ctx->s_stage_a, &ctx->s_stage_b,
                       &ctx->s_stage_c, &ctx->s_vis_part, &ctx->s_vis_score, &ctx->s_vis_n, &ctx->r_rows, &ctx->r_queries, &ctx->r_codes, &ctx->r_topk_ids, &ctx->r_topk_dist, &ctx->r_nret,
                       &ctx->r_counters, &ctx->t_cand_ids, &ctx->t_cand_sc, &ctx->t_ncand, &ctx->t_raw, &ctx->t_uniq_cnt, &ctx->t_ndec};
     for (DevBuf *b : bufs) release(*b);
-    for (int i = 0; i < 6; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 7; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -646,12 +658,12 @@ int fspann_touched_fetch(fspann_ctx *ctx, uint32_t *bitmap_out, int64_t n_words,
     return FSPANN_OK;
 }
 
-int64_t fspann_last_stage_ms(fspann_ctx *ctx, float out[5]) {
+int64_t fspann_last_stage_ms(fspann_ctx *ctx, float out[6]) {
     if (!ctx || !out) return -1;
-    for (int i = 0; i < 5; i++) out[i] = 0.f;
+    for (int i = 0; i < 6; i++) out[i] = 0.f;
     if (!ctx->ev_valid) return 0;
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return -1;
-    for (int i = 0; i < 5; i++) {
+    for (int i = 0; i < 6; i++) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, ctx->ev[i], ctx->ev[i + 1]) == cudaSuccess) out[i] = ms;
     }

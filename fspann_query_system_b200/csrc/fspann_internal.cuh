@@ -43,6 +43,7 @@ struct StoreView {
     const u128 *hpow;     // [kMaxKeys][npow+1] GHASH key powers H^1..H^npow (index 0 unused)
     int32_t npow;         // c + 4, c = ceil(8*dim/16)
     const uint32_t *te0;  // [256]
+    const uint4 *shoup;   // [kMaxKeys][16][256] GHASH multiply-by-H tables (one 64 KB table per live version)
     const uint8_t *deleted;
     int64_t n_deleted;
 };
@@ -89,6 +90,7 @@ struct RefineParams {
     double *dist;       // [Q*stride]
     uint8_t *verdict;   // [Q*stride]
     uint32_t *touched;  // [ceil(N/32)]
+    uint8_t *rec_verdict;  // [n_uniq] authentication verdict per distinct record (verify kernel -> decrypt kernel)
     // outputs
     int32_t *topk_ids;  // [Q][k]
     double *topk_dist;  // [Q][k]
@@ -104,6 +106,7 @@ int launch_route_fast(cudaStream_t s, const RoutingView &rv, const RouteParams &
                       int32_t *vis_part, uint8_t *vis_score, uint8_t *vis_n);
 int64_t route_scratch_ints(int32_t cap0, int32_t max_nodes);
 int launch_refine_group(cudaStream_t s, const StoreView &sv, const RefineParams &p);
+int launch_refine_verify(cudaStream_t s, const StoreView &sv, const RefineParams &p, int sm_count);
 int launch_refine_decrypt(cudaStream_t s, const StoreView &sv, const RefineParams &p, int sm_count);
 int launch_refine_topk(cudaStream_t s, const RefineParams &p);
 int launch_counters(cudaStream_t s, int64_t Q, const int32_t *raw, const int32_t *uniq, const int32_t *n_dec,

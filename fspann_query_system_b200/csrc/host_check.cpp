@@ -31,6 +31,25 @@ void fsp_hc_gfmul(const uint64_t *x, const uint64_t *y, uint64_t *z_fast, uint64
     z_fast[0] = f.hi; z_fast[1] = f.lo; z_ref[0] = r.hi; z_ref[1] = r.lo;
 }
 
+// Shoup 8-bit table multiply (the verify kernel's GHASH step) against the bit-serial reference.  Returns #mismatches.
+int fsp_hc_shoup_check(const uint64_t *h, const uint64_t *xs, int n) {
+    u128 H{h[0], h[1]};
+    std::vector<uint32_t> tab(4096 * 4);
+    ghash_make_shoup8(H, tab.data());
+    int bad = 0;
+    for (int i = 0; i < n; i++) {
+        u128 x{xs[2 * i], xs[2 * i + 1]};
+        const u128 ref = gf128_mul_ref(x, H);
+        uint32_t y[4] = {(uint32_t)(x.hi >> 32), (uint32_t)x.hi, (uint32_t)(x.lo >> 32), (uint32_t)x.lo}, z[4] = {0, 0, 0, 0};
+        for (int j = 0; j < 16; j++) {
+            const uint32_t b = (y[j / 4] >> (24 - 8 * (j % 4))) & 0xff;
+            for (int k = 0; k < 4; k++) z[k] ^= tab[((size_t)j * 256 + b) * 4 + k];
+        }
+        if (z[0] != (uint32_t)(ref.hi >> 32) || z[1] != (uint32_t)ref.hi || z[2] != (uint32_t)(ref.lo >> 32) || z[3] != (uint32_t)ref.lo) bad++;
+    }
+    return bad;
+}
+
 int fsp_hc_aad(int64_t id, int32_t ver, int32_t dim, uint8_t *buf) { return build_aad(id, ver, dim, buf); }
 uint32_t fsp_hc_java_hash(int32_t id) { return java_hash_decimal(id); }
 

@@ -137,12 +137,10 @@ int launch_refine_group(cudaStream_t s, const StoreView &sv, const RefineParams 
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// decrypt + verify + distance.  One warp owns up to 32 consecutive distinct records at a time:
-//   round 0   : lane l computes E_K(J0) of record l (the tag mask) -- 32 blocks, all lanes busy;
-//   per record: lanes split the ciphertext blocks (coalesced 128-bit loads), each lane runs AES-CTR on its blocks,
-//               multiplies them by the matching GHASH key power H^p (aggregated GHASH: sum_i X_i * H^(n-i)) and the
-//               warp XOR-reduces; plaintext goes to the warp's shared-memory row; then lanes take the (query, rank)
-//               pairs of the record and accumulate the exact FP64 distance from shared memory.
+// decrypt + distance.  One warp owns up to 32 consecutive distinct records at a time; per authenticated record the lanes
+// split the ciphertext blocks (coalesced 128-bit loads), each lane runs AES-CTR on its blocks, plaintext goes to the
+// warp's shared-memory row; then lanes take the (query, rank) pairs of the record and accumulate the exact FP64 distance
+// from shared memory.  Authentication (GHASH + tag) is done beforehand by refine_verify_kernel.
 // AES uses one T-table (Te0) replicated for the 32 banks so every lookup is conflict free; Te1..3 are rotations.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int RF_THREADS = 256;
@@ -163,68 +161,142 @@ __device__ __forceinline__ int find_key_slot(const int32_t *s_ver, int nkeys, in
     return slot;
 }
 
-// Decrypts record `id` with the whole warp.  Plaintext doubles -> pt_row[0..dim).  Returns the verdict (warp-uniform).
-// hdr = first 16 bytes of the record (iv | key_version), slot = key slot (>= 0), ej0 = E_K(J0) words.
-__device__ __forceinline__ int warp_decrypt_record(const StoreView &sv, const uint8_t *rec, int32_t id, uint4 hdr, int slot,
-                                                   const uint32_t ej0[4], const TeSmem &te, const uint32_t *s_rk, double *pt_row, int lane) {
-    const int dim = sv.dim;
-    const int nbytes = 8 * dim;
+// AES-CTR decryption of record `id` by the whole warp (authentication already done by refine_verify_kernel).
+// Plaintext doubles -> pt_row[0..dim).  Returns true when every value is finite (warp-uniform).
+__device__ __forceinline__ bool warp_decrypt_record(const StoreView &sv, const uint8_t *rec, uint4 hdr, int slot, const TeSmem &te,
+                                                    const uint32_t *s_rk, double *pt_row, int lane) {
+    const int nbytes = 8 * sv.dim;
     const int c = (nbytes + 15) >> 4;                     // ciphertext blocks (the last may hold only 8 bytes)
     const uint32_t iv0 = bswap32(hdr.x), iv1 = bswap32(hdr.y), iv2 = bswap32(hdr.z);
-    const int32_t version = (int32_t)hdr.w;
     const RkSmem rk{s_rk + slot * 60};
-    const u128 *hp = sv.hpow + (size_t)slot * (sv.npow + 1);
     const uint4 *ctv = reinterpret_cast<const uint4 *>(rec + 16);
-
-    u128 gh = {0, 0};
     bool finite = true;
     for (int blk = lane; blk < c; blk += 32) {
-        uint4 w = __ldg(ctv + blk);
-        uint32_t x0 = bswap32(w.x), x1 = bswap32(w.y), x2 = bswap32(w.z), x3 = bswap32(w.w);
-        const bool half = (blk == c - 1) && (nbytes & 15);  // odd dim: 8 ciphertext bytes, the rest is tag
-        if (half) { x2 = 0; x3 = 0; }
-        u128 X; X.hi = ((uint64_t)x0 << 32) | x1; X.lo = ((uint64_t)x2 << 32) | x3;
-        const u128 z = gf128_mul(X, hp[c + 1 - blk]);
-        gh.hi ^= z.hi; gh.lo ^= z.lo;
+        const uint4 w = __ldg(ctv + blk);
         uint32_t ks[4];
         aes256_encrypt(te, rk, iv0, iv1, iv2, (uint32_t)(blk + 2), ks);
-        const uint32_t p0 = x0 ^ ks[0], p1 = x1 ^ ks[1], p2 = x2 ^ ks[2], p3 = x3 ^ ks[3];
+        const uint32_t p0 = bswap32(w.x) ^ ks[0], p1 = bswap32(w.y) ^ ks[1];
         // big-endian FP64 (AGC:261-277): first word is the high half
         pt_row[2 * blk] = __hiloint2double((int)p0, (int)p1);
         finite &= ((p0 >> 20) & 0x7ffu) != 0x7ffu;
-        if (!half) {
+        if (!((blk == c - 1) && (nbytes & 15))) {          // odd dim: the last block holds one double, the rest is tag
+            const uint32_t p2 = bswap32(w.z) ^ ks[2], p3 = bswap32(w.w) ^ ks[3];
             pt_row[2 * blk + 1] = __hiloint2double((int)p2, (int)p3);
             finite &= ((p2 >> 20) & 0x7ffu) != 0x7ffu;
         }
     }
-    // AAD blocks and the length block (every lane builds the <= 48-byte AAD string; lanes 0..a-1 and lane 31 use it)
+    return __all_sync(0xffffffffu, finite);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Authentication: one LANE per distinct record.  GHASH runs as Horner's rule Y <- (Y ^ X_i) * H with the multiply done
+// by 16 look-ups into the key version's 8-bit Shoup table (64 KB in shared memory, one live version at a time), over the
+// AAD blocks ("id:<id>|v:<ver>|d:<dim>", EP:80-83), the ciphertext blocks and the length block; tag = GHASH ^ E_K(J0)
+// (NIST SP 800-38D).  Writes one verdict per distinct record: OK / TAG_FAIL (NO_KEY is the preset default).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int VF_THREADS = 256;
+
+struct ShoupSmem {
+    const uint4 *t;
+    __device__ __forceinline__ void mul(uint32_t &y0, uint32_t &y1, uint32_t &y2, uint32_t &y3) const {
+        uint4 z = t[y0 >> 24];
+        uint4 u;
+#define FSP_ACC(j, idx) u = t[(j) * 256 + (idx)]; z.x ^= u.x; z.y ^= u.y; z.z ^= u.z; z.w ^= u.w;
+        FSP_ACC(1, (y0 >> 16) & 0xff) FSP_ACC(2, (y0 >> 8) & 0xff) FSP_ACC(3, y0 & 0xff)
+        FSP_ACC(4, y1 >> 24) FSP_ACC(5, (y1 >> 16) & 0xff) FSP_ACC(6, (y1 >> 8) & 0xff) FSP_ACC(7, y1 & 0xff)
+        FSP_ACC(8, y2 >> 24) FSP_ACC(9, (y2 >> 16) & 0xff) FSP_ACC(10, (y2 >> 8) & 0xff) FSP_ACC(11, y2 & 0xff)
+        FSP_ACC(12, y3 >> 24) FSP_ACC(13, (y3 >> 16) & 0xff) FSP_ACC(14, (y3 >> 8) & 0xff) FSP_ACC(15, y3 & 0xff)
+#undef FSP_ACC
+        y0 = z.x; y1 = z.y; y2 = z.z; y3 = z.w;
+    }
+};
+
+// GHASH + tag check of one record by ONE lane.  `sh` = Shoup table of the record's key version, rk = its round keys.
+template <class SH>
+__device__ __forceinline__ bool lane_verify_record(const StoreView &sv, const uint8_t *rec, int32_t id, uint4 hdr, const SH &sh,
+                                                   const TeSmem &te, const RkSmem &rk) {
+    const int dim = sv.dim, nbytes = 8 * dim, c = (nbytes + 15) >> 4;
+    const int32_t version = (int32_t)hdr.w;
+    // ---- GHASH over AAD || ciphertext || lengths ----
+    uint32_t y0 = 0, y1 = 0, y2 = 0, y3 = 0;
     uint8_t aad[FSP_AAD_MAX];
     const int alen = build_aad((int64_t)id, version, dim, aad);
-    const int a = (alen + 15) >> 4;
-    if (lane < a) {
-        u128 X; X.hi = load_be64(aad + 16 * lane); X.lo = load_be64(aad + 16 * lane + 8);
-        const u128 z = gf128_mul(X, hp[c + 1 + a - lane]);
-        gh.hi ^= z.hi; gh.lo ^= z.lo;
+    for (int j = 0; j < (alen + 15) >> 4; j++) {
+        const uint64_t hi = load_be64(aad + 16 * j), lo = load_be64(aad + 16 * j + 8);
+        y0 ^= (uint32_t)(hi >> 32); y1 ^= (uint32_t)hi; y2 ^= (uint32_t)(lo >> 32); y3 ^= (uint32_t)lo;
+        sh.mul(y0, y1, y2, y3);
     }
-    if (lane == 31) {
-        u128 X; X.hi = (uint64_t)alen * 8u; X.lo = (uint64_t)nbytes * 8u;
-        const u128 z = gf128_mul(X, hp[1]);
-        gh.hi ^= z.hi; gh.lo ^= z.lo;
-    }
+    const uint4 *ctv = reinterpret_cast<const uint4 *>(rec + 16);
+    for (int b0 = 0; b0 < c; b0 += 8) {
+        uint4 w[8];
 #pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        gh.hi ^= __shfl_xor_sync(0xffffffffu, gh.hi, o);
-        gh.lo ^= __shfl_xor_sync(0xffffffffu, gh.lo, o);
+        for (int k = 0; k < 8; k++) w[k] = (b0 + k < c) ? __ldg(ctv + b0 + k) : make_uint4(0, 0, 0, 0);   // 128 contiguous bytes of this record
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (b0 + k < c) {
+                uint32_t x0 = bswap32(w[k].x), x1 = bswap32(w[k].y), x2 = bswap32(w[k].z), x3 = bswap32(w[k].w);
+                if ((b0 + k == c - 1) && (nbytes & 15)) { x2 = 0; x3 = 0; }     // odd dim: zero-pad the half block
+                y0 ^= x0; y1 ^= x1; y2 ^= x2; y3 ^= x3;
+                sh.mul(y0, y1, y2, y3);
+            }
+        }
     }
-    // tag = GHASH ^ E_K(J0); stored tag sits right after the ciphertext (8-byte aligned for every dim)
+    y1 ^= (uint32_t)alen * 8u;                       // [len(A)]64 || [len(C)]64 in bits
+    y3 ^= (uint32_t)nbytes * 8u;
+    sh.mul(y0, y1, y2, y3);
+    // ---- tag = GHASH ^ E_K(J0), J0 = IV || 0x00000001 ----
+    uint32_t ej0[4];
+    aes256_encrypt(te, rk, bswap32(hdr.x), bswap32(hdr.y), bswap32(hdr.z), 1u, ej0);
     const uint2 *tagp = reinterpret_cast<const uint2 *>(rec + 16 + nbytes);
     const uint2 t0 = __ldg(tagp), t1 = __ldg(tagp + 1);
-    const uint64_t tag_hi = ((uint64_t)bswap32(t0.x) << 32) | bswap32(t0.y), tag_lo = ((uint64_t)bswap32(t1.x) << 32) | bswap32(t1.y);
-    const uint64_t my_hi = gh.hi ^ (((uint64_t)ej0[0] << 32) | ej0[1]), my_lo = gh.lo ^ (((uint64_t)ej0[2] << 32) | ej0[3]);
-    const bool all_finite = __all_sync(0xffffffffu, finite);
-    if (my_hi != tag_hi || my_lo != tag_lo) return FSPANN_V_TAG_FAIL;     // AGC:159-165
-    if (!all_finite) return FSPANN_V_NON_FINITE;                           // QSI:253
-    return FSPANN_V_OK;
+    return (y0 ^ ej0[0]) == bswap32(t0.x) && (y1 ^ ej0[1]) == bswap32(t0.y) && (y2 ^ ej0[2]) == bswap32(t1.x) && (y3 ^ ej0[3]) == bswap32(t1.y);
+}
+
+__global__ void __launch_bounds__(VF_THREADS) refine_verify_kernel(StoreView sv, RefineParams p) {
+    extern __shared__ __align__(16) unsigned char vf_smem[];
+    uint4 *shoup_s = reinterpret_cast<uint4 *>(vf_smem);                      // [16][256]
+    uint32_t *te_s = reinterpret_cast<uint32_t *>(shoup_s + 4096);            // [256][32]
+    uint32_t *s_rk = te_s + 256 * 32;                                         // [kMaxKeys][60]
+    int32_t *s_ver = reinterpret_cast<int32_t *>(s_rk + kMaxKeys * 60);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < 256 * 32; i += VF_THREADS) te_s[i] = sv.te0[i >> 5];
+    const int nkeys = sv.keys->n;
+    for (int i = tid; i < nkeys * 60; i += VF_THREADS) s_rk[i] = sv.keys->rk[i / 60][i % 60];
+    for (int i = tid; i < kMaxKeys; i += VF_THREADS) s_ver[i] = i < nkeys ? sv.keys->version[i] : INT32_MIN;
+    const TeSmem te{te_s + lane};
+    const ShoupSmem sh{shoup_s};
+    const int n_uniq = p.totals[1];
+    const int n_chunks = (n_uniq + 31) >> 5;
+    const int warps_total = gridDim.x * (VF_THREADS / 32);
+
+    for (int vi = 0; vi < nkeys; vi++) {
+        __syncthreads();
+        for (int i = tid; i < 4096; i += VF_THREADS) shoup_s[i] = sv.shoup[(size_t)vi * 4096 + i];
+        __syncthreads();
+        const int32_t version = s_ver[vi];
+        const RkSmem rk{s_rk + vi * 60};
+        for (int chunk = blockIdx.x * (VF_THREADS / 32) + warp; chunk < n_chunks; chunk += warps_total) {
+            const int u = (chunk << 5) + lane;
+            if (u >= n_uniq) continue;
+            const int32_t id = p.uniq[u];
+            const uint8_t *rec = sv.rec + (size_t)id * sv.rec_stride;
+            const uint4 hdr = __ldg(reinterpret_cast<const uint4 *>(rec));
+            if ((int32_t)hdr.w != version) continue;
+            const bool ok = lane_verify_record(sv, rec, id, hdr, sh, te, rk);
+            p.rec_verdict[u] = ok ? FSPANN_V_OK : FSPANN_V_TAG_FAIL;        // AGC:159-165
+        }
+    }
+}
+
+int launch_refine_verify(cudaStream_t s, const StoreView &sv, const RefineParams &p, int sm_count) {
+    const size_t smem = sizeof(uint4) * 4096 + sizeof(uint32_t) * (256 * 32 + kMaxKeys * 60) + sizeof(int32_t) * kMaxKeys;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(refine_verify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+        configured = true;
+    }
+    refine_verify_kernel<<<sm_count * 2, VF_THREADS, smem, s>>>(sv, p);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
 __global__ void __launch_bounds__(RF_THREADS) refine_decrypt_kernel(StoreView sv, RefineParams p) {
@@ -255,32 +327,26 @@ __global__ void __launch_bounds__(RF_THREADS) refine_decrypt_kernel(StoreView sv
         const int base = chunk << 5;
         const int nrec = min(32, n_uniq - base);
 
-        // round 0: lane l prepares record l (header, key slot, E_K(J0))
-        int32_t my_id = -1; int my_slot = -1; uint4 my_hdr = make_uint4(0, 0, 0, 0); uint32_t my_ej0[4] = {0, 0, 0, 0};
+        // lane l fetches the header and the authentication verdict of record l
+        int32_t my_id = -1; int my_slot = -1; uint4 my_hdr = make_uint4(0, 0, 0, 0); int my_verdict = FSPANN_V_NO_KEY;
         if (lane < nrec) {
             my_id = p.uniq[base + lane];
             my_hdr = __ldg(reinterpret_cast<const uint4 *>(sv.rec + (size_t)my_id * sv.rec_stride));
             my_slot = find_key_slot(s_ver, nkeys, (int32_t)my_hdr.w);
-        }
-        {
-            const int sl = my_slot < 0 ? 0 : my_slot;   // lanes without a key still run the rounds (uniform control flow)
-            const RkSmem rk{s_rk + sl * 60};
-            aes256_encrypt(te, rk, bswap32(my_hdr.x), bswap32(my_hdr.y), bswap32(my_hdr.z), 1u, my_ej0);
+            my_verdict = my_slot < 0 ? FSPANN_V_NO_KEY : (int)p.rec_verdict[base + lane];        // KRS:82-88 -> QSI:265-270
         }
 
         for (int r = 0; r < nrec; r++) {
             const int32_t id = __shfl_sync(0xffffffffu, my_id, r);
             const int slot = __shfl_sync(0xffffffffu, my_slot, r);
+            int verdict = __shfl_sync(0xffffffffu, my_verdict, r);
             uint4 hdr;
             hdr.x = __shfl_sync(0xffffffffu, my_hdr.x, r); hdr.y = __shfl_sync(0xffffffffu, my_hdr.y, r);
             hdr.z = __shfl_sync(0xffffffffu, my_hdr.z, r); hdr.w = __shfl_sync(0xffffffffu, my_hdr.w, r);
-            uint32_t ej0[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) ej0[k] = __shfl_sync(0xffffffffu, my_ej0[k], r);
-
-            int verdict;
-            if (slot < 0) verdict = FSPANN_V_NO_KEY;                         // KRS:82-88 -> QSI:265-270
-            else verdict = warp_decrypt_record(sv, sv.rec + (size_t)id * sv.rec_stride, id, hdr, slot, ej0, te, s_rk, pt_row, lane);
+            if (verdict == FSPANN_V_OK) {      // plaintext is produced only for authenticated records
+                const bool finite = warp_decrypt_record(sv, sv.rec + (size_t)id * sv.rec_stride, hdr, slot, te, s_rk, pt_row, lane);
+                if (!finite) verdict = FSPANN_V_NON_FINITE;                                      // QSI:253
+            }
             __syncwarp();
 
             // the (query, rank) pairs that selected this record
@@ -473,9 +539,12 @@ __global__ void __launch_bounds__(RF_THREADS) debug_decrypt_kernel(StoreView sv,
             const int slot = find_key_slot(s_ver, nkeys, (int32_t)hdr.w);
             if (slot < 0) v = FSPANN_V_NO_KEY;
             else {
-                uint32_t ej0[4];
-                aes256_encrypt(te, RkSmem{s_rk + slot * 60}, bswap32(hdr.x), bswap32(hdr.y), bswap32(hdr.z), 1u, ej0);
-                v = warp_decrypt_record(sv, rec, id, hdr, slot, ej0, te, s_rk, pt_row, lane);
+                // lane 0 authenticates with the Shoup table read from global memory (debug path, speed irrelevant)
+                bool ok = false;
+                if (lane == 0) ok = lane_verify_record(sv, rec, id, hdr, ShoupSmem{sv.shoup + (size_t)slot * 4096}, te, RkSmem{s_rk + slot * 60});
+                ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
+                if (!ok) v = FSPANN_V_TAG_FAIL;
+                else v = warp_decrypt_record(sv, rec, hdr, slot, te, s_rk, pt_row, lane) ? FSPANN_V_OK : FSPANN_V_NON_FINITE;
             }
         }
         __syncwarp();

@@ -154,9 +154,9 @@ class GpuContext:
         return np.nonzero(bits)[0].astype(np.int32)
 
     def stage_ms(self):
-        out = (C.c_float * 5)()
+        out = (C.c_float * 6)()
         n = self.lib.fspann_last_stage_ms(self.ctx, out)
-        return dict(tokengen=out[0], route=out[1], group=out[2], decrypt=out[3], topk=out[4], launches=int(n))
+        return dict(tokengen=out[0], route=out[1], group=out[2], verify=out[3], decrypt=out[4], topk=out[5], launches=int(n))
 
     def set_option(self, name: str, value: int):
         self._ck(self.lib.fspann_set_option(self.ctx, C.c_char_p(name.encode()), C.c_int64(value)))

@@ -153,9 +153,9 @@ int fspann_search_batch_dev(fspann_ctx *ctx, int64_t Q, const double *d_queries,
 int fspann_touched_fetch(fspann_ctx *ctx, uint32_t *bitmap_out, int64_t n_words, int32_t clear);
 
 /* Per-stage device time in milliseconds of the last search/refine call (CUDA events on the context stream):
- * out[0]=tokengen, out[1]=route, out[2]=refine-group(count/scan/fill), out[3]=refine-decrypt+distance,
- * out[4]=top-k.  Returns the number of kernel launches of that call. */
-int64_t fspann_last_stage_ms(fspann_ctx *ctx, float out[5]);
+ * out[0]=tokengen, out[1]=route, out[2]=refine-group(count/scan/fill), out[3]=refine-verify (GHASH + tag),
+ * out[4]=refine-decrypt+distance, out[5]=top-k.  Returns the number of kernel launches of that call. */
+int64_t fspann_last_stage_ms(fspann_ctx *ctx, float out[6]);
 
 /* ---- debug build only (compiled with -DFSPANN_DEBUG_TAP): decrypted plaintext for parity tests -------------
  * Returns FSPANN_E_STATE in production builds, where plaintext never reaches global memory. */
