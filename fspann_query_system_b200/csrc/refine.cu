@@ -11,6 +11,8 @@
 // authenticated and decrypted ONCE, its plaintext lives only in shared memory, and every pair that selected it is
 // scored from there (exact sequential FP64, bit-identical to the Java loop).  Per-query top-k runs afterwards on
 // the scalar distances.  Plaintext never reaches global memory.
+#include <algorithm>
+
 #include "fspann_internal.cuh"
 
 namespace fsp {
@@ -143,8 +145,10 @@ int launch_refine_group(cudaStream_t s, const StoreView &sv, const RefineParams 
 // from shared memory.  Authentication (GHASH + tag) is done beforehand by refine_verify_kernel.
 // AES uses one T-table (Te0) replicated for the 32 banks so every lookup is conflict free; Te1..3 are rotations.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int RF_THREADS = 256;
+constexpr int RF_THREADS = 1024;   // one CTA per SM: the 64 KB-aligned AES table costs up to 128 KB of shared memory
 constexpr int RF_WARPS = RF_THREADS / 32;
+constexpr int DBG_THREADS = 256;
+constexpr int DBG_WARPS = DBG_THREADS / 32;
 
 struct TeSmem {
     const uint32_t *t;  // te_s + lane
@@ -155,26 +159,83 @@ struct RkSmem {
     __device__ __forceinline__ uint32_t operator()(int i) const { return r[i]; }
 };
 
+__device__ __forceinline__ void aes256_encrypt_fast(uint32_t K0, const uint32_t *rk, uint32_t s0, uint32_t s1, uint32_t s2, uint32_t s3,
+                                                    uint32_t out[4]);
+struct AesFast {      // production decrypt kernel
+    uint32_t K0;
+    __device__ __forceinline__ void operator()(const uint32_t *rk, uint32_t s0, uint32_t s1, uint32_t s2, uint32_t s3, uint32_t out[4]) const {
+        aes256_encrypt_fast(K0, rk, s0, s1, s2, s3, out);
+    }
+};
+struct AesPlain {     // same arithmetic through the generic FSP_HD routine (debug tap kernel)
+    TeSmem te;
+    __device__ __forceinline__ void operator()(const uint32_t *rk, uint32_t s0, uint32_t s1, uint32_t s2, uint32_t s3, uint32_t out[4]) const {
+        aes256_encrypt(te, RkSmem{rk}, s0, s1, s2, s3, out);
+    }
+};
+
 __device__ __forceinline__ int find_key_slot(const int32_t *s_ver, int nkeys, int32_t version) {
     int slot = -1;
     for (int i = 0; i < nkeys; i++) if (s_ver[i] == version) slot = i;
     return slot;
 }
 
+// ---- AES-256 with single-instruction table addressing --------------------------------------------------------------
+// Table layout in shared memory (64 KB, placed on a 64 KB boundary of the shared window): entry x occupies 256 bytes =
+// 64 four-byte columns; column `lane` holds Te0[x], column 32+lane holds Te2[x] = rot16(Te0[x]).  A lookup address is
+// tbase + x*256 + lane*4 (+128): x lands exactly in byte 1 of the address, so ONE PRMT builds it from the state word and
+// the per-lane constant K = tbase + lane*4 (whose byte 1 is zero), and every lane stays in its own bank (conflict free).
+// Te1 / Te3 are byte rotations of the looked-up Te0 / Te2 words.
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));     // read-only table: free to schedule
+    return v;
+}
+__device__ __forceinline__ uint32_t ror8(uint32_t x) { return __funnelshift_r(x, x, 8); }
+#define FSP_T0(s, k) lds32(__byte_perm((s), K0, 0x7604 | ((k) << 4)))
+#define FSP_T2(s, k) lds32(__byte_perm((s), K2, 0x7604 | ((k) << 4)))
+__device__ __forceinline__ void aes256_encrypt_fast(uint32_t K0, const uint32_t *rk, uint32_t s0, uint32_t s1, uint32_t s2, uint32_t s3,
+                                                    uint32_t out[4]) {
+    const uint32_t K2 = K0 + 128u;
+    s0 ^= rk[0]; s1 ^= rk[1]; s2 ^= rk[2]; s3 ^= rk[3];
+#pragma unroll
+    for (int r = 1; r < 14; r++) {
+        // t_i = Te0[s_i.b3] ^ Te1[s_{i+1}.b2] ^ Te2[s_{i+2}.b1] ^ Te3[s_{i+3}.b0] ^ rk,  Te1 = ror8(Te0), Te3 = ror8(Te2)
+        const uint32_t a0 = FSP_T0(s0, 3), b0 = FSP_T0(s1, 2), c0 = FSP_T2(s2, 1), d0 = FSP_T2(s3, 0);
+        const uint32_t a1 = FSP_T0(s1, 3), b1 = FSP_T0(s2, 2), c1 = FSP_T2(s3, 1), d1 = FSP_T2(s0, 0);
+        const uint32_t a2 = FSP_T0(s2, 3), b2 = FSP_T0(s3, 2), c2 = FSP_T2(s0, 1), d2 = FSP_T2(s1, 0);
+        const uint32_t a3 = FSP_T0(s3, 3), b3 = FSP_T0(s0, 2), c3 = FSP_T2(s1, 1), d3 = FSP_T2(s2, 0);
+        s0 = a0 ^ c0 ^ rk[4 * r + 0] ^ ror8(b0 ^ d0);      // ror8 is linear: one rotate serves Te1 and Te3
+        s1 = a1 ^ c1 ^ rk[4 * r + 1] ^ ror8(b1 ^ d1);
+        s2 = a2 ^ c2 ^ rk[4 * r + 2] ^ ror8(b2 ^ d2);
+        s3 = a3 ^ c3 ^ rk[4 * r + 3] ^ ror8(b3 ^ d3);
+    }
+    // last round: S[x] is byte 3 and byte 0 of Te2[x] = (s, 3s, 2s, s) and bytes 2, 1 of Te0[x] = (2s, s, s, 3s)
+#define FSP_LAST(a, b, c, d) ((FSP_T2(a, 3) & 0xff000000u) | (FSP_T0(b, 2) & 0x00ff0000u) | (FSP_T0(c, 1) & 0x0000ff00u) | (FSP_T2(d, 0) & 0x000000ffu))
+    out[0] = FSP_LAST(s0, s1, s2, s3) ^ rk[56];
+    out[1] = FSP_LAST(s1, s2, s3, s0) ^ rk[57];
+    out[2] = FSP_LAST(s2, s3, s0, s1) ^ rk[58];
+    out[3] = FSP_LAST(s3, s0, s1, s2) ^ rk[59];
+#undef FSP_LAST
+}
+#undef FSP_T0
+#undef FSP_T2
+
 // AES-CTR decryption of record `id` by the whole warp (authentication already done by refine_verify_kernel).
 // Plaintext doubles -> pt_row[0..dim).  Returns true when every value is finite (warp-uniform).
-__device__ __forceinline__ bool warp_decrypt_record(const StoreView &sv, const uint8_t *rec, uint4 hdr, int slot, const TeSmem &te,
+template <class AES>
+__device__ __forceinline__ bool warp_decrypt_record(const StoreView &sv, const uint8_t *rec, uint4 hdr, int slot, const AES &aes,
                                                     const uint32_t *s_rk, double *pt_row, int lane) {
     const int nbytes = 8 * sv.dim;
     const int c = (nbytes + 15) >> 4;                     // ciphertext blocks (the last may hold only 8 bytes)
     const uint32_t iv0 = bswap32(hdr.x), iv1 = bswap32(hdr.y), iv2 = bswap32(hdr.z);
-    const RkSmem rk{s_rk + slot * 60};
+    const uint32_t *rk = s_rk + slot * 60;
     const uint4 *ctv = reinterpret_cast<const uint4 *>(rec + 16);
     bool finite = true;
     for (int blk = lane; blk < c; blk += 32) {
         const uint4 w = __ldg(ctv + blk);
         uint32_t ks[4];
-        aes256_encrypt(te, rk, iv0, iv1, iv2, (uint32_t)(blk + 2), ks);
+        aes(rk, iv0, iv1, iv2, (uint32_t)(blk + 2), ks);
         const uint32_t p0 = bswap32(w.x) ^ ks[0], p1 = bswap32(w.y) ^ ks[1];
         // big-endian FP64 (AGC:261-277): first word is the high half
         pt_row[2 * blk] = __hiloint2double((int)p0, (int)p1);
@@ -194,7 +255,7 @@ __device__ __forceinline__ bool warp_decrypt_record(const StoreView &sv, const u
 // AAD blocks ("id:<id>|v:<ver>|d:<dim>", EP:80-83), the ciphertext blocks and the length block; tag = GHASH ^ E_K(J0)
 // (NIST SP 800-38D).  Writes one verdict per distinct record: OK / TAG_FAIL (NO_KEY is the preset default).
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int VF_THREADS = 256;
+constexpr int VF_THREADS = 384;
 
 struct ShoupSmem {
     const uint4 *t;
@@ -299,22 +360,28 @@ int launch_refine_verify(cudaStream_t s, const StoreView &sv, const RefineParams
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
-__global__ void __launch_bounds__(RF_THREADS) refine_decrypt_kernel(StoreView sv, RefineParams p) {
+__global__ void __launch_bounds__(RF_THREADS, 1) refine_decrypt_kernel(StoreView sv, RefineParams p) {
     extern __shared__ __align__(16) unsigned char rf_smem[];
-    uint32_t *te_s = reinterpret_cast<uint32_t *>(rf_smem);                 // [256][32] lane-replicated Te0
-    uint32_t *s_rk = te_s + 256 * 32;                                       // [kMaxKeys][60]
-    int32_t *s_ver = reinterpret_cast<int32_t *>(s_rk + kMaxKeys * 60);     // [kMaxKeys]
-    double *pt_all = reinterpret_cast<double *>(s_ver + kMaxKeys);          // [RF_WARPS][dim_pad]
+    // [pad to a 64 KB boundary of the shared window][AES tables 64 KB][round keys][versions][plaintext rows]
+    const uint32_t base_sa = (uint32_t)__cvta_generic_to_shared(rf_smem);
+    const uint32_t pad = (0x10000u - (base_sa & 0xffffu)) & 0xffffu;
+    uint32_t *tab = reinterpret_cast<uint32_t *>(rf_smem + pad);                         // [256][64]
+    uint32_t *s_rk = tab + 256 * 64;                                                      // [kMaxKeys][60]
+    int32_t *s_ver = reinterpret_cast<int32_t *>(s_rk + kMaxKeys * 60);                   // [kMaxKeys]
+    double *pt_all = reinterpret_cast<double *>(s_ver + kMaxKeys);                        // [RF_WARPS][dim_pad]
     const int dim = sv.dim, dim_pad = (dim + 1) & ~1;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    for (int i = tid; i < 256 * 32; i += RF_THREADS) te_s[i] = sv.te0[i >> 5];
+    for (int i = tid; i < 256 * 64; i += RF_THREADS) {
+        const uint32_t t0 = sv.te0[i >> 6];
+        tab[i] = (i & 32) ? __funnelshift_r(t0, t0, 16) : t0;
+    }
     const int nkeys = sv.keys->n;
     for (int i = tid; i < nkeys * 60; i += RF_THREADS) s_rk[i] = sv.keys->rk[i / 60][i % 60];
     for (int i = tid; i < kMaxKeys; i += RF_THREADS) s_ver[i] = i < nkeys ? sv.keys->version[i] : INT32_MIN;
     __syncthreads();
 
-    const TeSmem te{te_s + lane};
+    const AesFast te{base_sa + pad + (uint32_t)lane * 4u};
     double *pt_row = pt_all + (size_t)warp * dim_pad;
     const int n_uniq = p.totals[1];
     const int n_chunks = (n_uniq + 31) >> 5;
@@ -355,10 +422,36 @@ __global__ void __launch_bounds__(RF_THREADS) refine_decrypt_kernel(StoreView sv
                 const uint32_t pair = p.pairs[off + j];
                 if (verdict == FSPANN_V_OK) {
                     const double *qv = p.queries + (size_t)(pair / (uint32_t)p.stride) * dim;
-                    double s = 0.0;
-                    for (int i = 0; i < dim; i++) {                           // QSI:364-372, strict FP64, index order
-                        const double d = __dsub_rn(__ldg(qv + i), pt_row[i]);
-                        s = __dadd_rn(s, __dmul_rn(d, d));
+                    double s = 0.0;                                           // QSI:364-372, strict FP64, index order
+                    if ((dim & 1) == 0) {
+                        // 128-bit loads, 16 values in flight per lane; the adds stay strictly sequential
+                        const double2 *q2 = reinterpret_cast<const double2 *>(qv);
+                        const double2 *v2 = reinterpret_cast<const double2 *>(pt_row);
+                        const int n2 = dim >> 1;
+                        int i = 0;
+                        for (; i + 8 <= n2; i += 8) {
+                            double2 qq[8];
+#pragma unroll
+                            for (int u = 0; u < 8; u++) qq[u] = __ldg(q2 + i + u);
+#pragma unroll
+                            for (int u = 0; u < 8; u++) {
+                                const double2 vv = v2[i + u];
+                                const double d0 = __dsub_rn(qq[u].x, vv.x), d1 = __dsub_rn(qq[u].y, vv.y);
+                                s = __dadd_rn(s, __dmul_rn(d0, d0));
+                                s = __dadd_rn(s, __dmul_rn(d1, d1));
+                            }
+                        }
+                        for (; i < n2; i++) {
+                            const double2 q1 = __ldg(q2 + i), vv = v2[i];
+                            const double d0 = __dsub_rn(q1.x, vv.x), d1 = __dsub_rn(q1.y, vv.y);
+                            s = __dadd_rn(s, __dmul_rn(d0, d0));
+                            s = __dadd_rn(s, __dmul_rn(d1, d1));
+                        }
+                    } else {
+                        for (int i = 0; i < dim; i++) {
+                            const double d = __dsub_rn(__ldg(qv + i), pt_row[i]);
+                            s = __dadd_rn(s, __dmul_rn(d, d));
+                        }
                     }
                     p.dist[pair] = __dsqrt_rn(s);
                 }
@@ -372,14 +465,15 @@ __global__ void __launch_bounds__(RF_THREADS) refine_decrypt_kernel(StoreView sv
 
 int launch_refine_decrypt(cudaStream_t s, const StoreView &sv, const RefineParams &p, int sm_count) {
     const int dim_pad = (sv.dim + 1) & ~1;
-    const size_t smem = sizeof(uint32_t) * (256 * 32 + kMaxKeys * 60) + sizeof(int32_t) * kMaxKeys + sizeof(double) * (size_t)RF_WARPS * dim_pad;
+    const size_t smem = 0x10000 /* worst-case pad */ + sizeof(uint32_t) * (256 * 64 + kMaxKeys * 60) + sizeof(int32_t) * kMaxKeys +
+                        sizeof(double) * (size_t)RF_WARPS * dim_pad + 16;
+    if (smem > 227 * 1024) return -1;
     static size_t configured = 0;
     if (smem > configured) {
         if (cudaFuncSetAttribute(refine_decrypt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
         configured = smem;
     }
-    int per_sm = 2;
-    refine_decrypt_kernel<<<sm_count * per_sm, RF_THREADS, smem, s>>>(sv, p);
+    refine_decrypt_kernel<<<sm_count, RF_THREADS, smem, s>>>(sv, p);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
@@ -514,7 +608,7 @@ int launch_store_pack(cudaStream_t s, uint8_t *rec, int64_t rec_stride, int32_t 
 // "decrypted plaintexts are bit-exact".  Not compiled into the production library.
 // ------------------------------------------------------------------------------------------------------------------
 #ifdef FSPANN_DEBUG_TAP
-__global__ void __launch_bounds__(RF_THREADS) debug_decrypt_kernel(StoreView sv, int64_t n, const int32_t *ids, double *pt, uint8_t *verdict) {
+__global__ void __launch_bounds__(DBG_THREADS) debug_decrypt_kernel(StoreView sv, int64_t n, const int32_t *ids, double *pt, uint8_t *verdict) {
     extern __shared__ __align__(16) unsigned char rf_smem[];
     uint32_t *te_s = reinterpret_cast<uint32_t *>(rf_smem);
     uint32_t *s_rk = te_s + 256 * 32;
@@ -522,14 +616,14 @@ __global__ void __launch_bounds__(RF_THREADS) debug_decrypt_kernel(StoreView sv,
     double *pt_all = reinterpret_cast<double *>(s_ver + kMaxKeys);
     const int dim = sv.dim, dim_pad = (dim + 1) & ~1;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < 256 * 32; i += RF_THREADS) te_s[i] = sv.te0[i >> 5];
+    for (int i = tid; i < 256 * 32; i += DBG_THREADS) te_s[i] = sv.te0[i >> 5];
     const int nkeys = sv.keys->n;
-    for (int i = tid; i < nkeys * 60; i += RF_THREADS) s_rk[i] = sv.keys->rk[i / 60][i % 60];
-    for (int i = tid; i < kMaxKeys; i += RF_THREADS) s_ver[i] = i < nkeys ? sv.keys->version[i] : INT32_MIN;
+    for (int i = tid; i < nkeys * 60; i += DBG_THREADS) s_rk[i] = sv.keys->rk[i / 60][i % 60];
+    for (int i = tid; i < kMaxKeys; i += DBG_THREADS) s_ver[i] = i < nkeys ? sv.keys->version[i] : INT32_MIN;
     __syncthreads();
     const TeSmem te{te_s + lane};
     double *pt_row = pt_all + (size_t)warp * dim_pad;
-    for (int64_t j = (int64_t)blockIdx.x * RF_WARPS + warp; j < n; j += (int64_t)gridDim.x * RF_WARPS) {
+    for (int64_t j = (int64_t)blockIdx.x * DBG_WARPS + warp; j < n; j += (int64_t)gridDim.x * DBG_WARPS) {
         const int32_t id = ids[j];
         int v;
         if (id < 0 || id >= sv.N || is_deleted(sv, id)) v = FSPANN_V_NOT_FOUND;
@@ -544,7 +638,7 @@ __global__ void __launch_bounds__(RF_THREADS) debug_decrypt_kernel(StoreView sv,
                 if (lane == 0) ok = lane_verify_record(sv, rec, id, hdr, ShoupSmem{sv.shoup + (size_t)slot * 4096}, te, RkSmem{s_rk + slot * 60});
                 ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
                 if (!ok) v = FSPANN_V_TAG_FAIL;
-                else v = warp_decrypt_record(sv, rec, hdr, slot, te, s_rk, pt_row, lane) ? FSPANN_V_OK : FSPANN_V_NON_FINITE;
+                else v = warp_decrypt_record(sv, rec, hdr, slot, AesPlain{te}, s_rk, pt_row, lane) ? FSPANN_V_OK : FSPANN_V_NON_FINITE;
             }
         }
         __syncwarp();
@@ -555,10 +649,10 @@ __global__ void __launch_bounds__(RF_THREADS) debug_decrypt_kernel(StoreView sv,
 }
 int launch_debug_decrypt(cudaStream_t s, const StoreView &sv, int64_t n, const int32_t *ids, double *pt, uint8_t *verdict) {
     const int dim_pad = (sv.dim + 1) & ~1;
-    const size_t smem = sizeof(uint32_t) * (256 * 32 + kMaxKeys * 60) + sizeof(int32_t) * kMaxKeys + sizeof(double) * (size_t)RF_WARPS * dim_pad;
+    const size_t smem = sizeof(uint32_t) * (256 * 32 + kMaxKeys * 60) + sizeof(int32_t) * kMaxKeys + sizeof(double) * (size_t)DBG_WARPS * dim_pad;
     if (cudaFuncSetAttribute(debug_decrypt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-    int grid = (int)((n + RF_WARPS - 1) / RF_WARPS); if (grid > 148 * 2) grid = 148 * 2; if (grid < 1) grid = 1;
-    debug_decrypt_kernel<<<grid, RF_THREADS, smem, s>>>(sv, n, ids, pt, verdict);
+    int grid = (int)((n + DBG_WARPS - 1) / DBG_WARPS); if (grid > 148 * 2) grid = 148 * 2; if (grid < 1) grid = 1;
+    debug_decrypt_kernel<<<grid, DBG_THREADS, smem, s>>>(sv, n, ids, pt, verdict);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 #else
