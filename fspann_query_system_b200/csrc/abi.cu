@@ -46,6 +46,7 @@ struct fspann_ctx {
     int last_route_path = 0;     // 1 = shared-memory fast path, 2 = general path
     DevBuf s_queries, s_codes, s_cand_ids, s_cand_sc, s_ncand, s_raw, s_uniq_cnt, s_route_scratch, s_overflow;
     DevBuf s_rec_verdict;
+    DevKeyRing ring_host{};
     DevBuf s_cnt, s_flag, s_fill, s_uniq, s_pairs, s_bsums, s_totals, s_dist, s_verdict;
     DevBuf s_topk_ids, s_topk_dist, s_nret, s_ndec, s_counters;
     DevBuf s_stage_a, s_stage_b, s_stage_c;  // upload staging
@@ -135,6 +136,8 @@ int rebuild_keys(fspann_ctx *ctx) {
         n++;
     }
     ring.n = n;
+    ctx->ring_host = ring;
+    ctx->sv.keys_host = &ctx->ring_host;
     ENSURE(ctx->d_keyring, sizeof ring);
     ENSURE(ctx->d_hpow, sizeof(u128) * hp.size());
     ENSURE(ctx->d_shoup, sizeof(uint32_t) * shoup.size());

@@ -40,6 +40,7 @@ struct StoreView {
     int64_t rec_stride;
     const uint8_t *rec;
     const DevKeyRing *keys;
+    const DevKeyRing *keys_host;  // host copy of the same ring (passed by value to kernels that want it in the constant bank)
     const u128 *hpow;     // [kMaxKeys][npow+1] GHASH key powers H^1..H^npow (index 0 unused)
     int32_t npow;         // c + 4, c = ceil(8*dim/16)
     const uint32_t *te0;  // [256]

@@ -360,15 +360,13 @@ int launch_refine_verify(cudaStream_t s, const StoreView &sv, const RefineParams
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
-__global__ void __launch_bounds__(RF_THREADS, 1) refine_decrypt_kernel(StoreView sv, RefineParams p) {
+__global__ void __launch_bounds__(RF_THREADS, 1) refine_decrypt_kernel(const __grid_constant__ DevKeyRing ring, StoreView sv, RefineParams p) {
     extern __shared__ __align__(16) unsigned char rf_smem[];
     // [pad to a 64 KB boundary of the shared window][AES tables 64 KB][round keys][versions][plaintext rows]
     const uint32_t base_sa = (uint32_t)__cvta_generic_to_shared(rf_smem);
     const uint32_t pad = (0x10000u - (base_sa & 0xffffu)) & 0xffffu;
     uint32_t *tab = reinterpret_cast<uint32_t *>(rf_smem + pad);                         // [256][64]
-    uint32_t *s_rk = tab + 256 * 64;                                                      // [kMaxKeys][60]
-    int32_t *s_ver = reinterpret_cast<int32_t *>(s_rk + kMaxKeys * 60);                   // [kMaxKeys]
-    double *pt_all = reinterpret_cast<double *>(s_ver + kMaxKeys);                        // [RF_WARPS][dim_pad]
+    double *pt_all = reinterpret_cast<double *>(tab + 256 * 64);                           // [RF_WARPS][dim_pad]
     const int dim = sv.dim, dim_pad = (dim + 1) & ~1;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -376,9 +374,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) refine_decrypt_kernel(StoreView
         const uint32_t t0 = sv.te0[i >> 6];
         tab[i] = (i & 32) ? __funnelshift_r(t0, t0, 16) : t0;
     }
-    const int nkeys = sv.keys->n;
-    for (int i = tid; i < nkeys * 60; i += RF_THREADS) s_rk[i] = sv.keys->rk[i / 60][i % 60];
-    for (int i = tid; i < kMaxKeys; i += RF_THREADS) s_ver[i] = i < nkeys ? sv.keys->version[i] : INT32_MIN;
+    const int nkeys = ring.n;
     __syncthreads();
 
     const AesFast te{base_sa + pad + (uint32_t)lane * 4u};
@@ -399,7 +395,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) refine_decrypt_kernel(StoreView
         if (lane < nrec) {
             my_id = p.uniq[base + lane];
             my_hdr = __ldg(reinterpret_cast<const uint4 *>(sv.rec + (size_t)my_id * sv.rec_stride));
-            my_slot = find_key_slot(s_ver, nkeys, (int32_t)my_hdr.w);
+            for (int i = 0; i < nkeys; i++) if (ring.version[i] == (int32_t)my_hdr.w) my_slot = i;
             my_verdict = my_slot < 0 ? FSPANN_V_NO_KEY : (int)p.rec_verdict[base + lane];        // KRS:82-88 -> QSI:265-270
         }
 
@@ -411,7 +407,11 @@ __global__ void __launch_bounds__(RF_THREADS, 1) refine_decrypt_kernel(StoreView
             hdr.x = __shfl_sync(0xffffffffu, my_hdr.x, r); hdr.y = __shfl_sync(0xffffffffu, my_hdr.y, r);
             hdr.z = __shfl_sync(0xffffffffu, my_hdr.z, r); hdr.w = __shfl_sync(0xffffffffu, my_hdr.w, r);
             if (verdict == FSPANN_V_OK) {      // plaintext is produced only for authenticated records
-                const bool finite = warp_decrypt_record(sv, sv.rec + (size_t)id * sv.rec_stride, hdr, slot, te, s_rk, pt_row, lane);
+                // the loop counter is warp-uniform, so the round keys are read from the kernel-parameter constant bank through
+                // the uniform datapath instead of 60 shared-memory loads per block
+                bool finite = true;
+                for (int vi = 0; vi < nkeys; vi++)
+                    if (vi == slot) finite = warp_decrypt_record(sv, sv.rec + (size_t)id * sv.rec_stride, hdr, 0, te, ring.rk[vi], pt_row, lane);
                 if (!finite) verdict = FSPANN_V_NON_FINITE;                                      // QSI:253
             }
             __syncwarp();
@@ -465,15 +465,14 @@ __global__ void __launch_bounds__(RF_THREADS, 1) refine_decrypt_kernel(StoreView
 
 int launch_refine_decrypt(cudaStream_t s, const StoreView &sv, const RefineParams &p, int sm_count) {
     const int dim_pad = (sv.dim + 1) & ~1;
-    const size_t smem = 0x10000 /* worst-case pad */ + sizeof(uint32_t) * (256 * 64 + kMaxKeys * 60) + sizeof(int32_t) * kMaxKeys +
-                        sizeof(double) * (size_t)RF_WARPS * dim_pad + 16;
+    const size_t smem = 0x10000 /* worst-case pad */ + sizeof(uint32_t) * (256 * 64) + sizeof(double) * (size_t)RF_WARPS * dim_pad + 16;
     if (smem > 227 * 1024) return -1;
     static size_t configured = 0;
     if (smem > configured) {
         if (cudaFuncSetAttribute(refine_decrypt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
         configured = smem;
     }
-    refine_decrypt_kernel<<<sm_count, RF_THREADS, smem, s>>>(sv, p);
+    refine_decrypt_kernel<<<sm_count, RF_THREADS, smem, s>>>(*sv.keys_host, sv, p);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
