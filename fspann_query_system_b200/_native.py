@@ -13,13 +13,14 @@ DEBUG_LIB_PATH = os.path.join(_HERE, "csrc", "libfspann_gpu_debug.so")
 
 OK, E_ARG, E_STATE, E_CUDA, E_NOMEM = 0, -1, -2, -3, -4
 V_OK, V_NOT_FOUND, V_NO_KEY, V_TAG_FAIL, V_NON_FINITE = 0, 1, 2, 3, 4
+V_OTHER_SHARD = 0xFD
 COUNTERS = 6
 
 EXPORTS = [
     "fspann_ctx_create", "fspann_ctx_destroy", "fspann_last_error", "fspann_ctx_stream", "fspann_ctx_sync",
     "fspann_ctx_launch_count", "fspann_routing_upload", "fspann_gfunctions_upload", "fspann_deleted_set",
-    "fspann_store_upload", "fspann_store_update", "fspann_keys_set", "fspann_keys_retire", "fspann_tokengen_batch",
-    "fspann_route_batch", "fspann_refine_batch", "fspann_search_batch", "fspann_search_batch_dev", "fspann_touched_fetch",
+    "fspann_store_upload", "fspann_store_upload_shard", "fspann_store_update", "fspann_keys_set", "fspann_keys_retire", "fspann_tokengen_batch",
+    "fspann_route_batch", "fspann_refine_batch", "fspann_refine_batch_ex", "fspann_search_batch", "fspann_search_batch_dev", "fspann_touched_fetch",
     "fspann_last_stage_ms", "fspann_debug_decrypt", "fspann_set_option", "fspann_get_info",
 ]
 

@@ -47,8 +47,9 @@ struct fspann_ctx {
     DevBuf s_queries, s_codes, s_cand_ids, s_cand_sc, s_ncand, s_raw, s_uniq_cnt, s_route_scratch, s_overflow;
     DevBuf s_rec_verdict;
     DevKeyRing ring_host{};
+    int32_t *want_rank = nullptr;
     DevBuf s_cnt, s_flag, s_fill, s_uniq, s_pairs, s_bsums, s_totals, s_dist, s_verdict;
-    DevBuf s_topk_ids, s_topk_dist, s_nret, s_ndec, s_counters;
+    DevBuf s_topk_ids, s_topk_dist, s_topk_rank, s_nret, s_ndec, s_counters;
     DevBuf s_stage_a, s_stage_b, s_stage_c;  // upload staging
     DevBuf r_rows, r_queries, r_codes, r_topk_ids, r_topk_dist, r_nret, r_counters;  // retry subset
     DevBuf t_cand_ids, t_cand_sc, t_ncand, t_raw, t_uniq_cnt, t_ndec;               // retry subset route outputs
@@ -228,7 +229,7 @@ int do_refine(fspann_ctx *ctx, int64_t Q, const double *d_queries, const int32_t
     p.pairs = (uint32_t *)ctx->s_pairs.p; p.block_sums = (int32_t *)ctx->s_bsums.p; p.totals = (int32_t *)ctx->s_totals.p;
     p.dist = (double *)ctx->s_dist.p; p.verdict = (uint8_t *)ctx->s_verdict.p; p.touched = (uint32_t *)ctx->d_touched.p;
     p.rec_verdict = (uint8_t *)ctx->s_rec_verdict.p;
-    p.topk_ids = d_topk_ids; p.topk_dist = d_topk_dist; p.n_ret = d_nret; p.n_dec = d_ndec;
+    p.topk_ids = d_topk_ids; p.topk_dist = d_topk_dist; p.n_ret = d_nret; p.n_dec = d_ndec; p.topk_rank = ctx->want_rank;
     // unknown / retired key version is the default verdict (KRS:82-88); the verify kernel overwrites it per live version
     CK(cudaMemsetAsync(p.rec_verdict, FSPANN_V_NO_KEY, (size_t)std::min<int64_t>(n1, total + 1), ctx->stream));
     LAUNCHED(launch_refine_group(ctx->stream, sv, p));
@@ -284,7 +285,7 @@ void fspann_ctx_destroy(fspann_ctx *ctx) {
                       &ctx->d_keyring, &ctx->d_hpow, &ctx->d_shoup, &ctx->s_rec_verdict, &ctx->d_te0, &ctx->d_touched, &ctx->s_queries, &ctx->s_codes, &ctx->s_cand_ids,
                       &ctx->s_cand_sc, &ctx->s_ncand, &ctx->s_raw, &ctx->s_uniq_cnt, &ctx->s_route_scratch, &ctx->s_overflow, &ctx->s_cnt,
                       &ctx->s_flag, &ctx->s_fill, &ctx->s_uniq, &ctx->s_pairs, &ctx->s_bsums, &ctx->s_totals, &ctx->s_dist, &ctx->s_verdict,
-                      &ctx->s_topk_ids, &ctx->s_topk_dist, &ctx->s_nret, &ctx->s_ndec, &ctx->s_counters, &ctx->s_stage_a, &ctx->s_stage_b,
+                      &ctx->s_topk_ids, &ctx->s_topk_dist, &ctx->s_topk_rank, &ctx->s_nret, &ctx->s_ndec, &ctx->s_counters, &ctx->s_stage_a, &ctx->s_stage_b,
                       &ctx->s_stage_c, &ctx->s_vis_part, &ctx->s_vis_score, &ctx->s_vis_n, &ctx->r_rows, &ctx->r_queries, &ctx->r_codes, &ctx->r_topk_ids, &ctx->r_topk_dist, &ctx->r_nret,
                       &ctx->r_counters, &ctx->t_cand_ids, &ctx->t_cand_sc, &ctx->t_ncand, &ctx->t_raw, &ctx->t_uniq_cnt, &ctx->t_ndec};
     for (DevBuf *b : bufs) release(*b);
@@ -405,12 +406,15 @@ static int store_write(fspann_ctx *ctx, int64_t n, const int32_t *ids, const uin
     return 0;
 }
 
-int fspann_store_upload(fspann_ctx *ctx, int64_t N, int32_t dim, const uint8_t *iv, const uint8_t *ct, const int32_t *key_version) {
+int fspann_store_upload_shard(fspann_ctx *ctx, int64_t id_base, int64_t N, int64_t n_global, int32_t dim, const uint8_t *iv, const uint8_t *ct,
+                              const int32_t *key_version) {
     if (!ctx) return FSPANN_E_ARG;
     CK(cudaSetDevice(ctx->device));
     if (!iv || !ct || !key_version) return fail(ctx, FSPANN_E_ARG, "null array");
     if (N <= 0 || dim <= 0) return fail(ctx, FSPANN_E_ARG, "non-positive N/dim");
-    if (N >= (1LL << 31) - 1) return fail(ctx, FSPANN_E_ARG, "N too large for int32 ids");
+    if (id_base < 0 || n_global < id_base + N) return fail(ctx, FSPANN_E_ARG, "shard [%lld, %lld) outside the global id space %lld",
+                                                           (long long)id_base, (long long)(id_base + N), (long long)n_global);
+    if (n_global >= (1LL << 31) - 1) return fail(ctx, FSPANN_E_ARG, "N too large for int32 ids");
     ctx->store_ready = false;
     const int64_t stride = ((32 + 8LL * dim) + 15) / 16 * 16;
     ENSURE(ctx->d_rec, (size_t)N * stride + 64);
@@ -418,12 +422,17 @@ int fspann_store_upload(fspann_ctx *ctx, int64_t N, int32_t dim, const uint8_t *
     CK(cudaMemsetAsync(ctx->d_rec.p, 0, (size_t)N * stride + 64, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_touched.p, 0, sizeof(uint32_t) * (size_t)((N + 31) / 32 + 1), ctx->stream));
     const bool dim_changed = ctx->sv.dim != dim;
-    ctx->sv.N = N; ctx->sv.dim = dim; ctx->sv.rec_stride = stride; ctx->sv.rec = (const uint8_t *)ctx->d_rec.p;
+    ctx->sv.N = N; ctx->sv.id_base = id_base; ctx->sv.n_global = n_global;
+    ctx->sv.dim = dim; ctx->sv.rec_stride = stride; ctx->sv.rec = (const uint8_t *)ctx->d_rec.p;
     if (dim_changed || !ctx->sv.hpow) { int rc = rebuild_keys(ctx); if (rc) return rc; }
     int rc = store_write(ctx, N, nullptr, iv, ct, key_version);
     if (rc) return rc;
     ctx->store_ready = true;
     return FSPANN_OK;
+}
+
+int fspann_store_upload(fspann_ctx *ctx, int64_t N, int32_t dim, const uint8_t *iv, const uint8_t *ct, const int32_t *key_version) {
+    return fspann_store_upload_shard(ctx, 0, N, N, dim, iv, ct, key_version);
 }
 
 int fspann_store_update(fspann_ctx *ctx, int64_t n, const int32_t *ids, const uint8_t *iv, const uint8_t *ct, const int32_t *key_version) {
@@ -432,9 +441,12 @@ int fspann_store_update(fspann_ctx *ctx, int64_t n, const int32_t *ids, const ui
     if (!ctx->store_ready) return fail(ctx, FSPANN_E_STATE, "record store not uploaded");
     if (n == 0) return FSPANN_OK;
     if (!ids || !iv || !ct || !key_version || n < 0) return fail(ctx, FSPANN_E_ARG, "null array");
-    for (int64_t i = 0; i < n; i++)
-        if (ids[i] < 0 || ids[i] >= ctx->sv.N) return fail(ctx, FSPANN_E_ARG, "id %d out of range", ids[i]);
-    return store_write(ctx, n, ids, iv, ct, key_version);
+    std::vector<int32_t> local((size_t)n);
+    for (int64_t i = 0; i < n; i++) {
+        if (ids[i] < ctx->sv.id_base || ids[i] >= ctx->sv.id_base + ctx->sv.N) return fail(ctx, FSPANN_E_ARG, "id %d is not held by this context", ids[i]);
+        local[(size_t)i] = (int32_t)(ids[i] - ctx->sv.id_base);
+    }
+    return store_write(ctx, n, local.data(), iv, ct, key_version);
 }
 
 int fspann_keys_set(fspann_ctx *ctx, int32_t version, const uint8_t key[32]) {
@@ -506,6 +518,13 @@ int fspann_route_batch(fspann_ctx *ctx, int64_t Q, const uint64_t *codes, int32_
 int fspann_refine_batch(fspann_ctx *ctx, int64_t Q, const double *queries, const int32_t *cand_ids, const int32_t *n_cand,
                         int32_t cand_stride, int32_t k, int32_t *topk_ids_out, double *topk_dist_out, int32_t *n_ret_out,
                         uint8_t *verdict_out, int32_t *n_decrypted_out) {
+    return fspann_refine_batch_ex(ctx, Q, queries, cand_ids, n_cand, cand_stride, k, topk_ids_out, topk_dist_out, nullptr, n_ret_out, verdict_out,
+                                  n_decrypted_out);
+}
+
+int fspann_refine_batch_ex(fspann_ctx *ctx, int64_t Q, const double *queries, const int32_t *cand_ids, const int32_t *n_cand,
+                           int32_t cand_stride, int32_t k, int32_t *topk_ids_out, double *topk_dist_out, int32_t *topk_rank_out,
+                           int32_t *n_ret_out, uint8_t *verdict_out, int32_t *n_decrypted_out) {
     if (!ctx) return FSPANN_E_ARG;
     CK(cudaSetDevice(ctx->device));
     int rc = check_store(ctx); if (rc) return rc;
@@ -526,9 +545,13 @@ int fspann_refine_batch(fspann_ctx *ctx, int64_t Q, const double *queries, const
     rc = record_ev(ctx, 0); if (rc) return rc;
     rc = record_ev(ctx, 1); if (rc) return rc;
     rc = record_ev(ctx, 2); if (rc) return rc;
+    ENSURE(ctx->s_topk_rank, sizeof(int32_t) * (size_t)Q * k);
+    ctx->want_rank = topk_rank_out ? (int32_t *)ctx->s_topk_rank.p : nullptr;
     rc = do_refine(ctx, Q, (const double *)ctx->s_queries.p, (const int32_t *)ctx->s_cand_ids.p, (const int32_t *)ctx->s_ncand.p, cand_stride, k,
                    (int32_t *)ctx->s_topk_ids.p, (double *)ctx->s_topk_dist.p, (int32_t *)ctx->s_nret.p, (int32_t *)ctx->s_ndec.p, true);
+    ctx->want_rank = nullptr;
     if (rc) return rc;
+    if (topk_rank_out) CK(cudaMemcpyAsync(topk_rank_out, ctx->s_topk_rank.p, sizeof(int32_t) * (size_t)Q * k, cudaMemcpyDeviceToHost, ctx->stream));
     ctx->ev_valid = true; ctx->last_call_launches = ctx->launches - l0;
     CK(cudaMemcpyAsync(topk_ids_out, ctx->s_topk_ids.p, sizeof(int32_t) * (size_t)Q * k, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(topk_dist_out, ctx->s_topk_dist.p, sizeof(double) * (size_t)Q * k, cudaMemcpyDeviceToHost, ctx->stream));

@@ -35,7 +35,9 @@ struct RoutingView {
 // Record store as the kernels see it.  One record = [iv 12 B | key_version 4 B | ciphertext 8*dim B | tag 16 B | pad],
 // rec_stride a multiple of 16 so every record starts 128-bit aligned.
 struct StoreView {
-    int64_t N;
+    int64_t N;            // records held by this context: global ids [id_base, id_base + N)
+    int64_t id_base;      // first global id of this shard (0 for an unsharded store)
+    int64_t n_global;     // global id space [0, n_global); ids outside it do not exist
     int32_t dim;
     int64_t rec_stride;
     const uint8_t *rec;
@@ -96,6 +98,7 @@ struct RefineParams {
     int32_t *topk_ids;  // [Q][k]
     double *topk_dist;  // [Q][k]
     int32_t *n_ret, *n_dec;
+    int32_t *topk_rank;  // [Q][k] candidate position of each result (for the cross-shard merge), or nullptr
 };
 
 // launchers (each returns the number of kernels it launched, or -1 after setting a CUDA error)

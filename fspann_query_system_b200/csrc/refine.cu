@@ -32,8 +32,9 @@ __global__ void refine_count_kernel(StoreView sv, RefineParams p) {
         uint8_t v = 0xff;                               // 0xff = slot not part of the candidate list
         if (r < p.n_cand[q]) {
             const int32_t id = p.cand_ids[i];
-            if (id < 0 || id >= sv.N || is_deleted(sv, id)) v = FSPANN_V_NOT_FOUND;     // PIS:717-724
-            else { atomicAdd(&p.cnt[id], 1); v = 0xfe; }                                 // 0xfe = pending
+            if (id < 0 || id >= sv.n_global || is_deleted(sv, id)) v = FSPANN_V_NOT_FOUND;     // PIS:717-724
+            else if (id < sv.id_base || id >= sv.id_base + sv.N) v = 0xfd;                      // 0xfd = lives in another shard
+            else { atomicAdd(&p.cnt[id - sv.id_base], 1); v = 0xfe; }                           // 0xfe = pending
         }
         p.verdict[i] = v;
     }
@@ -118,7 +119,7 @@ __global__ void refine_fill_kernel(StoreView sv, RefineParams p) {
     const int64_t total = p.Q * (int64_t)p.stride;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         if (p.verdict[i] != 0xfe) continue;
-        const int32_t id = p.cand_ids[i];
+        const int32_t id = (int32_t)(p.cand_ids[i] - sv.id_base);
         const int pos = p.cnt[id] + atomicAdd(&p.fill[id], 1);
         p.pairs[pos] = (uint32_t)i;
     }
@@ -339,8 +340,9 @@ __global__ void __launch_bounds__(VF_THREADS) refine_verify_kernel(StoreView sv,
         for (int chunk = blockIdx.x * (VF_THREADS / 32) + warp; chunk < n_chunks; chunk += warps_total) {
             const int u = (chunk << 5) + lane;
             if (u >= n_uniq) continue;
-            const int32_t id = p.uniq[u];
-            const uint8_t *rec = sv.rec + (size_t)id * sv.rec_stride;
+            const int32_t li = p.uniq[u];                                   // index inside this shard
+            const int32_t id = (int32_t)(li + sv.id_base);                  // global id: what the AAD binds (EP:80-83)
+            const uint8_t *rec = sv.rec + (size_t)li * sv.rec_stride;
             const uint4 hdr = __ldg(reinterpret_cast<const uint4 *>(rec));
             if ((int32_t)hdr.w != version) continue;
             const bool ok = lane_verify_record(sv, rec, id, hdr, sh, te, rk);
@@ -528,12 +530,14 @@ __global__ void __launch_bounds__(TK_THREADS) refine_topk_kernel(RefineParams p)
             s_last_key = b; s_last_rank = br;
             p.topk_ids[(size_t)q * p.k + round] = p.cand_ids[(size_t)q * p.stride + br];
             p.topk_dist[(size_t)q * p.k + round] = __longlong_as_double((long long)b);
+            if (p.topk_rank) p.topk_rank[(size_t)q * p.k + round] = br;
         }
         __syncthreads();
     }
     for (int i = eff + tid; i < p.k; i += TK_THREADS) {
         p.topk_ids[(size_t)q * p.k + i] = -1;
         p.topk_dist[(size_t)q * p.k + i] = __longlong_as_double(0x7ff8000000000000ll);
+        if (p.topk_rank) p.topk_rank[(size_t)q * p.k + i] = 0x7fffffff;
     }
     if (tid == 0) { p.n_ret[q] = eff; if (p.n_dec) p.n_dec[q] = total_ok; }
 }
@@ -625,9 +629,9 @@ __global__ void __launch_bounds__(DBG_THREADS) debug_decrypt_kernel(StoreView sv
     for (int64_t j = (int64_t)blockIdx.x * DBG_WARPS + warp; j < n; j += (int64_t)gridDim.x * DBG_WARPS) {
         const int32_t id = ids[j];
         int v;
-        if (id < 0 || id >= sv.N || is_deleted(sv, id)) v = FSPANN_V_NOT_FOUND;
+        if (id < sv.id_base || id >= sv.id_base + sv.N || is_deleted(sv, id)) v = FSPANN_V_NOT_FOUND;
         else {
-            const uint8_t *rec = sv.rec + (size_t)id * sv.rec_stride;
+            const uint8_t *rec = sv.rec + (size_t)(id - sv.id_base) * sv.rec_stride;
             const uint4 hdr = __ldg(reinterpret_cast<const uint4 *>(rec));
             const int slot = find_key_slot(s_ver, nkeys, (int32_t)hdr.w);
             if (slot < 0) v = FSPANN_V_NO_KEY;

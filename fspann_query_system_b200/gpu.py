@@ -58,14 +58,19 @@ class GpuContext:
             flags = np.ascontiguousarray(flags, dtype=np.uint8)
             self._ck(self.lib.fspann_deleted_set(self.ctx, N.ptr(flags), C.c_int64(flags.shape[0])))
 
-    def store_upload(self, dim, iv, ct, key_version):
+    def store_upload(self, dim, iv, ct, key_version, id_base: int = 0, n_global: int | None = None):
+        """Whole store (default) or the shard of global ids [id_base, id_base + len(iv)) of an n_global-record store."""
         iv = np.ascontiguousarray(iv, dtype=np.uint8)
         ct = np.ascontiguousarray(ct, dtype=np.uint8)
         key_version = np.ascontiguousarray(key_version, dtype=np.int32)
         n = iv.shape[0]
         assert iv.shape == (n, 12) and ct.shape == (n, 8 * dim + 16) and key_version.shape == (n,)
-        self._ck(self.lib.fspann_store_upload(self.ctx, C.c_int64(n), dim, N.ptr(iv), N.ptr(ct), N.ptr(key_version)))
+        if n_global is None:
+            n_global = id_base + n
+        self._ck(self.lib.fspann_store_upload_shard(self.ctx, C.c_int64(id_base), C.c_int64(n), C.c_int64(n_global), dim, N.ptr(iv), N.ptr(ct),
+                                                    N.ptr(key_version)))
         self.N = n
+        self.id_base = id_base
         self.store_dim = dim
 
     def store_update(self, ids, iv, ct, key_version):
@@ -114,9 +119,10 @@ class GpuContext:
         nret = np.zeros(Q, dtype=np.int32)
         ver = np.full((Q, stride), 255, dtype=np.uint8)
         ndec = np.zeros(Q, dtype=np.int32)
-        self._ck(self.lib.fspann_refine_batch(self.ctx, C.c_int64(Q), N.ptr(queries), N.ptr(cand_ids), N.ptr(n_cand), C.c_int32(stride),
-                                              C.c_int32(k), N.ptr(tid), N.ptr(td), N.ptr(nret), N.ptr(ver), N.ptr(ndec)))
-        return dict(top_ids=tid, top_dist=td, n_ret=nret, verdict=ver, n_decrypted=ndec)
+        rank = np.full((Q, k), 0x7FFFFFFF, dtype=np.int32)
+        self._ck(self.lib.fspann_refine_batch_ex(self.ctx, C.c_int64(Q), N.ptr(queries), N.ptr(cand_ids), N.ptr(n_cand), C.c_int32(stride),
+                                                 C.c_int32(k), N.ptr(tid), N.ptr(td), N.ptr(rank), N.ptr(nret), N.ptr(ver), N.ptr(ndec)))
+        return dict(top_ids=tid, top_dist=td, top_rank=rank, n_ret=nret, verdict=ver, n_decrypted=ndec)
 
     def search_batch(self, queries, k, probes, hard_cap, B, ham_threshold=0, out=None):
         """Host buffers in, host buffers out.  `queries` may be a numpy array or (address, Q) of pinned memory via out=."""
@@ -151,7 +157,7 @@ class GpuContext:
         bm = np.zeros(words, dtype=np.uint32)
         self._ck(self.lib.fspann_touched_fetch(self.ctx, N.ptr(bm), C.c_int64(words), C.c_int32(1 if clear else 0)))
         bits = np.unpackbits(bm.view(np.uint8), bitorder="little")[: self.N]
-        return np.nonzero(bits)[0].astype(np.int32)
+        return (np.nonzero(bits)[0] + getattr(self, "id_base", 0)).astype(np.int32)
 
     def stage_ms(self):
         out = (C.c_float * 6)()

@@ -49,6 +49,7 @@ extern "C" {
 #define FSPANN_V_NO_KEY 2     /* keyService.getVersion threw: version unknown or retired (KRS:82-88)           */
 #define FSPANN_V_TAG_FAIL 3   /* AES-GCM tag mismatch (AGC:159-165)                                            */
 #define FSPANN_V_NON_FINITE 4 /* plaintext holds NaN/Inf (QSI:253, QSI:407-413)                                */
+#define FSPANN_V_OTHER_SHARD 0xFD /* sharded store only: the record is held by another GPU                       */
 
 #define FSPANN_BLOCK 64       /* DEFAULT_GREEDY_BLOCK_SIZE (PIS:92) */
 #define FSPANN_MAX_KEYS 16    /* live key versions held on the device */
@@ -99,6 +100,11 @@ int fspann_deleted_set(fspann_ctx *ctx, const uint8_t *flags, int64_t n);
  *   key_version int32 [N].  Replaces RocksDBMetadataManager.loadEncryptedPoint (RDB:530-544) on the hot path. */
 int fspann_store_upload(fspann_ctx *ctx, int64_t N, int32_t dim, const uint8_t *iv, const uint8_t *ct,
                         const int32_t *key_version);
+/* Database-sharded deployment (BASELINE config 4): this context holds only the records with global ids
+ * [id_base, id_base + N) of a store whose ids span [0, n_global).  AAD and candidate ids stay GLOBAL; a candidate that
+ * lives in another shard gets verdict 0xFD here and is refined by its owner.  fspann_store_upload = shard (0, N, N). */
+int fspann_store_upload_shard(fspann_ctx *ctx, int64_t id_base, int64_t N, int64_t n_global, int32_t dim,
+                              const uint8_t *iv, const uint8_t *ct, const int32_t *key_version);
 /* In-place replacement of n records: the result of Migrate = reencryptTouched (KRS:250-266).  Atomic with
  * respect to later batches (stream ordered). */
 int fspann_store_update(fspann_ctx *ctx, int64_t n, const int32_t *ids, const uint8_t *iv, const uint8_t *ct,
@@ -133,6 +139,13 @@ int fspann_route_batch(fspann_ctx *ctx, int64_t Q, const uint64_t *codes, int32_
 int fspann_refine_batch(fspann_ctx *ctx, int64_t Q, const double *queries, const int32_t *cand_ids,
                         const int32_t *n_cand, int32_t cand_stride, int32_t k, int32_t *topk_ids_out,
                         double *topk_dist_out, int32_t *n_ret_out, uint8_t *verdict_out, int32_t *n_decrypted_out);
+
+/* Same, plus topk_rank_out [Q][k]: the position of each result in its candidate list.  Per-shard results are merged
+ * across GPUs on (distance, rank), which reproduces the reference's stable sort (QSI:298) exactly. */
+int fspann_refine_batch_ex(fspann_ctx *ctx, int64_t Q, const double *queries, const int32_t *cand_ids,
+                           const int32_t *n_cand, int32_t cand_stride, int32_t k, int32_t *topk_ids_out,
+                           double *topk_dist_out, int32_t *topk_rank_out, int32_t *n_ret_out, uint8_t *verdict_out,
+                           int32_t *n_decrypted_out);
 
 /* ---- search (a4-a18): createToken + QueryServiceImpl.search for a batch, incl. the adaptive retry (QSI:327-337):
  * a query whose first pass returned < k results or decrypted < 10*k candidates is re-run once with 10 probes and
