@@ -381,6 +381,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) refine_decrypt_kernel(const __g
 
     const AesFast te{base_sa + pad + (uint32_t)lane * 4u};
     double *pt_row = pt_all + (size_t)warp * dim_pad;
+    const bool use_f32 = p.queries_f32 != nullptr && (dim & 3) == 0 && *p.f32_exact != 0;
     const int n_uniq = p.totals[1];
     const int n_chunks = (n_uniq + 31) >> 5;
 
@@ -425,7 +426,40 @@ __global__ void __launch_bounds__(RF_THREADS, 1) refine_decrypt_kernel(const __g
                 if (verdict == FSPANN_V_OK) {
                     const double *qv = p.queries + (size_t)(pair / (uint32_t)p.stride) * dim;
                     double s = 0.0;                                           // QSI:364-372, strict FP64, index order
-                    if ((dim & 1) == 0) {
+                    if (use_f32) {
+                        // every query value is exactly representable in FP32 (the reference's loaders read float32 and widen,
+                        // FvecsLoader.java:27-30): read the compact FP32 copy -- half the bytes through L1 -- and widen back;
+                        // the FP64 arithmetic is unchanged, so the distance is bit-identical
+                        const float4 *q4 = reinterpret_cast<const float4 *>(p.queries_f32 + (size_t)(pair / (uint32_t)p.stride) * dim);
+                        const double2 *v2 = reinterpret_cast<const double2 *>(pt_row);
+                        const int n4 = dim >> 2;
+                        int i = 0;
+                        for (; i + 8 <= n4; i += 8) {
+                            float4 qq[8];
+#pragma unroll
+                            for (int u = 0; u < 8; u++) qq[u] = __ldg(q4 + i + u);
+#pragma unroll
+                            for (int u = 0; u < 8; u++) {
+                                const double2 va = v2[2 * (i + u)], vb = v2[2 * (i + u) + 1];
+                                const double d0 = __dsub_rn((double)qq[u].x, va.x), d1 = __dsub_rn((double)qq[u].y, va.y);
+                                const double d2 = __dsub_rn((double)qq[u].z, vb.x), d3 = __dsub_rn((double)qq[u].w, vb.y);
+                                s = __dadd_rn(s, __dmul_rn(d0, d0));
+                                s = __dadd_rn(s, __dmul_rn(d1, d1));
+                                s = __dadd_rn(s, __dmul_rn(d2, d2));
+                                s = __dadd_rn(s, __dmul_rn(d3, d3));
+                            }
+                        }
+                        for (; i < n4; i++) {
+                            const float4 q1 = __ldg(q4 + i);
+                            const double2 va = v2[2 * i], vb = v2[2 * i + 1];
+                            const double d0 = __dsub_rn((double)q1.x, va.x), d1 = __dsub_rn((double)q1.y, va.y);
+                            const double d2 = __dsub_rn((double)q1.z, vb.x), d3 = __dsub_rn((double)q1.w, vb.y);
+                            s = __dadd_rn(s, __dmul_rn(d0, d0));
+                            s = __dadd_rn(s, __dmul_rn(d1, d1));
+                            s = __dadd_rn(s, __dmul_rn(d2, d2));
+                            s = __dadd_rn(s, __dmul_rn(d3, d3));
+                        }
+                    } else if ((dim & 1) == 0) {
                         // 128-bit loads, 16 values in flight per lane; the adds stay strictly sequential
                         const double2 *q2 = reinterpret_cast<const double2 *>(qv);
                         const double2 *v2 = reinterpret_cast<const double2 *>(pt_row);
@@ -475,6 +509,25 @@ int launch_refine_decrypt(cudaStream_t s, const StoreView &sv, const RefineParam
         configured = smem;
     }
     refine_decrypt_kernel<<<sm_count, RF_THREADS, smem, s>>>(*sv.keys_host, sv, p);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// FP32 copy of the query batch + a flag telling whether every value survived the round trip exactly.
+__global__ void queries_to_f32_kernel(const double *__restrict__ q, float *__restrict__ out, int64_t n, int32_t *exact) {
+    bool ok = true;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double v = q[i];
+        const float f = (float)v;
+        out[i] = f;
+        ok &= (double)f == v;
+    }
+    if (!__all_sync(0xffffffffu, ok) && (threadIdx.x & 31) == 0) atomicAnd(exact, 0);
+}
+int launch_queries_to_f32(cudaStream_t s, const double *q, float *out, int64_t n, int32_t *exact) {
+    if (n <= 0) return 0;
+    if (cudaMemsetAsync(exact, 0xff, sizeof(int32_t), s) != cudaSuccess) return -1;
+    int grid = (int)((n + 255) / 256); if (grid > 148 * 8) grid = 148 * 8;
+    queries_to_f32_kernel<<<grid, 256, 0, s>>>(q, out, n, exact);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

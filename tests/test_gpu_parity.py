@@ -116,3 +116,21 @@ def test_search_batch_matches_reference_search(wg, k, B):
         c = got["counters"][q]
         assert (c[0], c[1], c[2], c[3], bool(c[4])) == (ref["cand_total"], ref["cand_kept"], ref["cand_decrypted"], ref["returned"], ref["retried"])
     assert np.array_equal(ctx.touched(clear=True), np.nonzero(touched_ref)[0])
+
+
+def test_distance_paths_fp32_exact_and_general_fp64(wg):
+    """The distance phase reads a compact FP32 copy of the queries when every value is FP32-representable (the reference's
+    loaders widen float32 input), otherwise the FP64 rows: both must give the oracle's FP64 bits."""
+    w, ctx = wg
+    rng = np.random.default_rng(8)
+    assert np.array_equal(w.queries.astype(np.float32).astype(np.float64), w.queries)
+    q64 = w.queries + rng.normal(0, 1e-9, size=w.queries.shape)          # not representable in FP32
+    assert not np.array_equal(q64.astype(np.float32).astype(np.float64), q64)
+    for queries in (w.queries, q64):
+        got = ctx.search_batch(queries, 10, 5, 20000, 128)
+        codes = O.tokengen_batch(queries, w.g)
+        for q in range(queries.shape[0]):
+            ref = O.search(w.ix, w.store, queries[q], codes[q], 10, 5, 20000, 128)
+            n = len(ref["top_ids"])
+            assert got["n_ret"][q] == n and np.array_equal(got["top_ids"][q, :n], ref["top_ids"])
+            assert np.array_equal(got["top_dist"][q, :n].view(np.uint64), ref["top_dist"].view(np.uint64))
