@@ -475,7 +475,7 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) route_fast_kernel(RoutingView r
             vlen_s[v] = valid ? (uint8_t)min((int64_t)kBlock, n_ids - row) : 0;
             vs_s[v] = valid ? x.vis_score[vi] : 255;
         }
-        for (int i = tid; i < tbl / 2; i += RQ_THREADS) table_w[i] = 0xffffffffu;
+        for (int i = tid; i < tbl / 2; i += RQ_THREADS) table_w[i] = 0u;            // the region first serves as the duplicate filter
         if (tid < 256) s_hist[tid] = 0;
         if (tid == 0) { s_raw = 0; s_uniq = 0; s_m = 0; s_ncls = 0; }
         __syncthreads();
@@ -492,51 +492,104 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) route_fast_kernel(RoutingView r
             best_s[e] = 255;
         }
         __syncthreads();
-        // ---- 3. insert (open addressing, double hashing): table[slot] = newest position holding that id; each position links
-        //         to the previous newest one; the FIRST arrival's link is the terminator 0x8000|slot, so later phases find the
-        //         slot of any position by following its (short) chain instead of probing again ----
-        for (int e = tid; e < n_raw; e += RQ_THREADS) {
-            const int32_t id = ids_s[e];
-            if (id < 0) continue;
-            const uint32_t h = (uint32_t)id * 0x9E3779B1u;
-            uint32_t slot = h >> tshift;
-            const uint32_t step = ((h >> 7) | 1u) & tmask;             // odd => visits every slot of the power-of-two table
-            for (;;) {
-                uint32_t cur = *reinterpret_cast<volatile uint16_t *>(&table[slot]);
-                if (cur == RQ_EMPTY) {
-                    next_s[e] = (uint16_t)(0x8000u | slot);
-                    cur = cas16(table_w, slot, RQ_EMPTY, (uint32_t)e);
-                    if (cur == RQ_EMPTY) break;                       // claimed an empty slot: first arrival
-                }
-                if (ids_s[cur] == id) {                               // same id: become the newest element of its chain
-                    for (;;) {
-                        next_s[e] = (uint16_t)cur;
-                        const uint32_t prev = cas16(table_w, slot, cur, (uint32_t)e);
-                        if (prev == cur) break;
-                        cur = prev;                                   // still the same id (slots never change owner)
-                    }
-                    break;
-                }
-                slot = (slot + step) & tmask;
+        // ---- 3. duplicate filter.  ~95 % of the visited ids occur once, so the exact (hash-table + chain) machinery is only run on
+        //         the positions a 2-bit-per-bucket filter cannot clear: bit0 = "bucket taken", bit1 = "taken twice".  The filter
+        //         lives in the table region (8*tbl buckets); a position whose bucket never collided is the only occurrence of its id.
+        int my_raw = 0, my_uniq = 0, my_inv = 0;
+        {
+            uint32_t *F = table_w;
+            int fshift = 32; while ((1u << (32 - fshift)) < (uint32_t)tbl * 8u) fshift--;
+            for (int e = tid; e < n_raw; e += RQ_THREADS) {
+                const int32_t id = ids_s[e];
+                if (id < 0) continue;
+                const uint32_t h = ((uint32_t)id * 0x9E3779B1u) >> fshift;
+                const uint32_t sh = (h & 15u) * 2u;
+                const uint32_t old = atomicOr(&F[h >> 4], 1u << sh);
+                if ((old >> sh) & 1u) atomicOr(&F[h >> 4], 2u << sh);
             }
+            __syncthreads();
+            for (int e0 = 0; e0 < n_raw; e0 += RQ_THREADS) {
+                const int e = e0 + tid;
+                const int32_t id = e < n_raw ? ids_s[e] : -1;
+                bool single = false; uint32_t sc = 255;
+                if (id >= 0) {
+                    const uint32_t h = ((uint32_t)id * 0x9E3779B1u) >> fshift;
+                    if ((F[h >> 4] >> ((h & 15u) * 2u)) & 2u) { best_s[e] = 254; my_inv++; }      // needs the exact path
+                    else { single = true; sc = vs_s[e >> 6]; best_s[e] = (uint8_t)sc; my_raw++; my_uniq++; }
+                }
+                hist_add(s_hist, single, (int)sc, lane);
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) my_inv += __shfl_xor_sync(0xffffffffu, my_inv, o);
+            if (lane == 0 && my_inv) atomicAdd(&s_ncls, my_inv);
+            __syncthreads();
         }
+        const int n_inv = s_ncls;
         __syncthreads();
-        // ---- 4. finalise, one thread per POSITION (dense): every occurrence walks its id's (short) chain once and decides
-        //         (a) whether it strictly improved on all earlier visits of the id (PIS:747 -> lastRawVisited) and
-        //         (b) whether it is the first occurrence (= HashMap insertion order); the first one records the min score.
-        int my_raw = 0, my_uniq = 0;
-        for (int e0 = 0; e0 < n_raw; e0 += RQ_THREADS) {
-            const int e = e0 + tid;
-            const int32_t id = e < n_raw ? ids_s[e] : -1;
-            bool is_rep = false; uint32_t best = 255;
-            if (id >= 0) {
-                const uint32_t sc = vs_s[e >> 6];
-                uint32_t lk = next_s[e];
-                while (!(lk & 0x8000u)) lk = next_s[lk];               // terminator carries the slot
-                const uint32_t head = table[lk & 0x7fffu];
-                if (head == (uint32_t)e && (next_s[e] & 0x8000u)) {    // the only occurrence of this id (the common case)
-                    my_raw++; is_rep = true; best = sc;
-                } else {
+        if (tid == 0) s_ncls = 0;
+        // ---- 4. exact path on the involved positions: open addressing (double hashing) keyed by id, table[slot] = newest position
+        //         holding that id, every position links to the previous newest one, the FIRST arrival's link is the terminator
+        //         0x8000|slot (so the slot of any position is found by following its short chain).  Then every occurrence walks
+        //         its id's chain once: (a) did it strictly improve on all earlier visits (PIS:747 -> lastRawVisited), (b) is it the
+        //         first occurrence (= HashMap insertion order); the first one records the id's min score.
+        if (n_inv > 0) {
+            int tslots = 1024; while (tslots < 2 * n_inv && tslots < tbl) tslots <<= 1;
+            const bool use_wl = tslots + n_inv <= tbl;                 // room for a dense worklist behind the table?
+            uint16_t *wl = table + tslots;
+            const uint32_t smask = (uint32_t)tslots - 1u;
+            int sshift = 32; while ((1u << (32 - sshift)) < (uint32_t)tslots) sshift--;
+            for (int i = tid; i < tslots / 2; i += RQ_THREADS) table_w[i] = 0xffffffffu;
+            __syncthreads();
+            if (use_wl) {
+                for (int e0 = 0; e0 < n_raw; e0 += RQ_THREADS) {
+                    const int e = e0 + tid;
+                    const bool in = e < n_raw && best_s[e] == 254;
+                    const unsigned bal = __ballot_sync(0xffffffffu, in);
+                    int base = 0;
+                    if (lane == 0 && bal) base = atomicAdd(&s_ncls, __popc(bal));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (in) wl[base + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)e;
+                }
+                __syncthreads();
+            }
+            const int n_dom = use_wl ? n_inv : n_raw;
+            for (int i = tid; i < n_dom; i += RQ_THREADS) {
+                const int e = use_wl ? (int)wl[i] : i;
+                if (!use_wl && best_s[e] != 254) continue;
+                const int32_t id = ids_s[e];
+                const uint32_t h = (uint32_t)id * 0x9E3779B1u;
+                uint32_t slot = h >> sshift;
+                const uint32_t step = ((h >> 7) | 1u) & smask;         // odd => visits every slot of the power-of-two table
+                for (;;) {
+                    uint32_t cur = *reinterpret_cast<volatile uint16_t *>(&table[slot]);
+                    if (cur == RQ_EMPTY) {
+                        next_s[e] = (uint16_t)(0x8000u | slot);
+                        cur = cas16(table_w, slot, RQ_EMPTY, (uint32_t)e);
+                        if (cur == RQ_EMPTY) break;                   // claimed an empty slot: first arrival
+                    }
+                    if (ids_s[cur] == id) {                           // same id: become the newest element of its chain
+                        for (;;) {
+                            next_s[e] = (uint16_t)cur;
+                            const uint32_t prev = cas16(table_w, slot, cur, (uint32_t)e);
+                            if (prev == cur) break;
+                            cur = prev;                               // still the same id (slots never change owner)
+                        }
+                        break;
+                    }
+                    slot = (slot + step) & smask;
+                }
+            }
+            __syncthreads();
+            for (int i0 = 0; i0 < n_dom; i0 += RQ_THREADS) {
+                const int i = i0 + tid;
+                int e = -1;
+                if (i < n_dom) { e = use_wl ? (int)wl[i] : i; if (!use_wl && best_s[e] != 254) e = -1; }
+                bool is_rep = false; uint32_t best = 255;
+                if (e >= 0) {
+                    const uint32_t sc = vs_s[e >> 6];
+                    uint32_t lk = next_s[e];
+                    while (!(lk & 0x8000u)) lk = next_s[lk];           // terminator carries the slot
+                    const uint32_t head = table[lk & 0x7fffu];
                     uint32_t first = head; bool low = true;
                     for (uint32_t y = head;;) {
                         const uint32_t sy = vs_s[y >> 6];
@@ -549,10 +602,11 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) route_fast_kernel(RoutingView r
                     my_raw += low;
                     is_rep = first == (uint32_t)e;
                 }
-                if (is_rep) { my_uniq++; best_s[e] = (uint8_t)best; }
+                hist_add(s_hist, is_rep, (int)best, lane);
+                if (e >= 0) { my_uniq += is_rep; best_s[e] = (uint8_t)(is_rep ? best : 255u); }   // chain walks never read best_s
             }
-            hist_add(s_hist, is_rep, (int)best, lane);
         }
+        if (tid == 0) s_ncls = 0;                                      // reused below for the cut-class list
 #pragma unroll
         for (int o = 16; o; o >>= 1) { my_raw += __shfl_xor_sync(0xffffffffu, my_raw, o); my_uniq += __shfl_xor_sync(0xffffffffu, my_uniq, o); }
         if (lane == 0) { atomicAdd(&s_raw, my_raw); atomicAdd(&s_uniq, my_uniq); }
