@@ -185,14 +185,16 @@ static inline u128 gf128_mul_ref(const u128 &x, const u128 &y) {
 }
 
 // Shoup 8-bit tables for multiplication by a fixed H: T[j][b] = (byte b at byte position j of a block) * H, so
-// V * H = XOR_j T[j][byte_j(V)].  4096 entries of 4 big-endian words (64 KB per key version).  Host side.
-static inline void ghash_make_shoup8(const u128 &H, uint32_t *table /* [16][256][4] */) {
+// V * H = XOR_j T[j][byte_j(V)].  4096 entries of 4 big-endian words (64 KB per key version), stored BYTE-major:
+// entry (b, j) at index b*16 + j.  Its 16-byte bank group is then j mod 8, so a warp whose lanes walk the 16 byte
+// positions in lane-rotated order reads shared memory without bank conflicts.  Host side.
+static inline void ghash_make_shoup8(const u128 &H, uint32_t *table /* [256][16][4] */) {
     for (int j = 0; j < 16; j++)
         for (int b = 0; b < 256; b++) {
             u128 v{0, 0};
             if (j < 8) v.hi = (uint64_t)b << (56 - 8 * j); else v.lo = (uint64_t)b << (56 - 8 * (j - 8));
             const u128 z = gf128_mul_ref(v, H);
-            uint32_t *t = table + ((size_t)j * 256 + b) * 4;
+            uint32_t *t = table + ((size_t)b * 16 + j) * 4;
             t[0] = (uint32_t)(z.hi >> 32); t[1] = (uint32_t)z.hi; t[2] = (uint32_t)(z.lo >> 32); t[3] = (uint32_t)z.lo;
         }
 }

@@ -43,7 +43,7 @@ int fsp_hc_shoup_check(const uint64_t *h, const uint64_t *xs, int n) {
         uint32_t y[4] = {(uint32_t)(x.hi >> 32), (uint32_t)x.hi, (uint32_t)(x.lo >> 32), (uint32_t)x.lo}, z[4] = {0, 0, 0, 0};
         for (int j = 0; j < 16; j++) {
             const uint32_t b = (y[j / 4] >> (24 - 8 * (j % 4))) & 0xff;
-            for (int k = 0; k < 4; k++) z[k] ^= tab[((size_t)j * 256 + b) * 4 + k];
+            for (int k = 0; k < 4; k++) z[k] ^= tab[((size_t)b * 16 + j) * 4 + k];
         }
         if (z[0] != (uint32_t)(ref.hi >> 32) || z[1] != (uint32_t)ref.hi || z[2] != (uint32_t)(ref.lo >> 32) || z[3] != (uint32_t)ref.lo) bad++;
     }

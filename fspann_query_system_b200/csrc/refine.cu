@@ -259,15 +259,28 @@ __device__ __forceinline__ bool warp_decrypt_record(const StoreView &sv, const u
 constexpr int VF_THREADS = 384;
 
 struct ShoupSmem {
-    const uint4 *t;
+    const uint4 *t;   // [256][16] byte-major
+    int rot;          // lane & 15: this lane visits byte positions rot, rot+1, ... (mod 16)
+    // y <- y * H.  The 16 table look-ups are XOR-accumulated in a lane-rotated order: at step s lane l reads byte position
+    // (s + l) mod 16, whose entries sit in bank group (s + l) mod 8 -- distinct for the 8 lanes of a quarter warp.
     __device__ __forceinline__ void mul(uint32_t &y0, uint32_t &y1, uint32_t &y2, uint32_t &y3) const {
-        uint4 z = t[y0 >> 24];
-        uint4 u;
-#define FSP_ACC(j, idx) u = t[(j) * 256 + (idx)]; z.x ^= u.x; z.y ^= u.y; z.z ^= u.z; z.w ^= u.w;
-        FSP_ACC(1, (y0 >> 16) & 0xff) FSP_ACC(2, (y0 >> 8) & 0xff) FSP_ACC(3, y0 & 0xff)
-        FSP_ACC(4, y1 >> 24) FSP_ACC(5, (y1 >> 16) & 0xff) FSP_ACC(6, (y1 >> 8) & 0xff) FSP_ACC(7, y1 & 0xff)
-        FSP_ACC(8, y2 >> 24) FSP_ACC(9, (y2 >> 16) & 0xff) FSP_ACC(10, (y2 >> 8) & 0xff) FSP_ACC(11, y2 & 0xff)
-        FSP_ACC(12, y3 >> 24) FSP_ACC(13, (y3 >> 16) & 0xff) FSP_ACC(14, (y3 >> 8) & 0xff) FSP_ACC(15, y3 & 0xff)
+        // rotate the 16-byte vector left by `rot` bytes: whole words first (two conditional stages), then bytes
+        uint32_t a0 = y0, a1 = y1, a2 = y2, a3 = y3;
+        if (rot & 4) { const uint32_t t0 = a0; a0 = a1; a1 = a2; a2 = a3; a3 = t0; }
+        if (rot & 8) { const uint32_t t0 = a0, t1 = a1; a0 = a2; a1 = a3; a2 = t0; a3 = t1; }
+        const int sh = (rot & 3) * 8;
+        const uint32_t w0 = __funnelshift_l(a1, a0, sh), w1 = __funnelshift_l(a2, a1, sh), w2 = __funnelshift_l(a3, a2, sh),
+                       w3 = __funnelshift_l(a0, a3, sh);
+        const char *base = reinterpret_cast<const char *>(t);
+        const uint32_t r16 = (uint32_t)rot * 16u;
+        uint4 z = make_uint4(0, 0, 0, 0), u;
+        // byte s of the rotated vector is byte (s + rot) & 15 of y; entry (b, j) lives at byte offset b*256 + j*16
+#define FSP_ACC(st, wd, kb) u = *reinterpret_cast<const uint4 *>(base + __byte_perm((wd), 0, 0x4404 | ((kb) << 4)) + ((r16 + (st) * 16u) & 0xf0u)); \
+                         z.x ^= u.x; z.y ^= u.y; z.z ^= u.z; z.w ^= u.w;
+        FSP_ACC(0, w0, 3) FSP_ACC(1, w0, 2) FSP_ACC(2, w0, 1) FSP_ACC(3, w0, 0)
+        FSP_ACC(4, w1, 3) FSP_ACC(5, w1, 2) FSP_ACC(6, w1, 1) FSP_ACC(7, w1, 0)
+        FSP_ACC(8, w2, 3) FSP_ACC(9, w2, 2) FSP_ACC(10, w2, 1) FSP_ACC(11, w2, 0)
+        FSP_ACC(12, w3, 3) FSP_ACC(13, w3, 2) FSP_ACC(14, w3, 1) FSP_ACC(15, w3, 0)
 #undef FSP_ACC
         y0 = z.x; y1 = z.y; y2 = z.z; y3 = z.w;
     }
@@ -326,7 +339,7 @@ __global__ void __launch_bounds__(VF_THREADS) refine_verify_kernel(StoreView sv,
     for (int i = tid; i < nkeys * 60; i += VF_THREADS) s_rk[i] = sv.keys->rk[i / 60][i % 60];
     for (int i = tid; i < kMaxKeys; i += VF_THREADS) s_ver[i] = i < nkeys ? sv.keys->version[i] : INT32_MIN;
     const TeSmem te{te_s + lane};
-    const ShoupSmem sh{shoup_s};
+    const ShoupSmem sh{shoup_s, lane & 15};
     const int n_uniq = p.totals[1];
     const int n_chunks = (n_uniq + 31) >> 5;
     const int warps_total = gridDim.x * (VF_THREADS / 32);
@@ -691,7 +704,7 @@ __global__ void __launch_bounds__(DBG_THREADS) debug_decrypt_kernel(StoreView sv
             else {
                 // lane 0 authenticates with the Shoup table read from global memory (debug path, speed irrelevant)
                 bool ok = false;
-                if (lane == 0) ok = lane_verify_record(sv, rec, id, hdr, ShoupSmem{sv.shoup + (size_t)slot * 4096}, te, RkSmem{s_rk + slot * 60});
+                if (lane == 0) ok = lane_verify_record(sv, rec, id, hdr, ShoupSmem{sv.shoup + (size_t)slot * 4096, 0}, te, RkSmem{s_rk + slot * 60});
                 ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
                 if (!ok) v = FSPANN_V_TAG_FAIL;
                 else v = warp_decrypt_record(sv, rec, hdr, slot, AesPlain{te}, s_rk, pt_row, lane) ? FSPANN_V_OK : FSPANN_V_NON_FINITE;
