@@ -45,7 +45,7 @@ struct fspann_ctx {
     int opt_route_general = 0;   // force the general (sequential, cap-exact) Route kernel
     int last_route_path = 0;     // 1 = shared-memory fast path, 2 = general path
     DevBuf s_queries, s_codes, s_cand_ids, s_cand_sc, s_ncand, s_raw, s_uniq_cnt, s_route_scratch, s_overflow;
-    DevBuf s_rec_verdict, s_qf32, s_f32_exact;
+    DevBuf s_rec_verdict, s_qf32, s_qu8, s_f32_exact;
     DevKeyRing ring_host{};
     int32_t *want_rank = nullptr;
     DevBuf s_cnt, s_flag, s_fill, s_uniq, s_pairs, s_bsums, s_totals, s_dist, s_verdict;
@@ -231,9 +231,10 @@ int do_refine(fspann_ctx *ctx, int64_t Q, const double *d_queries, const int32_t
     p.rec_verdict = (uint8_t *)ctx->s_rec_verdict.p;
     p.topk_ids = d_topk_ids; p.topk_dist = d_topk_dist; p.n_ret = d_nret; p.n_dec = d_ndec; p.topk_rank = ctx->want_rank;
     ENSURE(ctx->s_qf32, sizeof(float) * (size_t)Q * sv.dim);
-    ENSURE(ctx->s_f32_exact, sizeof(int32_t));
-    p.queries_f32 = (const float *)ctx->s_qf32.p; p.f32_exact = (const int32_t *)ctx->s_f32_exact.p;
-    LAUNCHED(launch_queries_to_f32(ctx->stream, d_queries, (float *)ctx->s_qf32.p, Q * (int64_t)sv.dim, (int32_t *)ctx->s_f32_exact.p));
+    ENSURE(ctx->s_qu8, (size_t)Q * sv.dim + 16);
+    ENSURE(ctx->s_f32_exact, 2 * sizeof(int32_t));
+    p.queries_f32 = (const float *)ctx->s_qf32.p; p.queries_u8 = (const uint8_t *)ctx->s_qu8.p; p.f32_exact = (const int32_t *)ctx->s_f32_exact.p;
+    LAUNCHED(launch_queries_to_f32(ctx->stream, d_queries, (float *)ctx->s_qf32.p, (uint8_t *)ctx->s_qu8.p, Q * (int64_t)sv.dim, (int32_t *)ctx->s_f32_exact.p));
     // unknown / retired key version is the default verdict (KRS:82-88); the verify kernel overwrites it per live version
     CK(cudaMemsetAsync(p.rec_verdict, FSPANN_V_NO_KEY, (size_t)std::min<int64_t>(n1, total + 1), ctx->stream));
     LAUNCHED(launch_refine_group(ctx->stream, sv, p));
@@ -286,7 +287,7 @@ void fspann_ctx_destroy(fspann_ctx *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->d_alpha, &ctx->d_r, &ctx->d_omega, &ctx->d_keys, &ctx->d_rep, &ctx->d_ids, &ctx->d_deleted, &ctx->d_rec,
-                      &ctx->d_keyring, &ctx->d_hpow, &ctx->d_shoup, &ctx->s_rec_verdict, &ctx->s_qf32, &ctx->s_f32_exact, &ctx->d_te0, &ctx->d_touched, &ctx->s_queries, &ctx->s_codes, &ctx->s_cand_ids,
+                      &ctx->d_keyring, &ctx->d_hpow, &ctx->d_shoup, &ctx->s_rec_verdict, &ctx->s_qf32, &ctx->s_qu8, &ctx->s_f32_exact, &ctx->d_te0, &ctx->d_touched, &ctx->s_queries, &ctx->s_codes, &ctx->s_cand_ids,
                       &ctx->s_cand_sc, &ctx->s_ncand, &ctx->s_raw, &ctx->s_uniq_cnt, &ctx->s_route_scratch, &ctx->s_overflow, &ctx->s_cnt,
                       &ctx->s_flag, &ctx->s_fill, &ctx->s_uniq, &ctx->s_pairs, &ctx->s_bsums, &ctx->s_totals, &ctx->s_dist, &ctx->s_verdict,
                       &ctx->s_topk_ids, &ctx->s_topk_dist, &ctx->s_topk_rank, &ctx->s_nret, &ctx->s_ndec, &ctx->s_counters, &ctx->s_stage_a, &ctx->s_stage_b,

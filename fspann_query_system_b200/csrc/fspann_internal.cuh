@@ -80,7 +80,8 @@ struct RefineParams {
     int64_t Q;
     const double *queries;    // [Q][dim]
     const float *queries_f32; // [Q][dim] compact copy (or nullptr); valid for distances only when *f32_exact != 0
-    const int32_t *f32_exact;
+    const uint8_t *queries_u8; // [Q][dim] uint8 copy; valid when f32_exact[1] != 0 (all values are integers 0..255)
+    const int32_t *f32_exact;  // [2]: {FP32 copy exact, uint8 copy exact}
     const int32_t *cand_ids;  // [Q][stride]
     const int32_t *n_cand;    // [Q]
     int32_t stride, k;
@@ -114,7 +115,7 @@ int64_t route_scratch_ints(int32_t cap0, int32_t max_nodes);
 int launch_refine_group(cudaStream_t s, const StoreView &sv, const RefineParams &p);
 int launch_refine_verify(cudaStream_t s, const StoreView &sv, const RefineParams &p, int sm_count);
 int launch_refine_decrypt(cudaStream_t s, const StoreView &sv, const RefineParams &p, int sm_count);
-int launch_queries_to_f32(cudaStream_t s, const double *q, float *out, int64_t n, int32_t *exact);
+int launch_queries_to_f32(cudaStream_t s, const double *q, float *out, uint8_t *out8, int64_t n, int32_t *exact);
 int launch_refine_topk(cudaStream_t s, const RefineParams &p);
 int launch_counters(cudaStream_t s, int64_t Q, const int32_t *raw, const int32_t *uniq, const int32_t *n_dec,
                     const int32_t *n_ret, const int32_t *n_cand, int32_t retried, int64_t *counters);

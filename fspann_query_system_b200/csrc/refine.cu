@@ -394,7 +394,8 @@ __global__ void __launch_bounds__(RF_THREADS, 1) refine_decrypt_kernel(const __g
 
     const AesFast te{base_sa + pad + (uint32_t)lane * 4u};
     double *pt_row = pt_all + (size_t)warp * dim_pad;
-    const bool use_f32 = p.queries_f32 != nullptr && (dim & 3) == 0 && *p.f32_exact != 0;
+    const bool use_u8 = p.queries_u8 != nullptr && (dim & 15) == 0 && p.f32_exact[1] != 0;
+    const bool use_f32 = p.queries_f32 != nullptr && (dim & 3) == 0 && p.f32_exact[0] != 0;
     const int n_uniq = p.totals[1];
     const int n_chunks = (n_uniq + 31) >> 5;
 
@@ -439,7 +440,38 @@ __global__ void __launch_bounds__(RF_THREADS, 1) refine_decrypt_kernel(const __g
                 if (verdict == FSPANN_V_OK) {
                     const double *qv = p.queries + (size_t)(pair / (uint32_t)p.stride) * dim;
                     double s = 0.0;                                           // QSI:364-372, strict FP64, index order
-                    if (use_f32) {
+                    if (use_u8) {
+                        // every query value is an integer in [0, 255] (SIFT / .bvecs descriptors, loader/BvecsLoader): one 128-byte
+                        // line holds 128 dimensions, an eighth of the FP64 row.  Bytes are widened exactly (2^52 magic constant);
+                        // the FP64 arithmetic is unchanged, so the distance is bit-identical.
+                        const uint4 *q16 = reinterpret_cast<const uint4 *>(p.queries_u8 + (size_t)(pair / (uint32_t)p.stride) * dim);
+                        const double2 *v2 = reinterpret_cast<const double2 *>(pt_row);
+                        const int n16 = dim >> 4;
+                        for (int i0 = 0; i0 < n16; i0 += 8) {
+                            uint4 qq[8];
+#pragma unroll
+                            for (int u = 0; u < 8; u++) qq[u] = (i0 + u < n16) ? __ldg(q16 + i0 + u) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+                            for (int u = 0; u < 8; u++) {
+                                if (i0 + u < n16) {
+                                    const uint32_t wds[4] = {qq[u].x, qq[u].y, qq[u].z, qq[u].w};
+#pragma unroll
+                                    for (int c4 = 0; c4 < 4; c4++) {
+                                        const double2 va = v2[8 * (i0 + u) + 2 * c4], vb = v2[8 * (i0 + u) + 2 * c4 + 1];
+                                        const double q0 = __hiloint2double(0x43300000, (int)(wds[c4] & 0xffu)) - 4503599627370496.0;
+                                        const double q1 = __hiloint2double(0x43300000, (int)((wds[c4] >> 8) & 0xffu)) - 4503599627370496.0;
+                                        const double q2 = __hiloint2double(0x43300000, (int)((wds[c4] >> 16) & 0xffu)) - 4503599627370496.0;
+                                        const double q3 = __hiloint2double(0x43300000, (int)(wds[c4] >> 24)) - 4503599627370496.0;
+                                        const double d0 = __dsub_rn(q0, va.x), d1 = __dsub_rn(q1, va.y), d2 = __dsub_rn(q2, vb.x), d3 = __dsub_rn(q3, vb.y);
+                                        s = __dadd_rn(s, __dmul_rn(d0, d0));
+                                        s = __dadd_rn(s, __dmul_rn(d1, d1));
+                                        s = __dadd_rn(s, __dmul_rn(d2, d2));
+                                        s = __dadd_rn(s, __dmul_rn(d3, d3));
+                                    }
+                                }
+                            }
+                        }
+                    } else if (use_f32) {
                         // every query value is exactly representable in FP32 (the reference's loaders read float32 and widen,
                         // FvecsLoader.java:27-30): read the compact FP32 copy -- half the bytes through L1 -- and widen back;
                         // the FP64 arithmetic is unchanged, so the distance is bit-identical
@@ -525,22 +557,28 @@ int launch_refine_decrypt(cudaStream_t s, const StoreView &sv, const RefineParam
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
-// FP32 copy of the query batch + a flag telling whether every value survived the round trip exactly.
-__global__ void queries_to_f32_kernel(const double *__restrict__ q, float *__restrict__ out, int64_t n, int32_t *exact) {
-    bool ok = true;
+// Compact copies of the query batch (FP32 and uint8) + flags telling whether every value survived the round trip exactly:
+// exact[0] for FP32, exact[1] for uint8 (integers 0..255).
+__global__ void queries_compact_kernel(const double *__restrict__ q, float *__restrict__ out32, uint8_t *__restrict__ out8, int64_t n, int32_t *exact) {
+    bool ok32 = true, ok8 = true;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const double v = q[i];
         const float f = (float)v;
-        out[i] = f;
-        ok &= (double)f == v;
+        out32[i] = f;
+        ok32 &= (double)f == v;
+        const bool in8 = v >= 0.0 && v <= 255.0;
+        const int b = in8 ? (int)v : 0;
+        out8[i] = (uint8_t)b;
+        ok8 &= in8 && (double)b == v;
     }
-    if (!__all_sync(0xffffffffu, ok) && (threadIdx.x & 31) == 0) atomicAnd(exact, 0);
+    if (!__all_sync(0xffffffffu, ok32) && (threadIdx.x & 31) == 0) atomicAnd(&exact[0], 0);
+    if (!__all_sync(0xffffffffu, ok8) && (threadIdx.x & 31) == 0) atomicAnd(&exact[1], 0);
 }
-int launch_queries_to_f32(cudaStream_t s, const double *q, float *out, int64_t n, int32_t *exact) {
+int launch_queries_to_f32(cudaStream_t s, const double *q, float *out, uint8_t *out8, int64_t n, int32_t *exact) {
     if (n <= 0) return 0;
-    if (cudaMemsetAsync(exact, 0xff, sizeof(int32_t), s) != cudaSuccess) return -1;
+    if (cudaMemsetAsync(exact, 0xff, 2 * sizeof(int32_t), s) != cudaSuccess) return -1;
     int grid = (int)((n + 255) / 256); if (grid > 148 * 8) grid = 148 * 8;
-    queries_to_f32_kernel<<<grid, 256, 0, s>>>(q, out, n, exact);
+    queries_compact_kernel<<<grid, 256, 0, s>>>(q, out, out8, n, exact);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
