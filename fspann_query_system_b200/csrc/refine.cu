@@ -219,6 +219,56 @@ __device__ __forceinline__ void aes256_encrypt_fast(uint32_t K0, const uint32_t 
     out[3] = FSP_LAST(s3, s0, s1, s2) ^ rk[59];
 #undef FSP_LAST
 }
+
+// ---- CTR-mode specialisation: rounds 1 and 2 hoisted out of the per-block work ------------------------------------
+// Every counter block of one record is IV || ctr with the same IV, and ctr = 2 .. c+1 differs only in its low byte while
+// c <= 254 (dim <= 508).  After AddRoundKey only byte 0 of column 3 varies, so after round 1 only column 0 varies
+// (through Te3[s3.b0]) and in round 2 only the four look-ups fed by that column vary.  The 27 look-ups that depend on
+// (IV, key) alone are evaluated ONCE per record (CtrPre, one lane per record of a 32-record chunk); a block then costs
+// 1 + 4 look-ups for rounds 1-2 instead of 32 (197 per block instead of 224).
+struct CtrPre { uint32_t c0, d0, d1, d2, d3; };
+
+__device__ __forceinline__ CtrPre aes256_ctr_precompute(uint32_t K0, const uint32_t *rk, uint32_t iv0, uint32_t iv1, uint32_t iv2) {
+    const uint32_t K2 = K0 + 128u;
+    const uint32_t s0 = iv0 ^ rk[0], s1 = iv1 ^ rk[1], s2 = iv2 ^ rk[2], s3 = rk[3];     // ctr bytes 1..3 are zero
+    CtrPre o;
+    o.c0 = FSP_T0(s0, 3) ^ FSP_T2(s2, 1) ^ rk[4] ^ ror8(FSP_T0(s1, 2));               // + ror8(Te2[s3.b0]) per block
+    const uint32_t c1 = FSP_T0(s1, 3) ^ FSP_T2(s3, 1) ^ rk[5] ^ ror8(FSP_T0(s2, 2) ^ FSP_T2(s0, 0));
+    const uint32_t c2 = FSP_T0(s2, 3) ^ FSP_T2(s0, 1) ^ rk[6] ^ ror8(FSP_T0(s3, 2) ^ FSP_T2(s1, 0));
+    const uint32_t c3 = FSP_T0(s3, 3) ^ FSP_T2(s1, 1) ^ rk[7] ^ ror8(FSP_T0(s0, 2) ^ FSP_T2(s2, 0));
+    o.d0 = FSP_T2(c2, 1) ^ rk[8] ^ ror8(FSP_T0(c1, 2) ^ FSP_T2(c3, 0));               // + Te0[t0.b3]
+    o.d1 = FSP_T0(c1, 3) ^ FSP_T2(c3, 1) ^ rk[9] ^ ror8(FSP_T0(c2, 2));               // + ror8(Te2[t0.b0])
+    o.d2 = FSP_T0(c2, 3) ^ rk[10] ^ ror8(FSP_T0(c3, 2) ^ FSP_T2(c1, 0));              // + Te2[t0.b1]
+    o.d3 = FSP_T0(c3, 3) ^ FSP_T2(c1, 1) ^ rk[11] ^ ror8(FSP_T2(c2, 0));              // + ror8(Te0[t0.b2])
+    return o;
+}
+
+// E_K(IV || ctr) for ctr < 256 given the record's CtrPre.
+__device__ __forceinline__ void aes256_ctr_block(uint32_t K0, const uint32_t *rk, const CtrPre &pre, uint32_t ctr, uint32_t out[4]) {
+    const uint32_t K2 = K0 + 128u;
+    const uint32_t t0 = pre.c0 ^ ror8(FSP_T2(ctr ^ rk[3], 0));
+    uint32_t s0 = pre.d0 ^ FSP_T0(t0, 3);
+    uint32_t s1 = pre.d1 ^ ror8(FSP_T2(t0, 0));
+    uint32_t s2 = pre.d2 ^ FSP_T2(t0, 1);
+    uint32_t s3 = pre.d3 ^ ror8(FSP_T0(t0, 2));
+#pragma unroll
+    for (int r = 3; r < 14; r++) {
+        const uint32_t a0 = FSP_T0(s0, 3), b0 = FSP_T0(s1, 2), c0 = FSP_T2(s2, 1), d0 = FSP_T2(s3, 0);
+        const uint32_t a1 = FSP_T0(s1, 3), b1 = FSP_T0(s2, 2), c1 = FSP_T2(s3, 1), d1 = FSP_T2(s0, 0);
+        const uint32_t a2 = FSP_T0(s2, 3), b2 = FSP_T0(s3, 2), c2 = FSP_T2(s0, 1), d2 = FSP_T2(s1, 0);
+        const uint32_t a3 = FSP_T0(s3, 3), b3 = FSP_T0(s0, 2), c3 = FSP_T2(s1, 1), d3 = FSP_T2(s2, 0);
+        s0 = a0 ^ c0 ^ rk[4 * r + 0] ^ ror8(b0 ^ d0);
+        s1 = a1 ^ c1 ^ rk[4 * r + 1] ^ ror8(b1 ^ d1);
+        s2 = a2 ^ c2 ^ rk[4 * r + 2] ^ ror8(b2 ^ d2);
+        s3 = a3 ^ c3 ^ rk[4 * r + 3] ^ ror8(b3 ^ d3);
+    }
+#define FSP_LAST(a, b, c, d) ((FSP_T2(a, 3) & 0xff000000u) | (FSP_T0(b, 2) & 0x00ff0000u) | (FSP_T0(c, 1) & 0x0000ff00u) | (FSP_T2(d, 0) & 0x000000ffu))
+    out[0] = FSP_LAST(s0, s1, s2, s3) ^ rk[56];
+    out[1] = FSP_LAST(s1, s2, s3, s0) ^ rk[57];
+    out[2] = FSP_LAST(s2, s3, s0, s1) ^ rk[58];
+    out[3] = FSP_LAST(s3, s0, s1, s2) ^ rk[59];
+#undef FSP_LAST
+}
 #undef FSP_T0
 #undef FSP_T2
 
@@ -245,6 +295,31 @@ __device__ __forceinline__ bool warp_decrypt_record(const StoreView &sv, const u
             const uint32_t p2 = bswap32(w.z) ^ ks[2], p3 = bswap32(w.w) ^ ks[3];
             pt_row[2 * blk + 1] = __hiloint2double((int)p2, (int)p3);
             finite &= ((p2 >> 20) & 0x7ffu) != 0x7ffu;
+        }
+    }
+    return __all_sync(0xffffffffu, finite);
+}
+
+// Same with the record's hoisted round-1/2 constants (production kernel, c <= 254).
+__device__ __forceinline__ bool warp_decrypt_record_ctr(const StoreView &sv, const uint8_t *rec, uint32_t K0, const uint32_t *rk, const CtrPre &pre,
+                                                        double *pt_row, int lane) {
+    const int nbytes = 8 * sv.dim;
+    const int c = (nbytes + 15) >> 4;
+    const uint4 *ctv = reinterpret_cast<const uint4 *>(rec + 16);
+    bool finite = true;
+    for (int blk = lane; blk < c; blk += 32) {
+        const uint4 w = __ldg(ctv + blk);
+        uint32_t ks[4];
+        aes256_ctr_block(K0, rk, pre, (uint32_t)(blk + 2), ks);
+        const uint32_t p0 = bswap32(w.x) ^ ks[0], p1 = bswap32(w.y) ^ ks[1];
+        finite &= ((p0 >> 20) & 0x7ffu) != 0x7ffu;
+        if (!((blk == c - 1) && (nbytes & 15))) {
+            const uint32_t p2 = bswap32(w.z) ^ ks[2], p3 = bswap32(w.w) ^ ks[3];
+            finite &= ((p2 >> 20) & 0x7ffu) != 0x7ffu;
+            // big-endian FP64 (AGC:261-277): first word is the high half; one 128-bit store per block
+            *reinterpret_cast<double2 *>(pt_row + 2 * blk) = make_double2(__hiloint2double((int)p0, (int)p1), __hiloint2double((int)p2, (int)p3));
+        } else {
+            pt_row[2 * blk] = __hiloint2double((int)p0, (int)p1);   // odd dim: the last block holds one double, the rest is tag
         }
     }
     return __all_sync(0xffffffffu, finite);
@@ -375,15 +450,119 @@ int launch_refine_verify(cudaStream_t s, const StoreView &sv, const RefineParams
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
-__global__ void __launch_bounds__(RF_THREADS, 1) refine_decrypt_kernel(const __grid_constant__ DevKeyRing ring, StoreView sv, RefineParams p) {
+// Exact sequential FP64 squared distance between one query and the plaintext row `row` (shared memory), QSI:364-372: strict
+// FP64, index order, no FMA contraction.  The three query encodings are value-identical, so the result is bit-identical.
+__device__ __forceinline__ double pair_dist2(const RefineParams &p, bool use_u8, bool use_f32, int dim, const double *row, uint32_t q) {
+    double s = 0.0;
+    const double2 *v2 = reinterpret_cast<const double2 *>(row);
+    if (use_u8) {
+        // every query value is an integer in [0, 255] (SIFT / .bvecs descriptors, loader/BvecsLoader): one 128-byte
+        // line holds 128 dimensions, an eighth of the FP64 row.  Bytes are widened exactly (2^52 magic constant).
+        const uint4 *q16 = reinterpret_cast<const uint4 *>(p.queries_u8 + (size_t)q * dim);
+        const int n16 = dim >> 4;
+        for (int i0 = 0; i0 < n16; i0 += 8) {
+            uint4 qq[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) qq[u] = (i0 + u < n16) ? __ldg(q16 + i0 + u) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                if (i0 + u < n16) {
+                    const uint32_t wds[4] = {qq[u].x, qq[u].y, qq[u].z, qq[u].w};
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; c4++) {
+                        const double2 va = v2[8 * (i0 + u) + 2 * c4], vb = v2[8 * (i0 + u) + 2 * c4 + 1];
+                        const double q0 = __hiloint2double(0x43300000, (int)(wds[c4] & 0xffu)) - 4503599627370496.0;
+                        const double q1 = __hiloint2double(0x43300000, (int)((wds[c4] >> 8) & 0xffu)) - 4503599627370496.0;
+                        const double q2 = __hiloint2double(0x43300000, (int)((wds[c4] >> 16) & 0xffu)) - 4503599627370496.0;
+                        const double q3 = __hiloint2double(0x43300000, (int)(wds[c4] >> 24)) - 4503599627370496.0;
+                        const double d0 = __dsub_rn(q0, va.x), d1 = __dsub_rn(q1, va.y), d2 = __dsub_rn(q2, vb.x), d3 = __dsub_rn(q3, vb.y);
+                        s = __dadd_rn(s, __dmul_rn(d0, d0));
+                        s = __dadd_rn(s, __dmul_rn(d1, d1));
+                        s = __dadd_rn(s, __dmul_rn(d2, d2));
+                        s = __dadd_rn(s, __dmul_rn(d3, d3));
+                    }
+                }
+            }
+        }
+    } else if (use_f32) {
+        // every query value is exactly representable in FP32 (the reference's loaders read float32 and widen,
+        // FvecsLoader.java:27-30): read the compact FP32 copy -- half the bytes through L1 -- and widen back
+        const float4 *q4 = reinterpret_cast<const float4 *>(p.queries_f32 + (size_t)q * dim);
+        const int n4 = dim >> 2;
+        int i = 0;
+        for (; i + 8 <= n4; i += 8) {
+            float4 qq[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) qq[u] = __ldg(q4 + i + u);
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const double2 va = v2[2 * (i + u)], vb = v2[2 * (i + u) + 1];
+                const double d0 = __dsub_rn((double)qq[u].x, va.x), d1 = __dsub_rn((double)qq[u].y, va.y);
+                const double d2 = __dsub_rn((double)qq[u].z, vb.x), d3 = __dsub_rn((double)qq[u].w, vb.y);
+                s = __dadd_rn(s, __dmul_rn(d0, d0));
+                s = __dadd_rn(s, __dmul_rn(d1, d1));
+                s = __dadd_rn(s, __dmul_rn(d2, d2));
+                s = __dadd_rn(s, __dmul_rn(d3, d3));
+            }
+        }
+        for (; i < n4; i++) {
+            const float4 q1 = __ldg(q4 + i);
+            const double2 va = v2[2 * i], vb = v2[2 * i + 1];
+            const double d0 = __dsub_rn((double)q1.x, va.x), d1 = __dsub_rn((double)q1.y, va.y);
+            const double d2 = __dsub_rn((double)q1.z, vb.x), d3 = __dsub_rn((double)q1.w, vb.y);
+            s = __dadd_rn(s, __dmul_rn(d0, d0));
+            s = __dadd_rn(s, __dmul_rn(d1, d1));
+            s = __dadd_rn(s, __dmul_rn(d2, d2));
+            s = __dadd_rn(s, __dmul_rn(d3, d3));
+        }
+    } else if ((dim & 1) == 0) {
+        // 128-bit loads, 16 values in flight per lane; the adds stay strictly sequential
+        const double2 *q2 = reinterpret_cast<const double2 *>(p.queries + (size_t)q * dim);
+        const int n2 = dim >> 1;
+        int i = 0;
+        for (; i + 8 <= n2; i += 8) {
+            double2 qq[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) qq[u] = __ldg(q2 + i + u);
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const double2 vv = v2[i + u];
+                const double d0 = __dsub_rn(qq[u].x, vv.x), d1 = __dsub_rn(qq[u].y, vv.y);
+                s = __dadd_rn(s, __dmul_rn(d0, d0));
+                s = __dadd_rn(s, __dmul_rn(d1, d1));
+            }
+        }
+        for (; i < n2; i++) {
+            const double2 q1 = __ldg(q2 + i), vv = v2[i];
+            const double d0 = __dsub_rn(q1.x, vv.x), d1 = __dsub_rn(q1.y, vv.y);
+            s = __dadd_rn(s, __dmul_rn(d0, d0));
+            s = __dadd_rn(s, __dmul_rn(d1, d1));
+        }
+    } else {
+        const double *qv = p.queries + (size_t)q * dim;
+        for (int i = 0; i < dim; i++) {
+            const double d = __dsub_rn(__ldg(qv + i), row[i]);
+            s = __dadd_rn(s, __dmul_rn(d, d));
+        }
+    }
+    return s;
+}
+
+// Shared-memory map of refine_decrypt_kernel (dynamic, up to 227 KB):
+//   [region A: up to the next 64 KB boundary of the shared window][AES tables, 64 KB][region B]
+// Every warp owns `rows` plaintext rows of row_bytes = 8*dim_pad + 16 (the 16-byte skew puts the same column of different
+// rows into different bank groups); warps [0, warps_a) keep theirs in region A, the others in region B.
+struct DecryptLayout { int rows, warps_a, row_bytes; size_t smem; };
+
+__global__ void __launch_bounds__(RF_THREADS, 1) refine_decrypt_kernel(const __grid_constant__ DevKeyRing ring, StoreView sv, RefineParams p, DecryptLayout lay) {
     extern __shared__ __align__(16) unsigned char rf_smem[];
-    // [pad to a 64 KB boundary of the shared window][AES tables 64 KB][round keys][versions][plaintext rows]
     const uint32_t base_sa = (uint32_t)__cvta_generic_to_shared(rf_smem);
     const uint32_t pad = (0x10000u - (base_sa & 0xffffu)) & 0xffffu;
     uint32_t *tab = reinterpret_cast<uint32_t *>(rf_smem + pad);                         // [256][64]
-    double *pt_all = reinterpret_cast<double *>(tab + 256 * 64);                           // [RF_WARPS][dim_pad]
-    const int dim = sv.dim, dim_pad = (dim + 1) & ~1;
+    const int dim = sv.dim;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int R = lay.rows;
+    if ((uint32_t)(lay.warps_a * R * lay.row_bytes) > pad) __trap();                      // launcher assumed a larger region A
 
     for (int i = tid; i < 256 * 64; i += RF_THREADS) {
         const uint32_t t0 = sv.te0[i >> 6];
@@ -393,11 +572,13 @@ __global__ void __launch_bounds__(RF_THREADS, 1) refine_decrypt_kernel(const __g
     __syncthreads();
 
     const AesFast te{base_sa + pad + (uint32_t)lane * 4u};
-    double *pt_row = pt_all + (size_t)warp * dim_pad;
+    unsigned char *rows_base = warp < lay.warps_a ? rf_smem + (size_t)warp * R * lay.row_bytes
+                                                  : rf_smem + pad + 0x10000u + (size_t)(warp - lay.warps_a) * R * lay.row_bytes;
     const bool use_u8 = p.queries_u8 != nullptr && (dim & 15) == 0 && p.f32_exact[1] != 0;
     const bool use_f32 = p.queries_f32 != nullptr && (dim & 3) == 0 && p.f32_exact[0] != 0;
     const int n_uniq = p.totals[1];
     const int n_chunks = (n_uniq + 31) >> 5;
+    const bool ctr_fast = ((8 * dim + 15) >> 4) <= 254;       // every counter 2..c+1 fits in one byte
 
     for (;;) {
         int chunk = 0;
@@ -407,153 +588,107 @@ __global__ void __launch_bounds__(RF_THREADS, 1) refine_decrypt_kernel(const __g
         const int base = chunk << 5;
         const int nrec = min(32, n_uniq - base);
 
-        // lane l fetches the header and the authentication verdict of record l
+        // lane l fetches the header, the authentication verdict and the pair range of record l.  uniq[] is sorted by id and
+        // pairs[] is grouped in id order, so the pairs of consecutive distinct records are contiguous.
         int32_t my_id = -1; int my_slot = -1; uint4 my_hdr = make_uint4(0, 0, 0, 0); int my_verdict = FSPANN_V_NO_KEY;
+        int my_end = 0, my_off = 0;
         if (lane < nrec) {
             my_id = p.uniq[base + lane];
             my_hdr = __ldg(reinterpret_cast<const uint4 *>(sv.rec + (size_t)my_id * sv.rec_stride));
             for (int i = 0; i < nkeys; i++) if (ring.version[i] == (int32_t)my_hdr.w) my_slot = i;
             my_verdict = my_slot < 0 ? FSPANN_V_NO_KEY : (int)p.rec_verdict[base + lane];        // KRS:82-88 -> QSI:265-270
+            my_off = p.cnt[my_id]; my_end = p.cnt[my_id + 1];
+        }
+        // lane l: the (IV, key)-only part of AES rounds 1-2 of record l (see CtrPre)
+        CtrPre my_pre{0, 0, 0, 0, 0};
+        if (ctr_fast) {
+            for (int vi = 0; vi < nkeys; vi++)          // warp-uniform vi: round keys stay on the uniform datapath
+                if (vi == my_slot && my_verdict == FSPANN_V_OK)
+                    my_pre = aes256_ctr_precompute(te.K0, ring.rk[vi], bswap32(my_hdr.x), bswap32(my_hdr.y), bswap32(my_hdr.z));
         }
 
-        for (int r = 0; r < nrec; r++) {
-            const int32_t id = __shfl_sync(0xffffffffu, my_id, r);
-            const int slot = __shfl_sync(0xffffffffu, my_slot, r);
-            int verdict = __shfl_sync(0xffffffffu, my_verdict, r);
-            uint4 hdr;
-            hdr.x = __shfl_sync(0xffffffffu, my_hdr.x, r); hdr.y = __shfl_sync(0xffffffffu, my_hdr.y, r);
-            hdr.z = __shfl_sync(0xffffffffu, my_hdr.z, r); hdr.w = __shfl_sync(0xffffffffu, my_hdr.w, r);
-            if (verdict == FSPANN_V_OK) {      // plaintext is produced only for authenticated records
-                // the loop counter is warp-uniform, so the round keys are read from the kernel-parameter constant bank through
-                // the uniform datapath instead of 60 shared-memory loads per block
-                bool finite = true;
-                for (int vi = 0; vi < nkeys; vi++)
-                    if (vi == slot) finite = warp_decrypt_record(sv, sv.rec + (size_t)id * sv.rec_stride, hdr, 0, te, ring.rk[vi], pt_row, lane);
-                if (!finite) verdict = FSPANN_V_NON_FINITE;                                      // QSI:253
+        for (int g0 = 0; g0 < nrec; g0 += R) {
+            const int gn = min(R, nrec - g0);
+            // ---- decrypt the group's records into the warp's rows (plaintext never leaves shared memory) ----
+            for (int i = 0; i < gn; i++) {
+                const int r = g0 + i;
+                const int32_t id = __shfl_sync(0xffffffffu, my_id, r);
+                const int slot = __shfl_sync(0xffffffffu, my_slot, r);
+                const int verdict = __shfl_sync(0xffffffffu, my_verdict, r);
+                double *pt_row = reinterpret_cast<double *>(rows_base + (size_t)i * lay.row_bytes);
+                if (verdict == FSPANN_V_OK) {      // plaintext is produced only for authenticated records
+                    // the loop counter is warp-uniform, so the round keys are read from the kernel-parameter constant bank
+                    // through the uniform datapath instead of 60 shared-memory loads per block
+                    bool finite = true;
+                    if (ctr_fast) {
+                        CtrPre pre;
+                        pre.c0 = __shfl_sync(0xffffffffu, my_pre.c0, r); pre.d0 = __shfl_sync(0xffffffffu, my_pre.d0, r);
+                        pre.d1 = __shfl_sync(0xffffffffu, my_pre.d1, r); pre.d2 = __shfl_sync(0xffffffffu, my_pre.d2, r);
+                        pre.d3 = __shfl_sync(0xffffffffu, my_pre.d3, r);
+                        for (int vi = 0; vi < nkeys; vi++)
+                            if (vi == slot) finite = warp_decrypt_record_ctr(sv, sv.rec + (size_t)id * sv.rec_stride, te.K0, ring.rk[vi], pre, pt_row, lane);
+                    } else {
+                        uint4 hdr;
+                        hdr.x = __shfl_sync(0xffffffffu, my_hdr.x, r); hdr.y = __shfl_sync(0xffffffffu, my_hdr.y, r);
+                        hdr.z = __shfl_sync(0xffffffffu, my_hdr.z, r); hdr.w = __shfl_sync(0xffffffffu, my_hdr.w, r);
+                        for (int vi = 0; vi < nkeys; vi++)
+                            if (vi == slot) finite = warp_decrypt_record(sv, sv.rec + (size_t)id * sv.rec_stride, hdr, 0, te, ring.rk[vi], pt_row, lane);
+                    }
+                    if (!finite && lane == r) my_verdict = FSPANN_V_NON_FINITE;                  // QSI:253
+                }
             }
+            if (lane >= g0 && lane < g0 + gn && my_verdict == FSPANN_V_OK) atomicOr(&p.touched[my_id >> 5], 1u << (my_id & 31));   // QSI:262
             __syncwarp();
 
-            // the (query, rank) pairs that selected this record
-            const int off = p.cnt[id], n_pairs = p.cnt[id + 1] - off;
-            for (int j = lane; j < n_pairs; j += 32) {
-                const uint32_t pair = p.pairs[off + j];
-                if (verdict == FSPANN_V_OK) {
-                    const double *qv = p.queries + (size_t)(pair / (uint32_t)p.stride) * dim;
-                    double s = 0.0;                                           // QSI:364-372, strict FP64, index order
-                    if (use_u8) {
-                        // every query value is an integer in [0, 255] (SIFT / .bvecs descriptors, loader/BvecsLoader): one 128-byte
-                        // line holds 128 dimensions, an eighth of the FP64 row.  Bytes are widened exactly (2^52 magic constant);
-                        // the FP64 arithmetic is unchanged, so the distance is bit-identical.
-                        const uint4 *q16 = reinterpret_cast<const uint4 *>(p.queries_u8 + (size_t)(pair / (uint32_t)p.stride) * dim);
-                        const double2 *v2 = reinterpret_cast<const double2 *>(pt_row);
-                        const int n16 = dim >> 4;
-                        for (int i0 = 0; i0 < n16; i0 += 8) {
-                            uint4 qq[8];
-#pragma unroll
-                            for (int u = 0; u < 8; u++) qq[u] = (i0 + u < n16) ? __ldg(q16 + i0 + u) : make_uint4(0, 0, 0, 0);
-#pragma unroll
-                            for (int u = 0; u < 8; u++) {
-                                if (i0 + u < n16) {
-                                    const uint32_t wds[4] = {qq[u].x, qq[u].y, qq[u].z, qq[u].w};
-#pragma unroll
-                                    for (int c4 = 0; c4 < 4; c4++) {
-                                        const double2 va = v2[8 * (i0 + u) + 2 * c4], vb = v2[8 * (i0 + u) + 2 * c4 + 1];
-                                        const double q0 = __hiloint2double(0x43300000, (int)(wds[c4] & 0xffu)) - 4503599627370496.0;
-                                        const double q1 = __hiloint2double(0x43300000, (int)((wds[c4] >> 8) & 0xffu)) - 4503599627370496.0;
-                                        const double q2 = __hiloint2double(0x43300000, (int)((wds[c4] >> 16) & 0xffu)) - 4503599627370496.0;
-                                        const double q3 = __hiloint2double(0x43300000, (int)(wds[c4] >> 24)) - 4503599627370496.0;
-                                        const double d0 = __dsub_rn(q0, va.x), d1 = __dsub_rn(q1, va.y), d2 = __dsub_rn(q2, vb.x), d3 = __dsub_rn(q3, vb.y);
-                                        s = __dadd_rn(s, __dmul_rn(d0, d0));
-                                        s = __dadd_rn(s, __dmul_rn(d1, d1));
-                                        s = __dadd_rn(s, __dmul_rn(d2, d2));
-                                        s = __dadd_rn(s, __dmul_rn(d3, d3));
-                                    }
-                                }
-                            }
-                        }
-                    } else if (use_f32) {
-                        // every query value is exactly representable in FP32 (the reference's loaders read float32 and widen,
-                        // FvecsLoader.java:27-30): read the compact FP32 copy -- half the bytes through L1 -- and widen back;
-                        // the FP64 arithmetic is unchanged, so the distance is bit-identical
-                        const float4 *q4 = reinterpret_cast<const float4 *>(p.queries_f32 + (size_t)(pair / (uint32_t)p.stride) * dim);
-                        const double2 *v2 = reinterpret_cast<const double2 *>(pt_row);
-                        const int n4 = dim >> 2;
-                        int i = 0;
-                        for (; i + 8 <= n4; i += 8) {
-                            float4 qq[8];
-#pragma unroll
-                            for (int u = 0; u < 8; u++) qq[u] = __ldg(q4 + i + u);
-#pragma unroll
-                            for (int u = 0; u < 8; u++) {
-                                const double2 va = v2[2 * (i + u)], vb = v2[2 * (i + u) + 1];
-                                const double d0 = __dsub_rn((double)qq[u].x, va.x), d1 = __dsub_rn((double)qq[u].y, va.y);
-                                const double d2 = __dsub_rn((double)qq[u].z, vb.x), d3 = __dsub_rn((double)qq[u].w, vb.y);
-                                s = __dadd_rn(s, __dmul_rn(d0, d0));
-                                s = __dadd_rn(s, __dmul_rn(d1, d1));
-                                s = __dadd_rn(s, __dmul_rn(d2, d2));
-                                s = __dadd_rn(s, __dmul_rn(d3, d3));
-                            }
-                        }
-                        for (; i < n4; i++) {
-                            const float4 q1 = __ldg(q4 + i);
-                            const double2 va = v2[2 * i], vb = v2[2 * i + 1];
-                            const double d0 = __dsub_rn((double)q1.x, va.x), d1 = __dsub_rn((double)q1.y, va.y);
-                            const double d2 = __dsub_rn((double)q1.z, vb.x), d3 = __dsub_rn((double)q1.w, vb.y);
-                            s = __dadd_rn(s, __dmul_rn(d0, d0));
-                            s = __dadd_rn(s, __dmul_rn(d1, d1));
-                            s = __dadd_rn(s, __dmul_rn(d2, d2));
-                            s = __dadd_rn(s, __dmul_rn(d3, d3));
-                        }
-                    } else if ((dim & 1) == 0) {
-                        // 128-bit loads, 16 values in flight per lane; the adds stay strictly sequential
-                        const double2 *q2 = reinterpret_cast<const double2 *>(qv);
-                        const double2 *v2 = reinterpret_cast<const double2 *>(pt_row);
-                        const int n2 = dim >> 1;
-                        int i = 0;
-                        for (; i + 8 <= n2; i += 8) {
-                            double2 qq[8];
-#pragma unroll
-                            for (int u = 0; u < 8; u++) qq[u] = __ldg(q2 + i + u);
-#pragma unroll
-                            for (int u = 0; u < 8; u++) {
-                                const double2 vv = v2[i + u];
-                                const double d0 = __dsub_rn(qq[u].x, vv.x), d1 = __dsub_rn(qq[u].y, vv.y);
-                                s = __dadd_rn(s, __dmul_rn(d0, d0));
-                                s = __dadd_rn(s, __dmul_rn(d1, d1));
-                            }
-                        }
-                        for (; i < n2; i++) {
-                            const double2 q1 = __ldg(q2 + i), vv = v2[i];
-                            const double d0 = __dsub_rn(q1.x, vv.x), d1 = __dsub_rn(q1.y, vv.y);
-                            s = __dadd_rn(s, __dmul_rn(d0, d0));
-                            s = __dadd_rn(s, __dmul_rn(d1, d1));
-                        }
-                    } else {
-                        for (int i = 0; i < dim; i++) {
-                            const double d = __dsub_rn(__ldg(qv + i), pt_row[i]);
-                            s = __dadd_rn(s, __dmul_rn(d, d));
-                        }
+            // ---- score the group's (query, rank) pairs: lanes = pairs, 32 at a time across record boundaries ----
+            const int off0 = __shfl_sync(0xffffffffu, my_off, g0);
+            const int offE = __shfl_sync(0xffffffffu, my_end, g0 + gn - 1);
+            for (int j0 = off0; j0 < offE; j0 += 32) {
+                const int j = j0 + lane;
+                int i = 0;                                           // which record of the group owns pair j
+                for (int t = 0; t + 1 < gn; t++) i += (j >= __shfl_sync(0xffffffffu, my_end, g0 + t)) ? 1 : 0;
+                const int verdict = __shfl_sync(0xffffffffu, my_verdict, g0 + i);
+                if (j < offE) {
+                    const uint32_t pair = p.pairs[j];
+                    if (verdict == FSPANN_V_OK) {
+                        const double *row = reinterpret_cast<const double *>(rows_base + (size_t)i * lay.row_bytes);
+                        p.dist[pair] = __dsqrt_rn(pair_dist2(p, use_u8, use_f32, dim, row, pair / (uint32_t)p.stride));
                     }
-                    p.dist[pair] = __dsqrt_rn(s);
+                    p.verdict[pair] = (uint8_t)verdict;
                 }
-                p.verdict[pair] = (uint8_t)verdict;
             }
-            if (verdict == FSPANN_V_OK && lane == 0) atomicOr(&p.touched[id >> 5], 1u << (id & 31));   // QSI:262
             __syncwarp();
         }
     }
 }
 
-int launch_refine_decrypt(cudaStream_t s, const StoreView &sv, const RefineParams &p, int sm_count) {
-    const int dim_pad = (sv.dim + 1) & ~1;
-    const size_t smem = 0x10000 /* worst-case pad */ + sizeof(uint32_t) * (256 * 64) + sizeof(double) * (size_t)RF_WARPS * dim_pad + 16;
-    if (smem > 227 * 1024) return -1;
-    static size_t configured = 0;
-    if (smem > configured) {
-        if (cudaFuncSetAttribute(refine_decrypt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-        configured = smem;
+// Picks the number of plaintext rows per warp that fits (see DecryptLayout).
+static bool decrypt_layout(int dim, DecryptLayout &lay) {
+    const int dim_pad = (dim + 1) & ~1;
+    lay.row_bytes = 8 * dim_pad + 16;
+    const int a_avail = 0x10000 - 2048;                       // region A: the window starts with <= 2 KB of reserved / static memory
+    const int b_avail = 227 * 1024 - 2 * 0x10000 - 64;
+    for (int rows = 8; rows >= 1; rows--) {
+        const int per_warp = rows * lay.row_bytes;
+        const int wa = std::min(RF_WARPS, a_avail / per_warp), wb = RF_WARPS - wa;
+        if (wb * per_warp <= b_avail) {
+            lay.rows = rows; lay.warps_a = wa;
+            lay.smem = (size_t)2 * 0x10000 + (size_t)wb * per_warp + 16;
+            return true;
+        }
     }
-    refine_decrypt_kernel<<<sm_count, RF_THREADS, smem, s>>>(*sv.keys_host, sv, p);
+    return false;
+}
+
+int launch_refine_decrypt(cudaStream_t s, const StoreView &sv, const RefineParams &p, int sm_count) {
+    DecryptLayout lay;
+    if (!decrypt_layout(sv.dim, lay)) return -1;
+    static size_t configured = 0;
+    if (lay.smem > configured) {
+        if (cudaFuncSetAttribute(refine_decrypt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.smem) != cudaSuccess) return -1;
+        configured = lay.smem;
+    }
+    refine_decrypt_kernel<<<sm_count, RF_THREADS, lay.smem, s>>>(*sv.keys_host, sv, p, lay);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
