@@ -74,6 +74,7 @@ struct RouteFastExtra {
     int n_raw;    // T*D*probes*64
     int tbl;      // open-addressing slots (power of two)
     int sort_n;   // bitonic sort width (power of two >= B + slack)
+    int wl_extra; // dedicated worklist entries (the worklist continues over skey / sid)
 };
 
 struct RefineParams {

@@ -399,16 +399,20 @@ __device__ __forceinline__ uint32_t cas16(uint32_t *tw, uint32_t slot, uint32_t 
     }
 }
 
-size_t route_fast_smem(int TD, int probes, int n_raw, int tbl, int sort_n) {
+size_t route_fast_smem(int TD, int probes, int n_raw, int tbl, int sort_n, int wl_extra) {
+    const size_t nvis = (size_t)TD * probes, nvis16 = (nvis + 15) / 16 * 16;
     size_t s = 0;
-    s += sizeof(uint64_t) * sort_n;                 // skey
-    s += sizeof(int64_t) * TD * probes;             // vbase_s
     s += sizeof(int32_t) * n_raw;                   // ids_s
-    s += sizeof(int32_t) * sort_n;                  // sid
-    s += sizeof(uint16_t) * tbl;                    // table (later: dense list of the cut score class)
     s += sizeof(uint16_t) * n_raw;                  // next_s (later: low 16 bits of the Java hash)
     s += (size_t)n_raw;                             // best_s
-    s += 2 * (((size_t)TD * probes + 15) / 16 * 16); // vs_s, vlen_s
+    s = (s + 15) / 16 * 16;
+    s += sizeof(uint16_t) * tbl;                    // filter / exact table / class + selection lists
+    s += sizeof(int64_t) * nvis;                    // vbase_s
+    s += 2 * nvis16;                                // vs_s, vlen_s
+    s += sizeof(uint16_t) * nvis16;                 // lowvis_s
+    s += sizeof(uint16_t) * wl_extra;               // worklist head (continues into skey / sid)
+    s += sizeof(uint64_t) * sort_n;                 // skey
+    s += sizeof(int32_t) * sort_n;                  // sid
     return s + 64;
 }
 
@@ -441,31 +445,49 @@ __device__ __forceinline__ void hist_add(int32_t *hist, bool active, int bin, in
     if (lane == __ffs(peers) - 1) atomicAdd(&hist[bin], __popc(peers));
 }
 
+// warp-aggregated append to a shared list: returns this lane's slot (or -1), one shared atomic per warp
+__device__ __forceinline__ int list_slot(int32_t *counter, bool in, int lane) {
+    const unsigned bal = __ballot_sync(0xffffffffu, in);
+    int base = 0;
+    if (lane == 0 && bal) base = atomicAdd(counter, __popc(bal));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    return in ? base + __popc(bal & ((1u << lane) - 1u)) : -1;
+}
+
+// best_s encoding: 255 = not a representative position (invalid id, or a later occurrence of a duplicated id),
+// 254 = occurrence of a possibly duplicated id waiting for the exact path, s < 128 = the only occurrence of its id (score s),
+// 0x80 | s = first occurrence of a duplicated id whose minimum score over all occurrences is s.
+constexpr uint32_t RQ_DUP = 0x80u;
+
 __global__ void __launch_bounds__(RQ_THREADS, 1) route_fast_kernel(RoutingView rv, RouteParams p, RouteFastExtra x) {
     extern __shared__ __align__(16) unsigned char rq_smem[];
     const int TD = rv.TD, probes = p.probes, n_raw = x.n_raw, tbl = x.tbl, sort_n = x.sort_n, nvis = TD * probes;
-    uint64_t *skey = reinterpret_cast<uint64_t *>(rq_smem);
-    int64_t *vbase_s = reinterpret_cast<int64_t *>(skey + sort_n);          // per visit: offset of its partition row in rv.ids, or -1
-    int32_t *ids_s = reinterpret_cast<int32_t *>(vbase_s + nvis);
-    int32_t *sid = ids_s + n_raw;
-    uint32_t *table_w = reinterpret_cast<uint32_t *>(sid + sort_n);
+    const int nvis16 = (nvis + 15) / 16 * 16;
+    int32_t *ids_s = reinterpret_cast<int32_t *>(rq_smem);
+    uint16_t *next_s = reinterpret_cast<uint16_t *>(ids_s + n_raw);
+    uint8_t *best_s = reinterpret_cast<uint8_t *>(next_s + n_raw);
+    uint32_t *table_w = reinterpret_cast<uint32_t *>(rq_smem + ((size_t)7 * n_raw + 15) / 16 * 16);
     uint16_t *table = reinterpret_cast<uint16_t *>(table_w);
-    uint16_t *next_s = table + tbl;
-    uint8_t *best_s = reinterpret_cast<uint8_t *>(next_s + n_raw);           // rep positions: the id's best score; others: 255
-    uint8_t *vs_s = best_s + n_raw;
-    uint8_t *vlen_s = vs_s + (nvis + 15) / 16 * 16;                           // valid ids in the visited partition row
-    uint16_t *cls = table;                                                   // after step 4 the table is dead: dense class list
+    int64_t *vbase_s = reinterpret_cast<int64_t *>(table + tbl);                // per visit: offset of its partition row in rv.ids
+    uint8_t *vs_s = reinterpret_cast<uint8_t *>(vbase_s + nvis);               // per visit: Hamming score of the partition
+    uint8_t *vlen_s = vs_s + nvis16;                                           // valid ids in the visited partition row
+    uint16_t *lowvis_s = reinterpret_cast<uint16_t *>(vlen_s + nvis16);
+    uint16_t *wl = lowvis_s + nvis16;                                          // worklist: wl_extra entries, then over skey / sid
+    uint64_t *skey = reinterpret_cast<uint64_t *>(wl + x.wl_extra);
+    int32_t *sid = reinterpret_cast<int32_t *>(skey + sort_n);
+    const int wl_cap = x.wl_extra + 6 * sort_n;
+    uint16_t *cls = table;                                                     // after the exact path the table is dead: cut-class list ...
+    uint16_t *sel = table + n_raw;                                             // ... and the list of selected positions (sort_n entries)
     __shared__ int32_t s_hist[256];
-    __shared__ int32_t s_raw, s_uniq, s_m, s_ncls, s_pick[3];
+    __shared__ int32_t s_raw, s_uniq, s_m, s_ncls, s_nwl, s_nlow, s_pick[3];
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int64_t n_ids = rv.n_ids;
-    const uint32_t tmask = (uint32_t)tbl - 1u;
-    int tshift = 32; while ((1u << (32 - tshift)) < (uint32_t)tbl) tshift--;
+    int fshift = 32; while ((1u << (32 - fshift)) < (uint32_t)tbl * 8u) fshift--;
 
     for (int64_t q = blockIdx.x; q < p.Q; q += gridDim.x) {
         __syncthreads();
-        // ---- 1. stage visits, reset table ----
+        // ---- 1. stage visits, reset the duplicate filter (it lives in the table region: 8*tbl two-bit buckets) ----
         for (int v = tid; v < nvis; v += RQ_THREADS) {
             const int g = v / probes, j = v - g * probes;
             const int64_t vi = (q * TD + g) * probes + j;
@@ -475,58 +497,64 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) route_fast_kernel(RoutingView r
             vlen_s[v] = valid ? (uint8_t)min((int64_t)kBlock, n_ids - row) : 0;
             vs_s[v] = valid ? x.vis_score[vi] : 255;
         }
-        for (int i = tid; i < tbl / 2; i += RQ_THREADS) table_w[i] = 0u;            // the region first serves as the duplicate filter
+        for (int i = tid; i < tbl / 8; i += RQ_THREADS) reinterpret_cast<uint4 *>(table_w)[i] = make_uint4(0, 0, 0, 0);
         if (tid < 256) s_hist[tid] = 0;
-        if (tid == 0) { s_raw = 0; s_uniq = 0; s_m = 0; s_ncls = 0; }
+        if (tid == 0) { s_raw = 0; s_uniq = 0; s_m = 0; s_ncls = 0; s_nwl = 0; s_nlow = 0; }
         __syncthreads();
-        // ---- 2. gather ids (each partition row is 256 contiguous bytes) ----
-        for (int e = tid; e < n_raw; e += RQ_THREADS) {
-            const int v = e >> 6, pos = e & 63;
-            int32_t id = -1;
-            if (pos < (int)vlen_s[v]) {
-                id = __ldg(rv.ids + vbase_s[v] + pos);
-                if (rv.deleted && id >= 0 && id < rv.n_deleted && rv.deleted[id]) id = -1;     // PIS:739
-            }
-            ids_s[e] = id;
-            next_s[e] = (uint16_t)RQ_EMPTY;
-            best_s[e] = 255;
-        }
-        __syncthreads();
-        // ---- 3. duplicate filter.  ~95 % of the visited ids occur once, so the exact (hash-table + chain) machinery is only run on
-        //         the positions a 2-bit-per-bucket filter cannot clear: bit0 = "bucket taken", bit1 = "taken twice".  The filter
-        //         lives in the table region (8*tbl buckets); a position whose bucket never collided is the only occurrence of its id.
-        int my_raw = 0, my_uniq = 0, my_inv = 0;
-        {
-            uint32_t *F = table_w;
-            int fshift = 32; while ((1u << (32 - fshift)) < (uint32_t)tbl * 8u) fshift--;
-            for (int e = tid; e < n_raw; e += RQ_THREADS) {
-                const int32_t id = ids_s[e];
-                if (id < 0) continue;
-                const uint32_t h = ((uint32_t)id * 0x9E3779B1u) >> fshift;
-                const uint32_t sh = (h & 15u) * 2u;
-                const uint32_t old = atomicOr(&F[h >> 4], 1u << sh);
-                if ((old >> sh) & 1u) atomicOr(&F[h >> 4], 2u << sh);
-            }
-            __syncthreads();
-            for (int e0 = 0; e0 < n_raw; e0 += RQ_THREADS) {
-                const int e = e0 + tid;
-                const int32_t id = e < n_raw ? ids_s[e] : -1;
-                bool single = false; uint32_t sc = 255;
-                if (id >= 0) {
-                    const uint32_t h = ((uint32_t)id * 0x9E3779B1u) >> fshift;
-                    if ((F[h >> 4] >> ((h & 15u) * 2u)) & 2u) { best_s[e] = 254; my_inv++; }      // needs the exact path
-                    else { single = true; sc = vs_s[e >> 6]; best_s[e] = (uint8_t)sc; my_raw++; my_uniq++; }
+        // ---- 2. gather ids (each partition row is 256 contiguous bytes; 4 loads in flight per thread) and set the filter:
+        //         bit0 = "bucket taken", bit1 = "taken twice".  ~95 % of the visited ids occur once; a position whose bucket never
+        //         collided is the only occurrence of its id, everything else goes through the exact path below.
+        uint32_t *F = table_w;
+        for (int e0 = tid; e0 < n_raw; e0 += 4 * RQ_THREADS) {
+            int32_t idv[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int e = e0 + u * RQ_THREADS;
+                idv[u] = -1;
+                if (e < n_raw) {
+                    const int v = e >> 6, pos = e & 63;
+                    if (pos < (int)vlen_s[v]) idv[u] = __ldg(rv.ids + vbase_s[v] + pos);
                 }
-                hist_add(s_hist, single, (int)sc, lane);
             }
 #pragma unroll
-            for (int o = 16; o; o >>= 1) my_inv += __shfl_xor_sync(0xffffffffu, my_inv, o);
-            if (lane == 0 && my_inv) atomicAdd(&s_ncls, my_inv);
-            __syncthreads();
+            for (int u = 0; u < 4; u++) {
+                const int e = e0 + u * RQ_THREADS;
+                if (e < n_raw) {
+                    int32_t id = idv[u];
+                    if (rv.deleted && id >= 0 && id < rv.n_deleted && rv.deleted[id]) id = -1;     // PIS:739
+                    ids_s[e] = id;
+                    if (id >= 0) {
+                        const uint32_t h = ((uint32_t)id * 0x9E3779B1u) >> fshift;
+                        const uint32_t sh = (h & 15u) * 2u;
+                        const uint32_t old = atomicOr(&F[h >> 4], 1u << sh);
+                        if ((old >> sh) & 1u) atomicOr(&F[h >> 4], 2u << sh);
+                    }
+                }
+            }
         }
-        const int n_inv = s_ncls;
         __syncthreads();
-        if (tid == 0) s_ncls = 0;
+        // ---- 3. classify every position: single (final), or involved (-> worklist for the exact path).  A warp covers 32
+        //         consecutive positions of ONE visit, so its singles share one score: one histogram atomic per warp. ----
+        int my_raw = 0, my_uniq = 0;
+        bool wl_ok = true;
+        for (int e0 = 0; e0 < n_raw; e0 += RQ_THREADS) {
+            const int e = e0 + tid;
+            const int32_t id = e < n_raw ? ids_s[e] : -1;
+            bool single = false, inv = false;
+            if (id >= 0) {
+                const uint32_t h = ((uint32_t)id * 0x9E3779B1u) >> fshift;
+                inv = ((F[h >> 4] >> ((h & 15u) * 2u)) & 2u) != 0;
+                single = !inv;
+            }
+            const uint32_t sc = e < n_raw ? vs_s[e >> 6] : 255u;
+            if (e < n_raw) best_s[e] = (uint8_t)(single ? sc : (inv ? 254u : 255u));
+            const unsigned bs = __ballot_sync(0xffffffffu, single);
+            if (lane == 0 && bs) { const int c = __popc(bs); atomicAdd(&s_hist[sc], c); my_raw += c; my_uniq += c; }
+            const int slot = list_slot(&s_nwl, inv, lane);
+            if (inv) { if (slot < wl_cap) wl[slot] = (uint16_t)e; else wl_ok = false; }
+        }
+        wl_ok = __syncthreads_and(wl_ok ? 1 : 0) != 0;
+        const int n_inv = s_nwl;
         // ---- 4. exact path on the involved positions: open addressing (double hashing) keyed by id, table[slot] = newest position
         //         holding that id, every position links to the previous newest one, the FIRST arrival's link is the terminator
         //         0x8000|slot (so the slot of any position is found by following its short chain).  Then every occurrence walks
@@ -534,28 +562,14 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) route_fast_kernel(RoutingView r
         //         first occurrence (= HashMap insertion order); the first one records the id's min score.
         if (n_inv > 0) {
             int tslots = 1024; while (tslots < 2 * n_inv && tslots < tbl) tslots <<= 1;
-            const bool use_wl = tslots + n_inv <= tbl;                 // room for a dense worklist behind the table?
-            uint16_t *wl = table + tslots;
             const uint32_t smask = (uint32_t)tslots - 1u;
             int sshift = 32; while ((1u << (32 - sshift)) < (uint32_t)tslots) sshift--;
             for (int i = tid; i < tslots / 2; i += RQ_THREADS) table_w[i] = 0xffffffffu;
             __syncthreads();
-            if (use_wl) {
-                for (int e0 = 0; e0 < n_raw; e0 += RQ_THREADS) {
-                    const int e = e0 + tid;
-                    const bool in = e < n_raw && best_s[e] == 254;
-                    const unsigned bal = __ballot_sync(0xffffffffu, in);
-                    int base = 0;
-                    if (lane == 0 && bal) base = atomicAdd(&s_ncls, __popc(bal));
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (in) wl[base + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)e;
-                }
-                __syncthreads();
-            }
-            const int n_dom = use_wl ? n_inv : n_raw;
+            const int n_dom = wl_ok ? n_inv : n_raw;
             for (int i = tid; i < n_dom; i += RQ_THREADS) {
-                const int e = use_wl ? (int)wl[i] : i;
-                if (!use_wl && best_s[e] != 254) continue;
+                const int e = wl_ok ? (int)wl[i] : i;
+                if (!wl_ok && best_s[e] != 254) continue;
                 const int32_t id = ids_s[e];
                 const uint32_t h = (uint32_t)id * 0x9E3779B1u;
                 uint32_t slot = h >> sshift;
@@ -580,33 +594,28 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) route_fast_kernel(RoutingView r
                 }
             }
             __syncthreads();
-            for (int i0 = 0; i0 < n_dom; i0 += RQ_THREADS) {
-                const int i = i0 + tid;
-                int e = -1;
-                if (i < n_dom) { e = use_wl ? (int)wl[i] : i; if (!use_wl && best_s[e] != 254) e = -1; }
-                bool is_rep = false; uint32_t best = 255;
-                if (e >= 0) {
-                    const uint32_t sc = vs_s[e >> 6];
-                    uint32_t lk = next_s[e];
-                    while (!(lk & 0x8000u)) lk = next_s[lk];           // terminator carries the slot
-                    const uint32_t head = table[lk & 0x7fffu];
-                    uint32_t first = head; bool low = true;
-                    for (uint32_t y = head;;) {
-                        const uint32_t sy = vs_s[y >> 6];
-                        first = min(first, y); best = min(best, sy);
-                        if (y < (uint32_t)e && sy <= sc) low = false;
-                        const uint32_t ny = next_s[y];
-                        if (ny & 0x8000u) break;
-                        y = ny;
-                    }
-                    my_raw += low;
-                    is_rep = first == (uint32_t)e;
+            for (int i = tid; i < n_dom; i += RQ_THREADS) {
+                const int e = wl_ok ? (int)wl[i] : i;
+                if (!wl_ok && best_s[e] != 254) continue;
+                const uint32_t sc = vs_s[e >> 6];
+                uint32_t lk = next_s[e];
+                while (!(lk & 0x8000u)) lk = next_s[lk];               // terminator carries the slot
+                const uint32_t head = table[lk & 0x7fffu];
+                uint32_t first = head, best = 255; bool low = true;
+                for (uint32_t y = head;;) {
+                    const uint32_t sy = vs_s[y >> 6];
+                    first = min(first, y); best = min(best, sy);
+                    if (y < (uint32_t)e && sy <= sc) low = false;
+                    const uint32_t ny = next_s[y];
+                    if (ny & 0x8000u) break;
+                    y = ny;
                 }
-                hist_add(s_hist, is_rep, (int)best, lane);
-                if (e >= 0) { my_uniq += is_rep; best_s[e] = (uint8_t)(is_rep ? best : 255u); }   // chain walks never read best_s
+                my_raw += low;
+                const bool is_rep = first == (uint32_t)e;
+                if (is_rep) { atomicAdd(&s_hist[best], 1); my_uniq++; }
+                best_s[e] = (uint8_t)(is_rep ? (RQ_DUP | best) : 255u);                          // chain walks never read best_s
             }
         }
-        if (tid == 0) s_ncls = 0;                                      // reused below for the cut-class list
 #pragma unroll
         for (int o = 16; o; o >>= 1) { my_raw += __shfl_xor_sync(0xffffffffu, my_raw, o); my_uniq += __shfl_xor_sync(0xffffffffu, my_uniq, o); }
         if (lane == 0) { atomicAdd(&s_raw, my_raw); atomicAdd(&s_uniq, my_uniq); }
@@ -617,29 +626,51 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) route_fast_kernel(RoutingView r
         uint32_t capF = (uint32_t)p.cap0;
         while ((double)n_unique > 0.75 * (double)capF && capF < (1u << 30)) capF <<= 1;
         int cb = 0; while ((1u << cb) < capF) cb++;
-        // ---- 5. level 0 of the radix select = score histogram from step 4 ----
+        // ---- 5. level 0 of the radix select = the score histogram ----
         if (tid < 32) warp_pick_digit(s_hist, 256, 0, want, lane, s_pick);
         __syncthreads();
         const uint32_t sstar = (uint32_t)s_pick[0];    // cut score class
         int cum = s_pick[1];                           // entries with score < sstar (all selected)
         const int cls_n_expected = s_pick[2];
-        __syncthreads();
-        // ---- 6. dense list of the cut class; Java hash only for its members; exact select inside the class on
-        //         key2 = (Java bucket << 16) | first position, 8 bits per level ----
-        const int bits2 = cb + 16;
-        uint32_t prefix = 0; int used = 0;
         const bool need_levels = cum + cls_n_expected != want;
-        if (need_levels) {
-            for (int e0 = 0; e0 < n_raw; e0 += RQ_THREADS) {
-                const int e = e0 + tid;
-                const bool in = e < n_raw && best_s[e] == sstar && sstar != 255;
-                const unsigned bal = __ballot_sync(0xffffffffu, in);
-                int base = 0;
-                if (lane == 0 && bal) base = atomicAdd(&s_ncls, __popc(bal));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (in) cls[base + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)e;
+        // ---- 6. one scan of the positions that can hold a score <= s*: the visits whose own score is <= s* (singles), and the
+        //         worklist (first occurrences of duplicated ids carry their minimum over all visits).  Scores below s* are selected
+        //         outright; the cut class is listed for the exact select on (Java bucket, first position). ----
+        {
+            bool low = false;
+            if (tid < nvis) low = vlen_s[tid] != 0 && (uint32_t)vs_s[tid] <= sstar;
+            const int slot = list_slot(&s_nlow, low, lane);
+            if (low) lowvis_s[slot] = (uint16_t)tid;
+        }
+        __syncthreads();                                               // also: every thread has read s_pick
+        {
+            const int n_low = s_nlow * kBlock;
+            const int n_dup = n_inv == 0 ? 0 : (wl_ok ? n_inv : n_raw);
+            for (int i0 = 0; i0 < n_low + n_dup; i0 += RQ_THREADS) {
+                const int i = i0 + tid;
+                int e = -1; uint32_t sc = 255;
+                if (i < n_low) {
+                    e = (int)lowvis_s[i >> 6] * kBlock + (i & 63);
+                    const uint32_t b = best_s[e];
+                    sc = b < RQ_DUP ? b : 255u;                         // singles only; duplicates are taken from the worklist
+                } else if (i < n_low + n_dup) {
+                    e = wl_ok ? (int)wl[i - n_low] : i - n_low;
+                    const uint32_t b = best_s[e];
+                    sc = (b >= RQ_DUP && b < 254u) ? (b & 0x7fu) : 255u;
+                }
+                const bool below = sc < sstar || (sc == sstar && !need_levels && sc != 255u);
+                const bool incls = need_levels && sc == sstar && sc != 255u;
+                const int a = list_slot(&s_m, below, lane);
+                if (below && a < sort_n) sel[a] = (uint16_t)e;
+                const int c = list_slot(&s_ncls, incls, lane);
+                if (incls) cls[c] = (uint16_t)e;
             }
-            __syncthreads();
+        }
+        __syncthreads();
+        // ---- 7. exact select inside the cut class on key2 = (Java bucket << 16) | first position, 8 bits per level ----
+        if (need_levels) {
+            const int bits2 = cb + 16;
+            uint32_t prefix = 0; int used = 0;
             const int ncls = s_ncls;
             for (int i = tid; i < ncls; i += RQ_THREADS) { const uint32_t e = cls[i]; next_s[e] = (uint16_t)(java_hash_decimal(ids_s[e]) & 0xffffu); }
             __syncthreads();
@@ -669,41 +700,32 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) route_fast_kernel(RoutingView r
                 __syncthreads();
                 if (cum + bin == want || used >= bits2) break;
             }
-        }
-        const int sel_shift = bits2 - used;
-        // ---- 7. compact the selected positions (exactly `want`): everything below the cut class, plus the chosen part of it ----
-        for (int e0 = 0; e0 < n_raw; e0 += RQ_THREADS) {
-            const int e = e0 + tid;
-            bool sel = false;
-            if (e < n_raw) {
-                const uint32_t sc = best_s[e];
-                if (sc < sstar) sel = true;
-                else if (sc == sstar && sc != 255) {
-                    if (!need_levels) sel = true;
-                    else { const uint32_t key2 = (((uint32_t)next_s[e] & (capF - 1u)) << 16) | (uint32_t)e; sel = (key2 >> sel_shift) <= prefix; }
+            const int sel_shift = bits2 - used;
+            for (int i0 = 0; i0 < ncls; i0 += RQ_THREADS) {
+                const int i = i0 + tid;
+                bool take_it = false; uint32_t e = 0;
+                if (i < ncls) {
+                    e = cls[i];
+                    const uint32_t key2 = (((uint32_t)next_s[e] & (capF - 1u)) << 16) | e;
+                    take_it = (key2 >> sel_shift) <= prefix;
                 }
+                const int a = list_slot(&s_m, take_it, lane);
+                if (take_it && a < sort_n) sel[a] = (uint16_t)e;
             }
-            const unsigned bal = __ballot_sync(0xffffffffu, sel);
-            int base = 0;
-            if (lane == 0 && bal) base = atomicAdd(&s_m, __popc(bal));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (sel) { const int i = base + __popc(bal & ((1u << lane) - 1u)); if (i < sort_n) sid[i] = e; }
+            __syncthreads();
         }
-        __syncthreads();
         const int m = min(s_m, sort_n);
         // one selected entry per thread: full key (score | Java bucket | first position), Java hash evaluated densely here
         for (int i = tid; i < sort_n; i += RQ_THREADS) {
             uint64_t key = ~0ull; int32_t idv = -1;
             if (i < m) {
-                const int e = sid[i];
+                const int e = sel[i];
                 idv = ids_s[e];
                 const uint32_t bucket = java_hash_decimal(idv) & (capF - 1u);
-                key = ((uint64_t)best_s[e] << (cb + 16)) | ((uint64_t)bucket << 16) | (uint64_t)e;
+                key = ((uint64_t)(best_s[e] & 0x7fu) << (cb + 16)) | ((uint64_t)bucket << 16) | (uint64_t)e;
             }
-            skey[i] = key;
+            skey[i] = key; sid[i] = idv;                                // the worklist (which overlaps skey / sid) is dead by now
         }
-        __syncthreads();
-        for (int i = tid; i < sort_n; i += RQ_THREADS) sid[i] = i < m ? ids_s[sid[i]] : -1;
         __syncthreads();
         // ---- 8. bitonic sort: element i lives in thread i (registers), strides < 32 are exchanged with warp shuffles,
         //         larger strides through shared memory ----
@@ -757,13 +779,22 @@ bool route_fast_eligible(const RoutingView &rv, int probes, int64_t hard_cap, in
     const int64_t n_raw = (int64_t)rv.TD * probes * kBlock;
     if (n_raw > 32000) return false;                         // positions and slots carry a 1-bit tag in 16 bits
     if (n_raw - kBlock >= hard_cap) return false;          // the cap could bind: needs the sequential path
-    if (rv.m * rv.lambda > 254) return false;               // score 255 marks non-representative positions
+    if (rv.m * rv.lambda > 126) return false;               // scores are packed into 7 bits (see best_s encoding)
+    if ((int64_t)rv.TD * probes > RQ_THREADS) return false;
     int sort_n = 64; while (sort_n < B) sort_n <<= 1;
     int tbl = 1024; while (tbl < n_raw + n_raw / 4) tbl <<= 1;
     if (tbl > 32768) return false;
-    smem = route_fast_smem(rv.TD, probes, (int)n_raw, tbl, sort_n);
-    if (smem > 227 * 1024 - 2048) return false;
-    x.n_raw = (int)n_raw; x.tbl = tbl; x.sort_n = sort_n;
+    if (tbl < n_raw + sort_n) tbl <<= 1;                    // room for the class list and the selection list
+    if (tbl > 32768) return false;
+    const size_t limit = 227 * 1024 - 2048;
+    const size_t base = route_fast_smem(rv.TD, probes, (int)n_raw, tbl, sort_n, 0);
+    if (base > limit) return false;
+    // worklist of involved positions: wl_extra dedicated entries + the 6*sort_n that overlay skey / sid
+    int64_t wl_extra = std::max<int64_t>(0, n_raw - 6 * sort_n);
+    wl_extra = std::min<int64_t>(wl_extra, (int64_t)(limit - base) / 2);
+    wl_extra &= ~(int64_t)7;                                 // keeps skey 16-byte aligned
+    x.n_raw = (int)n_raw; x.tbl = tbl; x.sort_n = sort_n; x.wl_extra = (int)wl_extra;
+    smem = route_fast_smem(rv.TD, probes, (int)n_raw, tbl, sort_n, (int)wl_extra);
     return true;
 }
 
