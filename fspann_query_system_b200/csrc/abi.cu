@@ -43,6 +43,7 @@ struct fspann_ctx {
     // scratch (grow only)
     DevBuf s_vis_part, s_vis_score, s_vis_n;
     int opt_route_general = 0;   // force the general (sequential, cap-exact) Route kernel
+    int opt_route_wl_extra = -1; // test hook: clamp the fast path's dedicated worklist (forces the no-worklist fallback when exceeded)
     int last_route_path = 0;     // 1 = shared-memory fast path, 2 = general path
     DevBuf s_queries, s_codes, s_cand_ids, s_cand_sc, s_ncand, s_raw, s_uniq_cnt, s_route_scratch, s_overflow;
     DevBuf s_rec_verdict, s_qf32, s_qu8, s_f32_exact;
@@ -187,6 +188,7 @@ int do_route(fspann_ctx *ctx, int64_t Q, const uint64_t *d_codes, int probes, in
     RouteFastExtra fx{};
     size_t fsmem = 0;
     if (!ctx->opt_route_general && route_fast_eligible(rv, probes, hard_cap, B, fx, fsmem)) {
+        if (ctx->opt_route_wl_extra >= 0 && fx.wl_extra > ctx->opt_route_wl_extra) fx.wl_extra = ctx->opt_route_wl_extra & ~7;   // smem size kept
         ENSURE(ctx->s_vis_part, sizeof(int32_t) * (size_t)Q * rv.TD * probes);
         ENSURE(ctx->s_vis_score, (size_t)Q * rv.TD * probes);
         ENSURE(ctx->s_vis_n, (size_t)Q * rv.TD);
@@ -311,6 +313,7 @@ int64_t fspann_ctx_launch_count(const fspann_ctx *ctx) { return ctx ? ctx->launc
 int fspann_set_option(fspann_ctx *ctx, const char *name, int64_t value) {
     if (!ctx || !name) return FSPANN_E_ARG;
     if (!strcmp(name, "route_general")) { ctx->opt_route_general = value != 0; return FSPANN_OK; }
+    if (!strcmp(name, "route_wl_extra")) { ctx->opt_route_wl_extra = (int)value; return FSPANN_OK; }
     return fail(ctx, FSPANN_E_ARG, "unknown option %s", name);
 }
 int64_t fspann_get_info(fspann_ctx *ctx, const char *name) {

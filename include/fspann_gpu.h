@@ -68,8 +68,9 @@ int fspann_ctx_sync(fspann_ctx *ctx);
 int64_t fspann_ctx_launch_count(const fspann_ctx *ctx);
 
 /* Tuning / test switches: "route_general" = 1 forces the general Route kernel (sequential groups, exact HARD_CAP
- * semantics) even where the shared-memory fast path applies.  fspann_get_info: "last_route_path" (1 fast, 2 general),
- * "sm_count". */
+ * semantics) even where the shared-memory fast path applies; "route_wl_extra" = n >= 0 clamps the fast path's dedicated
+ * worklist to n entries (test hook for its overflow fallback), -1 = automatic.  fspann_get_info: "last_route_path"
+ * (1 fast, 2 general), "sm_count". */
 int fspann_set_option(fspann_ctx *ctx, const char *name, int64_t value);
 int64_t fspann_get_info(fspann_ctx *ctx, const char *name);
 

@@ -134,3 +134,40 @@ def test_distance_paths_fp32_exact_and_general_fp64(wg):
             n = len(ref["top_ids"])
             assert got["n_ret"][q] == n and np.array_equal(got["top_ids"][q, :n], ref["top_ids"])
             assert np.array_equal(got["top_dist"][q, :n].view(np.uint64), ref["top_dist"].view(np.uint64))
+
+
+@pytest.mark.parametrize("wl_extra", [-1, 0], ids=["worklist", "worklist-overflow-fallback"])
+def test_route_fast_path_with_every_id_duplicated(world_factory, wl_extra):
+    """Correlated tables: every table reuses table 0's projections (own offsets), so most ids are visited several times per
+    query with different scores and most positions take the fast path's exact (hash + chain) route.  wl_extra=0 clamps the worklist so it overflows and the kernel must fall
+    back to scanning every position.  Order, scores and raw/unique counters must still be the reference's."""
+    import copy
+    base_w = world_factory(**SMALL)
+    g = copy.deepcopy(base_w.g)
+    TD, D = g.T * g.D, g.D
+    for td in range(D, TD):
+        g.alpha[td], g.omega[td] = g.alpha[td % D], g.omega[td % D]     # same projections, different offsets r
+    codes_base = O.tokengen_batch(base_w.base, g)
+    ix = O.index_build(codes_base, g, O.staged_order(base_w.cfg.N))
+    from fspann_query_system_b200.gpu import GpuContext
+    ctx = GpuContext(0)
+    try:
+        ctx.routing_upload(g.dim, g.T, g.D, g.m, g.lam, g.alpha, g.r, g.omega, ix.min_key, ix.max_key, ix.rep, ix.ids)
+        ctx.set_option("route_wl_extra", wl_extra)
+        codes = O.tokengen_batch(base_w.queries, g)
+        for probes, B in [(5, 64), (8, 700)]:
+            out = ctx.route_batch(codes, probes, 1 << 20, B)
+            assert ctx.get_info("last_route_path") == 1
+            tot_raw = tot_unique = 0
+            for q in range(codes.shape[0]):
+                ids, sc, raw, mc = O.route(ix, codes[q], probes, 1 << 20)
+                n = min(B, len(ids))
+                tot_raw += raw; tot_unique += len(ids)
+                assert (out["n_cand"][q], out["unique"][q], out["raw_seen"][q]) == (n, len(ids), raw)
+                assert np.array_equal(out["cand_scores"][q, :n], sc[:n])
+                if mc < 9:
+                    assert np.array_equal(out["cand_ids"][q, :n], ids[:n]), f"query {q}"
+            assert tot_raw > tot_unique                                  # strict improvements (so: duplicates) really occur
+            assert tot_unique < 0.8 * codes.shape[0] * g.T * g.D * probes * 64
+    finally:
+        ctx.close()
