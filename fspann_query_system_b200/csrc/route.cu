@@ -479,7 +479,7 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) route_fast_kernel(RoutingView r
     uint16_t *cls = table;                                                     // after the exact path the table is dead: cut-class list ...
     uint16_t *sel = table + n_raw;                                             // ... and the list of selected positions (sort_n entries)
     __shared__ int32_t s_hist[256];
-    __shared__ int32_t s_raw, s_uniq, s_m, s_ncls, s_nwl, s_nlow, s_pick[3];
+    __shared__ int32_t s_raw, s_uniq, s_m, s_ncls, s_nwl, s_nlow, s_pick[3], s_wsum[32];
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int64_t n_ids = rv.n_ids;
@@ -715,61 +715,118 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) route_fast_kernel(RoutingView r
             __syncthreads();
         }
         const int m = min(s_m, sort_n);
-        // one selected entry per thread: full key (score | Java bucket | first position), Java hash evaluated densely here
-        for (int i = tid; i < sort_n; i += RQ_THREADS) {
-            uint64_t key = ~0ull; int32_t idv = -1;
-            if (i < m) {
-                const int e = sel[i];
-                idv = ids_s[e];
-                const uint32_t bucket = java_hash_decimal(idv) & (capF - 1u);
-                key = ((uint64_t)(best_s[e] & 0x7fu) << (cb + 16)) | ((uint64_t)bucket << 16) | (uint64_t)e;
+        int32_t *out_id = p.cand_ids + (size_t)q * p.B, *out_sc = p.cand_scores + (size_t)q * p.B;
+        int sb = 0; while ((1u << sb) <= sstar) sb++;                   // bits that hold every selected score (<= s*)
+        int rb = 0; while ((1 << rb) < sort_n) rb++;
+        if (sort_n <= RQ_THREADS && sb + cb + rb <= 32) {
+            // ---- 8a. 32-bit keys: (score | Java bucket | rank of the first position among the selected entries).  The rank comes
+            //          from a bitmap over positions + prefix popcounts, so it orders exactly like the position itself; the id is
+            //          parked in sid[rank] and only the key is sorted (one shuffle per compare-exchange). ----
+            uint32_t *bm = table_w;                                       // [nw] (the class list is dead)
+            const int nw = (n_raw + 31) >> 5;
+            uint16_t *pref = reinterpret_cast<uint16_t *>(bm + nw);       // [nw]; both end below the selection list at table + n_raw
+            uint32_t *key32 = reinterpret_cast<uint32_t *>(skey);
+            for (int i = tid; i < nw; i += RQ_THREADS) bm[i] = 0u;
+            __syncthreads();
+            const int my_e = tid < m ? (int)sel[tid] : -1;
+            if (my_e >= 0) atomicOr(&bm[my_e >> 5], 1u << (my_e & 31));
+            __syncthreads();
+            for (int w0 = 0; w0 < nw; w0 += RQ_THREADS) {                 // one pass (nw <= 1000)
+                const int w = w0 + tid;
+                const int c = w < nw ? __popc(bm[w]) : 0;
+                int tot;
+                const int ex = warp_excl_scan(c, lane, tot);
+                if (lane == 31) s_wsum[tid >> 5] = ex + c;
+                __syncthreads();
+                if (tid < 32) { int t2; const int v = s_wsum[tid]; const int e2 = warp_excl_scan(v, lane, t2); s_wsum[tid] = e2; }
+                __syncthreads();
+                if (w < nw) pref[w] = (uint16_t)(s_wsum[tid >> 5] + ex);
             }
-            skey[i] = key; sid[i] = idv;                                // the worklist (which overlaps skey / sid) is dead by now
-        }
-        __syncthreads();
-        // ---- 8. bitonic sort: element i lives in thread i (registers), strides < 32 are exchanged with warp shuffles,
-        //         larger strides through shared memory ----
-        if (sort_n <= RQ_THREADS) {
+            __syncthreads();
+            uint32_t a = 0xffffffffu;
+            if (my_e >= 0) {
+                const int32_t idv = ids_s[my_e];
+                const uint32_t rank = (uint32_t)pref[my_e >> 5] + (uint32_t)__popc(bm[my_e >> 5] & ((1u << (my_e & 31)) - 1u));
+                const uint32_t bucket = java_hash_decimal(idv) & (capF - 1u);
+                a = ((uint32_t)(best_s[my_e] & 0x7fu) << (cb + rb)) | (bucket << rb) | rank;
+                sid[rank] = idv;                                          // the worklist (which overlaps skey / sid) is dead by now
+            }
             const int i = tid;
-            uint64_t a = i < sort_n ? skey[i] : ~0ull;
-            int32_t av = i < sort_n ? sid[i] : -1;
             for (int k = 2; k <= sort_n; k <<= 1) {
                 for (int j = k >> 1; j > 0; j >>= 1) {
                     const bool asc = (i & k) == 0;
-                    uint64_t b; int32_t bv;
+                    uint32_t b;
                     if (j >= 32) {
                         __syncthreads();
-                        if (i < sort_n) { skey[i] = a; sid[i] = av; }
+                        if (i < sort_n) key32[i] = a;
                         __syncthreads();
-                        b = i < sort_n ? skey[i ^ j] : ~0ull; bv = i < sort_n ? sid[i ^ j] : -1;
+                        b = i < sort_n ? key32[i ^ j] : 0xffffffffu;
                     } else {
-                        b = __shfl_xor_sync(0xffffffffu, a, j); bv = __shfl_xor_sync(0xffffffffu, av, j);
+                        b = __shfl_xor_sync(0xffffffffu, a, j);
                     }
                     const bool lower = (i & j) == 0;                // this thread keeps the smaller of the pair when ascending
                     const bool take_b = (lower == asc) ? (b < a) : (b > a);
-                    if (take_b) { a = b; av = bv; }
+                    if (take_b) a = b;
                 }
             }
             __syncthreads();
-            if (i < sort_n) { skey[i] = a; sid[i] = av; }
-            __syncthreads();
+            if (i < want) { out_id[i] = sid[a & ((1u << rb) - 1u)]; out_sc[i] = (int32_t)(a >> (cb + rb)); }
         } else {
-            for (int k = 2; k <= sort_n; k <<= 1) {
-                for (int j = k >> 1; j > 0; j >>= 1) {
-                    for (int i = tid; i < sort_n; i += RQ_THREADS) {
-                        const int ixj = i ^ j;
-                        if (ixj > i) {
-                            const uint64_t a = skey[i], b = skey[ixj];
-                            const bool asc = (i & k) == 0;
-                            if ((a > b) == asc) { skey[i] = b; skey[ixj] = a; const int32_t t = sid[i]; sid[i] = sid[ixj]; sid[ixj] = t; }
+            // one selected entry per thread: full key (score | Java bucket | first position), Java hash evaluated densely here
+            for (int i = tid; i < sort_n; i += RQ_THREADS) {
+                uint64_t key = ~0ull; int32_t idv = -1;
+                if (i < m) {
+                    const int e = sel[i];
+                    idv = ids_s[e];
+                    const uint32_t bucket = java_hash_decimal(idv) & (capF - 1u);
+                    key = ((uint64_t)(best_s[e] & 0x7fu) << (cb + 16)) | ((uint64_t)bucket << 16) | (uint64_t)e;
+                }
+                skey[i] = key; sid[i] = idv;                                // the worklist (which overlaps skey / sid) is dead by now
+            }
+            __syncthreads();
+            // ---- 8. bitonic sort: element i lives in thread i (registers), strides < 32 are exchanged with warp shuffles,
+            //         larger strides through shared memory ----
+            if (sort_n <= RQ_THREADS) {
+                const int i = tid;
+                uint64_t a = i < sort_n ? skey[i] : ~0ull;
+                int32_t av = i < sort_n ? sid[i] : -1;
+                for (int k = 2; k <= sort_n; k <<= 1) {
+                    for (int j = k >> 1; j > 0; j >>= 1) {
+                        const bool asc = (i & k) == 0;
+                        uint64_t b; int32_t bv;
+                        if (j >= 32) {
+                            __syncthreads();
+                            if (i < sort_n) { skey[i] = a; sid[i] = av; }
+                            __syncthreads();
+                            b = i < sort_n ? skey[i ^ j] : ~0ull; bv = i < sort_n ? sid[i ^ j] : -1;
+                        } else {
+                            b = __shfl_xor_sync(0xffffffffu, a, j); bv = __shfl_xor_sync(0xffffffffu, av, j);
                         }
+                        const bool lower = (i & j) == 0;                // this thread keeps the smaller of the pair when ascending
+                        const bool take_b = (lower == asc) ? (b < a) : (b > a);
+                        if (take_b) { a = b; av = bv; }
                     }
-                    __syncthreads();
+                }
+                __syncthreads();
+                if (i < sort_n) { skey[i] = a; sid[i] = av; }
+                __syncthreads();
+            } else {
+                for (int k = 2; k <= sort_n; k <<= 1) {
+                    for (int j = k >> 1; j > 0; j >>= 1) {
+                        for (int i = tid; i < sort_n; i += RQ_THREADS) {
+                            const int ixj = i ^ j;
+                            if (ixj > i) {
+                                const uint64_t a = skey[i], b = skey[ixj];
+                                const bool asc = (i & k) == 0;
+                                if ((a > b) == asc) { skey[i] = b; skey[ixj] = a; const int32_t t = sid[i]; sid[i] = sid[ixj]; sid[ixj] = t; }
+                            }
+                        }
+                        __syncthreads();
+                    }
                 }
             }
+            for (int i = tid; i < want; i += RQ_THREADS) { out_id[i] = sid[i]; out_sc[i] = (int32_t)(skey[i] >> (cb + 16)); }
         }
-        int32_t *out_id = p.cand_ids + (size_t)q * p.B, *out_sc = p.cand_scores + (size_t)q * p.B;
-        for (int i = tid; i < want; i += RQ_THREADS) { out_id[i] = sid[i]; out_sc[i] = (int32_t)(skey[i] >> (cb + 16)); }
         if (tid == 0) { p.n_cand[q] = want; p.unique[q] = n_unique; p.raw_seen[q] = s_raw; }
     }
 }
