@@ -366,12 +366,22 @@ class ForwardSecureANNSystem:
         self.gpu.keys_set(v, self.keys.derive(v))
         return v
 
-    def reencryptTouched(self, ids, fresh_ivs, target_version: int):
-        done = HS.migrate(self.store_iv, self.store_ct, self.store_ver, ids, fresh_ivs, target_version, self.keys)
-        if done:
-            d = np.asarray(done, dtype=np.int32)
-            self.gpu.store_update(d, self.store_iv[d], self.store_ct[d], self.store_ver[d])
-        return done
+    def reencryptTouched(self, ids, fresh_ivs, target_version: int, on_device: bool = True):
+        """KRS:215-289.  on_device=True: Migrate runs on the GPU in place in the HBM store (fspann_migrate) and the new records
+        come back for the host's persistent copy; on_device=False: the host re-encrypts (the reference's own arrangement) and
+        mirrors the result with fspann_store_update."""
+        ids = np.asarray(ids, dtype=np.int32)
+        if not on_device:
+            done = HS.migrate(self.store_iv, self.store_ct, self.store_ver, ids, fresh_ivs, target_version, self.keys)
+            if done:
+                d = np.asarray(done, dtype=np.int32)
+                self.gpu.store_update(d, self.store_iv[d], self.store_ct[d], self.store_ver[d])
+            return done
+        out = self.gpu.migrate(ids, fresh_ivs, target_version)
+        sel = np.nonzero(out["reencrypted"])[0]
+        d = ids[sel]
+        self.store_iv[d], self.store_ct[d], self.store_ver[d] = out["iv"][sel], out["ct"][sel], target_version   # saveEncryptedPoint (KRS:268)
+        return d.tolist()
 
     def retire(self, version: int) -> bool:
         if np.any(self.store_ver == version):                       # KM:287-294: refuse while vectors are still bound

@@ -52,6 +52,7 @@ struct fspann_ctx {
     DevBuf s_cnt, s_flag, s_fill, s_uniq, s_pairs, s_bsums, s_totals, s_dist, s_verdict;
     DevBuf s_topk_ids, s_topk_dist, s_topk_rank, s_nret, s_ndec, s_counters;
     DevBuf s_stage_a, s_stage_b, s_stage_c;  // upload staging
+    DevBuf m_list, m_gid, m_iv, m_verdict, m_flag, m_rec, m_vec, m_out_iv, m_out_ct, m_out_ver;  // Migrate / bulk encryption
     DevBuf r_rows, r_queries, r_codes, r_topk_ids, r_topk_dist, r_nret, r_counters;  // retry subset
     DevBuf t_cand_ids, t_cand_sc, t_ncand, t_raw, t_uniq_cnt, t_ndec;               // retry subset route outputs
 
@@ -294,7 +295,8 @@ void fspann_ctx_destroy(fspann_ctx *ctx) {
                       &ctx->s_flag, &ctx->s_fill, &ctx->s_uniq, &ctx->s_pairs, &ctx->s_bsums, &ctx->s_totals, &ctx->s_dist, &ctx->s_verdict,
                       &ctx->s_topk_ids, &ctx->s_topk_dist, &ctx->s_topk_rank, &ctx->s_nret, &ctx->s_ndec, &ctx->s_counters, &ctx->s_stage_a, &ctx->s_stage_b,
                       &ctx->s_stage_c, &ctx->s_vis_part, &ctx->s_vis_score, &ctx->s_vis_n, &ctx->r_rows, &ctx->r_queries, &ctx->r_codes, &ctx->r_topk_ids, &ctx->r_topk_dist, &ctx->r_nret,
-                      &ctx->r_counters, &ctx->t_cand_ids, &ctx->t_cand_sc, &ctx->t_ncand, &ctx->t_raw, &ctx->t_uniq_cnt, &ctx->t_ndec};
+                      &ctx->r_counters, &ctx->t_cand_ids, &ctx->t_cand_sc, &ctx->t_ncand, &ctx->t_raw, &ctx->t_uniq_cnt, &ctx->t_ndec,
+                      &ctx->m_list, &ctx->m_gid, &ctx->m_iv, &ctx->m_verdict, &ctx->m_flag, &ctx->m_rec, &ctx->m_vec, &ctx->m_out_iv, &ctx->m_out_ct, &ctx->m_out_ver};
     for (DevBuf *b : bufs) release(*b);
     for (int i = 0; i < 7; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -455,6 +457,126 @@ int fspann_store_update(fspann_ctx *ctx, int64_t n, const int32_t *ids, const ui
         local[(size_t)i] = (int32_t)(ids[i] - ctx->sv.id_base);
     }
     return store_write(ctx, n, local.data(), iv, ct, key_version);
+}
+
+// ---- Migrate on the device: KeyRotationServiceImpl.reencryptTouched (KRS:215-289) -------------------------------------------
+int fspann_migrate(fspann_ctx *ctx, int64_t n, const int32_t *ids, const uint8_t *fresh_ivs, int32_t target_version,
+                   uint8_t *reencrypted_out, uint8_t *iv_out, uint8_t *ct_out, int64_t *n_reencrypted_out) {
+    if (!ctx) return FSPANN_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (n_reencrypted_out) *n_reencrypted_out = 0;
+    if (!ctx->store_ready) return fail(ctx, FSPANN_E_STATE, "record store not uploaded");
+    if (n < 0 || (n > 0 && (!ids || !fresh_ivs))) return fail(ctx, FSPANN_E_ARG, "null array");
+    if (!ctx->keys.count(target_version)) return fail(ctx, FSPANN_E_ARG, "target key version %d is not live (KRS:82-88)", target_version);
+    if (reencrypted_out) memset(reencrypted_out, 0, (size_t)n);
+    if (n == 0) return FSPANN_OK;                                                      // KRS:220-223
+    // new LinkedHashSet<>(touchedIds) (KRS:232): first occurrence of every id, in order; ids this store does not hold are
+    // skipped like a null loadEncryptedPoint (KRS:243).  pos[] = position of the kept entry in the caller's list.
+    std::vector<int32_t> local, pos;
+    {
+        std::vector<uint8_t> seen((size_t)ctx->sv.N, 0);
+        for (int64_t i = 0; i < n; i++) {
+            const int64_t li = (int64_t)ids[i] - ctx->sv.id_base;
+            if (li < 0 || li >= ctx->sv.N || seen[(size_t)li]) continue;
+            seen[(size_t)li] = 1;
+            local.push_back((int32_t)li); pos.push_back((int32_t)i);
+        }
+    }
+    const int dim = ctx->sv.dim;
+    const size_t ct_row = 8 * (size_t)dim + 16;
+    const int64_t chunk = 131072;
+    int64_t total = 0;
+    std::vector<uint8_t> h_iv, h_flag, h_oiv, h_oct;
+    for (int64_t s0 = 0; s0 < (int64_t)local.size(); s0 += chunk) {
+        const int c = (int)std::min<int64_t>(chunk, (int64_t)local.size() - s0);
+        ENSURE(ctx->m_list, sizeof(int32_t) * (size_t)c);
+        ENSURE(ctx->m_iv, (size_t)c * 12);
+        ENSURE(ctx->m_verdict, (size_t)c);
+        ENSURE(ctx->m_flag, (size_t)c);
+        h_iv.resize((size_t)c * 12);
+        for (int j = 0; j < c; j++) memcpy(&h_iv[(size_t)j * 12], fresh_ivs + (size_t)pos[(size_t)(s0 + j)] * 12, 12);
+        CK(cudaMemcpyAsync(ctx->m_list.p, local.data() + s0, sizeof(int32_t) * (size_t)c, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->m_iv.p, h_iv.data(), (size_t)c * 12, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemsetAsync(ctx->m_verdict.p, FSPANN_V_NO_KEY, (size_t)c, ctx->stream));   // getVersion(old) throws -> skip (KRS:277)
+        // decryptFromPoint under the stored version: authenticate first ...
+        LAUNCHED(launch_gcm_tag(ctx->stream, ctx->sv, (const int32_t *)ctx->m_list.p, nullptr, c, (uint8_t *)ctx->m_verdict.p, nullptr, ctx->sm_count));
+        // ... then decrypt + re-encrypt under the target version with the fresh IV, in place, and seal with the new tag
+        LAUNCHED(launch_migrate_xcrypt(ctx->stream, ctx->sv, c, (const int32_t *)ctx->m_list.p, (const uint8_t *)ctx->m_iv.p, target_version,
+                                       (const uint8_t *)ctx->m_verdict.p, (uint8_t *)ctx->m_flag.p, ctx->sm_count));
+        LAUNCHED(launch_gcm_tag(ctx->stream, ctx->sv, (const int32_t *)ctx->m_list.p, nullptr, c, nullptr, (const uint8_t *)ctx->m_flag.p, ctx->sm_count));
+        h_flag.resize((size_t)c);
+        CK(cudaMemcpyAsync(h_flag.data(), ctx->m_flag.p, (size_t)c, cudaMemcpyDeviceToHost, ctx->stream));
+        if (iv_out || ct_out) {
+            ENSURE(ctx->m_out_iv, (size_t)c * 12);
+            ENSURE(ctx->m_out_ct, (size_t)c * ct_row);
+            ENSURE(ctx->m_out_ver, sizeof(int32_t) * (size_t)c);
+            LAUNCHED(launch_store_unpack(ctx->stream, ctx->sv.rec, ctx->sv.rec_stride, dim, c, (const int32_t *)ctx->m_list.p, (uint8_t *)ctx->m_out_iv.p,
+                                         (uint8_t *)ctx->m_out_ct.p, (int32_t *)ctx->m_out_ver.p));
+            h_oiv.resize((size_t)c * 12); h_oct.resize((size_t)c * ct_row);
+            CK(cudaMemcpyAsync(h_oiv.data(), ctx->m_out_iv.p, (size_t)c * 12, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(h_oct.data(), ctx->m_out_ct.p, (size_t)c * ct_row, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (int j = 0; j < c; j++) {
+            if (!h_flag[(size_t)j]) continue;
+            const size_t at = (size_t)pos[(size_t)(s0 + j)];
+            total++;
+            if (reencrypted_out) reencrypted_out[at] = 1;
+            if (iv_out) memcpy(iv_out + at * 12, &h_oiv[(size_t)j * 12], 12);
+            if (ct_out) memcpy(ct_out + at * ct_row, &h_oct[(size_t)j * ct_row], ct_row);
+        }
+    }
+    if (n_reencrypted_out) *n_reencrypted_out = total;
+    return FSPANN_OK;
+}
+
+// ---- Setup-side bulk encryption: AesGcmCryptoService.encryptToPoint (AGC:55-112) for n vectors -----------------------------
+int fspann_encrypt_batch(fspann_ctx *ctx, int64_t n, int32_t dim, const int32_t *ids, const double *vectors, const uint8_t *ivs,
+                         int32_t version, uint8_t *ct_out) {
+    if (!ctx) return FSPANN_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (n < 0 || dim <= 0) return fail(ctx, FSPANN_E_ARG, "non-positive n/dim");
+    if (n == 0) return FSPANN_OK;
+    if (!ids || !vectors || !ivs || !ct_out) return fail(ctx, FSPANN_E_ARG, "id, plaintext, and key cannot be null");   // AGC:57-59
+    if (!ctx->keys.count(version)) return fail(ctx, FSPANN_E_ARG, "key version %d is not live (KRS:82-88)", version);
+    for (int64_t i = 0; i < n; i++) if (ids[i] < 0) return fail(ctx, FSPANN_E_ARG, "negative id %d", ids[i]);
+    const size_t ct_row = 8 * (size_t)dim + 16;
+    const int64_t stride = ((32 + 8LL * dim) + 15) / 16 * 16;
+    const int64_t chunk = 131072;
+    StoreView tv = ctx->sv;                       // key ring / tables of the context, records in a scratch buffer
+    tv.dim = dim; tv.rec_stride = stride; tv.id_base = 0; tv.deleted = nullptr; tv.n_deleted = 0;
+    for (int64_t s0 = 0; s0 < n; s0 += chunk) {
+        const int c = (int)std::min<int64_t>(chunk, n - s0);
+        ENSURE(ctx->m_rec, (size_t)c * stride + 64);
+        ENSURE(ctx->m_vec, sizeof(double) * (size_t)c * dim);
+        ENSURE(ctx->m_iv, (size_t)c * 12);
+        ENSURE(ctx->m_gid, sizeof(int32_t) * (size_t)c);
+        ENSURE(ctx->m_list, sizeof(int32_t) * (size_t)c);
+        ENSURE(ctx->m_flag, (size_t)c);
+        ENSURE(ctx->m_out_iv, (size_t)c * 12);
+        ENSURE(ctx->m_out_ct, (size_t)c * ct_row);
+        ENSURE(ctx->m_out_ver, sizeof(int32_t) * (size_t)c);
+        tv.rec = (const uint8_t *)ctx->m_rec.p; tv.N = c; tv.n_global = c;
+        std::vector<int32_t> iota((size_t)c);
+        for (int j = 0; j < c; j++) iota[(size_t)j] = j;
+        CK(cudaMemsetAsync(ctx->m_rec.p, 0, (size_t)c * stride + 64, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->m_vec.p, vectors + (size_t)s0 * dim, sizeof(double) * (size_t)c * dim, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->m_iv.p, ivs + (size_t)s0 * 12, (size_t)c * 12, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->m_gid.p, ids + s0, sizeof(int32_t) * (size_t)c, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->m_list.p, iota.data(), sizeof(int32_t) * (size_t)c, cudaMemcpyHostToDevice, ctx->stream));
+        LAUNCHED(launch_encrypt_xcrypt(ctx->stream, tv, c, (const double *)ctx->m_vec.p, (const uint8_t *)ctx->m_iv.p, version, (uint8_t *)ctx->m_flag.p,
+                                       ctx->sm_count));
+        LAUNCHED(launch_gcm_tag(ctx->stream, tv, (const int32_t *)ctx->m_list.p, (const int32_t *)ctx->m_gid.p, c, nullptr, (const uint8_t *)ctx->m_flag.p,
+                                ctx->sm_count));
+        LAUNCHED(launch_store_unpack(ctx->stream, tv.rec, stride, dim, c, nullptr, (uint8_t *)ctx->m_out_iv.p, (uint8_t *)ctx->m_out_ct.p,
+                                     (int32_t *)ctx->m_out_ver.p));
+        CK(cudaMemcpyAsync(ct_out + (size_t)s0 * ct_row, ctx->m_out_ct.p, (size_t)c * ct_row, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));   // iota / staging reuse
+    }
+    // the plaintext staging buffer is wiped: vectors never outlive the call on the device
+    CK(cudaMemsetAsync(ctx->m_vec.p, 0, ctx->m_vec.bytes, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FSPANN_OK;
 }
 
 int fspann_keys_set(fspann_ctx *ctx, int32_t version, const uint8_t key[32]) {

@@ -123,6 +123,14 @@ int launch_counters(cudaStream_t s, int64_t Q, const int32_t *raw, const int32_t
 int launch_gather_rows(cudaStream_t s, const void *src, void *dst, const int32_t *rows, int64_t n_rows, int64_t row_bytes, bool scatter);
 int launch_store_pack(cudaStream_t s, uint8_t *rec, int64_t rec_stride, int32_t dim, int64_t n, const int32_t *ids /* or null */,
                       const uint8_t *iv, const uint8_t *ct, const int32_t *ver);
+int launch_gcm_tag(cudaStream_t s, const StoreView &sv, const int32_t *list, const int32_t *gid, int n_list, uint8_t *verdict,
+                   const uint8_t *write_flag, int sm_count);
+int launch_migrate_xcrypt(cudaStream_t s, const StoreView &sv, int n, const int32_t *list, const uint8_t *fresh_iv, int32_t target_version,
+                          const uint8_t *verdict, uint8_t *flag, int sm_count);
+int launch_encrypt_xcrypt(cudaStream_t s, const StoreView &sv, int n, const double *vectors, const uint8_t *ivs, int32_t version, uint8_t *flag,
+                          int sm_count);
+int launch_store_unpack(cudaStream_t s, const uint8_t *rec, int64_t rec_stride, int32_t dim, int64_t n, const int32_t *rows, uint8_t *iv,
+                        uint8_t *ct, int32_t *ver);
 int launch_debug_decrypt(cudaStream_t s, const StoreView &sv, int64_t n, const int32_t *ids, double *pt, uint8_t *verdict);
 
 }  // namespace fsp

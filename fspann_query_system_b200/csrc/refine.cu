@@ -20,6 +20,11 @@ namespace fsp {
 // ------------------------------------------------------------------------------------------------------------------
 // grouping: pairs (q, rank) -> per-record lists
 // ------------------------------------------------------------------------------------------------------------------
+// record bytes are read-only inside every kernel that loads them through this helper (Migrate rewrites a record only after
+// its warp has loaded everything it needs from it), so the non-coherent path is safe
+template <class T>
+__device__ __forceinline__ T ld_rec(const T *p) { return __ldg(p); }
+
 __device__ __forceinline__ bool is_deleted(const StoreView &sv, int32_t id) {
     return sv.deleted && id < sv.n_deleted && sv.deleted[id];
 }
@@ -361,10 +366,11 @@ struct ShoupSmem {
     }
 };
 
-// GHASH + tag check of one record by ONE lane.  `sh` = Shoup table of the record's key version, rk = its round keys.
+// GCM tag of one record by ONE lane: tag = GHASH_H(AAD || ciphertext || lengths) ^ E_K(J0).  `sh` = Shoup table of the key
+// version named in the record header, rk = its round keys, id = the GLOBAL id the AAD binds (EP:80-83).
 template <class SH>
-__device__ __forceinline__ bool lane_verify_record(const StoreView &sv, const uint8_t *rec, int32_t id, uint4 hdr, const SH &sh,
-                                                   const TeSmem &te, const RkSmem &rk) {
+__device__ __forceinline__ void lane_gcm_tag(const StoreView &sv, const uint8_t *rec, int32_t id, uint4 hdr, const SH &sh, const TeSmem &te,
+                                             const RkSmem &rk, uint32_t tag[4]) {
     const int dim = sv.dim, nbytes = 8 * dim, c = (nbytes + 15) >> 4;
     const int32_t version = (int32_t)hdr.w;
     // ---- GHASH over AAD || ciphertext || lengths ----
@@ -380,7 +386,7 @@ __device__ __forceinline__ bool lane_verify_record(const StoreView &sv, const ui
     for (int b0 = 0; b0 < c; b0 += 8) {
         uint4 w[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) w[k] = (b0 + k < c) ? __ldg(ctv + b0 + k) : make_uint4(0, 0, 0, 0);   // 128 contiguous bytes of this record
+        for (int k = 0; k < 8; k++) w[k] = (b0 + k < c) ? ld_rec(ctv + b0 + k) : make_uint4(0, 0, 0, 0);   // 128 contiguous bytes of this record
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             if (b0 + k < c) {
@@ -397,13 +403,26 @@ __device__ __forceinline__ bool lane_verify_record(const StoreView &sv, const ui
     // ---- tag = GHASH ^ E_K(J0), J0 = IV || 0x00000001 ----
     uint32_t ej0[4];
     aes256_encrypt(te, rk, bswap32(hdr.x), bswap32(hdr.y), bswap32(hdr.z), 1u, ej0);
-    const uint2 *tagp = reinterpret_cast<const uint2 *>(rec + 16 + nbytes);
-    const uint2 t0 = __ldg(tagp), t1 = __ldg(tagp + 1);
-    return (y0 ^ ej0[0]) == bswap32(t0.x) && (y1 ^ ej0[1]) == bswap32(t0.y) && (y2 ^ ej0[2]) == bswap32(t1.x) && (y3 ^ ej0[3]) == bswap32(t1.y);
+    tag[0] = y0 ^ ej0[0]; tag[1] = y1 ^ ej0[1]; tag[2] = y2 ^ ej0[2]; tag[3] = y3 ^ ej0[3];
 }
 
-__global__ void __launch_bounds__(VF_THREADS) refine_verify_kernel(StoreView sv, RefineParams p) {
-    extern __shared__ __align__(16) unsigned char vf_smem[];
+// GHASH + tag check of one record by ONE lane (AGC:145-158: doFinal throws AEADBadTagException on a mismatch).
+template <class SH>
+__device__ __forceinline__ bool lane_verify_record(const StoreView &sv, const uint8_t *rec, int32_t id, uint4 hdr, const SH &sh,
+                                                   const TeSmem &te, const RkSmem &rk) {
+    uint32_t tag[4];
+    lane_gcm_tag(sv, rec, id, hdr, sh, te, rk, tag);
+    const uint2 *tagp = reinterpret_cast<const uint2 *>(rec + 16 + 8 * sv.dim);
+    const uint2 t0 = ld_rec(tagp), t1 = ld_rec(tagp + 1);
+    return tag[0] == bswap32(t0.x) && tag[1] == bswap32(t0.y) && tag[2] == bswap32(t1.x) && tag[3] == bswap32(t1.y);
+}
+
+// Shared body of the authentication kernels: one LANE per listed record, one key version (= one Shoup table in shared memory)
+// at a time.  list[u] = record index inside this store view; gid[u] = global id for the AAD (or nullptr: index + id_base).
+// write_flag == nullptr: verify, verdict[u] = OK / TAG_FAIL (records of unknown versions keep their preset verdict).
+// write_flag != nullptr: (re-)compute and STORE the tag of every record with write_flag[u] != 0 (encrypt / Migrate).
+__device__ __forceinline__ void gcm_tag_body(const StoreView &sv, const int32_t *__restrict__ list, const int32_t *__restrict__ gid, int n_list,
+                                             uint8_t *__restrict__ verdict, const uint8_t *__restrict__ write_flag, unsigned char *vf_smem) {
     uint4 *shoup_s = reinterpret_cast<uint4 *>(vf_smem);                      // [16][256]
     uint32_t *te_s = reinterpret_cast<uint32_t *>(shoup_s + 4096);            // [256][32]
     uint32_t *s_rk = te_s + 256 * 32;                                         // [kMaxKeys][60]
@@ -415,8 +434,7 @@ __global__ void __launch_bounds__(VF_THREADS) refine_verify_kernel(StoreView sv,
     for (int i = tid; i < kMaxKeys; i += VF_THREADS) s_ver[i] = i < nkeys ? sv.keys->version[i] : INT32_MIN;
     const TeSmem te{te_s + lane};
     const ShoupSmem sh{shoup_s, lane & 15};
-    const int n_uniq = p.totals[1];
-    const int n_chunks = (n_uniq + 31) >> 5;
+    const int n_chunks = (n_list + 31) >> 5;
     const int warps_total = gridDim.x * (VF_THREADS / 32);
 
     for (int vi = 0; vi < nkeys; vi++) {
@@ -427,16 +445,53 @@ __global__ void __launch_bounds__(VF_THREADS) refine_verify_kernel(StoreView sv,
         const RkSmem rk{s_rk + vi * 60};
         for (int chunk = blockIdx.x * (VF_THREADS / 32) + warp; chunk < n_chunks; chunk += warps_total) {
             const int u = (chunk << 5) + lane;
-            if (u >= n_uniq) continue;
-            const int32_t li = p.uniq[u];                                   // index inside this shard
-            const int32_t id = (int32_t)(li + sv.id_base);                  // global id: what the AAD binds (EP:80-83)
+            if (u >= n_list) continue;
+            if (write_flag && !write_flag[u]) continue;
+            const int32_t li = list[u];                                     // index inside this shard
+            const int32_t id = gid ? gid[u] : (int32_t)(li + sv.id_base);   // global id: what the AAD binds (EP:80-83)
             const uint8_t *rec = sv.rec + (size_t)li * sv.rec_stride;
-            const uint4 hdr = __ldg(reinterpret_cast<const uint4 *>(rec));
+            const uint4 hdr = ld_rec(reinterpret_cast<const uint4 *>(rec));
             if ((int32_t)hdr.w != version) continue;
-            const bool ok = lane_verify_record(sv, rec, id, hdr, sh, te, rk);
-            p.rec_verdict[u] = ok ? FSPANN_V_OK : FSPANN_V_TAG_FAIL;        // AGC:159-165
+            if (!write_flag) {
+                const bool ok = lane_verify_record(sv, rec, id, hdr, sh, te, rk);
+                verdict[u] = ok ? FSPANN_V_OK : FSPANN_V_TAG_FAIL;          // AGC:159-165
+            } else {
+                uint32_t tag[4];
+                lane_gcm_tag(sv, rec, id, hdr, sh, te, rk, tag);
+                uint2 *tagp = reinterpret_cast<uint2 *>(const_cast<uint8_t *>(rec) + 16 + 8 * sv.dim);
+                tagp[0] = make_uint2(bswap32(tag[0]), bswap32(tag[1]));
+                tagp[1] = make_uint2(bswap32(tag[2]), bswap32(tag[3]));
+            }
         }
     }
+}
+
+__global__ void __launch_bounds__(VF_THREADS) refine_verify_kernel(StoreView sv, RefineParams p) {
+    extern __shared__ __align__(16) unsigned char vf_smem[];
+    gcm_tag_body(sv, p.uniq, nullptr, p.totals[1], p.rec_verdict, nullptr, vf_smem);
+}
+
+// The same over an explicit host-sized list (Migrate / bulk encryption).
+__global__ void __launch_bounds__(VF_THREADS) gcm_tag_kernel(StoreView sv, const int32_t *list, const int32_t *gid, int n_list, uint8_t *verdict,
+                                                             const uint8_t *write_flag) {
+    extern __shared__ __align__(16) unsigned char vf_smem[];
+    gcm_tag_body(sv, list, gid, n_list, verdict, write_flag, vf_smem);
+}
+
+static size_t verify_smem_bytes() { return sizeof(uint4) * 4096 + sizeof(uint32_t) * (256 * 32 + kMaxKeys * 60) + sizeof(int32_t) * kMaxKeys; }
+
+int launch_gcm_tag(cudaStream_t s, const StoreView &sv, const int32_t *list, const int32_t *gid, int n_list, uint8_t *verdict,
+                   const uint8_t *write_flag, int sm_count) {
+    if (n_list <= 0) return 0;
+    const size_t smem = verify_smem_bytes();
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(gcm_tag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+        configured = true;
+    }
+    int grid = (n_list + VF_THREADS - 1) / VF_THREADS; if (grid > sm_count * 2) grid = sm_count * 2;
+    gcm_tag_kernel<<<grid, VF_THREADS, smem, s>>>(sv, list, gid, n_list, verdict, write_flag);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
 int launch_refine_verify(cudaStream_t s, const StoreView &sv, const RefineParams &p, int sm_count) {
@@ -842,6 +897,143 @@ int launch_store_pack(cudaStream_t s, uint8_t *rec, int64_t rec_stride, int32_t 
     const int64_t total = n * ((32 + 8LL * dim) / 4);
     int grid = (int)((total + 255) / 256); if (grid > 148 * 16) grid = 148 * 16;
     store_pack_kernel<<<grid, 256, 0, s>>>(rec, rec_stride, dim, n, ids, iv, ct, ver);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Record encryption on the device:
+//   Migrate  = KeyRotationServiceImpl.reencryptTouched (keymanagement/.../KeyRotationServiceImpl.java:215-289): decrypt under the
+//              stored version, re-encrypt under the target version with a fresh IV, in place in the HBM store;
+//   Encrypt  = AesGcmCryptoService.encryptToPoint (crypto/.../AesGcmCryptoService.java:55-112) for a batch of vectors.
+// Both are AES-CTR passes (one warp per record, a lane per 16-byte block) followed by gcm_tag_kernel in write mode.  In Migrate
+// the plaintext exists only as keystream XORs in registers: new_ct = old_ct ^ E_old(ctr) ^ E_new(ctr').
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int XC_THREADS = 256;
+constexpr int XC_WARPS = XC_THREADS / 32;
+
+struct XcryptSmem {
+    uint32_t *te_s, *s_rk; int32_t *s_ver; int nkeys;
+    __device__ __forceinline__ void init(unsigned char *smem, const StoreView &sv) {
+        te_s = reinterpret_cast<uint32_t *>(smem);
+        s_rk = te_s + 256 * 32;
+        s_ver = reinterpret_cast<int32_t *>(s_rk + kMaxKeys * 60);
+        nkeys = sv.keys->n;
+        for (int i = threadIdx.x; i < 256 * 32; i += XC_THREADS) te_s[i] = sv.te0[i >> 5];
+        for (int i = threadIdx.x; i < nkeys * 60; i += XC_THREADS) s_rk[i] = sv.keys->rk[i / 60][i % 60];
+        for (int i = threadIdx.x; i < kMaxKeys; i += XC_THREADS) s_ver[i] = i < nkeys ? sv.keys->version[i] : INT32_MIN;
+        __syncthreads();
+    }
+};
+static size_t xcrypt_smem_bytes() { return sizeof(uint32_t) * (256 * 32 + kMaxKeys * 60) + sizeof(int32_t) * kMaxKeys; }
+
+// verdict[j]: authentication verdict of list entry j under its STORED version (gcm_tag_kernel, verify mode; NO_KEY preset).
+// flag[j] <- 1 when the record was re-encrypted: stored version < target, key known, tag valid (KRS:243-279).
+__global__ void __launch_bounds__(XC_THREADS) migrate_xcrypt_kernel(StoreView sv, int n, const int32_t *__restrict__ list,
+                                                                    const uint8_t *__restrict__ fresh_iv, int32_t target_version,
+                                                                    const uint8_t *__restrict__ verdict, uint8_t *__restrict__ flag) {
+    extern __shared__ __align__(16) unsigned char xc_smem[];
+    XcryptSmem sm; sm.init(xc_smem, sv);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const TeSmem te{sm.te_s + lane};
+    const int slot_new = find_key_slot(sm.s_ver, sm.nkeys, target_version);
+    const int nbytes = 8 * sv.dim, c = (nbytes + 15) >> 4;
+    for (int j = blockIdx.x * XC_WARPS + warp; j < n; j += gridDim.x * XC_WARPS) {
+        uint8_t *rec = const_cast<uint8_t *>(sv.rec) + (size_t)list[j] * sv.rec_stride;
+        const uint4 hdr = *reinterpret_cast<const uint4 *>(rec);
+        const int slot_old = find_key_slot(sm.s_ver, sm.nkeys, (int32_t)hdr.w);
+        const bool go = slot_new >= 0 && slot_old >= 0 && (int32_t)hdr.w < target_version && verdict[j] == FSPANN_V_OK;
+        if (lane == 0) flag[j] = go ? 1 : 0;
+        if (!go) continue;                                                   // warp-uniform
+        const uint32_t *iv = reinterpret_cast<const uint32_t *>(fresh_iv + (size_t)j * 12);
+        const uint32_t n0 = iv[0], n1 = iv[1], n2 = iv[2];
+        const RkSmem rk_old{sm.s_rk + slot_old * 60}, rk_new{sm.s_rk + slot_new * 60};
+        uint4 *ctv = reinterpret_cast<uint4 *>(rec + 16);
+        for (int blk = lane; blk < c; blk += 32) {
+            uint4 w = ctv[blk];
+            uint32_t ka[4], kb[4];
+            aes256_encrypt(te, rk_old, bswap32(hdr.x), bswap32(hdr.y), bswap32(hdr.z), (uint32_t)(blk + 2), ka);
+            aes256_encrypt(te, rk_new, bswap32(n0), bswap32(n1), bswap32(n2), (uint32_t)(blk + 2), kb);
+            w.x ^= bswap32(ka[0] ^ kb[0]); w.y ^= bswap32(ka[1] ^ kb[1]);
+            if (!((blk == c - 1) && (nbytes & 15))) { w.z ^= bswap32(ka[2] ^ kb[2]); w.w ^= bswap32(ka[3] ^ kb[3]); }   // odd dim: the rest is tag
+            ctv[blk] = w;
+        }
+        __syncwarp();
+        if (lane == 0) *reinterpret_cast<uint4 *>(rec) = make_uint4(n0, n1, n2, (uint32_t)target_version);
+    }
+}
+
+// Builds n records [iv | version | AES-CTR(big-endian FP64 vector) | (tag left for gcm_tag_kernel)] in `out` (record layout of
+// the store, stride sv.rec_stride).  sv.rec must point at `out`; sv.dim is the vector length.
+__global__ void __launch_bounds__(XC_THREADS) encrypt_xcrypt_kernel(StoreView sv, int n, const double *__restrict__ vectors,
+                                                                    const uint8_t *__restrict__ ivs, int32_t version, uint8_t *__restrict__ flag) {
+    extern __shared__ __align__(16) unsigned char xc_smem[];
+    XcryptSmem sm; sm.init(xc_smem, sv);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const TeSmem te{sm.te_s + lane};
+    const int slot = find_key_slot(sm.s_ver, sm.nkeys, version);
+    const int dim = sv.dim, nbytes = 8 * dim, c = (nbytes + 15) >> 4;
+    for (int j = blockIdx.x * XC_WARPS + warp; j < n; j += gridDim.x * XC_WARPS) {
+        uint8_t *rec = const_cast<uint8_t *>(sv.rec) + (size_t)j * sv.rec_stride;
+        if (lane == 0) flag[j] = slot >= 0 ? 1 : 0;
+        if (slot < 0) continue;
+        const uint32_t *iv = reinterpret_cast<const uint32_t *>(ivs + (size_t)j * 12);
+        const uint32_t n0 = iv[0], n1 = iv[1], n2 = iv[2];
+        const RkSmem rk{sm.s_rk + slot * 60};
+        const double *v = vectors + (size_t)j * dim;
+        uint4 *ctv = reinterpret_cast<uint4 *>(rec + 16);
+        for (int blk = lane; blk < c; blk += 32) {
+            uint32_t ks[4];
+            aes256_encrypt(te, rk, bswap32(n0), bswap32(n1), bswap32(n2), (uint32_t)(blk + 2), ks);
+            const double a = v[2 * blk];                                    // serializeVector: big-endian FP64 (AGC:240-259)
+            uint4 w;
+            w.x = bswap32((uint32_t)__double2hiint(a) ^ ks[0]); w.y = bswap32((uint32_t)__double2loint(a) ^ ks[1]);
+            if (2 * blk + 1 < dim) {
+                const double b = v[2 * blk + 1];
+                w.z = bswap32((uint32_t)__double2hiint(b) ^ ks[2]); w.w = bswap32((uint32_t)__double2loint(b) ^ ks[3]);
+            } else { w.z = 0; w.w = 0; }
+            ctv[blk] = w;
+        }
+        if (lane == 0) *reinterpret_cast<uint4 *>(rec) = make_uint4(n0, n1, n2, (uint32_t)version);
+    }
+}
+
+int launch_migrate_xcrypt(cudaStream_t s, const StoreView &sv, int n, const int32_t *list, const uint8_t *fresh_iv, int32_t target_version,
+                          const uint8_t *verdict, uint8_t *flag, int sm_count) {
+    if (n <= 0) return 0;
+    const size_t smem = xcrypt_smem_bytes();
+    int grid = (n + XC_WARPS - 1) / XC_WARPS; if (grid > sm_count * 4) grid = sm_count * 4;
+    migrate_xcrypt_kernel<<<grid, XC_THREADS, smem, s>>>(sv, n, list, fresh_iv, target_version, verdict, flag);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+int launch_encrypt_xcrypt(cudaStream_t s, const StoreView &sv, int n, const double *vectors, const uint8_t *ivs, int32_t version, uint8_t *flag,
+                          int sm_count) {
+    if (n <= 0) return 0;
+    const size_t smem = xcrypt_smem_bytes();
+    int grid = (n + XC_WARPS - 1) / XC_WARPS; if (grid > sm_count * 4) grid = sm_count * 4;
+    encrypt_xcrypt_kernel<<<grid, XC_THREADS, smem, s>>>(sv, n, vectors, ivs, version, flag);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// Inverse of store_pack_kernel for listed records: rec[rows[r]] (or rec[r]) -> iv[r][12], ct[r][8*dim+16], ver[r].
+__global__ void store_unpack_kernel(const uint8_t *rec, int64_t rec_stride, int32_t dim, int64_t n, const int32_t *rows, uint8_t *iv, uint8_t *ct,
+                                    int32_t *ver) {
+    const int64_t ct_bytes = 8LL * dim + 16, words = (16 + ct_bytes) / 4;
+    const int64_t total = n * words;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / words, w = i - r * words;
+        const int64_t src_row = rows ? rows[r] : r;
+        const uint32_t v = reinterpret_cast<const uint32_t *>(rec + src_row * rec_stride)[w];
+        if (w < 3) reinterpret_cast<uint32_t *>(iv)[r * 3 + w] = v;
+        else if (w == 3) ver[r] = (int32_t)v;
+        else reinterpret_cast<uint32_t *>(ct)[r * (ct_bytes / 4) + (w - 4)] = v;
+    }
+}
+int launch_store_unpack(cudaStream_t s, const uint8_t *rec, int64_t rec_stride, int32_t dim, int64_t n, const int32_t *rows, uint8_t *iv,
+                        uint8_t *ct, int32_t *ver) {
+    if (n <= 0) return 0;
+    const int64_t total = n * ((32 + 8LL * dim) / 4);
+    int grid = (int)((total + 255) / 256); if (grid > 148 * 16) grid = 148 * 16;
+    store_unpack_kernel<<<grid, 256, 0, s>>>(rec, rec_stride, dim, n, rows, iv, ct, ver);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

@@ -80,6 +80,33 @@ class GpuContext:
         key_version = np.ascontiguousarray(key_version, dtype=np.int32)
         self._ck(self.lib.fspann_store_update(self.ctx, C.c_int64(ids.shape[0]), N.ptr(ids), N.ptr(iv), N.ptr(ct), N.ptr(key_version)))
 
+    def migrate(self, ids, fresh_ivs, target_version: int):
+        """reencryptTouched on the device (KRS:215-289).  Returns dict(reencrypted uint8[n], iv uint8[n,12], ct uint8[n,8d+16],
+        count): rows of iv/ct are valid where reencrypted[i] == 1."""
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        fresh_ivs = np.ascontiguousarray(fresh_ivs, dtype=np.uint8)
+        n = ids.shape[0]
+        assert fresh_ivs.shape == (n, 12)
+        done = np.zeros(n, dtype=np.uint8)
+        iv = np.zeros((n, 12), dtype=np.uint8)
+        ct = np.zeros((n, 8 * self.store_dim + 16), dtype=np.uint8)
+        cnt = C.c_int64(0)
+        self._ck(self.lib.fspann_migrate(self.ctx, C.c_int64(n), N.ptr(ids), N.ptr(fresh_ivs), C.c_int32(target_version), N.ptr(done),
+                                         N.ptr(iv), N.ptr(ct), C.byref(cnt)))
+        return dict(reencrypted=done, iv=iv, ct=ct, count=int(cnt.value))
+
+    def encrypt_batch(self, ids, vectors, ivs, version: int):
+        """encryptToPoint for a batch (AGC:55-112): FP64 [n, dim] -> ciphertext || tag uint8 [n, 8*dim+16]."""
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        vectors = np.ascontiguousarray(vectors, dtype=np.float64)
+        ivs = np.ascontiguousarray(ivs, dtype=np.uint8)
+        n, dim = vectors.shape
+        assert ids.shape == (n,) and ivs.shape == (n, 12)
+        ct = np.empty((n, 8 * dim + 16), dtype=np.uint8)
+        self._ck(self.lib.fspann_encrypt_batch(self.ctx, C.c_int64(n), C.c_int32(dim), N.ptr(ids), N.ptr(vectors), N.ptr(ivs),
+                                               C.c_int32(version), N.ptr(ct)))
+        return ct
+
     def keys_set(self, version: int, key: bytes):
         assert len(key) == 32
         self._ck(self.lib.fspann_keys_set(self.ctx, C.c_int32(version), C.c_char_p(key)))

@@ -111,6 +111,28 @@ int fspann_store_upload_shard(fspann_ctx *ctx, int64_t id_base, int64_t N, int64
 int fspann_store_update(fspann_ctx *ctx, int64_t n, const int32_t *ids, const uint8_t *iv, const uint8_t *ct,
                         const int32_t *key_version);
 
+/* ---- Migrate on the device: KeyRotationServiceImpl.reencryptTouched
+ * (keymanagement/src/main/java/com/fspann/key/KeyRotationServiceImpl.java:215-289).  For every id of the list, in order and
+ * once (new LinkedHashSet<>(touchedIds), KRS:232): skip if the store does not hold it (null load, KRS:243), if its stored
+ * version is >= target_version (KRS:248), if its key is gone or its tag fails ("forward-secure skip", KRS:277-279); otherwise
+ * AES-GCM decrypt under the stored version and re-encrypt under target_version with AAD id|v:target|d and the fresh IV
+ * fresh_ivs[i] (the 12 bytes cryptoService.encrypt would draw from SecureRandom, AGC:69-71), IN PLACE in the HBM store, so the
+ * next batch already sees the migrated record.  The plaintext never leaves registers.
+ *   reencrypted_out uint8 [n] (may be NULL): 1 where list entry i was re-encrypted;
+ *   iv_out uint8 [n][12], ct_out uint8 [n][8*dim+16] (may be NULL): the new record for the host's RocksDB / .point file
+ *   (metadataManager.saveEncryptedPoint, KRS:268), valid where reencrypted_out[i] = 1;
+ *   *n_reencrypted_out = ReencryptReport.reencrypted.  target_version must be a live key (fspann_keys_set). */
+int fspann_migrate(fspann_ctx *ctx, int64_t n, const int32_t *ids, const uint8_t *fresh_ivs, int32_t target_version,
+                   uint8_t *reencrypted_out, uint8_t *iv_out, uint8_t *ct_out, int64_t *n_reencrypted_out);
+
+/* ---- Setup-side bulk encryption: AesGcmCryptoService.encryptToPoint
+ * (crypto/src/main/java/com/fspann/crypto/AesGcmCryptoService.java:55-112) for n vectors: big-endian FP64 serialisation
+ * (AGC:240-259), AES-256-GCM under key `version` with the caller's 12-byte IVs and AAD "id:<id>|v:<version>|d:<dim>"
+ * (EP:80-83).  vectors FP64 [n][dim] -> ct_out uint8 [n][8*dim+16] (ciphertext || tag, Java doFinal layout), ready for
+ * fspann_store_upload.  Does not touch the store; the device copy of the vectors is wiped before returning. */
+int fspann_encrypt_batch(fspann_ctx *ctx, int64_t n, int32_t dim, const int32_t *ids, const double *vectors, const uint8_t *ivs,
+                         int32_t version, uint8_t *ct_out);
+
 /* Key ring K_t: KeyLifeCycleService.getVersion(v) -> 32-byte AES key (KRS:82-88, KM:221-237).
  * set = Rotate made version v available; retire = Retire deleted it (KM:274-317): records still bound to a
  * retired version then yield FSPANN_V_NO_KEY, exactly as the Java path counts a decryptError. */
