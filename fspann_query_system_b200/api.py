@@ -152,20 +152,13 @@ class PartitionedIndexService:
         if not np.array_equal(np.sort(ids), np.arange(n, dtype=np.int32)):
             raise IllegalArgumentError("ids must be the ordinals 0..N-1 (FSA:501,515)")
         self.gpu.gfunctions_upload(reg.dim, pc.tables, pc.divisions, pc.m, pc.lam, reg.alpha, reg.r, reg.omega)
-        codes = np.empty((n, pc.tables * pc.divisions, self.gpu.W), dtype=np.uint64)
-        step = 131072
         inv = np.empty(n, dtype=np.int64)
         inv[ids] = np.arange(n)
-        for s in range(0, n, step):                       # codes indexed by id
-            e = min(n, s + step)
-            codes[s:e] = self.gpu.tokengen_batch(vecs[inv[s:e]])
         # staged order: in insertion order, the 1000th and later first, then the 999 parked ones (PIS:280-298, 821-831)
-        pos = HS.staged_order(n)
-        staged_ids = ids[pos]
-        mn, mx, rep, pids = HS.build_partitions(codes, staged_ids)
-        self.gpu.routing_upload(reg.dim, pc.tables, pc.divisions, pc.m, pc.lam, reg.alpha, reg.r, reg.omega, mn, mx, rep, pids)
+        staged_ids = ids[HS.staged_order(n)]
+        # coding loop + GreedyPartitioner.build for every (t,d) on the device; the result is installed as the routing state
+        mn, mx, rep, pids = self.gpu.routing_build(vecs[inv], staged_ids)
         self.routing = HS.RoutingIndex(reg.dim, pc.tables, pc.divisions, pc.m, pc.lam, reg.alpha, reg.r, reg.omega, n, mn, mx, rep, pids)
-        self.base_codes = codes
         self.frozen = True
         self._ids, self._vecs = [], []
 
@@ -318,7 +311,8 @@ class QueryServiceImpl:
 
 class ForwardSecureANNSystem:
     """Facade for the path only: batchInsert -> finalizeForSearch -> createToken -> search (FSA:479, 977, 1673, 622).
-    Encryption at insert uses the host KeyManager (Setup stays on the host); the encrypted store is mirrored to HBM."""
+    Keys are derived by the host KeyManager; bulk encryption at insert, the index build and Migrate run on the device
+     and the host keeps the persistent mirror of the encrypted store."""
 
     def __init__(self, cfg: SystemConfig, dim: int, master_key: bytes, gfunctions, device: int = 0, iv_seed: int = 0, debug: bool = False):
         self.cfg, self.dim = cfg, dim
@@ -345,7 +339,7 @@ class ForwardSecureANNSystem:
             ivs = WL.record_ivs(n, self.iv_seed)
         v = self.keys.current
         self.store_iv = np.ascontiguousarray(ivs, dtype=np.uint8).copy()
-        self.store_ct = HS.encrypt_store(vectors, ids, v, self.keys.get_version(v), self.store_iv)
+        self.store_ct = self.gpu.encrypt_batch(ids, vectors, self.store_iv, v)      # encryptToPoint (AGC:55-112) on the device
         self.store_ver = np.full(n, v, dtype=np.int32)
         self.gpu.store_upload(self.dim, self.store_iv, self.store_ct, self.store_ver)
         self.index.insert_many(ids, vectors)

@@ -52,6 +52,8 @@ struct fspann_ctx {
     DevBuf s_cnt, s_flag, s_fill, s_uniq, s_pairs, s_bsums, s_totals, s_dist, s_verdict;
     DevBuf s_topk_ids, s_topk_dist, s_topk_rank, s_nret, s_ndec, s_counters;
     DevBuf s_stage_a, s_stage_b, s_stage_c;  // upload staging
+    DevBuf b_codes, b_staged, b_scratch, b_ids, b_keys, b_rep, b_flag;  // device index build
+    int last_build_treeified = 0;
     DevBuf m_list, m_gid, m_iv, m_verdict, m_flag, m_rec, m_vec, m_out_iv, m_out_ct, m_out_ver;  // Migrate / bulk encryption
     DevBuf r_rows, r_queries, r_codes, r_topk_ids, r_topk_dist, r_nret, r_counters;  // retry subset
     DevBuf t_cand_ids, t_cand_sc, t_ncand, t_raw, t_uniq_cnt, t_ndec;               // retry subset route outputs
@@ -296,6 +298,7 @@ void fspann_ctx_destroy(fspann_ctx *ctx) {
                       &ctx->s_topk_ids, &ctx->s_topk_dist, &ctx->s_topk_rank, &ctx->s_nret, &ctx->s_ndec, &ctx->s_counters, &ctx->s_stage_a, &ctx->s_stage_b,
                       &ctx->s_stage_c, &ctx->s_vis_part, &ctx->s_vis_score, &ctx->s_vis_n, &ctx->r_rows, &ctx->r_queries, &ctx->r_codes, &ctx->r_topk_ids, &ctx->r_topk_dist, &ctx->r_nret,
                       &ctx->r_counters, &ctx->t_cand_ids, &ctx->t_cand_sc, &ctx->t_ncand, &ctx->t_raw, &ctx->t_uniq_cnt, &ctx->t_ndec,
+                      &ctx->b_codes, &ctx->b_staged, &ctx->b_scratch, &ctx->b_ids, &ctx->b_keys, &ctx->b_rep, &ctx->b_flag,
                       &ctx->m_list, &ctx->m_gid, &ctx->m_iv, &ctx->m_verdict, &ctx->m_flag, &ctx->m_rec, &ctx->m_vec, &ctx->m_out_iv, &ctx->m_out_ct, &ctx->m_out_ver};
     for (DevBuf *b : bufs) release(*b);
     for (int i = 0; i < 7; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -322,6 +325,7 @@ int64_t fspann_get_info(fspann_ctx *ctx, const char *name) {
     if (!ctx || !name) return -1;
     if (!strcmp(name, "last_route_path")) return ctx->last_route_path;
     if (!strcmp(name, "sm_count")) return ctx->sm_count;
+    if (!strcmp(name, "build_treeified")) return ctx->last_build_treeified;
     return -1;
 }
 
@@ -335,7 +339,7 @@ int fspann_routing_upload(fspann_ctx *ctx, int32_t dim, int32_t T, int32_t D, in
     if (lambda > 32) return fail(ctx, FSPANN_E_ARG, "lambda > 32");
     if ((int64_t)m * lambda > 255) return fail(ctx, FSPANN_E_ARG, "m*lambda = %d > 255 code bits not supported", m * lambda);
     const int W = (m * lambda + 63) / 64, TD = T * D;
-    const size_t tg_smem = sizeof(double) * ((size_t)64 * (dim | 1) + (size_t)m * dim + 2 * (size_t)m) + 4 * (size_t)64 * 2 * W;
+    const size_t tg_smem = sizeof(double) * ((size_t)64 * (((dim + 1) & ~1) + 4) + (size_t)m * ((dim + 1) & ~1) + 2 * (size_t)m) + 4 * (size_t)64 * 2 * W;
     if (tg_smem > 227 * 1024) return fail(ctx, FSPANN_E_ARG, "dim=%d, m=%d need %zu B of shared memory for TokenGen (> 227 KB)", dim, m, tg_smem);
     for (int64_t i = 0; i < (int64_t)TD * m; i++)
         if (!(omega[i] > 0.0)) return fail(ctx, FSPANN_E_ARG, "omega_j <= 0 (Coding:85-87)");
@@ -374,6 +378,77 @@ int fspann_gfunctions_upload(fspann_ctx *ctx, int32_t dim, int32_t T, int32_t D,
     std::vector<int32_t> ii((size_t)T * D, id0);
     int rc = fspann_routing_upload(ctx, dim, T, D, m, lambda, alpha, r, omega, 1, mn.data(), mx.data(), rp.data(), ii.data());
     return rc;
+}
+
+// ---- Setup-side index build on the device: coding loop of PIS.insert / finalizeForSearch (PIS:331-346, 789-845)
+// + GreedyPartitioner.build (GP:37-76) for every (table, division), installed as the routing state ------------------------------
+int fspann_routing_build(fspann_ctx *ctx, int64_t N, const double *vectors, const int32_t *staged_ids, int64_t *min_key_out,
+                         int64_t *max_key_out, uint64_t *rep_code_out, int32_t *ids_out) {
+    if (!ctx) return FSPANN_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->routing_ready) return fail(ctx, FSPANN_E_STATE, "GFunctionRegistry not initialized: upload the GFunctions first (PIS:812-819)");
+    if (!vectors || !staged_ids) return fail(ctx, FSPANN_E_ARG, "null array");
+    if (N < 1000) return fail(ctx, FSPANN_E_STATE, "Cannot finalize index: only %lld samples collected (< MIN_SAMPLE_SIZE) (PIS:803-808)", (long long)N);
+    if (N >= (1LL << 31) - 1) return fail(ctx, FSPANN_E_ARG, "N too large for int32 ids");
+    RoutingView &rv = ctx->rv;
+    const int dim = rv.dim, TD = rv.TD, W = rv.W;
+    {   // ids are the ordinals 0..N-1 (FSA:501,515), each staged exactly once
+        std::vector<uint8_t> seen((size_t)N, 0);
+        for (int64_t i = 0; i < N; i++) {
+            const int32_t id = staged_ids[i];
+            if (id < 0 || id >= N || seen[(size_t)id]) return fail(ctx, FSPANN_E_ARG, "staged ids must be a permutation of 0..N-1 (bad id %d)", id);
+            seen[(size_t)id] = 1;
+        }
+    }
+    if (!all_finite(vectors, N * dim)) return fail(ctx, FSPANN_E_ARG, "Vector contains NaN/Inf (Coding:357-359)");
+    const int64_t P = (N + kBlock - 1) / kBlock;
+    // 1. code every vector for every (t,d): the TokenGen kernel over the base set, in chunks through a staging buffer
+    ENSURE(ctx->b_codes, sizeof(uint64_t) * (size_t)N * TD * W);
+    const int64_t chunk = 131072;
+    ENSURE(ctx->s_queries, sizeof(double) * (size_t)std::min(chunk, N) * dim);
+    for (int64_t s0 = 0; s0 < N; s0 += chunk) {
+        const int64_t c = std::min(chunk, N - s0);
+        CK(cudaMemcpyAsync(ctx->s_queries.p, vectors + (size_t)s0 * dim, sizeof(double) * (size_t)c * dim, cudaMemcpyHostToDevice, ctx->stream));
+        LAUNCHED(launch_tokengen(ctx->stream, rv, c, (const double *)ctx->s_queries.p, (uint64_t *)ctx->b_codes.p + (size_t)s0 * TD * W));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    // 2. partitions: HashMap iteration order -> stable sort by key -> blocks of 64
+    uint32_t cap = table_size_for(N);                                   // new HashMap<>(staged.size()) (PIS:413) ...
+    while ((double)N > 0.75 * (double)cap && cap < (1u << 30)) cap <<= 1;   // ... doubled while size > 0.75 * cap
+    const size_t scratch = partition_build_scratch_bytes(N);
+    ENSURE(ctx->b_staged, sizeof(int32_t) * (size_t)N);
+    ENSURE(ctx->b_scratch, scratch);
+    ENSURE(ctx->b_ids, sizeof(int32_t) * (size_t)TD * N);
+    ENSURE(ctx->b_keys, sizeof(int64_t) * 2 * (size_t)TD * P);
+    ENSURE(ctx->b_rep, sizeof(uint64_t) * (size_t)TD * P * W);
+    ENSURE(ctx->b_flag, sizeof(int32_t));
+    CK(cudaMemcpyAsync(ctx->b_staged.p, staged_ids, sizeof(int32_t) * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->b_flag.p, 0, sizeof(int32_t), ctx->stream));
+    LAUNCHED(launch_partition_build(ctx->stream, (const uint64_t *)ctx->b_codes.p, (const int32_t *)ctx->b_staged.p, N, TD, W, cap, rv.m * rv.lambda,
+                                    (int32_t *)ctx->b_ids.p, (int64_t *)ctx->b_keys.p, (uint64_t *)ctx->b_rep.p, ctx->b_scratch.p, ctx->b_scratch.bytes,
+                                    (int32_t *)ctx->b_flag.p));
+    int32_t tree = 0;
+    CK(cudaMemcpyAsync(&tree, ctx->b_flag.p, sizeof tree, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->last_build_treeified = tree;
+    // 3. freeze: the built arrays become the routing state (PIS:842)
+    ctx->routing_ready = false;
+    std::swap(ctx->d_ids, ctx->b_ids);
+    std::swap(ctx->d_keys, ctx->b_keys);
+    std::swap(ctx->d_rep, ctx->b_rep);
+    rv.n_ids = N; rv.P = P;
+    rv.keys = (const int64_t *)ctx->d_keys.p; rv.rep = (const uint64_t *)ctx->d_rep.p; rv.ids = (const int32_t *)ctx->d_ids.p;
+    ctx->routing_ready = true;
+    // optional copies for the host's own persistence, in fspann_routing_upload's layout
+    if (ids_out) CK(cudaMemcpy(ids_out, ctx->d_ids.p, sizeof(int32_t) * (size_t)TD * N, cudaMemcpyDeviceToHost));
+    if (rep_code_out) CK(cudaMemcpy(rep_code_out, ctx->d_rep.p, sizeof(uint64_t) * (size_t)TD * P * W, cudaMemcpyDeviceToHost));
+    if (min_key_out || max_key_out) {
+        std::vector<int64_t> inter(2 * (size_t)TD * P);
+        CK(cudaMemcpy(inter.data(), ctx->d_keys.p, sizeof(int64_t) * inter.size(), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < (size_t)TD * P; i++) { if (min_key_out) min_key_out[i] = inter[2 * i]; if (max_key_out) max_key_out[i] = inter[2 * i + 1]; }
+    }
+    release(ctx->b_codes); release(ctx->b_scratch); release(ctx->b_ids); release(ctx->b_keys); release(ctx->b_rep);
+    return FSPANN_OK;
 }
 
 int fspann_deleted_set(fspann_ctx *ctx, const uint8_t *flags, int64_t n) {

@@ -131,6 +131,9 @@ int launch_encrypt_xcrypt(cudaStream_t s, const StoreView &sv, int n, const doub
                           int sm_count);
 int launch_store_unpack(cudaStream_t s, const uint8_t *rec, int64_t rec_stride, int32_t dim, int64_t n, const int32_t *rows, uint8_t *iv,
                         uint8_t *ct, int32_t *ver);
+int launch_partition_build(cudaStream_t s, const uint64_t *codes, const int32_t *staged, int64_t n, int TD, int W, uint32_t cap, int code_bits,
+                           int32_t *ids_out, int64_t *keys_out, uint64_t *rep_out, void *scratch, size_t scratch_bytes, int32_t *treeified);
+size_t partition_build_scratch_bytes(int64_t n);
 int launch_debug_decrypt(cudaStream_t s, const StoreView &sv, int64_t n, const int32_t *ids, double *pt, uint8_t *verdict);
 
 }  // namespace fsp

@@ -51,6 +51,23 @@ class GpuContext:
                                                 N.ptr(min_key), N.ptr(max_key), N.ptr(rep), N.ptr(ids)))
         self.dim, self.T, self.D, self.m, self.lam, self.W = dim, T, D, m, lam, (m * lam + 63) // 64
 
+    def routing_build(self, vectors, staged_ids, want_arrays: bool = True):
+        """finalizeForSearch on the device: code the base set + GreedyPartitioner.build per (t,d); installs the routing state.
+        Returns (min_key, max_key, rep, ids) in routing_upload's layout when want_arrays."""
+        vectors = np.ascontiguousarray(vectors, dtype=np.float64)
+        staged_ids = np.ascontiguousarray(staged_ids, dtype=np.int32)
+        n = vectors.shape[0]
+        if vectors.ndim != 2 or vectors.shape[1] != self.dim:
+            raise N.IllegalArgumentError(f"Expected vector length {self.dim}")
+        TD, P = self.T * self.D, (n + 63) // 64
+        mn = mx = rep = ids = None
+        if want_arrays:
+            mn, mx = np.empty((TD, P), dtype=np.int64), np.empty((TD, P), dtype=np.int64)
+            rep, ids = np.empty((TD, P, self.W), dtype=np.uint64), np.empty((TD, n), dtype=np.int32)
+        self._ck(self.lib.fspann_routing_build(self.ctx, C.c_int64(n), N.ptr(vectors), N.ptr(staged_ids), N.ptr(mn), N.ptr(mx), N.ptr(rep),
+                                               N.ptr(ids)))
+        return mn, mx, rep, ids
+
     def deleted_set(self, flags):
         if flags is None:
             self._ck(self.lib.fspann_deleted_set(self.ctx, None, C.c_int64(0)))

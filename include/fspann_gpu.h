@@ -92,6 +92,20 @@ int fspann_routing_upload(fspann_ctx *ctx, int32_t dim, int32_t T, int32_t D, in
 int fspann_gfunctions_upload(fspann_ctx *ctx, int32_t dim, int32_t T, int32_t D, int32_t m, int32_t lambda,
                              const double *alpha, const double *r, const double *omega);
 
+/* Setup-side index build on the device.  Needs the GFunctions (fspann_gfunctions_upload).  Codes every vector for
+ * every (table, division) with the TokenGen kernel (the coding loop of PartitionedIndexService.insert / finalizeForSearch,
+ * PIS:331-346, 821-831) and runs GreedyPartitioner.build (GP:37-76) per division exactly as finalizeForSearch does: entries in
+ * java.util.HashMap<String,BitSet>(N) iteration order (PIS:413-420), stable sort by computeKey (GP:51, 87-96), blocks of 64,
+ * repCode = code of entry i + ((end-i-1)>>>1) (GP:60).  The result is installed as the routing state (= fspann_routing_upload).
+ *   vectors FP64 [N][dim] indexed by id (ids are the ordinals 0..N-1, FSA:501,515); staged_ids int32 [N] = insertion order into
+ *   the staging map (the 1000th and later vectors first, then the first 999: PIS:280-298, 821-831).
+ *   Optional host outputs (NULL to skip), fspann_routing_upload's layout: min_key/max_key int64 [T*D][P], rep_code uint64
+ *   [T*D][P][W], ids int32 [T*D][N].  fspann_get_info("build_treeified") = 1 if a HashMap bin held >= 9 entries (the JDK
+ *   treeifies it and its iteration order is unspecified; does not happen for decimal ids at the BASELINE sizes).
+ * Errors: FSPANN_E_STATE without GFunctions or with N < 1000 (PIS:803-819); FSPANN_E_ARG for NaN/Inf or ids that are not 0..N-1. */
+int fspann_routing_build(fspann_ctx *ctx, int64_t N, const double *vectors, const int32_t *staged_ids, int64_t *min_key_out,
+                         int64_t *max_key_out, uint64_t *rep_code_out, int32_t *ids_out);
+
 /* metadata.isDeleted(id) (common/.../RocksDBMetadataManager.java:203-224): flags[id] != 0 => deleted.
  * n may be 0 / flags NULL to clear.  Consulted by Route (PIS:739) and Refine (PIS:718). */
 int fspann_deleted_set(fspann_ctx *ctx, const uint8_t *flags, int64_t n);

@@ -212,7 +212,6 @@ def test_facade_flow_matches_reference_search(world_factory):
         sys_.finalizeForSearch()
         r = sys_.index.routing
         assert np.array_equal(r.ids, w.ix.ids) and np.array_equal(r.rep, w.ix.rep) and np.array_equal(r.min_key, w.ix.min_key)
-        assert np.array_equal(sys_.index.base_codes, w.codes)
         with pytest.raises(N.IllegalArgumentError):                     # FSA:1680-1688 dimension mismatch
             sys_.createToken(w.queries[0][:-1], 10, w.g.dim - 1)
         with pytest.raises(N.IllegalArgumentError):                     # QTF:65

@@ -171,3 +171,43 @@ def test_route_fast_path_with_every_id_duplicated(world_factory, wl_extra):
             assert tot_unique < 0.8 * codes.shape[0] * g.T * g.D * probes * 64
     finally:
         ctx.close()
+
+
+def test_routing_build_on_device_matches_reference_build(wg):
+    """finalizeForSearch on the device (coding loop + GreedyPartitioner.build per division): partition keys,
+    representative codes and id order are the reference's bit for bit, and the installed state routes like the oracle."""
+    from fspann_query_system_b200 import _native as N
+    from fspann_query_system_b200.gpu import GpuContext
+    w, _ = wg
+    g, ix, n = w.g, w.ix, w.cfg.N
+    ctx = GpuContext(0)
+    try:
+        with pytest.raises(N.IllegalStateError):                         # no GFunctions yet (PIS:812-819)
+            ctx.dim, ctx.T, ctx.D, ctx.W = g.dim, g.T, g.D, g.W
+            ctx.routing_build(w.base, O.staged_order(n))
+        ctx.gfunctions_upload(g.dim, g.T, g.D, g.m, g.lam, g.alpha, g.r, g.omega)
+        with pytest.raises(N.IllegalStateError):                         # PIS:803-808
+            ctx.routing_build(w.base[:999], O.staged_order(1000)[:999] % 999)
+        bad = O.staged_order(n).copy(); bad[5] = bad[6]
+        with pytest.raises(N.IllegalArgumentError):
+            ctx.routing_build(w.base, bad)
+        mn, mx, rep, ids = ctx.routing_build(w.base, O.staged_order(n))
+        assert ctx.get_info("build_treeified") == (1 if ix.max_chain >= 9 else 0)
+        assert np.array_equal(ids, ix.ids), "partition order of ids"
+        assert np.array_equal(mn, ix.min_key) and np.array_equal(mx, ix.max_key)
+        assert np.array_equal(rep, ix.rep)
+        codes = O.tokengen_batch(w.queries, g)
+        out = ctx.route_batch(codes, 5, 20000, 128)
+        for q in range(0, codes.shape[0], 3):
+            rids, sc, raw, mc = O.route(ix, codes[q], 5, 20000)
+            k = min(128, len(rids))
+            assert out["n_cand"][q] == k and out["raw_seen"][q] == raw and np.array_equal(out["cand_scores"][q, :k], sc[:k])
+            if mc < 9:
+                assert np.array_equal(out["cand_ids"][q, :k], rids[:k])
+        # a different insertion order gives the reference's (different) HashMap iteration order too
+        perm = np.random.default_rng(4).permutation(n).astype(np.int32)
+        ix2 = O.index_build(w.codes, g, perm)
+        mn2, mx2, rep2, ids2 = ctx.routing_build(w.base, perm)
+        assert np.array_equal(ids2, ix2.ids) and np.array_equal(rep2, ix2.rep) and np.array_equal(mn2, ix2.min_key) and np.array_equal(mx2, ix2.max_key)
+    finally:
+        ctx.close()
