@@ -88,31 +88,28 @@ def build_world(cfg: WL.Config, gpu, n_batches: int, rank: int):
     base = WL.base_vectors(cfg)
     alpha, r, omega = HS.build_gfunctions(base[:HS.MIN_SAMPLE_SIZE], cfg.m, cfg.lam, cfg.seed, cfg.T, cfg.D)
     log(f"base {base.shape} + GFunctions in {time.time() - t0:.1f}s")
+    # Setup on the device: coding of the base set + GreedyPartitioner.build per division, then bulk encryptToPoint
+    setup = {}
     t0 = time.time()
     gpu.gfunctions_upload(cfg.dim, cfg.T, cfg.D, cfg.m, cfg.lam, alpha, r, omega)
-    codes = np.empty((cfg.N, cfg.T * cfg.D, cfg.W), dtype=np.uint64)
-    for s in range(0, cfg.N, 131072):
-        e = min(cfg.N, s + 131072)
-        codes[s:e] = gpu.tokengen_batch(base[s:e])        # Setup-side bulk coding reuses the TokenGen kernel
-    log(f"base codes (GPU TokenGen) in {time.time() - t0:.1f}s")
-    t0 = time.time()
-    mn, mx, rep, ids = HS.build_partitions(codes, HS.staged_order(cfg.N))
-    gpu.routing_upload(cfg.dim, cfg.T, cfg.D, cfg.m, cfg.lam, alpha, r, omega, mn, mx, rep, ids)
-    log(f"greedy partitions ({cfg.T * cfg.D} x {mn.shape[1]}) in {time.time() - t0:.1f}s")
+    mn, mx, rep, ids = gpu.routing_build(base, HS.staged_order(cfg.N))
+    setup["coding_and_partition_build_s"] = time.time() - t0
+    log(f"base codes + greedy partitions ({cfg.T * cfg.D} x {mn.shape[1]}) on the device in {time.time() - t0:.1f}s (incl. H2D of the base set and D2H of the index)")
     t0 = time.time()
     km = HS.KeyManager(WL.MASTER_KEY)
     iv = WL.record_ivs(cfg.N, cfg.base_seed + 5)
-    ct = HS.encrypt_store(base, np.arange(cfg.N, dtype=np.int32), 1, km.derive(1), iv)
-    ver = np.ones(cfg.N, dtype=np.int32)
     gpu.keys_set(1, km.derive(1))
+    ct = gpu.encrypt_batch(np.arange(cfg.N, dtype=np.int32), base, iv, 1)
+    ver = np.ones(cfg.N, dtype=np.int32)
+    setup["encrypt_s"] = time.time() - t0
     gpu.store_upload(cfg.dim, iv, ct, ver)
-    log(f"encrypted store ({ct.nbytes / 1e9:.2f} GB) in {time.time() - t0:.1f}s")
+    log(f"encrypted store ({ct.nbytes / 1e9:.2f} GB) on the device in {setup['encrypt_s']:.1f}s")
     batches = []
     for b in range(n_batches):
         qcfg = cfg.scaled(name=cfg.name)
         object.__setattr__(qcfg, "query_seed", cfg.query_seed + 7919 * b + 104729 * rank)
         batches.append(WL.query_vectors(qcfg))
-    world = dict(alpha=alpha, r=r, omega=omega, mn=mn, mx=mx, rep=rep, ids=ids, iv=iv, ct=ct, ver=ver, keys={1: km.derive(1)}, base=base)
+    world = dict(alpha=alpha, r=r, omega=omega, mn=mn, mx=mx, rep=rep, ids=ids, iv=iv, ct=ct, ver=ver, keys={1: km.derive(1)}, base=base, setup=setup)
     return world, batches
 
 
@@ -304,6 +301,18 @@ def main():
     e2e_wall_ms = (time.perf_counter() - t_wall) * 1e3
     checksum = int(h_ids.to(torch.int64).sum().item())
 
+    # ---- recall@10 of what was just timed: exact ground truth and recall on the device, outside the timed region
+    recall = None
+    if rank == 0:
+        nq_gt = min(Q, 2000)
+        t0 = time.time()
+        gt = gpu.groundtruth(world["base"].astype(np.float32), batches[0][:nq_gt].astype(np.float32), k)
+        res = gpu.search_batch(batches[0][:nq_gt], k, cfg.probes, cfg.hard_cap, cfg.B)
+        rec = gpu.recall_batch(gt, res["top_ids"], k, res["n_ret"])
+        recall = {"recall_at_k": float(rec.mean()), "k": k, "queries": nq_gt, "groundtruth_s": time.time() - t0,
+                  "definition": "GroundtruthPrecompute.run + computeMetricsAtK (FSA:785-794), evaluated on the device"}
+        log(f"recall@{k} = {recall['recall_at_k']:.4f} over {nq_gt} queries (ground truth + search + recall in {recall['groundtruth_s']:.1f}s)")
+
     if world_size > 1:
         t = torch.tensor([ms, e2e_ms, e2e_wall_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -340,6 +349,7 @@ def main():
                             "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src,
                             "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": dec_ms, "pairs_per_launch": pairs / K},
                "stage_ms_per_step": {s: v / K for s, v in stage.items()},
+               "recall": recall, "setup_on_device_s": world["setup"],
                "cpu_baseline": cpu_baseline}
         print(json.dumps(out))
     gpu.close()

@@ -52,6 +52,7 @@ struct fspann_ctx {
     DevBuf s_cnt, s_flag, s_fill, s_uniq, s_pairs, s_bsums, s_totals, s_dist, s_verdict;
     DevBuf s_topk_ids, s_topk_dist, s_topk_rank, s_nret, s_ndec, s_counters;
     DevBuf s_stage_a, s_stage_b, s_stage_c;  // upload staging
+    DevBuf g_base, g_q, g_dist, g_ids, g_d2, g_flag, g_res, g_nret, g_rec;  // ground truth / recall
     DevBuf b_codes, b_staged, b_scratch, b_ids, b_keys, b_rep, b_flag;  // device index build
     int last_build_treeified = 0;
     DevBuf m_list, m_gid, m_iv, m_verdict, m_flag, m_rec, m_vec, m_out_iv, m_out_ct, m_out_ver;  // Migrate / bulk encryption
@@ -298,6 +299,7 @@ void fspann_ctx_destroy(fspann_ctx *ctx) {
                       &ctx->s_topk_ids, &ctx->s_topk_dist, &ctx->s_topk_rank, &ctx->s_nret, &ctx->s_ndec, &ctx->s_counters, &ctx->s_stage_a, &ctx->s_stage_b,
                       &ctx->s_stage_c, &ctx->s_vis_part, &ctx->s_vis_score, &ctx->s_vis_n, &ctx->r_rows, &ctx->r_queries, &ctx->r_codes, &ctx->r_topk_ids, &ctx->r_topk_dist, &ctx->r_nret,
                       &ctx->r_counters, &ctx->t_cand_ids, &ctx->t_cand_sc, &ctx->t_ncand, &ctx->t_raw, &ctx->t_uniq_cnt, &ctx->t_ndec,
+                      &ctx->g_base, &ctx->g_q, &ctx->g_dist, &ctx->g_ids, &ctx->g_d2, &ctx->g_flag, &ctx->g_res, &ctx->g_nret, &ctx->g_rec,
                       &ctx->b_codes, &ctx->b_staged, &ctx->b_scratch, &ctx->b_ids, &ctx->b_keys, &ctx->b_rep, &ctx->b_flag,
                       &ctx->m_list, &ctx->m_gid, &ctx->m_iv, &ctx->m_verdict, &ctx->m_flag, &ctx->m_rec, &ctx->m_vec, &ctx->m_out_iv, &ctx->m_out_ct, &ctx->m_out_ver};
     for (DevBuf *b : bufs) release(*b);
@@ -650,6 +652,66 @@ int fspann_encrypt_batch(fspann_ctx *ctx, int64_t n, int32_t dim, const int32_t 
     }
     // the plaintext staging buffer is wiped: vectors never outlive the call on the device
     CK(cudaMemsetAsync(ctx->m_vec.p, 0, ctx->m_vec.bytes, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FSPANN_OK;
+}
+
+// ---- exact ground truth and recall@K on the device: GroundtruthPrecompute.run (api/.../GroundtruthPrecompute.java:218-276)
+// and the recall of computeMetricsAtK (FSA:785-794) --------------------------------------------------------------------------
+static bool all_finite_f32(const float *v, int64_t n) {
+    for (int64_t i = 0; i < n; i++) if (!std::isfinite(v[i])) return false;
+    return true;
+}
+int fspann_groundtruth(fspann_ctx *ctx, int64_t N, int32_t dim, const float *base, int64_t Q, const float *queries, int32_t K,
+                       int32_t *gt_ids_out, double *gt_d2_out) {
+    if (!ctx) return FSPANN_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (!base || !queries || !gt_ids_out) return fail(ctx, FSPANN_E_ARG, "null array");
+    if (N <= 0 || Q <= 0 || dim <= 0) return fail(ctx, FSPANN_E_ARG, "Empty or malformed vector files (zero records).");   // GroundtruthPrecompute:241-243
+    if (N >= (1LL << 31) - 1) return fail(ctx, FSPANN_E_ARG, "N too large for int32 ids");
+    if (K < 1 || K > N || K > gt_max_k()) return fail(ctx, FSPANN_E_ARG, "K=%d must be in [1, min(N, %d)] (the caller clamps like kFinal, :238)", K, gt_max_k());
+    if (!all_finite_f32(base, N * dim) || !all_finite_f32(queries, Q * dim)) return fail(ctx, FSPANN_E_ARG, "vector contains NaN/Inf");
+    int64_t Qc = (int64_t)(2e9 / (8.0 * (double)N));
+    Qc = std::max<int64_t>(64, Qc / 64 * 64);
+    Qc = std::min<int64_t>(Qc, (Q + 63) / 64 * 64);
+    ENSURE(ctx->g_base, sizeof(float) * (size_t)N * dim);
+    ENSURE(ctx->g_q, sizeof(float) * (size_t)Qc * dim);
+    ENSURE(ctx->g_dist, sizeof(double) * (size_t)Qc * N);
+    ENSURE(ctx->g_ids, sizeof(int32_t) * (size_t)Qc * K);
+    ENSURE(ctx->g_d2, sizeof(double) * (size_t)Qc * K);
+    ENSURE(ctx->g_flag, sizeof(int32_t));
+    CK(cudaMemcpyAsync(ctx->g_base.p, base, sizeof(float) * (size_t)N * dim, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->g_flag.p, 0, sizeof(int32_t), ctx->stream));
+    for (int64_t q0 = 0; q0 < Q; q0 += Qc) {
+        const int c = (int)std::min(Qc, Q - q0);
+        CK(cudaMemcpyAsync(ctx->g_q.p, queries + (size_t)q0 * dim, sizeof(float) * (size_t)c * dim, cudaMemcpyHostToDevice, ctx->stream));
+        LAUNCHED(launch_gt_chunk(ctx->stream, (const float *)ctx->g_base.p, N, dim, (const float *)ctx->g_q.p, c, K, (double *)ctx->g_dist.p,
+                                 (int32_t *)ctx->g_ids.p, (double *)ctx->g_d2.p, (int32_t *)ctx->g_flag.p, ctx->sm_count));
+        CK(cudaMemcpyAsync(gt_ids_out + (size_t)q0 * K, ctx->g_ids.p, sizeof(int32_t) * (size_t)c * K, cudaMemcpyDeviceToHost, ctx->stream));
+        if (gt_d2_out) CK(cudaMemcpyAsync(gt_d2_out + (size_t)q0 * K, ctx->g_d2.p, sizeof(double) * (size_t)c * K, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    release(ctx->g_dist);
+    return FSPANN_OK;
+}
+
+int fspann_recall_batch(fspann_ctx *ctx, int64_t Q, int32_t K, const int32_t *gt_ids, int32_t gt_stride, const int32_t *result_ids,
+                        int32_t result_stride, const int32_t *n_ret, double *recall_out) {
+    if (!ctx) return FSPANN_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (Q == 0) return FSPANN_OK;
+    if (Q < 0 || !gt_ids || !result_ids || !recall_out) return fail(ctx, FSPANN_E_ARG, "null array");
+    if (K < 1 || gt_stride < K || result_stride < 1) return fail(ctx, FSPANN_E_ARG, "groundtruth row shorter than K=%d (FSA:779-782 returns NaN metrics)", K);
+    ENSURE(ctx->g_ids, sizeof(int32_t) * (size_t)Q * gt_stride);
+    ENSURE(ctx->g_res, sizeof(int32_t) * (size_t)Q * result_stride);
+    ENSURE(ctx->g_nret, sizeof(int32_t) * (size_t)Q);
+    ENSURE(ctx->g_rec, sizeof(double) * (size_t)Q);
+    CK(cudaMemcpyAsync(ctx->g_ids.p, gt_ids, sizeof(int32_t) * (size_t)Q * gt_stride, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->g_res.p, result_ids, sizeof(int32_t) * (size_t)Q * result_stride, cudaMemcpyHostToDevice, ctx->stream));
+    if (n_ret) CK(cudaMemcpyAsync(ctx->g_nret.p, n_ret, sizeof(int32_t) * (size_t)Q, cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCHED(launch_recall(ctx->stream, (int)Q, K, (const int32_t *)ctx->g_ids.p, gt_stride, (const int32_t *)ctx->g_res.p, std::min(result_stride, result_stride),
+                           n_ret ? (const int32_t *)ctx->g_nret.p : nullptr, (double *)ctx->g_rec.p));
+    CK(cudaMemcpyAsync(recall_out, ctx->g_rec.p, sizeof(double) * (size_t)Q, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return FSPANN_OK;
 }

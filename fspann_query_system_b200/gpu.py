@@ -196,6 +196,32 @@ class GpuContext:
                                                   C.c_void_p(d_ids), C.c_void_p(d_dist), C.c_void_p(d_nret),
                                                   C.c_void_p(d_counters) if d_counters else None))
 
+    def groundtruth(self, base_f32, queries_f32, K: int, want_d2: bool = False):
+        """GroundtruthPrecompute.run on the device: int32 [Q, K] ids ordered by (squared L2, id)."""
+        base_f32 = np.ascontiguousarray(base_f32, dtype=np.float32)
+        queries_f32 = np.ascontiguousarray(queries_f32, dtype=np.float32)
+        n, dim = base_f32.shape
+        Q = queries_f32.shape[0]
+        if queries_f32.shape[1] != dim:
+            raise N.IllegalArgumentError(f"Dim mismatch base={dim} query={queries_f32.shape[1]}")     # GroundtruthPrecompute:234-236
+        K = min(max(1, K), n)                                                                     # kFinal (:238)
+        ids = np.empty((Q, K), dtype=np.int32)
+        d2 = np.empty((Q, K), dtype=np.float64) if want_d2 else None
+        self._ck(self.lib.fspann_groundtruth(self.ctx, C.c_int64(n), C.c_int32(dim), N.ptr(base_f32), C.c_int64(Q), N.ptr(queries_f32),
+                                             C.c_int32(K), N.ptr(ids), N.ptr(d2)))
+        return (ids, d2) if want_d2 else ids
+
+    def recall_batch(self, gt_ids, result_ids, K: int, n_ret=None) -> np.ndarray:
+        """recall@K per query (FSA:785-794)."""
+        gt_ids = np.ascontiguousarray(gt_ids, dtype=np.int32)
+        result_ids = np.ascontiguousarray(result_ids, dtype=np.int32)
+        Q = gt_ids.shape[0]
+        nr = None if n_ret is None else np.ascontiguousarray(n_ret, dtype=np.int32)
+        out = np.empty(Q, dtype=np.float64)
+        self._ck(self.lib.fspann_recall_batch(self.ctx, C.c_int64(Q), C.c_int32(K), N.ptr(gt_ids), C.c_int32(gt_ids.shape[1]), N.ptr(result_ids),
+                                              C.c_int32(result_ids.shape[1]), N.ptr(nr), N.ptr(out)))
+        return out
+
     def touched(self, clear: bool = False) -> np.ndarray:
         words = (self.N + 31) // 32
         bm = np.zeros(words, dtype=np.uint32)

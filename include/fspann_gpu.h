@@ -198,6 +198,20 @@ int fspann_search_batch_dev(fspann_ctx *ctx, int64_t Q, const double *d_queries,
                             int64_t hard_cap, int32_t B, int32_t ham_threshold, int32_t allow_retry,
                             int32_t *d_topk_ids, double *d_topk_dist, int32_t *d_n_ret, int64_t *d_counters);
 
+/* ---- evaluation on the box ------------------------------------------------------------------------------
+ * Exact ground truth = GroundtruthPrecompute.run (api/src/main/java/com/fspann/api/GroundtruthPrecompute.java:218-276): for every
+ * query the K nearest base vectors by squared L2 computed like VecReader.l2sq (:144-163) -- per dimension a FLOAT subtraction
+ * q[i] - b[i] widened to double, squares summed sequentially in FP64 -- ordered by (distance, id) ascending (:168-189).
+ * base float32 [N][dim], queries float32 [Q][dim] (.fvecs content; .bvecs bytes are passed as the floats 0..255, which the
+ * reference's float - int arithmetic equals); K in [1, min(N, 1024)] (callers clamp like kFinal, :238).
+ * gt_ids_out int32 [Q][K]; gt_d2_out FP64 [Q][K] squared distances (may be NULL). */
+int fspann_groundtruth(fspann_ctx *ctx, int64_t N, int32_t dim, const float *base, int64_t Q, const float *queries, int32_t K,
+                       int32_t *gt_ids_out, double *gt_d2_out);
+/* recall@K of ForwardSecureANNSystem.computeMetricsAtK (api/.../ForwardSecureANNSystem.java:785-794):
+ * recall[q] = |{ i < min(K, n_ret[q]) : result_ids[q][i] in gt_ids[q][0..K) }| / K.  gt_stride >= K; n_ret may be NULL (= K). */
+int fspann_recall_batch(fspann_ctx *ctx, int64_t Q, int32_t K, const int32_t *gt_ids, int32_t gt_stride, const int32_t *result_ids,
+                        int32_t result_stride, const int32_t *n_ret, double *recall_out);
+
 /* Touched set (QSI:262, QSI:348-350 reencTracker.record): bitmap over ids (bit id&31 of word id>>5, N bits) of
  * every record that reached verdict OK since the last clear.  Feeds the host's selective re-encryption. */
 int fspann_touched_fetch(fspann_ctx *ctx, uint32_t *bitmap_out, int64_t n_words, int32_t clear);

@@ -697,3 +697,66 @@ void orc_search_batch(const orc_index_t *ix, const orc_store_t *st, const double
     }
     free(codes); free(cid); free(csc); free(ver);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Evaluation: exact ground truth and recall@K.
+ *   GTP = api/src/main/java/com/fspann/api/GroundtruthPrecompute.java,  FSA = api/.../ForwardSecureANNSystem.java
+ * ---------------------------------------------------------------------------------------------- */
+/* VecReader.l2sq (GTP:144-163): `double d = q[i] - v` is a FLOAT subtraction widened to double; sum += d*d in FP64. */
+static double orc_l2sq_f32(const float *q, const float *b, int d) {
+    double sum = 0.0;
+    for (int i = 0; i < d; i++) { float df = q[i] - b[i]; double dd = (double)df; sum += dd * dd; }
+    return sum;
+}
+/* BY_D_THEN_ID (GTP:168-171) */
+static int orc_gt_less(double da, int32_t ia, double db, int32_t ib) { return da < db || (da == db && ia < ib); }
+
+/* GTP:218-276 run(): per query a bounded max-heap over all base vectors (HeapK, GTP:173-189), ids ascending by (d, id).
+ * K must already be clamped to [1, N] (kFinal, GTP:238).  ids [Q][K], d2 [Q][K] (may be NULL). */
+void orc_groundtruth(const float *base, int64_t N, int d, const float *queries, int64_t Q, int K, int32_t *ids, double *d2) {
+    double *hd = (double *)malloc(sizeof(double) * (size_t)K);
+    int32_t *hi = (int32_t *)malloc(sizeof(int32_t) * (size_t)K);
+    for (int64_t q = 0; q < Q; q++) {
+        int n = 0;
+        for (int64_t b = 0; b < N; b++) {
+            double dist = orc_l2sq_f32(queries + (size_t)q * d, base + (size_t)b * d, d);
+            if (n == K && !orc_gt_less(dist, (int32_t)b, hd[0], hi[0])) continue;      /* GTP:180 */
+            int i;
+            if (n < K) { i = n++; }
+            else {  /* replace the root (the current worst) and sift down */
+                i = 0;
+                for (;;) {
+                    int l = 2 * i + 1, r = l + 1, big = -1;
+                    if (l < n) big = l;
+                    if (r < n && orc_gt_less(hd[l], hi[l], hd[r], hi[r])) big = r;
+                    if (big < 0 || !orc_gt_less(dist, (int32_t)b, hd[big], hi[big])) break;
+                    hd[i] = hd[big]; hi[i] = hi[big]; i = big;
+                }
+                hd[i] = dist; hi[i] = (int32_t)b;
+                continue;
+            }
+            /* sift up (max-heap on (d,id)) */
+            while (i > 0) {
+                int p = (i - 1) / 2;
+                if (!orc_gt_less(hd[p], hi[p], dist, (int32_t)b)) break;
+                hd[i] = hd[p]; hi[i] = hi[p]; i = p;
+            }
+            hd[i] = dist; hi[i] = (int32_t)b;
+        }
+        /* idsAscending (GTP:182-188): insertion sort of the K survivors by (d, id) */
+        for (int a = 1; a < n; a++) {
+            double dv = hd[a]; int32_t iv = hi[a]; int j = a - 1;
+            while (j >= 0 && orc_gt_less(dv, iv, hd[j], hi[j])) { hd[j + 1] = hd[j]; hi[j + 1] = hi[j]; j--; }
+            hd[j + 1] = dv; hi[j + 1] = iv;
+        }
+        for (int a = 0; a < K; a++) { ids[(size_t)q * K + a] = a < n ? hi[a] : -1; if (d2) d2[(size_t)q * K + a] = a < n ? hd[a] : NAN; }
+    }
+    free(hd); free(hi);
+}
+
+/* FSA:785-794: hits = results[0..min(K, n_ret)) found in gt[0..K); recall = hits / K. */
+double orc_recall_at_k(const int32_t *gt, const int32_t *res, int n_ret, int K) {
+    int hits = 0, n = n_ret < K ? n_ret : K;
+    for (int i = 0; i < n; i++) { int in = 0; for (int j = 0; j < K; j++) in |= gt[j] == res[i]; hits += in; }
+    return (double)hits / (double)K;
+}

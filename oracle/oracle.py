@@ -362,3 +362,25 @@ def migrate(store: Store, ids: np.ndarray, fresh_ivs: np.ndarray, target_version
     return int(lib().orc_migrate(C.c_int64(store.N), C.c_int(store.dim), _p(store.iv), _p(store.ct), _p(store.key_version), _p(ids),
                                  C.c_int64(ids.shape[0]), _p(fresh_ivs), C.c_int32(target_version), C.c_int32(st.n_keys),
                                  C.c_void_p(st.key_versions), C.c_void_p(st.keys)))
+
+
+def groundtruth(base_f32: np.ndarray, queries_f32: np.ndarray, K: int):
+    """GroundtruthPrecompute.run (GTP:218-276): ids int32 [Q, K] by (squared L2, id), and the squared distances."""
+    base_f32 = np.ascontiguousarray(base_f32, dtype=np.float32)
+    queries_f32 = np.ascontiguousarray(queries_f32, dtype=np.float32)
+    n, d = base_f32.shape
+    Q = queries_f32.shape[0]
+    K = min(max(1, K), n)
+    ids = np.empty((Q, K), dtype=np.int32)
+    d2 = np.empty((Q, K), dtype=np.float64)
+    lib().orc_groundtruth(_p(base_f32), C.c_int64(n), C.c_int(d), _p(queries_f32), C.c_int64(Q), C.c_int(K), _p(ids), _p(d2))
+    return ids, d2
+
+
+def recall_at_k(gt_row: np.ndarray, res_row: np.ndarray, n_ret: int, K: int) -> float:
+    """FSA:785-794."""
+    gt_row = np.ascontiguousarray(gt_row, dtype=np.int32)
+    res_row = np.ascontiguousarray(res_row, dtype=np.int32)
+    f = lib().orc_recall_at_k
+    f.restype = C.c_double
+    return float(f(_p(gt_row), _p(res_row), C.c_int(n_ret), C.c_int(K)))
