@@ -35,6 +35,17 @@ def log(*a):
         print("[bench]", *a, file=sys.stderr, flush=True)
 
 
+def load_traffic(workload_is_c2: bool):
+    """DRAM bytes per launch of the roofline kernel from the committed ncu --set full capture (C2 only), else None."""
+    if not workload_is_c2:
+        return None
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r1_decrypt_traffic.json")))
+        return float(d["dram_bytes_read"]) + float(d["dram_bytes_write"])
+    except Exception:
+        return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -171,6 +182,7 @@ def main():
     ap.add_argument("--n", type=int, default=0, help="override N (debug)")
     ap.add_argument("--q", type=int, default=0, help="override batch size (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-mixed", action="store_true", help="skip the config-5 Rotate + Migrate leg")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -313,6 +325,33 @@ def main():
                   "definition": "GroundtruthPrecompute.run + computeMetricsAtK (FSA:785-794), evaluated on the device"}
         log(f"recall@{k} = {recall['recall_at_k']:.4f} over {nq_gt} queries (ground truth + search + recall in {recall['groundtruth_s']:.1f}s)")
 
+    # ---- config 5: Rotate -> v2 + partial Migrate on the device, then the same batch again: results must not move (routing-ciphertext
+    #      orthogonality) and the per-record-version path must cost the same.  Outside the timed regions above.
+    mixed = None
+    if rank == 0 and world_size == 1 and not args.no_mixed:
+        ref_ids = gpu.search_batch(batches[0], k, cfg.probes, cfg.hard_cap, cfg.B)
+        km = HS.KeyManager(WL.MASTER_KEY)
+        gpu.keys_set(2, km.derive(2))                                                   # Rotate: v2 becomes available
+        mig = np.arange(0, cfg.N, 3, dtype=np.int32)
+        t0 = time.time()
+        out = gpu.migrate(mig, WL.record_ivs(len(mig), cfg.base_seed + 77), 2)         # Migrate ids = 0 (mod 3), in place in HBM
+        t_mig = time.time() - t0
+        for i in range(Wm):
+            step_dev(i)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(stream)
+        for i in range(K):
+            step_dev(Wm + i)
+        g1.record(stream)
+        barrier()
+        again = gpu.search_batch(batches[0], k, cfg.probes, cfg.hard_cap, cfg.B)
+        same = bool(np.array_equal(again["top_ids"], ref_ids["top_ids"]) and np.array_equal(again["top_dist"].view(np.uint64), ref_ids["top_dist"].view(np.uint64))
+                    and np.array_equal(again["counters"], ref_ids["counters"]))
+        mixed = {"migrated_records": int(out["count"]), "migrate_s_incl_copies": t_mig, "results_identical_after_rotate_migrate": same,
+                 "ms_per_step_mixed_versions": g0.elapsed_time(g1) / K, "versions": [1, 2]}
+        log(f"config 5: migrated {out['count']} records to v2 on the device in {t_mig:.2f}s; results identical: {same}; {mixed['ms_per_step_mixed_versions']:.2f} ms/step")
+
     if world_size > 1:
         t = torch.tensor([ms, e2e_ms, e2e_wall_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -346,10 +385,11 @@ def main():
                "e2e": {"value": e2e_val, "unit": "queries/s", "h2d_bytes_per_step": Q * dim * 8, "d2h_bytes_per_step": Q * k * 12 + Q * 4 + Q * 48,
                        "ms_per_step": e2e_ms / K, "wall_ms_per_step": e2e_wall_ms / K, "result_checksum": checksum},
                "roofline": {"bound": "hbm", "kernel": "refine_decrypt_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                            "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src,
+                            "frac": achieved / peak if peak else None, "traffic": load_traffic(args.config == "C2" and not args.n and not args.q),
+                            "traffic_unit": "bytes/launch (dram read+write, ncu; profiles/r1_decrypt_traffic.json)", "peak_source": peak_src,
                             "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": dec_ms, "pairs_per_launch": pairs / K},
                "stage_ms_per_step": {s: v / K for s, v in stage.items()},
-               "recall": recall, "setup_on_device_s": world["setup"],
+               "recall": recall, "setup_on_device_s": world["setup"], "mixed_versions": mixed,
                "cpu_baseline": cpu_baseline}
         print(json.dumps(out))
     gpu.close()

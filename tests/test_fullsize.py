@@ -1,0 +1,107 @@
+"""BASELINE configs[1] / configs[4] at FULL size (SIFT1M-shape 1M x 128, T=D=8, B=1024) through size-independent properties, plus
+an oracle spot check: device Setup (coding + partition build + bulk encryption), search, Rotate + partial Migrate on the device
+(config 5: results must not move), ground truth / recall.  One world, ~20 s on a B200 box."""
+import numpy as np
+import pytest
+
+from fspann_query_system_b200 import hostsetup as HS, workloads as WL
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def c2():
+    from fspann_query_system_b200.gpu import GpuContext
+    cfg = WL.CONFIGS["C2"]
+    base = WL.base_vectors(cfg)
+    alpha, r, omega = HS.build_gfunctions(base[:HS.MIN_SAMPLE_SIZE], cfg.m, cfg.lam, cfg.seed, cfg.T, cfg.D)
+    gpu = GpuContext(0)
+    gpu.gfunctions_upload(cfg.dim, cfg.T, cfg.D, cfg.m, cfg.lam, alpha, r, omega)
+    mn, mx, rep, ids = gpu.routing_build(base, HS.staged_order(cfg.N))
+    km = HS.KeyManager(WL.MASTER_KEY)
+    iv = WL.record_ivs(cfg.N, cfg.base_seed + 5)
+    gpu.keys_set(1, km.derive(1))
+    ct = gpu.encrypt_batch(np.arange(cfg.N, dtype=np.int32), base, iv, 1)
+    gpu.store_upload(cfg.dim, iv, ct, np.ones(cfg.N, dtype=np.int32))
+    queries = WL.query_vectors(cfg, 2000)
+    yield dict(cfg=cfg, gpu=gpu, base=base, alpha=alpha, r=r, omega=omega, mn=mn, mx=mx, rep=rep, ids=ids, iv=iv, ct=ct, km=km, queries=queries)
+    gpu.close()
+
+
+def test_device_built_index_is_a_valid_greedy_partitioning(c2):
+    cfg, mn, mx, ids = c2["cfg"], c2["mn"], c2["mx"], c2["ids"]
+    assert c2["gpu"].get_info("build_treeified") == 0                     # decimal ids up to 1M never fill a HashMap bin with 9 entries
+    assert ids.shape == (cfg.T * cfg.D, cfg.N) and mn.shape == (cfg.T * cfg.D, (cfg.N + 63) // 64)
+    assert (mn <= mx).all() and (mn[:, 1:] >= mx[:, :-1]).all() and (mn >= 0).all()      # disjoint sorted key ranges (GP:51-72)
+    for td in (0, 17, cfg.T * cfg.D - 1):
+        assert np.array_equal(np.sort(ids[td]), np.arange(cfg.N, dtype=np.int32))          # every id exactly once per division
+    # spot check against the host restatement of GP.build for one division
+    codes = c2["gpu"].tokengen_batch(c2["base"][:4096])
+    keys = HS.compute_keys(codes[:, 5, 0])
+    pos_of = np.empty(cfg.N, dtype=np.int64); pos_of[ids[5]] = np.arange(cfg.N)
+    p = pos_of[:4096] // 64
+    assert ((mn[5][p] <= keys) & (keys <= mx[5][p])).all()                                  # each id sits in the partition covering its key
+
+
+def test_search_matches_oracle_sample_and_is_invariant_under_rotate_migrate(c2):
+    cfg, gpu, q = c2["cfg"], c2["gpu"], c2["queries"]
+    k = cfg.k
+    got = gpu.search_batch(q, k, cfg.probes, cfg.hard_cap, cfg.B)
+    assert (got["n_ret"] == k).all() and (got["counters"][:, 5] == cfg.B).all()            # B candidates refined per query
+    assert (got["counters"][:, 2] == cfg.B).all()                                           # all authenticated and decrypted
+    assert (np.diff(got["top_dist"], axis=1) >= 0).all()                                    # sorted
+    # oracle spot check on 24 queries: ids exact, FP64 distances bit-exact
+    g = O.GFunctions(cfg.dim, cfg.T, cfg.D, cfg.m, cfg.lam, c2["alpha"], c2["r"], c2["omega"])
+    ix = O.Index(g, cfg.N, c2["mn"].shape[1], c2["mn"], c2["mx"], c2["rep"], c2["ids"])
+    st = O.Store(cfg.dim, c2["iv"], c2["ct"], np.ones(cfg.N, dtype=np.int32), {1: c2["km"].derive(1)})
+    codes = O.tokengen_batch(q[:24], g)
+    assert np.array_equal(gpu.tokengen_batch(q[:24]), codes)
+    for i in range(24):
+        ref = O.search(ix, st, q[i], codes[i], k, cfg.probes, cfg.hard_cap, cfg.B)
+        assert np.array_equal(got["top_ids"][i], ref["top_ids"])
+        assert np.array_equal(got["top_dist"][i].view(np.uint64), ref["top_dist"].view(np.uint64))
+    # config 5: Rotate -> v2, Migrate ids = 0 (mod 3) on the device with fresh IVs; then Rotate -> v3 and Migrate the touched set
+    gpu.touched(clear=True)
+    gpu.keys_set(2, c2["km"].derive(2))
+    mig = np.arange(0, cfg.N, 3, dtype=np.int32)
+    out = gpu.migrate(mig, WL.record_ivs(len(mig), 4242), 2)
+    assert out["count"] == len(mig) and out["reencrypted"].all()
+    assert not np.array_equal(out["ct"][:100], c2["ct"][mig[:100]])                         # ciphertexts really changed ...
+    again = gpu.search_batch(q, k, cfg.probes, cfg.hard_cap, cfg.B)
+    for key in ("top_ids", "n_ret", "counters"):                                            # ... results did not
+        assert np.array_equal(again[key], got[key]), key
+    assert np.array_equal(again["top_dist"].view(np.uint64), got["top_dist"].view(np.uint64))
+    touched = gpu.touched(clear=True)
+    assert 0 < len(touched) <= 2000 * cfg.B
+    gpu.keys_set(3, c2["km"].derive(3))
+    out3 = gpu.migrate(touched, WL.record_ivs(len(touched), 4243), 3)
+    assert out3["count"] == len(touched)
+    third = gpu.search_batch(q, k, cfg.probes, cfg.hard_cap, cfg.B)
+    assert np.array_equal(third["top_ids"], got["top_ids"]) and np.array_equal(third["top_dist"].view(np.uint64), got["top_dist"].view(np.uint64))
+    assert gpu.migrate(touched, WL.record_ivs(len(touched), 4244), 3)["count"] == 0         # idempotent
+    # a migrated record decrypts under its new version with the oracle (OpenSSL): AAD and tag are the reference's
+    j = 7
+    rc, pt = O.decrypt_point(int(touched[j]), 3, cfg.dim, c2["km"].derive(3), out3["iv"][j].tobytes(), out3["ct"][j].tobytes())
+    assert rc == 0 and np.array_equal(pt, c2["base"][touched[j]])
+
+
+def test_groundtruth_and_recall_at_full_size(c2):
+    cfg, gpu = c2["cfg"], c2["gpu"]
+    q = c2["queries"][:256]
+    b32, q32 = c2["base"].astype(np.float32), q.astype(np.float32)
+    gt, d2 = gpu.groundtruth(b32, q32, 10, want_d2=True)
+    assert (np.diff(d2, axis=1) >= 0).all()
+    for i in (0, 100, 255):                                                                  # brute-force check of whole rows
+        s = ((q32[i][None, :] - b32).astype(np.float64) ** 2).sum(1)                         # integer-valued data: exact in any order
+        o = np.lexsort((np.arange(cfg.N), s))[:10]
+        assert np.array_equal(gt[i], o) and np.array_equal(d2[i], s[o])
+    res = gpu.search_batch(q, 10, cfg.probes, cfg.hard_cap, cfg.B)
+    rec = gpu.recall_batch(gt, res["top_ids"], 10, res["n_ret"])
+    assert 0.2 < rec.mean() <= 1.0
+    # the true nearest neighbours found by the search carry the exact distance: sqrt of the ground-truth sum
+    for i in range(256):
+        hit = np.isin(res["top_ids"][i], gt[i])
+        for pos in np.nonzero(hit)[0]:
+            gi = int(np.nonzero(gt[i] == res["top_ids"][i][pos])[0][0])
+            assert res["top_dist"][i][pos] == np.sqrt(d2[i][gi])
