@@ -226,6 +226,9 @@ def main():
         return
 
     # ------------------------------------------------------------------ our arm
+    # stdout carries exactly ONE JSON line: anything a library prints there (e.g. NCCL's version banner) is sent to stderr
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
@@ -391,7 +394,7 @@ def main():
                "stage_ms_per_step": {s: v / K for s, v in stage.items()},
                "recall": recall, "setup_on_device_s": world["setup"], "mixed_versions": mixed,
                "cpu_baseline": cpu_baseline}
-        print(json.dumps(out))
+        print(json.dumps(out), file=real_stdout, flush=True)
     gpu.close()
     if world_size > 1:
         dist.destroy_process_group()
