@@ -45,6 +45,7 @@ struct fspann_ctx {
     int opt_route_general = 0;   // force the general (sequential, cap-exact) Route kernel
     int opt_route_wl_extra = -1; // test hook: clamp the fast path's dedicated worklist (forces the no-worklist fallback when exceeded)
     int last_route_path = 0;     // 1 = shared-memory fast path, 2 = general path
+    bool last_queries_finite = true;
     DevBuf s_queries, s_codes, s_cand_ids, s_cand_sc, s_ncand, s_raw, s_uniq_cnt, s_route_scratch, s_overflow;
     DevBuf s_rec_verdict, s_qf32, s_qu8, s_f32_exact;
     DevKeyRing ring_host{};
@@ -238,7 +239,7 @@ int do_refine(fspann_ctx *ctx, int64_t Q, const double *d_queries, const int32_t
     p.topk_ids = d_topk_ids; p.topk_dist = d_topk_dist; p.n_ret = d_nret; p.n_dec = d_ndec; p.topk_rank = ctx->want_rank;
     ENSURE(ctx->s_qf32, sizeof(float) * (size_t)Q * sv.dim);
     ENSURE(ctx->s_qu8, (size_t)Q * sv.dim + 16);
-    ENSURE(ctx->s_f32_exact, 2 * sizeof(int32_t));
+    ENSURE(ctx->s_f32_exact, 4 * sizeof(int32_t));
     p.queries_f32 = (const float *)ctx->s_qf32.p; p.queries_u8 = (const uint8_t *)ctx->s_qu8.p; p.f32_exact = (const int32_t *)ctx->s_f32_exact.p;
     LAUNCHED(launch_queries_to_f32(ctx->stream, d_queries, (float *)ctx->s_qf32.p, (uint8_t *)ctx->s_qu8.p, Q * (int64_t)sv.dim, (int32_t *)ctx->s_f32_exact.p));
     // unknown / retired key version is the default verdict (KRS:82-88); the verify kernel overwrites it per live version
@@ -881,9 +882,13 @@ int fspann_search_batch_dev(fspann_ctx *ctx, int64_t Q, const double *d_queries,
     if (allow_retry) {
         // QSI:327-337 + 444-447: once per query, if returned < K or decrypted < 10*K, redo with 10 probes.
         std::vector<int32_t> nret((size_t)Q), ndec((size_t)Q);
+        int32_t flags[4] = {1, 1, 1, 1};
         CK(cudaMemcpyAsync(nret.data(), d_n_ret, sizeof(int32_t) * (size_t)Q, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(ndec.data(), ctx->s_ndec.p, sizeof(int32_t) * (size_t)Q, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(flags, ctx->s_f32_exact.p, sizeof flags, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
+        ctx->last_queries_finite = flags[2] != 0;
+        if (!ctx->last_queries_finite) return fail(ctx, FSPANN_E_ARG, "Vector contains NaN/Inf (Coding:357-359)");
         std::vector<int32_t> rows;
         // a first pass with no decrypted candidate returns immediately (QSI:293: scored.isEmpty() -> return), no retry
         for (int64_t q = 0; q < Q; q++)
@@ -922,8 +927,10 @@ int fspann_search_batch(fspann_ctx *ctx, int64_t Q, const double *queries, int32
     if (k <= 0) return fail(ctx, FSPANN_E_ARG, "topK must be > 0 (QTF:65)");
     const int dim = ctx->rv.dim;
     // QSI:137: a query that is not all-finite returns an empty list; createToken would already have thrown
-    // (Coding:357-359), so the batch is rejected like the reference rejects the token.
-    if (!all_finite(queries, Q * dim)) return fail(ctx, FSPANN_E_ARG, "Vector contains NaN/Inf (Coding:357-359)");
+    // (Coding:357-359), so the batch is rejected like the reference rejects the token.  Small batches are checked on the host
+    // before any work; large ones by the device pass that scans every query value anyway (flag read with the retry counters),
+    // and nothing is copied back when it trips.
+    if (Q * dim <= 65536 && !all_finite(queries, Q * dim)) return fail(ctx, FSPANN_E_ARG, "Vector contains NaN/Inf (Coding:357-359)");
     ENSURE(ctx->s_queries, sizeof(double) * (size_t)Q * dim);
     ENSURE(ctx->s_topk_ids, sizeof(int32_t) * (size_t)Q * k); ENSURE(ctx->s_topk_dist, sizeof(double) * (size_t)Q * k);
     ENSURE(ctx->s_nret, sizeof(int32_t) * (size_t)Q); ENSURE(ctx->s_counters, sizeof(int64_t) * FSPANN_COUNTERS * (size_t)Q);

@@ -750,7 +750,7 @@ int launch_refine_decrypt(cudaStream_t s, const StoreView &sv, const RefineParam
 // Compact copies of the query batch (FP32 and uint8) + flags telling whether every value survived the round trip exactly:
 // exact[0] for FP32, exact[1] for uint8 (integers 0..255).
 __global__ void queries_compact_kernel(const double *__restrict__ q, float *__restrict__ out32, uint8_t *__restrict__ out8, int64_t n, int32_t *exact) {
-    bool ok32 = true, ok8 = true;
+    bool ok32 = true, ok8 = true, fin = true;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const double v = q[i];
         const float f = (float)v;
@@ -760,13 +760,16 @@ __global__ void queries_compact_kernel(const double *__restrict__ q, float *__re
         const int b = in8 ? (int)v : 0;
         out8[i] = (uint8_t)b;
         ok8 &= in8 && (double)b == v;
+        fin &= (((unsigned long long)__double_as_longlong(v) >> 52) & 0x7ffull) != 0x7ffull;     // isValid (QSI:407-413)
     }
     if (!__all_sync(0xffffffffu, ok32) && (threadIdx.x & 31) == 0) atomicAnd(&exact[0], 0);
     if (!__all_sync(0xffffffffu, ok8) && (threadIdx.x & 31) == 0) atomicAnd(&exact[1], 0);
+    if (!__all_sync(0xffffffffu, fin) && (threadIdx.x & 31) == 0) atomicAnd(&exact[2], 0);
 }
+// exact[0] / exact[1]: the FP32 / uint8 copy is value-identical; exact[2]: every value is finite.
 int launch_queries_to_f32(cudaStream_t s, const double *q, float *out, uint8_t *out8, int64_t n, int32_t *exact) {
     if (n <= 0) return 0;
-    if (cudaMemsetAsync(exact, 0xff, 2 * sizeof(int32_t), s) != cudaSuccess) return -1;
+    if (cudaMemsetAsync(exact, 0xff, 4 * sizeof(int32_t), s) != cudaSuccess) return -1;
     int grid = (int)((n + 255) / 256); if (grid > 148 * 8) grid = 148 * 8;
     queries_compact_kernel<<<grid, 256, 0, s>>>(q, out, out8, n, exact);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;

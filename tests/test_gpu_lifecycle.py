@@ -288,3 +288,24 @@ def test_rotate_migrate_retire_keep_results_invariant(world_factory):
             assert [int(i) for i, _ in res4[q]] == ref["top_ids"].tolist()
     finally:
         sys_.shutdown()
+
+
+def test_large_batch_with_a_non_finite_query_is_rejected_by_the_device_check(world_factory):
+    """Batches above 64k values skip the host scan: the device pass that compacts the queries also checks isValid (QSI:407-413);
+    the call fails like createToken would (Coding:357-359) and returns nothing."""
+    w = world_factory(**W1)
+    ctx = w.gpu_context()
+    try:
+        big = np.tile(w.queries, (60, 1))                                # 2400 x 32 = 76800 values
+        assert big.size > 65536
+        ok = ctx.search_batch(big, 10, 5, 20000, 64)
+        assert (ok["n_ret"] == 10).all()
+        for poison in (np.nan, np.inf, -np.inf):
+            bad = big.copy()
+            bad[1777, 13] = poison
+            with pytest.raises(N.IllegalArgumentError):
+                ctx.search_batch(bad, 10, 5, 20000, 64)
+        again = ctx.search_batch(big, 10, 5, 20000, 64)                  # the context is still usable
+        assert np.array_equal(again["top_ids"], ok["top_ids"])
+    finally:
+        ctx.close()
