@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) route_fast_kernel(RoutingView r
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int64_t n_ids = rv.n_ids;
-    int fshift = 32; while ((1u << (32 - fshift)) < (uint32_t)tbl * 8u) fshift--;
+    int fshift = 32; while ((1u << (32 - fshift)) < (uint32_t)tbl * 4u) fshift--;     // buckets per filter array (two arrays share the table region)
 
     for (int64_t q = blockIdx.x; q < p.Q; q += gridDim.x) {
         __syncthreads();
@@ -501,57 +501,100 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) route_fast_kernel(RoutingView r
         if (tid < 256) s_hist[tid] = 0;
         if (tid == 0) { s_raw = 0; s_uniq = 0; s_m = 0; s_ncls = 0; s_nwl = 0; s_nlow = 0; }
         __syncthreads();
-        // ---- 2. gather ids (each partition row is 256 contiguous bytes; 4 loads in flight per thread) and set the filter:
-        //         bit0 = "bucket taken", bit1 = "taken twice".  ~95 % of the visited ids occur once; a position whose bucket never
-        //         collided is the only occurrence of its id, everything else goes through the exact path below.
+        // ---- 2. gather ids and set the duplicate filter.  A thread owns 4 consecutive positions (one 16-byte slice of a 256-byte
+        //         partition row; two slices in flight).  The filter is TWO arrays of 2-bit buckets (different multiplicative
+        //         hashes): bit0 = "bucket taken", bit1 = "taken twice".  ~95 % of the visited ids occur once; an id whose bucket
+        //         was taken once in EITHER array is the only occurrence of its id, everything else takes the exact path below.
         uint32_t *F = table_w;
-        for (int e0 = tid; e0 < n_raw; e0 += 4 * RQ_THREADS) {
-            int32_t idv[4];
+        const uint32_t f2_off = (uint32_t)tbl >> 2;                        // second array: the upper half of the region (words)
+        const bool vec_ok = (n_ids & 3) == 0;
+        const int n4 = n_raw >> 2;
+        for (int q0 = tid; q0 < n4; q0 += 2 * RQ_THREADS) {
+            int4 idv[2];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int e = e0 + u * RQ_THREADS;
-                idv[u] = -1;
+            for (int u = 0; u < 2; u++) {
+                const int e = (q0 + u * RQ_THREADS) << 2;
+                idv[u] = make_int4(-1, -1, -1, -1);
                 if (e < n_raw) {
-                    const int v = e >> 6, pos = e & 63;
-                    if (pos < (int)vlen_s[v]) idv[u] = __ldg(rv.ids + vbase_s[v] + pos);
+                    const int v = e >> 6, pos = e & 63, len = (int)vlen_s[v];
+                    const int32_t *src = rv.ids + vbase_s[v] + pos;
+                    if (vec_ok && pos + 4 <= len) idv[u] = __ldg(reinterpret_cast<const int4 *>(src));
+                    else {
+                        if (pos + 0 < len) idv[u].x = __ldg(src + 0);
+                        if (pos + 1 < len) idv[u].y = __ldg(src + 1);
+                        if (pos + 2 < len) idv[u].z = __ldg(src + 2);
+                        if (pos + 3 < len) idv[u].w = __ldg(src + 3);
+                    }
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int e = e0 + u * RQ_THREADS;
+            for (int u = 0; u < 2; u++) {
+                const int e = (q0 + u * RQ_THREADS) << 2;
                 if (e < n_raw) {
-                    int32_t id = idv[u];
-                    if (rv.deleted && id >= 0 && id < rv.n_deleted && rv.deleted[id]) id = -1;     // PIS:739
-                    ids_s[e] = id;
-                    if (id >= 0) {
-                        const uint32_t h = ((uint32_t)id * 0x9E3779B1u) >> fshift;
-                        const uint32_t sh = (h & 15u) * 2u;
-                        const uint32_t old = atomicOr(&F[h >> 4], 1u << sh);
-                        if ((old >> sh) & 1u) atomicOr(&F[h >> 4], 2u << sh);
+                    int32_t id4[4] = {idv[u].x, idv[u].y, idv[u].z, idv[u].w};
+                    if (rv.deleted) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) if (id4[j] >= 0 && id4[j] < rv.n_deleted && rv.deleted[id4[j]]) id4[j] = -1;     // PIS:739
+                    }
+                    *reinterpret_cast<int4 *>(ids_s + e) = make_int4(id4[0], id4[1], id4[2], id4[3]);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        if (id4[j] >= 0) {
+                            const uint32_t h1 = ((uint32_t)id4[j] * 0x9E3779B1u) >> fshift, h2 = ((uint32_t)id4[j] * 0x85EBCA6Bu) >> fshift;
+                            const uint32_t s1 = (h1 & 15u) * 2u, s2 = (h2 & 15u) * 2u;
+                            const uint32_t o1 = atomicOr(&F[h1 >> 4], 1u << s1);
+                            if ((o1 >> s1) & 1u) atomicOr(&F[h1 >> 4], 2u << s1);
+                            const uint32_t o2 = atomicOr(&F[f2_off + (h2 >> 4)], 1u << s2);
+                            if ((o2 >> s2) & 1u) atomicOr(&F[f2_off + (h2 >> 4)], 2u << s2);
+                        }
                     }
                 }
             }
         }
         __syncthreads();
-        // ---- 3. classify every position: single (final), or involved (-> worklist for the exact path).  A warp covers 32
-        //         consecutive positions of ONE visit, so its singles share one score: one histogram atomic per warp. ----
+        // ---- 3. classify every position: single (final), or involved (-> worklist for the exact path).  A half-warp covers the 64
+        //         positions of ONE visit, so its singles share one score: one histogram atomic per half-warp. ----
         int my_raw = 0, my_uniq = 0;
         bool wl_ok = true;
-        for (int e0 = 0; e0 < n_raw; e0 += RQ_THREADS) {
-            const int e = e0 + tid;
-            const int32_t id = e < n_raw ? ids_s[e] : -1;
-            bool single = false, inv = false;
-            if (id >= 0) {
-                const uint32_t h = ((uint32_t)id * 0x9E3779B1u) >> fshift;
-                inv = ((F[h >> 4] >> ((h & 15u) * 2u)) & 2u) != 0;
-                single = !inv;
+        for (int q0 = 0; q0 < n4; q0 += RQ_THREADS) {
+            const int q4 = q0 + tid;
+            const bool valid = q4 < n4;
+            const int e = q4 << 2;
+            const int4 idq = valid ? *reinterpret_cast<const int4 *>(ids_s + e) : make_int4(-1, -1, -1, -1);
+            const int32_t id4[4] = {idq.x, idq.y, idq.z, idq.w};
+            const uint32_t sc = valid ? vs_s[e >> 6] : 255u;
+            uint32_t packed = 0, invmask = 0; int n_single = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                uint32_t b = 255u;
+                if (id4[j] >= 0) {
+                    const uint32_t h1 = ((uint32_t)id4[j] * 0x9E3779B1u) >> fshift;
+                    bool inv = ((F[h1 >> 4] >> ((h1 & 15u) * 2u)) & 2u) != 0;
+                    if (inv) {
+                        const uint32_t h2 = ((uint32_t)id4[j] * 0x85EBCA6Bu) >> fshift;
+                        inv = ((F[f2_off + (h2 >> 4)] >> ((h2 & 15u) * 2u)) & 2u) != 0;
+                    }
+                    if (inv) { b = 254u; invmask |= 1u << j; } else { b = sc; n_single++; }
+                }
+                packed |= b << (8 * j);
             }
-            const uint32_t sc = e < n_raw ? vs_s[e >> 6] : 255u;
-            if (e < n_raw) best_s[e] = (uint8_t)(single ? sc : (inv ? 254u : 255u));
-            const unsigned bs = __ballot_sync(0xffffffffu, single);
-            if (lane == 0 && bs) { const int c = __popc(bs); atomicAdd(&s_hist[sc], c); my_raw += c; my_uniq += c; }
-            const int slot = list_slot(&s_nwl, inv, lane);
-            if (inv) { if (slot < wl_cap) wl[slot] = (uint16_t)e; else wl_ok = false; }
+            if (valid) *reinterpret_cast<uint32_t *>(best_s + e) = packed;
+            // singles of the half-warp (one visit)
+            int hs = n_single;
+#pragma unroll
+            for (int o = 8; o; o >>= 1) hs += __shfl_xor_sync(0xffffffffu, hs, o);
+            if ((lane & 15) == 0 && hs) { atomicAdd(&s_hist[sc], hs); my_raw += hs; my_uniq += hs; }
+            // involved positions -> worklist (one shared atomic per warp)
+            const int c = __popc(invmask);
+            int tot;
+            const int off = warp_excl_scan(c, lane, tot);
+            int base = 0;
+            if (lane == 0 && tot) base = atomicAdd(&s_nwl, tot);
+            base = __shfl_sync(0xffffffffu, base, 0) + off;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if ((invmask >> j) & 1u) { if (base < wl_cap) wl[base] = (uint16_t)(e + j); else wl_ok = false; base++; }
+            }
         }
         wl_ok = __syncthreads_and(wl_ok ? 1 : 0) != 0;
         const int n_inv = s_nwl;
