@@ -454,6 +454,33 @@ __device__ __forceinline__ int list_slot(int32_t *counter, bool in, int lane) {
     return in ? base + __popc(bal & ((1u << lane) - 1u)) : -1;
 }
 
+// Bitonic sort of one 32-bit key per thread (element i lives in thread i): strides < 32 are exchanged with warp shuffles, larger
+// strides through `buf` in shared memory.  N > 0: the network for exactly N elements, fully unrolled; N == 0: n at run time.
+template <int N>
+__device__ __forceinline__ uint32_t bitonic_sort32(uint32_t a, int i, uint32_t *buf, int n_rt = 0) {
+    const int n = N > 0 ? N : n_rt;
+#pragma unroll
+    for (int k = 2; k <= n; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const bool asc = (i & k) == 0;
+            uint32_t b;
+            if (j >= 32) {
+                __syncthreads();
+                if (i < n) buf[i] = a;
+                __syncthreads();
+                b = i < n ? buf[i ^ j] : 0xffffffffu;
+            } else {
+                b = __shfl_xor_sync(0xffffffffu, a, j);
+            }
+            const bool lower = (i & j) == 0;                // this thread keeps the smaller of the pair when ascending
+            const bool take_b = (lower == asc) ? (b < a) : (b > a);
+            if (take_b) a = b;
+        }
+    }
+    return a;
+}
+
 // best_s encoding: 255 = not a representative position (invalid id, or a later occurrence of a duplicated id),
 // 254 = occurrence of a possibly duplicated id waiting for the exact path, s < 128 = the only occurrence of its id (score s),
 // 0x80 | s = first occurrence of a duplicated id whose minimum score over all occurrences is s.
@@ -795,23 +822,8 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) route_fast_kernel(RoutingView r
                 sid[rank] = idv;                                          // the worklist (which overlaps skey / sid) is dead by now
             }
             const int i = tid;
-            for (int k = 2; k <= sort_n; k <<= 1) {
-                for (int j = k >> 1; j > 0; j >>= 1) {
-                    const bool asc = (i & k) == 0;
-                    uint32_t b;
-                    if (j >= 32) {
-                        __syncthreads();
-                        if (i < sort_n) key32[i] = a;
-                        __syncthreads();
-                        b = i < sort_n ? key32[i ^ j] : 0xffffffffu;
-                    } else {
-                        b = __shfl_xor_sync(0xffffffffu, a, j);
-                    }
-                    const bool lower = (i & j) == 0;                // this thread keeps the smaller of the pair when ascending
-                    const bool take_b = (lower == asc) ? (b < a) : (b > a);
-                    if (take_b) a = b;
-                }
-            }
+            if (sort_n == RQ_THREADS) a = bitonic_sort32<RQ_THREADS>(a, i, key32);      // fully unrolled network (B in 513..1024)
+            else a = bitonic_sort32<0>(a, i, key32, sort_n);
             __syncthreads();
             if (i < want) { out_id[i] = sid[a & ((1u << rb) - 1u)]; out_sc[i] = (int32_t)(a >> (cb + rb)); }
         } else {
