@@ -946,6 +946,55 @@ int fspann_search_batch(fspann_ctx *ctx, int64_t Q, const double *queries, int32
     return FSPANN_OK;
 }
 
+// ---- device-resident building blocks of the database-sharded deployment (BASELINE config 4) ---------------------
+// Route is query-parallel (every rank routes its slice of the batch on the replicated index), Refine is data-parallel (every rank
+// refines, for ALL queries, the candidates its store shard holds); two all-gathers (candidate lists, per-shard top-k) connect them.
+int fspann_route_batch_dev(fspann_ctx *ctx, int64_t Q, const double *d_queries, int32_t probes, int64_t hard_cap, int32_t B,
+                           int32_t *d_cand_ids, int32_t *d_n_cand, int32_t *d_raw_seen, int32_t *d_unique) {
+    if (!ctx) return FSPANN_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    int rc = check_routing(ctx); if (rc) return rc;
+    if (ctx->rv.n_ids <= 1 && ctx->rv.P <= 1) return fail(ctx, FSPANN_E_STATE, "Index not finalized: only GFunctions uploaded");
+    if (Q == 0) return FSPANN_OK;
+    if (Q < 0 || !d_queries || !d_cand_ids || !d_n_cand) return fail(ctx, FSPANN_E_ARG, "null array");
+    if (B <= 0) return fail(ctx, FSPANN_E_ARG, "refinementLimit must be > 0");
+    if (probes <= 0) probes = 5;
+    const RoutingView &rv = ctx->rv;
+    ENSURE(ctx->s_codes, sizeof(uint64_t) * (size_t)Q * rv.TD * rv.W);
+    ENSURE(ctx->s_cand_sc, sizeof(int32_t) * (size_t)Q * B);
+    ENSURE(ctx->s_raw, sizeof(int32_t) * (size_t)Q); ENSURE(ctx->s_uniq_cnt, sizeof(int32_t) * (size_t)Q);
+    LAUNCHED(launch_tokengen(ctx->stream, rv, Q, d_queries, (uint64_t *)ctx->s_codes.p));
+    return do_route(ctx, Q, (const uint64_t *)ctx->s_codes.p, probes, hard_cap, B, d_cand_ids, (int32_t *)ctx->s_cand_sc.p, d_n_cand,
+                    d_raw_seen ? d_raw_seen : (int32_t *)ctx->s_raw.p, d_unique ? d_unique : (int32_t *)ctx->s_uniq_cnt.p);
+}
+
+int fspann_refine_batch_dev(fspann_ctx *ctx, int64_t Q, const double *d_queries, const int32_t *d_cand_ids, const int32_t *d_n_cand,
+                            int32_t cand_stride, int32_t k, int32_t *d_topk_ids, double *d_topk_dist, int32_t *d_topk_rank,
+                            int32_t *d_n_ret, int32_t *d_n_decrypted) {
+    if (!ctx) return FSPANN_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    int rc = check_store(ctx); if (rc) return rc;
+    if (Q == 0) return FSPANN_OK;
+    if (Q < 0 || !d_queries || !d_cand_ids || !d_n_cand || !d_topk_ids || !d_topk_dist || !d_n_ret) return fail(ctx, FSPANN_E_ARG, "null array");
+    if (k <= 0 || cand_stride <= 0) return fail(ctx, FSPANN_E_ARG, "topK and cand_stride must be > 0");
+    ENSURE(ctx->s_ndec, sizeof(int32_t) * (size_t)Q);
+    ctx->want_rank = d_topk_rank;
+    rc = do_refine(ctx, Q, d_queries, d_cand_ids, d_n_cand, cand_stride, k, d_topk_ids, d_topk_dist, d_n_ret,
+                   d_n_decrypted ? d_n_decrypted : (int32_t *)ctx->s_ndec.p, false);
+    ctx->want_rank = nullptr;
+    return rc;
+}
+
+int fspann_merge_topk_dev(fspann_ctx *ctx, int32_t n_shards, int64_t Q, int32_t k, const double *d_dist, const int32_t *d_rank,
+                          const int32_t *d_ids, int32_t *d_out_ids, double *d_out_dist, int32_t *d_out_n_ret) {
+    if (!ctx) return FSPANN_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (Q == 0) return FSPANN_OK;
+    if (n_shards <= 0 || Q < 0 || k <= 0 || !d_dist || !d_rank || !d_ids || !d_out_ids || !d_out_dist || !d_out_n_ret) return fail(ctx, FSPANN_E_ARG, "null array");
+    LAUNCHED(launch_merge_topk(ctx->stream, n_shards, Q, k, d_dist, d_rank, d_ids, d_out_ids, d_out_dist, d_out_n_ret));
+    return FSPANN_OK;
+}
+
 int fspann_touched_fetch(fspann_ctx *ctx, uint32_t *bitmap_out, int64_t n_words, int32_t clear) {
     if (!ctx) return FSPANN_E_ARG;
     CK(cudaSetDevice(ctx->device));

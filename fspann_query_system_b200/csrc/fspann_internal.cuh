@@ -139,6 +139,8 @@ int launch_gt_chunk(cudaStream_t s, const float *base, int64_t N, int dim, const
 int launch_recall(cudaStream_t s, int Q, int K, const int32_t *gt, int gt_stride, const int32_t *res, int res_stride, const int32_t *n_ret,
                   double *recall);
 int gt_max_k();
+int launch_merge_topk(cudaStream_t s, int S, int64_t Q, int k, const double *dist, const int32_t *rank, const int32_t *ids, int32_t *out_ids,
+                      double *out_dist, int32_t *out_nret);
 int launch_debug_decrypt(cudaStream_t s, const StoreView &sv, int64_t n, const int32_t *ids, double *pt, uint8_t *verdict);
 
 }  // namespace fsp

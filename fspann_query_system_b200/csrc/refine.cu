@@ -846,6 +846,52 @@ int launch_refine_topk(cudaStream_t s, const RefineParams &p) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// cross-shard merge (database-sharded store, BASELINE config 4): S per-shard top-k lists [S][Q][k] of (distance, candidate
+// rank, id), padded with id = -1 -> the global top-k ordered by (distance, rank).  The rank is the candidate's position in the
+// (identical on every shard) ordered candidate list, so this reproduces the reference's stable sort over all B candidates
+// (QSI:298-316) bit for bit.  One warp per query, k rounds of warp-wide arg-min.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void merge_topk_kernel(int S, int64_t Q, int k, const double *__restrict__ dist, const int32_t *__restrict__ rank, const int32_t *__restrict__ ids,
+                                  int32_t *__restrict__ out_ids, double *__restrict__ out_dist, int32_t *__restrict__ out_nret) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (q >= Q) return;
+    const int n = S * k;
+    unsigned long long lk = 0ull; int lr = -1;                       // last selected (key, rank)
+    int got = 0;
+    for (int round = 0; round < k; round++) {
+        unsigned long long best = ~0ull; int best_r = 0x7fffffff, best_id = -1;
+        for (int j = lane; j < n; j += 32) {
+            const int s = j / k, i = j - s * k;
+            const size_t at = ((size_t)s * Q + q) * k + i;
+            const int32_t id = ids[at];
+            if (id < 0) continue;
+            const unsigned long long key = (unsigned long long)__double_as_longlong(dist[at]);
+            const int r = rank[at];
+            const bool after = round == 0 || key > lk || (key == lk && r > lr);
+            if (after && (key < best || (key == best && r < best_r))) { best = key; best_r = r; best_id = id; }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const unsigned long long ok = __shfl_xor_sync(0xffffffffu, best, o);
+            const int orr = __shfl_xor_sync(0xffffffffu, best_r, o), oi = __shfl_xor_sync(0xffffffffu, best_id, o);
+            if (ok < best || (ok == best && orr < best_r)) { best = ok; best_r = orr; best_id = oi; }
+        }
+        if (best_id < 0) break;                                      // fewer than k results over all shards
+        lk = best; lr = best_r; got++;
+        if (lane == 0) { out_ids[q * k + round] = best_id; out_dist[q * k + round] = __longlong_as_double((long long)best); }
+    }
+    for (int i = got + lane; i < k; i += 32) { out_ids[q * k + i] = -1; out_dist[q * k + i] = __longlong_as_double(0x7ff8000000000000ll); }
+    if (lane == 0) out_nret[q] = got;
+}
+int launch_merge_topk(cudaStream_t s, int S, int64_t Q, int k, const double *dist, const int32_t *rank, const int32_t *ids, int32_t *out_ids,
+                      double *out_dist, int32_t *out_nret) {
+    if (Q <= 0) return 0;
+    merge_topk_kernel<<<(unsigned)((Q * 32 + 255) / 256), 256, 0, s>>>(S, Q, k, dist, rank, ids, out_ids, out_dist, out_nret);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // small helpers
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void counters_kernel(int64_t Q, const int32_t *raw, const int32_t *uniq, const int32_t *n_dec, const int32_t *n_ret,

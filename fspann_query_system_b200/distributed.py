@@ -3,8 +3,12 @@
 * query-parallel (BASELINE config 3): queries are independent (QSI.search shares no mutable state across queries), so the
   batch is split contiguously over ranks, every rank holds a replica of the routing index + store, and there is NO
   collective on the data path (`split_batch`; bench.py uses it for its weak-scaling runs).
-* database-sharded (BASELINE config 4): the routing index is replicated, so every rank derives the IDENTICAL ordered
-  candidate list; the encrypted store is sharded by contiguous global-id range; each rank authenticates + decrypts + scores
+* database-sharded (BASELINE config 4), device-resident form `DeviceShardedSearcher`: Route is query-parallel on the replicated
+  routing index (each rank routes its slice of the batch), the candidate lists are all-gathered (Q*B*4 bytes), every rank refines
+  for ALL queries the candidates its store shard holds, the per-shard top-k (distance, candidate rank, id) is all-gathered and merged
+  by `merge_topk_kernel` on (distance, rank).  Everything stays in HBM; the two all-gathers are NCCL over NVLink.
+* database-sharded, host-buffer form `ShardedSearcher` (also what the gloo CPU tests drive): the routing index is replicated, so
+  every rank derives the IDENTICAL ordered candidate list; the encrypted store is sharded by contiguous global-id range; each rank authenticates + decrypts + scores
   only the candidates it owns and emits its local top-k as (distance, candidate rank, id); ONE all-gather (NCCL over
   NVLink on GPUs, gloo in the CPU tests) of Q*k*(8+4+4) bytes per rank, then a k-way merge keyed on (distance, rank) --
   the rank reproduces the reference's stable sort tie order (QSI:298), so the merged result is bit-identical to a
@@ -96,3 +100,69 @@ class ShardedSearcher:
             retried[rows] = True
         return dict(top_ids=ids.cpu().numpy(), top_dist=dd.cpu().numpy(), n_ret=nret.cpu().numpy(), n_decrypted=nd.cpu().numpy(),
                     retried=retried.cpu().numpy(), unique=r["unique"], raw_seen=r["raw_seen"])
+
+
+class DeviceShardedSearcher:
+    """Database-sharded search with everything resident in HBM (BASELINE config 4).  `gpu` holds the replicated routing index and
+    this rank's store shard (store_upload(..., id_base=lo, n_global=N)).  Queries are a CUDA FP64 tensor [Q, dim] replicated on every
+    rank.  world_size 1 (no process group) degenerates to a single shard and is what the single-GPU tests exercise."""
+
+    def __init__(self, gpu, group=None):
+        self.gpu, self.group = gpu, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.dev = torch.device("cuda", gpu.device)
+        self.stream = torch.cuda.ExternalStream(gpu.stream(), device=self.dev)
+
+    def _all_gather(self, t: torch.Tensor) -> torch.Tensor:
+        """[...] -> [world, ...] (NCCL all-gather on the library's stream)."""
+        if self.world == 1:
+            return t[None]
+        out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
+        return out
+
+    def _pass(self, dq: torch.Tensor, k: int, probes: int, hard_cap: int, B: int):
+        Q = dq.shape[0]
+        g, W = self.gpu, self.world
+        per = (Q + W - 1) // W                                   # rows per rank (the last ranks may own fewer; padded for the gather)
+        lo, hi = min(Q, self.rank * per), min(Q, (self.rank + 1) * per)
+        i32 = dict(dtype=torch.int32, device=self.dev)
+        cand = torch.full((per, B), -1, **i32)
+        meta = torch.zeros((3, per), **i32)                      # n_cand, raw_seen, unique of my slice
+        if hi > lo:
+            g.route_batch_dev(hi - lo, dq[lo:hi].data_ptr(), probes, hard_cap, B, cand.data_ptr(), meta[0].data_ptr(), meta[1].data_ptr(), meta[2].data_ptr())
+        cand_all = self._all_gather(cand).reshape(W * per, B)[:Q]                 # every rank: the identical ordered candidate lists
+        meta_all = self._all_gather(meta).permute(1, 0, 2).reshape(3, W * per)[:, :Q].contiguous()
+        ids = torch.empty((Q, k), **i32)
+        rk = torch.empty((Q, k), **i32)
+        dd = torch.empty((Q, k), dtype=torch.float64, device=self.dev)
+        cnt = torch.empty((2, Q), **i32)                         # n_ret, n_decrypted on this shard
+        cand_all = cand_all.contiguous()
+        g.refine_batch_dev(Q, dq.data_ptr(), cand_all.data_ptr(), meta_all[0].data_ptr(), B, k, ids.data_ptr(), dd.data_ptr(), rk.data_ptr(),
+                           cnt[0].data_ptr(), cnt[1].data_ptr())
+        nd = cnt[1].to(torch.int64)
+        if W > 1:
+            dist.all_reduce(nd, group=self.group)
+        out_i = torch.empty((Q, k), **i32)
+        out_d = torch.empty((Q, k), dtype=torch.float64, device=self.dev)
+        out_n = torch.empty((Q,), **i32)
+        a_d, a_r, a_i = self._all_gather(dd), self._all_gather(rk), self._all_gather(ids)
+        g.merge_topk_dev(W, Q, k, a_d.data_ptr(), a_r.data_ptr(), a_i.data_ptr(), out_i.data_ptr(), out_d.data_ptr(), out_n.data_ptr())
+        return out_i, out_d, out_n, nd, meta_all
+
+    def search_batch_dev(self, dq: torch.Tensor, k: int, probes: int, hard_cap: int, B: int, allow_retry: bool = True):
+        """Returns device tensors dict(top_ids [Q,k], top_dist [Q,k], n_ret [Q], n_decrypted [Q], retried [Q], raw_seen, unique)."""
+        assert dq.is_cuda and dq.dtype == torch.float64 and dq.is_contiguous()
+        with torch.cuda.stream(self.stream):
+            ids, dd, nret, nd, meta = self._pass(dq, k, probes, hard_cap, B)
+            retried = torch.zeros_like(nret, dtype=torch.bool)
+            if allow_retry:
+                need = (nd > 0) & ((nret < k) | (nd < 10 * k))         # QSI:293, QSI:444-447; identical on every rank
+                rows = torch.nonzero(need).flatten()                   # (synchronises: the retry decision is made on the host side)
+                if rows.numel() > 0:
+                    ids2, dd2, nret2, nd2, meta2 = self._pass(dq[rows].contiguous(), k, 10, hard_cap, B)
+                    ids[rows], dd[rows], nret[rows], nd[rows] = ids2, dd2, nret2, nd2
+                    meta[:, rows] = meta2
+                    retried[rows] = True
+        return dict(top_ids=ids, top_dist=dd, n_ret=nret, n_decrypted=nd, retried=retried, raw_seen=meta[1], unique=meta[2])

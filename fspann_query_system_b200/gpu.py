@@ -222,6 +222,21 @@ class GpuContext:
                                               C.c_int32(result_ids.shape[1]), N.ptr(nr), N.ptr(out)))
         return out
 
+    # ---- device-resident building blocks of the database-sharded deployment (all arguments are device addresses)
+    def route_batch_dev(self, Q, d_queries, probes, hard_cap, B, d_cand_ids, d_n_cand, d_raw=None, d_unique=None):
+        self._ck(self.lib.fspann_route_batch_dev(self.ctx, C.c_int64(Q), C.c_void_p(d_queries), C.c_int32(probes), C.c_int64(hard_cap), C.c_int32(B),
+                                                 C.c_void_p(d_cand_ids), C.c_void_p(d_n_cand), C.c_void_p(d_raw) if d_raw else None,
+                                                 C.c_void_p(d_unique) if d_unique else None))
+
+    def refine_batch_dev(self, Q, d_queries, d_cand_ids, d_n_cand, stride, k, d_ids, d_dist, d_rank, d_nret, d_ndec=None):
+        self._ck(self.lib.fspann_refine_batch_dev(self.ctx, C.c_int64(Q), C.c_void_p(d_queries), C.c_void_p(d_cand_ids), C.c_void_p(d_n_cand),
+                                                  C.c_int32(stride), C.c_int32(k), C.c_void_p(d_ids), C.c_void_p(d_dist),
+                                                  C.c_void_p(d_rank) if d_rank else None, C.c_void_p(d_nret), C.c_void_p(d_ndec) if d_ndec else None))
+
+    def merge_topk_dev(self, S, Q, k, d_dist, d_rank, d_ids, d_out_ids, d_out_dist, d_out_nret):
+        self._ck(self.lib.fspann_merge_topk_dev(self.ctx, C.c_int32(S), C.c_int64(Q), C.c_int32(k), C.c_void_p(d_dist), C.c_void_p(d_rank),
+                                                C.c_void_p(d_ids), C.c_void_p(d_out_ids), C.c_void_p(d_out_dist), C.c_void_p(d_out_nret)))
+
     def touched(self, clear: bool = False) -> np.ndarray:
         words = (self.N + 31) // 32
         bm = np.zeros(words, dtype=np.uint32)

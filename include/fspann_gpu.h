@@ -212,6 +212,22 @@ int fspann_groundtruth(fspann_ctx *ctx, int64_t N, int32_t dim, const float *bas
 int fspann_recall_batch(fspann_ctx *ctx, int64_t Q, int32_t K, const int32_t *gt_ids, int32_t gt_stride, const int32_t *result_ids,
                         int32_t result_stride, const int32_t *n_ret, double *recall_out);
 
+/* ---- database-sharded deployment (BASELINE config 4), device-resident building blocks; all pointers are DEVICE pointers and
+ * the work is enqueued on the context stream without synchronising ------------------------------------------------------------
+ * Route is query-parallel on the replicated routing index (each GPU routes its slice of the batch), Refine is data-parallel on
+ * the sharded store (each GPU refines, for all queries, the candidates it holds), connected by two all-gathers (NCCL):
+ *   fspann_route_batch_dev   = createToken's coding + lookupCandidatesWithScores + first-B cut (QTF:98-131, PIS:592-715, QSI:153-214)
+ *   fspann_refine_batch_dev  = QSI:238-322 on this shard; d_topk_rank [Q][k] = position of each result in its candidate list
+ *   fspann_merge_topk_dev    = the global stable top-k (QSI:298-316) from n_shards per-shard lists laid out [n_shards][Q][k]
+ *                              (id = -1 pads), ordered by (distance, candidate rank). */
+int fspann_route_batch_dev(fspann_ctx *ctx, int64_t Q, const double *d_queries, int32_t probes, int64_t hard_cap, int32_t B,
+                           int32_t *d_cand_ids, int32_t *d_n_cand, int32_t *d_raw_seen, int32_t *d_unique);
+int fspann_refine_batch_dev(fspann_ctx *ctx, int64_t Q, const double *d_queries, const int32_t *d_cand_ids, const int32_t *d_n_cand,
+                            int32_t cand_stride, int32_t k, int32_t *d_topk_ids, double *d_topk_dist, int32_t *d_topk_rank,
+                            int32_t *d_n_ret, int32_t *d_n_decrypted);
+int fspann_merge_topk_dev(fspann_ctx *ctx, int32_t n_shards, int64_t Q, int32_t k, const double *d_dist, const int32_t *d_rank,
+                          const int32_t *d_ids, int32_t *d_out_ids, double *d_out_dist, int32_t *d_out_n_ret);
+
 /* Touched set (QSI:262, QSI:348-350 reencTracker.record): bitmap over ids (bit id&31 of word id>>5, N bits) of
  * every record that reached verdict OK since the last clear.  Feeds the host's selective re-encryption. */
 int fspann_touched_fetch(fspann_ctx *ctx, uint32_t *bitmap_out, int64_t n_words, int32_t clear);

@@ -170,3 +170,70 @@ def test_sharded_store_on_gpu_matches_single_store(world_factory):
     finally:
         for c, _, _ in shards:
             c.close()
+
+
+@pytest.mark.gpu
+def test_device_resident_sharded_blocks_and_merge_kernel(world_factory):
+    """Device-resident config-4 building blocks on one GPU: route_batch_dev + refine_batch_dev on two store shards (two contexts) +
+    merge_topk_kernel == unsharded search == oracle, incl. retried queries; DeviceShardedSearcher with a world of one."""
+    from fspann_query_system_b200.gpu import GpuContext
+    w = world_factory(N=3000, dim=32, Q=40, T=3, D=4, m=12, lam=2, n_versions=3)
+    g, ix = w.g, w.ix
+    dev = torch.device("cuda", 0)
+    shards = []
+    for r in range(2):
+        lo, hi = DD.shard_range(w.cfg.N, r, 2)
+        c = GpuContext(0)
+        c.routing_upload(g.dim, g.T, g.D, g.m, g.lam, g.alpha, g.r, g.omega, ix.min_key, ix.max_key, ix.rep, ix.ids)
+        for v, key in w.store.keys.items():
+            c.keys_set(v, key)
+        c.store_upload(g.dim, w.iv[lo:hi], w.ct[lo:hi], w.key_version[lo:hi], id_base=lo, n_global=w.cfg.N)
+        shards.append(c)
+    full = w.gpu_context()
+    try:
+        Q, k, B = w.queries.shape[0], 10, 128
+        dq = torch.from_numpy(w.queries).to(dev)
+        i32 = dict(dtype=torch.int32, device=dev)
+        cand = torch.full((Q, B), -1, **i32); ncand = torch.zeros(Q, **i32)
+        shards[0].route_batch_dev(Q, dq.data_ptr(), 5, 20000, B, cand.data_ptr(), ncand.data_ptr())
+        shards[0].sync()
+        codes = O.tokengen_batch(w.queries, w.g)
+        for q in range(Q):
+            rids = O.route(w.ix, codes[q], 5, 20000)[0]
+            n = min(B, len(rids))
+            assert int(ncand[q]) == n and np.array_equal(cand[q, :n].cpu().numpy(), rids[:n])
+        ids = torch.empty((2, Q, k), **i32); rk = torch.empty((2, Q, k), **i32)
+        dd = torch.empty((2, Q, k), dtype=torch.float64, device=dev)
+        nret = torch.empty((2, Q), **i32); ndec = torch.empty((2, Q), **i32)
+        for s, c in enumerate(shards):
+            c.refine_batch_dev(Q, dq.data_ptr(), cand.data_ptr(), ncand.data_ptr(), B, k, ids[s].data_ptr(), dd[s].data_ptr(), rk[s].data_ptr(),
+                               nret[s].data_ptr(), ndec[s].data_ptr())
+            c.sync()
+        out_i = torch.empty((Q, k), **i32); out_d = torch.empty((Q, k), dtype=torch.float64, device=dev); out_n = torch.empty(Q, **i32)
+        shards[0].merge_topk_dev(2, Q, k, dd.data_ptr(), rk.data_ptr(), ids.data_ptr(), out_i.data_ptr(), out_d.data_ptr(), out_n.data_ptr())
+        shards[0].sync()
+        for q in range(Q):
+            ref = O.search(w.ix, w.store, w.queries[q], codes[q], k, 5, 20000, B)
+            assert np.array_equal(out_i[q].cpu().numpy(), ref["top_ids"]) and int(out_n[q]) == len(ref["top_ids"])
+            assert np.array_equal(out_d[q].cpu().numpy().view(np.uint64), ref["top_dist"].view(np.uint64))
+            assert int(ndec[0, q] + ndec[1, q]) == ref["cand_decrypted"]
+        # a world of one over the unsharded store, with the adaptive retry (k=100, B=256 forces decrypted < 10*K)
+        s1 = DD.DeviceShardedSearcher(full)
+        for kk, BB in [(10, 64), (100, 256)]:
+            got = s1.search_batch_dev(dq, kk, 5, 20000, BB)
+            torch.cuda.synchronize()
+            n_retried = 0
+            for q in range(Q):
+                ref = O.search(w.ix, w.store, w.queries[q], codes[q], kk, 5, 20000, BB)
+                n = len(ref["top_ids"])
+                assert int(got["n_ret"][q]) == n and np.array_equal(got["top_ids"][q, :n].cpu().numpy(), ref["top_ids"])
+                assert np.array_equal(got["top_dist"][q, :n].cpu().numpy().view(np.uint64), ref["top_dist"].view(np.uint64))
+                assert bool(got["retried"][q]) == ref["retried"] and int(got["n_decrypted"][q]) == ref["cand_decrypted"]
+                assert (int(got["raw_seen"][q]), int(got["unique"][q])) == (ref["cand_total"], ref["cand_kept"])
+                n_retried += ref["retried"]
+            if kk == 100:
+                assert n_retried > 0
+    finally:
+        for c in shards:
+            c.close()
+        full.close()
