@@ -57,40 +57,66 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed regions: NVML from a thread every 2 ms (the timed regions last tens of
+    milliseconds, too short for `nvidia-smi -lms`); falls back to one nvidia-smi query if NVML is unavailable."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index: int):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.gpu, self.sm, self.mask, self.max_mhz, self.stop_flag, self.t, self.h = gpu_index, [], 0, None, False, None, None
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may renumber devices: match by PCI bus id of the torch device
+            import torch
+            bus = torch.cuda.get_device_properties(gpu_index).pci_bus_id if hasattr(torch.cuda.get_device_properties(gpu_index), "pci_bus_id") else None
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            if bus is not None:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    hh = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    if int(pynvml.nvmlDeviceGetPciInfo(hh).bus) == int(bus):
+                        self.h = hh
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv, self.h = None, None
+
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    self.mask |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
-        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+        if self.h is not None:
+            self.stop_flag = False
+            self.t = threading.Thread(target=self._loop, daemon=True)
             self.t.start()
-        except Exception:
-            self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+    def pause(self):
+        if self.t is not None:
+            self.stop_flag = True
+            self.t.join()
+            self.t = None
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+        self.pause()
+        if self.h is None:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=10).stdout.strip().split(",")
+                return {"sm_mhz": float(out[0]), "sm_max_mhz": float(out[1]), "reasons": ["sampled once after the run (NVML unavailable)"], "samples": 1}
+            except Exception:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi / NVML unavailable"], "samples": 0}
+        reasons = [n for bit, n in self.REASONS.items() if self.mask & bit]
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(self.sm)}
 
 
 def build_world(cfg: WL.Config, gpu, n_batches: int, rank: int):
@@ -276,7 +302,7 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     launches = gpu.launch_count() - l0
-    clocks = sampler.stop()
+    sampler.pause()
 
     # ---- roofline of the dominant kernel (refine decrypt+distance), measured live with CUDA events on the launching stream
     stage = dict(tokengen=0.0, route=0.0, group=0.0, verify=0.0, decrypt=0.0, topk=0.0)
@@ -306,6 +332,7 @@ def main():
         step_host(i)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.start()
     t_wall = time.perf_counter()
     f0.record(stream)
     for i in range(K):
@@ -314,6 +341,7 @@ def main():
     barrier()
     e2e_ms = max(f0.elapsed_time(f1), (time.perf_counter() - t_wall) * 1e3 * 0.0)
     e2e_wall_ms = (time.perf_counter() - t_wall) * 1e3
+    clocks = sampler.stop()
     checksum = int(h_ids.to(torch.int64).sum().item())
 
     # ---- recall@10 of what was just timed: exact ground truth and recall on the device, outside the timed region
