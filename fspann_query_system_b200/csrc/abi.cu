@@ -32,7 +32,9 @@ struct fspann_ctx {
     // routing state
     bool routing_ready = false;
     RoutingView rv{};
-    DevBuf d_alpha, d_r, d_omega, d_keys, d_rep, d_ids, d_deleted;
+    DevBuf d_alpha, d_r, d_omega, d_keys, d_rep, d_ids, d_deleted, d_alpha_f, d_alpha_norm, s_tg_work, s_tg_list;
+    int opt_tokengen_exact = 0;  // run the exact FP64 TokenGen kernel alone (no FP32 pre-filter)
+    int64_t opt_tg_list_cap = 0; // test hook: clamp the re-check list (forces the overflow -> exact-kernel fallback)
 
     // store
     bool store_ready = false;
@@ -174,6 +176,17 @@ int record_ev(fspann_ctx *ctx, int i) {
     return 0;
 }
 
+// TokenGen for Q device-resident queries: FP32 pre-filter + exact re-check (or the exact kernel alone), see tokengen.cu.
+int run_tokengen(fspann_ctx *ctx, int64_t Q, const double *d_queries, uint64_t *d_codes) {
+    int64_t cap = tokengen_list_capacity(ctx->rv, Q);
+    if (ctx->opt_tg_list_cap > 0) cap = std::min(cap, ctx->opt_tg_list_cap);
+    ENSURE(ctx->s_tg_work, 4 * sizeof(int32_t));
+    ENSURE(ctx->s_tg_list, sizeof(unsigned long long) * (size_t)cap);
+    LAUNCHED(launch_tokengen(ctx->stream, ctx->rv, Q, d_queries, d_codes, (int32_t *)ctx->s_tg_work.p, (unsigned long long *)ctx->s_tg_list.p, cap,
+                             ctx->opt_tokengen_exact != 0));
+    return 0;
+}
+
 // Route for Q queries whose codes are on the device.
 int do_route(fspann_ctx *ctx, int64_t Q, const uint64_t *d_codes, int probes, int64_t hard_cap, int B, int32_t *d_cand_ids,
              int32_t *d_cand_sc, int32_t *d_ncand, int32_t *d_raw, int32_t *d_uniq) {
@@ -293,7 +306,7 @@ void fspann_ctx_destroy(fspann_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    DevBuf *bufs[] = {&ctx->d_alpha, &ctx->d_r, &ctx->d_omega, &ctx->d_keys, &ctx->d_rep, &ctx->d_ids, &ctx->d_deleted, &ctx->d_rec,
+    DevBuf *bufs[] = {&ctx->d_alpha_f, &ctx->d_alpha_norm, &ctx->s_tg_work, &ctx->s_tg_list, &ctx->d_alpha, &ctx->d_r, &ctx->d_omega, &ctx->d_keys, &ctx->d_rep, &ctx->d_ids, &ctx->d_deleted, &ctx->d_rec,
                       &ctx->d_keyring, &ctx->d_hpow, &ctx->d_shoup, &ctx->s_rec_verdict, &ctx->s_qf32, &ctx->s_qu8, &ctx->s_f32_exact, &ctx->d_te0, &ctx->d_touched, &ctx->s_queries, &ctx->s_codes, &ctx->s_cand_ids,
                       &ctx->s_cand_sc, &ctx->s_ncand, &ctx->s_raw, &ctx->s_uniq_cnt, &ctx->s_route_scratch, &ctx->s_overflow, &ctx->s_cnt,
                       &ctx->s_flag, &ctx->s_fill, &ctx->s_uniq, &ctx->s_pairs, &ctx->s_bsums, &ctx->s_totals, &ctx->s_dist, &ctx->s_verdict,
@@ -322,6 +335,8 @@ int fspann_set_option(fspann_ctx *ctx, const char *name, int64_t value) {
     if (!ctx || !name) return FSPANN_E_ARG;
     if (!strcmp(name, "route_general")) { ctx->opt_route_general = value != 0; return FSPANN_OK; }
     if (!strcmp(name, "route_wl_extra")) { ctx->opt_route_wl_extra = (int)value; return FSPANN_OK; }
+    if (!strcmp(name, "tokengen_exact")) { ctx->opt_tokengen_exact = value != 0; return FSPANN_OK; }
+    if (!strcmp(name, "tokengen_list_cap")) { ctx->opt_tg_list_cap = value; return FSPANN_OK; }
     return fail(ctx, FSPANN_E_ARG, "unknown option %s", name);
 }
 int64_t fspann_get_info(fspann_ctx *ctx, const char *name) {
@@ -329,6 +344,12 @@ int64_t fspann_get_info(fspann_ctx *ctx, const char *name) {
     if (!strcmp(name, "last_route_path")) return ctx->last_route_path;
     if (!strcmp(name, "sm_count")) return ctx->sm_count;
     if (!strcmp(name, "build_treeified")) return ctx->last_build_treeified;
+    if (!strcmp(name, "tokengen_rechecked") || !strcmp(name, "tokengen_overflow")) {   // of the last TokenGen launch on this context
+        int32_t w[2] = {0, 0};
+        if (!ctx->s_tg_work.p || cudaSetDevice(ctx->device) != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess ||
+            cudaMemcpy(w, ctx->s_tg_work.p, sizeof w, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+        return !strcmp(name, "tokengen_rechecked") ? w[0] : w[1];
+    }
     return -1;
 }
 
@@ -357,6 +378,10 @@ int fspann_routing_upload(fspann_ctx *ctx, int32_t dim, int32_t T, int32_t D, in
     std::vector<int64_t> inter(2 * (size_t)TD * P);
     for (size_t i = 0; i < (size_t)TD * P; i++) { inter[2 * i] = min_key[i]; inter[2 * i + 1] = max_key[i]; }
     CK(cudaMemcpy(ctx->d_alpha.p, alpha, sizeof(double) * (size_t)TD * m * dim, cudaMemcpyHostToDevice));
+    ENSURE(ctx->d_alpha_f, sizeof(float) * (size_t)TD * m * dim);
+    ENSURE(ctx->d_alpha_norm, sizeof(float) * (size_t)TD * m);
+    LAUNCHED(launch_alpha_prepare(ctx->stream, (const double *)ctx->d_alpha.p, (int64_t)TD * m, dim, (float *)ctx->d_alpha_f.p, (float *)ctx->d_alpha_norm.p));
+    CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaMemcpy(ctx->d_r.p, r, sizeof(double) * (size_t)TD * m, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->d_omega.p, omega, sizeof(double) * (size_t)TD * m, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->d_keys.p, inter.data(), sizeof(int64_t) * inter.size(), cudaMemcpyHostToDevice));
@@ -365,6 +390,7 @@ int fspann_routing_upload(fspann_ctx *ctx, int32_t dim, int32_t T, int32_t D, in
     RoutingView &rv = ctx->rv;
     rv.dim = dim; rv.T = T; rv.D = D; rv.m = m; rv.lambda = lambda; rv.W = W; rv.TD = TD; rv.n_ids = n_ids; rv.P = P;
     rv.alpha = (const double *)ctx->d_alpha.p; rv.r = (const double *)ctx->d_r.p; rv.omega = (const double *)ctx->d_omega.p;
+    rv.alpha_f32 = (const float *)ctx->d_alpha_f.p; rv.alpha_norm = (const float *)ctx->d_alpha_norm.p;
     rv.keys = (const int64_t *)ctx->d_keys.p; rv.rep = (const uint64_t *)ctx->d_rep.p; rv.ids = (const int32_t *)ctx->d_ids.p;
     ctx->routing_ready = true;
     return FSPANN_OK;
@@ -412,7 +438,7 @@ int fspann_routing_build(fspann_ctx *ctx, int64_t N, const double *vectors, cons
     for (int64_t s0 = 0; s0 < N; s0 += chunk) {
         const int64_t c = std::min(chunk, N - s0);
         CK(cudaMemcpyAsync(ctx->s_queries.p, vectors + (size_t)s0 * dim, sizeof(double) * (size_t)c * dim, cudaMemcpyHostToDevice, ctx->stream));
-        LAUNCHED(launch_tokengen(ctx->stream, rv, c, (const double *)ctx->s_queries.p, (uint64_t *)ctx->b_codes.p + (size_t)s0 * TD * W));
+        { int rc_ = run_tokengen(ctx, c, (const double *)ctx->s_queries.p, (uint64_t *)ctx->b_codes.p + (size_t)s0 * TD * W); if (rc_) return rc_; }
         CK(cudaStreamSynchronize(ctx->stream));
     }
     // 2. partitions: HashMap iteration order -> stable sort by key -> blocks of 64
@@ -749,7 +775,7 @@ int fspann_tokengen_batch(fspann_ctx *ctx, int64_t Q, const double *queries, uin
     ENSURE(ctx->s_queries, sizeof(double) * (size_t)Q * rv.dim);
     ENSURE(ctx->s_codes, cb);
     CK(cudaMemcpyAsync(ctx->s_queries.p, queries, sizeof(double) * (size_t)Q * rv.dim, cudaMemcpyHostToDevice, ctx->stream));
-    LAUNCHED(launch_tokengen(ctx->stream, rv, Q, (const double *)ctx->s_queries.p, (uint64_t *)ctx->s_codes.p));
+    { int rc_ = run_tokengen(ctx, Q, (const double *)ctx->s_queries.p, (uint64_t *)ctx->s_codes.p); if (rc_) return rc_; }
     CK(cudaMemcpyAsync(codes_out, ctx->s_codes.p, cb, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return FSPANN_OK;
@@ -847,7 +873,7 @@ static int search_pass(fspann_ctx *ctx, int64_t Q, const double *d_queries, int 
     ENSURE(b_nd, sizeof(int32_t) * (size_t)Q);
     int rc;
     if (main_pass) { rc = record_ev(ctx, 0); if (rc) return rc; }
-    LAUNCHED(launch_tokengen(ctx->stream, rv, Q, d_queries, (uint64_t *)b_codes.p));
+    { int rc_ = run_tokengen(ctx, Q, d_queries, (uint64_t *)b_codes.p); if (rc_) return rc_; }
     if (main_pass) { rc = record_ev(ctx, 1); if (rc) return rc; }
     rc = do_route(ctx, Q, (const uint64_t *)b_codes.p, probes, hard_cap, B, (int32_t *)b_cid.p, (int32_t *)b_csc.p, (int32_t *)b_nc.p,
                   (int32_t *)b_raw.p, (int32_t *)b_un.p);
@@ -963,7 +989,7 @@ int fspann_route_batch_dev(fspann_ctx *ctx, int64_t Q, const double *d_queries, 
     ENSURE(ctx->s_codes, sizeof(uint64_t) * (size_t)Q * rv.TD * rv.W);
     ENSURE(ctx->s_cand_sc, sizeof(int32_t) * (size_t)Q * B);
     ENSURE(ctx->s_raw, sizeof(int32_t) * (size_t)Q); ENSURE(ctx->s_uniq_cnt, sizeof(int32_t) * (size_t)Q);
-    LAUNCHED(launch_tokengen(ctx->stream, rv, Q, d_queries, (uint64_t *)ctx->s_codes.p));
+    { int rc_ = run_tokengen(ctx, Q, d_queries, (uint64_t *)ctx->s_codes.p); if (rc_) return rc_; }
     return do_route(ctx, Q, (const uint64_t *)ctx->s_codes.p, probes, hard_cap, B, d_cand_ids, (int32_t *)ctx->s_cand_sc.p, d_n_cand,
                     d_raw_seen ? d_raw_seen : (int32_t *)ctx->s_raw.p, d_unique ? d_unique : (int32_t *)ctx->s_uniq_cnt.p);
 }

@@ -25,6 +25,8 @@ struct RoutingView {
     int32_t dim, T, D, m, lambda, W, TD;
     int64_t n_ids, P;
     const double *alpha, *r, *omega;  // [TD][m][dim], [TD][m], [TD][m]
+    const float *alpha_f32;           // [TD][m][dim] alpha rounded to FP32 (TokenGen pre-filter)
+    const float *alpha_norm;          // [TD][m] upper bounds of ||alpha_j||_2
     const int64_t *keys;              // [TD][P][2] interleaved (minKey, maxKey)
     const uint64_t *rep;              // [TD][P][W]
     const int32_t *ids;               // [TD][n_ids]
@@ -106,7 +108,10 @@ struct RefineParams {
 };
 
 // launchers (each returns the number of kernels it launched, or -1 after setting a CUDA error)
-int launch_tokengen(cudaStream_t s, const RoutingView &rv, int64_t Q, const double *queries, uint64_t *codes);
+int launch_tokengen(cudaStream_t s, const RoutingView &rv, int64_t Q, const double *queries, uint64_t *codes, int32_t *work,
+                    unsigned long long *list, int64_t list_cap, bool exact_only);
+int64_t tokengen_list_capacity(const RoutingView &rv, int64_t Q);
+int launch_alpha_prepare(cudaStream_t s, const double *alpha, int64_t rows, int dim, float *alpha_f, float *norm);
 int launch_route(cudaStream_t s, const RoutingView &rv, const RouteParams &p, int grid);
 int route_grid(int64_t Q, int sm_count);
 bool route_fast_eligible(const RoutingView &rv, int probes, int64_t hard_cap, int B, RouteFastExtra &x, size_t &smem);

@@ -56,8 +56,10 @@ __device__ __forceinline__ void tg_dot_block(const double *qa, const double *qb,
 }
 
 __global__ void __launch_bounds__(TG_THREADS, 2) tokengen_kernel(RoutingView rv, int64_t Q, const double *__restrict__ queries,
-                                                                 uint64_t *__restrict__ codes, int groups_per_cta, int qstride, int astride) {
+                                                                 uint64_t *__restrict__ codes, int groups_per_cta, int qstride, int astride,
+                                                                 const int32_t *__restrict__ run_if) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (run_if && *run_if == 0) return;                           // fallback launch behind the FP32 pre-filter: only after a worklist overflow
     const int dim = rv.dim, m = rv.m, W = rv.W, lambda = rv.lambda;
     double *qs = reinterpret_cast<double *>(smem_raw);             // [TG_QT][qstride]
     double *as = qs + (size_t)TG_QT * qstride;                     // [m][astride] alpha tile of the current group
@@ -134,8 +136,185 @@ __global__ void __launch_bounds__(TG_THREADS, 2) tokengen_kernel(RoutingView rv,
     }
 }
 
-int launch_tokengen(cudaStream_t s, const RoutingView &rv, int64_t Q, const double *queries, uint64_t *codes) {
-    if (Q <= 0) return 0;
+// =====================================================================================================================
+// FP32 pre-filter + exact re-check.  h_j = floor((y + r_j) / omega_j) only needs y = v . alpha_j to within the distance of
+// (y + r_j) / omega_j from the nearest integer, and omega_j is a sizeable fraction of the data's projection range
+// (Coding:224-237), so a single-precision dot product with a PROVEN error bound decides almost every h_j; the few that fall
+// inside the bound of a quantisation boundary are listed and recomputed with the exact sequential FP64 arithmetic above.
+//   |fl32(sum) - y_java| <= E(v, j) = C(dim) * ||v||_2 * ||alpha_j||_2,   C = 4 * ((dim + 2) * 2^-24 * 1.01 + 2^-22)
+//   (inputs rounded to FP32: 2 * 2^-24 per product; dim sequential FMAs: gamma_dim; Java's own FP64 rounding is < 2^-45; x4 safety)
+// decided  <=>  t = ((double)sum + r_j) / omega_j is farther than E / omega_j + 1e-9 * (1 + |t|) from both neighbouring integers
+//              and |t| < 2^30 (no saturation of Java's (int) cast).
+// Codes are bit-identical to the exact kernel by construction; tests/ compare the two paths over the full 1M-vector base set.
+// =====================================================================================================================
+constexpr int TF_QT = 128;       // queries per CTA: 2 halves of 64, a thread owns 2 queries (lane, lane + 32) of one half
+constexpr int TF_THREADS = 128;  // 4 warps = 2 query halves x 2 projection slices
+constexpr int TF_JB = 12;        // projections per thread (slice = ceil(m / 2) <= 12, i.e. m <= 24; larger m runs the exact kernel)
+
+__global__ void alpha_prepare_kernel(const double *__restrict__ alpha, int64_t rows, int dim, float *__restrict__ alpha_f, float *__restrict__ norm) {
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    double s = 0.0;
+    for (int i = 0; i < dim; i++) { const double a = alpha[r * dim + i]; alpha_f[r * dim + i] = (float)a; s += a * a; }
+    norm[r] = __double2float_ru(sqrt(s) * 1.000001);
+}
+int launch_alpha_prepare(cudaStream_t s, const double *alpha, int64_t rows, int dim, float *alpha_f, float *norm) {
+    if (rows <= 0) return 0;
+    alpha_prepare_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, s>>>(alpha, rows, dim, alpha_f, norm);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+template <int NJ>
+__device__ __forceinline__ void tf_dot_block(const float *qa, const float *qb, const float *as, int astride, int n4, int jb, float accA[TF_JB], float accB[TF_JB]) {
+#pragma unroll
+    for (int u = 0; u < NJ; u++) { accA[u] = 0.f; accB[u] = 0.f; }
+    const float4 *qa4 = reinterpret_cast<const float4 *>(qa), *qb4 = reinterpret_cast<const float4 *>(qb);
+    const float4 *a4 = reinterpret_cast<const float4 *>(as + (size_t)jb * astride);
+    const int as4 = astride >> 2;
+#pragma unroll 2
+    for (int i4 = 0; i4 < n4; i4++) {
+        const float4 va = qa4[i4], vb = qb4[i4];
+#pragma unroll
+        for (int u = 0; u < NJ; u++) {
+            const float4 al = a4[u * as4 + i4];
+            accA[u] = fmaf(va.x, al.x, accA[u]); accB[u] = fmaf(vb.x, al.x, accB[u]);
+            accA[u] = fmaf(va.y, al.y, accA[u]); accB[u] = fmaf(vb.y, al.y, accB[u]);
+            accA[u] = fmaf(va.z, al.z, accA[u]); accB[u] = fmaf(vb.z, al.z, accB[u]);
+            accA[u] = fmaf(va.w, al.w, accA[u]); accB[u] = fmaf(vb.w, al.w, accB[u]);
+        }
+    }
+}
+
+// work[0] = number of listed (q, g, j); work[1] = overflow flag; list entries = q << 24 | g << 8 | j  (g < 65536, j < 256)
+__global__ void __launch_bounds__(TF_THREADS, 2) tokengen_fast_kernel(RoutingView rv, int64_t Q, const double *__restrict__ queries,
+                                                                      uint64_t *__restrict__ codes, int groups_per_cta, int qstride, int astride,
+                                                                      float cbound, int32_t *__restrict__ work, unsigned long long *__restrict__ list,
+                                                                      int64_t list_cap) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int dim = rv.dim, m = rv.m, W = rv.W, lambda = rv.lambda;
+    float *qs = reinterpret_cast<float *>(smem_raw);               // [TF_QT][qstride] (rows zero-padded to a multiple of 4)
+    float *as = qs + (size_t)TF_QT * qstride;                      // [m][astride]
+    double *rs = reinterpret_cast<double *>(as + (size_t)m * astride);   // [m] r
+    double *os = rs + m;                                           // [m] omega
+    float *na = reinterpret_cast<float *>(os + m);                 // [m] ||alpha_j||
+    float *nv = na + ((m + 3) & ~3);                               // [TF_QT] ||v||
+    uint32_t *cs = reinterpret_cast<uint32_t *>(nv + TF_QT);       // [TF_QT][2*W] code words being assembled
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t q0 = (int64_t)blockIdx.x * TF_QT;
+    const int nq = (int)min((int64_t)TF_QT, Q - q0);
+    const int n4 = (dim + 3) >> 2;
+
+    // stage the query tile as FP32 (coalesced over the row-major FP64 input); one warp per row computes the row norm
+    for (int r = warp; r < TF_QT; r += TF_THREADS / 32) {
+        float ss = 0.f;
+        for (int i = lane; i < 4 * n4; i += 32) {
+            const float v = (r < nq && i < dim) ? (float)queries[(q0 + r) * dim + i] : 0.f;
+            qs[(size_t)r * qstride + i] = v;
+            ss = fmaf(v, v, ss);
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        if (lane == 0) nv[r] = __fmul_ru(__fsqrt_ru(ss), 1.0001f);
+    }
+
+    const int half = warp & 1, slice = warp >> 1;
+    const int jper = (m + 1) / 2;
+    const int j_lo = slice * jper, j_hi = min(m, j_lo + jper);
+    const int g_lo = blockIdx.y * groups_per_cta, g_hi = min(rv.TD, g_lo + groups_per_cta);
+    const int ra = half * 64 + lane, rb = ra + 32;
+    const float *qa = qs + (size_t)ra * qstride, *qb = qs + (size_t)rb * qstride;
+
+    for (int g = g_lo; g < g_hi; g++) {
+        __syncthreads();  // previous group's tile / code words fully consumed; query tile staged
+        const float *ag = rv.alpha_f32 + (size_t)g * m * dim;
+        for (int idx = tid; idx < m * 4 * n4; idx += TF_THREADS) { const int j = idx / (4 * n4), i = idx - j * 4 * n4; as[(size_t)j * astride + i] = i < dim ? ag[(size_t)j * dim + i] : 0.f; }
+        for (int idx = tid; idx < m; idx += TF_THREADS) { rs[idx] = rv.r[(size_t)g * m + idx]; os[idx] = rv.omega[(size_t)g * m + idx]; na[idx] = rv.alpha_norm[(size_t)g * m + idx]; }
+        for (int idx = tid; idx < TF_QT * 2 * W; idx += TF_THREADS) cs[idx] = 0u;
+        __syncthreads();
+
+        float accA[TF_JB], accB[TF_JB];
+        const int nj = j_hi - j_lo;
+        switch (nj) {
+            case 12: tf_dot_block<12>(qa, qb, as, astride, n4, j_lo, accA, accB); break;
+            case 11: tf_dot_block<11>(qa, qb, as, astride, n4, j_lo, accA, accB); break;
+            case 10: tf_dot_block<10>(qa, qb, as, astride, n4, j_lo, accA, accB); break;
+            case 9: tf_dot_block<9>(qa, qb, as, astride, n4, j_lo, accA, accB); break;
+            case 8: tf_dot_block<8>(qa, qb, as, astride, n4, j_lo, accA, accB); break;
+            case 7: tf_dot_block<7>(qa, qb, as, astride, n4, j_lo, accA, accB); break;
+            case 6: tf_dot_block<6>(qa, qb, as, astride, n4, j_lo, accA, accB); break;
+            case 5: tf_dot_block<5>(qa, qb, as, astride, n4, j_lo, accA, accB); break;
+            case 4: tf_dot_block<4>(qa, qb, as, astride, n4, j_lo, accA, accB); break;
+            case 3: tf_dot_block<3>(qa, qb, as, astride, n4, j_lo, accA, accB); break;
+            case 2: tf_dot_block<2>(qa, qb, as, astride, n4, j_lo, accA, accB); break;
+            case 1: tf_dot_block<1>(qa, qb, as, astride, n4, j_lo, accA, accB); break;
+            default: break;
+        }
+#pragma unroll
+        for (int u = 0; u < TF_JB; u++) {
+            if (u < nj) {
+                const int j = j_lo + u;
+#pragma unroll
+                for (int hb = 0; hb < 2; hb++) {
+                    const int qi = hb ? rb : ra;
+                    if (qi >= nq) continue;
+                    const float acc = hb ? accB[u] : accA[u];
+                    const double om = os[j];
+                    const double t = __ddiv_rn(__dadd_rn((double)acc, rs[j]), om);
+                    const double f = floor(t);
+                    const double slack = (double)(cbound * nv[qi] * na[j]) / om + 1e-9 * (1.0 + fabs(t));
+                    const bool decided = (t - f > slack) && (f + 1.0 - t > slack) && fabs(t) < 1073741824.0;   // also false for NaN / Inf
+                    if (decided) {
+                        const uint32_t hj = (uint32_t)__double2int_rz(f) ^ 0x80000000u;             // Coding:293
+                        for (int ib = 0; ib < lambda; ib++) {
+                            if (ib < 32 && ((hj >> ib) & 1u)) {
+                                const int pos = (lambda - 1 - ib) * m + j;                        // MSB-first bit planes (Coding:291-299)
+                                atomicOr(&cs[(size_t)qi * 2 * W + (pos >> 5)], 1u << (pos & 31));
+                            }
+                        }
+                    } else {
+                        const int at = atomicAdd(&work[0], 1);
+                        if (at < list_cap) list[at] = ((unsigned long long)(q0 + qi) << 24) | ((unsigned long long)g << 8) | (unsigned long long)j;
+                        else work[1] = 1;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        for (int idx = tid; idx < nq * W; idx += TF_THREADS) {
+            const int qq = idx / W, w = idx - qq * W;
+            const uint64_t lo = cs[(size_t)qq * 2 * W + 2 * w], hi = cs[(size_t)qq * 2 * W + 2 * w + 1];
+            codes[((q0 + qq) * rv.TD + g) * W + w] = lo | (hi << 32);
+        }
+    }
+}
+
+// Exact sequential FP64 value of every listed projection (Coding:250-258, 349-353), OR-ed into the code words.
+__global__ void tokengen_recheck_kernel(RoutingView rv, const double *__restrict__ queries, uint64_t *__restrict__ codes, const int32_t *__restrict__ work,
+                                        const unsigned long long *__restrict__ list, int64_t list_cap) {
+    if (work[1]) return;                                            // overflow: the exact kernel recomputes the whole batch
+    const int64_t n = min((int64_t)work[0], list_cap);
+    const int dim = rv.dim, m = rv.m, W = rv.W, lambda = rv.lambda;
+    for (int64_t it = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; it < n; it += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long e = list[it];
+        const int64_t q = (int64_t)(e >> 24);
+        const int g = (int)((e >> 8) & 0xffffu), j = (int)(e & 0xffu);
+        const double *v = queries + q * dim, *al = rv.alpha + ((size_t)g * m + j) * dim;
+        double acc = 0.0;
+        for (int i = 0; i < dim; i++) acc = __dadd_rn(acc, __dmul_rn(v[i], al[i]));
+        const double y = __dadd_rn(acc, rv.r[(size_t)g * m + j]);
+        const double f = floor(__ddiv_rn(y, rv.omega[(size_t)g * m + j]));
+        const uint32_t hj = (uint32_t)__double2int_rz(f) ^ 0x80000000u;
+        for (int ib = 0; ib < lambda; ib++) {
+            if (ib < 32 && ((hj >> ib) & 1u)) {
+                const int pos = (lambda - 1 - ib) * m + j;
+                atomicOr(reinterpret_cast<unsigned long long *>(codes + (q * rv.TD + g) * W + (pos >> 6)), 1ull << (pos & 63));
+            }
+        }
+    }
+}
+
+static int launch_tokengen_exact(cudaStream_t s, const RoutingView &rv, int64_t Q, const double *queries, uint64_t *codes, const int32_t *run_if) {
     const int dim_even = (rv.dim + 1) & ~1;
     int qstride = dim_even + 2;                      // doubles; 16-byte aligned rows whose granule count is odd => conflict-free 128-bit loads
     if (((qstride >> 1) & 1) == 0) qstride += 2;
@@ -155,8 +334,48 @@ int launch_tokengen(cudaStream_t s, const RoutingView &rv, int64_t Q, const doub
     const int groups_per_cta = (rv.TD + gsplit - 1) / gsplit;
     gsplit = (rv.TD + groups_per_cta - 1) / groups_per_cta;
     dim3 grid((unsigned)tiles, (unsigned)gsplit);
-    tokengen_kernel<<<grid, TG_THREADS, smem, s>>>(rv, Q, queries, codes, groups_per_cta, qstride, astride);
+    tokengen_kernel<<<grid, TG_THREADS, smem, s>>>(rv, Q, queries, codes, groups_per_cta, qstride, astride, run_if);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int64_t tokengen_list_capacity(const RoutingView &rv, int64_t Q) {
+    const int64_t total = Q * (int64_t)rv.TD * rv.m;
+    return std::max<int64_t>(65536, total / 8);
+}
+
+// work: int32[2] + list: uint64[tokengen_list_capacity] scratch (or nullptr / exact != 0: the exact kernel alone).
+int launch_tokengen(cudaStream_t s, const RoutingView &rv, int64_t Q, const double *queries, uint64_t *codes, int32_t *work,
+                    unsigned long long *list, int64_t list_cap, bool exact_only) {
+    if (Q <= 0) return 0;
+    const bool fast_ok = !exact_only && work && list && rv.alpha_f32 && rv.alpha_norm && (rv.m + 1) / 2 <= TF_JB && rv.TD < 65536 && rv.m < 256 &&
+                         Q < (1LL << 39);
+    if (!fast_ok) return launch_tokengen_exact(s, rv, Q, queries, codes, nullptr);
+    const int n4 = (rv.dim + 3) >> 2;
+    int qg = n4 + 1;                                 // row stride in 16-byte granules, odd => conflict-free 128-bit loads
+    if ((qg & 1) == 0) qg++;
+    const int qstride = 4 * qg, astride = 4 * n4;
+    const size_t smem = sizeof(float) * ((size_t)TF_QT * qstride + (size_t)rv.m * astride) + sizeof(double) * 2 * (size_t)rv.m +
+                        sizeof(float) * (((size_t)rv.m + 3) / 4 * 4 + TF_QT) + sizeof(uint32_t) * (size_t)TF_QT * 2 * rv.W;
+    if (smem > 113 * 1024) return launch_tokengen_exact(s, rv, Q, queries, codes, nullptr);
+    static size_t configured = 0;
+    if (smem > configured) {
+        if (cudaFuncSetAttribute(tokengen_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+        configured = smem;
+    }
+    if (cudaMemsetAsync(work, 0, 2 * sizeof(int32_t), s) != cudaSuccess) return -1;
+    const int64_t tiles = (Q + TF_QT - 1) / TF_QT;
+    int gsplit = (int)((296 * 6 + tiles - 1) / tiles);
+    if (gsplit < 1) gsplit = 1;
+    if (gsplit > rv.TD) gsplit = rv.TD;
+    const int groups_per_cta = (rv.TD + gsplit - 1) / gsplit;
+    gsplit = (rv.TD + groups_per_cta - 1) / groups_per_cta;
+    const float cbound = 4.0f * ((float)(rv.dim + 2) * 5.9604645e-8f * 1.01f + 2.3841858e-7f);
+    dim3 grid((unsigned)tiles, (unsigned)gsplit);
+    tokengen_fast_kernel<<<grid, TF_THREADS, smem, s>>>(rv, Q, queries, codes, groups_per_cta, qstride, astride, cbound, work, list, list_cap);
+    tokengen_recheck_kernel<<<148 * 2, 256, 0, s>>>(rv, queries, codes, work, list, list_cap);
+    if (cudaGetLastError() != cudaSuccess) return -1;
+    const int n = launch_tokengen_exact(s, rv, Q, queries, codes, work + 1);      // runs only after a worklist overflow
+    return n < 0 ? -1 : 2 + n;
 }
 
 }  // namespace fsp

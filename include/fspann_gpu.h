@@ -69,8 +69,10 @@ int64_t fspann_ctx_launch_count(const fspann_ctx *ctx);
 
 /* Tuning / test switches: "route_general" = 1 forces the general Route kernel (sequential groups, exact HARD_CAP
  * semantics) even where the shared-memory fast path applies; "route_wl_extra" = n >= 0 clamps the fast path's dedicated
- * worklist to n entries (test hook for its overflow fallback), -1 = automatic.  fspann_get_info: "last_route_path"
- * (1 fast, 2 general), "sm_count". */
+ * worklist to n entries (test hook for its overflow fallback), -1 = automatic; "tokengen_exact" = 1 runs the exact FP64 TokenGen
+ * kernel alone instead of the FP32 pre-filter + exact re-check (the codes are identical either way).  fspann_get_info:
+ * "last_route_path" (1 fast, 2 general), "sm_count", "build_treeified", "tokengen_rechecked" / "tokengen_overflow" (projections
+ * the last TokenGen launch had to re-check exactly / whether its list overflowed and the exact kernel recomputed the batch). */
 int fspann_set_option(fspann_ctx *ctx, const char *name, int64_t value);
 int64_t fspann_get_info(fspann_ctx *ctx, const char *name);
 

@@ -44,6 +44,24 @@ def test_device_built_index_is_a_valid_greedy_partitioning(c2):
     assert ((mn[5][p] <= keys) & (keys <= mx[5][p])).all()                                  # each id sits in the partition covering its key
 
 
+def test_tokengen_prefilter_equals_exact_kernel_on_the_whole_base_set(c2):
+    """1.5 G projections: the FP32 pre-filter + exact re-check must give the exact kernel's codes for every base vector."""
+    gpu, base = c2["gpu"], c2["base"]
+    tot_re = 0
+    for s in range(0, base.shape[0], 250_000):
+        fast = gpu.tokengen_batch(base[s:s + 250_000])
+        tot_re += gpu.get_info("tokengen_rechecked")
+        assert gpu.get_info("tokengen_overflow") == 0
+        gpu.set_option("tokengen_exact", 1)
+        try:
+            exact = gpu.tokengen_batch(base[s:s + 250_000])
+        finally:
+            gpu.set_option("tokengen_exact", 0)
+        assert np.array_equal(fast, exact)
+    frac = tot_re / (base.shape[0] * 64 * 24)
+    assert 0 < frac < 0.02, frac                                           # a fraction of a percent needs the exact arithmetic
+
+
 def test_search_matches_oracle_sample_and_is_invariant_under_rotate_migrate(c2):
     cfg, gpu, q = c2["cfg"], c2["gpu"], c2["queries"]
     k = cfg.k

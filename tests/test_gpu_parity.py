@@ -211,3 +211,45 @@ def test_routing_build_on_device_matches_reference_build(wg):
         assert np.array_equal(ids2, ix2.ids) and np.array_equal(rep2, ix2.rep) and np.array_equal(mn2, ix2.min_key) and np.array_equal(mx2, ix2.max_key)
     finally:
         ctx.close()
+
+
+def test_tokengen_prefilter_and_exact_kernel_agree_incl_boundary_vectors(wg):
+    """TokenGen runs an FP32 pre-filter with a proven error bound and re-checks the undecided projections with the exact sequential
+    FP64 arithmetic.  Codes must equal the exact kernel's and the oracle's: on ordinary data, on vectors constructed to sit ON
+    quantisation boundaries ((alpha.v + r)/omega within 1e-12 of an integer -> must be re-checked), on huge / tiny magnitudes, and
+    when the re-check list overflows (whole batch recomputed by the exact kernel)."""
+    w, ctx = wg
+    g = w.g
+    rng = np.random.default_rng(12)
+    base = w.base[:1500]
+    # boundary vectors: scale a data vector so that projection (td, j) lands exactly on k*omega - r
+    tricky = []
+    for s in range(200):
+        v = base[s].copy()
+        td, j = int(rng.integers(0, g.T * g.D)), int(rng.integers(0, g.m))
+        y = float(v @ g.alpha[td, j])
+        if abs(y) < 1e-6:
+            continue
+        k = np.floor((y + g.r[td, j]) / g.omega[td, j]) + rng.integers(0, 2)
+        target = k * g.omega[td, j] - g.r[td, j]
+        tricky.append(v * (target / y) * (1.0 + rng.choice([0.0, 1e-15, -1e-15, 3e-13, -3e-13])))
+    extremes = np.stack([base[0] * 1e30, base[1] * 1e-30, base[2] * 1e300, np.zeros(g.dim), -base[3]])
+    vecs = np.concatenate([base, np.asarray(tricky), extremes])
+    ref = O.tokengen_batch(vecs, g)
+    got = ctx.tokengen_batch(vecs)
+    n_re = ctx.get_info("tokengen_rechecked")
+    assert np.array_equal(got, ref)
+    total = vecs.shape[0] * g.T * g.D * g.m
+    assert len(tricky) <= n_re < 0.2 * total, (n_re, total)             # the boundary cases were re-checked; the bulk was not
+    assert ctx.get_info("tokengen_overflow") == 0
+    try:
+        ctx.set_option("tokengen_exact", 1)
+        assert np.array_equal(ctx.tokengen_batch(vecs), ref)
+        ctx.set_option("tokengen_exact", 0)
+        ctx.set_option("tokengen_list_cap", 8)                           # overflow -> the exact kernel recomputes the batch
+        assert np.array_equal(ctx.tokengen_batch(vecs), ref)
+        assert ctx.get_info("tokengen_overflow") == 1
+    finally:
+        ctx.set_option("tokengen_exact", 0)
+        ctx.set_option("tokengen_list_cap", 0)
+    assert np.array_equal(ctx.tokengen_batch(vecs[:7]), ref[:7]) and ctx.get_info("tokengen_overflow") == 0
