@@ -32,7 +32,7 @@ struct fspann_ctx {
     // routing state
     bool routing_ready = false;
     RoutingView rv{};
-    DevBuf d_alpha, d_r, d_omega, d_keys, d_rep, d_ids, d_deleted, d_alpha_f, d_alpha_norm, s_tg_work, s_tg_list;
+    DevBuf d_alpha, d_r, d_omega, d_keys, d_rep, d_ids, d_deleted, d_alpha_f, d_alpha_norm, s_tg_work, s_tg_list, s_tg_qf, s_tg_norm;
     int opt_tokengen_exact = 0;  // run the exact FP64 TokenGen kernel alone (no FP32 pre-filter)
     int64_t opt_tg_list_cap = 0; // test hook: clamp the re-check list (forces the overflow -> exact-kernel fallback)
 
@@ -182,8 +182,10 @@ int run_tokengen(fspann_ctx *ctx, int64_t Q, const double *d_queries, uint64_t *
     if (ctx->opt_tg_list_cap > 0) cap = std::min(cap, ctx->opt_tg_list_cap);
     ENSURE(ctx->s_tg_work, 4 * sizeof(int32_t));
     ENSURE(ctx->s_tg_list, sizeof(unsigned long long) * (size_t)cap);
+    ENSURE(ctx->s_tg_qf, sizeof(float) * (size_t)Q * (((size_t)ctx->rv.dim + 3) / 4 * 4));
+    ENSURE(ctx->s_tg_norm, sizeof(float) * (size_t)Q);
     LAUNCHED(launch_tokengen(ctx->stream, ctx->rv, Q, d_queries, d_codes, (int32_t *)ctx->s_tg_work.p, (unsigned long long *)ctx->s_tg_list.p, cap,
-                             ctx->opt_tokengen_exact != 0));
+                             (float *)ctx->s_tg_qf.p, (float *)ctx->s_tg_norm.p, ctx->opt_tokengen_exact != 0));
     return 0;
 }
 
@@ -306,7 +308,7 @@ void fspann_ctx_destroy(fspann_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    DevBuf *bufs[] = {&ctx->d_alpha_f, &ctx->d_alpha_norm, &ctx->s_tg_work, &ctx->s_tg_list, &ctx->d_alpha, &ctx->d_r, &ctx->d_omega, &ctx->d_keys, &ctx->d_rep, &ctx->d_ids, &ctx->d_deleted, &ctx->d_rec,
+    DevBuf *bufs[] = {&ctx->d_alpha_f, &ctx->d_alpha_norm, &ctx->s_tg_work, &ctx->s_tg_list, &ctx->s_tg_qf, &ctx->s_tg_norm, &ctx->d_alpha, &ctx->d_r, &ctx->d_omega, &ctx->d_keys, &ctx->d_rep, &ctx->d_ids, &ctx->d_deleted, &ctx->d_rec,
                       &ctx->d_keyring, &ctx->d_hpow, &ctx->d_shoup, &ctx->s_rec_verdict, &ctx->s_qf32, &ctx->s_qu8, &ctx->s_f32_exact, &ctx->d_te0, &ctx->d_touched, &ctx->s_queries, &ctx->s_codes, &ctx->s_cand_ids,
                       &ctx->s_cand_sc, &ctx->s_ncand, &ctx->s_raw, &ctx->s_uniq_cnt, &ctx->s_route_scratch, &ctx->s_overflow, &ctx->s_cnt,
                       &ctx->s_flag, &ctx->s_fill, &ctx->s_uniq, &ctx->s_pairs, &ctx->s_bsums, &ctx->s_totals, &ctx->s_dist, &ctx->s_verdict,

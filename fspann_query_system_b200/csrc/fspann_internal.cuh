@@ -109,7 +109,7 @@ struct RefineParams {
 
 // launchers (each returns the number of kernels it launched, or -1 after setting a CUDA error)
 int launch_tokengen(cudaStream_t s, const RoutingView &rv, int64_t Q, const double *queries, uint64_t *codes, int32_t *work,
-                    unsigned long long *list, int64_t list_cap, bool exact_only);
+                    unsigned long long *list, int64_t list_cap, float *qf, float *qnorm, bool exact_only);
 int64_t tokengen_list_capacity(const RoutingView &rv, int64_t Q);
 int launch_alpha_prepare(cudaStream_t s, const double *alpha, int64_t rows, int dim, float *alpha_f, float *norm);
 int launch_route(cudaStream_t s, const RoutingView &rv, const RouteParams &p, int grid);

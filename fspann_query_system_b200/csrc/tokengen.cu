@@ -164,6 +164,22 @@ int launch_alpha_prepare(cudaStream_t s, const double *alpha, int64_t rows, int 
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
+// FP32 copy of the query rows (zero-padded to dim4 = a multiple of 4 floats) and an upper bound of every row's 2-norm.
+__global__ void tokengen_prep_kernel(const double *__restrict__ queries, int64_t Q, int dim, int dim4, float *__restrict__ qf, float *__restrict__ norm) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (row >= Q) return;
+    float ss = 0.f;
+    for (int i = lane; i < dim4; i += 32) {
+        const float v = i < dim ? (float)queries[row * dim + i] : 0.f;
+        qf[row * dim4 + i] = v;
+        ss = fmaf(v, v, ss);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (lane == 0) norm[row] = __fmul_ru(__fsqrt_ru(ss), 1.0001f);
+}
+
 template <int NJ>
 __device__ __forceinline__ void tf_dot_block(const float *qa, const float *qb, const float *as, int astride, int n4, int jb, float accA[TF_JB], float accB[TF_JB]) {
 #pragma unroll
@@ -186,7 +202,7 @@ __device__ __forceinline__ void tf_dot_block(const float *qa, const float *qb, c
 }
 
 // work[0] = number of listed (q, g, j); work[1] = overflow flag; list entries = q << 24 | g << 8 | j  (g < 65536, j < 256)
-__global__ void __launch_bounds__(TF_THREADS, 2) tokengen_fast_kernel(RoutingView rv, int64_t Q, const double *__restrict__ queries,
+__global__ void __launch_bounds__(TF_THREADS, 2) tokengen_fast_kernel(RoutingView rv, int64_t Q, const float *__restrict__ qf, const float *__restrict__ qnorm,
                                                                       uint64_t *__restrict__ codes, int groups_per_cta, int qstride, int astride,
                                                                       float cbound, int32_t *__restrict__ work, unsigned long long *__restrict__ list,
                                                                       int64_t list_cap) {
@@ -197,7 +213,9 @@ __global__ void __launch_bounds__(TF_THREADS, 2) tokengen_fast_kernel(RoutingVie
     double *rs = reinterpret_cast<double *>(as + (size_t)m * astride);   // [m] r
     double *os = rs + m;                                           // [m] omega
     float *na = reinterpret_cast<float *>(os + m);                 // [m] ||alpha_j||
-    float *nv = na + ((m + 3) & ~3);                               // [TF_QT] ||v||
+    float *rf = na + ((m + 3) & ~3);                               // [m] r_j in FP32
+    float *iof = rf + ((m + 3) & ~3);                              // [m] 1 / omega_j in FP32
+    float *nv = iof + ((m + 3) & ~3);                              // [TF_QT] ||v||
     uint32_t *cs = reinterpret_cast<uint32_t *>(nv + TF_QT);       // [TF_QT][2*W] code words being assembled
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -205,18 +223,13 @@ __global__ void __launch_bounds__(TF_THREADS, 2) tokengen_fast_kernel(RoutingVie
     const int nq = (int)min((int64_t)TF_QT, Q - q0);
     const int n4 = (dim + 3) >> 2;
 
-    // stage the query tile as FP32 (coalesced over the row-major FP64 input); one warp per row computes the row norm
-    for (int r = warp; r < TF_QT; r += TF_THREADS / 32) {
-        float ss = 0.f;
-        for (int i = lane; i < 4 * n4; i += 32) {
-            const float v = (r < nq && i < dim) ? (float)queries[(q0 + r) * dim + i] : 0.f;
-            qs[(size_t)r * qstride + i] = v;
-            ss = fmaf(v, v, ss);
-        }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-        if (lane == 0) nv[r] = __fmul_ru(__fsqrt_ru(ss), 1.0001f);
+    // stage the FP32 query tile (128-bit loads from the prepared copy, several in flight per thread) and the row norms
+    for (int idx = tid; idx < TF_QT * n4; idx += TF_THREADS) {
+        const int r = idx / n4, c = idx - r * n4;
+        const float4 v = r < nq ? __ldg(reinterpret_cast<const float4 *>(qf + (q0 + r) * (int64_t)(4 * n4)) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4 *>(qs + (size_t)r * qstride + 4 * c) = v;
     }
+    for (int r = tid; r < TF_QT; r += TF_THREADS) nv[r] = r < nq ? qnorm[q0 + r] : 0.f;
 
     const int half = warp & 1, slice = warp >> 1;
     const int jper = (m + 1) / 2;
@@ -228,8 +241,13 @@ __global__ void __launch_bounds__(TF_THREADS, 2) tokengen_fast_kernel(RoutingVie
     for (int g = g_lo; g < g_hi; g++) {
         __syncthreads();  // previous group's tile / code words fully consumed; query tile staged
         const float *ag = rv.alpha_f32 + (size_t)g * m * dim;
-        for (int idx = tid; idx < m * 4 * n4; idx += TF_THREADS) { const int j = idx / (4 * n4), i = idx - j * 4 * n4; as[(size_t)j * astride + i] = i < dim ? ag[(size_t)j * dim + i] : 0.f; }
-        for (int idx = tid; idx < m; idx += TF_THREADS) { rs[idx] = rv.r[(size_t)g * m + idx]; os[idx] = rv.omega[(size_t)g * m + idx]; na[idx] = rv.alpha_norm[(size_t)g * m + idx]; }
+        if ((dim & 3) == 0) {
+            for (int idx = tid; idx < m * n4; idx += TF_THREADS) reinterpret_cast<float4 *>(as)[idx] = __ldg(reinterpret_cast<const float4 *>(ag) + idx);
+        } else {
+            for (int idx = tid; idx < m * 4 * n4; idx += TF_THREADS) { const int j = idx / (4 * n4), i = idx - j * 4 * n4; as[(size_t)j * astride + i] = i < dim ? ag[(size_t)j * dim + i] : 0.f; }
+        }
+        for (int idx = tid; idx < m; idx += TF_THREADS) { rs[idx] = rv.r[(size_t)g * m + idx]; os[idx] = rv.omega[(size_t)g * m + idx]; na[idx] = rv.alpha_norm[(size_t)g * m + idx];
+                                                           rf[idx] = (float)rs[idx]; iof[idx] = (float)(1.0 / os[idx]); }
         for (int idx = tid; idx < TF_QT * 2 * W; idx += TF_THREADS) cs[idx] = 0u;
         __syncthreads();
 
@@ -250,34 +268,52 @@ __global__ void __launch_bounds__(TF_THREADS, 2) tokengen_fast_kernel(RoutingVie
             case 1: tf_dot_block<1>(qa, qb, as, astride, n4, j_lo, accA, accB); break;
             default: break;
         }
+        // ---- decide h_j in single precision; undecided projections go to the exact re-check list and contribute no bits here ----
+        int32_t hA[TF_JB], hB[TF_JB];
+        uint32_t decA = 0, decB = 0;                                   // bit u: projection j_lo + u was decided here
 #pragma unroll
         for (int u = 0; u < TF_JB; u++) {
+            hA[u] = 0; hB[u] = 0;
             if (u < nj) {
                 const int j = j_lo + u;
+                const float rj = rf[j], io = iof[j], bj = cbound * na[j] * io;
 #pragma unroll
                 for (int hb = 0; hb < 2; hb++) {
                     const int qi = hb ? rb : ra;
-                    if (qi >= nq) continue;
-                    const float acc = hb ? accB[u] : accA[u];
-                    const double om = os[j];
-                    const double t = __ddiv_rn(__dadd_rn((double)acc, rs[j]), om);
-                    const double f = floor(t);
-                    const double slack = (double)(cbound * nv[qi] * na[j]) / om + 1e-9 * (1.0 + fabs(t));
-                    const bool decided = (t - f > slack) && (f + 1.0 - t > slack) && fabs(t) < 1073741824.0;   // also false for NaN / Inf
-                    if (decided) {
-                        const uint32_t hj = (uint32_t)__double2int_rz(f) ^ 0x80000000u;             // Coding:293
-                        for (int ib = 0; ib < lambda; ib++) {
-                            if (ib < 32 && ((hj >> ib) & 1u)) {
-                                const int pos = (lambda - 1 - ib) * m + j;                        // MSB-first bit planes (Coding:291-299)
-                                atomicOr(&cs[(size_t)qi * 2 * W + (pos >> 5)], 1u << (pos & 31));
-                            }
-                        }
-                    } else {
+                    const float t = ((hb ? accB[u] : accA[u]) + rj) * io;
+                    const float f = floorf(t);
+                    // |t - t_java| <= E / omega (dot product) + a few 2^-24 relative roundings of the FP32 epilogue (r, 1/omega, +, *)
+                    const float slack = bj * nv[qi] + 2e-6f * (1.0f + fabsf(t));
+                    const bool decided = (t - f > slack) && (f + 1.0f - t > slack) && fabsf(t) < 4194304.0f;      // false for NaN / Inf too
+                    if (decided) { if (hb) { hB[u] = (int32_t)f; decB |= 1u << u; } else { hA[u] = (int32_t)f; decA |= 1u << u; } }
+                    else if (qi < nq) {
                         const int at = atomicAdd(&work[0], 1);
                         if (at < list_cap) list[at] = ((unsigned long long)(q0 + qi) << 24) | ((unsigned long long)g << 8) | (unsigned long long)j;
                         else work[1] = 1;
                     }
                 }
+            }
+        }
+        // bit planes (Coding:291-299): plane ib holds bit ib of h_j at position (lambda-1-ib)*m + j; this thread's projections are
+        // consecutive, so a plane's bits form one <= 12-bit field spanning at most two 32-bit words
+        for (int ib = 0; ib < lambda && ib < 32; ib++) {
+            uint32_t fa = 0, fb = 0;
+#pragma unroll
+            for (int u = 0; u < TF_JB; u++) {
+                if (u < nj) {                                           // (h ^ 0x80000000) only flips bit 31 (Coding:293)
+                    fa |= ((((uint32_t)hA[u] ^ 0x80000000u) >> ib) & 1u) << u;
+                    fb |= ((((uint32_t)hB[u] ^ 0x80000000u) >> ib) & 1u) << u;
+                }
+            }
+            fa &= decA; fb &= decB;                                     // undecided entries get their bits from the exact re-check
+            const int pos0 = (lambda - 1 - ib) * m + j_lo, w0 = pos0 >> 5, sh = pos0 & 31;
+            if (ra < nq) {
+                if (fa << sh) atomicOr(&cs[(size_t)ra * 2 * W + w0], fa << sh);
+                if (sh && (fa >> (32 - sh))) atomicOr(&cs[(size_t)ra * 2 * W + w0 + 1], fa >> (32 - sh));
+            }
+            if (rb < nq) {
+                if (fb << sh) atomicOr(&cs[(size_t)rb * 2 * W + w0], fb << sh);
+                if (sh && (fb >> (32 - sh))) atomicOr(&cs[(size_t)rb * 2 * W + w0 + 1], fb >> (32 - sh));
             }
         }
         __syncthreads();
@@ -301,7 +337,15 @@ __global__ void tokengen_recheck_kernel(RoutingView rv, const double *__restrict
         const int g = (int)((e >> 8) & 0xffffu), j = (int)(e & 0xffu);
         const double *v = queries + q * dim, *al = rv.alpha + ((size_t)g * m + j) * dim;
         double acc = 0.0;
-        for (int i = 0; i < dim; i++) acc = __dadd_rn(acc, __dmul_rn(v[i], al[i]));
+        int i = 0;
+        for (; i + 8 <= dim; i += 8) {                                  // 16 independent loads in flight, strictly sequential adds
+            double a[8], b[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) { a[u] = __ldg(v + i + u); b[u] = __ldg(al + i + u); }
+#pragma unroll
+            for (int u = 0; u < 8; u++) acc = __dadd_rn(acc, __dmul_rn(a[u], b[u]));
+        }
+        for (; i < dim; i++) acc = __dadd_rn(acc, __dmul_rn(v[i], al[i]));
         const double y = __dadd_rn(acc, rv.r[(size_t)g * m + j]);
         const double f = floor(__ddiv_rn(y, rv.omega[(size_t)g * m + j]));
         const uint32_t hj = (uint32_t)__double2int_rz(f) ^ 0x80000000u;
@@ -345,9 +389,9 @@ int64_t tokengen_list_capacity(const RoutingView &rv, int64_t Q) {
 
 // work: int32[2] + list: uint64[tokengen_list_capacity] scratch (or nullptr / exact != 0: the exact kernel alone).
 int launch_tokengen(cudaStream_t s, const RoutingView &rv, int64_t Q, const double *queries, uint64_t *codes, int32_t *work,
-                    unsigned long long *list, int64_t list_cap, bool exact_only) {
+                    unsigned long long *list, int64_t list_cap, float *qf, float *qnorm, bool exact_only) {
     if (Q <= 0) return 0;
-    const bool fast_ok = !exact_only && work && list && rv.alpha_f32 && rv.alpha_norm && (rv.m + 1) / 2 <= TF_JB && rv.TD < 65536 && rv.m < 256 &&
+    const bool fast_ok = !exact_only && work && list && qf && qnorm && rv.alpha_f32 && rv.alpha_norm && (rv.m + 1) / 2 <= TF_JB && rv.TD < 65536 && rv.m < 256 &&
                          Q < (1LL << 39);
     if (!fast_ok) return launch_tokengen_exact(s, rv, Q, queries, codes, nullptr);
     const int n4 = (rv.dim + 3) >> 2;
@@ -355,7 +399,7 @@ int launch_tokengen(cudaStream_t s, const RoutingView &rv, int64_t Q, const doub
     if ((qg & 1) == 0) qg++;
     const int qstride = 4 * qg, astride = 4 * n4;
     const size_t smem = sizeof(float) * ((size_t)TF_QT * qstride + (size_t)rv.m * astride) + sizeof(double) * 2 * (size_t)rv.m +
-                        sizeof(float) * (((size_t)rv.m + 3) / 4 * 4 + TF_QT) + sizeof(uint32_t) * (size_t)TF_QT * 2 * rv.W;
+                        sizeof(float) * (3 * (((size_t)rv.m + 3) / 4 * 4) + TF_QT) + sizeof(uint32_t) * (size_t)TF_QT * 2 * rv.W;
     if (smem > 113 * 1024) return launch_tokengen_exact(s, rv, Q, queries, codes, nullptr);
     static size_t configured = 0;
     if (smem > configured) {
@@ -364,18 +408,20 @@ int launch_tokengen(cudaStream_t s, const RoutingView &rv, int64_t Q, const doub
     }
     if (cudaMemsetAsync(work, 0, 2 * sizeof(int32_t), s) != cudaSuccess) return -1;
     const int64_t tiles = (Q + TF_QT - 1) / TF_QT;
-    int gsplit = (int)((296 * 6 + tiles - 1) / tiles);
+    int gsplit = (int)((296 * 4 + tiles - 1) / tiles);
     if (gsplit < 1) gsplit = 1;
     if (gsplit > rv.TD) gsplit = rv.TD;
-    const int groups_per_cta = (rv.TD + gsplit - 1) / gsplit;
+    int groups_per_cta = (rv.TD + gsplit - 1) / gsplit;
+    if (groups_per_cta < 4) groups_per_cta = std::min(4, (int)rv.TD);   // amortise the tile staging over >= 4 groups
     gsplit = (rv.TD + groups_per_cta - 1) / groups_per_cta;
     const float cbound = 4.0f * ((float)(rv.dim + 2) * 5.9604645e-8f * 1.01f + 2.3841858e-7f);
     dim3 grid((unsigned)tiles, (unsigned)gsplit);
-    tokengen_fast_kernel<<<grid, TF_THREADS, smem, s>>>(rv, Q, queries, codes, groups_per_cta, qstride, astride, cbound, work, list, list_cap);
+    tokengen_prep_kernel<<<(unsigned)((Q * 32 + 255) / 256), 256, 0, s>>>(queries, Q, rv.dim, 4 * n4, qf, qnorm);
+    tokengen_fast_kernel<<<grid, TF_THREADS, smem, s>>>(rv, Q, qf, qnorm, codes, groups_per_cta, qstride, astride, cbound, work, list, list_cap);
     tokengen_recheck_kernel<<<148 * 2, 256, 0, s>>>(rv, queries, codes, work, list, list_cap);
     if (cudaGetLastError() != cudaSuccess) return -1;
     const int n = launch_tokengen_exact(s, rv, Q, queries, codes, work + 1);      // runs only after a worklist overflow
-    return n < 0 ? -1 : 2 + n;
+    return n < 0 ? -1 : 3 + n;
 }
 
 }  // namespace fsp
