@@ -381,6 +381,8 @@ def main():
                     and np.array_equal(again["counters"], ref_ids["counters"]))
         mixed = {"migrated_records": int(out["count"]), "migrate_s_incl_copies": t_mig, "results_identical_after_rotate_migrate": same,
                  "ms_per_step_mixed_versions": g0.elapsed_time(g1) / K, "versions": [1, 2]}
+        step_dev(0)
+        mixed["stage_ms"] = {kk: vv for kk, vv in gpu.stage_ms().items() if kk != "launches"}
         log(f"config 5: migrated {out['count']} records to v2 on the device in {t_mig:.2f}s; results identical: {same}; {mixed['ms_per_step_mixed_versions']:.2f} ms/step")
 
     if world_size > 1:

@@ -49,7 +49,7 @@ struct fspann_ctx {
     int last_route_path = 0;     // 1 = shared-memory fast path, 2 = general path
     bool last_queries_finite = true;
     DevBuf s_queries, s_codes, s_cand_ids, s_cand_sc, s_ncand, s_raw, s_uniq_cnt, s_route_scratch, s_overflow;
-    DevBuf s_rec_verdict, s_qf32, s_qu8, s_f32_exact;
+    DevBuf s_rec_verdict, s_qf32, s_qu8, s_f32_exact, s_vorder, s_voff;
     DevKeyRing ring_host{};
     int32_t *want_rank = nullptr;
     DevBuf s_cnt, s_flag, s_fill, s_uniq, s_pairs, s_bsums, s_totals, s_dist, s_verdict;
@@ -261,6 +261,13 @@ int do_refine(fspann_ctx *ctx, int64_t Q, const double *d_queries, const int32_t
     CK(cudaMemsetAsync(p.rec_verdict, FSPANN_V_NO_KEY, (size_t)std::min<int64_t>(n1, total + 1), ctx->stream));
     LAUNCHED(launch_refine_group(ctx->stream, sv, p));
     if (stage_events) { int rc = record_ev(ctx, 3); if (rc) return rc; }
+    if (ctx->ring_host.n > 1) {      // several live key versions (after a Rotate): every verify pass walks a dense list of its own records
+        const int64_t n_upper = std::min<int64_t>(n1, total + 1);
+        ENSURE(ctx->s_vorder, sizeof(int32_t) * (size_t)n_upper);
+        ENSURE(ctx->s_voff, sizeof(int32_t) * (3 * kMaxKeys + 4));
+        p.vorder = (int32_t *)ctx->s_vorder.p; p.voff = (int32_t *)ctx->s_voff.p; p.vcnt = p.voff + kMaxKeys + 1;
+        LAUNCHED(launch_version_bucket(ctx->stream, sv, p, n_upper));
+    }
     LAUNCHED(launch_refine_verify(ctx->stream, sv, p, ctx->sm_count));
     if (stage_events) { int rc = record_ev(ctx, 4); if (rc) return rc; }
     LAUNCHED(launch_refine_decrypt(ctx->stream, sv, p, ctx->sm_count));
@@ -308,7 +315,7 @@ void fspann_ctx_destroy(fspann_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    DevBuf *bufs[] = {&ctx->d_alpha_f, &ctx->d_alpha_norm, &ctx->s_tg_work, &ctx->s_tg_list, &ctx->s_tg_qf, &ctx->s_tg_norm, &ctx->d_alpha, &ctx->d_r, &ctx->d_omega, &ctx->d_keys, &ctx->d_rep, &ctx->d_ids, &ctx->d_deleted, &ctx->d_rec,
+    DevBuf *bufs[] = {&ctx->d_alpha_f, &ctx->d_alpha_norm, &ctx->s_vorder, &ctx->s_voff, &ctx->s_tg_work, &ctx->s_tg_list, &ctx->s_tg_qf, &ctx->s_tg_norm, &ctx->d_alpha, &ctx->d_r, &ctx->d_omega, &ctx->d_keys, &ctx->d_rep, &ctx->d_ids, &ctx->d_deleted, &ctx->d_rec,
                       &ctx->d_keyring, &ctx->d_hpow, &ctx->d_shoup, &ctx->s_rec_verdict, &ctx->s_qf32, &ctx->s_qu8, &ctx->s_f32_exact, &ctx->d_te0, &ctx->d_touched, &ctx->s_queries, &ctx->s_codes, &ctx->s_cand_ids,
                       &ctx->s_cand_sc, &ctx->s_ncand, &ctx->s_raw, &ctx->s_uniq_cnt, &ctx->s_route_scratch, &ctx->s_overflow, &ctx->s_cnt,
                       &ctx->s_flag, &ctx->s_fill, &ctx->s_uniq, &ctx->s_pairs, &ctx->s_bsums, &ctx->s_totals, &ctx->s_dist, &ctx->s_verdict,

@@ -100,6 +100,9 @@ struct RefineParams {
     uint8_t *verdict;   // [Q*stride]
     uint32_t *touched;  // [ceil(N/32)]
     uint8_t *rec_verdict;  // [n_uniq] authentication verdict per distinct record (verify kernel -> decrypt kernel)
+    int32_t *vorder;       // [n_uniq] positions of uniq[] bucketed by key-version slot, or nullptr (one live version)
+    int32_t *voff;         // [kMaxKeys + 1] bucket offsets
+    int32_t *vcnt;         // [2 * kMaxKeys] bucket counts / scatter cursors
     // outputs
     int32_t *topk_ids;  // [Q][k]
     double *topk_dist;  // [Q][k]
@@ -120,6 +123,7 @@ int launch_route_fast(cudaStream_t s, const RoutingView &rv, const RouteParams &
 int64_t route_scratch_ints(int32_t cap0, int32_t max_nodes);
 int launch_refine_group(cudaStream_t s, const StoreView &sv, const RefineParams &p);
 int launch_refine_verify(cudaStream_t s, const StoreView &sv, const RefineParams &p, int sm_count);
+int launch_version_bucket(cudaStream_t s, const StoreView &sv, const RefineParams &p, int64_t n_upper);
 int launch_refine_decrypt(cudaStream_t s, const StoreView &sv, const RefineParams &p, int sm_count);
 int launch_queries_to_f32(cudaStream_t s, const double *q, float *out, uint8_t *out8, int64_t n, int32_t *exact);
 int launch_refine_topk(cudaStream_t s, const RefineParams &p);

@@ -421,8 +421,11 @@ __device__ __forceinline__ bool lane_verify_record(const StoreView &sv, const ui
 // at a time.  list[u] = record index inside this store view; gid[u] = global id for the AAD (or nullptr: index + id_base).
 // write_flag == nullptr: verify, verdict[u] = OK / TAG_FAIL (records of unknown versions keep their preset verdict).
 // write_flag != nullptr: (re-)compute and STORE the tag of every record with write_flag[u] != 0 (encrypt / Migrate).
+// vorder / voff (optional): list positions bucketed by key-version slot (voff[slot] .. voff[slot+1]) so that with several live
+// versions every pass walks a DENSE list of its own records instead of all records with most lanes masked off.
 __device__ __forceinline__ void gcm_tag_body(const StoreView &sv, const int32_t *__restrict__ list, const int32_t *__restrict__ gid, int n_list,
-                                             uint8_t *__restrict__ verdict, const uint8_t *__restrict__ write_flag, unsigned char *vf_smem) {
+                                             uint8_t *__restrict__ verdict, const uint8_t *__restrict__ write_flag, unsigned char *vf_smem,
+                                             const int32_t *__restrict__ vorder = nullptr, const int32_t *__restrict__ voff = nullptr) {
     uint4 *shoup_s = reinterpret_cast<uint4 *>(vf_smem);                      // [16][256]
     uint32_t *te_s = reinterpret_cast<uint32_t *>(shoup_s + 4096);            // [256][32]
     uint32_t *s_rk = te_s + 256 * 32;                                         // [kMaxKeys][60]
@@ -434,18 +437,21 @@ __device__ __forceinline__ void gcm_tag_body(const StoreView &sv, const int32_t 
     for (int i = tid; i < kMaxKeys; i += VF_THREADS) s_ver[i] = i < nkeys ? sv.keys->version[i] : INT32_MIN;
     const TeSmem te{te_s + lane};
     const ShoupSmem sh{shoup_s, lane & 15};
-    const int n_chunks = (n_list + 31) >> 5;
     const int warps_total = gridDim.x * (VF_THREADS / 32);
 
     for (int vi = 0; vi < nkeys; vi++) {
+        const int v_lo = vorder ? voff[vi] : 0, v_n = vorder ? voff[vi + 1] - v_lo : n_list;
+        if (v_n <= 0) continue;                                             // uniform across the grid
         __syncthreads();
         for (int i = tid; i < 4096; i += VF_THREADS) shoup_s[i] = sv.shoup[(size_t)vi * 4096 + i];
         __syncthreads();
         const int32_t version = s_ver[vi];
         const RkSmem rk{s_rk + vi * 60};
+        const int n_chunks = (v_n + 31) >> 5;
         for (int chunk = blockIdx.x * (VF_THREADS / 32) + warp; chunk < n_chunks; chunk += warps_total) {
-            const int u = (chunk << 5) + lane;
-            if (u >= n_list) continue;
+            const int idx = (chunk << 5) + lane;
+            if (idx >= v_n) continue;
+            const int u = vorder ? vorder[v_lo + idx] : idx;
             if (write_flag && !write_flag[u]) continue;
             const int32_t li = list[u];                                     // index inside this shard
             const int32_t id = gid ? gid[u] : (int32_t)(li + sv.id_base);   // global id: what the AAD binds (EP:80-83)
@@ -468,7 +474,44 @@ __device__ __forceinline__ void gcm_tag_body(const StoreView &sv, const int32_t 
 
 __global__ void __launch_bounds__(VF_THREADS) refine_verify_kernel(StoreView sv, RefineParams p) {
     extern __shared__ __align__(16) unsigned char vf_smem[];
-    gcm_tag_body(sv, p.uniq, nullptr, p.totals[1], p.rec_verdict, nullptr, vf_smem);
+    gcm_tag_body(sv, p.uniq, nullptr, p.totals[1], p.rec_verdict, nullptr, vf_smem, p.vorder, p.voff);
+}
+
+// Buckets the distinct records of the batch by key-version slot (only launched when several versions are live).
+//   pass 0: vcnt[slot]++            pass 1 (after the host-free prefix in version_offsets_kernel): vorder[voff[slot] + cursor[slot]++] = u
+__global__ void version_bucket_kernel(StoreView sv, RefineParams p, int pass) {
+    const int n = p.totals[1], nkeys = sv.keys->n, lane = threadIdx.x & 31;
+    const int n_round = (n + 31) & ~31;                                     // whole warps stay in the loop (warp-aggregated atomics)
+    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < n_round; u += gridDim.x * blockDim.x) {
+        int slot = -1;
+        if (u < n) {
+            const uint4 hdr = ld_rec(reinterpret_cast<const uint4 *>(sv.rec + (size_t)p.uniq[u] * sv.rec_stride));
+            for (int i = 0; i < nkeys; i++) if (sv.keys->version[i] == (int32_t)hdr.w) slot = i;
+        }
+        // unknown / retired version (slot -1): verdict stays NO_KEY.  One atomic per (warp, slot).
+        const unsigned peers = __match_any_sync(0xffffffffu, slot);
+        if (slot < 0) continue;
+        const int leader = __ffs(peers) - 1, rank = __popc(peers & ((1u << lane) - 1u));
+        int base = 0;
+        if (lane == leader) base = atomicAdd(&p.vcnt[(pass ? kMaxKeys : 0) + slot], __popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        if (pass) p.vorder[p.voff[slot] + base + rank] = u;
+    }
+}
+__global__ void version_offsets_kernel(RefineParams p) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        int run = 0;
+        for (int i = 0; i < kMaxKeys; i++) { p.voff[i] = run; run += p.vcnt[i]; }
+        p.voff[kMaxKeys] = run;
+    }
+}
+int launch_version_bucket(cudaStream_t s, const StoreView &sv, const RefineParams &p, int64_t n_upper) {
+    if (cudaMemsetAsync(p.vcnt, 0, sizeof(int32_t) * 2 * kMaxKeys, s) != cudaSuccess) return -1;
+    int grid = (int)std::min<int64_t>((n_upper + 255) / 256, 148 * 8); if (grid < 1) grid = 1;
+    version_bucket_kernel<<<grid, 256, 0, s>>>(sv, p, 0);
+    version_offsets_kernel<<<1, 32, 0, s>>>(p);
+    version_bucket_kernel<<<grid, 256, 0, s>>>(sv, p, 1);
+    return cudaGetLastError() == cudaSuccess ? 3 : -1;
 }
 
 // The same over an explicit host-sized list (Migrate / bulk encryption).
