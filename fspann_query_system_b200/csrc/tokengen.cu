@@ -392,7 +392,7 @@ int launch_tokengen(cudaStream_t s, const RoutingView &rv, int64_t Q, const doub
                     unsigned long long *list, int64_t list_cap, float *qf, float *qnorm, bool exact_only) {
     if (Q <= 0) return 0;
     const bool fast_ok = !exact_only && work && list && qf && qnorm && rv.alpha_f32 && rv.alpha_norm && (rv.m + 1) / 2 <= TF_JB && rv.TD < 65536 && rv.m < 256 &&
-                         Q < (1LL << 39);
+                         Q * (int64_t)rv.TD * rv.m < (1LL << 31);        // the re-check counter is an int32: it can never wrap
     if (!fast_ok) return launch_tokengen_exact(s, rv, Q, queries, codes, nullptr);
     const int n4 = (rv.dim + 3) >> 2;
     int qg = n4 + 1;                                 // row stride in 16-byte granules, odd => conflict-free 128-bit loads
