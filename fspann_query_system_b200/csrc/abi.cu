@@ -26,6 +26,8 @@ struct fspann_ctx {
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
+    int32_t *h_pin = nullptr;                    // pinned host staging for the per-batch retry decision (n_ret, n_decrypted, flags)
+    size_t h_pin_ints = 0;
     std::string err;
     int64_t launches = 0;
 
@@ -328,6 +330,7 @@ void fspann_ctx_destroy(fspann_ctx *ctx) {
     for (DevBuf *b : bufs) release(*b);
     for (int i = 0; i < 7; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     delete ctx;
 }
 
@@ -916,11 +919,18 @@ int fspann_search_batch_dev(fspann_ctx *ctx, int64_t Q, const double *d_queries,
     ctx->ev_valid = true;
     if (allow_retry) {
         // QSI:327-337 + 444-447: once per query, if returned < K or decrypted < 10*K, redo with 10 probes.
-        std::vector<int32_t> nret((size_t)Q), ndec((size_t)Q);
-        int32_t flags[4] = {1, 1, 1, 1};
-        CK(cudaMemcpyAsync(nret.data(), d_n_ret, sizeof(int32_t) * (size_t)Q, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(ndec.data(), ctx->s_ndec.p, sizeof(int32_t) * (size_t)Q, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(flags, ctx->s_f32_exact.p, sizeof flags, cudaMemcpyDeviceToHost, ctx->stream));
+        // pinned staging: D2H into pageable memory would be a staged, blocking copy
+        const size_t need = 2 * (size_t)Q + 4;
+        if (ctx->h_pin_ints < need) {
+            if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+            ctx->h_pin = nullptr; ctx->h_pin_ints = 0;
+            CK(cudaHostAlloc((void **)&ctx->h_pin, sizeof(int32_t) * (need + need / 4), cudaHostAllocDefault));
+            ctx->h_pin_ints = need + need / 4;
+        }
+        int32_t *nret = ctx->h_pin, *ndec = ctx->h_pin + Q, *flags = ctx->h_pin + 2 * Q;
+        CK(cudaMemcpyAsync(nret, d_n_ret, sizeof(int32_t) * (size_t)Q, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ndec, ctx->s_ndec.p, sizeof(int32_t) * (size_t)Q, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(flags, ctx->s_f32_exact.p, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         ctx->last_queries_finite = flags[2] != 0;
         if (!ctx->last_queries_finite) return fail(ctx, FSPANN_E_ARG, "Vector contains NaN/Inf (Coding:357-359)");
