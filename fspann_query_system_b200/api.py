@@ -354,6 +354,47 @@ class ForwardSecureANNSystem:
             raise IllegalArgumentError(f"Query dimension mismatch: expected={self.dim} got={None if q is None else len(q)}")
         return self.tokenFactory.create(q, topK)
 
+    # -- callers of the path
+    def evalSimple(self, q, topK: int, dim: int):                   # QueryFacade.evalSimple (FSA:863-875)
+        return self.queryService.search(self.createToken(q, topK, dim))
+
+    def runQueries(self, queries, dim: int, gt_ids=None, k_variants=(1, 10, 20, 40, 60, 80, 100)):
+        """FSA:622-748 for a batch: one token per query at MAX_K = max(kVariants) (FSA:634,661), search, the probes-only fallback
+        max(2p, 4) for queries that came back empty (FSA:667-678), then per-K prefix metrics.  gt_ids: int32 [Q, >= MAX_K] ground truth
+        (fspann_groundtruth / GroundtruthPrecompute) or None.  Returns dict(results=[[QueryResult]], recall={K: mean recall@K},
+        returned={K: mean |prefix|}, fallback=[query indices that needed the fallback])."""
+        queries = np.ascontiguousarray(queries, dtype=np.float64)
+        max_k = int(max(k_variants))
+        rt = self.cfg.runtime
+        if rt.probeOverride >= 0:
+            self.index.setProbeOverride(rt.probeOverride)            # FSA:641-644
+        if rt.refinementLimit > 0:
+            self.queryService.setRefinementLimit(rt.refinementLimit)
+        tokens = [self.createToken(queries[i], max_k, dim) for i in range(queries.shape[0])]
+        results = self.queryService.searchBatch(tokens)
+        empty = [i for i, r in enumerate(results) if not r]
+        if empty:
+            base = rt.probeOverride if rt.probeOverride >= 0 else self.index.getDefaultMaxProbes()
+            self.index.setProbeOverride(max(base * 2, 4))
+            again = self.queryService.searchBatch([tokens[i] for i in empty])
+            self.index.clearProbeOverride()                          # "DO NOT touch refinement limit" (FSA:677)
+            for i, r in zip(empty, again):
+                results[i] = r
+        self.index.clearProbeOverride()
+        self.queryService.clearRefinementLimit()
+        recall, returned = {}, {}
+        Q = queries.shape[0]
+        ids = np.full((Q, max_k), -1, dtype=np.int32)
+        nret = np.zeros(Q, dtype=np.int32)
+        for i, r in enumerate(results):
+            nret[i] = len(r)
+            ids[i, :len(r)] = [int(x.id) for x in r]
+        for k in k_variants:
+            returned[k] = float(np.minimum(nret, k).mean())
+            if gt_ids is not None and gt_ids.shape[1] >= k:
+                recall[k] = float(self.gpu.recall_batch(np.ascontiguousarray(gt_ids[:, :k]), ids, k, np.minimum(nret, k)).mean())   # FSA:785-794
+        return dict(results=results, recall=recall, returned=returned, fallback=empty)
+
     # -- lifecycle driven from the host (Rotate / Migrate / Retire), mirrored into the GPU state
     def rotateKeyOnly(self) -> int:
         v = self.keys.rotate_key_only()

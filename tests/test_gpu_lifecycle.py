@@ -309,3 +309,44 @@ def test_large_batch_with_a_non_finite_query_is_rejected_by_the_device_check(wor
         assert np.array_equal(again["top_ids"], ok["top_ids"])
     finally:
         ctx.close()
+
+
+def test_run_queries_max_k_token_fallback_and_per_k_recall(world_factory):
+    """FSA.runQueries (FSA:622-748): one token at MAX_K, per-K prefix metrics against ground truth, and the probes-only fallback
+    max(2p, 4) for queries whose first search came back empty (here: every candidate of the first pass is deleted)."""
+    w = world_factory(**W1)
+    sys_ = make_system(w)
+    try:
+        sys_.batchInsert(w.base, ivs=w.iv)
+        sys_.finalizeForSearch()
+        kv = (1, 10, 20)
+        gt = sys_.gpu.groundtruth(w.base.astype(np.float32), w.queries.astype(np.float32), max(kv))
+        out = sys_.runQueries(w.queries, w.g.dim, gt, kv)
+        assert out["fallback"] == [] and all(len(r) == max(kv) for r in out["results"])
+        codes = O.tokengen_batch(w.queries, w.g)
+        for q in range(w.queries.shape[0]):
+            ref = O.search(w.ix, w.store, w.queries[q], codes[q], max(kv), 5, 20000, sys_.cfg.runtime.refinementLimit)
+            assert [int(r.id) for r in out["results"][q]] == ref["top_ids"].tolist()
+            for k in kv:                                              # prefix metrics: recall@K on the first K of the MAX_K result
+                got = O.recall_at_k(gt[q, :k], ref["top_ids"], min(k, len(ref["top_ids"])), k)
+                assert 0.0 <= got <= 1.0
+        for k in kv:
+            ref_mean = np.mean([O.recall_at_k(gt[q, :k], np.array([int(r.id) for r in out["results"][q]], dtype=np.int32), min(k, max(kv)), k)
+                                for q in range(w.queries.shape[0])])
+            assert abs(out["recall"][k] - ref_mean) < 1e-12 and out["returned"][k] == k
+        assert sys_.index.effectiveMaxProbes() == 5                    # overrides cleared (FSA:745-746)
+        # fallback: delete everything query 0 reaches with 5 probes; with max(2*5, 4) = 10 probes it finds other candidates
+        first = sys_.index.lookupCandidatesWithScores(sys_.createToken(w.queries[0], 10, w.g.dim), limit=100000)
+        deleted = np.zeros(w.cfg.N, dtype=np.uint8)
+        deleted[[i for i, _ in first]] = 1
+        sys_.gpu.deleted_set(deleted)
+        out2 = sys_.runQueries(w.queries[:3], w.g.dim, None, (10,))
+        assert 0 in out2["fallback"]
+        ixd = O.Index(w.ix.g, w.ix.N, w.ix.P, w.ix.min_key, w.ix.max_key, w.ix.rep, w.ix.ids, deleted)
+        std = O.Store(w.store.dim, w.store.iv, w.store.ct, w.store.key_version, w.store.keys, deleted)
+        ref10 = O.search(ixd, std, w.queries[0], codes[0], 10, 10, 20000, sys_.cfg.runtime.refinementLimit)
+        assert [int(r.id) for r in out2["results"][0]] == ref10["top_ids"].tolist()
+        assert sys_.evalSimple(w.queries[1], 10, w.g.dim) == out2["results"][1]
+    finally:
+        sys_.gpu.deleted_set(None)
+        sys_.shutdown()
