@@ -151,7 +151,7 @@ int launch_refine_group(cudaStream_t s, const StoreView &sv, const RefineParams 
 // from shared memory.  Authentication (GHASH + tag) is done beforehand by refine_verify_kernel.
 // AES uses one T-table (Te0) replicated for the 32 banks so every lookup is conflict free; Te1..3 are rotations.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int RF_THREADS = 1024;   // one CTA per SM: the 64 KB-aligned AES table costs up to 128 KB of shared memory
+constexpr int RF_THREADS = 768;    // one CTA per SM (the 64 KB-aligned AES table costs up to 128 KB of shared memory); 24 warps measured best of 16..32
 constexpr int RF_WARPS = RF_THREADS / 32;
 constexpr int DBG_THREADS = 256;
 constexpr int DBG_WARPS = DBG_THREADS / 32;
