@@ -336,7 +336,7 @@ __device__ __forceinline__ bool warp_decrypt_record_ctr(const StoreView &sv, con
 // AAD blocks ("id:<id>|v:<ver>|d:<dim>", EP:80-83), the ciphertext blocks and the length block; tag = GHASH ^ E_K(J0)
 // (NIST SP 800-38D).  Writes one verdict per distinct record: OK / TAG_FAIL (NO_KEY is the preset default).
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int VF_THREADS = 384;
+constexpr int VF_THREADS = 256;
 
 struct ShoupSmem {
     const uint4 *t;   // [256][16] byte-major
