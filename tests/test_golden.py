@@ -66,3 +66,46 @@ def test_cuda_path_reproduces_golden():
             assert np.array_equal(f["verdict"][q, :G["ncand"][q]], G["verdict"][q, :G["ncand"][q]])
     finally:
         ctx.close()
+
+
+# ---- SURVEY 8(f) additions: Migrate, ground truth, recall (tests/golden/fspann_8f.npz, made by make_golden_8f.py)
+F8 = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fspann_8f.npz"))
+
+
+def test_oracle_reproduces_golden_8f():
+    keys = {1: G["key1"].tobytes(), 2: G["key2"].tobytes(), 3: F8["key3"].tobytes()}
+    st = O.Store(dim, G["iv"].copy(), G["ct"].copy(), G["key_version"].copy(), keys)
+    ids = F8["migrate_ids"]
+    assert O.migrate(st, np.where((ids >= 0) & (ids < N), ids, -1), F8["fresh_ivs"], 3) == int(F8["migrated"])
+    assert np.array_equal(st.iv, F8["iv_after"]) and np.array_equal(st.ct, F8["ct_after"]) and np.array_equal(st.key_version, F8["ver_after"])
+    gt, d2 = O.groundtruth(G["base"].astype(np.float32), G["queries"].astype(np.float32), 8)
+    assert np.array_equal(gt, F8["gt_ids"]) and np.array_equal(d2.view(np.uint64), F8["gt_d2"].view(np.uint64))
+    rec = [O.recall_at_k(gt[q, :5], G["top_ids"][q], int(G["nret"][q]), 5) for q in range(Q)]
+    assert np.array_equal(np.array(rec), F8["recall5"])
+
+
+@pytest.mark.gpu
+def test_cuda_path_reproduces_golden_8f():
+    from fspann_query_system_b200.gpu import GpuContext
+    ctx = GpuContext(0)
+    try:
+        ctx.routing_upload(dim, T, D, m, lam, G["alpha"], G["r"], G["omega"], G["min_key"], G["max_key"], G["rep"], G["ids"])
+        for v, kk in ((1, G["key1"]), (2, G["key2"]), (3, F8["key3"])):
+            ctx.keys_set(v, kk.tobytes())
+        ctx.store_upload(dim, G["iv"], G["ct"], G["key_version"])
+        out = ctx.migrate(F8["migrate_ids"], F8["fresh_ivs"], 3)
+        assert out["count"] == int(F8["migrated"])
+        sel = np.nonzero(out["reencrypted"])[0]
+        rows = F8["migrate_ids"][sel]
+        assert np.array_equal(out["iv"][sel], F8["iv_after"][rows]) and np.array_equal(out["ct"][sel], F8["ct_after"][rows])
+        assert (F8["ver_after"][rows] == 3).all() and len(sel) == int((F8["ver_after"] != G["key_version"]).sum())
+        s = ctx.search_batch(G["queries"], k, probes, hard_cap, B)               # routing-ciphertext orthogonality: the golden results hold
+        for q in range(Q):
+            nr = G["nret"][q]
+            assert s["n_ret"][q] == nr and np.array_equal(s["top_ids"][q, :nr], G["top_ids"][q, :nr])
+        gt, d2 = ctx.groundtruth(G["base"].astype(np.float32), G["queries"].astype(np.float32), 8, want_d2=True)
+        assert np.array_equal(gt, F8["gt_ids"]) and np.array_equal(d2.view(np.uint64), F8["gt_d2"].view(np.uint64))
+        rec = ctx.recall_batch(gt[:, :5].copy(), G["top_ids"], 5, G["nret"])
+        assert np.array_equal(rec, F8["recall5"])
+    finally:
+        ctx.close()
