@@ -211,8 +211,18 @@ class PartitionedIndexService:
         self.lastTouchedIds = out["cand_ids"][0, :n].tolist()
         return list(zip(out["cand_ids"][0, :n].tolist(), out["cand_scores"][0, :n].tolist()))
 
+    def lookupCandidateIds(self, token: QueryToken, limit: int | None = None):
+        """PIS:459-582, the ids-only twin of lookupCandidatesWithScores (same traversal and order)."""
+        return [i for i, _ in self.lookupCandidatesWithScores(token, limit)]
+
     def getLastRawCandidateCount(self):
         return self.lastRawVisited
+
+    def getLastTouchedIds(self):        # PIS:860-866
+        return list(self.lastTouchedIds)
+
+    def getLastTouchedCount(self):
+        return len(self.lastTouchedIds)
 
 
 class QueryTokenFactory:
