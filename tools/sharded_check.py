@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Database-sharded search (BASELINE config 4) over N GPUs: parity with a single unsharded store + timing.
 
-  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tools/sharded_check.py [--n 1000000]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tools/sharded_check.py [--records 1000000]
 
 Every rank holds the replicated routing index and the store shard of a contiguous global-id range; DeviceShardedSearcher routes
 query-parallel, all-gathers the candidate lists, refines its shard, all-gathers + merges the per-shard top-k (NCCL).  Rank 0 also
@@ -25,7 +25,7 @@ from fspann_query_system_b200.gpu import GpuContext  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="C2")
-    ap.add_argument("--n", type=int, default=0)
+    ap.add_argument("--records", type=int, default=0, help="override N")
     ap.add_argument("--steps", type=int, default=5)
     args = ap.parse_args()
     real_stdout = os.fdopen(os.dup(1), "w"); os.dup2(2, 1)
@@ -34,8 +34,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
     cfg = WL.CONFIGS[args.config]
-    if args.n:
-        cfg = cfg.scaled(N=args.n)
+    if args.records:
+        cfg = cfg.scaled(N=args.records)
     base = WL.base_vectors(cfg)
     alpha, r, omega = HS.build_gfunctions(base[:HS.MIN_SAMPLE_SIZE], cfg.m, cfg.lam, cfg.seed, cfg.T, cfg.D)
     gpu = GpuContext(lr)
