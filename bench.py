@@ -339,7 +339,7 @@ def main():
         step_host(Wm + i)
     f1.record(stream)
     barrier()
-    e2e_ms = max(f0.elapsed_time(f1), (time.perf_counter() - t_wall) * 1e3 * 0.0)
+    e2e_ms = f0.elapsed_time(f1)
     e2e_wall_ms = (time.perf_counter() - t_wall) * 1e3
     clocks = sampler.stop()
     checksum = int(h_ids.to(torch.int64).sum().item())

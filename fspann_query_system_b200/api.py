@@ -125,19 +125,27 @@ class PartitionedIndexService:
         self._vecs.append(v)
 
     def insert_many(self, ids: np.ndarray, vectors: np.ndarray):
+        """Bulk form of insert(): APPENDS to what is already staged (a second batchInsert continues the index, FSA:501,515)."""
         if self.frozen:
             raise IllegalStateError("Index already finalized")
-        self._bulk = (np.asarray(ids, dtype=np.int32), np.ascontiguousarray(vectors, dtype=np.float64))
+        ids, vectors = np.asarray(ids, dtype=np.int32), np.ascontiguousarray(vectors, dtype=np.float64)
+        if hasattr(self, "_bulk"):
+            if vectors.shape[1] != self._bulk[1].shape[1]:
+                raise IllegalArgumentError(f"Mixed dimensions not supported in single index: got {vectors.shape[1]}, expected {self._bulk[1].shape[1]}")
+            ids, vectors = np.concatenate([self._bulk[0], ids]), np.concatenate([self._bulk[1], vectors])
+        self._bulk = (ids, vectors)
 
     def finalizeForSearch(self):
         """PIS:789-845: code every staged vector for every (t,d) (on the GPU, same kernel as TokenGen), build the greedy
         partitions in staged order, freeze, upload the routing state."""
         if self.frozen:
             return
-        if hasattr(self, "_bulk"):
-            ids, vecs = self._bulk
-        else:
-            ids, vecs = np.asarray(self._ids, dtype=np.int32), (np.stack(self._vecs) if self._vecs else np.zeros((0, 1)))
+        ids, vecs = np.asarray(self._ids, dtype=np.int32), (np.stack(self._vecs) if self._vecs else None)
+        if hasattr(self, "_bulk"):                       # bulk-staged rows come first, single insert()s after them
+            ids = np.concatenate([self._bulk[0], ids])
+            vecs = self._bulk[1] if vecs is None else np.concatenate([self._bulk[1], vecs])
+        if vecs is None:
+            vecs = np.zeros((0, 1))
         n = ids.shape[0]
         if n < HS.MIN_SAMPLE_SIZE:
             raise IllegalStateError(f"Cannot finalize index: only {n} samples collected (< MIN_SAMPLE_SIZE)")   # PIS:803-808
@@ -190,8 +198,8 @@ class PartitionedIndexService:
 
     # -- Route
     def lookupCandidatesWithScores(self, token: QueryToken, limit: int | None = None):
-        """PIS:592-715.  Returns [(id, hammingDist)] for the first `limit` candidates (default: refinementLimit) in the
-        reference's order; getLastRawCandidateCount / getLastTouchedCount as in the reference."""
+        """PIS:592-715.  Returns [(id, hammingDist)] of every unique candidate in the reference's order (or the first `limit`);
+        getLastRawCandidateCount / getLastTouchedIds / getLastTouchedCount cover all of them, as in the reference."""
         if token is None:
             raise IllegalArgumentError("token")
         if not self.frozen:
@@ -202,13 +210,17 @@ class PartitionedIndexService:
             raise IllegalStateError(f"Token tables mismatch: token={token.bitCodes.shape[0]} index={self.cfg.paper.tables}")
         if token.dimension != self.gpu.dim:
             return []
-        B = limit if limit is not None else self.cfg.runtime.refinementLimit
         codes = token.bitCodes.reshape(1, -1, self.gpu.W)
-        out = self.gpu.route_batch(codes, self.effectiveMaxProbes(), self.hardCap(), B, self.cfg.runtime.hammingPrefilterThreshold)
+        # the reference returns ALL unique candidates (<= HARD_CAP + 63), score-sorted, and records every one of them as touched
+        # (PIS:690-702: result.size() = bestScore.size()); `limit` only trims what this call hands back
+        full = min(self.hardCap() + 64, self.cfg.paper.tables * self.cfg.paper.divisions * max(self.effectiveMaxProbes(), 1) * 64)
+        out = self.gpu.route_batch(codes, self.effectiveMaxProbes(), self.hardCap(), max(full, 1), self.cfg.runtime.hammingPrefilterThreshold)
         n = int(out["n_cand"][0])
         self.lastRawVisited = int(out["raw_seen"][0])
         self.lastUnique = int(out["unique"][0])
         self.lastTouchedIds = out["cand_ids"][0, :n].tolist()
+        if limit is not None:
+            n = min(n, limit)
         return list(zip(out["cand_ids"][0, :n].tolist(), out["cand_scores"][0, :n].tolist()))
 
     def lookupCandidateIds(self, token: QueryToken, limit: int | None = None):
@@ -227,6 +239,8 @@ class PartitionedIndexService:
 
 class QueryTokenFactory:
     def __init__(self, gpu: GpuContext, keys: HS.KeyManager, cfg: SystemConfig, registry: GFunctionRegistry, rng=None):
+        """rng: TEST-ONLY deterministic IV source (an object with .bytes(n)).  The default draws every 96-bit IV from the operating
+        system's CSPRNG like the reference's SecureRandom (QTF:152-154): a (key, IV) pair must never repeat under AES-GCM."""
         self.gpu, self.keys, self.cfg, self.registry = gpu, keys, cfg, registry
         self.rng = rng
 
@@ -246,6 +260,15 @@ class QueryTokenFactory:
         iv = self.rng.bytes(12) if self.rng is not None else os.urandom(12)
         ct = HS.encrypt_query(vec, self.keys.get_version(version), iv)
         return QueryToken(codes, iv, ct, max(1, topK), max(1, pc.tables), vec.shape[0], version, pc.lam, f"dim_{vec.shape[0]}_v{version}")
+
+    def derive(self, tok: QueryToken, newTopK: int) -> QueryToken:
+        """QTF:182-200: the same token (codes, IV, ciphertext, version) with another topK -- no new TokenGen, no new encryption."""
+        if tok is None:
+            raise IllegalArgumentError("token is null")
+        if newTopK <= 0:
+            raise IllegalArgumentError("newTopK must be > 0")
+        return QueryToken(tok.getBitCodes(), tok.iv, tok.encryptedQuery, newTopK, tok.numTables, tok.dimension, tok.version, tok.lam,
+                          tok.encryptionContext)
 
 
 class QueryServiceImpl:
@@ -285,14 +308,22 @@ class QueryServiceImpl:
         return res[0]
 
     def searchBatch(self, tokens):
+        """QueryServiceImpl.search for a list of tokens.  Routes on each token's OWN codes (token.getBitCodes(), PIS:600) through
+        fspann_search_tokens -- TokenGen ran once, when the token was created -- and refines against the decrypted query."""
         if not self.index.isFrozen():
             raise IllegalStateError("Index not finalized")
         self.touchedThisSession = set()
-        qs, ks, keep = [], [], []
+        qs, cs, ks, keep = [], [], [], []
         for i, t in enumerate(tokens):
-            q = None if t is None else self._decrypt_token(t)
-            if q is not None:
-                qs.append(q); ks.append(t.topK); keep.append(i)
+            if t is None:
+                continue
+            if t.bitCodes is None:
+                raise IllegalStateError("MSANNP violation: QueryToken missing BitSet codes")       # PIS:604-606
+            if t.bitCodes.shape[0] != self.cfg.paper.tables:
+                raise IllegalStateError(f"Token tables mismatch: token={t.bitCodes.shape[0]} index={self.cfg.paper.tables}")
+            q = self._decrypt_token(t)
+            if q is not None and t.dimension == self.gpu.dim:
+                qs.append(q); cs.append(t.bitCodes.reshape(-1, self.gpu.W)); ks.append(t.topK); keep.append(i)
         results = [[] for _ in tokens]
         if not qs:
             return results
@@ -300,9 +331,11 @@ class QueryServiceImpl:
         if len(set(ks)) != 1:
             raise IllegalArgumentError("searchBatch needs one topK per batch (derive tokens per K like FSA:634)")
         rt = self.cfg.runtime
-        out = self.gpu.search_batch(np.stack(qs), k, self.index.effectiveMaxProbes(), self.index.hardCap(),
-                                    self.getEffectiveRefinementLimit(), rt.hammingPrefilterThreshold)
-        self.index.clearProbeOverride()                           # QSI:343 finally
+        try:
+            out = self.gpu.search_tokens(np.stack(cs), np.stack(qs), k, self.index.effectiveMaxProbes(), self.index.hardCap(),
+                                         self.getEffectiveRefinementLimit(), rt.hammingPrefilterThreshold)
+        finally:
+            self.index.clearProbeOverride()                       # QSI:342-346: cleared in `finally`, also when the search throws
         for j, i in enumerate(keep):
             n = int(out["n_ret"][j])
             results[i] = [QueryResult(str(int(out["top_ids"][j, r])), float(out["top_dist"][j, r])) for r in range(n)]
@@ -324,7 +357,11 @@ class ForwardSecureANNSystem:
     Keys are derived by the host KeyManager; bulk encryption at insert, the index build and Migrate run on the device
      and the host keeps the persistent mirror of the encrypted store."""
 
-    def __init__(self, cfg: SystemConfig, dim: int, master_key: bytes, gfunctions, device: int = 0, iv_seed: int = 0, debug: bool = False):
+    def __init__(self, cfg: SystemConfig, dim: int, master_key: bytes, gfunctions, device: int = 0, iv_seed: int | None = None,
+                 debug: bool = False):
+        """iv_seed=None (default): every record and query IV comes from the OS CSPRNG, like the reference's SecureRandom (AGC:66-67,
+        QTF:152-154).  iv_seed=<int> is a TEST-ONLY switch that makes the IVs reproducible; never use it with a real master key --
+        two runs would then encrypt different data under the same (key, IV), which breaks AES-GCM."""
         self.cfg, self.dim = cfg, dim
         self.gpu = GpuContext(device, debug=debug)
         self.keys = HS.KeyManager(master_key)
@@ -333,24 +370,38 @@ class ForwardSecureANNSystem:
         alpha, r, omega = gfunctions
         self.registry.initialize(dim, pc.m, pc.lam, pc.tables, pc.divisions, alpha, r, omega)
         self.index = PartitionedIndexService(self.gpu, cfg, self.registry)
-        self.tokenFactory = QueryTokenFactory(self.gpu, self.keys, cfg, self.registry, np.random.default_rng(iv_seed + 1))
+        self.tokenFactory = QueryTokenFactory(self.gpu, self.keys, cfg, self.registry,
+                                              None if iv_seed is None else np.random.default_rng(iv_seed + 1))
         self.queryService = QueryServiceImpl(self.index, self.gpu, self.keys, cfg)
         self.iv_seed = iv_seed
+        self.store_iv = self.store_ct = self.store_ver = None
         self.gpu.keys_set(1, self.keys.derive(1))
 
     def batchInsert(self, vectors: np.ndarray, ivs: np.ndarray | None = None):
+        """FSA:479-560: ids continue the ordinals of what was inserted before (FSA:501,515), so a second call APPENDS.  `ivs`
+        (uint8 [n,12]) must come from a CSPRNG; when omitted they are drawn from os.urandom (or the test-only seeded generator)."""
         vectors = np.ascontiguousarray(vectors, dtype=np.float64)
         if vectors.shape[1] != self.dim:
             raise IllegalArgumentError(f"Expected vector length {self.dim}")
+        if self.index.isFrozen():
+            raise IllegalStateError("Index already finalized")
         n = vectors.shape[0]
-        ids = np.arange(n, dtype=np.int32)                         # FSA:501,515 id = ordinal
+        n0 = 0 if getattr(self, "store_iv", None) is None else self.store_iv.shape[0]
+        ids = np.arange(n0, n0 + n, dtype=np.int32)                # FSA:501,515 id = ordinal
         if ivs is None:
-            from . import workloads as WL
-            ivs = WL.record_ivs(n, self.iv_seed)
+            if self.iv_seed is None:
+                ivs = np.frombuffer(os.urandom(12 * n), dtype=np.uint8).reshape(n, 12)
+            else:
+                from . import workloads as WL
+                ivs = WL.record_ivs(n, self.iv_seed + n0)
         v = self.keys.current
-        self.store_iv = np.ascontiguousarray(ivs, dtype=np.uint8).copy()
-        self.store_ct = self.gpu.encrypt_batch(ids, vectors, self.store_iv, v)      # encryptToPoint (AGC:55-112) on the device
-        self.store_ver = np.full(n, v, dtype=np.int32)
+        ivs = np.ascontiguousarray(ivs, dtype=np.uint8).copy()
+        ct = self.gpu.encrypt_batch(ids, vectors, ivs, v)          # encryptToPoint (AGC:55-112) on the device
+        if n0:
+            self.store_iv, self.store_ct = np.concatenate([self.store_iv, ivs]), np.concatenate([self.store_ct, ct])
+            self.store_ver = np.concatenate([self.store_ver, np.full(n, v, dtype=np.int32)])
+        else:
+            self.store_iv, self.store_ct, self.store_ver = ivs, ct, np.full(n, v, dtype=np.int32)
         self.gpu.store_upload(self.dim, self.store_iv, self.store_ct, self.store_ver)
         self.index.insert_many(ids, vectors)
 

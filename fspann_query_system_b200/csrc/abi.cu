@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <map>
+#include <mutex>
 
 #include "fspann_internal.cuh"
 
@@ -24,7 +25,7 @@ struct DevBuf {
 
 struct fspann_ctx {
     int device = 0;
-    int sm_count = 148;
+    int sm_count = 1;                            // multiProcessorCount of ctx->device (set by fspann_ctx_create)
     cudaStream_t stream = nullptr;
     int32_t *h_pin = nullptr;                    // pinned host staging for the per-batch retry decision (n_ret, n_decrypted, flags)
     size_t h_pin_ints = 0;
@@ -51,7 +52,7 @@ struct fspann_ctx {
     int last_route_path = 0;     // 1 = shared-memory fast path, 2 = general path
     bool last_queries_finite = true;
     DevBuf s_queries, s_codes, s_cand_ids, s_cand_sc, s_ncand, s_raw, s_uniq_cnt, s_route_scratch, s_overflow;
-    DevBuf s_rec_verdict, s_qf32, s_qu8, s_f32_exact, s_vorder, s_voff;
+    DevBuf s_rec_verdict, s_qf32, s_qu8, s_f32_exact, s_vorder, s_voff, s_qfinite, s_retry_out, s_codes_in;
     DevKeyRing ring_host{};
     int32_t *want_rank = nullptr;
     DevBuf s_cnt, s_flag, s_fill, s_uniq, s_pairs, s_bsums, s_totals, s_dist, s_verdict;
@@ -123,8 +124,8 @@ struct RkHost { const uint32_t *r; uint32_t operator()(int i) const { return r[i
 // Rebuilds the device key ring (round keys) and GHASH key-power tables from ctx->keys.
 int rebuild_keys(fspann_ctx *ctx) {
     static uint32_t te0[256];
-    static bool te_init = false;
-    if (!te_init) { aes_make_te0(te0); te_init = true; }
+    static std::once_flag te_once;                 // contexts may be created from several host threads (one per GPU)
+    std::call_once(te_once, [] { aes_make_te0(te0); });
     DevKeyRing ring;
     memset(&ring, 0, sizeof ring);
     const int dim = ctx->sv.dim > 0 ? ctx->sv.dim : 0;
@@ -187,7 +188,7 @@ int run_tokengen(fspann_ctx *ctx, int64_t Q, const double *d_queries, uint64_t *
     ENSURE(ctx->s_tg_qf, sizeof(float) * (size_t)Q * (((size_t)ctx->rv.dim + 3) / 4 * 4));
     ENSURE(ctx->s_tg_norm, sizeof(float) * (size_t)Q);
     LAUNCHED(launch_tokengen(ctx->stream, ctx->rv, Q, d_queries, d_codes, (int32_t *)ctx->s_tg_work.p, (unsigned long long *)ctx->s_tg_list.p, cap,
-                             (float *)ctx->s_tg_qf.p, (float *)ctx->s_tg_norm.p, ctx->opt_tokengen_exact != 0));
+                             (float *)ctx->s_tg_qf.p, (float *)ctx->s_tg_norm.p, ctx->opt_tokengen_exact != 0, ctx->sm_count));
     return 0;
 }
 
@@ -257,8 +258,11 @@ int do_refine(fspann_ctx *ctx, int64_t Q, const double *d_queries, const int32_t
     ENSURE(ctx->s_qf32, sizeof(float) * (size_t)Q * sv.dim);
     ENSURE(ctx->s_qu8, (size_t)Q * sv.dim + 16);
     ENSURE(ctx->s_f32_exact, 4 * sizeof(int32_t));
+    ENSURE(ctx->s_qfinite, (size_t)Q + 16);
     p.queries_f32 = (const float *)ctx->s_qf32.p; p.queries_u8 = (const uint8_t *)ctx->s_qu8.p; p.f32_exact = (const int32_t *)ctx->s_f32_exact.p;
-    LAUNCHED(launch_queries_to_f32(ctx->stream, d_queries, (float *)ctx->s_qf32.p, (uint8_t *)ctx->s_qu8.p, Q * (int64_t)sv.dim, (int32_t *)ctx->s_f32_exact.p));
+    p.qfinite = (const uint8_t *)ctx->s_qfinite.p;
+    LAUNCHED(launch_queries_to_f32(ctx->stream, d_queries, (float *)ctx->s_qf32.p, (uint8_t *)ctx->s_qu8.p, Q, sv.dim, (int32_t *)ctx->s_f32_exact.p,
+                                   (uint8_t *)ctx->s_qfinite.p));
     // unknown / retired key version is the default verdict (KRS:82-88); the verify kernel overwrites it per live version
     CK(cudaMemsetAsync(p.rec_verdict, FSPANN_V_NO_KEY, (size_t)std::min<int64_t>(n1, total + 1), ctx->stream));
     LAUNCHED(launch_refine_group(ctx->stream, sv, p));
@@ -297,8 +301,9 @@ int fspann_ctx_create(int device, fspann_ctx **out) {
     fspann_ctx *ctx = new fspann_ctx();
     ctx->device = device;
     if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return FSPANN_E_CUDA; }
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    ctx->sm_count = cur_sm_count();
+    // > 48 KB of dynamic shared memory is a per-device opt-in of each kernel: configure THIS device (a process may hold one context per GPU)
+    if (configure_tokengen_kernels() || configure_route_kernels() || configure_refine_kernels()) { delete ctx; return FSPANN_E_CUDA; }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return FSPANN_E_CUDA; }
     for (int i = 0; i < 7; i++) cudaEventCreate(&ctx->ev[i]);
     uint32_t te0[256];
@@ -317,7 +322,7 @@ void fspann_ctx_destroy(fspann_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    DevBuf *bufs[] = {&ctx->d_alpha_f, &ctx->d_alpha_norm, &ctx->s_vorder, &ctx->s_voff, &ctx->s_tg_work, &ctx->s_tg_list, &ctx->s_tg_qf, &ctx->s_tg_norm, &ctx->d_alpha, &ctx->d_r, &ctx->d_omega, &ctx->d_keys, &ctx->d_rep, &ctx->d_ids, &ctx->d_deleted, &ctx->d_rec,
+    DevBuf *bufs[] = {&ctx->d_alpha_f, &ctx->d_alpha_norm, &ctx->s_vorder, &ctx->s_voff, &ctx->s_qfinite, &ctx->s_retry_out, &ctx->s_codes_in, &ctx->s_tg_work, &ctx->s_tg_list, &ctx->s_tg_qf, &ctx->s_tg_norm, &ctx->d_alpha, &ctx->d_r, &ctx->d_omega, &ctx->d_keys, &ctx->d_rep, &ctx->d_ids, &ctx->d_deleted, &ctx->d_rec,
                       &ctx->d_keyring, &ctx->d_hpow, &ctx->d_shoup, &ctx->s_rec_verdict, &ctx->s_qf32, &ctx->s_qu8, &ctx->s_f32_exact, &ctx->d_te0, &ctx->d_touched, &ctx->s_queries, &ctx->s_codes, &ctx->s_cand_ids,
                       &ctx->s_cand_sc, &ctx->s_ncand, &ctx->s_raw, &ctx->s_uniq_cnt, &ctx->s_route_scratch, &ctx->s_overflow, &ctx->s_cnt,
                       &ctx->s_flag, &ctx->s_fill, &ctx->s_uniq, &ctx->s_pairs, &ctx->s_bsums, &ctx->s_totals, &ctx->s_dist, &ctx->s_verdict,
@@ -868,9 +873,10 @@ int fspann_refine_batch_ex(fspann_ctx *ctx, int64_t Q, const double *queries, co
     return FSPANN_OK;
 }
 
-// One full pass (tokengen -> route -> refine -> counters) over device-resident queries.
-static int search_pass(fspann_ctx *ctx, int64_t Q, const double *d_queries, int k, int probes, int64_t hard_cap, int B, int retried,
-                       int32_t *d_topk_ids, double *d_topk_dist, int32_t *d_nret, int64_t *d_counters, bool main_pass) {
+// One full pass (tokengen -> route -> refine -> counters) over device-resident queries.  d_codes_in != nullptr: the token's own
+// codes are routed on (PIS:600 token.getBitCodes()) and TokenGen does not run.
+static int search_pass(fspann_ctx *ctx, int64_t Q, const double *d_queries, const uint64_t *d_codes_in, int k, int probes, int64_t hard_cap, int B,
+                       int retried, int32_t *d_topk_ids, double *d_topk_dist, int32_t *d_nret, int64_t *d_counters, bool main_pass) {
     const RoutingView &rv = ctx->rv;
     DevBuf &b_codes = main_pass ? ctx->s_codes : ctx->r_codes;
     DevBuf &b_cid = main_pass ? ctx->s_cand_ids : ctx->t_cand_ids;
@@ -879,25 +885,110 @@ static int search_pass(fspann_ctx *ctx, int64_t Q, const double *d_queries, int 
     DevBuf &b_raw = main_pass ? ctx->s_raw : ctx->t_raw;
     DevBuf &b_un = main_pass ? ctx->s_uniq_cnt : ctx->t_uniq_cnt;
     DevBuf &b_nd = main_pass ? ctx->s_ndec : ctx->t_ndec;
-    ENSURE(b_codes, sizeof(uint64_t) * (size_t)Q * rv.TD * rv.W);
+    if (!d_codes_in) ENSURE(b_codes, sizeof(uint64_t) * (size_t)Q * rv.TD * rv.W);
     ENSURE(b_cid, sizeof(int32_t) * (size_t)Q * B); ENSURE(b_csc, sizeof(int32_t) * (size_t)Q * B);
     ENSURE(b_nc, sizeof(int32_t) * (size_t)Q); ENSURE(b_raw, sizeof(int32_t) * (size_t)Q); ENSURE(b_un, sizeof(int32_t) * (size_t)Q);
     ENSURE(b_nd, sizeof(int32_t) * (size_t)Q);
     int rc;
     if (main_pass) { rc = record_ev(ctx, 0); if (rc) return rc; }
-    { int rc_ = run_tokengen(ctx, Q, d_queries, (uint64_t *)b_codes.p); if (rc_) return rc_; }
+    if (!d_codes_in) { int rc_ = run_tokengen(ctx, Q, d_queries, (uint64_t *)b_codes.p); if (rc_) return rc_; }
     if (main_pass) { rc = record_ev(ctx, 1); if (rc) return rc; }
-    rc = do_route(ctx, Q, (const uint64_t *)b_codes.p, probes, hard_cap, B, (int32_t *)b_cid.p, (int32_t *)b_csc.p, (int32_t *)b_nc.p,
-                  (int32_t *)b_raw.p, (int32_t *)b_un.p);
+    rc = do_route(ctx, Q, d_codes_in ? d_codes_in : (const uint64_t *)b_codes.p, probes, hard_cap, B, (int32_t *)b_cid.p, (int32_t *)b_csc.p,
+                  (int32_t *)b_nc.p, (int32_t *)b_raw.p, (int32_t *)b_un.p);
     if (rc) return rc;
     if (main_pass) { rc = record_ev(ctx, 2); if (rc) return rc; }
     rc = do_refine(ctx, Q, d_queries, (const int32_t *)b_cid.p, (const int32_t *)b_nc.p, B, k, d_topk_ids, d_topk_dist, d_nret, (int32_t *)b_nd.p, main_pass);
     if (rc) return rc;
     if (d_counters)
         LAUNCHED(launch_counters(ctx->stream, Q, (const int32_t *)b_raw.p, (const int32_t *)b_un.p, (const int32_t *)b_nd.p, d_nret,
-                                 (const int32_t *)b_nc.p, retried, d_counters));
+                                 (const int32_t *)b_nc.p, retried, d_counters, (const uint8_t *)ctx->s_qfinite.p));
     return 0;
 }
+
+namespace {
+struct HostOut {            // host result buffers of the host-pointer entry points (nullptr members are skipped)
+    int32_t *topk_ids; double *topk_dist; int32_t *n_ret; int64_t *counters;
+};
+
+int copy_results(fspann_ctx *ctx, int64_t Q, int k, const HostOut &h, const int32_t *d_ids, const double *d_dist, const int32_t *d_nret, const int64_t *d_cnt) {
+    CK(cudaMemcpyAsync(h.topk_ids, d_ids, sizeof(int32_t) * (size_t)Q * k, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(h.topk_dist, d_dist, sizeof(double) * (size_t)Q * k, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(h.n_ret, d_nret, sizeof(int32_t) * (size_t)Q, cudaMemcpyDeviceToHost, ctx->stream));
+    if (h.counters && d_cnt) CK(cudaMemcpyAsync(h.counters, d_cnt, sizeof(int64_t) * FSPANN_COUNTERS * (size_t)Q, cudaMemcpyDeviceToHost, ctx->stream));
+    return 0;
+}
+
+// createToken + QueryServiceImpl.search for a batch whose queries (and optionally codes) are resident in HBM.
+//  * The adaptive retry (QSI:327-337, 444-447) is decided ON THE DEVICE (retry_select_kernel): the host reads back two integers
+//    (how many queries retry, whether a query held NaN/Inf) together with the results, so the common no-retry batch costs ONE
+//    stream synchronisation; only a batch that does retry runs the second pass (10 probes, those rows only) and copies again.
+//  * host != nullptr: results are copied to the host buffers (the host-pointer entry points); otherwise nothing is copied and,
+//    without allow_retry, nothing synchronises.
+//  * reject_nonfinite: fail the call with FSPANN_E_ARG when a query holds NaN/Inf (createToken throws, Coding:357-359); otherwise such
+//    a query just returns empty and touches nothing (QSI:137).
+int search_core(fspann_ctx *ctx, int64_t Q, const double *d_queries, const uint64_t *d_codes_in, int k, int probes, int64_t hard_cap, int B,
+                bool allow_retry, bool reject_nonfinite, int32_t *d_topk_ids, double *d_topk_dist, int32_t *d_n_ret, int64_t *d_counters,
+                const HostOut *host) {
+    if (probes <= 0) probes = 5;   // DEFAULT_MAX_PROBES (PIS:93) when no override is configured (PIS:880-888)
+    const int64_t l0 = ctx->launches;
+    int rc = search_pass(ctx, Q, d_queries, d_codes_in, k, probes, hard_cap, B, 0, d_topk_ids, d_topk_dist, d_n_ret, d_counters, true);
+    if (rc) return rc;
+    ctx->ev_valid = true;
+    const bool need_flags = allow_retry || reject_nonfinite;
+    if (need_flags) {
+        if (!ctx->h_pin) { CK(cudaHostAlloc((void **)&ctx->h_pin, sizeof(int32_t) * 16, cudaHostAllocDefault)); ctx->h_pin_ints = 16; }
+        ENSURE(ctx->r_rows, sizeof(int32_t) * (size_t)Q);
+        ENSURE(ctx->s_retry_out, sizeof(int32_t) * 4);
+        LAUNCHED(launch_retry_select(ctx->stream, Q, k, d_n_ret, (const int32_t *)ctx->s_ndec.p, (const int32_t *)ctx->s_f32_exact.p,
+                                     (int32_t *)ctx->r_rows.p, (int32_t *)ctx->s_retry_out.p));
+        CK(cudaMemcpyAsync(ctx->h_pin, ctx->s_retry_out.p, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (host) { rc = copy_results(ctx, Q, k, *host, d_topk_ids, d_topk_dist, d_n_ret, d_counters); if (rc) return rc; }
+    if (need_flags || host) CK(cudaStreamSynchronize(ctx->stream));
+    if (need_flags) {
+        ctx->last_queries_finite = ctx->h_pin[1] == 0;
+        if (reject_nonfinite && !ctx->last_queries_finite) return fail(ctx, FSPANN_E_ARG, "Vector contains NaN/Inf (Coding:357-359)");
+        const int64_t R = allow_retry ? ctx->h_pin[0] : 0;
+        if (R > 0) {
+            const int dim = ctx->rv.dim;
+            const size_t code_row = sizeof(uint64_t) * (size_t)ctx->rv.TD * ctx->rv.W;
+            ENSURE(ctx->r_queries, sizeof(double) * (size_t)R * dim);
+            ENSURE(ctx->r_topk_ids, sizeof(int32_t) * (size_t)R * k); ENSURE(ctx->r_topk_dist, sizeof(double) * (size_t)R * k);
+            ENSURE(ctx->r_nret, sizeof(int32_t) * (size_t)R); ENSURE(ctx->r_counters, sizeof(int64_t) * FSPANN_COUNTERS * (size_t)R);
+            const int32_t *rows = (const int32_t *)ctx->r_rows.p;
+            LAUNCHED(launch_gather_rows(ctx->stream, d_queries, ctx->r_queries.p, rows, R, sizeof(double) * dim, false));
+            const uint64_t *codes2 = nullptr;
+            if (d_codes_in) {
+                ENSURE(ctx->r_codes, code_row * (size_t)R);
+                LAUNCHED(launch_gather_rows(ctx->stream, d_codes_in, ctx->r_codes.p, rows, R, (int64_t)code_row, false));
+                codes2 = (const uint64_t *)ctx->r_codes.p;
+            }
+            rc = search_pass(ctx, R, (const double *)ctx->r_queries.p, codes2, k, 10, hard_cap, B, 1, (int32_t *)ctx->r_topk_ids.p,
+                             (double *)ctx->r_topk_dist.p, (int32_t *)ctx->r_nret.p, d_counters ? (int64_t *)ctx->r_counters.p : nullptr, false);
+            if (rc) return rc;
+            LAUNCHED(launch_gather_rows(ctx->stream, ctx->r_topk_ids.p, d_topk_ids, rows, R, sizeof(int32_t) * k, true));
+            LAUNCHED(launch_gather_rows(ctx->stream, ctx->r_topk_dist.p, d_topk_dist, rows, R, sizeof(double) * k, true));
+            LAUNCHED(launch_gather_rows(ctx->stream, ctx->r_nret.p, d_n_ret, rows, R, sizeof(int32_t), true));
+            if (d_counters)
+                LAUNCHED(launch_gather_rows(ctx->stream, ctx->r_counters.p, d_counters, rows, R, sizeof(int64_t) * FSPANN_COUNTERS, true));
+            if (host) { rc = copy_results(ctx, Q, k, *host, d_topk_ids, d_topk_dist, d_n_ret, d_counters); if (rc) return rc; }
+            CK(cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    ctx->last_call_launches = ctx->launches - l0;
+    return FSPANN_OK;
+}
+
+int check_search_args(fspann_ctx *ctx, int64_t Q, int k, int B) {
+    int rc = check_routing(ctx); if (rc) return rc;
+    rc = check_store(ctx); if (rc) return rc;
+    if (ctx->rv.n_ids <= 1 && ctx->rv.P <= 1) return fail(ctx, FSPANN_E_STATE, "Index not finalized: only GFunctions uploaded");
+    if (Q < 0) return fail(ctx, FSPANN_E_ARG, "negative batch size");
+    if (k <= 0) return fail(ctx, FSPANN_E_ARG, "topK must be > 0 (QTF:65)");
+    if (B <= 0) return fail(ctx, FSPANN_E_ARG, "refinementLimit must be > 0");
+    return 0;
+}
+}  // namespace
 
 int fspann_search_batch_dev(fspann_ctx *ctx, int64_t Q, const double *d_queries, int32_t k, int32_t probes, int64_t hard_cap, int32_t B,
                             int32_t ham_threshold, int32_t allow_retry, int32_t *d_topk_ids, double *d_topk_dist, int32_t *d_n_ret,
@@ -905,90 +996,65 @@ int fspann_search_batch_dev(fspann_ctx *ctx, int64_t Q, const double *d_queries,
     (void)ham_threshold;
     if (!ctx) return FSPANN_E_ARG;
     CK(cudaSetDevice(ctx->device));
-    int rc = check_routing(ctx); if (rc) return rc;
-    rc = check_store(ctx); if (rc) return rc;
-    if (ctx->rv.n_ids <= 1 && ctx->rv.P <= 1) return fail(ctx, FSPANN_E_STATE, "Index not finalized: only GFunctions uploaded");
+    int rc = check_search_args(ctx, Q, k, B); if (rc) return rc;
     if (Q == 0) return FSPANN_OK;
-    if (Q < 0 || !d_queries || !d_topk_ids || !d_topk_dist || !d_n_ret) return fail(ctx, FSPANN_E_ARG, "null array");
-    if (k <= 0) return fail(ctx, FSPANN_E_ARG, "topK must be > 0 (QTF:65)");
-    if (B <= 0) return fail(ctx, FSPANN_E_ARG, "refinementLimit must be > 0");
-    if (probes <= 0) probes = 5;   // DEFAULT_MAX_PROBES (PIS:93) when no override is configured (PIS:880-888)
-    const int64_t l0 = ctx->launches;
-    rc = search_pass(ctx, Q, d_queries, k, probes, hard_cap, B, 0, d_topk_ids, d_topk_dist, d_n_ret, d_counters, true);
-    if (rc) return rc;
-    ctx->ev_valid = true;
-    if (allow_retry) {
-        // QSI:327-337 + 444-447: once per query, if returned < K or decrypted < 10*K, redo with 10 probes.
-        // pinned staging: D2H into pageable memory would be a staged, blocking copy
-        const size_t need = 2 * (size_t)Q + 4;
-        if (ctx->h_pin_ints < need) {
-            if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
-            ctx->h_pin = nullptr; ctx->h_pin_ints = 0;
-            CK(cudaHostAlloc((void **)&ctx->h_pin, sizeof(int32_t) * (need + need / 4), cudaHostAllocDefault));
-            ctx->h_pin_ints = need + need / 4;
-        }
-        int32_t *nret = ctx->h_pin, *ndec = ctx->h_pin + Q, *flags = ctx->h_pin + 2 * Q;
-        CK(cudaMemcpyAsync(nret, d_n_ret, sizeof(int32_t) * (size_t)Q, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(ndec, ctx->s_ndec.p, sizeof(int32_t) * (size_t)Q, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(flags, ctx->s_f32_exact.p, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        ctx->last_queries_finite = flags[2] != 0;
-        if (!ctx->last_queries_finite) return fail(ctx, FSPANN_E_ARG, "Vector contains NaN/Inf (Coding:357-359)");
-        std::vector<int32_t> rows;
-        // a first pass with no decrypted candidate returns immediately (QSI:293: scored.isEmpty() -> return), no retry
-        for (int64_t q = 0; q < Q; q++)
-            if (ndec[q] > 0 && (nret[q] < k || ndec[q] < 10 * k)) rows.push_back((int32_t)q);
-        const int64_t R = (int64_t)rows.size();
-        if (R > 0) {
-            const int dim = ctx->rv.dim;
-            ENSURE(ctx->r_rows, sizeof(int32_t) * (size_t)R); ENSURE(ctx->r_queries, sizeof(double) * (size_t)R * dim);
-            ENSURE(ctx->r_topk_ids, sizeof(int32_t) * (size_t)R * k); ENSURE(ctx->r_topk_dist, sizeof(double) * (size_t)R * k);
-            ENSURE(ctx->r_nret, sizeof(int32_t) * (size_t)R); ENSURE(ctx->r_counters, sizeof(int64_t) * FSPANN_COUNTERS * (size_t)R);
-            CK(cudaMemcpyAsync(ctx->r_rows.p, rows.data(), sizeof(int32_t) * (size_t)R, cudaMemcpyHostToDevice, ctx->stream));
-            LAUNCHED(launch_gather_rows(ctx->stream, d_queries, ctx->r_queries.p, (const int32_t *)ctx->r_rows.p, R, sizeof(double) * dim, false));
-            rc = search_pass(ctx, R, (const double *)ctx->r_queries.p, k, 10, hard_cap, B, 1, (int32_t *)ctx->r_topk_ids.p,
-                             (double *)ctx->r_topk_dist.p, (int32_t *)ctx->r_nret.p, d_counters ? (int64_t *)ctx->r_counters.p : nullptr, false);
-            if (rc) return rc;
-            LAUNCHED(launch_gather_rows(ctx->stream, ctx->r_topk_ids.p, d_topk_ids, (const int32_t *)ctx->r_rows.p, R, sizeof(int32_t) * k, true));
-            LAUNCHED(launch_gather_rows(ctx->stream, ctx->r_topk_dist.p, d_topk_dist, (const int32_t *)ctx->r_rows.p, R, sizeof(double) * k, true));
-            LAUNCHED(launch_gather_rows(ctx->stream, ctx->r_nret.p, d_n_ret, (const int32_t *)ctx->r_rows.p, R, sizeof(int32_t), true));
-            if (d_counters)
-                LAUNCHED(launch_gather_rows(ctx->stream, ctx->r_counters.p, d_counters, (const int32_t *)ctx->r_rows.p, R, sizeof(int64_t) * FSPANN_COUNTERS, true));
-            CK(cudaStreamSynchronize(ctx->stream));   // rows vector is read by the H2D copy above
-        }
-    }
-    ctx->last_call_launches = ctx->launches - l0;
-    return FSPANN_OK;
+    if (!d_queries || !d_topk_ids || !d_topk_dist || !d_n_ret) return fail(ctx, FSPANN_E_ARG, "null array");
+    return search_core(ctx, Q, d_queries, nullptr, k, probes, hard_cap, B, allow_retry != 0, allow_retry != 0, d_topk_ids, d_topk_dist, d_n_ret,
+                       d_counters, nullptr);
 }
 
-int fspann_search_batch(fspann_ctx *ctx, int64_t Q, const double *queries, int32_t k, int32_t probes, int64_t hard_cap, int32_t B,
-                        int32_t ham_threshold, int32_t *topk_ids_out, double *topk_dist_out, int32_t *n_ret_out, int64_t *counters_out) {
+int fspann_search_tokens_dev(fspann_ctx *ctx, int64_t Q, const uint64_t *d_codes, const double *d_queries, int32_t k, int32_t probes,
+                             int64_t hard_cap, int32_t B, int32_t ham_threshold, int32_t allow_retry, int32_t *d_topk_ids, double *d_topk_dist,
+                             int32_t *d_n_ret, int64_t *d_counters) {
+    (void)ham_threshold;
     if (!ctx) return FSPANN_E_ARG;
     CK(cudaSetDevice(ctx->device));
-    int rc = check_routing(ctx); if (rc) return rc;
-    rc = check_store(ctx); if (rc) return rc;
+    int rc = check_search_args(ctx, Q, k, B); if (rc) return rc;
     if (Q == 0) return FSPANN_OK;
-    if (Q < 0 || !queries || !topk_ids_out || !topk_dist_out || !n_ret_out) return fail(ctx, FSPANN_E_ARG, "null array");
-    if (k <= 0) return fail(ctx, FSPANN_E_ARG, "topK must be > 0 (QTF:65)");
+    if (!d_codes || !d_queries || !d_topk_ids || !d_topk_dist || !d_n_ret) return fail(ctx, FSPANN_E_ARG, "null array");
+    return search_core(ctx, Q, d_queries, d_codes, k, probes, hard_cap, B, allow_retry != 0, false, d_topk_ids, d_topk_dist, d_n_ret, d_counters,
+                       nullptr);
+}
+
+static int search_host(fspann_ctx *ctx, int64_t Q, const uint64_t *codes, const double *queries, int32_t k, int32_t probes, int64_t hard_cap, int32_t B,
+                       int32_t *topk_ids_out, double *topk_dist_out, int32_t *n_ret_out, int64_t *counters_out) {
+    if (!ctx) return FSPANN_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    int rc = check_search_args(ctx, Q, k, B); if (rc) return rc;
+    if (Q == 0) return FSPANN_OK;
+    if (!queries || !topk_ids_out || !topk_dist_out || !n_ret_out) return fail(ctx, FSPANN_E_ARG, "null array");
     const int dim = ctx->rv.dim;
-    // QSI:137: a query that is not all-finite returns an empty list; createToken would already have thrown
-    // (Coding:357-359), so the batch is rejected like the reference rejects the token.  Small batches are checked on the host
-    // before any work; large ones by the device pass that scans every query value anyway (flag read with the retry counters),
-    // and nothing is copied back when it trips.
-    if (Q * dim <= 65536 && !all_finite(queries, Q * dim)) return fail(ctx, FSPANN_E_ARG, "Vector contains NaN/Inf (Coding:357-359)");
+    // createToken (no codes supplied) throws on NaN/Inf (Coding:357-359): small batches are checked on the host before any work, large
+    // ones by the device pass that scans every query value anyway (flag read back with the retry decision).  With codes supplied the
+    // token exists already and QSI:137 applies instead: that query returns empty, the others are unaffected.
+    if (!codes && Q * dim <= 65536 && !all_finite(queries, Q * dim)) return fail(ctx, FSPANN_E_ARG, "Vector contains NaN/Inf (Coding:357-359)");
     ENSURE(ctx->s_queries, sizeof(double) * (size_t)Q * dim);
     ENSURE(ctx->s_topk_ids, sizeof(int32_t) * (size_t)Q * k); ENSURE(ctx->s_topk_dist, sizeof(double) * (size_t)Q * k);
     ENSURE(ctx->s_nret, sizeof(int32_t) * (size_t)Q); ENSURE(ctx->s_counters, sizeof(int64_t) * FSPANN_COUNTERS * (size_t)Q);
     CK(cudaMemcpyAsync(ctx->s_queries.p, queries, sizeof(double) * (size_t)Q * dim, cudaMemcpyHostToDevice, ctx->stream));
-    rc = fspann_search_batch_dev(ctx, Q, (const double *)ctx->s_queries.p, k, probes, hard_cap, B, ham_threshold, 1, (int32_t *)ctx->s_topk_ids.p,
-                                 (double *)ctx->s_topk_dist.p, (int32_t *)ctx->s_nret.p, (int64_t *)ctx->s_counters.p);
-    if (rc) return rc;
-    CK(cudaMemcpyAsync(topk_ids_out, ctx->s_topk_ids.p, sizeof(int32_t) * (size_t)Q * k, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(topk_dist_out, ctx->s_topk_dist.p, sizeof(double) * (size_t)Q * k, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(n_ret_out, ctx->s_nret.p, sizeof(int32_t) * (size_t)Q, cudaMemcpyDeviceToHost, ctx->stream));
-    if (counters_out) CK(cudaMemcpyAsync(counters_out, ctx->s_counters.p, sizeof(int64_t) * FSPANN_COUNTERS * (size_t)Q, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    return FSPANN_OK;
+    const uint64_t *d_codes = nullptr;
+    if (codes) {
+        const size_t cb = sizeof(uint64_t) * (size_t)Q * ctx->rv.TD * ctx->rv.W;
+        ENSURE(ctx->s_codes_in, cb);
+        CK(cudaMemcpyAsync(ctx->s_codes_in.p, codes, cb, cudaMemcpyHostToDevice, ctx->stream));
+        d_codes = (const uint64_t *)ctx->s_codes_in.p;
+    }
+    const HostOut h{topk_ids_out, topk_dist_out, n_ret_out, counters_out};
+    return search_core(ctx, Q, (const double *)ctx->s_queries.p, d_codes, k, probes, hard_cap, B, true, codes == nullptr, (int32_t *)ctx->s_topk_ids.p,
+                       (double *)ctx->s_topk_dist.p, (int32_t *)ctx->s_nret.p, (int64_t *)ctx->s_counters.p, &h);
+}
+
+int fspann_search_batch(fspann_ctx *ctx, int64_t Q, const double *queries, int32_t k, int32_t probes, int64_t hard_cap, int32_t B,
+                        int32_t ham_threshold, int32_t *topk_ids_out, double *topk_dist_out, int32_t *n_ret_out, int64_t *counters_out) {
+    (void)ham_threshold;
+    return search_host(ctx, Q, nullptr, queries, k, probes, hard_cap, B, topk_ids_out, topk_dist_out, n_ret_out, counters_out);
+}
+
+int fspann_search_tokens(fspann_ctx *ctx, int64_t Q, const uint64_t *codes, const double *queries, int32_t k, int32_t probes, int64_t hard_cap,
+                         int32_t B, int32_t ham_threshold, int32_t *topk_ids_out, double *topk_dist_out, int32_t *n_ret_out, int64_t *counters_out) {
+    (void)ham_threshold;
+    if (ctx && Q > 0 && !codes) return fail(ctx, FSPANN_E_STATE, "MSANNP violation: QueryToken missing BitSet codes (PIS:604-606)");
+    return search_host(ctx, Q, codes, queries, k, probes, hard_cap, B, topk_ids_out, topk_dist_out, n_ret_out, counters_out);
 }
 
 // ---- device-resident building blocks of the database-sharded deployment (BASELINE config 4) ---------------------

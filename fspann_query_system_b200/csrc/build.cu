@@ -71,7 +71,7 @@ int launch_partition_build(cudaStream_t s, const uint64_t *codes, const int32_t 
     const size_t tmp = std::max(tmp64, tmp32);
     void *cub_tmp = take(tmp);
     if ((size_t)(sp - (unsigned char *)scratch) > scratch_bytes) return -1;
-    int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 16);
+    int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)cur_sm_count() * 16);
     int launched = 0;
     // 1. HashMap iteration order (shared by every division)
     build_bucket_kernel<<<grid, 256, 0, s>>>(staged, n, cap - 1u, (uint32_t *)k_a, p_a);

@@ -84,7 +84,8 @@ struct RefineParams {
     const double *queries;    // [Q][dim]
     const float *queries_f32; // [Q][dim] compact copy (or nullptr); valid for distances only when *f32_exact != 0
     const uint8_t *queries_u8; // [Q][dim] uint8 copy; valid when f32_exact[1] != 0 (all values are integers 0..255)
-    const int32_t *f32_exact;  // [2]: {FP32 copy exact, uint8 copy exact}
+    const int32_t *f32_exact;  // [3]: {FP32 copy exact, uint8 copy exact, every value finite}
+    const uint8_t *qfinite;    // [Q] 1 = the query row is all-finite (QSI:137 / QSI:407-413); nullptr = not checked
     const int32_t *cand_ids;  // [Q][stride]
     const int32_t *n_cand;    // [Q]
     int32_t stride, k;
@@ -110,9 +111,32 @@ struct RefineParams {
     int32_t *topk_rank;  // [Q][k] candidate position of each result (for the cross-shard merge), or nullptr
 };
 
+// Opt a kernel in to the device's full dynamic shared memory (opt-in limit minus the kernel's static shared memory) on the CURRENT
+// device.  The attribute is per device: fspann_ctx_create runs the configure_*_kernels() functions after cudaSetDevice, so one
+// process may drive any number of GPUs (one context each).
+template <class K>
+inline int opt_in_smem(K kernel) {
+    cudaFuncAttributes a;
+    int dev = 0, optin = 0;
+    if (cudaFuncGetAttributes(&a, kernel) != cudaSuccess || cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return -1;
+    const int dyn = optin - (int)a.sharedSizeBytes;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn) == cudaSuccess ? 0 : -1;
+}
+// SM count of the current device (grid caps of the grid-stride helper kernels)
+inline int cur_sm_count() {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 1;
+    return n;
+}
+constexpr int kMaxDynSmem = 227 * 1024;   // shared memory one CTA can opt in to on sm_100a (static + dynamic)
+int configure_tokengen_kernels();
+int configure_route_kernels();
+int configure_refine_kernels();
+
 // launchers (each returns the number of kernels it launched, or -1 after setting a CUDA error)
 int launch_tokengen(cudaStream_t s, const RoutingView &rv, int64_t Q, const double *queries, uint64_t *codes, int32_t *work,
-                    unsigned long long *list, int64_t list_cap, float *qf, float *qnorm, bool exact_only);
+                    unsigned long long *list, int64_t list_cap, float *qf, float *qnorm, bool exact_only, int sm_count);
 int64_t tokengen_list_capacity(const RoutingView &rv, int64_t Q);
 int launch_alpha_prepare(cudaStream_t s, const double *alpha, int64_t rows, int dim, float *alpha_f, float *norm);
 int launch_route(cudaStream_t s, const RoutingView &rv, const RouteParams &p, int grid);
@@ -125,10 +149,11 @@ int launch_refine_group(cudaStream_t s, const StoreView &sv, const RefineParams 
 int launch_refine_verify(cudaStream_t s, const StoreView &sv, const RefineParams &p, int sm_count);
 int launch_version_bucket(cudaStream_t s, const StoreView &sv, const RefineParams &p, int64_t n_upper);
 int launch_refine_decrypt(cudaStream_t s, const StoreView &sv, const RefineParams &p, int sm_count);
-int launch_queries_to_f32(cudaStream_t s, const double *q, float *out, uint8_t *out8, int64_t n, int32_t *exact);
+int launch_queries_to_f32(cudaStream_t s, const double *q, float *out, uint8_t *out8, int64_t Q, int dim, int32_t *exact, uint8_t *qfinite);
+int launch_retry_select(cudaStream_t s, int64_t Q, int k, const int32_t *n_ret, const int32_t *n_dec, const int32_t *exact, int32_t *rows, int32_t *out);
 int launch_refine_topk(cudaStream_t s, const RefineParams &p);
 int launch_counters(cudaStream_t s, int64_t Q, const int32_t *raw, const int32_t *uniq, const int32_t *n_dec,
-                    const int32_t *n_ret, const int32_t *n_cand, int32_t retried, int64_t *counters);
+                    const int32_t *n_ret, const int32_t *n_cand, int32_t retried, int64_t *counters, const uint8_t *qfinite);
 int launch_gather_rows(cudaStream_t s, const void *src, void *dst, const int32_t *rows, int64_t n_rows, int64_t row_bytes, bool scatter);
 int launch_store_pack(cudaStream_t s, uint8_t *rec, int64_t rec_stride, int32_t dim, int64_t n, const int32_t *ids /* or null */,
                       const uint8_t *iv, const uint8_t *ct, const int32_t *ver);

@@ -35,7 +35,7 @@ __global__ void refine_count_kernel(StoreView sv, RefineParams p) {
         const int64_t q = i / p.stride;
         const int r = (int)(i - q * p.stride);
         uint8_t v = 0xff;                               // 0xff = slot not part of the candidate list
-        if (r < p.n_cand[q]) {
+        if (r < p.n_cand[q] && (!p.qfinite || p.qfinite[q])) {   // QSI:137: a query with NaN/Inf returns empty and touches nothing
             const int32_t id = p.cand_ids[i];
             if (id < 0 || id >= sv.n_global || is_deleted(sv, id)) v = FSPANN_V_NOT_FOUND;     // PIS:717-724
             else if (id < sv.id_base || id >= sv.id_base + sv.N) v = 0xfd;                      // 0xfd = lives in another shard
@@ -134,7 +134,7 @@ int launch_refine_group(cudaStream_t s, const StoreView &sv, const RefineParams 
     const int64_t n = sv.N + 1;  // one extra slot so cnt[N] = total after the scan
     if (cudaMemsetAsync(p.cnt, 0, sizeof(int32_t) * (size_t)n, s) != cudaSuccess) return -1;
     const int64_t total = p.Q * (int64_t)p.stride;
-    int grid = (int)((total + 255) / 256); if (grid > 148 * 16) grid = 148 * 16; if (grid < 1) grid = 1;
+    int grid = (int)((total + 255) / 256); { const int cap = cur_sm_count() * 16; if (grid > cap) grid = cap; } if (grid < 1) grid = 1;
     refine_count_kernel<<<grid, 256, 0, s>>>(sv, p);
     const int nblocks = (int)((n + SCAN_ITEMS - 1) / SCAN_ITEMS);
     scan_partial_kernel<<<nblocks, SCAN_THREADS, 0, s>>>(p.cnt, n, p.block_sums);
@@ -507,7 +507,7 @@ __global__ void version_offsets_kernel(RefineParams p) {
 }
 int launch_version_bucket(cudaStream_t s, const StoreView &sv, const RefineParams &p, int64_t n_upper) {
     if (cudaMemsetAsync(p.vcnt, 0, sizeof(int32_t) * 2 * kMaxKeys, s) != cudaSuccess) return -1;
-    int grid = (int)std::min<int64_t>((n_upper + 255) / 256, 148 * 8); if (grid < 1) grid = 1;
+    int grid = (int)std::min<int64_t>((n_upper + 255) / 256, (int64_t)cur_sm_count() * 8); if (grid < 1) grid = 1;
     version_bucket_kernel<<<grid, 256, 0, s>>>(sv, p, 0);
     version_offsets_kernel<<<1, 32, 0, s>>>(p);
     version_bucket_kernel<<<grid, 256, 0, s>>>(sv, p, 1);
@@ -527,11 +527,6 @@ int launch_gcm_tag(cudaStream_t s, const StoreView &sv, const int32_t *list, con
                    const uint8_t *write_flag, int sm_count) {
     if (n_list <= 0) return 0;
     const size_t smem = verify_smem_bytes();
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(gcm_tag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-        configured = true;
-    }
     int grid = (n_list + VF_THREADS - 1) / VF_THREADS; if (grid > sm_count * 2) grid = sm_count * 2;
     gcm_tag_kernel<<<grid, VF_THREADS, smem, s>>>(sv, list, gid, n_list, verdict, write_flag);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
@@ -539,11 +534,6 @@ int launch_gcm_tag(cudaStream_t s, const StoreView &sv, const int32_t *list, con
 
 int launch_refine_verify(cudaStream_t s, const StoreView &sv, const RefineParams &p, int sm_count) {
     const size_t smem = sizeof(uint4) * 4096 + sizeof(uint32_t) * (256 * 32 + kMaxKeys * 60) + sizeof(int32_t) * kMaxKeys;
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(refine_verify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-        configured = true;
-    }
     refine_verify_kernel<<<sm_count * 2, VF_THREADS, smem, s>>>(sv, p);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
@@ -778,43 +768,76 @@ static bool decrypt_layout(int dim, DecryptLayout &lay) {
     return false;
 }
 
+int configure_refine_kernels() {   // per-device opt-in to > 48 KB of dynamic shared memory (see opt_in_smem)
+    if (opt_in_smem(gcm_tag_kernel) || opt_in_smem(refine_verify_kernel) || opt_in_smem(refine_decrypt_kernel)) return -1;
+    return 0;
+}
+
 int launch_refine_decrypt(cudaStream_t s, const StoreView &sv, const RefineParams &p, int sm_count) {
     DecryptLayout lay;
     if (!decrypt_layout(sv.dim, lay)) return -1;
-    static size_t configured = 0;
-    if (lay.smem > configured) {
-        if (cudaFuncSetAttribute(refine_decrypt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.smem) != cudaSuccess) return -1;
-        configured = lay.smem;
-    }
     refine_decrypt_kernel<<<sm_count, RF_THREADS, lay.smem, s>>>(*sv.keys_host, sv, p, lay);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
 // Compact copies of the query batch (FP32 and uint8) + flags telling whether every value survived the round trip exactly:
 // exact[0] for FP32, exact[1] for uint8 (integers 0..255).
-__global__ void queries_compact_kernel(const double *__restrict__ q, float *__restrict__ out32, uint8_t *__restrict__ out8, int64_t n, int32_t *exact) {
-    bool ok32 = true, ok8 = true, fin = true;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const double v = q[i];
-        const float f = (float)v;
-        out32[i] = f;
-        ok32 &= (double)f == v;
-        const bool in8 = v >= 0.0 && v <= 255.0;
-        const int b = in8 ? (int)v : 0;
-        out8[i] = (uint8_t)b;
-        ok8 &= in8 && (double)b == v;
-        fin &= (((unsigned long long)__double_as_longlong(v) >> 52) & 0x7ffull) != 0x7ffull;     // isValid (QSI:407-413)
+// One warp per query row; qfinite[q] = 1 when every value of the row is finite (isValid, QSI:407-413).
+__global__ void queries_compact_kernel(const double *__restrict__ q, float *__restrict__ out32, uint8_t *__restrict__ out8, int64_t Q, int dim,
+                                       int32_t *exact, uint8_t *__restrict__ qfinite) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    bool ok32 = true, ok8 = true, fin_all = true;
+    for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < Q; row += warps) {
+        bool fin = true;
+        for (int i = lane; i < dim; i += 32) {
+            const int64_t at = row * dim + i;
+            const double v = q[at];
+            const float f = (float)v;
+            out32[at] = f;
+            ok32 &= (double)f == v;
+            const bool in8 = v >= 0.0 && v <= 255.0;
+            const int b = in8 ? (int)v : 0;
+            out8[at] = (uint8_t)b;
+            ok8 &= in8 && (double)b == v;
+            fin &= (((unsigned long long)__double_as_longlong(v) >> 52) & 0x7ffull) != 0x7ffull;
+        }
+        fin = __all_sync(0xffffffffu, fin);
+        if (lane == 0) qfinite[row] = fin ? 1 : 0;
+        fin_all &= fin;
     }
-    if (!__all_sync(0xffffffffu, ok32) && (threadIdx.x & 31) == 0) atomicAnd(&exact[0], 0);
-    if (!__all_sync(0xffffffffu, ok8) && (threadIdx.x & 31) == 0) atomicAnd(&exact[1], 0);
-    if (!__all_sync(0xffffffffu, fin) && (threadIdx.x & 31) == 0) atomicAnd(&exact[2], 0);
+    if (!__all_sync(0xffffffffu, ok32) && lane == 0) atomicAnd(&exact[0], 0);
+    if (!__all_sync(0xffffffffu, ok8) && lane == 0) atomicAnd(&exact[1], 0);
+    if (!__all_sync(0xffffffffu, fin_all) && lane == 0) atomicAnd(&exact[2], 0);
 }
 // exact[0] / exact[1]: the FP32 / uint8 copy is value-identical; exact[2]: every value is finite.
-int launch_queries_to_f32(cudaStream_t s, const double *q, float *out, uint8_t *out8, int64_t n, int32_t *exact) {
-    if (n <= 0) return 0;
+int launch_queries_to_f32(cudaStream_t s, const double *q, float *out, uint8_t *out8, int64_t Q, int dim, int32_t *exact, uint8_t *qfinite) {
+    if (Q <= 0) return 0;
     if (cudaMemsetAsync(exact, 0xff, 4 * sizeof(int32_t), s) != cudaSuccess) return -1;
-    int grid = (int)((n + 255) / 256); if (grid > 148 * 8) grid = 148 * 8;
-    queries_compact_kernel<<<grid, 256, 0, s>>>(q, out, out8, n, exact);
+    int grid = (int)((Q * 32 + 255) / 256); { const int cap = cur_sm_count() * 8; if (grid > cap) grid = cap; }
+    queries_compact_kernel<<<grid, 256, 0, s>>>(q, out, out8, Q, dim, exact, qfinite);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// Adaptive retry decision on the device (QSI:327-337 + 444-447): rows[] = the queries whose first pass decrypted something but returned
+// < k results or decrypted < 10*k candidates; out[0] = their number, out[1] = 1 when some query of the batch holds NaN/Inf.
+__global__ void retry_select_kernel(int64_t Q, int k, const int32_t *__restrict__ n_ret, const int32_t *__restrict__ n_dec, const int32_t *__restrict__ exact,
+                                    int32_t *__restrict__ rows, int32_t *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool need = false;
+    if (q < Q) { const int nd = n_dec[q]; need = nd > 0 && (n_ret[q] < k || nd < 10 * k); }   // QSI:293: nothing decrypted -> plain return, no retry
+    const unsigned bal = __ballot_sync(0xffffffffu, need);
+    int base = 0;
+    if (lane == 0 && bal) base = atomicAdd(&out[0], __popc(bal));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (need) rows[base + __popc(bal & ((1u << lane) - 1u))] = (int32_t)q;
+    if (q == 0) out[1] = exact[2] == 0 ? 1 : 0;
+}
+int launch_retry_select(cudaStream_t s, int64_t Q, int k, const int32_t *n_ret, const int32_t *n_dec, const int32_t *exact, int32_t *rows, int32_t *out) {
+    if (Q <= 0) return 0;
+    if (cudaMemsetAsync(out, 0, 2 * sizeof(int32_t), s) != cudaSuccess) return -1;
+    retry_select_kernel<<<(unsigned)((Q + 255) / 256), 256, 0, s>>>(Q, k, n_ret, n_dec, exact, rows, out);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
@@ -938,16 +961,17 @@ int launch_merge_topk(cudaStream_t s, int S, int64_t Q, int k, const double *dis
 // small helpers
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void counters_kernel(int64_t Q, const int32_t *raw, const int32_t *uniq, const int32_t *n_dec, const int32_t *n_ret,
-                                const int32_t *n_cand, int32_t retried, int64_t *counters) {
+                                const int32_t *n_cand, int32_t retried, int64_t *counters, const uint8_t *qfinite) {
     const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (q >= Q) return;
     int64_t *c = counters + q * FSPANN_COUNTERS;
+    if (qfinite && !qfinite[q]) { for (int i = 0; i < FSPANN_COUNTERS; i++) c[i] = 0; return; }   // QSI:137 returns before any lookup
     c[0] = raw ? raw[q] : 0; c[1] = uniq ? uniq[q] : 0; c[2] = n_dec[q]; c[3] = n_ret[q]; c[4] = retried; c[5] = n_cand[q];
 }
 int launch_counters(cudaStream_t s, int64_t Q, const int32_t *raw, const int32_t *uniq, const int32_t *n_dec, const int32_t *n_ret,
-                    const int32_t *n_cand, int32_t retried, int64_t *counters) {
+                    const int32_t *n_cand, int32_t retried, int64_t *counters, const uint8_t *qfinite) {
     if (Q <= 0) return 0;
-    counters_kernel<<<(unsigned)((Q + 255) / 256), 256, 0, s>>>(Q, raw, uniq, n_dec, n_ret, n_cand, retried, counters);
+    counters_kernel<<<(unsigned)((Q + 255) / 256), 256, 0, s>>>(Q, raw, uniq, n_dec, n_ret, n_cand, retried, counters, qfinite);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
@@ -963,7 +987,7 @@ __global__ void gather_rows_kernel(const uint32_t *src, uint32_t *dst, const int
 int launch_gather_rows(cudaStream_t s, const void *src, void *dst, const int32_t *rows, int64_t n_rows, int64_t row_bytes, bool scatter) {
     if (n_rows <= 0) return 0;
     const int64_t words = row_bytes / 4, total = n_rows * words;
-    int grid = (int)((total + 255) / 256); if (grid > 148 * 8) grid = 148 * 8;
+    int grid = (int)((total + 255) / 256); { const int cap = cur_sm_count() * 8; if (grid > cap) grid = cap; }
     gather_rows_kernel<<<grid, 256, 0, s>>>((const uint32_t *)src, (uint32_t *)dst, rows, n_rows, words, scatter ? 1 : 0);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
@@ -987,7 +1011,7 @@ int launch_store_pack(cudaStream_t s, uint8_t *rec, int64_t rec_stride, int32_t 
                       const uint8_t *ct, const int32_t *ver) {
     if (n <= 0) return 0;
     const int64_t total = n * ((32 + 8LL * dim) / 4);
-    int grid = (int)((total + 255) / 256); if (grid > 148 * 16) grid = 148 * 16;
+    int grid = (int)((total + 255) / 256); { const int cap = cur_sm_count() * 16; if (grid > cap) grid = cap; }
     store_pack_kernel<<<grid, 256, 0, s>>>(rec, rec_stride, dim, n, ids, iv, ct, ver);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
@@ -1124,7 +1148,7 @@ int launch_store_unpack(cudaStream_t s, const uint8_t *rec, int64_t rec_stride, 
                         uint8_t *ct, int32_t *ver) {
     if (n <= 0) return 0;
     const int64_t total = n * ((32 + 8LL * dim) / 4);
-    int grid = (int)((total + 255) / 256); if (grid > 148 * 16) grid = 148 * 16;
+    int grid = (int)((total + 255) / 256); { const int cap = cur_sm_count() * 16; if (grid > cap) grid = cap; }
     store_unpack_kernel<<<grid, 256, 0, s>>>(rec, rec_stride, dim, n, rows, iv, ct, ver);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
@@ -1177,7 +1201,7 @@ int launch_debug_decrypt(cudaStream_t s, const StoreView &sv, int64_t n, const i
     const int dim_pad = (sv.dim + 1) & ~1;
     const size_t smem = sizeof(uint32_t) * (256 * 32 + kMaxKeys * 60) + sizeof(int32_t) * kMaxKeys + sizeof(double) * (size_t)DBG_WARPS * dim_pad;
     if (cudaFuncSetAttribute(debug_decrypt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-    int grid = (int)((n + DBG_WARPS - 1) / DBG_WARPS); if (grid > 148 * 2) grid = 148 * 2; if (grid < 1) grid = 1;
+    int grid = (int)((n + DBG_WARPS - 1) / DBG_WARPS); { const int cap = cur_sm_count() * 2; if (grid > cap) grid = cap; } if (grid < 1) grid = 1;
     debug_decrypt_kernel<<<grid, DBG_THREADS, smem, s>>>(sv, n, ids, pt, verdict);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }

@@ -910,14 +910,13 @@ bool route_fast_eligible(const RoutingView &rv, int probes, int64_t hard_cap, in
     return true;
 }
 
+int configure_route_kernels() {   // per-device opt-in, see configure_tokengen_kernels
+    return opt_in_smem(route_fast_kernel) || opt_in_smem(route_kernel) ? -1 : 0;
+}
+
 int launch_route_fast(cudaStream_t s, const RoutingView &rv, const RouteParams &p, RouteFastExtra x, size_t smem, int sm_count,
                       int32_t *vis_part, uint8_t *vis_score, uint8_t *vis_n) {
     if (p.Q <= 0) return 0;
-    static size_t configured = 0;
-    if (smem > configured) {
-        if (cudaFuncSetAttribute(route_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-        configured = smem;
-    }
     const int64_t nthreads = p.Q * rv.TD;
     route_probe_kernel<<<(unsigned)((nthreads + 127) / 128), 128, 0, s>>>(rv, p.Q, p.codes, p.probes, vis_part, vis_score, vis_n);
     x.vis_part = vis_part; x.vis_score = vis_score; x.vis_n = vis_n;

@@ -358,21 +358,22 @@ __global__ void tokengen_recheck_kernel(RoutingView rv, const double *__restrict
     }
 }
 
-static int launch_tokengen_exact(cudaStream_t s, const RoutingView &rv, int64_t Q, const double *queries, uint64_t *codes, const int32_t *run_if) {
+// The opt-in to > 48 KB of dynamic shared memory is a per-DEVICE attribute of each kernel: fspann_ctx_create calls this after
+// cudaSetDevice, so every context's device is configured no matter how many GPUs one process drives.
+int configure_tokengen_kernels() {
+    return opt_in_smem(tokengen_kernel) || opt_in_smem(tokengen_fast_kernel) ? -1 : 0;
+}
+
+static int launch_tokengen_exact(cudaStream_t s, const RoutingView &rv, int64_t Q, const double *queries, uint64_t *codes, const int32_t *run_if, int sm_count) {
     const int dim_even = (rv.dim + 1) & ~1;
     int qstride = dim_even + 2;                      // doubles; 16-byte aligned rows whose granule count is odd => conflict-free 128-bit loads
     if (((qstride >> 1) & 1) == 0) qstride += 2;
     const int astride = dim_even;
     const size_t smem = sizeof(double) * ((size_t)TG_QT * qstride + (size_t)rv.m * astride + 2 * (size_t)rv.m) + sizeof(uint32_t) * (size_t)TG_QT * 2 * rv.W;
-    if (smem > 227 * 1024) return -1;
-    static size_t configured = 0;
-    if (smem > configured) {
-        if (cudaFuncSetAttribute(tokengen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-        configured = smem;
-    }
+    if (smem > (size_t)kMaxDynSmem) return -1;
     // enough CTAs for >= 8 waves of the 2-per-SM slots when the batch allows it (tail below ~10 %)
     const int64_t tiles = (Q + TG_QT - 1) / TG_QT;
-    int gsplit = (int)((296 * 8 + tiles - 1) / tiles);
+    int gsplit = (int)((2LL * sm_count * 8 + tiles - 1) / tiles);
     if (gsplit < 1) gsplit = 1;
     if (gsplit > rv.TD) gsplit = rv.TD;
     const int groups_per_cta = (rv.TD + gsplit - 1) / gsplit;
@@ -389,26 +390,21 @@ int64_t tokengen_list_capacity(const RoutingView &rv, int64_t Q) {
 
 // work: int32[2] + list: uint64[tokengen_list_capacity] scratch (or nullptr / exact != 0: the exact kernel alone).
 int launch_tokengen(cudaStream_t s, const RoutingView &rv, int64_t Q, const double *queries, uint64_t *codes, int32_t *work,
-                    unsigned long long *list, int64_t list_cap, float *qf, float *qnorm, bool exact_only) {
+                    unsigned long long *list, int64_t list_cap, float *qf, float *qnorm, bool exact_only, int sm_count) {
     if (Q <= 0) return 0;
     const bool fast_ok = !exact_only && work && list && qf && qnorm && rv.alpha_f32 && rv.alpha_norm && (rv.m + 1) / 2 <= TF_JB && rv.TD < 65536 && rv.m < 256 &&
                          Q * (int64_t)rv.TD * rv.m < (1LL << 31);        // the re-check counter is an int32: it can never wrap
-    if (!fast_ok) return launch_tokengen_exact(s, rv, Q, queries, codes, nullptr);
+    if (!fast_ok) return launch_tokengen_exact(s, rv, Q, queries, codes, nullptr, sm_count);
     const int n4 = (rv.dim + 3) >> 2;
     int qg = n4 + 1;                                 // row stride in 16-byte granules, odd => conflict-free 128-bit loads
     if ((qg & 1) == 0) qg++;
     const int qstride = 4 * qg, astride = 4 * n4;
     const size_t smem = sizeof(float) * ((size_t)TF_QT * qstride + (size_t)rv.m * astride) + sizeof(double) * 2 * (size_t)rv.m +
                         sizeof(float) * (3 * (((size_t)rv.m + 3) / 4 * 4) + TF_QT) + sizeof(uint32_t) * (size_t)TF_QT * 2 * rv.W;
-    if (smem > 113 * 1024) return launch_tokengen_exact(s, rv, Q, queries, codes, nullptr);
-    static size_t configured = 0;
-    if (smem > configured) {
-        if (cudaFuncSetAttribute(tokengen_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-        configured = smem;
-    }
+    if (smem > 113 * 1024) return launch_tokengen_exact(s, rv, Q, queries, codes, nullptr, sm_count);
     if (cudaMemsetAsync(work, 0, 2 * sizeof(int32_t), s) != cudaSuccess) return -1;
     const int64_t tiles = (Q + TF_QT - 1) / TF_QT;
-    int gsplit = (int)((296 * 4 + tiles - 1) / tiles);
+    int gsplit = (int)((2LL * sm_count * 4 + tiles - 1) / tiles);
     if (gsplit < 1) gsplit = 1;
     if (gsplit > rv.TD) gsplit = rv.TD;
     int groups_per_cta = (rv.TD + gsplit - 1) / gsplit;
@@ -418,9 +414,9 @@ int launch_tokengen(cudaStream_t s, const RoutingView &rv, int64_t Q, const doub
     dim3 grid((unsigned)tiles, (unsigned)gsplit);
     tokengen_prep_kernel<<<(unsigned)((Q * 32 + 255) / 256), 256, 0, s>>>(queries, Q, rv.dim, 4 * n4, qf, qnorm);
     tokengen_fast_kernel<<<grid, TF_THREADS, smem, s>>>(rv, Q, qf, qnorm, codes, groups_per_cta, qstride, astride, cbound, work, list, list_cap);
-    tokengen_recheck_kernel<<<148 * 2, 256, 0, s>>>(rv, queries, codes, work, list, list_cap);
+    tokengen_recheck_kernel<<<sm_count * 2, 256, 0, s>>>(rv, queries, codes, work, list, list_cap);
     if (cudaGetLastError() != cudaSuccess) return -1;
-    const int n = launch_tokengen_exact(s, rv, Q, queries, codes, work + 1);      // runs only after a worklist overflow
+    const int n = launch_tokengen_exact(s, rv, Q, queries, codes, work + 1, sm_count);      // runs only after a worklist overflow
     return n < 0 ? -1 : 3 + n;
 }
 

@@ -182,6 +182,27 @@ class GpuContext:
                                               N.ptr(out["n_ret"]), N.ptr(out["counters"])))
         return out
 
+    def search_tokens(self, codes, queries, k, probes, hard_cap, B, ham_threshold=0):
+        """QueryServiceImpl.search on the tokens' own codes (PIS:600): no TokenGen; a NaN/Inf query returns empty (QSI:137)."""
+        queries = np.ascontiguousarray(queries, dtype=np.float64)
+        if queries.ndim != 2 or queries.shape[1] != self.dim:
+            raise N.IllegalArgumentError(f"Query dimension mismatch: expected={self.dim} got={queries.shape[-1]}")
+        Q = queries.shape[0]
+        if codes is not None:
+            codes = np.ascontiguousarray(codes, dtype=np.uint64).reshape(Q, self.T * self.D, self.W)
+        out = dict(top_ids=np.full((Q, k), -1, dtype=np.int32), top_dist=np.full((Q, k), np.nan, dtype=np.float64),
+                   n_ret=np.zeros(Q, dtype=np.int32), counters=np.zeros((Q, N.COUNTERS), dtype=np.int64))
+        self._ck(self.lib.fspann_search_tokens(self.ctx, C.c_int64(Q), N.ptr(codes), N.ptr(queries), C.c_int32(k), C.c_int32(probes),
+                                               C.c_int64(hard_cap), C.c_int32(B), C.c_int32(ham_threshold), N.ptr(out["top_ids"]),
+                                               N.ptr(out["top_dist"]), N.ptr(out["n_ret"]), N.ptr(out["counters"])))
+        return out
+
+    def search_tokens_dev(self, Q, d_codes, d_queries, k, probes, hard_cap, B, ham_threshold, allow_retry, d_ids, d_dist, d_nret, d_counters=None):
+        self._ck(self.lib.fspann_search_tokens_dev(self.ctx, C.c_int64(Q), C.c_void_p(d_codes), C.c_void_p(d_queries), C.c_int32(k),
+                                                   C.c_int32(probes), C.c_int64(hard_cap), C.c_int32(B), C.c_int32(ham_threshold),
+                                                   C.c_int32(allow_retry), C.c_void_p(d_ids), C.c_void_p(d_dist), C.c_void_p(d_nret),
+                                                   C.c_void_p(d_counters) if d_counters else None))
+
     def search_batch_raw(self, Q, queries_addr, k, probes, hard_cap, B, ham_threshold, ids_addr, dist_addr, nret_addr, counters_addr):
         """Host-pointer call with caller-provided (e.g. pinned) buffers given as raw addresses."""
         self._ck(self.lib.fspann_search_batch(self.ctx, C.c_int64(Q), C.c_void_p(queries_addr), C.c_int32(k), C.c_int32(probes),

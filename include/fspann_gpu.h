@@ -188,17 +188,36 @@ int fspann_refine_batch_ex(fspann_ctx *ctx, int64_t Q, const double *queries, co
 
 /* ---- search (a4-a18): createToken + QueryServiceImpl.search for a batch, incl. the adaptive retry (QSI:327-337):
  * a query whose first pass returned < k results or decrypted < 10*k candidates is re-run once with 10 probes and
- * the second result is returned.  counters int64 [Q][FSPANN_COUNTERS] (may be NULL). */
+ * the second result is returned.  counters int64 [Q][FSPANN_COUNTERS] (may be NULL).  The retry decision is taken on the device; the
+ * host reads back two integers with the results, so a batch without retries costs one stream synchronisation.  A query holding NaN/Inf
+ * fails the call with FSPANN_E_ARG like createToken throws (Coding:357-359); the output buffers are then unspecified and the
+ * offending queries have touched no record. */
 int fspann_search_batch(fspann_ctx *ctx, int64_t Q, const double *queries, int32_t k, int32_t probes,
                         int64_t hard_cap, int32_t B, int32_t ham_threshold, int32_t *topk_ids_out,
                         double *topk_dist_out, int32_t *n_ret_out, int64_t *counters_out);
 
 /* Device-resident variant: d_queries, d_topk_ids, d_topk_dist, d_n_ret, d_counters are DEVICE pointers; work is
- * enqueued on the context stream and the call returns without synchronising.  The adaptive retry needs the
- * per-query first-pass counters on the host, so it is applied only when allow_retry != 0 (which synchronises). */
+ * enqueued on the context stream and the call returns without synchronising.  The adaptive retry needs the number of
+ * retrying queries on the host (two integers, decided on the device), so it is applied only when allow_retry != 0 (which synchronises
+ * once).  With allow_retry == 0 a query holding NaN/Inf returns empty (QSI:137) instead of failing the call. */
 int fspann_search_batch_dev(fspann_ctx *ctx, int64_t Q, const double *d_queries, int32_t k, int32_t probes,
                             int64_t hard_cap, int32_t B, int32_t ham_threshold, int32_t allow_retry,
                             int32_t *d_topk_ids, double *d_topk_dist, int32_t *d_n_ret, int64_t *d_counters);
+
+/* ---- search on the token's own codes: QueryServiceImpl.search(QueryToken) as written (QSI:100-352).  The reference routes on
+ * token.getBitCodes() (index/.../PartitionedIndexService.java:600) -- the codes the CLIENT computed in QueryTokenFactory.create /
+ * derive (query/.../QueryTokenFactory.java:98-131, 182-200) -- and never recomputes them from the decrypted query, so TokenGen runs
+ * once per query (in fspann_tokengen_batch, when the token is made) and not again here.  codes uint64 [Q][T*D][W] as produced by
+ * fspann_tokengen_batch; queries FP64 [Q][dim] = the decrypted token payloads (AGC:189-204).  Differences from fspann_search_batch:
+ * no TokenGen kernel; a query holding NaN/Inf does not fail the call, it returns an empty list and touches nothing (QSI:137) while the
+ * rest of the batch is served; codes == NULL fails with FSPANN_E_STATE ("QueryToken missing BitSet codes", PIS:604-606).  The adaptive
+ * retry re-routes the same codes with 10 probes (QSI:327-337).  The _dev variant takes device pointers (see fspann_search_batch_dev). */
+int fspann_search_tokens(fspann_ctx *ctx, int64_t Q, const uint64_t *codes, const double *queries, int32_t k, int32_t probes,
+                         int64_t hard_cap, int32_t B, int32_t ham_threshold, int32_t *topk_ids_out, double *topk_dist_out,
+                         int32_t *n_ret_out, int64_t *counters_out);
+int fspann_search_tokens_dev(fspann_ctx *ctx, int64_t Q, const uint64_t *d_codes, const double *d_queries, int32_t k, int32_t probes,
+                             int64_t hard_cap, int32_t B, int32_t ham_threshold, int32_t allow_retry, int32_t *d_topk_ids,
+                             double *d_topk_dist, int32_t *d_n_ret, int64_t *d_counters);
 
 /* ---- evaluation on the box ------------------------------------------------------------------------------
  * Exact ground truth = GroundtruthPrecompute.run (api/src/main/java/com/fspann/api/GroundtruthPrecompute.java:218-276): for every

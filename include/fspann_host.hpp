@@ -245,6 +245,15 @@ class QueryTokenFactory {
         return t;
     }
 
+    // QTF:182-200: the same token (codes, IV, ciphertext, version) with another topK -- no new TokenGen, no new encryption
+    QueryToken derive(const QueryToken *tok, int newTopK) const {
+        if (!tok) throw IllegalArgumentException("token is null");
+        if (newTopK <= 0) throw IllegalArgumentException("newTopK must be > 0");
+        QueryToken t = *tok;
+        t.topK = newTopK;
+        return t;
+    }
+
    private:
     PartitionedIndexService &index_;
     KeyManager &keys_;
@@ -265,11 +274,15 @@ class QueryServiceImpl {
         std::vector<std::vector<QueryResult>> out((size_t)Q);
         if (Q == 0) return out;
         const int dim = index_.dimension(), k = tokens[0].topK;
+        const size_t code_words = (size_t)index_.config().paper.tables * index_.config().paper.divisions * index_.W();
         std::vector<double> qs;
+        std::vector<uint64_t> codes;                                 // the tokens' OWN codes: Route runs on token.getBitCodes() (PIS:600)
         std::vector<int> keep;
         for (int i = 0; i < Q; i++) {
             const QueryToken &t = tokens[(size_t)i];
             if (t.topK != k) throw IllegalArgumentException("searchBatch needs one topK per batch (derive tokens per K like FSA:634)");
+            if (t.bitCodes.empty()) throw IllegalStateException("MSANNP violation: QueryToken missing BitSet codes");          // PIS:604-606
+            if (t.numTables != index_.config().paper.tables || t.bitCodes.size() != code_words) throw IllegalStateException("Token tables mismatch");
             std::vector<uint8_t> key;
             try { key = keys_.getVersion(t.version); } catch (const IllegalArgumentException &) { key = keys_.getVersion(keys_.getCurrentVersion()); }   // QSI:124-129
             const std::vector<double> q = detail::gcm_decrypt_doubles(key, t.iv, t.encryptedQuery);
@@ -277,6 +290,7 @@ class QueryServiceImpl {
             for (double v : q) finite = finite && std::isfinite(v);
             if (!finite) continue;                                                                              // QSI:137 -> empty result
             qs.insert(qs.end(), q.begin(), q.end());
+            codes.insert(codes.end(), t.bitCodes.begin(), t.bitCodes.end());
             keep.push_back(i);
         }
         const int R = (int)keep.size();
@@ -285,10 +299,11 @@ class QueryServiceImpl {
         std::vector<int32_t> ids((size_t)R * k), nret((size_t)R);
         std::vector<double> dist((size_t)R * k);
         counters_.assign((size_t)R * FSPANN_COUNTERS, 0);
-        index_.gpu().check(fspann_search_batch(index_.gpu().get(), R, qs.data(), k, index_.effectiveMaxProbes(), index_.hardCap(),
-                                               refineOverride_ > 0 ? refineOverride_ : rt.refinementLimit, rt.hammingPrefilterThreshold, ids.data(), dist.data(),
-                                               nret.data(), counters_.data()));
-        index_.clearProbeOverride();                                                                            // QSI:343 (finally)
+        const int rc = fspann_search_tokens(index_.gpu().get(), R, codes.data(), qs.data(), k, index_.effectiveMaxProbes(), index_.hardCap(),
+                                            refineOverride_ > 0 ? refineOverride_ : rt.refinementLimit, rt.hammingPrefilterThreshold, ids.data(),
+                                            dist.data(), nret.data(), counters_.data());
+        index_.clearProbeOverride();                                                                            // QSI:342-346 (finally: also when the search fails)
+        index_.gpu().check(rc);
         for (int j = 0; j < R; j++)
             for (int r = 0; r < nret[(size_t)j]; r++) out[(size_t)keep[(size_t)j]].push_back({std::to_string(ids[(size_t)j * k + r]), dist[(size_t)j * k + r]});
         const int64_t *c = &counters_[(size_t)(R - 1) * FSPANN_COUNTERS];                                       // getLast* describe the last query

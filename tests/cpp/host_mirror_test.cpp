@@ -31,6 +31,9 @@ typedef struct {
 void orc_search_batch(const orc_index_t *ix, const orc_store_t *st, const double *queries, int64_t q0, int64_t q1, const double *alpha, const double *r,
                       const double *omega, int k, int probes, int64_t hard_cap, int B, int ham_threshold, int32_t *top_ids, double *top_dist, int32_t *n_ret,
                       int64_t *counters);
+int orc_search(const orc_index_t *ix, const orc_store_t *st, const double *q_plain, const uint64_t *codes, int k, int probes, int64_t hard_cap, int B,
+               int ham_threshold, int32_t *top_ids, double *top_dist, int32_t *cand_ids, int32_t *cand_scores, uint8_t *verdict, int64_t *counters,
+               uint8_t *touched);
 }
 
 using namespace fspann;
@@ -151,6 +154,35 @@ int main() {
         }
     };
     same_as_oracle(res1, {1});
+
+    // ---- derive (QTF:182-200) keeps codes / IV / ciphertext; search routes on the token's OWN codes (PIS:600), never on codes
+    //      recomputed from the decrypted query: a token carrying query 1's codes and query 0's ciphertext gets query 1's candidates
+    {
+        const QueryToken d3 = sys.tokenFactory().derive(&tokens[2], 3);
+        CHECK(d3.topK == 3 && d3.bitCodes == tokens[2].bitCodes && d3.iv == tokens[2].iv && d3.encryptedQuery == tokens[2].encryptedQuery);
+        const auto r3 = sys.queryService().search(&d3);
+        CHECK(r3.size() == 3 && r3[0].id == res1[2][0].id && r3[2].id == res1[2][2].id);
+        CHECK(throws<IllegalArgumentException>([&] { sys.tokenFactory().derive(&tokens[2], 0); }));
+        CHECK(throws<IllegalArgumentException>([&] { sys.tokenFactory().derive(nullptr, 3); }));
+        QueryToken sw = tokens[0];
+        sw.bitCodes = tokens[1].bitCodes;
+        const auto rs = sys.queryService().search(&sw);
+        orc_index_t ix{dim, cfg.paper.tables, cfg.paper.divisions, m, cfg.paper.lambda, W, N, P, mn.data(), mx.data(), rep.data(), pids.data(), nullptr, 0};
+        const auto k1 = sys.keys().derive(1);
+        const int32_t kv1 = 1;
+        orc_store_t st{N, dim, sys.store_iv.data(), sys.store_ct.data(), sys.store_ver.data(), nullptr, nullptr, 1, &kv1, k1.data()};
+        std::vector<int32_t> oid((size_t)k), cid(65), csc(65);
+        std::vector<double> od((size_t)k);
+        std::vector<uint8_t> ver(65);
+        int64_t cnt[6];
+        const int n = orc_search(&ix, &st, queries.data(), tokens[1].bitCodes.data(), k, 5, sys.index().hardCap(), cfg.runtime.refinementLimit, 0, oid.data(),
+                                 od.data(), cid.data(), csc.data(), ver.data(), cnt, nullptr);
+        CHECK((int)rs.size() == n);
+        for (int r = 0; r < n; r++) CHECK(rs[(size_t)r].id == std::to_string(oid[(size_t)r]) && std::memcmp(&rs[(size_t)r].distance, &od[(size_t)r], 8) == 0);
+        QueryToken nocodes = tokens[0];
+        nocodes.bitCodes.clear();
+        CHECK(throws<IllegalStateException>([&] { sys.queryService().search(&nocodes); }));       // PIS:604-606
+    }
 
     // ---- Rotate -> v2, Migrate ids = 0 (mod 3) on the device: results must not move; Retire v1 is refused while records are bound
     CHECK(sys.rotateKeyOnly() == 2);

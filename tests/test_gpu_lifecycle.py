@@ -223,8 +223,10 @@ def test_facade_flow_matches_reference_search(world_factory):
             assert np.array_equal(t.bitCodes.reshape(-1, w.g.W), codes[q]) and t.version == 1 and len(t.encryptedQuery) == 8 * w.g.dim + 16
             cands = sys_.index.lookupCandidatesWithScores(t)
             ids, sc, raw, _ = O.route(w.ix, codes[q], 5, 20000)
-            assert [c[0] for c in cands] == ids[:64].tolist() and [c[1] for c in cands] == sc[:64].tolist()
+            assert [c[0] for c in cands] == ids.tolist() and [c[1] for c in cands] == sc.tolist()      # every unique candidate (PIS:690-696)
             assert sys_.index.getLastRawCandidateCount() == raw
+            assert sys_.index.getLastTouchedCount() == len(ids) and sys_.index.getLastTouchedIds() == ids.tolist()   # PIS:698-702
+            assert sys_.index.lookupCandidateIds(t, limit=64) == ids[:64].tolist()
         results = sys_.queryService.searchBatch(tokens)
         for q, res in enumerate(results):
             ref = O.search(w.ix, w.store, w.queries[q], codes[q], 10, 5, 20000, 64)
@@ -292,7 +294,7 @@ def test_rotate_migrate_retire_keep_results_invariant(world_factory):
 
 def test_large_batch_with_a_non_finite_query_is_rejected_by_the_device_check(world_factory):
     """Batches above 64k values skip the host scan: the device pass that compacts the queries also checks isValid (QSI:407-413);
-    the call fails like createToken would (Coding:357-359) and returns nothing."""
+    the call fails like createToken would (Coding:357-359); the output buffers are unspecified then."""
     w = world_factory(**W1)
     ctx = w.gpu_context()
     try:
