@@ -9,7 +9,16 @@ A "step" = one pass of the hot path over one batch of synthetic queries (BASELIN
 routing index and the record store and searches its own 10k batch per step (weak scaling, no data-path collective).
 `value`  = queries/sec with the query batches already resident in HBM (CUDA events on the library's stream).
 `e2e`    = the same through the host-buffer C-ABI call (pinned host queries -> H2D -> search -> D2H of results).
-The oracle (oracle/) is used ONLY for the cpu_baseline / --impl reference legs, as the thing being timed there.
+Further legs of the same JSON line (all outside the timed regions of value / e2e):
+  roofline.stage_frac / reuse_factor / no_reuse : the whole refine stage (group + verify + decrypt + top-k) against the HBM roofline, how
+                      many (query, candidate) pairs share one decrypted record, and the same stage with NO reuse (every pair names a
+                      different record);
+  sharded           : ONE batch over the store sharded by id range across the N GPUs through fspann_sharded_search_batch_dev (NCCL
+                      all-gathers inside the C library) -- strong scaling of config 4's split, checked against the unsharded result;
+  strong_replicated : ONE batch split N ways over replicated state (config 3's split) -- strong scaling without any collective;
+  configs           : (N=1) BASELINE configs 1, 3, the config-4 shape at a single-GPU size and the reference's published operating point
+                      SIFT_P6_BALANCED, each with a sample checked against the oracle.
+The oracle (oracle/) is used ONLY for the cpu_baseline / --impl reference legs (as the thing being timed) and as the checker of samples.
 """
 from __future__ import annotations
 
@@ -119,19 +128,20 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(self.sm)}
 
 
-def build_world(cfg: WL.Config, gpu, n_batches: int, rank: int):
+def build_world(cfg: WL.Config, gpu, n_batches: int, rank: int, quiet: bool = False):
     """Setup (host side, untimed): synthetic base set, GFunctions, encrypted store, greedy partitions; upload to HBM."""
     t0 = time.time()
+    log_ = (lambda *a: None) if quiet else log
     base = WL.base_vectors(cfg)
     alpha, r, omega = HS.build_gfunctions(base[:HS.MIN_SAMPLE_SIZE], cfg.m, cfg.lam, cfg.seed, cfg.T, cfg.D)
-    log(f"base {base.shape} + GFunctions in {time.time() - t0:.1f}s")
+    log_(f"base {base.shape} + GFunctions in {time.time() - t0:.1f}s")
     # Setup on the device (SURVEY 8f-2): coding of the base set + GreedyPartitioner.build per division, then bulk encryptToPoint
     setup = {}
     t0 = time.time()
     gpu.gfunctions_upload(cfg.dim, cfg.T, cfg.D, cfg.m, cfg.lam, alpha, r, omega)
     mn, mx, rep, ids = gpu.routing_build(base, HS.staged_order(cfg.N))
     setup["coding_and_partition_build_s"] = time.time() - t0
-    log(f"base codes + greedy partitions ({cfg.T * cfg.D} x {mn.shape[1]}) on the device in {time.time() - t0:.1f}s (incl. H2D of the base set and D2H of the index)")
+    log_(f"base codes + greedy partitions ({cfg.T * cfg.D} x {mn.shape[1]}) on the device in {time.time() - t0:.1f}s (incl. H2D of the base set and D2H of the index)")
     t0 = time.time()
     km = HS.KeyManager(WL.MASTER_KEY)
     iv = WL.record_ivs(cfg.N, cfg.base_seed + 5)
@@ -140,14 +150,105 @@ def build_world(cfg: WL.Config, gpu, n_batches: int, rank: int):
     ver = np.ones(cfg.N, dtype=np.int32)
     setup["encrypt_s"] = time.time() - t0
     gpu.store_upload(cfg.dim, iv, ct, ver)
-    log(f"encrypted store ({ct.nbytes / 1e9:.2f} GB) on the device in {setup['encrypt_s']:.1f}s")
-    batches = []
+    log_(f"encrypted store ({ct.nbytes / 1e9:.2f} GB) on the device in {setup['encrypt_s']:.1f}s")
+    batches = make_batches(cfg, n_batches, rank)
+    world = dict(alpha=alpha, r=r, omega=omega, mn=mn, mx=mx, rep=rep, ids=ids, iv=iv, ct=ct, ver=ver, keys={1: km.derive(1)}, base=base, setup=setup)
+    return world, batches
+
+
+def make_batches(cfg, n_batches: int, rank: int):
+    out = []
     for b in range(n_batches):
         qcfg = cfg.scaled(name=cfg.name)
         object.__setattr__(qcfg, "query_seed", cfg.query_seed + 7919 * b + 104729 * rank)
-        batches.append(WL.query_vectors(qcfg))
-    world = dict(alpha=alpha, r=r, omega=omega, mn=mn, mx=mx, rep=rep, ids=ids, iv=iv, ct=ct, ver=ver, keys={1: km.derive(1)}, base=base, setup=setup)
-    return world, batches
+        out.append(WL.query_vectors(qcfg))
+    return out
+
+
+class DevRunner:
+    """Device-resident buffers + timing of K steps of one search entry point on the library's stream."""
+
+    def __init__(self, gpu, torch, local_rank, Q, k):
+        self.gpu, self.torch, self.Q, self.k = gpu, torch, Q, k
+        self.stream = torch.cuda.ExternalStream(gpu.stream(), device=torch.device("cuda", local_rank))
+        self.ids = torch.empty((Q, k), dtype=torch.int32, device="cuda")
+        self.dist = torch.empty((Q, k), dtype=torch.float64, device="cuda")
+        self.nret = torch.empty((Q,), dtype=torch.int32, device="cuda")
+        self.cnt = torch.empty((Q, 6), dtype=torch.int64, device="cuda")
+
+    def timed(self, fn, K, Wm, barrier):
+        torch = self.torch
+        for i in range(Wm):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(self.stream)
+        for i in range(K):
+            fn(Wm + i)
+        e1.record(self.stream)
+        barrier()
+        return e0.elapsed_time(e1)
+
+    def result(self):
+        t = self.torch
+        t.cuda.synchronize(); self.gpu.sync()
+        return dict(top_ids=self.ids.cpu().numpy(), top_dist=self.dist.cpu().numpy(), n_ret=self.nret.cpu().numpy(), counters=self.cnt.cpu().numpy())
+
+
+def same_result(a, b, counters=True):
+    ok = np.array_equal(a["top_ids"], b["top_ids"]) and np.array_equal(a["top_dist"].view(np.uint64), b["top_dist"].view(np.uint64)) and \
+        np.array_equal(a["n_ret"], b["n_ret"])
+    return bool(ok and (not counters or np.array_equal(a["counters"], b["counters"])))
+
+
+def oracle_sample_check(cfg, world, gpu, queries, nq, threads):
+    """First nq queries through the oracle (all host threads) vs the GPU: ids exact, FP64 distances bit-exact, counters equal."""
+    O, ix, st = oracle_objects(cfg, world)
+    dt, ref = cpu_run(cfg, O, ix, st, queries[:nq], threads)
+    got = gpu.search_batch(queries[:nq], cfg.k, cfg.probes, cfg.hard_cap, cfg.B)
+    return same_result(got, ref), nq / dt
+
+
+def run_extra_config(name, cfg, torch, local_rank, steps, warmup, threads, log_fn):
+    """One of BASELINE's other configs on one GPU: Setup on the device, `steps` timed batches, a sample checked against the oracle."""
+    from fspann_query_system_b200.gpu import GpuContext
+    t0 = time.time()
+    gpu = GpuContext(local_rank)
+    try:
+        world, batches = build_world(cfg, gpu, min(steps + warmup, 3), 0, quiet=True)
+        Q, k = cfg.Q, cfg.k
+        run = DevRunner(gpu, torch, local_rank, Q, k)
+        d_b = [torch.from_numpy(b).cuda() for b in batches]
+        torch.cuda.synchronize()
+
+        def barrier():
+            torch.cuda.synchronize(); gpu.sync()
+
+        def step(i):
+            gpu.search_batch_dev(Q, d_b[i % len(d_b)].data_ptr(), k, cfg.probes, cfg.hard_cap, cfg.B, 0, 1, run.ids.data_ptr(), run.dist.data_ptr(),
+                                 run.nret.data_ptr(), run.cnt.data_ptr())
+        ms = run.timed(step, steps, warmup, barrier)
+        step(0)
+        stage = {kk: vv for kk, vv in gpu.stage_ms().items() if kk != "launches"}
+        res = run.result()
+        pairs = int(res["counters"][:, 5].sum())
+        touched = int(gpu.touched(clear=True).size)
+        stage_ms = stage["group"] + stage["verify"] + stage["decrypt"] + stage["topk"]
+        alg = pairs * (8 * cfg.dim + 36) + Q * (8 * cfg.dim + 12 * k)
+        peak, _ = load_peaks()
+        nq = min(Q, 64 if cfg.B > 4096 or cfg.N > 2_000_000 else 256)
+        ok, cpu_qps = oracle_sample_check(cfg, world, gpu, batches[0], nq, threads)
+        out = {"workload": f"{cfg.name}: N={cfg.N} d={cfg.dim} T={cfg.T} D={cfg.D} m={cfg.m} probes={cfg.probes} B={cfg.B} k={cfg.k} cap={cfg.hard_cap} Q={Q}",
+               "queries_per_s": Q * steps / (ms * 1e-3), "ms_per_batch": ms / steps, "stage_ms": stage, "route_path": {1: "fast", 2: "general"}.get(gpu.get_info("last_route_path"), "?"),
+               "refine_stage_frac_of_hbm": alg / (stage_ms * 1e-3) / 1e9 / peak if stage_ms > 0 else None,
+               "reuse_factor": pairs / max(touched, 1), "mean_returned": float(res["n_ret"].mean()), "retried_queries": int(res["counters"][:, 4].sum()),
+               "gpu_matches_oracle_on_sample": ok, "oracle_sample_queries": nq, "cpu_port_queries_per_s": cpu_qps, "cpu_threads": threads,
+               "setup_on_device_s": world["setup"], "leg_wall_s": None}
+        out["leg_wall_s"] = time.time() - t0
+        log_fn(f"config {name}: {out['queries_per_s']:.0f} q/s, {out['ms_per_batch']:.2f} ms/batch, route={out['route_path']}, oracle sample ok={ok}, {out['leg_wall_s']:.1f}s")
+        return out
+    finally:
+        gpu.close()
 
 
 def oracle_objects(cfg, world):
@@ -209,6 +310,9 @@ def main():
     ap.add_argument("--q", type=int, default=0, help="override batch size (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-mixed", action="store_true", help="skip the config-5 Rotate + Migrate leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the legs for BASELINE configs 1 / 3 / 4-shape and the published operating point")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the database-sharded and strong-scaling legs")
+    ap.add_argument("--extras", default="C1,C3,C4s,P6", help="which extra configs to run at N=1")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -317,6 +421,52 @@ def main():
     alg_bytes = pairs / K * (8 * dim + 36) + Q * (8 * dim + 12 * k)       # per pair 8d+36 B, per query 8d+12k B
     peak, peak_src = load_peaks()
     achieved = alg_bytes / (dec_ms * 1e-3) / 1e9 if dec_ms > 0 else 0.0
+    # the whole refine STAGE (group + verify + decrypt + top-k) against the same roofline, and how much of it is record reuse:
+    # reuse_factor = (query, candidate) pairs per distinct record decrypted in the batch
+    refine_stage_ms = (stage["group"] + stage["verify"] + stage["decrypt"] + stage["topk"]) / K
+    gpu.touched(clear=True)
+    step_dev(Wm)
+    barrier()
+    distinct = int(gpu.touched(clear=True).size)
+    pairs_one = int(d_cnt[:, 5].sum().item())
+    reuse = pairs_one / max(distinct, 1)
+    stage_achieved = alg_bytes / (refine_stage_ms * 1e-3) / 1e9 if refine_stage_ms > 0 else 0.0
+
+    # ---- no_reuse: the same refine stage when NO record is shared between pairs -- the candidate lists are a permutation of the store
+    #      (every record decrypted once and scored once), through fspann_refine_batch_dev.  This is what config 4's 100M records look like.
+    no_reuse = None
+    if rank == 0:
+        Bn = cfg.B
+        Qn = min(Q, cfg.N // Bn)
+        if Qn >= 8:
+            perm = np.random.default_rng(12345).permutation(cfg.N)[: Qn * Bn].astype(np.int32).reshape(Qn, Bn)
+            d_cand = torch.from_numpy(perm).cuda()
+            d_nc = torch.full((Qn,), Bn, dtype=torch.int32, device="cuda")
+            d_rk = torch.empty((Qn, k), dtype=torch.int32, device="cuda")
+            d_nd = torch.empty((Qn,), dtype=torch.int32, device="cuda")
+            torch.cuda.synchronize()
+
+            def step_nr(i):
+                gpu.refine_batch_dev(Qn, d_batches[i % n_batches].data_ptr(), d_cand.data_ptr(), d_nc.data_ptr(), Bn, k, d_ids.data_ptr(), d_dist.data_ptr(),
+                                     d_rk.data_ptr(), d_nret.data_ptr(), d_nd.data_ptr())
+            for i in range(Wm):
+                step_nr(i)
+            torch.cuda.synchronize(); gpu.sync()
+            n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n0.record(stream)
+            for i in range(K):
+                step_nr(Wm + i)
+            n1.record(stream)
+            torch.cuda.synchronize(); gpu.sync()
+            nr_ms = n0.elapsed_time(n1) / K
+            nr_bytes = Qn * Bn * (8 * dim + 36) + Qn * (8 * dim + 12 * k)
+            ok_nr = bool((d_nd == Bn).all().item())
+            no_reuse = {"ms_per_launch": nr_ms, "pairs": Qn * Bn, "distinct_records": Qn * Bn, "algorithmic_bytes": nr_bytes,
+                        "achieved": nr_bytes / (nr_ms * 1e-3) / 1e9, "frac": nr_bytes / (nr_ms * 1e-3) / 1e9 / peak, "all_decrypted": ok_nr,
+                        "what": "refine stage (group + verify + decrypt + top-k) with candidate lists = a permutation of the store: reuse factor 1.0",
+                        "limiter": "AES-256-GCM without AES/CLMUL instructions is bound by shared-memory table look-ups (LSU), not by HBM; see profiles/"}
+            gpu.touched(clear=True)
+            del d_cand
 
     # ---- e2e: host buffers through the public C-ABI call (pinned queries -> H2D -> search -> D2H results)
     h_q = [torch.from_numpy(b).pin_memory() for b in batches]
@@ -355,6 +505,68 @@ def main():
         recall = {"recall_at_k": float(rec.mean()), "k": k, "queries": nq_gt, "groundtruth_s": time.time() - t0,
                   "definition": "GroundtruthPrecompute.run + computeMetricsAtK (FSA:785-794), evaluated on the device"}
         log(f"recall@{k} = {recall['recall_at_k']:.4f} over {nq_gt} queries (ground truth + search + recall in {recall['groundtruth_s']:.1f}s)")
+
+
+    # ---- strong scaling of ONE batch: (a) split N ways over replicated state (config 3's split, no collective);
+    #      (b) the store sharded by id range across the N GPUs through fspann_sharded_search_batch_dev (config 4's split: NCCL
+    #      all-gathers of the candidate lists and of the per-shard top-k INSIDE the C library).  Same batches on every rank.
+    sharded = strong = None
+    if not args.no_sharded:
+        from fspann_query_system_b200 import distributed as DD
+        common = batches if rank == 0 else make_batches(cfg, n_batches, 0)
+        d_common = d_batches if rank == 0 else [torch.from_numpy(b).cuda() for b in common]
+        run = DevRunner(gpu, torch, local_rank, Q, k)
+        refs = []
+        for b in range(min(2, n_batches)):                               # unsharded results of the same batches (replicated store, every rank)
+            gpu.search_batch_dev(Q, d_common[b].data_ptr(), k, cfg.probes, cfg.hard_cap, cfg.B, 0, 1, run.ids.data_ptr(), run.dist.data_ptr(),
+                                 run.nret.data_ptr(), run.cnt.data_ptr())
+            refs.append(run.result())
+        if world_size > 1:
+            qlo, qhi = DD.split_batch(Q, rank, world_size)
+
+            def step_sr(i):
+                gpu.search_batch_dev(qhi - qlo, d_common[i % n_batches].data_ptr() + qlo * dim * 8, k, cfg.probes, cfg.hard_cap, cfg.B, 0, 1,
+                                     run.ids.data_ptr(), run.dist.data_ptr(), run.nret.data_ptr(), run.cnt.data_ptr())
+            sr_ms = run.timed(step_sr, K, Wm, barrier)
+            t = torch.tensor([sr_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sr_ms = float(t.item())
+            strong = {"ms_per_batch": sr_ms / K, "queries_per_s": Q * K / (sr_ms * 1e-3), "queries_per_gpu": qhi - qlo,
+                      "what": f"one {Q}-query batch split {world_size} ways, routing index + store replicated, no collective (max over ranks)"}
+        slo, shi = DD.shard_range(cfg.N, rank, world_size)
+        gpu.store_upload(dim, world["iv"][slo:shi], world["ct"][slo:shi], world["ver"][slo:shi], id_base=slo, n_global=cfg.N)
+        cid = [gpu.comm_unique_id() if (rank == 0 and world_size > 1) else None]
+        if world_size > 1:
+            dist.broadcast_object_list(cid, src=0)
+        gpu.comm_init(world_size, rank, cid[0])
+
+        def step_sh(i):
+            gpu.sharded_search_batch_dev(Q, d_common[i % n_batches].data_ptr(), k, cfg.probes, cfg.hard_cap, cfg.B, 1, run.ids.data_ptr(),
+                                         run.dist.data_ptr(), run.nret.data_ptr(), run.cnt.data_ptr())
+        sh_l0 = gpu.launch_count()
+        sh_ms = run.timed(step_sh, K, Wm, barrier)
+        sh_launches = (gpu.launch_count() - sh_l0) / (K + Wm)
+        eq = True
+        for b in range(len(refs)):
+            step_sh(b)
+            eq = eq and same_result(run.result(), refs[b])
+        sh_stage = gpu.sharded_stage_ms()
+        sh_refine = {kk: vv for kk, vv in gpu.stage_ms().items() if kk in ("group", "verify", "decrypt", "topk")}
+        if world_size > 1:
+            t = torch.tensor([sh_ms, 0.0 if eq else 1.0], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sh_ms, eq = float(t[0].item()), bool(t[1].item() == 0.0)
+        sharded = {"n_shards": world_size, "ms_per_batch": sh_ms / K, "queries_per_s": Q * K / (sh_ms * 1e-3), "equals_unsharded": eq,
+                   "stage_ms": {"route_my_slice": sh_stage["route"], "allgather_candidates": sh_stage["allgather_candidates"],
+                                "refine_my_shard": sh_stage["refine"], "allgather_topk_and_merge": sh_stage["allgather_topk_merge"], "refine_split": sh_refine},
+                   "allgather_bytes": sh_stage["gather_bytes"], "allgather_ms": sh_stage["allgather_candidates"] + sh_stage["allgather_topk_merge"],
+                   "gpu_launches_per_batch": sh_launches, "records_per_shard": shi - slo,
+                   "what": f"one {Q}-query batch, store sharded by id range over {world_size} GPU(s), routing index replicated; "
+                           "fspann_sharded_search_batch_dev: NCCL all-gather x2 + all-reduce inside libfspann_gpu.so (max over ranks)"}
+        log(f"sharded x{world_size}: {sharded['ms_per_batch']:.3f} ms/batch, equals unsharded: {eq}; stages {sharded['stage_ms']}")
+        gpu.comm_destroy()
+        if world_size == 1:                                               # later legs (config 5, CPU sample) use the whole store again
+            gpu.store_upload(dim, world["iv"], world["ct"], world["ver"])
 
     # ---- config 5: Rotate -> v2 + partial Migrate on the device, then the same batch again: results must not move (routing-ciphertext
     #      orthogonality) and the per-record-version path must cost the same.  Outside the timed regions above.
@@ -411,6 +623,22 @@ def main():
                         "sample": f"first {nq} queries of batch 0, {threads} threads; single-thread: {min(nq, 96) / dt1:.1f} queries/s on {min(nq, 96)} queries",
                         "single_thread_value": min(nq, 96) / dt1, "gpu_matches_oracle_on_sample": same}
 
+
+    # ---- the other BASELINE configs and the reference's published operating point, one GPU each (N=1 runs only)
+    configs_out = None
+    if rank == 0 and world_size == 1 and not args.no_extras:
+        configs_out = {}
+        threads = os.cpu_count() or 1
+        for name in [x for x in args.extras.split(",") if x]:
+            try:
+                configs_out[name] = run_extra_config(name, WL.CONFIGS[name], torch, local_rank, 3, 2, threads, log)
+            except Exception as e:      # noqa: BLE001  -- an extra leg must never take the headline number down with it
+                configs_out[name] = {"error": f"{type(e).__name__}: {e}"}
+                log(f"config {name} failed: {e}")
+        if "P6" in configs_out and "error" not in configs_out["P6"]:
+            configs_out["P6"]["published"] = {"art_ms_per_query": 2828.0, "recall_at_10": 0.838, "hardware": "Xeon E5-2630 v4, Java 21, one query at a time",
+                                              "source": "README.md:300, config_sift1m.json:59-71", "note": "published, different hardware and real SIFT1M data"}
+
     if rank == 0:
         out = {"metric": metric, "value": value, "unit": "queries/s", "n_gpus": world_size, "steps": K, "warmup": Wm, "ms_per_step": ms / K,
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
@@ -420,9 +648,16 @@ def main():
                "roofline": {"bound": "hbm", "kernel": "refine_decrypt_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                             "frac": achieved / peak if peak else None, "traffic": load_traffic(args.config == "C2" and not args.n and not args.q),
                             "traffic_unit": "bytes/launch (dram read+write, ncu; profiles/r1_decrypt_traffic.json)", "peak_source": peak_src,
-                            "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": dec_ms, "pairs_per_launch": pairs / K},
+                            "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": dec_ms, "pairs_per_launch": pairs / K,
+                            "stage_ms": refine_stage_ms, "stage_achieved": stage_achieved, "stage_frac": stage_achieved / peak if peak else None,
+                            "stage_what": "group + verify + decrypt + top-k: the whole refine stage, same algorithmic bytes",
+                            "reuse_factor": reuse, "distinct_records_per_launch": distinct,
+                            "reuse_note": "records are decrypted once per batch and scored once per (query, candidate) pair; frac and stage_frac count the "
+                                          "algorithmic bytes of every pair, so they scale with reuse_factor -- no_reuse is the same stage at reuse 1.0",
+                            "no_reuse": no_reuse},
                "stage_ms_per_step": {s: v / K for s, v in stage.items()},
                "recall": recall, "setup_on_device_s": world["setup"], "mixed_versions": mixed,
+               "sharded": sharded, "strong_replicated": strong, "configs": configs_out,
                "cpu_baseline": cpu_baseline}
         print(json.dumps(out), file=real_stdout, flush=True)
     gpu.close()

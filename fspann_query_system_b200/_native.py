@@ -22,6 +22,8 @@ EXPORTS = [
     "fspann_store_upload", "fspann_store_upload_shard", "fspann_store_update", "fspann_keys_set", "fspann_keys_retire", "fspann_tokengen_batch",
     "fspann_route_batch", "fspann_refine_batch", "fspann_refine_batch_ex", "fspann_search_batch", "fspann_search_batch_dev", "fspann_search_tokens", "fspann_search_tokens_dev", "fspann_touched_fetch",
     "fspann_last_stage_ms", "fspann_debug_decrypt", "fspann_set_option", "fspann_get_info", "fspann_migrate", "fspann_encrypt_batch", "fspann_routing_build", "fspann_groundtruth", "fspann_recall_batch", "fspann_route_batch_dev", "fspann_refine_batch_dev", "fspann_merge_topk_dev",
+    "fspann_comm_unique_id", "fspann_comm_init", "fspann_comm_destroy", "fspann_sharded_search_batch", "fspann_sharded_search_batch_dev",
+    "fspann_sharded_last_stage_ms",
 ]
 
 _libs = {}
@@ -40,6 +42,7 @@ def load(debug: bool = False):
     lib.fspann_ctx_launch_count.restype = C.c_int64
     lib.fspann_last_stage_ms.restype = C.c_int64
     lib.fspann_get_info.restype = C.c_int64
+    lib.fspann_sharded_last_stage_ms.restype = C.c_int64
     _libs[path] = lib
     return lib
 

@@ -10,67 +10,12 @@
 #include <map>
 #include <mutex>
 
-#include "fspann_internal.cuh"
+#include "abi_internal.cuh"
 
 using namespace fsp;
+using namespace fspabi;
 
-namespace {
-
-struct DevBuf {
-    void *p = nullptr;
-    size_t bytes = 0;
-};
-
-}  // namespace
-
-struct fspann_ctx {
-    int device = 0;
-    int sm_count = 1;                            // multiProcessorCount of ctx->device (set by fspann_ctx_create)
-    cudaStream_t stream = nullptr;
-    int32_t *h_pin = nullptr;                    // pinned host staging for the per-batch retry decision (n_ret, n_decrypted, flags)
-    size_t h_pin_ints = 0;
-    std::string err;
-    int64_t launches = 0;
-
-    // routing state
-    bool routing_ready = false;
-    RoutingView rv{};
-    DevBuf d_alpha, d_r, d_omega, d_keys, d_rep, d_ids, d_deleted, d_alpha_f, d_alpha_norm, s_tg_work, s_tg_list, s_tg_qf, s_tg_norm;
-    int opt_tokengen_exact = 0;  // run the exact FP64 TokenGen kernel alone (no FP32 pre-filter)
-    int64_t opt_tg_list_cap = 0; // test hook: clamp the re-check list (forces the overflow -> exact-kernel fallback)
-
-    // store
-    bool store_ready = false;
-    StoreView sv{};
-    DevBuf d_rec, d_keyring, d_hpow, d_shoup, d_te0, d_touched;
-    std::map<int32_t, std::vector<uint8_t>> keys;  // live versions -> raw key
-
-    // scratch (grow only)
-    DevBuf s_vis_part, s_vis_score, s_vis_n;
-    int opt_route_general = 0;   // force the general (sequential, cap-exact) Route kernel
-    int opt_route_wl_extra = -1; // test hook: clamp the fast path's dedicated worklist (forces the no-worklist fallback when exceeded)
-    int last_route_path = 0;     // 1 = shared-memory fast path, 2 = general path
-    bool last_queries_finite = true;
-    DevBuf s_queries, s_codes, s_cand_ids, s_cand_sc, s_ncand, s_raw, s_uniq_cnt, s_route_scratch, s_overflow;
-    DevBuf s_rec_verdict, s_qf32, s_qu8, s_f32_exact, s_vorder, s_voff, s_qfinite, s_retry_out, s_codes_in;
-    DevKeyRing ring_host{};
-    int32_t *want_rank = nullptr;
-    DevBuf s_cnt, s_flag, s_fill, s_uniq, s_pairs, s_bsums, s_totals, s_dist, s_verdict;
-    DevBuf s_topk_ids, s_topk_dist, s_topk_rank, s_nret, s_ndec, s_counters;
-    DevBuf s_stage_a, s_stage_b, s_stage_c;  // upload staging
-    DevBuf g_base, g_q, g_dist, g_ids, g_d2, g_flag, g_res, g_nret, g_rec;  // ground truth / recall
-    DevBuf b_codes, b_staged, b_scratch, b_ids, b_keys, b_rep, b_flag;  // device index build
-    int last_build_treeified = 0;
-    DevBuf m_list, m_gid, m_iv, m_verdict, m_flag, m_rec, m_vec, m_out_iv, m_out_ct, m_out_ver;  // Migrate / bulk encryption
-    DevBuf r_rows, r_queries, r_codes, r_topk_ids, r_topk_dist, r_nret, r_counters;  // retry subset
-    DevBuf t_cand_ids, t_cand_sc, t_ncand, t_raw, t_uniq_cnt, t_ndec;               // retry subset route outputs
-
-    cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    bool ev_valid = false;
-    int64_t last_call_launches = 0;
-};
-
-namespace {
+namespace fspabi {
 
 int fail(fspann_ctx *c, int code, const char *fmt, ...) {
     char buf[512];
@@ -81,20 +26,6 @@ int fail(fspann_ctx *c, int code, const char *fmt, ...) {
     if (c) c->err = buf;
     return code;
 }
-
-#define CK(call)                                                                                          \
-    do {                                                                                                  \
-        cudaError_t e__ = (call);                                                                         \
-        if (e__ != cudaSuccess) return fail(ctx, e__ == cudaErrorMemoryAllocation ? FSPANN_E_NOMEM : FSPANN_E_CUDA, \
-                                            "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
-    } while (0)
-
-#define LAUNCHED(expr)                                                                              \
-    do {                                                                                            \
-        int n__ = (expr);                                                                           \
-        if (n__ < 0) return fail(ctx, FSPANN_E_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(cudaGetLastError()), __FILE__, __LINE__); \
-        ctx->launches += n__;                                                                       \
-    } while (0)
 
 int ensure(fspann_ctx *ctx, DevBuf &b, size_t bytes) {
     if (bytes == 0) bytes = 16;
@@ -107,7 +38,6 @@ int ensure(fspann_ctx *ctx, DevBuf &b, size_t bytes) {
     b.bytes = want;
     return 0;
 }
-#define ENSURE(buf, bytes) do { int rc__ = ensure(ctx, buf, bytes); if (rc__) return rc__; } while (0)
 
 void release(DevBuf &b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.bytes = 0; }
 
@@ -288,7 +218,7 @@ bool all_finite(const double *v, int64_t n) {
     return true;
 }
 
-}  // namespace
+}  // namespace fspabi
 
 extern "C" {
 
@@ -333,6 +263,7 @@ void fspann_ctx_destroy(fspann_ctx *ctx) {
                       &ctx->b_codes, &ctx->b_staged, &ctx->b_scratch, &ctx->b_ids, &ctx->b_keys, &ctx->b_rep, &ctx->b_flag,
                       &ctx->m_list, &ctx->m_gid, &ctx->m_iv, &ctx->m_verdict, &ctx->m_flag, &ctx->m_rec, &ctx->m_vec, &ctx->m_out_iv, &ctx->m_out_ct, &ctx->m_out_ver};
     for (DevBuf *b : bufs) release(*b);
+    sharded_release(ctx);
     for (int i = 0; i < 7; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
@@ -875,7 +806,8 @@ int fspann_refine_batch_ex(fspann_ctx *ctx, int64_t Q, const double *queries, co
 
 // One full pass (tokengen -> route -> refine -> counters) over device-resident queries.  d_codes_in != nullptr: the token's own
 // codes are routed on (PIS:600 token.getBitCodes()) and TokenGen does not run.
-static int search_pass(fspann_ctx *ctx, int64_t Q, const double *d_queries, const uint64_t *d_codes_in, int k, int probes, int64_t hard_cap, int B,
+namespace fspabi {
+int search_pass(fspann_ctx *ctx, int64_t Q, const double *d_queries, const uint64_t *d_codes_in, int k, int probes, int64_t hard_cap, int B,
                        int retried, int32_t *d_topk_ids, double *d_topk_dist, int32_t *d_nret, int64_t *d_counters, bool main_pass) {
     const RoutingView &rv = ctx->rv;
     DevBuf &b_codes = main_pass ? ctx->s_codes : ctx->r_codes;
@@ -904,6 +836,7 @@ static int search_pass(fspann_ctx *ctx, int64_t Q, const double *d_queries, cons
                                  (const int32_t *)b_nc.p, retried, d_counters, (const uint8_t *)ctx->s_qfinite.p));
     return 0;
 }
+}  // namespace fspabi
 
 namespace {
 struct HostOut {            // host result buffers of the host-pointer entry points (nullptr members are skipped)

@@ -819,25 +819,35 @@ int launch_queries_to_f32(cudaStream_t s, const double *q, float *out, uint8_t *
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
-// Adaptive retry decision on the device (QSI:327-337 + 444-447): rows[] = the queries whose first pass decrypted something but returned
-// < k results or decrypted < 10*k candidates; out[0] = their number, out[1] = 1 when some query of the batch holds NaN/Inf.
-__global__ void retry_select_kernel(int64_t Q, int k, const int32_t *__restrict__ n_ret, const int32_t *__restrict__ n_dec, const int32_t *__restrict__ exact,
-                                    int32_t *__restrict__ rows, int32_t *__restrict__ out) {
-    const int lane = threadIdx.x & 31;
-    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool need = false;
-    if (q < Q) { const int nd = n_dec[q]; need = nd > 0 && (n_ret[q] < k || nd < 10 * k); }   // QSI:293: nothing decrypted -> plain return, no retry
-    const unsigned bal = __ballot_sync(0xffffffffu, need);
-    int base = 0;
-    if (lane == 0 && bal) base = atomicAdd(&out[0], __popc(bal));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (need) rows[base + __popc(bal & ((1u << lane) - 1u))] = (int32_t)q;
-    if (q == 0) out[1] = exact[2] == 0 ? 1 : 0;
+// Adaptive retry decision on the device (QSI:327-337 + 444-447): rows[] = the queries, IN INCREASING ORDER, whose first pass decrypted
+// something but returned < k results or decrypted < 10*k candidates; out[0] = their number, out[1] = 1 when some query of the batch
+// holds NaN/Inf.  One 1024-thread block, ordered compaction (the sharded search needs the same row order on every rank).
+__global__ void __launch_bounds__(1024) retry_select_kernel(int64_t Q, int k, const int32_t *__restrict__ n_ret, const int32_t *__restrict__ n_dec,
+                                                            const int32_t *__restrict__ exact, int32_t *__restrict__ rows, int32_t *__restrict__ out) {
+    __shared__ int s_w[32];
+    __shared__ int s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int64_t q0 = 0; q0 < Q; q0 += 1024) {
+        const int64_t q = q0 + tid;
+        bool need = false;
+        if (q < Q) { const int nd = n_dec[q]; need = nd > 0 && (n_ret[q] < k || nd < 10 * k); }   // QSI:293: nothing decrypted -> plain return, no retry
+        const unsigned bal = __ballot_sync(0xffffffffu, need);
+        if (lane == 0) s_w[warp] = __popc(bal);
+        __syncthreads();
+        int before = s_base, total = 0;
+        for (int w = 0; w < 32; w++) { const int c = s_w[w]; if (w < warp) before += c; total += c; }
+        if (need) rows[before + __popc(bal & ((1u << lane) - 1u))] = (int32_t)q;
+        __syncthreads();
+        if (tid == 0) s_base += total;
+        __syncthreads();
+    }
+    if (tid == 0) { out[0] = s_base; out[1] = exact[2] == 0 ? 1 : 0; }
 }
 int launch_retry_select(cudaStream_t s, int64_t Q, int k, const int32_t *n_ret, const int32_t *n_dec, const int32_t *exact, int32_t *rows, int32_t *out) {
     if (Q <= 0) return 0;
-    if (cudaMemsetAsync(out, 0, 2 * sizeof(int32_t), s) != cudaSuccess) return -1;
-    retry_select_kernel<<<(unsigned)((Q + 255) / 256), 256, 0, s>>>(Q, k, n_ret, n_dec, exact, rows, out);
+    retry_select_kernel<<<1, 1024, 0, s>>>(Q, k, n_ret, n_dec, exact, rows, out);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
@@ -905,9 +915,72 @@ __global__ void __launch_bounds__(TK_THREADS) refine_topk_kernel(RefineParams p)
     if (tid == 0) { p.n_ret[q] = eff; if (p.n_dec) p.n_dec[q] = total_ok; }
 }
 
+// Register-resident form for candidate lists of <= TK_THREADS * E entries (B <= 1024 with E = 8): every thread loads its E (distance,
+// verdict) entries ONCE (rank r = tid + TK_THREADS * j, coalesced), then k rounds of: thread-local minimum -> warp shuffle minimum ->
+// four per-warp minima through shared memory -> the owner retires the selected entry.  One __syncthreads per round, no re-reads.
+template <int E>
+__global__ void __launch_bounds__(TK_THREADS) refine_topk_reg_kernel(RefineParams p) {
+    __shared__ unsigned long long s_key[2][TK_THREADS / 32];
+    __shared__ int s_rank[2][TK_THREADS / 32];
+    __shared__ int s_ndec[TK_THREADS / 32];
+    const int64_t q = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = p.n_cand[q];
+    const double *dist = p.dist + (size_t)q * p.stride;
+    const uint8_t *ver = p.verdict + (size_t)q * p.stride;
+    unsigned long long key[E];
+    int ndec = 0;
+#pragma unroll
+    for (int j = 0; j < E; j++) {
+        const int r = tid + TK_THREADS * j;
+        key[j] = ~0ull;
+        if (r < n && ver[r] == FSPANN_V_OK) { key[j] = (unsigned long long)__double_as_longlong(dist[r]); ndec++; }   // dist >= +0.0: bits order like values
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) ndec += __shfl_xor_sync(0xffffffffu, ndec, o);
+    if (lane == 0) s_ndec[warp] = ndec;
+    __syncthreads();
+    int total_ok = 0;
+#pragma unroll
+    for (int w = 0; w < TK_THREADS / 32; w++) total_ok += s_ndec[w];
+    const int eff = min(p.k, total_ok);
+    for (int round = 0; round < eff; round++) {
+        unsigned long long best = ~0ull; int best_r = 0x7fffffff;
+#pragma unroll
+        for (int j = 0; j < E; j++) if (key[j] < best) { best = key[j]; best_r = tid + TK_THREADS * j; }   // ties: the lower rank (smaller j) stays
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const unsigned long long ok = __shfl_xor_sync(0xffffffffu, best, o);
+            const int orr = __shfl_xor_sync(0xffffffffu, best_r, o);
+            if (ok < best || (ok == best && orr < best_r)) { best = ok; best_r = orr; }
+        }
+        const int buf = round & 1;
+        if (lane == 0) { s_key[buf][warp] = best; s_rank[buf][warp] = best_r; }
+        __syncthreads();
+        unsigned long long b = s_key[buf][0]; int br = s_rank[buf][0];
+#pragma unroll
+        for (int w = 1; w < TK_THREADS / 32; w++) { const unsigned long long kk = s_key[buf][w]; const int rr = s_rank[buf][w]; if (kk < b || (kk == b && rr < br)) { b = kk; br = rr; } }
+        if ((br & (TK_THREADS - 1)) == tid) {                      // the owner retires the entry and emits the result (QSI:298-316)
+#pragma unroll
+            for (int j = 0; j < E; j++) if (j == br / TK_THREADS) key[j] = ~0ull;
+            p.topk_ids[(size_t)q * p.k + round] = p.cand_ids[(size_t)q * p.stride + br];
+            p.topk_dist[(size_t)q * p.k + round] = __longlong_as_double((long long)b);
+            if (p.topk_rank) p.topk_rank[(size_t)q * p.k + round] = br;
+        }
+    }
+    for (int i = eff + tid; i < p.k; i += TK_THREADS) {
+        p.topk_ids[(size_t)q * p.k + i] = -1;
+        p.topk_dist[(size_t)q * p.k + i] = __longlong_as_double(0x7ff8000000000000ll);
+        if (p.topk_rank) p.topk_rank[(size_t)q * p.k + i] = 0x7fffffff;
+    }
+    if (tid == 0) { p.n_ret[q] = eff; if (p.n_dec) p.n_dec[q] = total_ok; }
+}
+
 int launch_refine_topk(cudaStream_t s, const RefineParams &p) {
     if (p.Q <= 0) return 0;
-    refine_topk_kernel<<<(unsigned)p.Q, TK_THREADS, 0, s>>>(p);
+    if (p.stride <= TK_THREADS * 8) refine_topk_reg_kernel<8><<<(unsigned)p.Q, TK_THREADS, 0, s>>>(p);
+    else if (p.stride <= TK_THREADS * 16) refine_topk_reg_kernel<16><<<(unsigned)p.Q, TK_THREADS, 0, s>>>(p);
+    else refine_topk_kernel<<<(unsigned)p.Q, TK_THREADS, 0, s>>>(p);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

@@ -258,6 +258,46 @@ class GpuContext:
         self._ck(self.lib.fspann_merge_topk_dev(self.ctx, C.c_int32(S), C.c_int64(Q), C.c_int32(k), C.c_void_p(d_dist), C.c_void_p(d_rank),
                                                 C.c_void_p(d_ids), C.c_void_p(d_out_ids), C.c_void_p(d_out_dist), C.c_void_p(d_out_nret)))
 
+    # ---- database-sharded search as one call: the NCCL collectives run inside the library (include/fspann_gpu.h)
+    def comm_unique_id(self) -> bytes:
+        buf = (C.c_uint8 * 128)()
+        rc = self.lib.fspann_comm_unique_id(buf)
+        if rc != N.OK:
+            raise N.IllegalStateError("NCCL unavailable: fspann_comm_unique_id failed (libnccl.so.2 not loadable; set FSPANN_NCCL_LIB)")
+        return bytes(buf)
+
+    def comm_init(self, n_ranks: int, rank: int, comm_id: bytes | None = None):
+        """COLLECTIVE over the n_ranks contexts holding the shards of one store (rank r holds the r-th id range)."""
+        buf = (C.c_uint8 * 128).from_buffer_copy(comm_id) if comm_id is not None else None
+        self._ck(self.lib.fspann_comm_init(self.ctx, C.c_int32(n_ranks), C.c_int32(rank), buf))
+
+    def comm_destroy(self):
+        self._ck(self.lib.fspann_comm_destroy(self.ctx))
+
+    def sharded_search_batch(self, queries, k, probes, hard_cap, B):
+        """COLLECTIVE: every rank passes the same batch and gets the same (unsharded-identical) result."""
+        queries = np.ascontiguousarray(queries, dtype=np.float64)
+        if queries.ndim != 2 or queries.shape[1] != self.dim:
+            raise N.IllegalArgumentError(f"Query dimension mismatch: expected={self.dim} got={queries.shape[-1]}")
+        Q = queries.shape[0]
+        out = dict(top_ids=np.full((Q, k), -1, dtype=np.int32), top_dist=np.full((Q, k), np.nan, dtype=np.float64),
+                   n_ret=np.zeros(Q, dtype=np.int32), counters=np.zeros((Q, N.COUNTERS), dtype=np.int64))
+        self._ck(self.lib.fspann_sharded_search_batch(self.ctx, C.c_int64(Q), N.ptr(queries), C.c_int32(k), C.c_int32(probes), C.c_int64(hard_cap),
+                                                      C.c_int32(B), N.ptr(out["top_ids"]), N.ptr(out["top_dist"]), N.ptr(out["n_ret"]),
+                                                      N.ptr(out["counters"])))
+        return out
+
+    def sharded_search_batch_dev(self, Q, d_queries, k, probes, hard_cap, B, allow_retry, d_ids, d_dist, d_nret, d_counters=None):
+        self._ck(self.lib.fspann_sharded_search_batch_dev(self.ctx, C.c_int64(Q), C.c_void_p(d_queries), C.c_int32(k), C.c_int32(probes),
+                                                          C.c_int64(hard_cap), C.c_int32(B), C.c_int32(allow_retry), C.c_void_p(d_ids),
+                                                          C.c_void_p(d_dist), C.c_void_p(d_nret), C.c_void_p(d_counters) if d_counters else None))
+
+    def sharded_stage_ms(self):
+        out = (C.c_float * 4)()
+        nbytes = C.c_int64(0)
+        n = self.lib.fspann_sharded_last_stage_ms(self.ctx, out, C.byref(nbytes))
+        return dict(route=out[0], allgather_candidates=out[1], refine=out[2], allgather_topk_merge=out[3], gather_bytes=int(nbytes.value), launches=int(n))
+
     def touched(self, clear: bool = False) -> np.ndarray:
         words = (self.N + 31) // 32
         bm = np.zeros(words, dtype=np.uint32)

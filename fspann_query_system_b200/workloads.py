@@ -55,7 +55,12 @@ C1 = Config("C1-sift10k", 10_000, 128, 100, 4, 8, 24, 2, 13, 5, 256, 10, 20_000,
 C2 = Config("C2-sift1m", 1_000_000, 128, 10_000, 8, 8, 24, 2, 13, 5, 1024, 10, 24_000, "sift", 1002, 2002, 4096)
 C3 = Config("C3-glove1.2m", 1_200_000, 100, 10_000, 8, 8, 22, 2, 13, 5, 1024, 10, 24_000, "glove", 1003, 2003)
 C4 = Config("C4-deep100m", 100_000_000, 96, 10_000, 8, 8, 24, 2, 13, 5, 1024, 10, 24_000, "deep", 1004, 2004)
-CONFIGS = {"C1": C1, "C2": C2, "C3": C3, "C4": C4, "C5": C2}
+# config 4's shape (Deep-like 96-d, T = D = 8) at a size one GPU's host can build in seconds: the bench's single-GPU stand-in for C4
+C4S = Config("C4s-deep4m", 4_000_000, 96, 10_000, 8, 8, 24, 2, 13, 5, 1024, 10, 24_000, "deep", 1004, 2004)
+# the reference's only published operating point (README.md:300, ART 2828 ms): profile SIFT_P6_BALANCED of config_sift1m.json:59-71 --
+# tables 6, probeOverride 6, refinementLimit 16000, maxGlobalCandidates 20000 -- queried at MAX_K = 100 like FSA.runQueries (FSA:634)
+P6 = Config("P6-sift1m-balanced", 1_000_000, 128, 1_000, 6, 8, 24, 2, 13, 6, 16_000, 100, 20_000, "sift", 1002, 2002, 4096)
+CONFIGS = {"C1": C1, "C2": C2, "C3": C3, "C4": C4, "C4s": C4S, "C5": C2, "P6": P6}
 
 
 def _sift(n: int, dim: int, centres: int, seed: int, centre_seed: int) -> np.ndarray:

@@ -249,6 +249,37 @@ int fspann_refine_batch_dev(fspann_ctx *ctx, int64_t Q, const double *d_queries,
 int fspann_merge_topk_dev(fspann_ctx *ctx, int32_t n_shards, int64_t Q, int32_t k, const double *d_dist, const int32_t *d_rank,
                           const int32_t *d_ids, int32_t *d_out_ids, double *d_out_dist, int32_t *d_out_n_ret);
 
+/* ---- database-sharded search as ONE call (config 4): the NCCL collectives run inside this library -------------------------------
+ * One context per GPU, each holding the replicated routing state and ITS shard of the store (fspann_store_upload_shard); the W contexts
+ * form a communicator.  They may live in W processes (one per GPU) or in W threads of one process (one JVM, a thread per GPU).
+ *   fspann_comm_unique_id : any one participant draws an id (ncclGetUniqueId) and hands the 128 bytes to the others;
+ *   fspann_comm_init      : COLLECTIVE -- every participant calls it with the same id, n_ranks and its own rank (ncclCommInitRank on the
+ *                           context's device).  n_ranks == 1 needs no id and no NCCL.  rank r must hold the r-th id range of the store.
+ *   fspann_sharded_search_batch(_dev) : COLLECTIVE -- every participant calls it with the SAME query batch and parameters and receives
+ *                           the same result, bit-identical to fspann_search_batch on an unsharded store: rank r codes + routes rows
+ *                           [r*ceil(Q/W), ...) of the batch (QTF:98-131, PIS:592-715), the ordered candidate lists are all-gathered
+ *                           (Q*B*4 bytes), every rank refines the candidates its shard holds for all queries (QSI:238-322), the per-shard
+ *                           top-k (distance, candidate rank, id) is all-gathered and merged on (distance, rank) -- the reference's stable
+ *                           sort (QSI:298) -- and the adaptive retry (QSI:327-337) is decided from the merged counts.  counters as in
+ *                           fspann_search_batch (candDecrypted = sum over the shards).  The host-pointer variant rejects NaN/Inf queries
+ *                           with FSPANN_E_ARG before any collective; the _dev variant takes device pointers and synchronises only for
+ *                           the retry decision (allow_retry != 0).
+ * NCCL (libnccl.so.2) is loaded at run time: the copy already present in the process, else the system's, else $FSPANN_NCCL_LIB.
+ * Without it fspann_comm_unique_id / fspann_comm_init (n_ranks > 1) fail with FSPANN_E_STATE and everything else works. */
+#define FSPANN_COMM_ID_BYTES 128
+int fspann_comm_unique_id(uint8_t id_out[FSPANN_COMM_ID_BYTES]);
+int fspann_comm_init(fspann_ctx *ctx, int32_t n_ranks, int32_t rank, const uint8_t id[FSPANN_COMM_ID_BYTES]);
+int fspann_comm_destroy(fspann_ctx *ctx);
+int fspann_sharded_search_batch(fspann_ctx *ctx, int64_t Q, const double *queries, int32_t k, int32_t probes, int64_t hard_cap, int32_t B,
+                                int32_t *topk_ids_out, double *topk_dist_out, int32_t *n_ret_out, int64_t *counters_out);
+int fspann_sharded_search_batch_dev(fspann_ctx *ctx, int64_t Q, const double *d_queries, int32_t k, int32_t probes, int64_t hard_cap,
+                                    int32_t B, int32_t allow_retry, int32_t *d_topk_ids, double *d_topk_dist, int32_t *d_n_ret,
+                                    int64_t *d_counters);
+/* Device time of the last sharded call's first pass (CUDA events on the context stream), milliseconds: out[0] = TokenGen + Route of this
+ * rank's slice, out[1] = all-gather of the candidate lists, out[2] = Refine on this shard (fspann_last_stage_ms splits it further),
+ * out[3] = all-gather of the per-shard top-k + merge.  *gather_bytes_out = bytes this rank received through the collectives. */
+int64_t fspann_sharded_last_stage_ms(fspann_ctx *ctx, float out[4], int64_t *gather_bytes_out);
+
 /* Touched set (QSI:262, QSI:348-350 reencTracker.record): bitmap over ids (bit id&31 of word id>>5, N bits) of
  * every record that reached verdict OK since the last clear.  Feeds the host's selective re-encryption. */
 int fspann_touched_fetch(fspann_ctx *ctx, uint32_t *bitmap_out, int64_t n_words, int32_t clear);

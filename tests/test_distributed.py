@@ -237,3 +237,82 @@ def test_device_resident_sharded_blocks_and_merge_kernel(world_factory):
         for c in shards:
             c.close()
         full.close()
+
+
+# ---- database-sharded search as ONE C-ABI call (NCCL inside libfspann_gpu.so) -------------------------------------------------------
+def _upload_shard(w, dev, lo, hi, n_ranks, rank, comm_id):
+    from fspann_query_system_b200.gpu import GpuContext
+    g, ix = w.g, w.ix
+    c = GpuContext(dev)
+    c.routing_upload(g.dim, g.T, g.D, g.m, g.lam, g.alpha, g.r, g.omega, ix.min_key, ix.max_key, ix.rep, ix.ids)
+    for v, key in w.store.keys.items():
+        c.keys_set(v, key)
+    c.store_upload(g.dim, w.store.iv[lo:hi], w.store.ct[lo:hi], w.store.key_version[lo:hi], id_base=lo, n_global=w.cfg.N)
+    c.comm_init(n_ranks, rank, comm_id)
+    return c
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k,B", [(10, 256), (100, 256)])
+def test_sharded_abi_single_rank_equals_unsharded(world_factory, k, B):
+    """fspann_sharded_search_batch with a one-rank communicator (no NCCL needed) walks the whole sharded pipeline -- slice routing,
+    refine with candidate ranks, merge, device-side retry (k=100, B=256 retries every query) -- and must equal fspann_search_batch."""
+    w = world_factory(N=20000, dim=128, Q=64, T=4, D=8, m=24, lam=2)
+    full = w.gpu_context()
+    sh = _upload_shard(w, 0, 0, w.cfg.N, 1, 0, None)
+    try:
+        ref = full.search_batch(w.queries, k, 5, 20000, B)
+        got = sh.sharded_search_batch(w.queries, k, 5, 20000, B)
+        for key in ("top_ids", "n_ret", "counters"):
+            assert np.array_equal(got[key], ref[key]), key
+        assert np.array_equal(got["top_dist"].view(np.uint64), ref["top_dist"].view(np.uint64))
+        assert (got["counters"][:, 4] == (1 if k == 100 else 0)).all()
+        st = sh.sharded_stage_ms()
+        assert st["launches"] > 0 and st["gather_bytes"] == 0
+        bad = w.queries.copy(); bad[5, 7] = np.inf
+        with pytest.raises(Exception):
+            sh.sharded_search_batch(bad, k, 5, 20000, B)
+    finally:
+        full.close(); sh.close()
+
+
+@pytest.mark.gpu
+def test_sharded_abi_two_gpus_one_process_threads(world_factory):
+    """Two contexts on two GPUs in ONE process (a thread per GPU, the JVM deployment of INTEGRATION.md): comm_init + sharded search
+    from both threads; both ranks return the unsharded result bit for bit, with mixed key versions and the retry pass."""
+    import threading
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    w = world_factory(N=20000, dim=128, Q=64, T=4, D=8, m=24, lam=2, n_versions=2)
+    full = w.gpu_context()
+    cid = full.comm_unique_id()
+    half = w.cfg.N // 2 + 37
+    outs, errs, ctxs = {}, [], [None, None]
+
+    def run(rank):
+        try:
+            lo, hi = (0, half) if rank == 0 else (half, w.cfg.N)
+            c = _upload_shard(w, rank, lo, hi, 2, rank, cid)
+            ctxs[rank] = c
+            outs[rank] = [c.sharded_search_batch(w.queries, k, 5, 20000, 256) for k in (10, 100)]
+            outs[(rank, "stage")] = c.sharded_stage_ms()
+        except Exception as e:      # noqa: BLE001
+            errs.append(e)
+    ts = [threading.Thread(target=run, args=(r,)) for r in range(2)]
+    [t.start() for t in ts]; [t.join(timeout=300) for t in ts]
+    try:
+        assert not errs, errs
+        for i, k in enumerate((10, 100)):
+            ref = full.search_batch(w.queries, k, 5, 20000, 256)
+            for rank in range(2):
+                got = outs[rank][i]
+                for key in ("top_ids", "n_ret", "counters"):
+                    assert np.array_equal(got[key], ref[key]), (rank, k, key)
+                assert np.array_equal(got["top_dist"].view(np.uint64), ref["top_dist"].view(np.uint64))
+        assert outs[(0, "stage")]["gather_bytes"] > 0
+    finally:
+        full.close()
+        for c in ctxs:
+            if c is not None:
+                c.close()

@@ -27,6 +27,8 @@ def main():
     ap.add_argument("--config", default="C2")
     ap.add_argument("--records", type=int, default=0, help="override N")
     ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--python-collectives", action="store_true", help="use distributed.DeviceShardedSearcher (torch.distributed all-gathers) "
+                    "instead of fspann_sharded_search_batch_dev (NCCL inside the C library)")
     args = ap.parse_args()
     real_stdout = os.fdopen(os.dup(1), "w"); os.dup2(2, 1)
     rank, world, lr = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -47,7 +49,27 @@ def main():
     iv = WL.record_ivs(cfg.N, cfg.base_seed + 5)
     ct = gpu.encrypt_batch(np.arange(lo, hi, dtype=np.int32), base[lo:hi], iv[lo:hi], 1)
     gpu.store_upload(cfg.dim, iv[lo:hi], ct, np.ones(hi - lo, dtype=np.int32), id_base=lo, n_global=cfg.N)   # this rank's shard only
-    searcher = DD.DeviceShardedSearcher(gpu)
+    if args.python_collectives:
+        searcher = DD.DeviceShardedSearcher(gpu)
+    else:                                                                            # the product path: ONE C-ABI call per batch
+        ids = [gpu.comm_unique_id() if rank == 0 else None]
+        if world > 1:
+            dist.broadcast_object_list(ids, src=0)
+        gpu.comm_init(world, rank, ids[0])
+
+        class AbiSearcher:
+            def __init__(self):
+                self.stream = torch.cuda.ExternalStream(gpu.stream(), device=torch.device("cuda", lr))
+
+            def search_batch_dev(self, dq, k, probes, hard_cap, B):
+                Q = dq.shape[0]
+                o = dict(top_ids=torch.empty((Q, k), dtype=torch.int32, device="cuda"), top_dist=torch.empty((Q, k), dtype=torch.float64, device="cuda"),
+                         n_ret=torch.empty((Q,), dtype=torch.int32, device="cuda"), counters=torch.empty((Q, 6), dtype=torch.int64, device="cuda"))
+                torch.cuda.current_stream().synchronize()
+                gpu.sharded_search_batch_dev(Q, dq.data_ptr(), k, probes, hard_cap, B, 1, o["top_ids"].data_ptr(), o["top_dist"].data_ptr(),
+                                             o["n_ret"].data_ptr(), o["counters"].data_ptr())
+                return o
+        searcher = AbiSearcher()
     batches = []
     for b in range(3):
         qcfg = cfg.scaled(name=cfg.name)
@@ -56,6 +78,7 @@ def main():
     for b in batches:                                                                # warm-up
         out = searcher.search_batch_dev(b, cfg.k, cfg.probes, cfg.hard_cap, cfg.B)
     torch.cuda.synchronize()
+    gpu.sync()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -63,9 +86,11 @@ def main():
     for s in range(args.steps):
         out = searcher.search_batch_dev(batches[s % 3], cfg.k, cfg.probes, cfg.hard_cap, cfg.B)
     torch.cuda.synchronize()
+    gpu.sync()
     if world > 1:
         dist.barrier()
     dt = time.perf_counter() - t0
+    stage = None if args.python_collectives else dict(gpu.sharded_stage_ms(), refine_split=gpu.stage_ms())
     same = None
     if rank == 0:
         full = GpuContext(lr)
@@ -80,7 +105,8 @@ def main():
                     and np.array_equal(out["n_ret"].cpu().numpy(), ref["n_ret"]))
         print(json.dumps({"mode": "database-sharded (config 4 shape)", "n_gpus": world, "N": cfg.N, "dim": cfg.dim, "Q": cfg.Q, "B": cfg.B,
                           "ms_per_batch": 1e3 * dt / args.steps, "queries_per_s": cfg.Q * args.steps / dt,
-                          "sharded_equals_unsharded": same, "timing": "wall clock around the steps (barrier + synchronize on both sides)"}),
+                          "sharded_equals_unsharded": same, "collectives": "torch.distributed" if args.python_collectives else "C ABI (NCCL in libfspann_gpu.so)",
+                          "stage_ms_rank0": stage, "timing": "wall clock around the steps (barrier + synchronize on both sides)"}),
               file=real_stdout, flush=True)
         full.close()
     gpu.close()
