@@ -410,6 +410,8 @@ size_t route_fast_smem(int TD, int probes, int n_raw, int tbl, int sort_n, int w
     s += sizeof(int64_t) * nvis;                    // vbase_s
     s += 2 * nvis16;                                // vs_s, vlen_s
     s += sizeof(uint16_t) * nvis16;                 // lowvis_s
+    s += sizeof(uint16_t) * nvis16;                 // inv_cnt (involved / deleted positions per visit)
+    s += sizeof(uint32_t) * (((size_t)n_raw + 31) / 32 + 3) / 4 * 4;   // inv_bm (one bit per position: involved)
     s += sizeof(uint16_t) * wl_extra;               // worklist head (continues into skey / sid)
     s += sizeof(uint64_t) * sort_n;                 // skey
     s += sizeof(int32_t) * sort_n;                  // sid
@@ -481,9 +483,9 @@ __device__ __forceinline__ uint32_t bitonic_sort32(uint32_t a, int i, uint32_t *
     return a;
 }
 
-// best_s encoding: 255 = not a representative position (invalid id, or a later occurrence of a duplicated id),
-// 254 = occurrence of a possibly duplicated id waiting for the exact path, s < 128 = the only occurrence of its id (score s),
-// 0x80 | s = first occurrence of a duplicated id whose minimum score over all occurrences is s.
+// best_s is valid only for INVOLVED positions (bit set in inv_bm; written by the exact path): 255 = a later occurrence of a duplicated
+// id, 0x80 | s = first occurrence of an id whose minimum score over all occurrences is s.  Every other valid position is the only
+// occurrence of its id and its score is its visit's score vs_s[e >> 6].
 constexpr uint32_t RQ_DUP = 0x80u;
 
 __global__ void __launch_bounds__(RQ_THREADS, 1) route_fast_kernel(RoutingView rv, RouteParams p, RouteFastExtra x) {
@@ -499,7 +501,10 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) route_fast_kernel(RoutingView r
     uint8_t *vs_s = reinterpret_cast<uint8_t *>(vbase_s + nvis);               // per visit: Hamming score of the partition
     uint8_t *vlen_s = vs_s + nvis16;                                           // valid ids in the visited partition row
     uint16_t *lowvis_s = reinterpret_cast<uint16_t *>(vlen_s + nvis16);
-    uint16_t *wl = lowvis_s + nvis16;                                          // worklist: wl_extra entries, then over skey / sid
+    uint16_t *inv_cnt = lowvis_s + nvis16;                                     // per visit: positions that are NOT singles (involved, or deleted ids)
+    uint32_t *inv_bm = reinterpret_cast<uint32_t *>(inv_cnt + nvis16);         // bit e: position e is involved (its score lives in best_s[e])
+    const int nbm = ((n_raw + 31) / 32 + 3) / 4 * 4;
+    uint16_t *wl = reinterpret_cast<uint16_t *>(inv_bm + nbm);                 // worklist: wl_extra entries, then over skey / sid
     uint64_t *skey = reinterpret_cast<uint64_t *>(wl + x.wl_extra);
     int32_t *sid = reinterpret_cast<int32_t *>(skey + sort_n);
     const int wl_cap = x.wl_extra + 6 * sort_n;
@@ -510,7 +515,7 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) route_fast_kernel(RoutingView r
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int64_t n_ids = rv.n_ids;
-    int fshift = 32; while ((1u << (32 - fshift)) < (uint32_t)tbl * 4u) fshift--;     // buckets per filter array (two arrays share the table region)
+    const int fshift = 32 - (31 - __clz(tbl * 4 - 1) + 1);                             // buckets per filter array = tbl * 4 (a power of two; two arrays share the table region)
 
     for (int64_t q = blockIdx.x; q < p.Q; q += gridDim.x) {
         __syncthreads();
@@ -525,6 +530,8 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) route_fast_kernel(RoutingView r
             vs_s[v] = valid ? x.vis_score[vi] : 255;
         }
         for (int i = tid; i < tbl / 8; i += RQ_THREADS) reinterpret_cast<uint4 *>(table_w)[i] = make_uint4(0, 0, 0, 0);
+        for (int i = tid; i < nbm; i += RQ_THREADS) inv_bm[i] = 0u;
+        for (int i = tid; i < nvis16 / 2; i += RQ_THREADS) reinterpret_cast<uint32_t *>(inv_cnt)[i] = 0u;
         if (tid < 256) s_hist[tid] = 0;
         if (tid == 0) { s_raw = 0; s_uniq = 0; s_m = 0; s_ncls = 0; s_nwl = 0; s_nlow = 0; }
         __syncthreads();
@@ -561,7 +568,10 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) route_fast_kernel(RoutingView r
                     int32_t id4[4] = {idv[u].x, idv[u].y, idv[u].z, idv[u].w};
                     if (rv.deleted) {
 #pragma unroll
-                        for (int j = 0; j < 4; j++) if (id4[j] >= 0 && id4[j] < rv.n_deleted && rv.deleted[id4[j]]) id4[j] = -1;     // PIS:739
+                        int dead = 0;
+#pragma unroll
+                        for (int j = 0; j < 4; j++) if (id4[j] >= 0 && id4[j] < rv.n_deleted && rv.deleted[id4[j]]) { id4[j] = -1; dead++; }     // PIS:739
+                        if (dead) atomicAdd(reinterpret_cast<unsigned int *>(inv_cnt) + (e >> 7), (unsigned)dead << (((e >> 6) & 1) * 16));
                     }
                     *reinterpret_cast<int4 *>(ids_s + e) = make_int4(id4[0], id4[1], id4[2], id4[3]);
 #pragma unroll
@@ -579,67 +589,58 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) route_fast_kernel(RoutingView r
             }
         }
         __syncthreads();
-        // ---- 3. classify every position: single (final), or involved (-> worklist for the exact path).  A half-warp covers the 64
-        //         positions of ONE visit, so its singles share one score: one histogram atomic per half-warp. ----
+        // ---- 3. classify every position: single (nothing to do: its score is its visit's score) or involved (-> bitmap + worklist for
+        //         the exact path, ~12 % of the positions).  Singles are counted per VISIT afterwards: valid - deleted - involved.
         int my_raw = 0, my_uniq = 0;
         bool wl_ok = true;
-        for (int q0 = 0; q0 < n4; q0 += RQ_THREADS) {
-            const int q4 = q0 + tid;
-            const bool valid = q4 < n4;
+        for (int q4 = tid; q4 < n4; q4 += RQ_THREADS) {
             const int e = q4 << 2;
-            const int4 idq = valid ? *reinterpret_cast<const int4 *>(ids_s + e) : make_int4(-1, -1, -1, -1);
+            const int4 idq = *reinterpret_cast<const int4 *>(ids_s + e);
             const int32_t id4[4] = {idq.x, idq.y, idq.z, idq.w};
-            const uint32_t sc = valid ? vs_s[e >> 6] : 255u;
-            uint32_t packed = 0, invmask = 0; int n_single = 0;
+            uint32_t invmask = 0;
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                uint32_t b = 255u;
                 if (id4[j] >= 0) {
                     const uint32_t h1 = ((uint32_t)id4[j] * 0x9E3779B1u) >> fshift;
-                    bool inv = ((F[h1 >> 4] >> ((h1 & 15u) * 2u)) & 2u) != 0;
-                    if (inv) {
+                    if ((F[h1 >> 4] >> ((h1 & 15u) * 2u)) & 2u) {
                         const uint32_t h2 = ((uint32_t)id4[j] * 0x85EBCA6Bu) >> fshift;
-                        inv = ((F[f2_off + (h2 >> 4)] >> ((h2 & 15u) * 2u)) & 2u) != 0;
+                        if ((F[f2_off + (h2 >> 4)] >> ((h2 & 15u) * 2u)) & 2u) invmask |= 1u << j;
                     }
-                    if (inv) { b = 254u; invmask |= 1u << j; } else { b = sc; n_single++; }
                 }
-                packed |= b << (8 * j);
             }
-            if (valid) *reinterpret_cast<uint32_t *>(best_s + e) = packed;
-            // singles of the half-warp (one visit)
-            int hs = n_single;
+            if (invmask) {
+                const int c = __popc(invmask);
+                int base = atomicAdd(&s_nwl, c);
+                atomicAdd(reinterpret_cast<unsigned int *>(inv_cnt) + (e >> 7), (unsigned)c << (((e >> 6) & 1) * 16));
+                atomicOr(&inv_bm[e >> 5], invmask << (e & 31));
 #pragma unroll
-            for (int o = 8; o; o >>= 1) hs += __shfl_xor_sync(0xffffffffu, hs, o);
-            if ((lane & 15) == 0 && hs) { atomicAdd(&s_hist[sc], hs); my_raw += hs; my_uniq += hs; }
-            // involved positions -> worklist (one shared atomic per warp)
-            const int c = __popc(invmask);
-            int tot;
-            const int off = warp_excl_scan(c, lane, tot);
-            int base = 0;
-            if (lane == 0 && tot) base = atomicAdd(&s_nwl, tot);
-            base = __shfl_sync(0xffffffffu, base, 0) + off;
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                if ((invmask >> j) & 1u) { if (base < wl_cap) wl[base] = (uint16_t)(e + j); else wl_ok = false; base++; }
+                for (int j = 0; j < 4; j++) {
+                    if ((invmask >> j) & 1u) { if (base < wl_cap) wl[base] = (uint16_t)(e + j); else wl_ok = false; base++; }
+                }
             }
         }
         wl_ok = __syncthreads_and(wl_ok ? 1 : 0) != 0;
         const int n_inv = s_nwl;
+        if (tid < nvis) {                                                  // the singles of visit `tid` share its score
+            const int singles = (int)vlen_s[tid] - (int)inv_cnt[tid];
+            if (singles > 0) { atomicAdd(&s_hist[vs_s[tid]], singles); my_raw += singles; my_uniq += singles; }
+        }
         // ---- 4. exact path on the involved positions: open addressing (double hashing) keyed by id, table[slot] = newest position
         //         holding that id, every position links to the previous newest one, the FIRST arrival's link is the terminator
         //         0x8000|slot (so the slot of any position is found by following its short chain).  Then every occurrence walks
         //         its id's chain once: (a) did it strictly improve on all earlier visits (PIS:747 -> lastRawVisited), (b) is it the
         //         first occurrence (= HashMap insertion order); the first one records the id's min score.
         if (n_inv > 0) {
-            int tslots = 1024; while (tslots < 2 * n_inv && tslots < tbl) tslots <<= 1;
+            int tslots = 2 * n_inv <= 1024 ? 1024 : 1 << (32 - __clz(2 * n_inv - 1));
+            if (tslots > tbl) tslots = tbl;
             const uint32_t smask = (uint32_t)tslots - 1u;
-            int sshift = 32; while ((1u << (32 - sshift)) < (uint32_t)tslots) sshift--;
+            const int sshift = 32 - (31 - __clz(tslots));
             for (int i = tid; i < tslots / 2; i += RQ_THREADS) table_w[i] = 0xffffffffu;
             __syncthreads();
             const int n_dom = wl_ok ? n_inv : n_raw;
             for (int i = tid; i < n_dom; i += RQ_THREADS) {
                 const int e = wl_ok ? (int)wl[i] : i;
-                if (!wl_ok && best_s[e] != 254) continue;
+                if (!wl_ok && !((inv_bm[e >> 5] >> (e & 31)) & 1u)) continue;
                 const int32_t id = ids_s[e];
                 const uint32_t h = (uint32_t)id * 0x9E3779B1u;
                 uint32_t slot = h >> sshift;
@@ -666,7 +667,7 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) route_fast_kernel(RoutingView r
             __syncthreads();
             for (int i = tid; i < n_dom; i += RQ_THREADS) {
                 const int e = wl_ok ? (int)wl[i] : i;
-                if (!wl_ok && best_s[e] != 254) continue;
+                if (!wl_ok && !((inv_bm[e >> 5] >> (e & 31)) & 1u)) continue;
                 const uint32_t sc = vs_s[e >> 6];
                 uint32_t lk = next_s[e];
                 while (!(lk & 0x8000u)) lk = next_s[lk];               // terminator carries the slot
@@ -695,7 +696,7 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) route_fast_kernel(RoutingView r
         // Java's final table size for this many entries (HashMap.resize doubles while size > 0.75*cap); <= 65536 here
         uint32_t capF = (uint32_t)p.cap0;
         while ((double)n_unique > 0.75 * (double)capF && capF < (1u << 30)) capF <<= 1;
-        int cb = 0; while ((1u << cb) < capF) cb++;
+        const int cb = capF <= 1u ? 0 : 32 - __clz(capF - 1u);
         // ---- 5. level 0 of the radix select = the score histogram ----
         if (tid < 32) warp_pick_digit(s_hist, 256, 0, want, lane, s_pick);
         __syncthreads();
@@ -720,13 +721,14 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) route_fast_kernel(RoutingView r
                 const int i = i0 + tid;
                 int e = -1; uint32_t sc = 255;
                 if (i < n_low) {
-                    e = (int)lowvis_s[i >> 6] * kBlock + (i & 63);
-                    const uint32_t b = best_s[e];
-                    sc = b < RQ_DUP ? b : 255u;                         // singles only; duplicates are taken from the worklist
+                    const int v = (int)lowvis_s[i >> 6];
+                    e = v * kBlock + (i & 63);
+                    const bool single = ids_s[e] >= 0 && !((inv_bm[e >> 5] >> (e & 31)) & 1u);
+                    sc = single ? (uint32_t)vs_s[v] : 255u;             // singles only; duplicates are taken from the worklist
                 } else if (i < n_low + n_dup) {
                     e = wl_ok ? (int)wl[i - n_low] : i - n_low;
-                    const uint32_t b = best_s[e];
-                    sc = (b >= RQ_DUP && b < 254u) ? (b & 0x7fu) : 255u;
+                    const uint32_t b = (wl_ok || ((inv_bm[e >> 5] >> (e & 31)) & 1u)) ? best_s[e] : 255u;
+                    sc = (b >= RQ_DUP && b < 255u) ? (b & 0x7fu) : 255u;
                 }
                 const bool below = sc < sstar || (sc == sstar && !need_levels && sc != 255u);
                 const bool incls = need_levels && sc == sstar && sc != 255u;
@@ -786,8 +788,8 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) route_fast_kernel(RoutingView r
         }
         const int m = min(s_m, sort_n);
         int32_t *out_id = p.cand_ids + (size_t)q * p.B, *out_sc = p.cand_scores + (size_t)q * p.B;
-        int sb = 0; while ((1u << sb) <= sstar) sb++;                   // bits that hold every selected score (<= s*)
-        int rb = 0; while ((1 << rb) < sort_n) rb++;
+        const int sb = 32 - __clz(sstar);                               // bits that hold every selected score (<= s*)
+        const int rb = sort_n <= 1 ? 0 : 32 - __clz(sort_n - 1);
         if (sort_n <= RQ_THREADS && sb + cb + rb <= 32) {
             // ---- 8a. 32-bit keys: (score | Java bucket | rank of the first position among the selected entries).  The rank comes
             //          from a bitmap over positions + prefix popcounts, so it orders exactly like the position itself; the id is
@@ -818,7 +820,8 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) route_fast_kernel(RoutingView r
                 const int32_t idv = ids_s[my_e];
                 const uint32_t rank = (uint32_t)pref[my_e >> 5] + (uint32_t)__popc(bm[my_e >> 5] & ((1u << (my_e & 31)) - 1u));
                 const uint32_t bucket = java_hash_decimal(idv) & (capF - 1u);
-                a = ((uint32_t)(best_s[my_e] & 0x7fu) << (cb + rb)) | (bucket << rb) | rank;
+                const uint32_t sc_e = ((inv_bm[my_e >> 5] >> (my_e & 31)) & 1u) ? (uint32_t)(best_s[my_e] & 0x7fu) : (uint32_t)vs_s[my_e >> 6];
+                a = (sc_e << (cb + rb)) | (bucket << rb) | rank;
                 sid[rank] = idv;                                          // the worklist (which overlaps skey / sid) is dead by now
             }
             const int i = tid;
@@ -834,7 +837,8 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) route_fast_kernel(RoutingView r
                     const int e = sel[i];
                     idv = ids_s[e];
                     const uint32_t bucket = java_hash_decimal(idv) & (capF - 1u);
-                    key = ((uint64_t)(best_s[e] & 0x7fu) << (cb + 16)) | ((uint64_t)bucket << 16) | (uint64_t)e;
+                    const uint32_t sc_e = ((inv_bm[e >> 5] >> (e & 31)) & 1u) ? (uint32_t)(best_s[e] & 0x7fu) : (uint32_t)vs_s[e >> 6];
+                    key = ((uint64_t)sc_e << (cb + 16)) | ((uint64_t)bucket << 16) | (uint64_t)e;
                 }
                 skey[i] = key; sid[i] = idv;                                // the worklist (which overlaps skey / sid) is dead by now
             }
