@@ -23,7 +23,8 @@ EXPORTS = [
     "fspann_route_batch", "fspann_refine_batch", "fspann_refine_batch_ex", "fspann_search_batch", "fspann_search_batch_dev", "fspann_search_tokens", "fspann_search_tokens_dev", "fspann_touched_fetch",
     "fspann_last_stage_ms", "fspann_debug_decrypt", "fspann_set_option", "fspann_get_info", "fspann_migrate", "fspann_encrypt_batch", "fspann_routing_build", "fspann_groundtruth", "fspann_recall_batch", "fspann_route_batch_dev", "fspann_refine_batch_dev", "fspann_merge_topk_dev",
     "fspann_comm_unique_id", "fspann_comm_init", "fspann_comm_destroy", "fspann_sharded_search_batch", "fspann_sharded_search_batch_dev",
-    "fspann_sharded_last_stage_ms",
+    "fspann_sharded_last_stage_ms", "fspann_routing_build_begin", "fspann_routing_build_add", "fspann_routing_build_add_dev",
+    "fspann_routing_build_finish", "fspann_store_alloc_shard", "fspann_store_encrypt_dev",
 ]
 
 _libs = {}

@@ -358,48 +358,90 @@ int fspann_gfunctions_upload(fspann_ctx *ctx, int32_t dim, int32_t T, int32_t D,
 }
 
 // ---- Setup-side index build on the device: coding loop of PIS.insert / finalizeForSearch (PIS:331-346, 789-845)
-// + GreedyPartitioner.build (GP:37-76) for every (table, division), installed as the routing state ------------------------------
-int fspann_routing_build(fspann_ctx *ctx, int64_t N, const double *vectors, const int32_t *staged_ids, int64_t *min_key_out,
-                         int64_t *max_key_out, uint64_t *rep_code_out, int32_t *ids_out) {
+// + GreedyPartitioner.build (GP:37-76) for every (table, division), installed as the routing state.  Chunked form: begin -> add* ->
+// finish, so a base set that does not fit the host (config 4: 100 M x 96) streams through in pieces; fspann_routing_build is the
+// one-call wrapper ------------------------------------------------------------------------------------------------------------
+int fspann_routing_build_begin(fspann_ctx *ctx, int64_t N) {
     if (!ctx) return FSPANN_E_ARG;
     CK(cudaSetDevice(ctx->device));
     if (!ctx->routing_ready) return fail(ctx, FSPANN_E_STATE, "GFunctionRegistry not initialized: upload the GFunctions first (PIS:812-819)");
-    if (!vectors || !staged_ids) return fail(ctx, FSPANN_E_ARG, "null array");
     if (N < 1000) return fail(ctx, FSPANN_E_STATE, "Cannot finalize index: only %lld samples collected (< MIN_SAMPLE_SIZE) (PIS:803-808)", (long long)N);
     if (N >= (1LL << 31) - 1) return fail(ctx, FSPANN_E_ARG, "N too large for int32 ids");
+    ENSURE(ctx->b_codes, sizeof(uint64_t) * (size_t)N * ctx->rv.TD * ctx->rv.W);
+    ctx->build_n = N; ctx->build_added = 0;
+    return FSPANN_OK;
+}
+
+static int build_add_dev(fspann_ctx *ctx, int64_t first_id, int64_t n, const double *d_vectors) {
+    if (ctx->build_n <= 0) return fail(ctx, FSPANN_E_STATE, "fspann_routing_build_begin has not been called");
+    if (first_id < 0 || n < 0 || first_id + n > ctx->build_n) return fail(ctx, FSPANN_E_ARG, "ids [%lld, %lld) outside 0..N-1", (long long)first_id, (long long)(first_id + n));
+    const RoutingView &rv = ctx->rv;
+    const int64_t chunk = 1 << 20;                               // the TokenGen re-check list is sized per launch
+    for (int64_t s0 = 0; s0 < n; s0 += chunk) {
+        const int64_t c = std::min(chunk, n - s0);
+        int rc = run_tokengen(ctx, c, d_vectors + (size_t)s0 * rv.dim, (uint64_t *)ctx->b_codes.p + (size_t)(first_id + s0) * rv.TD * rv.W);
+        if (rc) return rc;
+    }
+    ctx->build_added += n;
+    return FSPANN_OK;
+}
+
+int fspann_routing_build_add_dev(fspann_ctx *ctx, int64_t first_id, int64_t n, const double *d_vectors) {
+    if (!ctx) return FSPANN_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (n > 0 && !d_vectors) return fail(ctx, FSPANN_E_ARG, "null array");
+    return build_add_dev(ctx, first_id, n, d_vectors);
+}
+
+int fspann_routing_build_add(fspann_ctx *ctx, int64_t first_id, int64_t n, const double *vectors) {
+    if (!ctx) return FSPANN_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (n > 0 && !vectors) return fail(ctx, FSPANN_E_ARG, "null array");
+    const int dim = ctx->rv.dim;
+    if (!all_finite(vectors, n * dim)) return fail(ctx, FSPANN_E_ARG, "Vector contains NaN/Inf (Coding:357-359)");
+    const int64_t chunk = 131072;
+    ENSURE(ctx->s_queries, sizeof(double) * (size_t)std::min(chunk, std::max<int64_t>(n, 1)) * dim);
+    for (int64_t s0 = 0; s0 < n; s0 += chunk) {
+        const int64_t c = std::min(chunk, n - s0);
+        CK(cudaMemcpyAsync(ctx->s_queries.p, vectors + (size_t)s0 * dim, sizeof(double) * (size_t)c * dim, cudaMemcpyHostToDevice, ctx->stream));
+        int rc = build_add_dev(ctx, first_id + s0, c, (const double *)ctx->s_queries.p);
+        if (rc) return rc;
+        CK(cudaStreamSynchronize(ctx->stream));                 // the staging buffer is reused
+    }
+    return FSPANN_OK;
+}
+
+int fspann_routing_build_finish(fspann_ctx *ctx, const int32_t *staged_ids, int64_t *min_key_out, int64_t *max_key_out, uint64_t *rep_code_out,
+                                int32_t *ids_out) {
+    if (!ctx) return FSPANN_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const int64_t N = ctx->build_n;
+    if (N <= 0) return fail(ctx, FSPANN_E_STATE, "fspann_routing_build_begin has not been called");
+    if (ctx->build_added != N) return fail(ctx, FSPANN_E_STATE, "only %lld of %lld vectors were added", (long long)ctx->build_added, (long long)N);
     RoutingView &rv = ctx->rv;
-    const int dim = rv.dim, TD = rv.TD, W = rv.W;
-    {   // ids are the ordinals 0..N-1 (FSA:501,515), each staged exactly once
+    const int TD = rv.TD, W = rv.W;
+    const int64_t P = (N + kBlock - 1) / kBlock;
+    ENSURE(ctx->b_staged, sizeof(int32_t) * (size_t)N);
+    if (staged_ids) {   // ids are the ordinals 0..N-1 (FSA:501,515), each staged exactly once
         std::vector<uint8_t> seen((size_t)N, 0);
         for (int64_t i = 0; i < N; i++) {
             const int32_t id = staged_ids[i];
             if (id < 0 || id >= N || seen[(size_t)id]) return fail(ctx, FSPANN_E_ARG, "staged ids must be a permutation of 0..N-1 (bad id %d)", id);
             seen[(size_t)id] = 1;
         }
+        CK(cudaMemcpyAsync(ctx->b_staged.p, staged_ids, sizeof(int32_t) * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
+    } else {            // the facade's insertion order: the 1000th and later vectors first, then the first 999 (PIS:280-298, 821-831)
+        LAUNCHED(launch_staged_order(ctx->stream, (int32_t *)ctx->b_staged.p, N));
     }
-    if (!all_finite(vectors, N * dim)) return fail(ctx, FSPANN_E_ARG, "Vector contains NaN/Inf (Coding:357-359)");
-    const int64_t P = (N + kBlock - 1) / kBlock;
-    // 1. code every vector for every (t,d): the TokenGen kernel over the base set, in chunks through a staging buffer
-    ENSURE(ctx->b_codes, sizeof(uint64_t) * (size_t)N * TD * W);
-    const int64_t chunk = 131072;
-    ENSURE(ctx->s_queries, sizeof(double) * (size_t)std::min(chunk, N) * dim);
-    for (int64_t s0 = 0; s0 < N; s0 += chunk) {
-        const int64_t c = std::min(chunk, N - s0);
-        CK(cudaMemcpyAsync(ctx->s_queries.p, vectors + (size_t)s0 * dim, sizeof(double) * (size_t)c * dim, cudaMemcpyHostToDevice, ctx->stream));
-        { int rc_ = run_tokengen(ctx, c, (const double *)ctx->s_queries.p, (uint64_t *)ctx->b_codes.p + (size_t)s0 * TD * W); if (rc_) return rc_; }
-        CK(cudaStreamSynchronize(ctx->stream));
-    }
-    // 2. partitions: HashMap iteration order -> stable sort by key -> blocks of 64
+    // partitions: HashMap iteration order -> stable sort by key -> blocks of 64
     uint32_t cap = table_size_for(N);                                   // new HashMap<>(staged.size()) (PIS:413) ...
     while ((double)N > 0.75 * (double)cap && cap < (1u << 30)) cap <<= 1;   // ... doubled while size > 0.75 * cap
     const size_t scratch = partition_build_scratch_bytes(N);
-    ENSURE(ctx->b_staged, sizeof(int32_t) * (size_t)N);
     ENSURE(ctx->b_scratch, scratch);
     ENSURE(ctx->b_ids, sizeof(int32_t) * (size_t)TD * N);
     ENSURE(ctx->b_keys, sizeof(int64_t) * 2 * (size_t)TD * P);
     ENSURE(ctx->b_rep, sizeof(uint64_t) * (size_t)TD * P * W);
     ENSURE(ctx->b_flag, sizeof(int32_t));
-    CK(cudaMemcpyAsync(ctx->b_staged.p, staged_ids, sizeof(int32_t) * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemsetAsync(ctx->b_flag.p, 0, sizeof(int32_t), ctx->stream));
     LAUNCHED(launch_partition_build(ctx->stream, (const uint64_t *)ctx->b_codes.p, (const int32_t *)ctx->b_staged.p, N, TD, W, cap, rv.m * rv.lambda,
                                     (int32_t *)ctx->b_ids.p, (int64_t *)ctx->b_keys.p, (uint64_t *)ctx->b_rep.p, ctx->b_scratch.p, ctx->b_scratch.bytes,
@@ -408,7 +450,7 @@ int fspann_routing_build(fspann_ctx *ctx, int64_t N, const double *vectors, cons
     CK(cudaMemcpyAsync(&tree, ctx->b_flag.p, sizeof tree, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->last_build_treeified = tree;
-    // 3. freeze: the built arrays become the routing state (PIS:842)
+    // freeze: the built arrays become the routing state (PIS:842)
     ctx->routing_ready = false;
     std::swap(ctx->d_ids, ctx->b_ids);
     std::swap(ctx->d_keys, ctx->b_keys);
@@ -416,6 +458,7 @@ int fspann_routing_build(fspann_ctx *ctx, int64_t N, const double *vectors, cons
     rv.n_ids = N; rv.P = P;
     rv.keys = (const int64_t *)ctx->d_keys.p; rv.rep = (const uint64_t *)ctx->d_rep.p; rv.ids = (const int32_t *)ctx->d_ids.p;
     ctx->routing_ready = true;
+    ctx->build_n = 0; ctx->build_added = 0;
     // optional copies for the host's own persistence, in fspann_routing_upload's layout
     if (ids_out) CK(cudaMemcpy(ids_out, ctx->d_ids.p, sizeof(int32_t) * (size_t)TD * N, cudaMemcpyDeviceToHost));
     if (rep_code_out) CK(cudaMemcpy(rep_code_out, ctx->d_rep.p, sizeof(uint64_t) * (size_t)TD * P * W, cudaMemcpyDeviceToHost));
@@ -426,6 +469,15 @@ int fspann_routing_build(fspann_ctx *ctx, int64_t N, const double *vectors, cons
     }
     release(ctx->b_codes); release(ctx->b_scratch); release(ctx->b_ids); release(ctx->b_keys); release(ctx->b_rep);
     return FSPANN_OK;
+}
+
+int fspann_routing_build(fspann_ctx *ctx, int64_t N, const double *vectors, const int32_t *staged_ids, int64_t *min_key_out,
+                         int64_t *max_key_out, uint64_t *rep_code_out, int32_t *ids_out) {
+    if (!ctx) return FSPANN_E_ARG;
+    if (!vectors || !staged_ids) return fail(ctx, FSPANN_E_ARG, "null array");
+    int rc = fspann_routing_build_begin(ctx, N); if (rc) return rc;
+    rc = fspann_routing_build_add(ctx, 0, N, vectors); if (rc) return rc;
+    return fspann_routing_build_finish(ctx, staged_ids, min_key_out, max_key_out, rep_code_out, ids_out);
 }
 
 int fspann_deleted_set(fspann_ctx *ctx, const uint8_t *flags, int64_t n) {
@@ -490,6 +542,57 @@ int fspann_store_upload_shard(fspann_ctx *ctx, int64_t id_base, int64_t N, int64
     int rc = store_write(ctx, N, nullptr, iv, ct, key_version);
     if (rc) return rc;
     ctx->store_ready = true;
+    return FSPANN_OK;
+}
+
+// Empty (zeroed) shard whose records arrive later through fspann_store_encrypt_dev / fspann_store_update: Setup of a store that is
+// produced on the device and never fits the host in one piece (config 4).
+int fspann_store_alloc_shard(fspann_ctx *ctx, int64_t id_base, int64_t N, int64_t n_global, int32_t dim) {
+    if (!ctx) return FSPANN_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (N <= 0 || dim <= 0) return fail(ctx, FSPANN_E_ARG, "non-positive N/dim");
+    if (id_base < 0 || n_global < id_base + N) return fail(ctx, FSPANN_E_ARG, "shard [%lld, %lld) outside the global id space %lld",
+                                                           (long long)id_base, (long long)(id_base + N), (long long)n_global);
+    if (n_global >= (1LL << 31) - 1) return fail(ctx, FSPANN_E_ARG, "N too large for int32 ids");
+    ctx->store_ready = false;
+    const int64_t stride = ((32 + 8LL * dim) + 15) / 16 * 16;
+    ENSURE(ctx->d_rec, (size_t)N * stride + 64);
+    ENSURE(ctx->d_touched, sizeof(uint32_t) * (size_t)((N + 31) / 32 + 1));
+    CK(cudaMemsetAsync(ctx->d_rec.p, 0, (size_t)N * stride + 64, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_touched.p, 0, sizeof(uint32_t) * (size_t)((N + 31) / 32 + 1), ctx->stream));
+    const bool dim_changed = ctx->sv.dim != dim;
+    ctx->sv.N = N; ctx->sv.id_base = id_base; ctx->sv.n_global = n_global;
+    ctx->sv.dim = dim; ctx->sv.rec_stride = stride; ctx->sv.rec = (const uint8_t *)ctx->d_rec.p;
+    if (dim_changed || !ctx->sv.hpow) { int rc = rebuild_keys(ctx); if (rc) return rc; }
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->store_ready = true;      // records of version 0 with a zero tag never authenticate: an unwritten row is a TAG_FAIL / NO_KEY candidate
+    return FSPANN_OK;
+}
+
+// encryptToPoint (AGC:55-112) for the n vectors of ids first_id .. first_id+n-1, written DIRECTLY into this context's HBM store
+// (device-resident FP64 vectors [n][dim] and IVs [n][12]; AAD id:<id>|v:<version>|d:<dim>).  The ids must lie inside the shard.
+int fspann_store_encrypt_dev(fspann_ctx *ctx, int64_t first_id, int64_t n, const double *d_vectors, const uint8_t *d_ivs, int32_t version) {
+    if (!ctx) return FSPANN_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->store_ready) return fail(ctx, FSPANN_E_STATE, "record store not allocated (fspann_store_alloc_shard / fspann_store_upload_shard)");
+    if (n == 0) return FSPANN_OK;
+    if (n < 0 || !d_vectors || !d_ivs) return fail(ctx, FSPANN_E_ARG, "null array");
+    if (first_id < ctx->sv.id_base || first_id + n > ctx->sv.id_base + ctx->sv.N) return fail(ctx, FSPANN_E_ARG, "ids [%lld, %lld) are not held by this context",
+                                                                                            (long long)first_id, (long long)(first_id + n));
+    if (!ctx->keys.count(version)) return fail(ctx, FSPANN_E_ARG, "key version %d is not live (KRS:82-88)", version);
+    const int64_t chunk = 1 << 20;
+    StoreView tv = ctx->sv;
+    tv.deleted = nullptr; tv.n_deleted = 0;
+    for (int64_t s0 = 0; s0 < n; s0 += chunk) {
+        const int c = (int)std::min<int64_t>(chunk, n - s0);
+        ENSURE(ctx->m_list, sizeof(int32_t) * (size_t)c);
+        ENSURE(ctx->m_flag, (size_t)c);
+        tv.rec = ctx->sv.rec + (size_t)(first_id + s0 - ctx->sv.id_base) * ctx->sv.rec_stride;
+        tv.N = c; tv.id_base = first_id + s0;                     // the AAD binds the GLOBAL id (EP:80-83)
+        LAUNCHED(launch_iota(ctx->stream, (int32_t *)ctx->m_list.p, c));
+        LAUNCHED(launch_encrypt_xcrypt(ctx->stream, tv, c, d_vectors + (size_t)s0 * tv.dim, d_ivs + (size_t)s0 * 12, version, (uint8_t *)ctx->m_flag.p, ctx->sm_count));
+        LAUNCHED(launch_gcm_tag(ctx->stream, tv, (const int32_t *)ctx->m_list.p, nullptr, c, nullptr, (const uint8_t *)ctx->m_flag.p, ctx->sm_count));
+    }
     return FSPANN_OK;
 }
 

@@ -53,6 +53,7 @@ struct fspann_ctx {
     DevBuf g_base, g_q, g_dist, g_ids, g_d2, g_flag, g_res, g_nret, g_rec;  // ground truth / recall
     DevBuf b_codes, b_staged, b_scratch, b_ids, b_keys, b_rep, b_flag;  // device index build
     int last_build_treeified = 0;
+    int64_t build_n = 0, build_added = 0;       // fspann_routing_build_begin / add / finish
     DevBuf m_list, m_gid, m_iv, m_verdict, m_flag, m_rec, m_vec, m_out_iv, m_out_ct, m_out_ver;  // Migrate / bulk encryption
     DevBuf r_rows, r_queries, r_codes, r_topk_ids, r_topk_dist, r_nret, r_counters;  // retry subset
     DevBuf t_cand_ids, t_cand_sc, t_ncand, t_raw, t_uniq_cnt, t_ndec;               // retry subset route outputs

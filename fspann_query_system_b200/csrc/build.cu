@@ -54,6 +54,22 @@ __global__ void build_emit_kernel(const uint64_t *__restrict__ codes, const int3
     }
 }
 
+// staged[i] = the facade's insertion order into the staging map: ids 999 .. n-1, then 0 .. 998 (PIS:280-298, 821-831); iota: out[i] = i
+__global__ void staged_order_kernel(int32_t *__restrict__ staged, int64_t n, int iota) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        staged[i] = iota ? (int32_t)i : (int32_t)(i < n - 999 ? i + 999 : i - (n - 999));
+}
+int launch_staged_order(cudaStream_t s, int32_t *staged, int64_t n) {
+    if (n <= 0) return 0;
+    staged_order_kernel<<<(int)std::min<int64_t>((n + 255) / 256, (int64_t)cur_sm_count() * 16), 256, 0, s>>>(staged, n, 0);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+int launch_iota(cudaStream_t s, int32_t *out, int64_t n) {
+    if (n <= 0) return 0;
+    staged_order_kernel<<<(int)std::min<int64_t>((n + 255) / 256, (int64_t)cur_sm_count() * 16), 256, 0, s>>>(out, n, 1);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
 static int bits_for(uint64_t maxv) { int b = 1; while (b < 64 && (maxv >> b)) b++; return b; }
 
 // codes [N][TD][W] (by id), staged [N] on the device -> ids [TD][N], keys [TD][P][2], rep [TD][P][W] on the device.

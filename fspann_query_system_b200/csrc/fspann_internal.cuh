@@ -168,6 +168,8 @@ int launch_store_unpack(cudaStream_t s, const uint8_t *rec, int64_t rec_stride, 
 int launch_partition_build(cudaStream_t s, const uint64_t *codes, const int32_t *staged, int64_t n, int TD, int W, uint32_t cap, int code_bits,
                            int32_t *ids_out, int64_t *keys_out, uint64_t *rep_out, void *scratch, size_t scratch_bytes, int32_t *treeified);
 size_t partition_build_scratch_bytes(int64_t n);
+int launch_staged_order(cudaStream_t s, int32_t *staged, int64_t n);
+int launch_iota(cudaStream_t s, int32_t *out, int64_t n);
 int launch_gt_chunk(cudaStream_t s, const float *base, int64_t N, int dim, const float *queries, int Qc, int K, double *dist, int32_t *out_ids,
                     double *out_d2, int32_t *tie_overflow, int sm_count);
 int launch_recall(cudaStream_t s, int Q, int K, const int32_t *gt, int gt_stride, const int32_t *res, int res_stride, const int32_t *n_ret,

@@ -68,6 +68,34 @@ class GpuContext:
                                                N.ptr(ids)))
         return mn, mx, rep, ids
 
+    # ---- the same build in pieces (a base set that does not fit the host: BASELINE config 4)
+    def routing_build_begin(self, n: int):
+        self._ck(self.lib.fspann_routing_build_begin(self.ctx, C.c_int64(n)))
+
+    def routing_build_add(self, first_id: int, vectors):
+        vectors = np.ascontiguousarray(vectors, dtype=np.float64)
+        self._ck(self.lib.fspann_routing_build_add(self.ctx, C.c_int64(first_id), C.c_int64(vectors.shape[0]), N.ptr(vectors)))
+
+    def routing_build_add_dev(self, first_id: int, n: int, d_vectors: int):
+        self._ck(self.lib.fspann_routing_build_add_dev(self.ctx, C.c_int64(first_id), C.c_int64(n), C.c_void_p(d_vectors)))
+
+    def routing_build_finish(self, staged_ids=None, want_arrays: bool = False, n: int = 0):
+        st = None if staged_ids is None else np.ascontiguousarray(staged_ids, dtype=np.int32)
+        mn = mx = rep = ids = None
+        if want_arrays:
+            TD, P = self.T * self.D, (n + 63) // 64
+            mn, mx = np.empty((TD, P), dtype=np.int64), np.empty((TD, P), dtype=np.int64)
+            rep, ids = np.empty((TD, P, self.W), dtype=np.uint64), np.empty((TD, n), dtype=np.int32)
+        self._ck(self.lib.fspann_routing_build_finish(self.ctx, N.ptr(st), N.ptr(mn), N.ptr(mx), N.ptr(rep), N.ptr(ids)))
+        return mn, mx, rep, ids
+
+    def store_alloc_shard(self, dim: int, id_base: int, n: int, n_global: int):
+        self._ck(self.lib.fspann_store_alloc_shard(self.ctx, C.c_int64(id_base), C.c_int64(n), C.c_int64(n_global), C.c_int32(dim)))
+        self.N, self.id_base, self.store_dim = n, id_base, dim
+
+    def store_encrypt_dev(self, first_id: int, n: int, d_vectors: int, d_ivs: int, version: int):
+        self._ck(self.lib.fspann_store_encrypt_dev(self.ctx, C.c_int64(first_id), C.c_int64(n), C.c_void_p(d_vectors), C.c_void_p(d_ivs), C.c_int32(version)))
+
     def deleted_set(self, flags):
         if flags is None:
             self._ck(self.lib.fspann_deleted_set(self.ctx, None, C.c_int64(0)))

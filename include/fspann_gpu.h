@@ -108,6 +108,17 @@ int fspann_gfunctions_upload(fspann_ctx *ctx, int32_t dim, int32_t T, int32_t D,
 int fspann_routing_build(fspann_ctx *ctx, int64_t N, const double *vectors, const int32_t *staged_ids, int64_t *min_key_out,
                          int64_t *max_key_out, uint64_t *rep_code_out, int32_t *ids_out);
 
+/* The same build in pieces, for a base set that does not fit the host at once (BASELINE config 4: 100 M x 96): begin(N) reserves the code
+ * array [N][T*D][W] in HBM, add / add_dev code the vectors of ids first_id .. first_id+n-1 (host FP64 rows, or rows already resident in
+ * HBM) in any order, each id exactly once, and finish runs GreedyPartitioner.build per division and installs the routing state.
+ * staged_ids == NULL means the facade's own insertion order (ids 999 .. N-1, then 0 .. 998: PIS:280-298, 821-831), generated on the
+ * device.  fspann_routing_build = begin + add(0, N) + finish. */
+int fspann_routing_build_begin(fspann_ctx *ctx, int64_t N);
+int fspann_routing_build_add(fspann_ctx *ctx, int64_t first_id, int64_t n, const double *vectors);
+int fspann_routing_build_add_dev(fspann_ctx *ctx, int64_t first_id, int64_t n, const double *d_vectors);
+int fspann_routing_build_finish(fspann_ctx *ctx, const int32_t *staged_ids, int64_t *min_key_out, int64_t *max_key_out,
+                                uint64_t *rep_code_out, int32_t *ids_out);
+
 /* metadata.isDeleted(id) (common/.../RocksDBMetadataManager.java:203-224): flags[id] != 0 => deleted.
  * n may be 0 / flags NULL to clear.  Consulted by Route (PIS:739) and Refine (PIS:718). */
 int fspann_deleted_set(fspann_ctx *ctx, const uint8_t *flags, int64_t n);
@@ -122,6 +133,12 @@ int fspann_store_upload(fspann_ctx *ctx, int64_t N, int32_t dim, const uint8_t *
  * lives in another shard gets verdict 0xFD here and is refined by its owner.  fspann_store_upload = shard (0, N, N). */
 int fspann_store_upload_shard(fspann_ctx *ctx, int64_t id_base, int64_t N, int64_t n_global, int32_t dim,
                               const uint8_t *iv, const uint8_t *ct, const int32_t *key_version);
+/* Setup of a shard that is produced on the device (config 4): alloc_shard reserves an empty shard for the global ids
+ * [id_base, id_base + N); fspann_store_encrypt_dev runs encryptToPoint (AGC:55-112; AAD id:<id>|v:<version>|d:<dim>, EP:80-83) for the
+ * device-resident FP64 vectors [n][dim] of ids first_id .. first_id+n-1 with the device-resident IVs [n][12] and writes the records
+ * straight into the HBM store.  A row never written keeps key version 0 and verdict NO_KEY. */
+int fspann_store_alloc_shard(fspann_ctx *ctx, int64_t id_base, int64_t N, int64_t n_global, int32_t dim);
+int fspann_store_encrypt_dev(fspann_ctx *ctx, int64_t first_id, int64_t n, const double *d_vectors, const uint8_t *d_ivs, int32_t version);
 /* In-place replacement of n records: the result of Migrate = reencryptTouched (KRS:250-266).  Atomic with
  * respect to later batches (stream ordered). */
 int fspann_store_update(fspann_ctx *ctx, int64_t n, const int32_t *ids, const uint8_t *iv, const uint8_t *ct,
