@@ -305,13 +305,27 @@ __device__ __forceinline__ bool warp_decrypt_record(const StoreView &sv, const u
     return __all_sync(0xffffffffu, finite);
 }
 
-// Same with the record's hoisted round-1/2 constants (production kernel, c <= 254).
+// Integer test of one plaintext double given as its IEEE words: true when the value is an integer in [0, 255] (+0.0 included, -0.0 not);
+// *byte receives it.  SIFT / .bvecs descriptors (loader/.../BvecsLoader.java) are such integers: for them the squared differences and
+// every partial sum of QSI:364-372 are exact integers < 2^53, so the distance may be accumulated in integer arithmetic bit for bit.
+__device__ __forceinline__ bool small_int_of_double(uint32_t hi, uint32_t lo, uint32_t &byte) {
+    const int e = (int)(hi >> 20) - 1023;                      // a set sign bit makes e > 7
+    const uint32_t frac = hi & 0xfffffu;
+    const bool zero = (hi | lo) == 0u;
+    const int sh = 20 - (e & 31);
+    const bool ok = lo == 0u && e >= 0 && e <= 7 && (frac & ((1u << sh) - 1u)) == 0u;
+    byte = zero ? 0u : ((0x100000u | frac) >> sh) & 0xffu;
+    return zero || ok;
+}
+
+// Same with the record's hoisted round-1/2 constants (production kernel, c <= 254).  u8_row != nullptr: also writes the plaintext as bytes
+// and reports (warp-uniform) in *all_small_int whether EVERY value of the record is an integer in [0, 255].
 __device__ __forceinline__ bool warp_decrypt_record_ctr(const StoreView &sv, const uint8_t *rec, uint32_t K0, const uint32_t *rk, const CtrPre &pre,
-                                                        double *pt_row, int lane) {
+                                                        double *pt_row, int lane, uint8_t *u8_row, bool *all_small_int) {
     const int nbytes = 8 * sv.dim;
     const int c = (nbytes + 15) >> 4;
     const uint4 *ctv = reinterpret_cast<const uint4 *>(rec + 16);
-    bool finite = true;
+    bool finite = true, small = true;
     for (int blk = lane; blk < c; blk += 32) {
         const uint4 w = __ldg(ctv + blk);
         uint32_t ks[4];
@@ -323,10 +337,80 @@ __device__ __forceinline__ bool warp_decrypt_record_ctr(const StoreView &sv, con
             finite &= ((p2 >> 20) & 0x7ffu) != 0x7ffu;
             // big-endian FP64 (AGC:261-277): first word is the high half; one 128-bit store per block
             *reinterpret_cast<double2 *>(pt_row + 2 * blk) = make_double2(__hiloint2double((int)p0, (int)p1), __hiloint2double((int)p2, (int)p3));
+            if (u8_row) {
+                uint32_t b0, b1;
+                small &= small_int_of_double(p0, p1, b0);
+                small &= small_int_of_double(p2, p3, b1);
+                *reinterpret_cast<uint16_t *>(u8_row + 2 * blk) = (uint16_t)(b0 | (b1 << 8));
+            }
         } else {
             pt_row[2 * blk] = __hiloint2double((int)p0, (int)p1);   // odd dim: the last block holds one double, the rest is tag
+            small = false;                                          // the byte path needs dim % 16 == 0 anyway
         }
     }
+    if (all_small_int) *all_small_int = u8_row != nullptr && __all_sync(0xffffffffu, small);
+    return __all_sync(0xffffffffu, finite);
+}
+
+// ---- TMA staging of records (cp.async.bulk, 1-D) ------------------------------------------------------------------------------------
+// A warp's elected lane arms the warp's mbarrier with the byte count of the group's records and issues ONE bulk copy per record
+// (global -> that record's shared-memory row; the record is 16-byte aligned and a multiple of 16 bytes long).  The copy engine moves the
+// bytes; the lanes wait on the barrier's phase, then AES-CTR runs IN PLACE on the staged row (ciphertext words out, plaintext doubles in),
+// so the ciphertext is read from HBM exactly once per batch and never travels through the LSU's global path.
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// AES-CTR decryption IN PLACE of a record staged in shared memory by tma_load_1d: row = [iv 12 | version 4 | ciphertext | tag], the
+// plaintext doubles replace the ciphertext at row + 16.  Same outputs as warp_decrypt_record_ctr.
+__device__ __forceinline__ bool warp_decrypt_staged_ctr(int dim, unsigned char *row, uint32_t K0, const uint32_t *rk, const CtrPre &pre, int lane,
+                                                        uint8_t *u8_row, bool *all_small_int) {
+    const int nbytes = 8 * dim;
+    const int c = (nbytes + 15) >> 4;
+    uint4 *ctv = reinterpret_cast<uint4 *>(row + 16);
+    bool finite = true, small = true;
+    for (int blk = lane; blk < c; blk += 32) {
+        const uint4 w = ctv[blk];
+        uint32_t ks[4];
+        aes256_ctr_block(K0, rk, pre, (uint32_t)(blk + 2), ks);
+        const uint32_t p0 = bswap32(w.x) ^ ks[0], p1 = bswap32(w.y) ^ ks[1];
+        finite &= ((p0 >> 20) & 0x7ffu) != 0x7ffu;
+        if (!((blk == c - 1) && (nbytes & 15))) {
+            const uint32_t p2 = bswap32(w.z) ^ ks[2], p3 = bswap32(w.w) ^ ks[3];
+            finite &= ((p2 >> 20) & 0x7ffu) != 0x7ffu;
+            // big-endian FP64 (AGC:261-277): first word is the high half; little-endian double = (lo, hi)
+            ctv[blk] = make_uint4(p1, p0, p3, p2);
+            if (u8_row) {
+                uint32_t b0, b1;
+                small &= small_int_of_double(p0, p1, b0);
+                small &= small_int_of_double(p2, p3, b1);
+                *reinterpret_cast<uint16_t *>(u8_row + 2 * blk) = (uint16_t)(b0 | (b1 << 8));
+            }
+        } else {
+            *reinterpret_cast<uint2 *>(row + 16 + 16 * blk) = make_uint2(p1, p0);   // odd dim: the last block holds one double, the rest is tag
+            small = false;
+        }
+    }
+    if (all_small_int) *all_small_int = u8_row != nullptr && __all_sync(0xffffffffu, small);
     return __all_sync(0xffffffffu, finite);
 }
 
@@ -540,6 +624,32 @@ int launch_refine_verify(cudaStream_t s, const StoreView &sv, const RefineParams
 
 // Exact sequential FP64 squared distance between one query and the plaintext row `row` (shared memory), QSI:364-372: strict
 // FP64, index order, no FMA contraction.  The three query encodings are value-identical, so the result is bit-identical.
+// Both the query and the record hold integers in [0, 255]: sum of squared byte differences with |a-b| per byte (VABSDIFF4) and a 4-way
+// integer dot product (DP4A).  Every partial sum of the reference's FP64 loop is then an exact integer, so (double)acc IS its result.
+__device__ __forceinline__ double pair_dist2_bytes(const RefineParams &p, int dim, const uint8_t *row_u8, uint32_t q) {
+    const uint4 *q16 = reinterpret_cast<const uint4 *>(p.queries_u8 + (size_t)q * dim);
+    const uint4 *v16 = reinterpret_cast<const uint4 *>(row_u8);
+    const int n16 = dim >> 4;
+    uint32_t acc = 0;
+    for (int i0 = 0; i0 < n16; i0 += 8) {
+        uint4 qq[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) qq[u] = (i0 + u < n16) ? __ldg(q16 + i0 + u) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            if (i0 + u < n16) {
+                const uint4 vv = v16[i0 + u];
+                uint32_t d;
+                d = __vabsdiffu4(qq[u].x, vv.x); acc = __dp4a(d, d, acc);
+                d = __vabsdiffu4(qq[u].y, vv.y); acc = __dp4a(d, d, acc);
+                d = __vabsdiffu4(qq[u].z, vv.z); acc = __dp4a(d, d, acc);
+                d = __vabsdiffu4(qq[u].w, vv.w); acc = __dp4a(d, d, acc);
+            }
+        }
+    }
+    return (double)acc;
+}
+
 __device__ __forceinline__ double pair_dist2(const RefineParams &p, bool use_u8, bool use_f32, int dim, const double *row, uint32_t q) {
     double s = 0.0;
     const double2 *v2 = reinterpret_cast<const double2 *>(row);
@@ -640,7 +750,8 @@ __device__ __forceinline__ double pair_dist2(const RefineParams &p, bool use_u8,
 //   [region A: up to the next 64 KB boundary of the shared window][AES tables, 64 KB][region B]
 // Every warp owns `rows` plaintext rows of row_bytes = 8*dim_pad + 16 (the 16-byte skew puts the same column of different
 // rows into different bank groups); warps [0, warps_a) keep theirs in region A, the others in region B.
-struct DecryptLayout { int rows, warps_a, row_bytes; size_t smem; };
+struct DecryptLayout { int rows, warps_a, row_bytes, u8_row_bytes, rec_bytes; size_t smem; };   // u8_row_bytes > 0: byte copies of the rows follow region B;
+                                                                                             // rec_bytes > 0: rows are TMA-staged records (plaintext at +16)
 
 __global__ void __launch_bounds__(RF_THREADS, 1) refine_decrypt_kernel(const __grid_constant__ DevKeyRing ring, StoreView sv, RefineParams p, DecryptLayout lay) {
     extern __shared__ __align__(16) unsigned char rf_smem[];
@@ -651,6 +762,10 @@ __global__ void __launch_bounds__(RF_THREADS, 1) refine_decrypt_kernel(const __g
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int R = lay.rows;
     if ((uint32_t)(lay.warps_a * R * lay.row_bytes) > pad) __trap();                      // launcher assumed a larger region A
+    __shared__ __align__(8) uint64_t s_mbar[RF_WARPS];                                    // one TMA barrier per warp
+    if (lane == 0) { mbar_init(&s_mbar[warp], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    uint32_t phase = 0;
+    const int pt_off = lay.rec_bytes ? 16 : 0;                                            // staged rows: [iv | version | plaintext-in-place | tag]
 
     for (int i = tid; i < 256 * 64; i += RF_THREADS) {
         const uint32_t t0 = sv.te0[i >> 6];
@@ -662,6 +777,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) refine_decrypt_kernel(const __g
     const AesFast te{base_sa + pad + (uint32_t)lane * 4u};
     unsigned char *rows_base = warp < lay.warps_a ? rf_smem + (size_t)warp * R * lay.row_bytes
                                                   : rf_smem + pad + 0x10000u + (size_t)(warp - lay.warps_a) * R * lay.row_bytes;
+    unsigned char *u8_base = rf_smem + pad + 0x10000u + (size_t)(RF_WARPS - lay.warps_a) * R * lay.row_bytes + (size_t)warp * R * lay.u8_row_bytes;
     const bool use_u8 = p.queries_u8 != nullptr && (dim & 15) == 0 && p.f32_exact[1] != 0;
     const bool use_f32 = p.queries_f32 != nullptr && (dim & 3) == 0 && p.f32_exact[0] != 0;
     const int n_uniq = p.totals[1];
@@ -680,6 +796,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) refine_decrypt_kernel(const __g
         // pairs[] is grouped in id order, so the pairs of consecutive distinct records are contiguous.
         int32_t my_id = -1; int my_slot = -1; uint4 my_hdr = make_uint4(0, 0, 0, 0); int my_verdict = FSPANN_V_NO_KEY;
         int my_end = 0, my_off = 0;
+        bool my_small = false;                               // record `lane` of the chunk holds only integers in [0, 255] (byte row valid)
         if (lane < nrec) {
             my_id = p.uniq[base + lane];
             my_hdr = __ldg(reinterpret_cast<const uint4 *>(sv.rec + (size_t)my_id * sv.rec_stride));
@@ -697,13 +814,31 @@ __global__ void __launch_bounds__(RF_THREADS, 1) refine_decrypt_kernel(const __g
 
         for (int g0 = 0; g0 < nrec; g0 += R) {
             const int gn = min(R, nrec - g0);
-            // ---- decrypt the group's records into the warp's rows (plaintext never leaves shared memory) ----
+            // ---- stage the group's authenticated records: one bulk copy (TMA) per record into its row, completion on the warp's mbarrier ----
+            if (lay.rec_bytes) {
+                const unsigned okmask = __ballot_sync(0xffffffffu, lane >= g0 && lane < g0 + gn && my_verdict == FSPANN_V_OK);
+                if (okmask) {                                           // warp-uniform
+                    if (lane == 0) {
+                        fence_proxy_async();                            // the rows were last touched through the generic proxy
+                        mbar_expect_tx(&s_mbar[warp], (uint32_t)(__popc(okmask) * lay.rec_bytes));
+                    }
+                    for (int i = 0; i < gn; i++) {
+                        const int32_t id = __shfl_sync(0xffffffffu, my_id, g0 + i);
+                        if (lane == 0 && ((okmask >> (g0 + i)) & 1u))
+                            tma_load_1d(rows_base + (size_t)i * lay.row_bytes, sv.rec + (size_t)id * sv.rec_stride, (uint32_t)lay.rec_bytes, &s_mbar[warp]);
+                    }
+                    mbar_wait(&s_mbar[warp], phase);
+                    phase ^= 1u;
+                }
+            }
+            // ---- decrypt the group's records in their rows (plaintext never leaves shared memory) ----
             for (int i = 0; i < gn; i++) {
                 const int r = g0 + i;
                 const int32_t id = __shfl_sync(0xffffffffu, my_id, r);
                 const int slot = __shfl_sync(0xffffffffu, my_slot, r);
                 const int verdict = __shfl_sync(0xffffffffu, my_verdict, r);
-                double *pt_row = reinterpret_cast<double *>(rows_base + (size_t)i * lay.row_bytes);
+                unsigned char *row = rows_base + (size_t)i * lay.row_bytes;
+                double *pt_row = reinterpret_cast<double *>(row + pt_off);
                 if (verdict == FSPANN_V_OK) {      // plaintext is produced only for authenticated records
                     // the loop counter is warp-uniform, so the round keys are read from the kernel-parameter constant bank
                     // through the uniform datapath instead of 60 shared-memory loads per block
@@ -713,8 +848,14 @@ __global__ void __launch_bounds__(RF_THREADS, 1) refine_decrypt_kernel(const __g
                         pre.c0 = __shfl_sync(0xffffffffu, my_pre.c0, r); pre.d0 = __shfl_sync(0xffffffffu, my_pre.d0, r);
                         pre.d1 = __shfl_sync(0xffffffffu, my_pre.d1, r); pre.d2 = __shfl_sync(0xffffffffu, my_pre.d2, r);
                         pre.d3 = __shfl_sync(0xffffffffu, my_pre.d3, r);
-                        for (int vi = 0; vi < nkeys; vi++)
-                            if (vi == slot) finite = warp_decrypt_record_ctr(sv, sv.rec + (size_t)id * sv.rec_stride, te.K0, ring.rk[vi], pre, pt_row, lane);
+                        bool small = false;
+                        uint8_t *u8_row = (use_u8 && lay.u8_row_bytes) ? u8_base + (size_t)i * lay.u8_row_bytes : nullptr;
+                        for (int vi = 0; vi < nkeys; vi++) {
+                            if (vi != slot) continue;
+                            if (lay.rec_bytes) finite = warp_decrypt_staged_ctr(dim, row, te.K0, ring.rk[vi], pre, lane, u8_row, &small);
+                            else finite = warp_decrypt_record_ctr(sv, sv.rec + (size_t)id * sv.rec_stride, te.K0, ring.rk[vi], pre, pt_row, lane, u8_row, &small);
+                        }
+                        if (lane == r) my_small = small;
                     } else {
                         uint4 hdr;
                         hdr.x = __shfl_sync(0xffffffffu, my_hdr.x, r); hdr.y = __shfl_sync(0xffffffffu, my_hdr.y, r);
@@ -736,11 +877,15 @@ __global__ void __launch_bounds__(RF_THREADS, 1) refine_decrypt_kernel(const __g
                 int i = 0;                                           // which record of the group owns pair j
                 for (int t = 0; t + 1 < gn; t++) i += (j >= __shfl_sync(0xffffffffu, my_end, g0 + t)) ? 1 : 0;
                 const int verdict = __shfl_sync(0xffffffffu, my_verdict, g0 + i);
+                const bool small = __shfl_sync(0xffffffffu, my_small ? 1 : 0, g0 + i) != 0;
                 if (j < offE) {
                     const uint32_t pair = p.pairs[j];
                     if (verdict == FSPANN_V_OK) {
-                        const double *row = reinterpret_cast<const double *>(rows_base + (size_t)i * lay.row_bytes);
-                        p.dist[pair] = __dsqrt_rn(pair_dist2(p, use_u8, use_f32, dim, row, pair / (uint32_t)p.stride));
+                        const uint32_t q = pair / (uint32_t)p.stride;
+                        double d2;
+                        if (small) d2 = pair_dist2_bytes(p, dim, u8_base + (size_t)i * lay.u8_row_bytes, q);
+                        else d2 = pair_dist2(p, use_u8, use_f32, dim, reinterpret_cast<const double *>(rows_base + (size_t)i * lay.row_bytes + pt_off), q);
+                        p.dist[pair] = __dsqrt_rn(d2);
                     }
                     p.verdict[pair] = (uint8_t)verdict;
                 }
@@ -751,17 +896,21 @@ __global__ void __launch_bounds__(RF_THREADS, 1) refine_decrypt_kernel(const __g
 }
 
 // Picks the number of plaintext rows per warp that fits (see DecryptLayout).
-static bool decrypt_layout(int dim, DecryptLayout &lay) {
+static bool decrypt_layout(int dim, int64_t rec_stride, DecryptLayout &lay) {
     const int dim_pad = (dim + 1) & ~1;
-    lay.row_bytes = 8 * dim_pad + 16;
+    const bool ctr_fast = ((8 * dim + 15) >> 4) <= 254;
+    lay.rec_bytes = ctr_fast ? (int)rec_stride : 0;          // TMA staging needs the in-place CTR path
+    lay.row_bytes = lay.rec_bytes ? lay.rec_bytes + 16 : 8 * dim_pad + 16;   // + 16: the same column of different rows lands in different bank groups
     const int a_avail = 0x10000 - 2048;                       // region A: the window starts with <= 2 KB of reserved / static memory
     const int b_avail = 227 * 1024 - 2 * 0x10000 - 64;
+    lay.u8_row_bytes = (dim & 15) == 0 ? dim + 16 : 0;       // byte rows (integer-valued data), 16-byte skew like the FP64 rows
     for (int rows = 8; rows >= 1; rows--) {
         const int per_warp = rows * lay.row_bytes;
         const int wa = std::min(RF_WARPS, a_avail / per_warp), wb = RF_WARPS - wa;
-        if (wb * per_warp <= b_avail) {
+        const int u8_total = RF_WARPS * rows * lay.u8_row_bytes;
+        if (wb * per_warp + u8_total <= b_avail) {
             lay.rows = rows; lay.warps_a = wa;
-            lay.smem = (size_t)2 * 0x10000 + (size_t)wb * per_warp + 16;
+            lay.smem = (size_t)2 * 0x10000 + (size_t)wb * per_warp + (size_t)u8_total + 16;
             return true;
         }
     }
@@ -775,7 +924,7 @@ int configure_refine_kernels() {   // per-device opt-in to > 48 KB of dynamic sh
 
 int launch_refine_decrypt(cudaStream_t s, const StoreView &sv, const RefineParams &p, int sm_count) {
     DecryptLayout lay;
-    if (!decrypt_layout(sv.dim, lay)) return -1;
+    if (!decrypt_layout(sv.dim, sv.rec_stride, lay)) return -1;
     refine_decrypt_kernel<<<sm_count, RF_THREADS, lay.smem, s>>>(*sv.keys_host, sv, p, lay);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
@@ -915,71 +1064,67 @@ __global__ void __launch_bounds__(TK_THREADS) refine_topk_kernel(RefineParams p)
     if (tid == 0) { p.n_ret[q] = eff; if (p.n_dec) p.n_dec[q] = total_ok; }
 }
 
-// Register-resident form for candidate lists of <= TK_THREADS * E entries (B <= 1024 with E = 8): every thread loads its E (distance,
-// verdict) entries ONCE (rank r = tid + TK_THREADS * j, coalesced), then k rounds of: thread-local minimum -> warp shuffle minimum ->
-// four per-warp minima through shared memory -> the owner retires the selected entry.  One __syncthreads per round, no re-reads.
+// Register-resident form, ONE WARP per query, for candidate lists of <= 32 * E entries (B <= 1024 with E = 32): every lane loads its E
+// (verdict, distance) entries ONCE (rank r = lane + 32 * j, coalesced; all verdict bytes first, then the distances of the decrypted
+// ones), then k rounds of: lane-local minimum -> warp shuffle minimum -> the owner lane retires the selected entry.  No shared memory,
+// no block barrier, no re-reads.  Ties on the distance keep the lower candidate rank (the reference's stable sort, QSI:298).
+constexpr int TKW_WARPS = 4;
 template <int E>
-__global__ void __launch_bounds__(TK_THREADS) refine_topk_reg_kernel(RefineParams p) {
-    __shared__ unsigned long long s_key[2][TK_THREADS / 32];
-    __shared__ int s_rank[2][TK_THREADS / 32];
-    __shared__ int s_ndec[TK_THREADS / 32];
-    const int64_t q = blockIdx.x;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+__global__ void __launch_bounds__(TKW_WARPS * 32) refine_topk_warp_kernel(RefineParams p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = (int64_t)blockIdx.x * TKW_WARPS + (threadIdx.x >> 5);
+    if (q >= p.Q) return;
     const int n = p.n_cand[q];
     const double *dist = p.dist + (size_t)q * p.stride;
     const uint8_t *ver = p.verdict + (size_t)q * p.stride;
+    uint8_t vv[E];
+#pragma unroll
+    for (int j = 0; j < E; j++) { const int r = lane + 32 * j; vv[j] = r < n ? ver[r] : (uint8_t)0xff; }
     unsigned long long key[E];
     int ndec = 0;
 #pragma unroll
     for (int j = 0; j < E; j++) {
-        const int r = tid + TK_THREADS * j;
-        key[j] = ~0ull;
-        if (r < n && ver[r] == FSPANN_V_OK) { key[j] = (unsigned long long)__double_as_longlong(dist[r]); ndec++; }   // dist >= +0.0: bits order like values
+        const bool ok = vv[j] == FSPANN_V_OK;
+        key[j] = ok ? (unsigned long long)__double_as_longlong(dist[lane + 32 * j]) : ~0ull;     // dist >= +0.0: the bits order like the values
+        ndec += ok;
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) ndec += __shfl_xor_sync(0xffffffffu, ndec, o);
-    if (lane == 0) s_ndec[warp] = ndec;
-    __syncthreads();
-    int total_ok = 0;
-#pragma unroll
-    for (int w = 0; w < TK_THREADS / 32; w++) total_ok += s_ndec[w];
-    const int eff = min(p.k, total_ok);
+    const int eff = min(p.k, ndec);
     for (int round = 0; round < eff; round++) {
-        unsigned long long best = ~0ull; int best_r = 0x7fffffff;
+        unsigned long long best = ~0ull; int bj = 0;
 #pragma unroll
-        for (int j = 0; j < E; j++) if (key[j] < best) { best = key[j]; best_r = tid + TK_THREADS * j; }   // ties: the lower rank (smaller j) stays
+        for (int j = 0; j < E; j++) if (key[j] < best) { best = key[j]; bj = j; }          // ties: the lower rank (smaller j) stays
+        int best_r = lane + 32 * bj;
+        unsigned long long b = best; int br = best_r;
 #pragma unroll
         for (int o = 16; o; o >>= 1) {
-            const unsigned long long ok = __shfl_xor_sync(0xffffffffu, best, o);
-            const int orr = __shfl_xor_sync(0xffffffffu, best_r, o);
-            if (ok < best || (ok == best && orr < best_r)) { best = ok; best_r = orr; }
+            const unsigned long long ok = __shfl_xor_sync(0xffffffffu, b, o);
+            const int orr = __shfl_xor_sync(0xffffffffu, br, o);
+            if (ok < b || (ok == b && orr < br)) { b = ok; br = orr; }
         }
-        const int buf = round & 1;
-        if (lane == 0) { s_key[buf][warp] = best; s_rank[buf][warp] = best_r; }
-        __syncthreads();
-        unsigned long long b = s_key[buf][0]; int br = s_rank[buf][0];
+        if (br == best_r && b == best) {                              // the owner lane retires the entry and emits the result (QSI:298-316)
 #pragma unroll
-        for (int w = 1; w < TK_THREADS / 32; w++) { const unsigned long long kk = s_key[buf][w]; const int rr = s_rank[buf][w]; if (kk < b || (kk == b && rr < br)) { b = kk; br = rr; } }
-        if ((br & (TK_THREADS - 1)) == tid) {                      // the owner retires the entry and emits the result (QSI:298-316)
-#pragma unroll
-            for (int j = 0; j < E; j++) if (j == br / TK_THREADS) key[j] = ~0ull;
+            for (int j = 0; j < E; j++) key[j] = (j == bj) ? ~0ull : key[j];
             p.topk_ids[(size_t)q * p.k + round] = p.cand_ids[(size_t)q * p.stride + br];
             p.topk_dist[(size_t)q * p.k + round] = __longlong_as_double((long long)b);
             if (p.topk_rank) p.topk_rank[(size_t)q * p.k + round] = br;
         }
     }
-    for (int i = eff + tid; i < p.k; i += TK_THREADS) {
+    for (int i = eff + lane; i < p.k; i += 32) {
         p.topk_ids[(size_t)q * p.k + i] = -1;
         p.topk_dist[(size_t)q * p.k + i] = __longlong_as_double(0x7ff8000000000000ll);
         if (p.topk_rank) p.topk_rank[(size_t)q * p.k + i] = 0x7fffffff;
     }
-    if (tid == 0) { p.n_ret[q] = eff; if (p.n_dec) p.n_dec[q] = total_ok; }
+    if (lane == 0) { p.n_ret[q] = eff; if (p.n_dec) p.n_dec[q] = ndec; }
 }
 
 int launch_refine_topk(cudaStream_t s, const RefineParams &p) {
     if (p.Q <= 0) return 0;
-    if (p.stride <= TK_THREADS * 8) refine_topk_reg_kernel<8><<<(unsigned)p.Q, TK_THREADS, 0, s>>>(p);
-    else if (p.stride <= TK_THREADS * 16) refine_topk_reg_kernel<16><<<(unsigned)p.Q, TK_THREADS, 0, s>>>(p);
+    const unsigned grid = (unsigned)((p.Q + TKW_WARPS - 1) / TKW_WARPS);
+    if (p.stride <= 32 * 8) refine_topk_warp_kernel<8><<<grid, TKW_WARPS * 32, 0, s>>>(p);
+    else if (p.stride <= 32 * 16) refine_topk_warp_kernel<16><<<grid, TKW_WARPS * 32, 0, s>>>(p);
+    else if (p.stride <= 32 * 32) refine_topk_warp_kernel<32><<<grid, TKW_WARPS * 32, 0, s>>>(p);
     else refine_topk_kernel<<<(unsigned)p.Q, TK_THREADS, 0, s>>>(p);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }

@@ -352,3 +352,38 @@ def test_run_queries_max_k_token_fallback_and_per_k_recall(world_factory):
     finally:
         sys_.gpu.deleted_set(None)
         sys_.shutdown()
+
+
+def test_byte_distance_path_and_its_fallback_are_bit_exact(world_factory):
+    """Integer-valued records (SIFT / .bvecs) take the integer distance path (VABSDIFF4 + DP4A); any record holding a value that is not
+    an integer in [0, 255] (fraction, negative, 256, -0.0, denormal) must fall back to the sequential FP64 loop.  Both against the oracle."""
+    w = world_factory(**W1)
+    base = w.base.copy()
+    rng = np.random.default_rng(99)
+    odd = rng.choice(w.cfg.N, size=600, replace=False)
+    vals = [0.5, -3.0, 256.0, -0.0, 5e-324, 254.99999999999997, 1e300, 255.0, 0.0, 128.0]
+    for n_, i in enumerate(odd):
+        base[i, rng.integers(0, base.shape[1])] = vals[n_ % len(vals)]
+    ct = O.encrypt_store(base, 1, w.store.keys[1], w.iv)
+    st = O.Store(w.g.dim, w.iv, ct, w.key_version, dict(w.store.keys))
+    ctx = w.gpu_context()
+    try:
+        ctx.store_upload(w.g.dim, w.iv, ct, w.key_version)
+        codes = O.tokengen_batch(w.queries, w.g)
+        Q, B = w.queries.shape[0], 96
+        cand = np.full((Q, B), -1, dtype=np.int32)
+        for q in range(Q):                                            # half routed candidates, half of the doctored records
+            ids = O.route(w.ix, codes[q], 5, 20000)[0][:B // 2]
+            extra = rng.choice(odd, size=B - len(ids), replace=False)
+            cand[q] = np.concatenate([ids, extra]).astype(np.int32)
+        nc = np.full(Q, B, dtype=np.int32)
+        for queries in (w.queries, w.queries + 0.25):                 # byte-exact queries, then queries that disable the byte path
+            out = ctx.refine_batch(queries, cand, nc, 10)
+            for q in range(Q):
+                ref = O.refine(st, queries[q], cand[q], 10)
+                assert np.array_equal(out["verdict"][q], ref["verdict"])
+                n = len(ref["top_ids"])
+                assert out["n_ret"][q] == n and np.array_equal(out["top_ids"][q, :n], ref["top_ids"])
+                assert np.array_equal(out["top_dist"][q, :n].view(np.uint64), ref["top_dist"].view(np.uint64))
+    finally:
+        ctx.close()

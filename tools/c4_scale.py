@@ -162,15 +162,19 @@ def main():
     out = None
     if rank == 0:
         # (2) the returned distances, re-derived: regenerate each returned vector and recompute the sequential FP64 L2 (QSI:364-372)
-        need = sorted({int(i) // chunk for i in h_ids[:ns].ravel() if i >= 0})
+        want = sorted({int(i) for i in h_ids[:ns].ravel() if i >= 0})
         exact, total = 0, 0
-        cache = {}
-        for c in need:
-            cache[c] = gen_chunk(c, min(chunk, N - c * chunk), dim, cfg.base_seed).cpu().numpy()
+        rows = {}                                                                      # only the returned rows leave the device
+        for c in sorted({i // chunk for i in want}):
+            x = gen_chunk(c, min(chunk, N - c * chunk), dim, cfg.base_seed)
+            sel = [i for i in want if i // chunk == c]
+            got = x[torch.tensor([i % chunk for i in sel], device="cuda")].cpu().numpy()
+            rows.update({i: got[n_] for n_, i in enumerate(sel)})
+            del x
         q0 = batches[0][:ns].cpu().numpy()
         for q in range(ns):
             for j in range(int(h_nr[q])):
-                i = int(h_ids[q, j]); v = cache[i // chunk][i % chunk]
+                i = int(h_ids[q, j]); v = rows[i]
                 s = 0.0
                 for t_ in range(dim):
                     d = q0[q, t_] - v[t_]
