@@ -180,6 +180,7 @@ int do_refine(fspann_ctx *ctx, int64_t Q, const double *d_queries, const int32_t
     ENSURE(ctx->s_rec_verdict, (size_t)std::min<int64_t>(n1, total + 1) + 64);
     RefineParams p{};
     p.Q = Q; p.queries = d_queries; p.cand_ids = d_cand_ids; p.n_cand = d_ncand; p.stride = stride; p.k = k;
+    set_stride_divisor(p);
     p.cnt = (int32_t *)ctx->s_cnt.p; p.fill = (int32_t *)ctx->s_fill.p; p.uniq = (int32_t *)ctx->s_uniq.p;
     p.pairs = (uint32_t *)ctx->s_pairs.p; p.block_sums = (int32_t *)ctx->s_bsums.p; p.totals = (int32_t *)ctx->s_totals.p;
     p.dist = (double *)ctx->s_dist.p; p.verdict = (uint8_t *)ctx->s_verdict.p; p.touched = (uint32_t *)ctx->d_touched.p;

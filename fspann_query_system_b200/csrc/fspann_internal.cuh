@@ -89,6 +89,7 @@ struct RefineParams {
     const int32_t *cand_ids;  // [Q][stride]
     const int32_t *n_cand;    // [Q]
     int32_t stride, k;
+    uint32_t div_magic, div_shift;  // pair / stride = (umulhi(pair, div_magic) + pair) >> div_shift for pair < 2^31 (set_stride_divisor)
     // grouping scratch
     int32_t *cnt;       // [N+1]  pairs per record -> exclusive offsets after the scan
     int32_t *flag_pref; // [N+1]  exclusive prefix of (cnt>0)
@@ -133,6 +134,13 @@ constexpr int kMaxDynSmem = 227 * 1024;   // shared memory one CTA can opt in to
 int configure_tokengen_kernels();
 int configure_route_kernels();
 int configure_refine_kernels();
+
+inline void set_stride_divisor(RefineParams &p) {
+    uint32_t l = 0;
+    while ((1ull << l) < (uint64_t)p.stride) l++;
+    p.div_shift = l;
+    p.div_magic = (uint32_t)(((((uint64_t)1 << l) - (uint64_t)p.stride) << 32) / (uint64_t)p.stride + 1);
+}
 
 // launchers (each returns the number of kernels it launched, or -1 after setting a CUDA error)
 int launch_tokengen(cudaStream_t s, const RoutingView &rv, int64_t Q, const double *queries, uint64_t *codes, int32_t *work,

@@ -29,11 +29,14 @@ __device__ __forceinline__ bool is_deleted(const StoreView &sv, int32_t id) {
     return sv.deleted && id < sv.n_deleted && sv.deleted[id];
 }
 
+// q = pair / stride for pair < 2^31 with the host-precomputed multiplier (division by an invariant: one IMAD.HI, one add, one shift)
+__device__ __forceinline__ uint32_t pair_query(const RefineParams &p, uint32_t pair) { return (__umulhi(pair, p.div_magic) + pair) >> p.div_shift; }
+
 __global__ void refine_count_kernel(StoreView sv, RefineParams p) {
-    const int64_t total = p.Q * (int64_t)p.stride;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t q = i / p.stride;
-        const int r = (int)(i - q * p.stride);
+    const uint32_t total = (uint32_t)(p.Q * (int64_t)p.stride);          // < 2^31 (checked by the caller)
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const uint32_t q = pair_query(p, i);
+        const int r = (int)(i - q * (uint32_t)p.stride);
         uint8_t v = 0xff;                               // 0xff = slot not part of the candidate list
         if (r < p.n_cand[q] && (!p.qfinite || p.qfinite[q])) {   // QSI:137: a query with NaN/Inf returns empty and touches nothing
             const int32_t id = p.cand_ids[i];
@@ -881,7 +884,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) refine_decrypt_kernel(const __g
                 if (j < offE) {
                     const uint32_t pair = p.pairs[j];
                     if (verdict == FSPANN_V_OK) {
-                        const uint32_t q = pair / (uint32_t)p.stride;
+                        const uint32_t q = pair_query(p, pair);
                         double d2;
                         if (small) d2 = pair_dist2_bytes(p, dim, u8_base + (size_t)i * lay.u8_row_bytes, q);
                         else d2 = pair_dist2(p, use_u8, use_f32, dim, reinterpret_cast<const double *>(rows_base + (size_t)i * lay.row_bytes + pt_off), q);
