@@ -19,7 +19,7 @@ COUNTERS = 6
 EXPORTS = [
     "fspann_ctx_create", "fspann_ctx_destroy", "fspann_last_error", "fspann_ctx_stream", "fspann_ctx_sync",
     "fspann_ctx_launch_count", "fspann_routing_upload", "fspann_gfunctions_upload", "fspann_deleted_set",
-    "fspann_store_upload", "fspann_store_upload_shard", "fspann_store_update", "fspann_keys_set", "fspann_keys_retire", "fspann_tokengen_batch",
+    "fspann_store_upload", "fspann_store_upload_shard", "fspann_store_update", "fspann_keys_set", "fspann_keys_retire", "fspann_tokengen_batch", "fspann_tokengen_batch_dev",
     "fspann_route_batch", "fspann_refine_batch", "fspann_refine_batch_ex", "fspann_search_batch", "fspann_search_batch_dev", "fspann_search_tokens", "fspann_search_tokens_dev", "fspann_touched_fetch",
     "fspann_last_stage_ms", "fspann_debug_decrypt", "fspann_set_option", "fspann_get_info", "fspann_migrate", "fspann_encrypt_batch", "fspann_routing_build", "fspann_groundtruth", "fspann_recall_batch", "fspann_route_batch_dev", "fspann_refine_batch_dev", "fspann_merge_topk_dev",
     "fspann_comm_unique_id", "fspann_comm_init", "fspann_comm_destroy", "fspann_sharded_search_batch", "fspann_sharded_search_batch_dev",

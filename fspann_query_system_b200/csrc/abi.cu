@@ -118,7 +118,8 @@ int run_tokengen(fspann_ctx *ctx, int64_t Q, const double *d_queries, uint64_t *
     ENSURE(ctx->s_tg_qf, sizeof(float) * (size_t)Q * (((size_t)ctx->rv.dim + 3) / 4 * 4));
     ENSURE(ctx->s_tg_norm, sizeof(float) * (size_t)Q);
     LAUNCHED(launch_tokengen(ctx->stream, ctx->rv, Q, d_queries, d_codes, (int32_t *)ctx->s_tg_work.p, (unsigned long long *)ctx->s_tg_list.p, cap,
-                             (float *)ctx->s_tg_qf.p, (float *)ctx->s_tg_norm.p, ctx->opt_tokengen_exact != 0, ctx->sm_count));
+                             (float *)ctx->s_tg_qf.p, (float *)ctx->s_tg_norm.p, ctx->opt_tokengen_exact ? 1 : ctx->opt_tokengen_mode, ctx->sm_count,
+                             &ctx->last_tokengen_path));
     return 0;
 }
 
@@ -253,7 +254,7 @@ void fspann_ctx_destroy(fspann_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    DevBuf *bufs[] = {&ctx->d_alpha_f, &ctx->d_alpha_norm, &ctx->s_vorder, &ctx->s_voff, &ctx->s_qfinite, &ctx->s_retry_out, &ctx->s_codes_in, &ctx->s_tg_work, &ctx->s_tg_list, &ctx->s_tg_qf, &ctx->s_tg_norm, &ctx->d_alpha, &ctx->d_r, &ctx->d_omega, &ctx->d_keys, &ctx->d_rep, &ctx->d_ids, &ctx->d_deleted, &ctx->d_rec,
+    DevBuf *bufs[] = {&ctx->d_alpha_f, &ctx->d_alpha_norm, &ctx->d_alpha_tc, &ctx->s_vorder, &ctx->s_voff, &ctx->s_qfinite, &ctx->s_retry_out, &ctx->s_codes_in, &ctx->s_tg_work, &ctx->s_tg_list, &ctx->s_tg_qf, &ctx->s_tg_norm, &ctx->d_alpha, &ctx->d_r, &ctx->d_omega, &ctx->d_keys, &ctx->d_rep, &ctx->d_ids, &ctx->d_deleted, &ctx->d_rec,
                       &ctx->d_keyring, &ctx->d_hpow, &ctx->d_shoup, &ctx->s_rec_verdict, &ctx->s_qf32, &ctx->s_qu8, &ctx->s_f32_exact, &ctx->d_te0, &ctx->d_touched, &ctx->s_queries, &ctx->s_codes, &ctx->s_cand_ids,
                       &ctx->s_cand_sc, &ctx->s_ncand, &ctx->s_raw, &ctx->s_uniq_cnt, &ctx->s_route_scratch, &ctx->s_overflow, &ctx->s_cnt,
                       &ctx->s_flag, &ctx->s_fill, &ctx->s_uniq, &ctx->s_pairs, &ctx->s_bsums, &ctx->s_totals, &ctx->s_dist, &ctx->s_verdict,
@@ -285,16 +286,19 @@ int fspann_set_option(fspann_ctx *ctx, const char *name, int64_t value) {
     if (!strcmp(name, "route_general")) { ctx->opt_route_general = value != 0; return FSPANN_OK; }
     if (!strcmp(name, "route_wl_extra")) { ctx->opt_route_wl_extra = (int)value; return FSPANN_OK; }
     if (!strcmp(name, "tokengen_exact")) { ctx->opt_tokengen_exact = value != 0; return FSPANN_OK; }
+    if (!strcmp(name, "tokengen_mode")) { ctx->opt_tokengen_mode = (int)value; return FSPANN_OK; }
     if (!strcmp(name, "tokengen_list_cap")) { ctx->opt_tg_list_cap = value; return FSPANN_OK; }
     return fail(ctx, FSPANN_E_ARG, "unknown option %s", name);
 }
 int64_t fspann_get_info(fspann_ctx *ctx, const char *name) {
     if (!ctx || !name) return -1;
     if (!strcmp(name, "last_route_path")) return ctx->last_route_path;
+    if (!strcmp(name, "last_tokengen_path")) return ctx->last_tokengen_path;
     if (!strcmp(name, "sm_count")) return ctx->sm_count;
     if (!strcmp(name, "build_treeified")) return ctx->last_build_treeified;
     if (!strcmp(name, "tokengen_rechecked") || !strcmp(name, "tokengen_overflow")) {   // of the last TokenGen launch on this context
         int32_t w[2] = {0, 0};
+        if (ctx->last_tokengen_path == 1) return 0;                  // the exact kernel alone ran: nothing was listed
         if (!ctx->s_tg_work.p || cudaSetDevice(ctx->device) != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess ||
             cudaMemcpy(w, ctx->s_tg_work.p, sizeof w, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
         return !strcmp(name, "tokengen_rechecked") ? w[0] : w[1];
@@ -330,6 +334,17 @@ int fspann_routing_upload(fspann_ctx *ctx, int32_t dim, int32_t T, int32_t D, in
     ENSURE(ctx->d_alpha_f, sizeof(float) * (size_t)TD * m * dim);
     ENSURE(ctx->d_alpha_norm, sizeof(float) * (size_t)TD * m);
     LAUNCHED(launch_alpha_prepare(ctx->stream, (const double *)ctx->d_alpha.p, (int64_t)TD * m, dim, (float *)ctx->d_alpha_f.p, (float *)ctx->d_alpha_norm.p));
+    const uint16_t *alpha_tc = nullptr;
+    {   // alpha as BF16 pieces in tensor-core tile layout (tokengen_tc.cu); shapes it does not cover keep alpha_tc = nullptr
+        RoutingView tv{};
+        tv.dim = dim; tv.T = T; tv.D = D; tv.m = m; tv.lambda = lambda; tv.W = W; tv.TD = TD; tv.alpha = (const double *)ctx->d_alpha.p;
+        const size_t tc_bytes = tokengen_tc_alpha_bytes(tv);
+        if (tc_bytes) {
+            ENSURE(ctx->d_alpha_tc, tc_bytes);
+            LAUNCHED(launch_alpha_tc_prepare(ctx->stream, tv, (uint16_t *)ctx->d_alpha_tc.p));
+            alpha_tc = (const uint16_t *)ctx->d_alpha_tc.p;
+        }
+    }
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaMemcpy(ctx->d_r.p, r, sizeof(double) * (size_t)TD * m, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->d_omega.p, omega, sizeof(double) * (size_t)TD * m, cudaMemcpyHostToDevice));
@@ -339,7 +354,7 @@ int fspann_routing_upload(fspann_ctx *ctx, int32_t dim, int32_t T, int32_t D, in
     RoutingView &rv = ctx->rv;
     rv.dim = dim; rv.T = T; rv.D = D; rv.m = m; rv.lambda = lambda; rv.W = W; rv.TD = TD; rv.n_ids = n_ids; rv.P = P;
     rv.alpha = (const double *)ctx->d_alpha.p; rv.r = (const double *)ctx->d_r.p; rv.omega = (const double *)ctx->d_omega.p;
-    rv.alpha_f32 = (const float *)ctx->d_alpha_f.p; rv.alpha_norm = (const float *)ctx->d_alpha_norm.p;
+    rv.alpha_f32 = (const float *)ctx->d_alpha_f.p; rv.alpha_norm = (const float *)ctx->d_alpha_norm.p; rv.alpha_tc = alpha_tc;
     rv.keys = (const int64_t *)ctx->d_keys.p; rv.rep = (const uint64_t *)ctx->d_rep.p; rv.ids = (const int32_t *)ctx->d_ids.p;
     ctx->routing_ready = true;
     return FSPANN_OK;
@@ -830,6 +845,20 @@ int fspann_tokengen_batch(fspann_ctx *ctx, int64_t Q, const double *queries, uin
     { int rc_ = run_tokengen(ctx, Q, (const double *)ctx->s_queries.p, (uint64_t *)ctx->s_codes.p); if (rc_) return rc_; }
     CK(cudaMemcpyAsync(codes_out, ctx->s_codes.p, cb, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return FSPANN_OK;
+}
+
+int fspann_tokengen_batch_dev(fspann_ctx *ctx, int64_t Q, const double *d_queries, uint64_t *d_codes) {
+    if (!ctx) return FSPANN_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    int rc = check_routing(ctx); if (rc) return rc;
+    if (Q == 0) return FSPANN_OK;
+    if (Q < 0 || !d_queries || !d_codes) return fail(ctx, FSPANN_E_ARG, "null array");
+    const int64_t chunk = 1 << 20;                               // the re-check list is sized per launch
+    for (int64_t s0 = 0; s0 < Q; s0 += chunk) {
+        rc = run_tokengen(ctx, std::min(chunk, Q - s0), d_queries + (size_t)s0 * ctx->rv.dim, d_codes + (size_t)s0 * ctx->rv.TD * ctx->rv.W);
+        if (rc) return rc;
+    }
     return FSPANN_OK;
 }
 

@@ -28,6 +28,9 @@ struct fspann_ctx {
     bool routing_ready = false;
     RoutingView rv{};
     DevBuf d_alpha, d_r, d_omega, d_keys, d_rep, d_ids, d_deleted, d_alpha_f, d_alpha_norm, s_tg_work, s_tg_list, s_tg_qf, s_tg_norm;
+    DevBuf d_alpha_tc;           // alpha as BF16 pieces in UMMA tile layout (tensor-core TokenGen)
+    int opt_tokengen_mode = 0;   // 0 automatic (tensor cores when the shape allows), 2 = FP32 pre-filter only
+    int last_tokengen_path = 0;  // 1 exact, 2 FP32 pre-filter, 3 tensor-core pre-filter
     int opt_tokengen_exact = 0;  // run the exact FP64 TokenGen kernel alone (no FP32 pre-filter)
     int64_t opt_tg_list_cap = 0; // test hook: clamp the re-check list (forces the overflow -> exact-kernel fallback)
 

@@ -27,6 +27,7 @@ struct RoutingView {
     const double *alpha, *r, *omega;  // [TD][m][dim], [TD][m], [TD][m]
     const float *alpha_f32;           // [TD][m][dim] alpha rounded to FP32 (TokenGen pre-filter)
     const float *alpha_norm;          // [TD][m] upper bounds of ||alpha_j||_2
+    const uint16_t *alpha_tc;         // alpha as three BF16 pieces in UMMA tile layout (tokengen_tc.cu), or nullptr
     const int64_t *keys;              // [TD][P][2] interleaved (minKey, maxKey)
     const uint64_t *rep;              // [TD][P][W]
     const int32_t *ids;               // [TD][n_ids]
@@ -144,7 +145,13 @@ inline void set_stride_divisor(RefineParams &p) {
 
 // launchers (each returns the number of kernels it launched, or -1 after setting a CUDA error)
 int launch_tokengen(cudaStream_t s, const RoutingView &rv, int64_t Q, const double *queries, uint64_t *codes, int32_t *work,
-                    unsigned long long *list, int64_t list_cap, float *qf, float *qnorm, bool exact_only, int sm_count);
+                    unsigned long long *list, int64_t list_cap, float *qf, float *qnorm, int mode, int sm_count, int *path_out);
+// tokengen_tc.cu: the pre-filter's contraction on the tensor cores (tcgen05.mma, accumulator in TMEM)
+size_t tokengen_tc_alpha_bytes(const RoutingView &rv);
+int launch_alpha_tc_prepare(cudaStream_t s, const RoutingView &rv, uint16_t *out);
+int launch_tokengen_tc(cudaStream_t s, const RoutingView &rv, int64_t Q, const double *queries, const uint16_t *alpha_tc, uint64_t *codes, int32_t *work,
+                       unsigned long long *list, int64_t list_cap, int sm_count);
+int configure_tokengen_tc_kernels();
 int64_t tokengen_list_capacity(const RoutingView &rv, int64_t Q);
 int launch_alpha_prepare(cudaStream_t s, const double *alpha, int64_t rows, int dim, float *alpha_f, float *norm);
 int launch_route(cudaStream_t s, const RoutingView &rv, const RouteParams &p, int grid);

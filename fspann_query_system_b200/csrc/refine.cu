@@ -784,7 +784,10 @@ __global__ void __launch_bounds__(RF_THREADS, 1) refine_decrypt_kernel(const __g
     const bool use_u8 = p.queries_u8 != nullptr && (dim & 15) == 0 && p.f32_exact[1] != 0;
     const bool use_f32 = p.queries_f32 != nullptr && (dim & 3) == 0 && p.f32_exact[0] != 0;
     const int n_uniq = p.totals[1];
-    const int n_chunks = (n_uniq + 31) >> 5;
+    // records per chunk: 32 for a full batch; fewer when the batch names few distinct records (a small batch, or one shard of a sharded
+    // store), so that every warp of the grid gets work instead of 32 records queueing behind one warp
+    const int cs = max(1, min(32, n_uniq / (int)(gridDim.x * RF_WARPS)));
+    const int n_chunks = (n_uniq + cs - 1) / cs;
     const bool ctr_fast = ((8 * dim + 15) >> 4) <= 254;       // every counter 2..c+1 fits in one byte
 
     for (;;) {
@@ -792,8 +795,8 @@ __global__ void __launch_bounds__(RF_THREADS, 1) refine_decrypt_kernel(const __g
         if (lane == 0) chunk = atomicAdd(&p.totals[2], 1);
         chunk = __shfl_sync(0xffffffffu, chunk, 0);
         if (chunk >= n_chunks) break;
-        const int base = chunk << 5;
-        const int nrec = min(32, n_uniq - base);
+        const int base = chunk * cs;
+        const int nrec = min(cs, n_uniq - base);
 
         // lane l fetches the header, the authentication verdict and the pair range of record l.  uniq[] is sorted by id and
         // pairs[] is grouped in id order, so the pairs of consecutive distinct records are contiguous.
@@ -977,25 +980,19 @@ int launch_queries_to_f32(cudaStream_t s, const double *q, float *out, uint8_t *
 __global__ void __launch_bounds__(1024) retry_select_kernel(int64_t Q, int k, const int32_t *__restrict__ n_ret, const int32_t *__restrict__ n_dec,
                                                             const int32_t *__restrict__ exact, int32_t *__restrict__ rows, int32_t *__restrict__ out) {
     __shared__ int s_w[32];
-    __shared__ int s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_base = 0;
+    const int64_t per = (Q + 1023) / 1024, lo = min(Q, tid * per), hi = min(Q, lo + per);    // thread t owns rows [lo, hi): order = thread order
+    int mine = 0;
+    for (int64_t q = lo; q < hi; q++) { const int nd = n_dec[q]; mine += nd > 0 && (n_ret[q] < k || nd < 10 * k); }   // QSI:293: nothing decrypted -> no retry
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+    if (lane == 31) s_w[warp] = incl;
     __syncthreads();
-    for (int64_t q0 = 0; q0 < Q; q0 += 1024) {
-        const int64_t q = q0 + tid;
-        bool need = false;
-        if (q < Q) { const int nd = n_dec[q]; need = nd > 0 && (n_ret[q] < k || nd < 10 * k); }   // QSI:293: nothing decrypted -> plain return, no retry
-        const unsigned bal = __ballot_sync(0xffffffffu, need);
-        if (lane == 0) s_w[warp] = __popc(bal);
-        __syncthreads();
-        int before = s_base, total = 0;
-        for (int w = 0; w < 32; w++) { const int c = s_w[w]; if (w < warp) before += c; total += c; }
-        if (need) rows[before + __popc(bal & ((1u << lane) - 1u))] = (int32_t)q;
-        __syncthreads();
-        if (tid == 0) s_base += total;
-        __syncthreads();
-    }
-    if (tid == 0) { out[0] = s_base; out[1] = exact[2] == 0 ? 1 : 0; }
+    int before = incl - mine, total = 0;
+    for (int w = 0; w < 32; w++) { const int c = s_w[w]; if (w < warp) before += c; total += c; }
+    if (mine) for (int64_t q = lo; q < hi; q++) { const int nd = n_dec[q]; if (nd > 0 && (n_ret[q] < k || nd < 10 * k)) rows[before++] = (int32_t)q; }
+    if (tid == 0) { out[0] = total; out[1] = exact[2] == 0 ? 1 : 0; }
 }
 int launch_retry_select(cudaStream_t s, int64_t Q, int k, const int32_t *n_ret, const int32_t *n_dec, const int32_t *exact, int32_t *rows, int32_t *out) {
     if (Q <= 0) return 0;

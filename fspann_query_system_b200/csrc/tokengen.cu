@@ -361,7 +361,7 @@ __global__ void tokengen_recheck_kernel(RoutingView rv, const double *__restrict
 // The opt-in to > 48 KB of dynamic shared memory is a per-DEVICE attribute of each kernel: fspann_ctx_create calls this after
 // cudaSetDevice, so every context's device is configured no matter how many GPUs one process drives.
 int configure_tokengen_kernels() {
-    return opt_in_smem(tokengen_kernel) || opt_in_smem(tokengen_fast_kernel) ? -1 : 0;
+    return opt_in_smem(tokengen_kernel) || opt_in_smem(tokengen_fast_kernel) || configure_tokengen_tc_kernels() ? -1 : 0;
 }
 
 static int launch_tokengen_exact(cudaStream_t s, const RoutingView &rv, int64_t Q, const double *queries, uint64_t *codes, const int32_t *run_if, int sm_count) {
@@ -388,10 +388,25 @@ int64_t tokengen_list_capacity(const RoutingView &rv, int64_t Q) {
     return std::max<int64_t>(65536, total / 8);
 }
 
-// work: int32[2] + list: uint64[tokengen_list_capacity] scratch (or nullptr / exact != 0: the exact kernel alone).
+// work: int32[2] + list: uint64[tokengen_list_capacity] scratch.  mode: 0 = automatic (tensor-core pre-filter when the shape allows it, else
+// the FP32 pre-filter, else exact), 1 = the exact FP64 kernel alone, 2 = FP32 pre-filter (no tensor cores).  *path_out: 1 exact, 2 FP32, 3 tensor.
 int launch_tokengen(cudaStream_t s, const RoutingView &rv, int64_t Q, const double *queries, uint64_t *codes, int32_t *work,
-                    unsigned long long *list, int64_t list_cap, float *qf, float *qnorm, bool exact_only, int sm_count) {
+                    unsigned long long *list, int64_t list_cap, float *qf, float *qnorm, int mode, int sm_count, int *path_out) {
     if (Q <= 0) return 0;
+    const bool exact_only = mode == 1;
+    if (path_out) *path_out = 1;
+    if (mode == 0 && work && list && rv.alpha_tc && rv.alpha_norm && Q * (int64_t)rv.TD * rv.m < (1LL << 31)) {
+        if (cudaMemsetAsync(work, 0, 2 * sizeof(int32_t), s) != cudaSuccess) return -1;
+        const int n_tc = launch_tokengen_tc(s, rv, Q, queries, rv.alpha_tc, codes, work, list, list_cap, sm_count);
+        if (n_tc < 0) return -1;
+        if (n_tc > 0) {
+            tokengen_recheck_kernel<<<sm_count * 2, 256, 0, s>>>(rv, queries, codes, work, list, list_cap);
+            if (cudaGetLastError() != cudaSuccess) return -1;
+            const int n = launch_tokengen_exact(s, rv, Q, queries, codes, work + 1, sm_count);      // runs only after a worklist overflow
+            if (path_out) *path_out = 3;
+            return n < 0 ? -1 : n_tc + 1 + n;
+        }
+    }
     const bool fast_ok = !exact_only && work && list && qf && qnorm && rv.alpha_f32 && rv.alpha_norm && (rv.m + 1) / 2 <= TF_JB && rv.TD < 65536 && rv.m < 256 &&
                          Q * (int64_t)rv.TD * rv.m < (1LL << 31);        // the re-check counter is an int32: it can never wrap
     if (!fast_ok) return launch_tokengen_exact(s, rv, Q, queries, codes, nullptr, sm_count);
@@ -417,6 +432,7 @@ int launch_tokengen(cudaStream_t s, const RoutingView &rv, int64_t Q, const doub
     tokengen_recheck_kernel<<<sm_count * 2, 256, 0, s>>>(rv, queries, codes, work, list, list_cap);
     if (cudaGetLastError() != cudaSuccess) return -1;
     const int n = launch_tokengen_exact(s, rv, Q, queries, codes, work + 1, sm_count);      // runs only after a worklist overflow
+    if (path_out) *path_out = 2;
     return n < 0 ? -1 : 3 + n;
 }
 

@@ -169,6 +169,9 @@ class GpuContext:
         self._ck(self.lib.fspann_tokengen_batch(self.ctx, C.c_int64(Q), N.ptr(queries), N.ptr(codes)))
         return codes
 
+    def tokengen_batch_dev(self, Q, d_queries, d_codes):
+        self._ck(self.lib.fspann_tokengen_batch_dev(self.ctx, C.c_int64(Q), C.c_void_p(d_queries), C.c_void_p(d_codes)))
+
     def route_batch(self, codes, probes, hard_cap, B, ham_threshold=0):
         codes = np.ascontiguousarray(codes, dtype=np.uint64)
         Q = codes.shape[0]

@@ -70,7 +70,9 @@ int64_t fspann_ctx_launch_count(const fspann_ctx *ctx);
 /* Tuning / test switches: "route_general" = 1 forces the general Route kernel (sequential groups, exact HARD_CAP
  * semantics) even where the shared-memory fast path applies; "route_wl_extra" = n >= 0 clamps the fast path's dedicated
  * worklist to n entries (test hook for its overflow fallback), -1 = automatic; "tokengen_exact" = 1 runs the exact FP64 TokenGen
- * kernel alone instead of the FP32 pre-filter + exact re-check (the codes are identical either way).  fspann_get_info:
+ * kernel alone instead of a pre-filter + exact re-check; "tokengen_mode" = 0 (default) runs the pre-filter's contraction on the tensor
+ * cores (tcgen05.mma on BF16-split operands, accumulator in TMEM) when the shape allows it, 2 = on the FP32 FMA pipe (the codes are
+ * identical in every mode).  fspann_get_info: "last_tokengen_path" (1 exact, 2 FP32 pre-filter, 3 tensor-core pre-filter),
  * "last_route_path" (1 fast, 2 general), "sm_count", "build_treeified", "tokengen_rechecked" / "tokengen_overflow" (projections
  * the last TokenGen launch had to re-check exactly / whether its list overflowed and the exact kernel recomputed the batch). */
 int fspann_set_option(fspann_ctx *ctx, const char *name, int64_t value);
@@ -176,6 +178,8 @@ int fspann_keys_retire(fspann_ctx *ctx, int32_t version);
  * queries FP64 [Q][dim] -> codes uint64 [Q][T*D][W].  A query holding NaN/Inf fails the whole call with
  * FSPANN_E_ARG (Coding:355-360 requireVector). */
 int fspann_tokengen_batch(fspann_ctx *ctx, int64_t Q, const double *queries, uint64_t *codes_out);
+/* Device-resident variant (no copies, no synchronisation, no NaN/Inf scan): Setup-side bulk coding of vectors already in HBM. */
+int fspann_tokengen_batch_dev(fspann_ctx *ctx, int64_t Q, const double *d_queries, uint64_t *d_codes);
 
 /* ---- Route (a6-a12): lookupCandidatesWithScores + the first-B cut of QueryServiceImpl stage A.5 ------------
  * (PIS:592-753, QSI:153-214).  probes = effectiveMaxProbes() (PIS:880-888), hard_cap = max(maxGlobalCandidates,

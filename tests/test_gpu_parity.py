@@ -215,8 +215,8 @@ def test_routing_build_on_device_matches_reference_build(wg):
 
 
 def test_tokengen_prefilter_and_exact_kernel_agree_incl_boundary_vectors(wg):
-    """TokenGen runs an FP32 pre-filter with a proven error bound and re-checks the undecided projections with the exact sequential
-    FP64 arithmetic.  Codes must equal the exact kernel's and the oracle's: on ordinary data, on vectors constructed to sit ON
+    """TokenGen runs a reduced-precision pre-filter (tensor cores: BF16-split tcgen05.mma with the accumulator in TMEM; or the FP32 FMA
+    pipe) with an error bound and re-checks the undecided projections with the exact sequential FP64 arithmetic.  Codes must equal the exact kernel's and the oracle's: on ordinary data, on vectors constructed to sit ON
     quantisation boundaries ((alpha.v + r)/omega within 1e-12 of an integer -> must be re-checked), on huge / tiny magnitudes, and
     when the re-check list overflows (whole batch recomputed by the exact kernel)."""
     w, ctx = wg
@@ -237,21 +237,28 @@ def test_tokengen_prefilter_and_exact_kernel_agree_incl_boundary_vectors(wg):
     extremes = np.stack([base[0] * 1e30, base[1] * 1e-30, base[2] * 1e300, np.zeros(g.dim), -base[3]])
     vecs = np.concatenate([base, np.asarray(tricky), extremes])
     ref = O.tokengen_batch(vecs, g)
-    got = ctx.tokengen_batch(vecs)
-    n_re = ctx.get_info("tokengen_rechecked")
-    assert np.array_equal(got, ref)
     total = vecs.shape[0] * g.T * g.D * g.m
-    if g.m <= 24:                                                        # (m > 24 dispatches to the exact kernel: nothing to re-check)
-        assert len(tricky) <= n_re < 0.2 * total, (n_re, total)         # the boundary cases were re-checked; the bulk was not
-    assert ctx.get_info("tokengen_overflow") == 0
+    paths = set()
     try:
+        for mode in (0, 2):                                              # 0: tensor-core pre-filter (tcgen05) where the shape allows, 2: FP32 pre-filter
+            ctx.set_option("tokengen_mode", mode)
+            got = ctx.tokengen_batch(vecs)
+            n_re, path = ctx.get_info("tokengen_rechecked"), ctx.get_info("last_tokengen_path")
+            paths.add(path)
+            assert np.array_equal(got, ref), (mode, path)
+            if path != 1:                                                # (path 1 = the exact kernel alone: nothing to re-check)
+                assert len(tricky) <= n_re < 0.2 * total, (n_re, total)  # the boundary cases were re-checked; the bulk was not
+            assert ctx.get_info("tokengen_overflow") == 0
+            ctx.set_option("tokengen_list_cap", 8)                       # overflow -> the exact kernel recomputes the batch
+            assert np.array_equal(ctx.tokengen_batch(vecs), ref)
+            assert ctx.get_info("tokengen_overflow") == (1 if path != 1 else 0)
+            ctx.set_option("tokengen_list_cap", 0)
         ctx.set_option("tokengen_exact", 1)
-        assert np.array_equal(ctx.tokengen_batch(vecs), ref)
-        ctx.set_option("tokengen_exact", 0)
-        ctx.set_option("tokengen_list_cap", 8)                           # overflow -> the exact kernel recomputes the batch
-        assert np.array_equal(ctx.tokengen_batch(vecs), ref)
-        assert ctx.get_info("tokengen_overflow") == (1 if g.m <= 24 else 0)
+        assert np.array_equal(ctx.tokengen_batch(vecs), ref) and ctx.get_info("last_tokengen_path") == 1
     finally:
         ctx.set_option("tokengen_exact", 0)
+        ctx.set_option("tokengen_mode", 0)
         ctx.set_option("tokengen_list_cap", 0)
+    if g.dim <= 128 and g.W == 1:
+        assert 3 in paths                                                # the tensor-core path did run for this shape
     assert np.array_equal(ctx.tokengen_batch(vecs[:7]), ref[:7]) and ctx.get_info("tokengen_overflow") == 0
