@@ -49,7 +49,7 @@ def load_traffic(workload_is_c2: bool):
     if not workload_is_c2:
         return None
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r1_decrypt_traffic.json")))
+        d = json.load(open(os.path.join(ROOT, "profiles", "r2_decrypt_traffic.json")))
         return float(d["dram_bytes_read"]) + float(d["dram_bytes_write"])
     except Exception:
         return None
@@ -647,7 +647,7 @@ def main():
                        "ms_per_step": e2e_ms / K, "wall_ms_per_step": e2e_wall_ms / K, "result_checksum": checksum},
                "roofline": {"bound": "hbm", "kernel": "refine_decrypt_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                             "frac": achieved / peak if peak else None, "traffic": load_traffic(args.config == "C2" and not args.n and not args.q),
-                            "traffic_unit": "bytes/launch (dram read+write, ncu; profiles/r1_decrypt_traffic.json)", "peak_source": peak_src,
+                            "traffic_unit": "bytes/launch (dram read+write, ncu; profiles/r2_decrypt_traffic.json)", "peak_source": peak_src,
                             "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": dec_ms, "pairs_per_launch": pairs / K,
                             "stage_ms": refine_stage_ms, "stage_achieved": stage_achieved, "stage_frac": stage_achieved / peak if peak else None,
                             "stage_what": "group + verify + decrypt + top-k: the whole refine stage, same algorithmic bytes",
