@@ -546,12 +546,12 @@ def main():
         sh_l0 = gpu.launch_count()
         sh_ms = run.timed(step_sh, K, Wm, barrier)
         sh_launches = (gpu.launch_count() - sh_l0) / (K + Wm)
+        sh_stage = gpu.sharded_stage_ms()                                 # of the LAST timed step (ranks in lock-step: no harness skew)
+        sh_refine = {kk: vv for kk, vv in gpu.stage_ms().items() if kk in ("group", "verify", "decrypt", "topk")}
         eq = True
         for b in range(len(refs)):
             step_sh(b)
             eq = eq and same_result(run.result(), refs[b])
-        sh_stage = gpu.sharded_stage_ms()
-        sh_refine = {kk: vv for kk, vv in gpu.stage_ms().items() if kk in ("group", "verify", "decrypt", "topk")}
         if world_size > 1:
             t = torch.tensor([sh_ms, 0.0 if eq else 1.0], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -24,6 +24,14 @@ public final class FspannGpu implements AutoCloseable {
     private static final MethodHandle KEYS_RETIRE  = h("fspann_keys_retire",  FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT));
     private static final MethodHandle SEARCH       = h("fspann_search_batch", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_LONG, ADDRESS, JAVA_INT, JAVA_INT,
             JAVA_LONG, JAVA_INT, JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
+    private static final MethodHandle SEARCH_TOK   = h("fspann_search_tokens", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_LONG, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT,
+            JAVA_LONG, JAVA_INT, JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
+    private static final MethodHandle COMM_ID      = h("fspann_comm_unique_id", FunctionDescriptor.of(JAVA_INT, ADDRESS));
+    private static final MethodHandle COMM_INIT    = h("fspann_comm_init", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS));
+    private static final MethodHandle STORE_SHARD  = h("fspann_store_upload_shard", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_LONG, JAVA_LONG, JAVA_LONG, JAVA_INT,
+            ADDRESS, ADDRESS, ADDRESS));
+    private static final MethodHandle SHARDED      = h("fspann_sharded_search_batch", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_LONG, ADDRESS, JAVA_INT, JAVA_INT,
+            JAVA_LONG, JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
     private static final MethodHandle TOUCHED      = h("fspann_touched_fetch", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, JAVA_INT));
 
     private final MemorySegment ctx;
@@ -57,6 +65,33 @@ public final class FspannGpu implements AutoCloseable {
     public void searchBatch(long q, MemorySegment queries, int k, int probes, long hardCap, int refinementLimit, int hammingThreshold,
                             MemorySegment idsOut, MemorySegment distOut, MemorySegment nRetOut, MemorySegment countersOut) throws Throwable {
         check((int) SEARCH.invokeExact(ctx, q, queries, k, probes, hardCap, refinementLimit, hammingThreshold, idsOut, distOut, nRetOut, countersOut));
+    }
+    /** QueryServiceImpl.search on the tokens' own codes (PIS:600): codes = q*T*D*W longs (BitSet.toLongArray words), queries = decrypted payloads. */
+    public void searchTokens(long q, MemorySegment codes, MemorySegment queries, int k, int probes, long hardCap, int refinementLimit, int hammingThreshold,
+                             MemorySegment idsOut, MemorySegment distOut, MemorySegment nRetOut, MemorySegment countersOut) throws Throwable {
+        check((int) SEARCH_TOK.invokeExact(ctx, q, codes, queries, k, probes, hardCap, refinementLimit, hammingThreshold, idsOut, distOut, nRetOut, countersOut));
+    }
+
+    // ---- database-sharded deployment (BASELINE config 4): one FspannGpu per GPU, the NCCL collectives run inside the library
+    /** Any one participant draws the 128-byte communicator id and hands it to the others. */
+    public static byte[] commUniqueId() throws Throwable {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment id = a.allocate(128);
+            if ((int) COMM_ID.invokeExact(id) != 0) throw new IllegalStateException("NCCL unavailable (libnccl.so.2 not loadable; set FSPANN_NCCL_LIB)");
+            return id.toArray(JAVA_BYTE);
+        }
+    }
+    /** Collective: every participant calls it with the same id and its own rank; rank r holds the r-th contiguous id range of the store. */
+    public void commInit(int nRanks, int rank, byte[] id) throws Throwable {
+        try (Arena a = Arena.ofConfined()) { check((int) COMM_INIT.invokeExact(ctx, nRanks, rank, a.allocateArray(JAVA_BYTE, id))); }
+    }
+    public void storeUploadShard(long idBase, long n, long nGlobal, int dim, MemorySegment iv, MemorySegment ct, MemorySegment keyVersion) throws Throwable {
+        check((int) STORE_SHARD.invokeExact(ctx, idBase, n, nGlobal, dim, iv, ct, keyVersion));
+    }
+    /** Collective: the same batch on every participant, the same (unsharded-identical) result on every participant. */
+    public void shardedSearchBatch(long q, MemorySegment queries, int k, int probes, long hardCap, int refinementLimit,
+                                   MemorySegment idsOut, MemorySegment distOut, MemorySegment nRetOut, MemorySegment countersOut) throws Throwable {
+        check((int) SHARDED.invokeExact(ctx, q, queries, k, probes, hardCap, refinementLimit, idsOut, distOut, nRetOut, countersOut));
     }
     // routingUpload / storeUpload / storeUpdate / touchedFetch follow the same pattern.
 

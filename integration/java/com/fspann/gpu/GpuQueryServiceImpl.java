@@ -27,19 +27,32 @@ public final class GpuQueryServiceImpl implements QueryService {
         if (!index.isFrozen()) throw new IllegalStateException("Index not finalized");       // PIS:594
         int q = tokens.size(), dim = tokens.get(0).getDimension(), k = tokens.get(0).getTopK();
         try (Arena a = Arena.ofConfined()) {
+            var paper = cfg.getPaper();
+            int td = paper.getTables() * paper.getDivisions(), w = (paper.getM() * paper.getLambda() + 63) / 64;
             MemorySegment qs = a.allocateArray(JAVA_DOUBLE, (long) q * dim);
+            MemorySegment codes = a.allocateArray(JAVA_LONG, (long) q * td * w);   // zero-filled: BitSet.toLongArray drops trailing zero words
             for (int i = 0; i < q; i++) {                                    // QSI:124-135: decrypt the query inside the trusted component
                 QueryToken t = tokens.get(i);
                 KeyVersion kv; try { kv = keys.getVersion(t.getVersion()); } catch (Throwable e) { kv = keys.getCurrentVersion(); }
                 double[] v = crypto.decryptQuery(t.getEncryptedQuery(), t.getIv(), kv.getKey());
                 MemorySegment.copy(v, 0, qs, JAVA_DOUBLE, (long) i * dim * 8, dim);
+                BitSet[][] bc = t.getBitCodes();                             // Route runs on the token's OWN codes (PIS:600): no second TokenGen
+                if (bc == null) throw new IllegalStateException("MSANNP violation: QueryToken missing BitSet codes");   // PIS:604-606
+                for (int tt = 0; tt < paper.getTables(); tt++)
+                    for (int d = 0; d < paper.getDivisions(); d++) {
+                        long[] words = bc[tt][d].toLongArray();
+                        for (int x = 0; x < words.length && x < w; x++) codes.setAtIndex(JAVA_LONG, ((long) i * td + (long) tt * paper.getDivisions() + d) * w + x, words[x]);
+                    }
             }
             MemorySegment ids = a.allocateArray(JAVA_INT, (long) q * k), dist = a.allocateArray(JAVA_DOUBLE, (long) q * k),
                           nRet = a.allocateArray(JAVA_INT, q), cnt = a.allocateArray(JAVA_LONG, (long) q * 6);
             var rt = cfg.getRuntime();
-            gpu.searchBatch(q, qs, k, index.effectiveMaxProbes(), Math.max(rt.getMaxGlobalCandidates(), rt.getRefinementLimit()),
-                            getEffectiveRefinementLimit(rt.getRefinementLimit()), rt.getHammingPrefilterThreshold(), ids, dist, nRet, cnt);
-            index.clearProbeOverride();                                      // QSI:343 (finally)
+            try {
+                gpu.searchTokens(q, codes, qs, k, index.effectiveMaxProbes(), Math.max(rt.getMaxGlobalCandidates(), rt.getRefinementLimit()),
+                                 getEffectiveRefinementLimit(rt.getRefinementLimit()), rt.getHammingPrefilterThreshold(), ids, dist, nRet, cnt);
+            } finally {
+                index.clearProbeOverride();                                  // QSI:342-346 (finally)
+            }
             List<List<QueryResult>> out = new ArrayList<>(q);
             for (int i = 0; i < q; i++) {
                 int n = nRet.getAtIndex(JAVA_INT, i);
