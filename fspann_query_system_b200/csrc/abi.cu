@@ -155,6 +155,7 @@ int do_route(fspann_ctx *ctx, int64_t Q, const uint64_t *d_codes, int probes, in
     const int grid = route_grid(Q, ctx->sm_count);
     ENSURE(ctx->s_route_scratch, sizeof(int32_t) * (size_t)p.scratch_ints * grid);
     ENSURE(ctx->s_overflow, sizeof(int32_t));
+    CK(cudaMemsetAsync(ctx->s_overflow.p, 0, sizeof(int32_t), ctx->stream));     // per call; read back by fspann_get_info("route_treeified")
     p.scratch = (int32_t *)ctx->s_route_scratch.p;
     p.chain_overflow = (int32_t *)ctx->s_overflow.p;
     LAUNCHED(launch_route(ctx->stream, rv, p, grid));
@@ -294,6 +295,13 @@ int64_t fspann_get_info(fspann_ctx *ctx, const char *name) {
     if (!ctx || !name) return -1;
     if (!strcmp(name, "last_route_path")) return ctx->last_route_path;
     if (!strcmp(name, "last_tokengen_path")) return ctx->last_tokengen_path;
+    if (!strcmp(name, "route_treeified")) {   // general Route kernel: did a bestScore bin of the last call reach 9 entries (the JDK would treeify it)?
+        int32_t f = 0;
+        if (ctx->last_route_path != 2 || !ctx->s_overflow.p) return 0;
+        if (cudaSetDevice(ctx->device) != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess ||
+            cudaMemcpy(&f, ctx->s_overflow.p, sizeof f, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+        return f;
+    }
     if (!strcmp(name, "sm_count")) return ctx->sm_count;
     if (!strcmp(name, "build_treeified")) return ctx->last_build_treeified;
     if (!strcmp(name, "tokengen_rechecked") || !strcmp(name, "tokengen_overflow")) {   // of the last TokenGen launch on this context

@@ -73,7 +73,8 @@ int64_t fspann_ctx_launch_count(const fspann_ctx *ctx);
  * kernel alone instead of a pre-filter + exact re-check; "tokengen_mode" = 0 (default) runs the pre-filter's contraction on the tensor
  * cores (tcgen05.mma on BF16-split operands, accumulator in TMEM) when the shape allows it, 2 = on the FP32 FMA pipe (the codes are
  * identical in every mode).  fspann_get_info: "last_tokengen_path" (1 exact, 2 FP32 pre-filter, 3 tensor-core pre-filter),
- * "last_route_path" (1 fast, 2 general), "sm_count", "build_treeified", "tokengen_rechecked" / "tokengen_overflow" (projections
+ * "last_route_path" (1 fast, 2 general), "route_treeified" (general path only: 1 if a bin of a query's bestScore map reached 9 entries in the
+ * last call -- the JDK treeifies such a bin and its iteration order is not modelled), "sm_count", "build_treeified", "tokengen_rechecked" / "tokengen_overflow" (projections
  * the last TokenGen launch had to re-check exactly / whether its list overflowed and the exact kernel recomputed the batch). */
 int fspann_set_option(fspann_ctx *ctx, const char *name, int64_t value);
 int64_t fspann_get_info(fspann_ctx *ctx, const char *name);

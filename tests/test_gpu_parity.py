@@ -54,8 +54,10 @@ def test_route_candidates_ordered_bit_exact(wg, probes, hard_cap, B, general):
         ctx.set_option("route_general", 0)
     if general:
         assert ctx.get_info("last_route_path") == 2
+    worst_chain = 0
     for q in range(codes.shape[0]):
         ids, sc, raw, mc = O.route(w.ix, codes[q], probes, hard_cap)
+        worst_chain = max(worst_chain, mc)
         n = min(B, len(ids))
         assert out["n_cand"][q] == n
         assert out["unique"][q] == len(ids)
@@ -69,6 +71,10 @@ def test_route_candidates_ordered_bit_exact(wg, probes, hard_cap, B, general):
                 assert set(out["cand_ids"][q, :n].tolist()) == set(ids.tolist())
             continue
         assert np.array_equal(out["cand_ids"][q, :n], ids[:n]), f"query {q}"
+    flag = ctx.get_info("route_treeified")
+    if general and worst_chain >= 9:   # the general kernel reports a bin of 9 (it checks at the map's initial capacity: it may flag more than the oracle's final-capacity audit, never less)
+        assert flag == 1
+    assert flag in (0, 1) and (flag == 0 or ctx.get_info("last_route_path") == 2)
 
 
 def test_refine_verdicts_topk_bit_exact(wg):
