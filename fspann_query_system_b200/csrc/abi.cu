@@ -30,6 +30,7 @@ int fail(fspann_ctx *c, int code, const char *fmt, ...) {
 int ensure(fspann_ctx *ctx, DevBuf &b, size_t bytes) {
     if (bytes == 0) bytes = 16;
     if (b.bytes >= bytes) return 0;
+    if (ctx) ctx->epoch++;                                         // a buffer moves: captured graphs hold stale pointers
     if (b.p) { cudaFree(b.p); b.p = nullptr; b.bytes = 0; }
     size_t want = bytes + (bytes >> 3);
     cudaError_t e = cudaMalloc(&b.p, want);
@@ -79,6 +80,7 @@ int rebuild_keys(fspann_ctx *ctx) {
     }
     ring.n = n;
     ctx->ring_host = ring;
+    ctx->epoch++;                                                  // the key ring is a by-value kernel argument
     ctx->sv.keys_host = &ctx->ring_host;
     ENSURE(ctx->d_keyring, sizeof ring);
     ENSURE(ctx->d_hpow, sizeof(u128) * hp.size());
@@ -105,6 +107,7 @@ int check_store(fspann_ctx *ctx) {
 }
 
 int record_ev(fspann_ctx *ctx, int i) {
+    if (ctx->capturing) return 0;
     CK(cudaEventRecord(ctx->ev[i], ctx->stream));
     return 0;
 }
@@ -174,6 +177,7 @@ int do_refine(fspann_ctx *ctx, int64_t Q, const double *d_queries, const int32_t
     ENSURE(ctx->s_cnt, sizeof(int32_t) * (size_t)n1);
     ENSURE(ctx->s_fill, sizeof(int32_t) * (size_t)n1);
     ENSURE(ctx->s_uniq, sizeof(int32_t) * (size_t)std::min<int64_t>(n1, total + 1));
+    ENSURE(ctx->s_uoff, sizeof(int32_t) * ((size_t)std::min<int64_t>(n1, total + 1) + 2));
     ENSURE(ctx->s_pairs, sizeof(uint32_t) * (size_t)(total + 1));
     ENSURE(ctx->s_bsums, sizeof(int32_t) * 2 * (size_t)(nblocks + 1));
     ENSURE(ctx->s_totals, sizeof(int32_t) * 4);
@@ -183,7 +187,7 @@ int do_refine(fspann_ctx *ctx, int64_t Q, const double *d_queries, const int32_t
     RefineParams p{};
     p.Q = Q; p.queries = d_queries; p.cand_ids = d_cand_ids; p.n_cand = d_ncand; p.stride = stride; p.k = k;
     set_stride_divisor(p);
-    p.cnt = (int32_t *)ctx->s_cnt.p; p.fill = (int32_t *)ctx->s_fill.p; p.uniq = (int32_t *)ctx->s_uniq.p;
+    p.cnt = (int32_t *)ctx->s_cnt.p; p.fill = (int32_t *)ctx->s_fill.p; p.uniq = (int32_t *)ctx->s_uniq.p; p.uoff = (int32_t *)ctx->s_uoff.p;
     p.pairs = (uint32_t *)ctx->s_pairs.p; p.block_sums = (int32_t *)ctx->s_bsums.p; p.totals = (int32_t *)ctx->s_totals.p;
     p.dist = (double *)ctx->s_dist.p; p.verdict = (uint8_t *)ctx->s_verdict.p; p.touched = (uint32_t *)ctx->d_touched.p;
     p.rec_verdict = (uint8_t *)ctx->s_rec_verdict.p;
@@ -258,7 +262,7 @@ void fspann_ctx_destroy(fspann_ctx *ctx) {
     DevBuf *bufs[] = {&ctx->d_alpha_f, &ctx->d_alpha_norm, &ctx->d_alpha_tc, &ctx->s_vorder, &ctx->s_voff, &ctx->s_qfinite, &ctx->s_retry_out, &ctx->s_codes_in, &ctx->s_tg_work, &ctx->s_tg_list, &ctx->s_tg_qf, &ctx->s_tg_norm, &ctx->d_alpha, &ctx->d_r, &ctx->d_omega, &ctx->d_keys, &ctx->d_rep, &ctx->d_ids, &ctx->d_deleted, &ctx->d_rec,
                       &ctx->d_keyring, &ctx->d_hpow, &ctx->d_shoup, &ctx->s_rec_verdict, &ctx->s_qf32, &ctx->s_qu8, &ctx->s_f32_exact, &ctx->d_te0, &ctx->d_touched, &ctx->s_queries, &ctx->s_codes, &ctx->s_cand_ids,
                       &ctx->s_cand_sc, &ctx->s_ncand, &ctx->s_raw, &ctx->s_uniq_cnt, &ctx->s_route_scratch, &ctx->s_overflow, &ctx->s_cnt,
-                      &ctx->s_flag, &ctx->s_fill, &ctx->s_uniq, &ctx->s_pairs, &ctx->s_bsums, &ctx->s_totals, &ctx->s_dist, &ctx->s_verdict,
+                      &ctx->s_flag, &ctx->s_fill, &ctx->s_uniq, &ctx->s_uoff, &ctx->s_pairs, &ctx->s_bsums, &ctx->s_totals, &ctx->s_dist, &ctx->s_verdict,
                       &ctx->s_topk_ids, &ctx->s_topk_dist, &ctx->s_topk_rank, &ctx->s_nret, &ctx->s_ndec, &ctx->s_counters, &ctx->s_stage_a, &ctx->s_stage_b,
                       &ctx->s_stage_c, &ctx->s_vis_part, &ctx->s_vis_score, &ctx->s_vis_n, &ctx->r_rows, &ctx->r_queries, &ctx->r_codes, &ctx->r_topk_ids, &ctx->r_topk_dist, &ctx->r_nret,
                       &ctx->r_counters, &ctx->t_cand_ids, &ctx->t_cand_sc, &ctx->t_ncand, &ctx->t_raw, &ctx->t_uniq_cnt, &ctx->t_ndec,
@@ -266,6 +270,8 @@ void fspann_ctx_destroy(fspann_ctx *ctx) {
                       &ctx->b_codes, &ctx->b_staged, &ctx->b_scratch, &ctx->b_ids, &ctx->b_keys, &ctx->b_rep, &ctx->b_flag,
                       &ctx->m_list, &ctx->m_gid, &ctx->m_iv, &ctx->m_verdict, &ctx->m_flag, &ctx->m_rec, &ctx->m_vec, &ctx->m_out_iv, &ctx->m_out_ct, &ctx->m_out_ver};
     for (DevBuf *b : bufs) release(*b);
+    for (auto &g : ctx->graphs) cudaGraphExecDestroy(g.exec);
+    ctx->graphs.clear();
     sharded_release(ctx);
     for (int i = 0; i < 7; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -284,6 +290,8 @@ int64_t fspann_ctx_launch_count(const fspann_ctx *ctx) { return ctx ? ctx->launc
 
 int fspann_set_option(fspann_ctx *ctx, const char *name, int64_t value) {
     if (!ctx || !name) return FSPANN_E_ARG;
+    ctx->epoch++;
+    if (!strcmp(name, "graphs")) { ctx->opt_graphs = value != 0; return FSPANN_OK; }
     if (!strcmp(name, "route_general")) { ctx->opt_route_general = value != 0; return FSPANN_OK; }
     if (!strcmp(name, "route_wl_extra")) { ctx->opt_route_wl_extra = (int)value; return FSPANN_OK; }
     if (!strcmp(name, "tokengen_exact")) { ctx->opt_tokengen_exact = value != 0; return FSPANN_OK; }
@@ -303,6 +311,8 @@ int64_t fspann_get_info(fspann_ctx *ctx, const char *name) {
         return f;
     }
     if (!strcmp(name, "sm_count")) return ctx->sm_count;
+    if (!strcmp(name, "graph_replays")) return ctx->graph_replays;
+    if (!strcmp(name, "graph_captures")) return ctx->graph_captures;
     if (!strcmp(name, "build_treeified")) return ctx->last_build_treeified;
     if (!strcmp(name, "tokengen_rechecked") || !strcmp(name, "tokengen_overflow")) {   // of the last TokenGen launch on this context
         int32_t w[2] = {0, 0};
@@ -481,6 +491,7 @@ int fspann_routing_build_finish(fspann_ctx *ctx, const int32_t *staged_ids, int6
     std::swap(ctx->d_rep, ctx->b_rep);
     rv.n_ids = N; rv.P = P;
     rv.keys = (const int64_t *)ctx->d_keys.p; rv.rep = (const uint64_t *)ctx->d_rep.p; rv.ids = (const int32_t *)ctx->d_ids.p;
+    ctx->epoch++;
     ctx->routing_ready = true;
     ctx->build_n = 0; ctx->build_added = 0;
     // optional copies for the host's own persistence, in fspann_routing_upload's layout
@@ -507,6 +518,7 @@ int fspann_routing_build(fspann_ctx *ctx, int64_t N, const double *vectors, cons
 int fspann_deleted_set(fspann_ctx *ctx, const uint8_t *flags, int64_t n) {
     if (!ctx) return FSPANN_E_ARG;
     CK(cudaSetDevice(ctx->device));
+    ctx->epoch++;
     if (!flags || n <= 0) {
         ctx->rv.deleted = nullptr; ctx->rv.n_deleted = 0; ctx->sv.deleted = nullptr; ctx->sv.n_deleted = 0;
         return FSPANN_OK;
@@ -560,6 +572,7 @@ int fspann_store_upload_shard(fspann_ctx *ctx, int64_t id_base, int64_t N, int64
     CK(cudaMemsetAsync(ctx->d_rec.p, 0, (size_t)N * stride + 64, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_touched.p, 0, sizeof(uint32_t) * (size_t)((N + 31) / 32 + 1), ctx->stream));
     const bool dim_changed = ctx->sv.dim != dim;
+    ctx->epoch++;
     ctx->sv.N = N; ctx->sv.id_base = id_base; ctx->sv.n_global = n_global;
     ctx->sv.dim = dim; ctx->sv.rec_stride = stride; ctx->sv.rec = (const uint8_t *)ctx->d_rec.p;
     if (dim_changed || !ctx->sv.hpow) { int rc = rebuild_keys(ctx); if (rc) return rc; }
@@ -585,6 +598,7 @@ int fspann_store_alloc_shard(fspann_ctx *ctx, int64_t id_base, int64_t N, int64_
     CK(cudaMemsetAsync(ctx->d_rec.p, 0, (size_t)N * stride + 64, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_touched.p, 0, sizeof(uint32_t) * (size_t)((N + 31) / 32 + 1), ctx->stream));
     const bool dim_changed = ctx->sv.dim != dim;
+    ctx->epoch++;
     ctx->sv.N = N; ctx->sv.id_base = id_base; ctx->sv.n_global = n_global;
     ctx->sv.dim = dim; ctx->sv.rec_stride = stride; ctx->sv.rec = (const uint8_t *)ctx->d_rec.p;
     if (dim_changed || !ctx->sv.hpow) { int rc = rebuild_keys(ctx); if (rc) return rc; }
@@ -1005,16 +1019,67 @@ int search_core(fspann_ctx *ctx, int64_t Q, const double *d_queries, const uint6
                 const HostOut *host) {
     if (probes <= 0) probes = 5;   // DEFAULT_MAX_PROBES (PIS:93) when no override is configured (PIS:880-888)
     const int64_t l0 = ctx->launches;
-    int rc = search_pass(ctx, Q, d_queries, d_codes_in, k, probes, hard_cap, B, 0, d_topk_ids, d_topk_dist, d_n_ret, d_counters, true);
-    if (rc) return rc;
-    ctx->ev_valid = true;
     const bool need_flags = allow_retry || reject_nonfinite;
+    int rc;
+    // first pass + retry decision: eager, or (small batches, from the second use of the same shape and buffers on) one CUDA-graph launch
+    auto first_pass = [&]() -> int {
+        int rc_ = search_pass(ctx, Q, d_queries, d_codes_in, k, probes, hard_cap, B, 0, d_topk_ids, d_topk_dist, d_n_ret, d_counters, true);
+        if (rc_) return rc_;
+        if (need_flags) {
+            ENSURE(ctx->r_rows, sizeof(int32_t) * (size_t)Q);
+            ENSURE(ctx->s_retry_out, sizeof(int32_t) * 4);
+            LAUNCHED(launch_retry_select(ctx->stream, Q, k, d_n_ret, (const int32_t *)ctx->s_ndec.p, (const int32_t *)ctx->s_f32_exact.p,
+                                         (int32_t *)ctx->r_rows.p, (int32_t *)ctx->s_retry_out.p));
+        }
+        return 0;
+    };
+    bool done = false;
+    if (ctx->opt_graphs && Q <= 64) {
+        const std::array<int64_t, 12> key = {Q, k, probes, hard_cap, B, (int64_t)(intptr_t)d_queries, (int64_t)(intptr_t)d_codes_in, (int64_t)(intptr_t)d_topk_ids,
+                                             (int64_t)(intptr_t)d_topk_dist, (int64_t)(intptr_t)d_n_ret, (int64_t)(intptr_t)d_counters ^ (need_flags ? 1 : 0), ctx->epoch};
+        for (auto &g : ctx->graphs)
+            if (g.key == key) {
+                CK(cudaGraphLaunch(g.exec, ctx->stream));
+                ctx->launches += g.launches;
+                ctx->graph_replays++;
+                ctx->ev_valid = false;
+                done = true;
+                break;
+            }
+        if (!done && ctx->graph_seen == key) {                     // second use, nothing moved in between: capture, then launch
+            const int64_t lc = ctx->launches;
+            ctx->capturing = true;
+            cudaError_t ce = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal);
+            int rc_ = ce == cudaSuccess ? first_pass() : FSPANN_E_CUDA;
+            cudaGraph_t graph = nullptr;
+            if (ce == cudaSuccess) ce = cudaStreamEndCapture(ctx->stream, &graph);
+            ctx->capturing = false;
+            cudaGraphExec_t exec = nullptr;
+            if (rc_ == 0 && ce == cudaSuccess && graph && ctx->epoch == key[11] && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+                if (ctx->graphs.size() >= 16) { cudaGraphExecDestroy(ctx->graphs.front().exec); ctx->graphs.erase(ctx->graphs.begin()); }
+                ctx->graphs.push_back({key, exec, ctx->launches - lc});
+                ctx->graph_captures++;
+                CK(cudaGraphLaunch(exec, ctx->stream));
+                ctx->ev_valid = false;
+                done = true;
+            } else {
+                cudaGetLastError();                                // a failed capture leaves a sticky-looking (but cleared) error: fall back to eager
+                ctx->launches = lc;
+            }
+            if (graph) cudaGraphDestroy(graph);
+        }
+        if (!done) {
+            rc = first_pass(); if (rc) return rc;
+            ctx->ev_valid = true;
+            done = true;
+            std::array<int64_t, 12> seen = key;
+            seen[11] = ctx->epoch;                                 // the eager pass may have grown a buffer
+            ctx->graph_seen = seen;
+        }
+    }
+    if (!done) { rc = first_pass(); if (rc) return rc; ctx->ev_valid = true; }
     if (need_flags) {
         if (!ctx->h_pin) { CK(cudaHostAlloc((void **)&ctx->h_pin, sizeof(int32_t) * 16, cudaHostAllocDefault)); ctx->h_pin_ints = 16; }
-        ENSURE(ctx->r_rows, sizeof(int32_t) * (size_t)Q);
-        ENSURE(ctx->s_retry_out, sizeof(int32_t) * 4);
-        LAUNCHED(launch_retry_select(ctx->stream, Q, k, d_n_ret, (const int32_t *)ctx->s_ndec.p, (const int32_t *)ctx->s_f32_exact.p,
-                                     (int32_t *)ctx->r_rows.p, (int32_t *)ctx->s_retry_out.p));
         CK(cudaMemcpyAsync(ctx->h_pin, ctx->s_retry_out.p, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     }
     if (host) { rc = copy_results(ctx, Q, k, *host, d_topk_ids, d_topk_dist, d_n_ret, d_counters); if (rc) return rc; }
@@ -1026,14 +1091,15 @@ int search_core(fspann_ctx *ctx, int64_t Q, const double *d_queries, const uint6
         if (R > 0) {
             const int dim = ctx->rv.dim;
             const size_t code_row = sizeof(uint64_t) * (size_t)ctx->rv.TD * ctx->rv.W;
-            ENSURE(ctx->r_queries, sizeof(double) * (size_t)R * dim);
-            ENSURE(ctx->r_topk_ids, sizeof(int32_t) * (size_t)R * k); ENSURE(ctx->r_topk_dist, sizeof(double) * (size_t)R * k);
-            ENSURE(ctx->r_nret, sizeof(int32_t) * (size_t)R); ENSURE(ctx->r_counters, sizeof(int64_t) * FSPANN_COUNTERS * (size_t)R);
+            const size_t Rc = (size_t)(Q <= 64 ? Q : R);               // small batches: size once, so a later, larger retry set moves nothing (graphs)
+            ENSURE(ctx->r_queries, sizeof(double) * Rc * dim);
+            ENSURE(ctx->r_topk_ids, sizeof(int32_t) * Rc * k); ENSURE(ctx->r_topk_dist, sizeof(double) * Rc * k);
+            ENSURE(ctx->r_nret, sizeof(int32_t) * Rc); ENSURE(ctx->r_counters, sizeof(int64_t) * FSPANN_COUNTERS * Rc);
             const int32_t *rows = (const int32_t *)ctx->r_rows.p;
             LAUNCHED(launch_gather_rows(ctx->stream, d_queries, ctx->r_queries.p, rows, R, sizeof(double) * dim, false));
             const uint64_t *codes2 = nullptr;
             if (d_codes_in) {
-                ENSURE(ctx->r_codes, code_row * (size_t)R);
+                ENSURE(ctx->r_codes, code_row * Rc);
                 LAUNCHED(launch_gather_rows(ctx->stream, d_codes_in, ctx->r_codes.p, rows, R, (int64_t)code_row, false));
                 codes2 = (const uint64_t *)ctx->r_codes.p;
             }

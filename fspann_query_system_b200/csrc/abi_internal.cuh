@@ -1,5 +1,6 @@
 // abi_internal.cuh -- the context behind the C ABI and the host-side helpers shared by abi.cu and sharded.cu.
 #pragma once
+#include <array>
 #include <map>
 #include <string>
 #include <vector>
@@ -50,7 +51,7 @@ struct fspann_ctx {
     DevBuf s_rec_verdict, s_qf32, s_qu8, s_f32_exact, s_vorder, s_voff, s_qfinite, s_retry_out, s_codes_in;
     DevKeyRing ring_host{};
     int32_t *want_rank = nullptr;
-    DevBuf s_cnt, s_flag, s_fill, s_uniq, s_pairs, s_bsums, s_totals, s_dist, s_verdict;
+    DevBuf s_cnt, s_flag, s_fill, s_uniq, s_uoff, s_pairs, s_bsums, s_totals, s_dist, s_verdict;
     DevBuf s_topk_ids, s_topk_dist, s_topk_rank, s_nret, s_ndec, s_counters;
     DevBuf s_stage_a, s_stage_b, s_stage_c;  // upload staging
     DevBuf g_base, g_q, g_dist, g_ids, g_d2, g_flag, g_res, g_nret, g_rec;  // ground truth / recall
@@ -70,6 +71,16 @@ struct fspann_ctx {
     cudaEvent_t sh_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     bool sh_ev_valid = false;
     int64_t sh_gather_bytes = 0;                 // bytes this rank RECEIVED through the collectives of the last sharded pass
+
+    // CUDA graphs for small batches: the whole first pass (TokenGen .. counters, retry decision) of a (Q, k, probes, cap, B, buffers) combination
+    // is captured on its second use and replayed afterwards; `epoch` changes whenever a pointer or a by-value kernel argument may have changed
+    struct GraphEntry { std::array<int64_t, 12> key; cudaGraphExec_t exec; int64_t launches; };
+    std::vector<GraphEntry> graphs;
+    std::array<int64_t, 12> graph_seen{};        // key of the last eager small-batch pass (capture happens on its repetition)
+    int64_t epoch = 1;
+    int opt_graphs = 1;
+    bool capturing = false;
+    int64_t graph_replays = 0, graph_captures = 0;
 
     cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool ev_valid = false;

@@ -95,7 +95,8 @@ struct RefineParams {
     int32_t *cnt;       // [N+1]  pairs per record -> exclusive offsets after the scan
     int32_t *flag_pref; // [N+1]  exclusive prefix of (cnt>0)
     int32_t *fill;      // [N]
-    int32_t *uniq;      // [<= min(N, Q*stride)]
+    int32_t *uniq;      // [<= min(N, Q*stride)]  distinct records named by the batch, ascending
+    int32_t *uoff;      // [n_uniq + 1] where the pairs of distinct record #u start in pairs[] (uoff[n_uniq] = number of pairs)
     uint32_t *pairs;    // [Q*stride]
     int32_t *block_sums;  // scan scratch
     int32_t *totals;    // [4]: n_pairs, n_uniq, work counter, spare

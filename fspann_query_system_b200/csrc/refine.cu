@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_partial_kernel(const int32_
     block_excl_scan2(acc, &tot);
     if (threadIdx.x == 0) { block_sums[2 * blockIdx.x] = tot.x; block_sums[2 * blockIdx.x + 1] = tot.y; }
 }
-__global__ void __launch_bounds__(SCAN_THREADS) scan_sums_kernel(int32_t *block_sums, int nblocks, int32_t *totals) {
+__global__ void __launch_bounds__(SCAN_THREADS) scan_sums_kernel(int32_t *block_sums, int nblocks, int32_t *totals, int32_t *uoff) {
     __shared__ int2 carry;
     if (threadIdx.x == 0) carry = make_int2(0, 0);
     __syncthreads();
@@ -97,11 +97,11 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_sums_kernel(int32_t *block_
         if (threadIdx.x == 0) { carry.x = c.x + tot.x; carry.y = c.y + tot.y; }
         __syncthreads();
     }
-    if (threadIdx.x == 0) { totals[0] = carry.x; totals[1] = carry.y; totals[2] = 0; totals[3] = 0; }
+    if (threadIdx.x == 0) { totals[0] = carry.x; totals[1] = carry.y; totals[2] = 0; totals[3] = 0; uoff[carry.y] = carry.x; }   // sentinel: end of the last record's pairs
 }
 // Rewrites cnt[] in place to exclusive offsets, writes flag prefix, the unique-id list and zeroes fill[].
 __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(int32_t *__restrict__ cnt, int64_t n, const int32_t *__restrict__ block_sums,
-                                                                  int32_t *__restrict__ uniq, int32_t *__restrict__ fill) {
+                                                                  int32_t *__restrict__ uniq, int32_t *__restrict__ uoff, int32_t *__restrict__ fill) {
     const int64_t b0 = (int64_t)blockIdx.x * SCAN_ITEMS;
     // thread owns SCAN_PER_THREAD consecutive items so the in-block order is the id order
     int c[SCAN_PER_THREAD];
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(int32_t *__res
         if (i < n) {
             cnt[i] = ex.x;
             fill[i] = 0;
-            if (c[k] > 0) uniq[ex.y] = (int32_t)i;
+            if (c[k] > 0) { uniq[ex.y] = (int32_t)i; uoff[ex.y] = ex.x; }   // distinct record #ex.y and where its pairs start
             ex.x += c[k]; ex.y += c[k] > 0;
         }
     }
@@ -133,16 +133,98 @@ __global__ void refine_fill_kernel(StoreView sv, RefineParams p) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Small batches (Q * stride <= GS_MAX pairs: a handful of queries): ONE CTA classifies the candidate slots, sorts the pending
+// (record, pair) keys in shared memory and emits the same grouping (uniq / uoff / pairs / totals) -- instead of a memset, a count,
+// three scans over the N-entry arrays and a fill (six launches touching ~16 MB at N = 1 M).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int GS_THREADS = 1024;
+constexpr int GS_MAX = 8192;                     // pairs; 8 per thread; 64 KB of 64-bit keys
+__global__ void __launch_bounds__(GS_THREADS) refine_group_small_kernel(StoreView sv, RefineParams p) {
+    extern __shared__ __align__(16) unsigned char gs_smem[];
+    unsigned long long *s_key = reinterpret_cast<unsigned long long *>(gs_smem);   // [n_sort] (local record index << 13) | pair index; ~0 = not pending
+    __shared__ int s_wsum[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int total = (int)(p.Q * (int64_t)p.stride);
+    int n_sort = 1024; while (n_sort < total) n_sort <<= 1;
+    for (int i = tid; i < n_sort; i += GS_THREADS) {
+        unsigned long long key = ~0ull;
+        if (i < total) {
+            const uint32_t q = pair_query(p, (uint32_t)i);
+            const int r = i - (int)q * p.stride;
+            uint8_t v = 0xff;
+            if (r < p.n_cand[q] && (!p.qfinite || p.qfinite[q])) {
+                const int32_t id = p.cand_ids[i];
+                if (id < 0 || id >= sv.n_global || is_deleted(sv, id)) v = FSPANN_V_NOT_FOUND;
+                else if (id < sv.id_base || id >= sv.id_base + sv.N) v = 0xfd;
+                else { v = 0xfe; key = ((unsigned long long)(uint32_t)(id - sv.id_base) << 13) | (unsigned long long)i; }
+            }
+            p.verdict[i] = v;
+        }
+        s_key[i] = key;
+    }
+    __syncthreads();
+    for (int k = 2; k <= n_sort; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < n_sort; i += GS_THREADS) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned long long a = s_key[i], b = s_key[ixj];
+                    if ((a > b) == ((i & k) == 0)) { s_key[i] = b; s_key[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    // pending pairs are now sorted by (record, pair); thread t owns the contiguous run [t*per, (t+1)*per)
+    const int per = n_sort / GS_THREADS, lo = tid * per;
+    int heads = 0, pend = 0;
+    for (int i = lo; i < lo + per; i++) {
+        const unsigned long long key = s_key[i];
+        if (key == ~0ull) continue;
+        pend++;
+        heads += (i == 0 || (s_key[i - 1] >> 13) != (key >> 13)) ? 1 : 0;
+    }
+    // block-wide exclusive prefix of (heads, pend)
+    int ih = heads, ip = pend;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int a = __shfl_up_sync(0xffffffffu, ih, o), b = __shfl_up_sync(0xffffffffu, ip, o);
+        if (lane >= o) { ih += a; ip += b; }
+    }
+    if (lane == 31) s_wsum[warp] = ih;
+    __syncthreads();
+    int bh = 0, th = 0;
+    for (int w = 0; w < 32; w++) { const int c = s_wsum[w]; if (w < warp) bh += c; th += c; }
+    __syncthreads();
+    if (lane == 31) s_wsum[warp] = ip;
+    __syncthreads();
+    int bp = 0, tp = 0;
+    for (int w = 0; w < 32; w++) { const int c = s_wsum[w]; if (w < warp) bp += c; tp += c; }
+    int u = bh + ih - heads, pos = bp + ip - pend;
+    for (int i = lo; i < lo + per; i++) {
+        const unsigned long long key = s_key[i];
+        if (key == ~0ull) continue;
+        if (i == 0 || (s_key[i - 1] >> 13) != (key >> 13)) { p.uniq[u] = (int32_t)(key >> 13); p.uoff[u] = pos; u++; }
+        p.pairs[pos++] = (uint32_t)(key & 0x1fffu);
+    }
+    if (tid == 0) { p.totals[0] = tp; p.totals[1] = th; p.totals[2] = 0; p.totals[3] = 0; p.uoff[th] = tp; }
+}
+
 int launch_refine_group(cudaStream_t s, const StoreView &sv, const RefineParams &p) {
+    const int64_t total = p.Q * (int64_t)p.stride;
+    if (total <= GS_MAX) {
+        int n_sort = 1024; while (n_sort < total) n_sort <<= 1;
+        refine_group_small_kernel<<<1, GS_THREADS, sizeof(unsigned long long) * (size_t)n_sort, s>>>(sv, p);
+        return cudaGetLastError() == cudaSuccess ? 1 : -1;
+    }
     const int64_t n = sv.N + 1;  // one extra slot so cnt[N] = total after the scan
     if (cudaMemsetAsync(p.cnt, 0, sizeof(int32_t) * (size_t)n, s) != cudaSuccess) return -1;
-    const int64_t total = p.Q * (int64_t)p.stride;
     int grid = (int)((total + 255) / 256); { const int cap = cur_sm_count() * 16; if (grid > cap) grid = cap; } if (grid < 1) grid = 1;
     refine_count_kernel<<<grid, 256, 0, s>>>(sv, p);
     const int nblocks = (int)((n + SCAN_ITEMS - 1) / SCAN_ITEMS);
     scan_partial_kernel<<<nblocks, SCAN_THREADS, 0, s>>>(p.cnt, n, p.block_sums);
-    scan_sums_kernel<<<1, SCAN_THREADS, 0, s>>>(p.block_sums, nblocks, p.totals);
-    scan_apply_kernel<<<nblocks, SCAN_THREADS, 0, s>>>(p.cnt, n, p.block_sums, p.uniq, p.fill);
+    scan_sums_kernel<<<1, SCAN_THREADS, 0, s>>>(p.block_sums, nblocks, p.totals, p.uoff);
+    scan_apply_kernel<<<nblocks, SCAN_THREADS, 0, s>>>(p.cnt, n, p.block_sums, p.uniq, p.uoff, p.fill);
     refine_fill_kernel<<<grid, 256, 0, s>>>(sv, p);
     return cudaGetLastError() == cudaSuccess ? 5 : -1;
 }
@@ -808,7 +890,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) refine_decrypt_kernel(const __g
             my_hdr = __ldg(reinterpret_cast<const uint4 *>(sv.rec + (size_t)my_id * sv.rec_stride));
             for (int i = 0; i < nkeys; i++) if (ring.version[i] == (int32_t)my_hdr.w) my_slot = i;
             my_verdict = my_slot < 0 ? FSPANN_V_NO_KEY : (int)p.rec_verdict[base + lane];        // KRS:82-88 -> QSI:265-270
-            my_off = p.cnt[my_id]; my_end = p.cnt[my_id + 1];
+            my_off = p.uoff[base + lane]; my_end = p.uoff[base + lane + 1];
         }
         // lane l: the (IV, key)-only part of AES rounds 1-2 of record l (see CtrPre)
         CtrPre my_pre{0, 0, 0, 0, 0};
@@ -924,7 +1006,7 @@ static bool decrypt_layout(int dim, int64_t rec_stride, DecryptLayout &lay) {
 }
 
 int configure_refine_kernels() {   // per-device opt-in to > 48 KB of dynamic shared memory (see opt_in_smem)
-    if (opt_in_smem(gcm_tag_kernel) || opt_in_smem(refine_verify_kernel) || opt_in_smem(refine_decrypt_kernel)) return -1;
+    if (opt_in_smem(gcm_tag_kernel) || opt_in_smem(refine_verify_kernel) || opt_in_smem(refine_decrypt_kernel) || opt_in_smem(refine_group_small_kernel)) return -1;
     return 0;
 }
 

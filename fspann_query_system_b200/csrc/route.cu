@@ -197,7 +197,11 @@ __global__ void __launch_bounds__(RT_THREADS) route_kernel(RoutingView rv, Route
                             old = prev;
                         }
                         my_raw++;
-                        if (len >= 8) s_overflow = 1;    // 9th entry in a bin: Java would treeify
+                        // 9th entry in a bin: Java would treeify.  `len` was counted before pushes that raced with this one, so
+                        // re-count behind the node now that it is linked: the last node pushed into a bin sees the whole chain.
+                        int behind = 0;
+                        for (int32_t c = old; c >= 0 && behind < 8; c = ld(&sc.nnext[c])) behind++;
+                        if (behind >= 8) s_overflow = 1;
                     }
                 }
                 __syncthreads();

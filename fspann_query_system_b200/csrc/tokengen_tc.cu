@@ -162,7 +162,7 @@ __device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t (&v)[8]) {
 // work[0] = number of listed (q, g, j); work[1] = overflow flag; list entries = q << 24 | g << 8 | j (as tokengen_fast_kernel)
 __global__ void __launch_bounds__(TC_THREADS, 1) tokengen_tc_kernel(RoutingView rv, TcPlan pl, int64_t Q, const double *__restrict__ queries,
                                                                     const uint16_t *__restrict__ alpha_tc, uint64_t *__restrict__ codes, float cbound,
-                                                                    int32_t *__restrict__ work, unsigned long long *__restrict__ list, int64_t list_cap) {
+                                                                    int32_t *__restrict__ work, unsigned long long *__restrict__ list, int64_t list_cap, int split) {
     extern __shared__ __align__(128) unsigned char tc_smem[];
     __shared__ __align__(8) uint64_t s_bar_tma, s_bar_mma;
     __shared__ uint32_t s_tmem;
@@ -219,9 +219,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tokengen_tc_kernel(RoutingView 
         tc_commit(&s_bar_mma);                                         // arrives when every MMA above has completed
     };
 
-    if (tid == TC_ISSUER && blockIdx.x < a_tiles) load_b(0);
+    // Few A tiles (a small batch): `split` CTAs share one A tile and take the alpha tiles t0, t0 + split, ... so the batch still spreads over the SMs
+    const int t0 = (int)(blockIdx.x % (unsigned)split), a_lane = (int)(blockIdx.x / (unsigned)split), a_step = (int)(gridDim.x / (unsigned)split);
+    if (tid == TC_ISSUER && a_lane < a_tiles && t0 < pl.n_tiles) load_b(t0);
     int buf = 0;
-    for (int64_t at = blockIdx.x; at < a_tiles; at += gridDim.x) {
+    for (int64_t at = a_lane; at < a_tiles && t0 < pl.n_tiles; at += a_step) {
         const int64_t q0 = at * TC_M;
         // ---- stage the A tile: FP64 -> FP32 -> three BF16 pieces in the canonical layout; row norms; "more than one piece" flag ----
         if (tid < TC_M) nv2[tid] = 0.f;
@@ -258,17 +260,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tokengen_tc_kernel(RoutingView 
         const int row = quarter * 32 + lane;                          // TMEM lane = vector of the tile handled by this thread (epilogue warps)
         // C_tc * (upper bound of ||v||_2; float atomics: any order).  C_tc scales with the number of MMAs accumulated per projection.
         const float nv = warp < TC_EPI_WARPS ? __fmul_ru(__fmul_ru(__fsqrt_ru(nv2[row]), 1.0002f), n_a == 1 ? cbound : 2.0f * cbound) : 0.f;
-        if (tid == TC_ISSUER) issue_mma(0, buf, n_a);
+        if (tid == TC_ISSUER) issue_mma(t0, buf, n_a);
 
-        for (int t = 0; t < pl.n_tiles; t++) {
+        for (int t = t0; t < pl.n_tiles; t += split) {
             const int g_lo = t * G, g_n = min(G, TD - g_lo);
             tc_mbar_wait(&s_bar_mma, mma_phase);                       // accumulator `buf` holds tile t; the B buffer is free again
             mma_phase ^= 1u;
             tc_fence_after();
             if (tid == TC_ISSUER) {
                 // next alpha tile -> B buffer, and (same A tile) its MMAs into the OTHER accumulator buffer, all under this tile's epilogue
-                if (t + 1 < pl.n_tiles) { load_b(t + 1); issue_mma(t + 1, buf ^ 1, n_a); }
-                else if (at + gridDim.x < a_tiles) load_b(0);          // first tile of the next A tile: only the TMA (A is not staged yet)
+                if (t + split < pl.n_tiles) { load_b(t + split); issue_mma(t + split, buf ^ 1, n_a); }
+                else if (at + a_step < a_tiles) load_b(t0);            // first tile of the next A tile: only the TMA (A is not staged yet)
             }
             // ---- epilogue: warp = (TMEM lane quarter, group slot); thread = vector; one (t,d) group of m projections at a time ----
             if (warp < TC_EPI_WARPS) {
@@ -339,9 +341,11 @@ int launch_tokengen_tc(cudaStream_t s, const RoutingView &rv, int64_t Q, const d
     TcPlan pl;
     if (!alpha_tc || !tokengen_tc_plan(rv, pl)) return 0;
     const int64_t a_tiles = (Q + TC_M - 1) / TC_M;
-    const int grid = (int)std::min<int64_t>(a_tiles, sm_count);
+    int split = 1;                                    // CTAs per A tile
+    if (a_tiles < sm_count) split = (int)std::min<int64_t>(pl.n_tiles, sm_count / a_tiles);
+    const int grid = (int)std::min<int64_t>(a_tiles * split, (int64_t)(sm_count / split) * split);
     const float cbound = 6e-5f;                       // one-piece v (24 MMAs per projection); doubled in the kernel for three-piece v (48 MMAs)
-    tokengen_tc_kernel<<<grid, TC_THREADS, pl.smem, s>>>(rv, pl, Q, queries, alpha_tc, codes, cbound, work, list, list_cap);
+    tokengen_tc_kernel<<<grid, TC_THREADS, pl.smem, s>>>(rv, pl, Q, queries, alpha_tc, codes, cbound, work, list, list_cap, split);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

@@ -72,7 +72,10 @@ int64_t fspann_ctx_launch_count(const fspann_ctx *ctx);
  * worklist to n entries (test hook for its overflow fallback), -1 = automatic; "tokengen_exact" = 1 runs the exact FP64 TokenGen
  * kernel alone instead of a pre-filter + exact re-check; "tokengen_mode" = 0 (default) runs the pre-filter's contraction on the tensor
  * cores (tcgen05.mma on BF16-split operands, accumulator in TMEM) when the shape allows it, 2 = on the FP32 FMA pipe (the codes are
- * identical in every mode).  fspann_get_info: "last_tokengen_path" (1 exact, 2 FP32 pre-filter, 3 tensor-core pre-filter),
+ * identical in every mode); "graphs" = 1 (default) lets a search of <= 64 queries replay its first pass (TokenGen .. counters and the
+ * retry decision) as ONE captured CUDA graph from the third call with the same shape and buffers on (the second call captures; any upload,
+ * key, option or buffer change drops the match), 0 = always launch kernel by kernel -- results are identical either way.  fspann_get_info:
+ * "graph_captures" / "graph_replays" (how many such graphs were built / launched on this context), "last_tokengen_path" (1 exact, 2 FP32 pre-filter, 3 tensor-core pre-filter),
  * "last_route_path" (1 fast, 2 general), "route_treeified" (general path only: 1 if a bin of a query's bestScore map reached 9 entries in the
  * last call -- the JDK treeifies such a bin and its iteration order is not modelled), "sm_count", "build_treeified", "tokengen_rechecked" / "tokengen_overflow" (projections
  * the last TokenGen launch had to re-check exactly / whether its list overflowed and the exact kernel recomputed the batch). */

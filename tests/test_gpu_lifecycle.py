@@ -387,3 +387,45 @@ def test_byte_distance_path_and_its_fallback_are_bit_exact(world_factory):
                 assert np.array_equal(out["top_dist"][q, :n].view(np.uint64), ref["top_dist"].view(np.uint64))
     finally:
         ctx.close()
+
+
+def test_small_batch_graph_replay_is_bit_exact_and_follows_state_changes(world_factory):
+    """Batches of <= 64 queries replay their first pass as a captured CUDA graph (abi.cu search_core).  The replay must read the
+    CURRENT queries, and a deletion / key change between calls must invalidate it: every call is checked against the oracle."""
+    w = world_factory(**W3)
+    ctx = w.gpu_context()
+    try:
+        rng = np.random.default_rng(12)
+        for Q in (1, 8, 40):
+            for rep in range(5):
+                w.queries = np.ascontiguousarray(w.base[rng.choice(w.cfg.N, Q, replace=False)] + rng.normal(0, 0.05, (Q, w.cfg.dim)))
+                check_search(ctx, w, w.store)
+        print("graph captures/replays:", ctx.get_info("graph_captures"), ctx.get_info("graph_replays"))
+        assert ctx.get_info("graph_captures") >= 3 and ctx.get_info("graph_replays") >= 6
+        # state changes between identical calls
+        r0 = ctx.get_info("graph_replays")
+        deleted = (rng.random(w.cfg.N) < 0.3).astype(np.uint8)
+        ctx.deleted_set(deleted)
+        check_search(ctx, w, w.store, deleted=deleted)
+        ctx.deleted_set(None)
+        ctx.keys_retire(2)
+        st = O.Store(w.store.dim, w.iv, w.ct, w.key_version, {v: k for v, k in w.store.keys.items() if v != 2})
+        for rep in range(3):
+            check_search(ctx, w, st)
+        ctx.keys_set(2, w.store.keys[2])
+        for rep in range(3):
+            check_search(ctx, w, w.store)
+        assert ctx.get_info("graph_replays") > r0
+        # graphs off: same answers, no replays
+        ctx.set_option("graphs", 0)
+        r1 = ctx.get_info("graph_replays")
+        for rep in range(3):
+            check_search(ctx, w, w.store)
+        assert ctx.get_info("graph_replays") == r1
+        # a batch whose queries force the adaptive retry (far from everything) through the replayed path
+        ctx.set_option("graphs", 1)
+        w.queries = np.ascontiguousarray(w.queries * 50.0 + 1000.0)
+        for rep in range(4):
+            check_search(ctx, w, w.store)
+    finally:
+        ctx.close()
