@@ -146,11 +146,16 @@ int do_route(fspann_ctx *ctx, int64_t Q, const uint64_t *d_codes, int probes, in
     size_t fsmem = 0;
     if (!ctx->opt_route_general && route_fast_eligible(rv, probes, hard_cap, B, fx, fsmem)) {
         if (ctx->opt_route_wl_extra >= 0 && fx.wl_extra > ctx->opt_route_wl_extra) fx.wl_extra = ctx->opt_route_wl_extra & ~7;   // smem size kept
+        if (ctx->opt_route_wl_extra >= 0 && fx.v2_wl_cap > ctx->opt_route_wl_extra) fx.v2_wl_cap = std::max(16, ctx->opt_route_wl_extra & ~15);
+        if (ctx->opt_route_v1) fx.v2_smem = 0;
+        ENSURE(ctx->s_route_ovf, sizeof(int32_t) * ((size_t)Q + 4));
+        fx.ovf_n = (int32_t *)ctx->s_route_ovf.p; fx.ovf_list = fx.ovf_n + 4;
         ENSURE(ctx->s_vis_part, sizeof(int32_t) * (size_t)Q * rv.TD * probes);
         ENSURE(ctx->s_vis_score, (size_t)Q * rv.TD * probes);
         ENSURE(ctx->s_vis_n, (size_t)Q * rv.TD);
         LAUNCHED(launch_route_fast(ctx->stream, rv, p, fx, fsmem, ctx->sm_count, (int32_t *)ctx->s_vis_part.p, (uint8_t *)ctx->s_vis_score.p,
                                    (uint8_t *)ctx->s_vis_n.p));
+        ctx->last_route_v2 = fx.v2_smem != 0;
         ctx->last_route_path = 1;
         return 0;
     }
@@ -261,7 +266,7 @@ void fspann_ctx_destroy(fspann_ctx *ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->d_alpha_f, &ctx->d_alpha_norm, &ctx->d_alpha_tc, &ctx->s_vorder, &ctx->s_voff, &ctx->s_qfinite, &ctx->s_retry_out, &ctx->s_codes_in, &ctx->s_tg_work, &ctx->s_tg_list, &ctx->s_tg_qf, &ctx->s_tg_norm, &ctx->d_alpha, &ctx->d_r, &ctx->d_omega, &ctx->d_keys, &ctx->d_rep, &ctx->d_ids, &ctx->d_deleted, &ctx->d_rec,
                       &ctx->d_keyring, &ctx->d_hpow, &ctx->d_shoup, &ctx->s_rec_verdict, &ctx->s_qf32, &ctx->s_qu8, &ctx->s_f32_exact, &ctx->d_te0, &ctx->d_touched, &ctx->s_queries, &ctx->s_codes, &ctx->s_cand_ids,
-                      &ctx->s_cand_sc, &ctx->s_ncand, &ctx->s_raw, &ctx->s_uniq_cnt, &ctx->s_route_scratch, &ctx->s_overflow, &ctx->s_cnt,
+                      &ctx->s_cand_sc, &ctx->s_ncand, &ctx->s_raw, &ctx->s_uniq_cnt, &ctx->s_route_scratch, &ctx->s_overflow, &ctx->s_route_ovf, &ctx->s_cnt,
                       &ctx->s_flag, &ctx->s_fill, &ctx->s_uniq, &ctx->s_uoff, &ctx->s_pairs, &ctx->s_bsums, &ctx->s_totals, &ctx->s_dist, &ctx->s_verdict,
                       &ctx->s_topk_ids, &ctx->s_topk_dist, &ctx->s_topk_rank, &ctx->s_nret, &ctx->s_ndec, &ctx->s_counters, &ctx->s_stage_a, &ctx->s_stage_b,
                       &ctx->s_stage_c, &ctx->s_vis_part, &ctx->s_vis_score, &ctx->s_vis_n, &ctx->r_rows, &ctx->r_queries, &ctx->r_codes, &ctx->r_topk_ids, &ctx->r_topk_dist, &ctx->r_nret,
@@ -294,6 +299,7 @@ int fspann_set_option(fspann_ctx *ctx, const char *name, int64_t value) {
     if (!strcmp(name, "graphs")) { ctx->opt_graphs = value != 0; return FSPANN_OK; }
     if (!strcmp(name, "route_general")) { ctx->opt_route_general = value != 0; return FSPANN_OK; }
     if (!strcmp(name, "route_wl_extra")) { ctx->opt_route_wl_extra = (int)value; return FSPANN_OK; }
+    if (!strcmp(name, "route_v1")) { ctx->opt_route_v1 = value != 0; return FSPANN_OK; }
     if (!strcmp(name, "tokengen_exact")) { ctx->opt_tokengen_exact = value != 0; return FSPANN_OK; }
     if (!strcmp(name, "tokengen_mode")) { ctx->opt_tokengen_mode = (int)value; return FSPANN_OK; }
     if (!strcmp(name, "tokengen_list_cap")) { ctx->opt_tg_list_cap = value; return FSPANN_OK; }
@@ -303,6 +309,14 @@ int64_t fspann_get_info(fspann_ctx *ctx, const char *name) {
     if (!ctx || !name) return -1;
     if (!strcmp(name, "last_route_path")) return ctx->last_route_path;
     if (!strcmp(name, "last_tokengen_path")) return ctx->last_tokengen_path;
+    if (!strcmp(name, "route_overflowed")) {   // fast path, two-CTA kernel: queries of the last call that went to the one-CTA kernel
+        int32_t f = 0;
+        if (ctx->last_route_path != 1 || !ctx->last_route_v2 || !ctx->s_route_ovf.p) return 0;
+        if (cudaSetDevice(ctx->device) != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess ||
+            cudaMemcpy(&f, ctx->s_route_ovf.p, sizeof f, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+        return f;
+    }
+    if (!strcmp(name, "last_route_v2")) return ctx->last_route_v2;
     if (!strcmp(name, "route_treeified")) {   // general Route kernel: did a bestScore bin of the last call reach 9 entries (the JDK would treeify it)?
         int32_t f = 0;
         if (ctx->last_route_path != 2 || !ctx->s_overflow.p) return 0;

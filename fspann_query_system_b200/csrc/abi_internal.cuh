@@ -44,10 +44,12 @@ struct fspann_ctx {
     // scratch (grow only)
     DevBuf s_vis_part, s_vis_score, s_vis_n;
     int opt_route_general = 0;   // force the general (sequential, cap-exact) Route kernel
+    int opt_route_v1 = 0;        // use the one-CTA-per-SM fast Route kernel only (A/B switch)
+    int last_route_v2 = 0;
     int opt_route_wl_extra = -1; // test hook: clamp the fast path's dedicated worklist (forces the no-worklist fallback when exceeded)
     int last_route_path = 0;     // 1 = shared-memory fast path, 2 = general path
     bool last_queries_finite = true;
-    DevBuf s_queries, s_codes, s_cand_ids, s_cand_sc, s_ncand, s_raw, s_uniq_cnt, s_route_scratch, s_overflow;
+    DevBuf s_queries, s_codes, s_cand_ids, s_cand_sc, s_ncand, s_raw, s_uniq_cnt, s_route_scratch, s_overflow, s_route_ovf;
     DevBuf s_rec_verdict, s_qf32, s_qu8, s_f32_exact, s_vorder, s_voff, s_qfinite, s_retry_out, s_codes_in;
     DevKeyRing ring_host{};
     int32_t *want_rank = nullptr;

@@ -78,6 +78,11 @@ struct RouteFastExtra {
     int tbl;      // open-addressing slots (power of two)
     int sort_n;   // bitonic sort width (power of two >= B + slack)
     int wl_extra; // dedicated worklist entries (the worklist continues over skey / sid)
+    // route_fast2_kernel (two CTAs per SM): 0 = not eligible
+    size_t v2_smem;
+    int v2_region, v2_cls_cap, v2_wl_cap;
+    int32_t *ovf_n, *ovf_list;            // queries route_fast2_kernel hands to route_fast_kernel
+    const int32_t *qlist, *qlist_n;       // route_fast_kernel: serve these queries only (nullptr = all)
 };
 
 struct RefineParams {

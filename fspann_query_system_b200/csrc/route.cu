@@ -480,8 +480,7 @@ __device__ __forceinline__ uint32_t bitonic_sort32(uint32_t a, int i, uint32_t *
                 b = __shfl_xor_sync(0xffffffffu, a, j);
             }
             const bool lower = (i & j) == 0;                // this thread keeps the smaller of the pair when ascending
-            const bool take_b = (lower == asc) ? (b < a) : (b > a);
-            if (take_b) a = b;
+            a = (lower == asc) ? min(a, b) : max(a, b);     // (a select between VIMNMX results; the if/else form compiles to branches)
         }
     }
     return a;
@@ -521,7 +520,9 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) route_fast_kernel(RoutingView r
     const int64_t n_ids = rv.n_ids;
     const int fshift = 32 - (31 - __clz(tbl * 4 - 1) + 1);                             // buckets per filter array = tbl * 4 (a power of two; two arrays share the table region)
 
-    for (int64_t q = blockIdx.x; q < p.Q; q += gridDim.x) {
+    const int64_t n_q = x.qlist ? (int64_t)*x.qlist_n : p.Q;          // all queries, or the overflow list of route_fast2_kernel
+    for (int64_t qi = blockIdx.x; qi < n_q; qi += gridDim.x) {
+        const int64_t q = x.qlist ? (int64_t)x.qlist[qi] : qi;
         __syncthreads();
         // ---- 1. stage visits, reset the duplicate filter (it lives in the table region: 8*tbl two-bit buckets) ----
         for (int v = tid; v < nvis; v += RQ_THREADS) {
@@ -571,7 +572,6 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) route_fast_kernel(RoutingView r
                 if (e < n_raw) {
                     int32_t id4[4] = {idv[u].x, idv[u].y, idv[u].z, idv[u].w};
                     if (rv.deleted) {
-#pragma unroll
                         int dead = 0;
 #pragma unroll
                         for (int j = 0; j < 4; j++) if (id4[j] >= 0 && id4[j] < rv.n_deleted && rv.deleted[id4[j]]) { id4[j] = -1; dead++; }     // PIS:739
@@ -894,6 +894,442 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) route_fast_kernel(RoutingView r
     }
 }
 
+// =====================================================================================================================
+// Fast path, second generation (round 2): TWO 512-thread CTAs per SM instead of one 1024-thread CTA, so one query's barriers and
+// shared-memory latencies are covered by the other query's work.  The per-query state is cut from ~225 KB to <= 113 KB:
+//   * the gathered ids are NOT kept in shared memory: the classify pass and the selection scan re-read them from L2 (the partition
+//     rows were just read by the filter pass; 82 KB per query);
+//   * everything the exact path needs (id, position, chain link, minimum score) is indexed by WORKLIST slot, not by position, and the
+//     worklist has a fixed capacity (~22 % of the positions at C2; a query that exceeds it, a cut class larger than its list or a sort
+//     key wider than 32 bits is appended to an overflow list and served by route_fast_kernel in a second launch);
+//   * the bitonic sort holds two keys per thread and double-buffers its shared-memory exchanges (one barrier per stage).
+// Same results as route_fast_kernel bit for bit (same filters, same exact path, same selection keys).
+// =====================================================================================================================
+constexpr int R2_THREADS = 512;
+constexpr int R2_SELBYTES = 7168;          // sel_id int32[1024] + sel_pos uint16[1024] + sel_sc uint8[1024]
+
+struct Route2Layout { int region, cls_cap, wl_cap; size_t smem; };
+
+static bool route2_layout(int TD, int probes, int n_raw, int tbl, Route2Layout &L) {
+    const int nvis = TD * probes, nvis16 = (nvis + 15) / 16 * 16;
+    const int nbm = ((n_raw + 31) / 32 + 3) / 4 * 4;
+    L.region = std::max(2 * tbl, 28672);
+    L.cls_cap = std::min(n_raw, ((L.region - R2_SELBYTES) / 4) & ~7);
+    const size_t fixed = (size_t)L.region + sizeof(int64_t) * nvis + 2 * (size_t)nvis16 + 2 * sizeof(uint16_t) * (size_t)nvis16 + sizeof(uint32_t) * (size_t)nbm + 64;
+    const size_t limit = 114432;                                       // 2 x (dynamic + 1.2 KB static + 1 KB reserve) <= 228 KB per SM
+    if (fixed + 9 * 1024 > limit) return false;
+    int64_t cap = (int64_t)(limit - fixed) / 9;
+    cap = std::min<int64_t>(cap, n_raw);
+    int slots_max = 1; while (slots_max * 2 <= L.region / 2) slots_max <<= 1;   // exact table: uint16 slots inside the region, a power of two
+    cap = std::min<int64_t>(cap, slots_max / 4 * 3);                   // load factor <= 0.75; slots < 32768 and worklist slots < 32768 fit the 15-bit links
+    cap &= ~(int64_t)15;
+    if (cap < 16) return false;
+    L.wl_cap = (int)cap;
+    L.smem = fixed + 9 * (size_t)cap;
+    return true;
+}
+
+// Bitonic sort of TWO 32-bit keys per thread (elements tid and tid + R2_THREADS); strides < 32 by shuffles, larger ones through the
+// double buffer `buf` (2 x 2*R2_THREADS words; one barrier per stage), stride R2_THREADS inside the thread.  N > 0: unrolled network.
+template <int N>
+__device__ __forceinline__ void bitonic_sort32x2(uint32_t &a0, uint32_t &a1, int tid, uint32_t *buf, int n_rt = 0) {
+    const int n = N > 0 ? N : n_rt;
+    int phase = 0;
+#pragma unroll
+    for (int k = 2; k <= n; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j == R2_THREADS) {                                   // k == 2 * R2_THREADS: ascending everywhere
+                if (a1 < a0) { const uint32_t t = a0; a0 = a1; a1 = t; }
+                continue;
+            }
+            uint32_t b0, b1;
+            if (j >= 32) {
+                uint32_t *bb = buf + phase * (2 * R2_THREADS);
+                bb[tid] = a0; bb[tid + R2_THREADS] = a1;
+                __syncthreads();
+                b0 = bb[tid ^ j]; b1 = bb[(tid ^ j) + R2_THREADS];
+                phase ^= 1;
+            } else {
+                b0 = __shfl_xor_sync(0xffffffffu, a0, j); b1 = __shfl_xor_sync(0xffffffffu, a1, j);
+            }
+            const bool lower = (tid & j) == 0;
+            const bool asc0 = (tid & k) == 0, asc1 = ((tid + R2_THREADS) & k) == 0;
+            a0 = (lower == asc0) ? min(a0, b0) : max(a0, b0);
+            a1 = (lower == asc1) ? min(a1, b1) : max(a1, b1);
+        }
+    }
+}
+
+template <bool HAS_DEL>
+__global__ void __launch_bounds__(R2_THREADS, 2) route_fast2_kernel(RoutingView rv, RouteParams p, RouteFastExtra x) {
+    extern __shared__ __align__(16) unsigned char rq_smem[];
+    const int TD = rv.TD, probes = p.probes, n_raw = x.n_raw, tbl = x.tbl, sort_n = x.sort_n, nvis = TD * probes;
+    const int nvis16 = (nvis + 15) / 16 * 16;
+    const int region = x.v2_region, cls_cap = x.v2_cls_cap, wl_cap = x.v2_wl_cap;
+    uint32_t *F = reinterpret_cast<uint32_t *>(rq_smem);                       // phase 1-3: duplicate filters (2 x 4*tbl two-bit buckets)
+    uint32_t *table_w = F;                                                     // phase 4: exact table of worklist slots
+    uint16_t *table = reinterpret_cast<uint16_t *>(rq_smem);
+    uint16_t *cls_pos = table, *cls_hash = table + cls_cap;                    // phase 6-7: the cut class (position, low 16 bits of the Java hash)
+    unsigned char *selb = rq_smem + region - R2_SELBYTES;                      // phase 6-8: the selected entries
+    int32_t *sel_id = reinterpret_cast<int32_t *>(selb);
+    uint16_t *sel_pos = reinterpret_cast<uint16_t *>(selb + 4096);
+    uint8_t *sel_sc = selb + 6144;
+    const int nw = (n_raw + 31) >> 5, nwp = (nw + 3) & ~3;
+    uint32_t *bm = reinterpret_cast<uint32_t *>(rq_smem);                       // phase 8 (the class list is dead): position bitmap, prefix, sort buffers
+    uint16_t *pref = reinterpret_cast<uint16_t *>(bm + nwp);
+    uint32_t *key32 = reinterpret_cast<uint32_t *>(rq_smem + (((size_t)6 * nwp + 15) & ~(size_t)15));
+    int32_t *sid = reinterpret_cast<int32_t *>(key32 + 4 * R2_THREADS);
+    int64_t *vbase_s = reinterpret_cast<int64_t *>(rq_smem + region);
+    uint8_t *vs_s = reinterpret_cast<uint8_t *>(vbase_s + nvis);
+    uint8_t *vlen_s = vs_s + nvis16;
+    uint16_t *lowvis_s = reinterpret_cast<uint16_t *>(vlen_s + nvis16);
+    uint16_t *inv_cnt = lowvis_s + nvis16;
+    uint32_t *inv_bm = reinterpret_cast<uint32_t *>(inv_cnt + nvis16);
+    const int nbm = ((n_raw + 31) / 32 + 3) / 4 * 4;
+    int32_t *wl_id = reinterpret_cast<int32_t *>(inv_bm + nbm);
+    uint16_t *wl_pos = reinterpret_cast<uint16_t *>(wl_id + wl_cap);
+    uint16_t *wl_next = wl_pos + wl_cap;
+    uint8_t *wl_best = reinterpret_cast<uint8_t *>(wl_next + wl_cap);
+    __shared__ int32_t s_hist[256];
+    __shared__ int32_t s_raw, s_uniq, s_m, s_ncls, s_nwl, s_nlow, s_pick[3], s_wsum[32];
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int64_t n_ids = rv.n_ids;
+    const int fshift = 32 - (31 - __clz(tbl * 4 - 1) + 1);
+    const uint32_t f2_off = (uint32_t)tbl >> 2;
+    const bool vec_ok = (n_ids & 3) == 0;
+    const int n4 = n_raw >> 2;
+    const uint8_t *__restrict__ deleted = rv.deleted;
+
+    // ids of the 4 consecutive positions starting at e (-1: beyond the partition row, -2: a deleted id, PIS:739)
+    auto gather4 = [&](int e, int32_t (&id4)[4]) {
+        const int v = e >> 6, pos = e & 63, len = (int)vlen_s[v];
+        const int32_t *src = rv.ids + vbase_s[v] + pos;
+        if (vec_ok && pos + 4 <= len) {
+            const int4 t = __ldg(reinterpret_cast<const int4 *>(src));
+            id4[0] = t.x; id4[1] = t.y; id4[2] = t.z; id4[3] = t.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++) id4[j] = pos + j < len ? __ldg(src + j) : -1;
+        }
+        if (HAS_DEL) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) if (id4[j] >= 0 && id4[j] < rv.n_deleted && deleted[id4[j]]) id4[j] = -2;
+        }
+    };
+    auto filter_set = [&](int32_t id) {
+        const uint32_t h1 = ((uint32_t)id * 0x9E3779B1u) >> fshift, h2 = ((uint32_t)id * 0x85EBCA6Bu) >> fshift;
+        const uint32_t s1 = (h1 & 15u) * 2u, s2 = (h2 & 15u) * 2u;
+        const uint32_t o1 = atomicOr(&F[h1 >> 4], 1u << s1);
+        if ((o1 >> s1) & 1u) atomicOr(&F[h1 >> 4], 2u << s1);
+        const uint32_t o2 = atomicOr(&F[f2_off + (h2 >> 4)], 1u << s2);
+        if ((o2 >> s2) & 1u) atomicOr(&F[f2_off + (h2 >> 4)], 2u << s2);
+    };
+    auto filter_twice = [&](int32_t id) -> bool {                        // taken twice in BOTH filters: not provably a single occurrence
+        const uint32_t h1 = ((uint32_t)id * 0x9E3779B1u) >> fshift;
+        if (!((F[h1 >> 4] >> ((h1 & 15u) * 2u)) & 2u)) return false;
+        const uint32_t h2 = ((uint32_t)id * 0x85EBCA6Bu) >> fshift;
+        return ((F[f2_off + (h2 >> 4)] >> ((h2 & 15u) * 2u)) & 2u) != 0;
+    };
+
+    for (int64_t q = blockIdx.x; q < p.Q; q += gridDim.x) {
+        __syncthreads();
+        // ---- 1. stage visits, reset the filters ----
+        for (int v = tid; v < nvis; v += R2_THREADS) {
+            const int g = v / probes, j = v - g * probes;
+            const int64_t vi = (q * TD + g) * probes + j;
+            const bool valid = j < (int)x.vis_n[q * TD + g];
+            const int64_t row = valid ? (int64_t)x.vis_part[vi] * kBlock : 0;
+            vbase_s[v] = (int64_t)g * n_ids + row;
+            vlen_s[v] = valid ? (uint8_t)min((int64_t)kBlock, n_ids - row) : 0;
+            vs_s[v] = valid ? x.vis_score[vi] : 255;
+        }
+        for (int i = tid; i < tbl / 8; i += R2_THREADS) reinterpret_cast<uint4 *>(F)[i] = make_uint4(0, 0, 0, 0);
+        for (int i = tid; i < nbm; i += R2_THREADS) inv_bm[i] = 0u;
+        for (int i = tid; i < nvis16 / 2; i += R2_THREADS) reinterpret_cast<uint32_t *>(inv_cnt)[i] = 0u;
+        if (tid < 256) s_hist[tid] = 0;
+        if (tid == 0) { s_raw = 0; s_uniq = 0; s_m = 0; s_ncls = 0; s_nwl = 0; s_nlow = 0; }
+        __syncthreads();
+        // ---- 2. gather ids (16-byte slices of the 256-byte partition rows, two in flight) and set the two 2-bit filters ----
+        for (int q0 = tid; q0 < n4; q0 += 2 * R2_THREADS) {
+            int32_t idv[2][4];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int e = (q0 + u * R2_THREADS) << 2;
+                if (e < n_raw) gather4(e, idv[u]);
+                else { idv[u][0] = idv[u][1] = idv[u][2] = idv[u][3] = -1; }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                if ((idv[u][0] | idv[u][1] | idv[u][2] | idv[u][3]) >= 0) {      // the common case: four live ids, no per-id test
+#pragma unroll
+                    for (int j = 0; j < 4; j++) filter_set(idv[u][j]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) if (idv[u][j] >= 0) filter_set(idv[u][j]);
+                }
+            }
+        }
+        __syncthreads();
+        // ---- 3. classify (ids re-read from L2): single, or involved -> bitmap + per-visit counter + worklist (slot: id, position) ----
+        int my_raw = 0, my_uniq = 0;
+        bool fits = true;
+        for (int q0 = tid; q0 < n4; q0 += 2 * R2_THREADS) {
+            int32_t idv[2][4];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int e = (q0 + u * R2_THREADS) << 2;
+                if (e < n_raw) gather4(e, idv[u]);
+                else { idv[u][0] = idv[u][1] = idv[u][2] = idv[u][3] = -1; }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int e = (q0 + u * R2_THREADS) << 2;
+                uint32_t invmask = 0; int dead = 0;
+                if ((idv[u][0] | idv[u][1] | idv[u][2] | idv[u][3]) >= 0) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) invmask |= filter_twice(idv[u][j]) ? 1u << j : 0u;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        if (idv[u][j] >= 0) invmask |= filter_twice(idv[u][j]) ? 1u << j : 0u;
+                        else if (HAS_DEL && idv[u][j] == -2) dead++;
+                    }
+                }
+                if (invmask | (uint32_t)dead) {
+                    const int c = __popc(invmask);
+                    atomicAdd(reinterpret_cast<unsigned int *>(inv_cnt) + (e >> 7), (unsigned)(c + dead) << (((e >> 6) & 1) * 16));
+                    if (c) {
+                        int base = atomicAdd(&s_nwl, c);
+                        atomicOr(&inv_bm[e >> 5], invmask << (e & 31));
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            if ((invmask >> j) & 1u) {
+                                if (base < wl_cap) { wl_id[base] = idv[u][j]; wl_pos[base] = (uint16_t)(e + j); } else fits = false;
+                                base++;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        fits = __syncthreads_and(fits ? 1 : 0) != 0;
+        const int n_inv = s_nwl;
+        if (fits && tid < nvis) {                                          // the singles of visit `tid` share its score
+            const int singles = (int)vlen_s[tid] - (int)inv_cnt[tid];
+            if (singles > 0) { atomicAdd(&s_hist[vs_s[tid]], singles); my_raw += singles; my_uniq += singles; }
+        }
+        // ---- 4. exact path over the worklist (see route_fast_kernel; links and table entries are worklist slots) ----
+        if (fits && n_inv > 0) {
+            int tslots = 2 * n_inv <= 1024 ? 1024 : 1 << (32 - __clz(2 * n_inv - 1));
+            if (tslots * 2 > region) tslots = region / 2;                  // region is a power of two or 28672 (-> 8192 slots would not fit: clamp to 2^k below)
+            tslots = 1 << (31 - __clz(tslots));
+            const uint32_t smask = (uint32_t)tslots - 1u;
+            const int sshift = 32 - (31 - __clz(tslots));
+            for (int i = tid; i < tslots / 2; i += R2_THREADS) table_w[i] = 0xffffffffu;
+            __syncthreads();
+            for (int i = tid; i < n_inv; i += R2_THREADS) {
+                const int32_t id = wl_id[i];
+                const uint32_t h = (uint32_t)id * 0x9E3779B1u;
+                uint32_t slot = h >> sshift;
+                const uint32_t step = ((h >> 7) | 1u) & smask;
+                for (;;) {
+                    uint32_t cur = *reinterpret_cast<volatile uint16_t *>(&table[slot]);
+                    if (cur == RQ_EMPTY) {
+                        wl_next[i] = (uint16_t)(0x8000u | slot);
+                        cur = cas16(table_w, slot, RQ_EMPTY, (uint32_t)i);
+                        if (cur == RQ_EMPTY) break;
+                    }
+                    if (wl_id[cur] == id) {
+                        for (;;) {
+                            wl_next[i] = (uint16_t)cur;
+                            const uint32_t prev = cas16(table_w, slot, cur, (uint32_t)i);
+                            if (prev == cur) break;
+                            cur = prev;
+                        }
+                        break;
+                    }
+                    slot = (slot + step) & smask;
+                }
+            }
+            __syncthreads();
+            for (int i = tid; i < n_inv; i += R2_THREADS) {
+                const uint32_t e = wl_pos[i];
+                const uint32_t sc = vs_s[e >> 6];
+                uint32_t lk = wl_next[i];
+                while (!(lk & 0x8000u)) lk = wl_next[lk];
+                const uint32_t head = table[lk & 0x7fffu];
+                uint32_t first = 0xffffu, best = 255; bool low = true;
+                for (uint32_t y = head;;) {
+                    const uint32_t ey = wl_pos[y], sy = vs_s[ey >> 6];
+                    first = min(first, ey); best = min(best, sy);
+                    if (ey < e && sy <= sc) low = false;
+                    const uint32_t ny = wl_next[y];
+                    if (ny & 0x8000u) break;
+                    y = ny;
+                }
+                my_raw += low;
+                const bool is_rep = first == e;
+                if (is_rep) { atomicAdd(&s_hist[best], 1); my_uniq++; }
+                wl_best[i] = (uint8_t)(is_rep ? (RQ_DUP | best) : 255u);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) { my_raw += __shfl_xor_sync(0xffffffffu, my_raw, o); my_uniq += __shfl_xor_sync(0xffffffffu, my_uniq, o); }
+        if (lane == 0) { atomicAdd(&s_raw, my_raw); atomicAdd(&s_uniq, my_uniq); }
+        __syncthreads();
+        const int n_unique = s_uniq;
+        const int want = min(p.B, n_unique);
+        uint32_t capF = (uint32_t)p.cap0;
+        while ((double)n_unique > 0.75 * (double)capF && capF < (1u << 30)) capF <<= 1;
+        const int cb = capF <= 1u ? 0 : 32 - __clz(capF - 1u);
+        // ---- 5. score histogram -> cut class ----
+        if (tid < 32) warp_pick_digit(s_hist, 256, 0, want, lane, s_pick);
+        __syncthreads();
+        const uint32_t sstar = (uint32_t)s_pick[0];
+        int cum = s_pick[1];
+        const int cls_n_expected = s_pick[2];
+        const bool need_levels = cum + cls_n_expected != want;
+        const int sb = 32 - __clz(sstar);
+        const int rb = sort_n <= 1 ? 0 : 32 - __clz(sort_n - 1);
+        // what this kernel does not hold: more involved positions than worklist slots, a cut class beyond its list, keys wider than 32 bits
+        if (!fits || (need_levels && cls_n_expected > cls_cap) || sb + cb + rb > 32 || capF > 65536u) {
+            if (tid == 0) x.ovf_list[atomicAdd(x.ovf_n, 1)] = (int32_t)q;
+            continue;
+        }
+        // ---- 6. scan the positions that can hold a score <= s*: the visits with score <= s* (singles; ids re-read) and the worklist ----
+        {
+            bool low = false;
+            if (tid < nvis) low = vlen_s[tid] != 0 && (uint32_t)vs_s[tid] <= sstar;
+            const int slot = list_slot(&s_nlow, low, lane);
+            if (low) lowvis_s[slot] = (uint16_t)tid;
+        }
+        __syncthreads();
+        {
+            const int n_low = s_nlow * kBlock;
+            for (int i0 = 0; i0 < n_low + n_inv; i0 += R2_THREADS) {
+                const int i = i0 + tid;
+                int e = 0; uint32_t sc = 255; int32_t id = -1;
+                if (i < n_low) {
+                    const int v = (int)lowvis_s[i >> 6], pos = i & 63;
+                    e = v * kBlock + pos;
+                    if (pos < (int)vlen_s[v] && !((inv_bm[e >> 5] >> (e & 31)) & 1u)) {
+                        id = __ldg(rv.ids + vbase_s[v] + pos);
+                        if (!(HAS_DEL && id >= 0 && id < rv.n_deleted && deleted[id])) sc = (uint32_t)vs_s[v];
+                    }
+                } else if (i < n_low + n_inv) {
+                    const int w = i - n_low;
+                    const uint32_t b = wl_best[w];
+                    if (b >= RQ_DUP && b < 255u) { sc = b & 0x7fu; e = (int)wl_pos[w]; id = wl_id[w]; }
+                }
+                const bool below = sc < sstar || (sc == sstar && !need_levels && sc != 255u);
+                const bool incls = need_levels && sc == sstar && sc != 255u;
+                const int a = list_slot(&s_m, below, lane);
+                if (below && a < sort_n) { sel_id[a] = id; sel_pos[a] = (uint16_t)e; sel_sc[a] = (uint8_t)sc; }
+                const int c = list_slot(&s_ncls, incls, lane);
+                if (incls) { cls_pos[c] = (uint16_t)e; cls_hash[c] = (uint16_t)(java_hash_decimal(id) & 0xffffu); }
+            }
+        }
+        __syncthreads();
+        // ---- 7. exact select inside the cut class on key2 = (Java bucket << 16) | first position, 8 bits per level ----
+        if (need_levels) {
+            const int bits2 = cb + 16;
+            uint32_t prefix = 0; int used = 0;
+            const int ncls = s_ncls;
+            for (;;) {
+                const int take = min(8, bits2 - used);
+                const int shift = bits2 - used - take;
+                if (tid < 256) s_hist[tid] = 0;
+                __syncthreads();
+                for (int i0 = 0; i0 < ncls; i0 += R2_THREADS) {
+                    const int i = i0 + tid;
+                    bool in = false; int bin = 0;
+                    if (i < ncls) {
+                        const uint32_t key2 = (((uint32_t)cls_hash[i] & (capF - 1u)) << 16) | (uint32_t)cls_pos[i];
+                        in = used == 0 || (key2 >> (shift + take)) == prefix;
+                        bin = (int)((key2 >> shift) & ((1u << take) - 1u));
+                    }
+                    hist_add(s_hist, in, bin, lane);
+                }
+                __syncthreads();
+                if (tid < 32) warp_pick_digit(s_hist, 1 << take, cum, want, lane, s_pick);
+                __syncthreads();
+                prefix = (prefix << take) | (uint32_t)s_pick[0];
+                used += take;
+                cum = s_pick[1];
+                const int bin = s_pick[2];
+                __syncthreads();
+                if (cum + bin == want || used >= bits2) break;
+            }
+            const int sel_shift = bits2 - used;
+            for (int i0 = 0; i0 < ncls; i0 += R2_THREADS) {
+                const int i = i0 + tid;
+                bool take_it = false; uint32_t e = 0;
+                if (i < ncls) {
+                    e = cls_pos[i];
+                    const uint32_t key2 = (((uint32_t)cls_hash[i] & (capF - 1u)) << 16) | e;
+                    take_it = (key2 >> sel_shift) <= prefix;
+                }
+                const int a = list_slot(&s_m, take_it, lane);
+                if (take_it && a < sort_n) {
+                    sel_id[a] = __ldg(rv.ids + vbase_s[e >> 6] + (e & 63));    // the id at a position (single or first occurrence alike)
+                    sel_pos[a] = (uint16_t)e; sel_sc[a] = (uint8_t)sstar;
+                }
+            }
+            __syncthreads();
+        }
+        // ---- 8. 32-bit keys (score | Java bucket | rank of the position among the selected), two per thread, key-only bitonic sort ----
+        const int m = min(s_m, sort_n);
+        int32_t *out_id = p.cand_ids + (size_t)q * p.B, *out_sc = p.cand_scores + (size_t)q * p.B;
+        int my_e[2]; int32_t my_id[2]; uint32_t my_sc[2];
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int i = tid + u * R2_THREADS;
+            my_e[u] = i < m ? (int)sel_pos[i] : -1;
+            my_id[u] = i < m ? sel_id[i] : -1;
+            my_sc[u] = i < m ? (uint32_t)sel_sc[i] : 0u;
+        }
+        __syncthreads();                                                   // the class list is dead; sel_* are in registers
+        for (int i = tid; i < nwp; i += R2_THREADS) bm[i] = 0u;
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < 2; u++) if (my_e[u] >= 0) atomicOr(&bm[my_e[u] >> 5], 1u << (my_e[u] & 31));
+        __syncthreads();
+        for (int w0 = 0; w0 < nwp; w0 += 2 * R2_THREADS) {                 // one pass (nw <= 1000)
+            const int w = w0 + 2 * tid;
+            const int c0 = w < nwp ? __popc(bm[w]) : 0, c1 = w + 1 < nwp ? __popc(bm[w + 1]) : 0;
+            int tot;
+            const int ex = warp_excl_scan(c0 + c1, lane, tot);
+            if (lane == 31) s_wsum[tid >> 5] = ex + c0 + c1;
+            __syncthreads();
+            if (tid < 32) { int t2; const int v = tid < R2_THREADS / 32 ? s_wsum[tid] : 0; const int e2 = warp_excl_scan(v, lane, t2); s_wsum[tid] = e2; }
+            __syncthreads();
+            if (w < nwp) { pref[w] = (uint16_t)(s_wsum[tid >> 5] + ex); pref[w + 1] = (uint16_t)(s_wsum[tid >> 5] + ex + c0); }
+        }
+        __syncthreads();
+        uint32_t a[2] = {0xffffffffu, 0xffffffffu};
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            if (my_e[u] >= 0) {
+                const uint32_t rank = (uint32_t)pref[my_e[u] >> 5] + (uint32_t)__popc(bm[my_e[u] >> 5] & ((1u << (my_e[u] & 31)) - 1u));
+                const uint32_t bucket = java_hash_decimal(my_id[u]) & (capF - 1u);
+                a[u] = (my_sc[u] << (cb + rb)) | (bucket << rb) | rank;
+                sid[rank] = my_id[u];
+            }
+        }
+        if (sort_n == 2 * R2_THREADS) bitonic_sort32x2<2 * R2_THREADS>(a[0], a[1], tid, key32);
+        else bitonic_sort32x2<0>(a[0], a[1], tid, key32, sort_n);
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int i = tid + u * R2_THREADS;
+            if (i < want) { out_id[i] = sid[a[u] & ((1u << rb) - 1u)]; out_sc[i] = (int32_t)(a[u] >> (cb + rb)); }
+        }
+        if (tid == 0) { p.n_cand[q] = want; p.unique[q] = n_unique; p.raw_seen[q] = s_raw; }
+    }
+}
+
 bool route_fast_eligible(const RoutingView &rv, int probes, int64_t hard_cap, int B, RouteFastExtra &x, size_t &smem) {
     if (probes < 1) return false;
     const int64_t n_raw = (int64_t)rv.TD * probes * kBlock;
@@ -915,11 +1351,18 @@ bool route_fast_eligible(const RoutingView &rv, int probes, int64_t hard_cap, in
     wl_extra &= ~(int64_t)7;                                 // keeps skey 16-byte aligned
     x.n_raw = (int)n_raw; x.tbl = tbl; x.sort_n = sort_n; x.wl_extra = (int)wl_extra;
     smem = route_fast_smem(rv.TD, probes, (int)n_raw, tbl, sort_n, (int)wl_extra);
+    // second-generation kernel (two CTAs per SM): B <= 1024 and a worklist of at least 1/8 of the positions
+    Route2Layout L{};
+    x.v2_smem = 0;
+    if (sort_n <= 2 * R2_THREADS && (int64_t)rv.TD * probes <= R2_THREADS && route2_layout(rv.TD, probes, (int)n_raw, tbl, L) &&
+        (L.wl_cap >= n_raw / 8 || L.wl_cap >= n_raw)) {
+        x.v2_region = L.region; x.v2_cls_cap = L.cls_cap; x.v2_wl_cap = L.wl_cap; x.v2_smem = L.smem;
+    }
     return true;
 }
 
 int configure_route_kernels() {   // per-device opt-in, see configure_tokengen_kernels
-    return opt_in_smem(route_fast_kernel) || opt_in_smem(route_kernel) ? -1 : 0;
+    return opt_in_smem(route_fast_kernel) || opt_in_smem(route_fast2_kernel<false>) || opt_in_smem(route_fast2_kernel<true>) || opt_in_smem(route_kernel) ? -1 : 0;
 }
 
 int launch_route_fast(cudaStream_t s, const RoutingView &rv, const RouteParams &p, RouteFastExtra x, size_t smem, int sm_count,
@@ -928,7 +1371,18 @@ int launch_route_fast(cudaStream_t s, const RoutingView &rv, const RouteParams &
     const int64_t nthreads = p.Q * rv.TD;
     route_probe_kernel<<<(unsigned)((nthreads + 127) / 128), 128, 0, s>>>(rv, p.Q, p.codes, p.probes, vis_part, vis_score, vis_n);
     x.vis_part = vis_part; x.vis_score = vis_score; x.vis_n = vis_n;
-    int grid = (int)std::min<int64_t>(p.Q, sm_count);
+    const int grid = (int)std::min<int64_t>(p.Q, sm_count);
+    if (x.v2_smem && x.ovf_n) {
+        // two CTAs per SM; the queries it cannot hold (worklist / class list / key width) come back in ovf_list for the one-CTA kernel
+        if (cudaMemsetAsync(x.ovf_n, 0, sizeof(int32_t), s) != cudaSuccess) return -1;
+        const int grid2 = (int)std::min<int64_t>(p.Q, 2 * (int64_t)sm_count);
+        if (rv.deleted) route_fast2_kernel<true><<<grid2, R2_THREADS, x.v2_smem, s>>>(rv, p, x);
+        else route_fast2_kernel<false><<<grid2, R2_THREADS, x.v2_smem, s>>>(rv, p, x);
+        x.qlist = x.ovf_list; x.qlist_n = x.ovf_n;
+        route_fast_kernel<<<grid, RQ_THREADS, smem, s>>>(rv, p, x);
+        return cudaGetLastError() == cudaSuccess ? 3 : -1;
+    }
+    x.qlist = nullptr; x.qlist_n = nullptr;
     route_fast_kernel<<<grid, RQ_THREADS, smem, s>>>(rv, p, x);
     return cudaGetLastError() == cudaSuccess ? 2 : -1;
 }

@@ -37,7 +37,7 @@ def test_tokengen_codes_bit_exact(wg):
     assert np.array_equal(ctx.tokengen_batch(w.base[:777]), w.codes[:777])
 
 
-@pytest.mark.parametrize("general", [0, 1], ids=["fast-path", "general-path"])
+@pytest.mark.parametrize("general", [0, 2, 1], ids=["fast-path", "fast-path-one-cta", "general-path"])
 @pytest.mark.parametrize("probes,hard_cap,B", [(5, 20000, 64), (5, 20000, 100000), (3, 700, 256), (10, 2000, 1500), (1, 50, 40), (5, 1 << 20, 300),
                                                (5, 24000, 1024), (2, 20000, 1)])
 def test_route_candidates_ordered_bit_exact(wg, probes, hard_cap, B, general):
@@ -47,13 +47,20 @@ def test_route_candidates_ordered_bit_exact(wg, probes, hard_cap, B, general):
     codes = O.tokengen_batch(w.queries, w.g)
     hard_cap = max(hard_cap, min(B, 5000)) if hard_cap < B and B < 100000 else hard_cap
     B = min(B, 8192)
-    ctx.set_option("route_general", general)
+    ctx.set_option("route_general", int(general == 1))
+    ctx.set_option("route_v1", int(general == 2))
     try:
         out = ctx.route_batch(codes, probes, hard_cap, B)
     finally:
         ctx.set_option("route_general", 0)
-    if general:
+        ctx.set_option("route_v1", 0)
+    if general == 1:
         assert ctx.get_info("last_route_path") == 2
+    elif ctx.get_info("last_route_path") == 1:
+        # fast path: the two-CTA kernel serves B <= 1024 unless forced off; queries it handed to the one-CTA kernel are counted
+        assert ctx.get_info("last_route_v2") == (1 if general == 0 and B <= 1024 else 0)
+        assert 0 <= ctx.get_info("route_overflowed") <= codes.shape[0]
+    general = int(general == 1)
     worst_chain = 0
     for q in range(codes.shape[0]):
         ids, sc, raw, mc = O.route(w.ix, codes[q], probes, hard_cap)
@@ -165,6 +172,8 @@ def test_route_fast_path_with_every_id_duplicated(world_factory, wl_extra):
         for probes, B in [(5, 64), (8, 700)]:
             out = ctx.route_batch(codes, probes, 1 << 20, B)
             assert ctx.get_info("last_route_path") == 1
+            if wl_extra == 0 and ctx.get_info("last_route_v2"):          # two-CTA kernel with a 16-entry worklist: queries overflow into the one-CTA kernel
+                assert ctx.get_info("route_overflowed") > 0
             tot_raw = tot_unique = 0
             for q in range(codes.shape[0]):
                 ids, sc, raw, mc = O.route(ix, codes[q], probes, 1 << 20)
