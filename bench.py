@@ -493,6 +493,11 @@ def main():
     e2e_wall_ms = (time.perf_counter() - t_wall) * 1e3
     clocks = sampler.stop()
     checksum = int(h_ids.to(torch.int64).sum().item())
+    # the host-buffer call (chunked upload overlapped with TokenGen + Route) must return what the device-resident call returns
+    step_dev(Wm + K - 1)
+    barrier()
+    e2e_same = bool(torch.equal(h_ids, d_ids.cpu()) and torch.equal(h_dist.view(torch.int64), d_dist.cpu().view(torch.int64)) and
+                    torch.equal(h_nret, d_nret.cpu()) and torch.equal(h_cnt, d_cnt.cpu()))
 
     # ---- recall@10 of what was just timed: exact ground truth and recall on the device, outside the timed region
     recall = None
@@ -644,7 +649,7 @@ def main():
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                "clocks": clocks, "gpu_launches": launches,
                "e2e": {"value": e2e_val, "unit": "queries/s", "h2d_bytes_per_step": Q * dim * 8, "d2h_bytes_per_step": Q * k * 12 + Q * 4 + Q * 48,
-                       "ms_per_step": e2e_ms / K, "wall_ms_per_step": e2e_wall_ms / K, "result_checksum": checksum},
+                       "ms_per_step": e2e_ms / K, "wall_ms_per_step": e2e_wall_ms / K, "result_checksum": checksum, "equals_device_path": e2e_same},
                "roofline": {"bound": "hbm", "kernel": "refine_decrypt_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                             "frac": achieved / peak if peak else None, "traffic": load_traffic(args.config == "C2" and not args.n and not args.q),
                             "traffic_unit": "bytes/launch (dram read+write, ncu; profiles/r2_decrypt_traffic.json)", "peak_source": peak_src,

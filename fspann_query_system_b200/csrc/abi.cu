@@ -248,6 +248,8 @@ int fspann_ctx_create(int device, fspann_ctx **out) {
     if (configure_tokengen_kernels() || configure_route_kernels() || configure_refine_kernels()) { delete ctx; return FSPANN_E_CUDA; }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return FSPANN_E_CUDA; }
     for (int i = 0; i < 7; i++) cudaEventCreate(&ctx->ev[i]);
+    if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { fspann_ctx_destroy(ctx); return FSPANN_E_CUDA; }
+    for (int i = 0; i < 5; i++) cudaEventCreateWithFlags(&ctx->h2d_ev[i], cudaEventDisableTiming);
     uint32_t te0[256];
     aes_make_te0(te0);
     if (ensure(ctx, ctx->d_te0, sizeof te0) || cudaMemcpy(ctx->d_te0.p, te0, sizeof te0, cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -279,6 +281,8 @@ void fspann_ctx_destroy(fspann_ctx *ctx) {
     ctx->graphs.clear();
     sharded_release(ctx);
     for (int i = 0; i < 7; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 5; i++) if (ctx->h2d_ev[i]) cudaEventDestroy(ctx->h2d_ev[i]);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     delete ctx;
@@ -300,6 +304,7 @@ int fspann_set_option(fspann_ctx *ctx, const char *name, int64_t value) {
     if (!strcmp(name, "route_general")) { ctx->opt_route_general = value != 0; return FSPANN_OK; }
     if (!strcmp(name, "route_wl_extra")) { ctx->opt_route_wl_extra = (int)value; return FSPANN_OK; }
     if (!strcmp(name, "route_v1")) { ctx->opt_route_v1 = value != 0; return FSPANN_OK; }
+    if (!strcmp(name, "h2d_overlap")) { ctx->opt_h2d_overlap = (int)std::min<int64_t>(std::max<int64_t>(value, 0), 4); return FSPANN_OK; }
     if (!strcmp(name, "tokengen_exact")) { ctx->opt_tokengen_exact = value != 0; return FSPANN_OK; }
     if (!strcmp(name, "tokengen_mode")) { ctx->opt_tokengen_mode = (int)value; return FSPANN_OK; }
     if (!strcmp(name, "tokengen_list_cap")) { ctx->opt_tg_list_cap = value; return FSPANN_OK; }
@@ -991,12 +996,34 @@ int search_pass(fspann_ctx *ctx, int64_t Q, const double *d_queries, const uint6
     ENSURE(b_nc, sizeof(int32_t) * (size_t)Q); ENSURE(b_raw, sizeof(int32_t) * (size_t)Q); ENSURE(b_un, sizeof(int32_t) * (size_t)Q);
     ENSURE(b_nd, sizeof(int32_t) * (size_t)Q);
     int rc;
+    // upload plan of the host-pointer entries (consumed here, once)
+    const int chunks = main_pass && !d_codes_in ? ctx->h2d_chunks : 0;
+    const bool late = main_pass && ctx->h2d_late;
+    int64_t cq[5];
+    for (int c = 0; c < 5; c++) cq[c] = ctx->h2d_q0[c];
+    ctx->h2d_chunks = 0; ctx->h2d_late = false;
     if (main_pass) { rc = record_ev(ctx, 0); if (rc) return rc; }
-    if (!d_codes_in) { int rc_ = run_tokengen(ctx, Q, d_queries, (uint64_t *)b_codes.p); if (rc_) return rc_; }
-    if (main_pass) { rc = record_ev(ctx, 1); if (rc) return rc; }
-    rc = do_route(ctx, Q, d_codes_in ? d_codes_in : (const uint64_t *)b_codes.p, probes, hard_cap, B, (int32_t *)b_cid.p, (int32_t *)b_csc.p,
-                  (int32_t *)b_nc.p, (int32_t *)b_raw.p, (int32_t *)b_un.p);
-    if (rc) return rc;
+    if (chunks > 0) {
+        // TokenGen + Route per arriving chunk (both are independent per query); Refine below groups the whole batch
+        const size_t crow = (size_t)rv.TD * rv.W;
+        for (int c = 0; c < chunks; c++) {
+            const int64_t q0 = cq[c], n = cq[c + 1] - cq[c];
+            if (n <= 0) continue;
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->h2d_ev[c], 0));
+            { int rc_ = run_tokengen(ctx, n, d_queries + (size_t)q0 * rv.dim, (uint64_t *)b_codes.p + (size_t)q0 * crow); if (rc_) return rc_; }
+            if (c == 0) { rc = record_ev(ctx, 1); if (rc) return rc; }
+            rc = do_route(ctx, n, (const uint64_t *)b_codes.p + (size_t)q0 * crow, probes, hard_cap, B, (int32_t *)b_cid.p + (size_t)q0 * B,
+                          (int32_t *)b_csc.p + (size_t)q0 * B, (int32_t *)b_nc.p + q0, (int32_t *)b_raw.p + q0, (int32_t *)b_un.p + q0);
+            if (rc) return rc;
+        }
+    } else {
+        if (!d_codes_in) { int rc_ = run_tokengen(ctx, Q, d_queries, (uint64_t *)b_codes.p); if (rc_) return rc_; }
+        if (main_pass) { rc = record_ev(ctx, 1); if (rc) return rc; }
+        rc = do_route(ctx, Q, d_codes_in ? d_codes_in : (const uint64_t *)b_codes.p, probes, hard_cap, B, (int32_t *)b_cid.p, (int32_t *)b_csc.p,
+                      (int32_t *)b_nc.p, (int32_t *)b_raw.p, (int32_t *)b_un.p);
+        if (rc) return rc;
+    }
+    if (late) CK(cudaStreamWaitEvent(ctx->stream, ctx->h2d_ev[4], 0));     // the queries themselves: Refine is their first reader
     if (main_pass) { rc = record_ev(ctx, 2); if (rc) return rc; }
     rc = do_refine(ctx, Q, d_queries, (const int32_t *)b_cid.p, (const int32_t *)b_nc.p, B, k, d_topk_ids, d_topk_dist, d_nret, (int32_t *)b_nd.p, main_pass);
     if (rc) return rc;
@@ -1185,17 +1212,52 @@ static int search_host(fspann_ctx *ctx, int64_t Q, const uint64_t *codes, const 
     ENSURE(ctx->s_queries, sizeof(double) * (size_t)Q * dim);
     ENSURE(ctx->s_topk_ids, sizeof(int32_t) * (size_t)Q * k); ENSURE(ctx->s_topk_dist, sizeof(double) * (size_t)Q * k);
     ENSURE(ctx->s_nret, sizeof(int32_t) * (size_t)Q); ENSURE(ctx->s_counters, sizeof(int64_t) * FSPANN_COUNTERS * (size_t)Q);
-    CK(cudaMemcpyAsync(ctx->s_queries.p, queries, sizeof(double) * (size_t)Q * dim, cudaMemcpyHostToDevice, ctx->stream));
     const uint64_t *d_codes = nullptr;
+    ctx->h2d_chunks = 0; ctx->h2d_late = false;
+    const bool overlap = ctx->opt_h2d_overlap > 0 && Q >= 4096;
+    if (overlap) {                                                          // nothing of an earlier call still reads s_queries (host entries end synchronised)
+        CK(cudaEventRecord(ctx->h2d_ev[4], ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->h2d_ev[4], 0));
+    }
     if (codes) {
         const size_t cb = sizeof(uint64_t) * (size_t)Q * ctx->rv.TD * ctx->rv.W;
         ENSURE(ctx->s_codes_in, cb);
         CK(cudaMemcpyAsync(ctx->s_codes_in.p, codes, cb, cudaMemcpyHostToDevice, ctx->stream));
         d_codes = (const uint64_t *)ctx->s_codes_in.p;
+        if (overlap) {                                                      // Route needs only the codes: the query upload runs beside it
+            CK(cudaMemcpyAsync(ctx->s_queries.p, queries, sizeof(double) * (size_t)Q * dim, cudaMemcpyHostToDevice, ctx->copy_stream));
+            CK(cudaEventRecord(ctx->h2d_ev[4], ctx->copy_stream));
+            ctx->h2d_late = true;
+        } else {
+            CK(cudaMemcpyAsync(ctx->s_queries.p, queries, sizeof(double) * (size_t)Q * dim, cudaMemcpyHostToDevice, ctx->stream));
+        }
+    } else if (overlap) {
+        // up to 4 chunks, each a multiple of the Route grid (2 CTAs per SM) so no chunk ends in a partial wave
+        const int64_t wave = 2 * (int64_t)ctx->sm_count;
+        const int nch = std::max(2, ctx->opt_h2d_overlap);
+        const int64_t per = ((Q + 3) / 4 + wave - 1) / wave * wave;         // nch = 2: a quarter first, then the rest
+        int n = 0;
+        for (int64_t q0 = 0; q0 < Q && n < nch; q0 += per) {
+            const int64_t q1 = n == nch - 1 ? Q : std::min<int64_t>(Q, q0 + per);
+            ctx->h2d_q0[n] = q0; ctx->h2d_q0[n + 1] = q1;
+            CK(cudaMemcpyAsync((double *)ctx->s_queries.p + (size_t)q0 * dim, queries + (size_t)q0 * dim, sizeof(double) * (size_t)(q1 - q0) * dim,
+                               cudaMemcpyHostToDevice, ctx->copy_stream));
+            CK(cudaEventRecord(ctx->h2d_ev[n], ctx->copy_stream));
+            n++;
+            if (q1 >= Q) break;
+        }
+        ctx->h2d_chunks = n;
+    } else {
+        CK(cudaMemcpyAsync(ctx->s_queries.p, queries, sizeof(double) * (size_t)Q * dim, cudaMemcpyHostToDevice, ctx->stream));
     }
     const HostOut h{topk_ids_out, topk_dist_out, n_ret_out, counters_out};
-    return search_core(ctx, Q, (const double *)ctx->s_queries.p, d_codes, k, probes, hard_cap, B, true, codes == nullptr, (int32_t *)ctx->s_topk_ids.p,
-                       (double *)ctx->s_topk_dist.p, (int32_t *)ctx->s_nret.p, (int64_t *)ctx->s_counters.p, &h);
+    rc = search_core(ctx, Q, (const double *)ctx->s_queries.p, d_codes, k, probes, hard_cap, B, true, codes == nullptr, (int32_t *)ctx->s_topk_ids.p,
+                     (double *)ctx->s_topk_dist.p, (int32_t *)ctx->s_nret.p, (int64_t *)ctx->s_counters.p, &h);
+    if (ctx->h2d_chunks || ctx->h2d_late) {                                 // the call failed before its first pass consumed the upload plan
+        ctx->h2d_chunks = 0; ctx->h2d_late = false;
+        cudaStreamSynchronize(ctx->copy_stream);
+    }
+    return rc;
 }
 
 int fspann_search_batch(fspann_ctx *ctx, int64_t Q, const double *queries, int32_t k, int32_t probes, int64_t hard_cap, int32_t B,

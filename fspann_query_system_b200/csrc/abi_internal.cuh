@@ -20,6 +20,14 @@ struct fspann_ctx {
     int device = 0;
     int sm_count = 1;                            // multiProcessorCount of ctx->device (set by fspann_ctx_create)
     cudaStream_t stream = nullptr;
+    // host-pointer search entries: the query upload runs on `copy_stream` in up to 4 chunks (h2d_ev), so TokenGen + Route of chunk c overlap
+    // the PCIe copy of chunk c+1; with supplied codes the whole query upload overlaps Route (h2d_late).  Consumed by search_pass.
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t h2d_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    int h2d_chunks = 0;            // > 0: chunk c = queries [h2d_q0[c], h2d_q0[c+1]) arrives with h2d_ev[c]
+    int64_t h2d_q0[5] = {0, 0, 0, 0, 0};
+    bool h2d_late = false;         // the queries arrive with h2d_ev[4] (needed by Refine only)
+    int opt_h2d_overlap = 2;       // chunks of the overlapped query upload (0 = one copy on the main stream)
     int32_t *h_pin = nullptr;                    // pinned host staging for the per-batch retry decision (n_ret, n_decrypted, flags)
     size_t h_pin_ints = 0;
     std::string err;

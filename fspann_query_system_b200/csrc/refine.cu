@@ -505,7 +505,10 @@ __device__ __forceinline__ bool warp_decrypt_staged_ctr(int dim, unsigned char *
 // AAD blocks ("id:<id>|v:<ver>|d:<dim>", EP:80-83), the ciphertext blocks and the length block; tag = GHASH ^ E_K(J0)
 // (NIST SP 800-38D).  Writes one verdict per distinct record: OK / TAG_FAIL (NO_KEY is the preset default).
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int VF_THREADS = 256;
+constexpr int VF_THREADS = 512;            // one CTA per SM: 64 KB Shoup table + 32 KB Te + 16 warps x 5 KB of ciphertext staging
+constexpr int VF_SLICE = 4;                // ciphertext blocks staged per record and step (64 bytes)
+constexpr int VF_ROW = VF_SLICE * 16 + 16; // staged row pitch: 80 bytes -> the 128-bit reads of a quarter warp fall into 8 distinct bank groups
+constexpr int VF_STAGE = 32 * VF_ROW;      // one buffer of one warp
 
 struct ShoupSmem {
     const uint4 *t;   // [256][16] byte-major
@@ -575,6 +578,77 @@ __device__ __forceinline__ void lane_gcm_tag(const StoreView &sv, const uint8_t 
     tag[0] = y0 ^ ej0[0]; tag[1] = y1 ^ ej0[1]; tag[2] = y2 ^ ej0[2]; tag[3] = y3 ^ ej0[3];
 }
 
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// The same tag for the 32 records of a WARP (lane l owns record l; rec == nullptr: the lane idles), with the ciphertext staged through
+// shared memory: a lane-per-record read of 16 bytes touches 32 different 128-byte lines per warp instruction and costs the LSU as much as
+// half of the Shoup look-ups.  Here the warp copies VF_SLICE blocks of all its records per step with cp.async (4 lanes per record: 64
+// contiguous bytes, whole sectors; global -> shared without registers), double-buffered, and every lane then reads its own row with
+// conflict-free 128-bit shared loads.  `stage` = this warp's 2 x VF_STAGE bytes.
+template <class SH>
+__device__ __forceinline__ void warp_gcm_tag_staged(const StoreView &sv, const uint8_t *rec, int32_t id, uint4 hdr, const SH &sh, const TeSmem &te,
+                                                    const RkSmem &rk, unsigned char *stage, int lane, uint32_t tag[4]) {
+    const int dim = sv.dim, nbytes = 8 * dim, c = (nbytes + 15) >> 4;
+    const int n_slices = (c + VF_SLICE - 1) / VF_SLICE;
+    const int32_t version = (int32_t)hdr.w;
+    const unsigned long long ctp = rec ? (unsigned long long)(uintptr_t)(rec + 16) : 0ull;
+    auto issue = [&](int sl, int b) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int src = j * 8 + (lane >> 2);
+            const unsigned long long pr = __shfl_sync(0xffffffffu, ctp, src);
+            const int blk = sl * VF_SLICE + (lane & 3);
+            if (pr && blk < c) cp_async16(stage + b * VF_STAGE + src * VF_ROW + (lane & 3) * 16, reinterpret_cast<const void *>((uintptr_t)(pr + (size_t)blk * 16)));
+        }
+        cp_async_commit();
+    };
+    issue(0, 0);
+    // ---- GHASH over AAD || ciphertext || lengths ----
+    uint32_t y0 = 0, y1 = 0, y2 = 0, y3 = 0;
+    int alen = 0;
+    if (rec) {
+        uint8_t aad[FSP_AAD_MAX];
+        alen = build_aad((int64_t)id, version, dim, aad);
+        for (int j = 0; j < (alen + 15) >> 4; j++) {
+            const uint64_t hi = load_be64(aad + 16 * j), lo = load_be64(aad + 16 * j + 8);
+            y0 ^= (uint32_t)(hi >> 32); y1 ^= (uint32_t)hi; y2 ^= (uint32_t)(lo >> 32); y3 ^= (uint32_t)lo;
+            sh.mul(y0, y1, y2, y3);
+        }
+    }
+    for (int sl = 0; sl < n_slices; sl++) {
+        if (sl + 1 < n_slices) { issue(sl + 1, (sl + 1) & 1); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        __syncwarp();
+        if (rec) {
+            const uint4 *row = reinterpret_cast<const uint4 *>(stage + (sl & 1) * VF_STAGE + lane * VF_ROW);
+#pragma unroll
+            for (int k = 0; k < VF_SLICE; k++) {
+                const int blk = sl * VF_SLICE + k;
+                if (blk < c) {
+                    const uint4 w = row[k];
+                    uint32_t x0 = bswap32(w.x), x1 = bswap32(w.y), x2 = bswap32(w.z), x3 = bswap32(w.w);
+                    if ((blk == c - 1) && (nbytes & 15)) { x2 = 0; x3 = 0; }     // odd dim: zero-pad the half block
+                    y0 ^= x0; y1 ^= x1; y2 ^= x2; y3 ^= x3;
+                    sh.mul(y0, y1, y2, y3);
+                }
+            }
+        }
+        __syncwarp();                                                           // the buffer is refilled two steps later
+    }
+    if (!rec) return;
+    y1 ^= (uint32_t)alen * 8u;                       // [len(A)]64 || [len(C)]64 in bits
+    y3 ^= (uint32_t)nbytes * 8u;
+    sh.mul(y0, y1, y2, y3);
+    // ---- tag = GHASH ^ E_K(J0), J0 = IV || 0x00000001 ----
+    uint32_t ej0[4];
+    aes256_encrypt(te, rk, bswap32(hdr.x), bswap32(hdr.y), bswap32(hdr.z), 1u, ej0);
+    tag[0] = y0 ^ ej0[0]; tag[1] = y1 ^ ej0[1]; tag[2] = y2 ^ ej0[2]; tag[3] = y3 ^ ej0[3];
+}
+
 // GHASH + tag check of one record by ONE lane (AGC:145-158: doFinal throws AEADBadTagException on a mismatch).
 template <class SH>
 __device__ __forceinline__ bool lane_verify_record(const StoreView &sv, const uint8_t *rec, int32_t id, uint4 hdr, const SH &sh,
@@ -599,6 +673,7 @@ __device__ __forceinline__ void gcm_tag_body(const StoreView &sv, const int32_t 
     uint32_t *te_s = reinterpret_cast<uint32_t *>(shoup_s + 4096);            // [256][32]
     uint32_t *s_rk = te_s + 256 * 32;                                         // [kMaxKeys][60]
     int32_t *s_ver = reinterpret_cast<int32_t *>(s_rk + kMaxKeys * 60);
+    unsigned char *stage_s = reinterpret_cast<unsigned char *>(s_ver + kMaxKeys);   // [warps][2][VF_STAGE]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < 256 * 32; i += VF_THREADS) te_s[i] = sv.te0[i >> 5];
     const int nkeys = sv.keys->n;
@@ -617,23 +692,30 @@ __device__ __forceinline__ void gcm_tag_body(const StoreView &sv, const int32_t 
         const int32_t version = s_ver[vi];
         const RkSmem rk{s_rk + vi * 60};
         const int n_chunks = (v_n + 31) >> 5;
-        for (int chunk = blockIdx.x * (VF_THREADS / 32) + warp; chunk < n_chunks; chunk += warps_total) {
+        for (int chunk = blockIdx.x * (VF_THREADS / 32) + warp; chunk < n_chunks; chunk += warps_total) {   // whole warps stay in the loop
             const int idx = (chunk << 5) + lane;
-            if (idx >= v_n) continue;
-            const int u = vorder ? vorder[v_lo + idx] : idx;
-            if (write_flag && !write_flag[u]) continue;
-            const int32_t li = list[u];                                     // index inside this shard
-            const int32_t id = gid ? gid[u] : (int32_t)(li + sv.id_base);   // global id: what the AAD binds (EP:80-83)
-            const uint8_t *rec = sv.rec + (size_t)li * sv.rec_stride;
-            const uint4 hdr = ld_rec(reinterpret_cast<const uint4 *>(rec));
-            if ((int32_t)hdr.w != version) continue;
+            const uint8_t *rec = nullptr;
+            int32_t id = 0, u = -1;
+            uint4 hdr = make_uint4(0, 0, 0, 0);
+            if (idx < v_n) {
+                u = vorder ? vorder[v_lo + idx] : idx;
+                if (!(write_flag && !write_flag[u])) {
+                    const int32_t li = list[u];                                 // index inside this shard
+                    id = gid ? gid[u] : (int32_t)(li + sv.id_base);             // global id: what the AAD binds (EP:80-83)
+                    const uint8_t *r = sv.rec + (size_t)li * sv.rec_stride;
+                    hdr = ld_rec(reinterpret_cast<const uint4 *>(r));
+                    if ((int32_t)hdr.w == version) rec = r;
+                }
+            }
+            uint32_t tag[4] = {0, 0, 0, 0};
+            warp_gcm_tag_staged(sv, rec, id, hdr, sh, te, rk, stage_s + (size_t)warp * 2 * VF_STAGE, lane, tag);
+            if (!rec) continue;
+            uint2 *tagp = reinterpret_cast<uint2 *>(const_cast<uint8_t *>(rec) + 16 + 8 * sv.dim);
             if (!write_flag) {
-                const bool ok = lane_verify_record(sv, rec, id, hdr, sh, te, rk);
+                const uint2 t0 = ld_rec(tagp), t1 = ld_rec(tagp + 1);         // AGC:145-158: doFinal throws AEADBadTagException on a mismatch
+                const bool ok = tag[0] == bswap32(t0.x) && tag[1] == bswap32(t0.y) && tag[2] == bswap32(t1.x) && tag[3] == bswap32(t1.y);
                 verdict[u] = ok ? FSPANN_V_OK : FSPANN_V_TAG_FAIL;          // AGC:159-165
             } else {
-                uint32_t tag[4];
-                lane_gcm_tag(sv, rec, id, hdr, sh, te, rk, tag);
-                uint2 *tagp = reinterpret_cast<uint2 *>(const_cast<uint8_t *>(rec) + 16 + 8 * sv.dim);
                 tagp[0] = make_uint2(bswap32(tag[0]), bswap32(tag[1]));
                 tagp[1] = make_uint2(bswap32(tag[2]), bswap32(tag[3]));
             }
@@ -641,7 +723,7 @@ __device__ __forceinline__ void gcm_tag_body(const StoreView &sv, const int32_t 
     }
 }
 
-__global__ void __launch_bounds__(VF_THREADS) refine_verify_kernel(StoreView sv, RefineParams p) {
+__global__ void __launch_bounds__(VF_THREADS, 1) refine_verify_kernel(StoreView sv, RefineParams p) {
     extern __shared__ __align__(16) unsigned char vf_smem[];
     gcm_tag_body(sv, p.uniq, nullptr, p.totals[1], p.rec_verdict, nullptr, vf_smem, p.vorder, p.voff);
 }
@@ -684,26 +766,27 @@ int launch_version_bucket(cudaStream_t s, const StoreView &sv, const RefineParam
 }
 
 // The same over an explicit host-sized list (Migrate / bulk encryption).
-__global__ void __launch_bounds__(VF_THREADS) gcm_tag_kernel(StoreView sv, const int32_t *list, const int32_t *gid, int n_list, uint8_t *verdict,
+__global__ void __launch_bounds__(VF_THREADS, 1) gcm_tag_kernel(StoreView sv, const int32_t *list, const int32_t *gid, int n_list, uint8_t *verdict,
                                                              const uint8_t *write_flag) {
     extern __shared__ __align__(16) unsigned char vf_smem[];
     gcm_tag_body(sv, list, gid, n_list, verdict, write_flag, vf_smem);
 }
 
-static size_t verify_smem_bytes() { return sizeof(uint4) * 4096 + sizeof(uint32_t) * (256 * 32 + kMaxKeys * 60) + sizeof(int32_t) * kMaxKeys; }
+static size_t verify_smem_bytes() {
+    return sizeof(uint4) * 4096 + sizeof(uint32_t) * (256 * 32 + kMaxKeys * 60) + sizeof(int32_t) * kMaxKeys + (size_t)(VF_THREADS / 32) * 2 * VF_STAGE;
+}
 
 int launch_gcm_tag(cudaStream_t s, const StoreView &sv, const int32_t *list, const int32_t *gid, int n_list, uint8_t *verdict,
                    const uint8_t *write_flag, int sm_count) {
     if (n_list <= 0) return 0;
     const size_t smem = verify_smem_bytes();
-    int grid = (n_list + VF_THREADS - 1) / VF_THREADS; if (grid > sm_count * 2) grid = sm_count * 2;
+    int grid = (n_list + VF_THREADS - 1) / VF_THREADS; if (grid > sm_count) grid = sm_count;
     gcm_tag_kernel<<<grid, VF_THREADS, smem, s>>>(sv, list, gid, n_list, verdict, write_flag);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
 int launch_refine_verify(cudaStream_t s, const StoreView &sv, const RefineParams &p, int sm_count) {
-    const size_t smem = sizeof(uint4) * 4096 + sizeof(uint32_t) * (256 * 32 + kMaxKeys * 60) + sizeof(int32_t) * kMaxKeys;
-    refine_verify_kernel<<<sm_count * 2, VF_THREADS, smem, s>>>(sv, p);
+    refine_verify_kernel<<<sm_count, VF_THREADS, verify_smem_bytes(), s>>>(sv, p);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
