@@ -1284,12 +1284,162 @@ __global__ void __launch_bounds__(TKW_WARPS * 32) refine_topk_warp_kernel(Refine
     if (lane == 0) { p.n_ret[q] = eff; if (p.n_dec) p.n_dec[q] = ndec; }
 }
 
+// Candidate lists longer than 1024 (e.g. the reference's SIFT_P6 operating point, B = 16000, k = 100): exact radix SELECT of the k-th
+// smallest (distance bits, rank) instead of k block-wide arg-min rounds.  One 256-thread CTA per query:
+//   1. eight 8-bit levels (most significant first) over the IEEE bit patterns of the decrypted candidates' distances -> the longest
+//      prefix P of the k-th smallest key and how many keys are smaller (warp-aggregated shared histograms);
+//   2. one ORDERED pass over the list: keys below P are taken, keys equal to P in candidate order until k are taken (the reference's
+//      stable sort keeps the earlier candidate on a tie, QSI:298) -> <= k (key, rank) pairs, in candidate order;
+//   3. bitonic sort of those on (key, rank), write-out.
+constexpr int TS_THREADS = 256;
+constexpr int TS_MAXK = 2048;
+
+__global__ void __launch_bounds__(TS_THREADS) refine_topk_select_kernel(RefineParams p) {
+    __shared__ int32_t s_hist[256];
+    __shared__ int32_t s_w[TS_THREADS / 32 + 1], s_w2[TS_THREADS / 32 + 1];
+    __shared__ int32_t s_pick[3], s_cnt;
+    __shared__ unsigned long long s_key[TS_MAXK];
+    __shared__ int32_t s_rank[TS_MAXK];
+    const int64_t q = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = p.n_cand[q];
+    const double *dist = p.dist + (size_t)q * p.stride;
+    const uint8_t *ver = p.verdict + (size_t)q * p.stride;
+
+    int ndec = 0;
+    for (int r = tid; r < n; r += TS_THREADS) ndec += ver[r] == FSPANN_V_OK;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) ndec += __shfl_xor_sync(0xffffffffu, ndec, o);
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+    if (lane == 0) atomicAdd(&s_cnt, ndec);
+    __syncthreads();
+    const int total_ok = s_cnt;
+    const int eff = min(p.k, total_ok);
+    __syncthreads();
+
+    if (eff > 0) {
+        // ---- 1. radix select: prefix of the eff-th smallest key ----
+        unsigned long long prefix = 0ull;
+        int cum = 0, used = 0;
+        for (; used < 64; used += 8) {
+            const int shift = 56 - used;
+            s_hist[tid] = 0;
+            __syncthreads();
+            for (int r0 = 0; r0 < n; r0 += TS_THREADS) {
+                const int r = r0 + tid;
+                bool in = false; int bin = 0;
+                if (r < n && ver[r] == FSPANN_V_OK) {
+                    const unsigned long long key = (unsigned long long)__double_as_longlong(dist[r]);
+                    in = used == 0 || (key >> (shift + 8)) == prefix;
+                    bin = (int)((key >> shift) & 0xffull);
+                }
+                const unsigned act = __ballot_sync(0xffffffffu, in);
+                if (in) {
+                    const unsigned peers = __match_any_sync(act, bin);
+                    if (lane == __ffs(peers) - 1) atomicAdd(&s_hist[bin], __popc(peers));
+                }
+            }
+            __syncthreads();
+            if (warp == 0) {                                   // first bin d with cum + sum(hist[0..d]) >= eff
+                int loc[8], sum = 0;
+#pragma unroll
+                for (int u = 0; u < 8; u++) { loc[u] = s_hist[lane * 8 + u]; sum += loc[u]; }
+                int incl = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+                const int excl = cum + incl - sum;
+                const unsigned hit = __ballot_sync(0xffffffffu, excl + sum >= eff);
+                const int owner = __ffs(hit) - 1;              // total_ok >= eff: some lane hits
+                if (lane == owner) {
+                    int c = excl, u = 0;
+                    for (; u < 7; u++) { if (c + loc[u] >= eff) break; c += loc[u]; }
+                    s_pick[0] = lane * 8 + u; s_pick[1] = c; s_pick[2] = loc[u];
+                }
+            }
+            __syncthreads();
+            prefix = (prefix << 8) | (unsigned long long)s_pick[0];
+            cum = s_pick[1];
+            const int bin_n = s_pick[2];
+            __syncthreads();
+            if (cum + bin_n == eff) { used += 8; break; }      // the whole bin is selected: no finer split needed
+        }
+        const int pshift = 64 - used;                          // keys compare through their top `used` bits
+        const int need_tie = eff - cum;
+        // ---- 2. ordered pass: below the prefix -> taken; equal -> taken in candidate order until need_tie ----
+        int run_sel = 0, run_tie = 0;                          // block-uniform running counts
+        for (int r0 = 0; r0 < n; r0 += TS_THREADS) {
+            const int r = r0 + tid;
+            bool less = false, tie = false; unsigned long long key = 0ull;
+            if (r < n && ver[r] == FSPANN_V_OK) {
+                key = (unsigned long long)__double_as_longlong(dist[r]);
+                const unsigned long long kp = pshift >= 64 ? 0ull : key >> pshift;
+                less = kp < prefix; tie = kp == prefix;
+            }
+            const unsigned bt = __ballot_sync(0xffffffffu, tie), bl = __ballot_sync(0xffffffffu, less);
+            if (lane == 0) { s_w[warp] = __popc(bt); s_w2[warp] = __popc(bl); }
+            __syncthreads();
+            int tie_before = run_tie, tie_total = 0, less_before = 0, less_total = 0;
+            for (int w = 0; w < TS_THREADS / 32; w++) {
+                const int ct = s_w[w], cl = s_w2[w];
+                if (w < warp) { tie_before += ct; less_before += cl; }
+                tie_total += ct; less_total += cl;
+            }
+            const unsigned lt = (1u << lane) - 1u;
+            const int my_tie_ord = tie_before + __popc(bt & lt);
+            const bool take = less || (tie && my_tie_ord < need_tie);
+            // slot: ordered over (less | taken ties) -- ties taken before this thread in the chunk: min(ordinal, need_tie) bookkeeping
+            const unsigned btake = __ballot_sync(0xffffffffu, take);
+            __syncthreads();
+            if (lane == 0) s_w[warp] = __popc(btake);
+            __syncthreads();
+            int before = run_sel, tot = 0;
+            for (int w = 0; w < TS_THREADS / 32; w++) { const int c = s_w[w]; if (w < warp) before += c; tot += c; }
+            if (take) { const int slot = before + __popc(btake & lt); s_key[slot] = key; s_rank[slot] = r; }
+            run_sel += tot; run_tie += tie_total;
+            (void)less_before; (void)less_total;
+            __syncthreads();
+        }
+        // ---- 3. bitonic sort of the eff pairs on (key, rank) ----
+        int m = 1; while (m < eff) m <<= 1;
+        for (int i = eff + tid; i < m; i += TS_THREADS) { s_key[i] = ~0ull; s_rank[i] = 0x7fffffff; }
+        __syncthreads();
+        for (int kk = 2; kk <= m; kk <<= 1) {
+            for (int j = kk >> 1; j > 0; j >>= 1) {
+                for (int i = tid; i < m; i += TS_THREADS) {
+                    const int ixj = i ^ j;
+                    if (ixj > i) {
+                        const unsigned long long a = s_key[i], b = s_key[ixj];
+                        const int ra = s_rank[i], rb = s_rank[ixj];
+                        const bool gt = a > b || (a == b && ra > rb);
+                        if (gt == ((i & kk) == 0)) { s_key[i] = b; s_key[ixj] = a; s_rank[i] = rb; s_rank[ixj] = ra; }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        for (int i = tid; i < eff; i += TS_THREADS) {
+            const int br = s_rank[i];
+            p.topk_ids[(size_t)q * p.k + i] = p.cand_ids[(size_t)q * p.stride + br];
+            p.topk_dist[(size_t)q * p.k + i] = __longlong_as_double((long long)s_key[i]);
+            if (p.topk_rank) p.topk_rank[(size_t)q * p.k + i] = br;
+        }
+    }
+    for (int i = eff + tid; i < p.k; i += TS_THREADS) {
+        p.topk_ids[(size_t)q * p.k + i] = -1;
+        p.topk_dist[(size_t)q * p.k + i] = __longlong_as_double(0x7ff8000000000000ll);
+        if (p.topk_rank) p.topk_rank[(size_t)q * p.k + i] = 0x7fffffff;
+    }
+    if (tid == 0) { p.n_ret[q] = eff; if (p.n_dec) p.n_dec[q] = total_ok; }
+}
+
 int launch_refine_topk(cudaStream_t s, const RefineParams &p) {
     if (p.Q <= 0) return 0;
     const unsigned grid = (unsigned)((p.Q + TKW_WARPS - 1) / TKW_WARPS);
     if (p.stride <= 32 * 8) refine_topk_warp_kernel<8><<<grid, TKW_WARPS * 32, 0, s>>>(p);
     else if (p.stride <= 32 * 16) refine_topk_warp_kernel<16><<<grid, TKW_WARPS * 32, 0, s>>>(p);
     else if (p.stride <= 32 * 32) refine_topk_warp_kernel<32><<<grid, TKW_WARPS * 32, 0, s>>>(p);
+    else if (p.k <= TS_MAXK) refine_topk_select_kernel<<<(unsigned)p.Q, TS_THREADS, 0, s>>>(p);
     else refine_topk_kernel<<<(unsigned)p.Q, TK_THREADS, 0, s>>>(p);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }

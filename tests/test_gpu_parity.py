@@ -112,7 +112,34 @@ def test_refine_verdicts_topk_bit_exact(wg):
         assert np.array_equal(out["top_dist"][q, :n].view(np.uint64), ref["top_dist"].view(np.uint64)), "distances must be bit-exact FP64"
 
 
-@pytest.mark.parametrize("k,B", [(10, 64), (100, 256), (1, 16)])
+@pytest.mark.parametrize("k", [1, 10, 64, 300])
+def test_refine_long_lists_with_exact_distance_ties(wg, k):
+    """Candidate lists beyond 1024 entries take the radix-select top-k.  Lists that name the same records several times give many
+    EXACT distance ties, which the reference's stable sort (QSI:298) resolves by candidate order; ragged / empty lists included."""
+    w, ctx = wg
+    Q = min(12, w.queries.shape[0])
+    B = 2500
+    rng = np.random.default_rng(17 + k)
+    cand = np.full((Q, B), -1, dtype=np.int32)
+    ncand = np.zeros(Q, dtype=np.int32)
+    for q in range(Q):
+        n = [B, 1100, 0, 1025, 2499][q % 5]
+        distinct = rng.choice(w.cfg.N, size=min(w.cfg.N, max(1, n // (1 + q % 4))), replace=False)
+        lst = rng.choice(distinct, size=n, replace=True) if n else np.zeros(0, dtype=np.int64)
+        cand[q, :n] = lst
+        if n > 10:
+            cand[q, 5] = w.cfg.N + 3                                    # notFound among them
+        ncand[q] = n
+    out = ctx.refine_batch(w.queries[:Q], cand, ncand, k)
+    for q in range(Q):
+        ref = O.refine(w.store, w.queries[q], cand[q, :ncand[q]], k)
+        n = len(ref["top_ids"])
+        assert out["n_ret"][q] == n and out["n_decrypted"][q] == ref["n_decrypted"]
+        assert np.array_equal(out["top_ids"][q, :n], ref["top_ids"]), q
+        assert np.array_equal(out["top_dist"][q, :n].view(np.uint64), ref["top_dist"].view(np.uint64))
+
+
+@pytest.mark.parametrize("k,B", [(10, 64), (100, 256), (1, 16), (100, 3000), (7, 1500)])     # B > 1024: radix-select top-k
 def test_search_batch_matches_reference_search(wg, k, B):
     """QSI.search incl. the adaptive retry (k=100,B=256 forces decrypted < 10*K -> second pass with 10 probes)."""
     w, ctx = wg
