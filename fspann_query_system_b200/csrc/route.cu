@@ -1018,23 +1018,32 @@ __global__ void __launch_bounds__(R2_THREADS, 2) route_fast2_kernel(RoutingView 
             for (int j = 0; j < 4; j++) if (id4[j] >= 0 && id4[j] < rv.n_deleted && deleted[id4[j]]) id4[j] = -2;
         }
     };
+    const uint32_t F_sa = (uint32_t)__cvta_generic_to_shared(F);
     auto filter_set = [&](int32_t id) {
         const uint32_t h1 = ((uint32_t)id * 0x9E3779B1u) >> fshift, h2 = ((uint32_t)id * 0x85EBCA6Bu) >> fshift;
         const uint32_t s1 = (h1 & 15u) * 2u, s2 = (h2 & 15u) * 2u;
-        const uint32_t o1 = atomicOr(&F[h1 >> 4], 1u << s1);
-        if ((o1 >> s1) & 1u) atomicOr(&F[h1 >> 4], 2u << s1);
-        const uint32_t o2 = atomicOr(&F[f2_off + (h2 >> 4)], 1u << s2);
-        if ((o2 >> s2) & 1u) atomicOr(&F[f2_off + (h2 >> 4)], 2u << s2);
+        const uint32_t a1 = F_sa + (h1 >> 4) * 4u, a2 = F_sa + (f2_off + (h2 >> 4)) * 4u;
+        // "taken" bit with the old value back; the "taken twice" bit only when it was taken already: a PREDICATED reduction (the C++ `if`
+        // around an atomic compiles to a divergent branch with convergence barriers, 6 extra instructions per id and filter)
+        uint32_t o1, o2;
+        asm volatile("atom.shared.or.b32 %0, [%1], %2;" : "=r"(o1) : "r"(a1), "r"(1u << s1) : "memory");
+        asm volatile("atom.shared.or.b32 %0, [%1], %2;" : "=r"(o2) : "r"(a2), "r"(1u << s2) : "memory");
+        asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p red.shared.or.b32 [%0], %1; }" ::"r"(a1), "r"(2u << s1), "r"((o1 >> s1) & 1u) : "memory");
+        asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p red.shared.or.b32 [%0], %1; }" ::"r"(a2), "r"(2u << s2), "r"((o2 >> s2) & 1u) : "memory");
     };
     auto filter_twice = [&](int32_t id) -> bool {                        // taken twice in BOTH filters: not provably a single occurrence
-        const uint32_t h1 = ((uint32_t)id * 0x9E3779B1u) >> fshift;
-        if (!((F[h1 >> 4] >> ((h1 & 15u) * 2u)) & 2u)) return false;
-        const uint32_t h2 = ((uint32_t)id * 0x85EBCA6Bu) >> fshift;
-        return ((F[f2_off + (h2 >> 4)] >> ((h2 & 15u) * 2u)) & 2u) != 0;
+        // both look-ups unconditionally: with 32 lanes some lane nearly always needs the second one, so a short-circuit only adds a branch
+        const uint32_t h1 = ((uint32_t)id * 0x9E3779B1u) >> fshift, h2 = ((uint32_t)id * 0x85EBCA6Bu) >> fshift;
+        return ((F[h1 >> 4] >> ((h1 & 15u) * 2u)) & (F[f2_off + (h2 >> 4)] >> ((h2 & 15u) * 2u)) & 2u) != 0;
     };
 
-    for (int64_t q = blockIdx.x; q < p.Q; q += gridDim.x) {
+    __shared__ int32_t s_q;
+    for (;;) {
         __syncthreads();
+        if (tid == 0) s_q = atomicAdd(x.ovf_n + 1, 1);                      // dynamic query assignment: the cost per query varies (worklist size, cut class)
+        __syncthreads();
+        const int64_t q = s_q;
+        if (q >= p.Q) break;
         // ---- 1. stage visits, reset the filters ----
         for (int v = tid; v < nvis; v += R2_THREADS) {
             const int g = v / probes, j = v - g * probes;
@@ -1097,19 +1106,19 @@ __global__ void __launch_bounds__(R2_THREADS, 2) route_fast2_kernel(RoutingView 
                         else if (HAS_DEL && idv[u][j] == -2) dead++;
                     }
                 }
+                // (warp-collective bookkeeping -- REDUX + shuffles + ballots instead of these three shared atomics -- was measured slower: 1.95 vs 1.86 ms)
                 if (invmask | (uint32_t)dead) {
                     const int c = __popc(invmask);
                     atomicAdd(reinterpret_cast<unsigned int *>(inv_cnt) + (e >> 7), (unsigned)(c + dead) << (((e >> 6) & 1) * 16));
                     if (c) {
                         int base = atomicAdd(&s_nwl, c);
                         atomicOr(&inv_bm[e >> 5], invmask << (e & 31));
+                        if (base + c <= wl_cap) {
 #pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            if ((invmask >> j) & 1u) {
-                                if (base < wl_cap) { wl_id[base] = idv[u][j]; wl_pos[base] = (uint16_t)(e + j); } else fits = false;
-                                base++;
+                            for (int j = 0; j < 4; j++) {
+                                if ((invmask >> j) & 1u) { wl_id[base] = idv[u][j]; wl_pos[base] = (uint16_t)(e + j); base++; }
                             }
-                        }
+                        } else fits = false;
                     }
                 }
             }
@@ -1374,7 +1383,7 @@ int launch_route_fast(cudaStream_t s, const RoutingView &rv, const RouteParams &
     const int grid = (int)std::min<int64_t>(p.Q, sm_count);
     if (x.v2_smem && x.ovf_n) {
         // two CTAs per SM; the queries it cannot hold (worklist / class list / key width) come back in ovf_list for the one-CTA kernel
-        if (cudaMemsetAsync(x.ovf_n, 0, sizeof(int32_t), s) != cudaSuccess) return -1;
+        if (cudaMemsetAsync(x.ovf_n, 0, 2 * sizeof(int32_t), s) != cudaSuccess) return -1;     // [0] overflow count, [1] next query
         const int grid2 = (int)std::min<int64_t>(p.Q, 2 * (int64_t)sm_count);
         if (rv.deleted) route_fast2_kernel<true><<<grid2, R2_THREADS, x.v2_smem, s>>>(rv, p, x);
         else route_fast2_kernel<false><<<grid2, R2_THREADS, x.v2_smem, s>>>(rv, p, x);
