@@ -905,7 +905,8 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) route_fast_kernel(RoutingView r
 //   * the bitonic sort holds two keys per thread and double-buffers its shared-memory exchanges (one barrier per stage).
 // Same results as route_fast_kernel bit for bit (same filters, same exact path, same selection keys).
 // =====================================================================================================================
-constexpr int R2_THREADS = 512;
+constexpr int R2_THREADS = 512;           // 16 warps per CTA, two CTAs per SM (768 threads = 48 warps per SM at 40 registers was measured slower: 2.00 vs 1.80 ms)
+constexpr int R2_H = 512;                 // the sort works on 2 x R2_H keys held by the first R2_H threads
 constexpr int R2_SELBYTES = 7168;          // sel_id int32[1024] + sel_pos uint16[1024] + sel_sc uint8[1024]
 
 struct Route2Layout { int region, cls_cap, wl_cap; size_t smem; };
@@ -929,32 +930,34 @@ static bool route2_layout(int TD, int probes, int n_raw, int tbl, Route2Layout &
     return true;
 }
 
-// Bitonic sort of TWO 32-bit keys per thread (elements tid and tid + R2_THREADS); strides < 32 by shuffles, larger ones through the
-// double buffer `buf` (2 x 2*R2_THREADS words; one barrier per stage), stride R2_THREADS inside the thread.  N > 0: unrolled network.
+// Bitonic sort of TWO 32-bit keys per thread (elements tid and tid + R2_H of threads tid < R2_H; the other threads only keep the barriers
+// company); strides < 32 by shuffles, larger ones through the double buffer `buf` (2 x 2*R2_H words; one barrier per stage), stride R2_H
+// inside the thread.  N > 0: unrolled network.
 template <int N>
 __device__ __forceinline__ void bitonic_sort32x2(uint32_t &a0, uint32_t &a1, int tid, uint32_t *buf, int n_rt = 0) {
     const int n = N > 0 ? N : n_rt;
+    const bool on = tid < R2_H;
     int phase = 0;
 #pragma unroll
     for (int k = 2; k <= n; k <<= 1) {
 #pragma unroll
         for (int j = k >> 1; j > 0; j >>= 1) {
-            if (j == R2_THREADS) {                                   // k == 2 * R2_THREADS: ascending everywhere
+            if (j == R2_H) {                                         // k == 2 * R2_H: ascending everywhere
                 if (a1 < a0) { const uint32_t t = a0; a0 = a1; a1 = t; }
                 continue;
             }
             uint32_t b0, b1;
             if (j >= 32) {
-                uint32_t *bb = buf + phase * (2 * R2_THREADS);
-                bb[tid] = a0; bb[tid + R2_THREADS] = a1;
+                uint32_t *bb = buf + phase * (2 * R2_H);
+                if (on) { bb[tid] = a0; bb[tid + R2_H] = a1; }
                 __syncthreads();
-                b0 = bb[tid ^ j]; b1 = bb[(tid ^ j) + R2_THREADS];
+                b0 = on ? bb[tid ^ j] : a0; b1 = on ? bb[(tid ^ j) + R2_H] : a1;
                 phase ^= 1;
             } else {
                 b0 = __shfl_xor_sync(0xffffffffu, a0, j); b1 = __shfl_xor_sync(0xffffffffu, a1, j);
             }
             const bool lower = (tid & j) == 0;
-            const bool asc0 = (tid & k) == 0, asc1 = ((tid + R2_THREADS) & k) == 0;
+            const bool asc0 = (tid & k) == 0, asc1 = ((tid + R2_H) & k) == 0;
             a0 = (lower == asc0) ? min(a0, b0) : max(a0, b0);
             a1 = (lower == asc1) ? min(a1, b1) : max(a1, b1);
         }
@@ -979,7 +982,7 @@ __global__ void __launch_bounds__(R2_THREADS, 2) route_fast2_kernel(RoutingView 
     uint32_t *bm = reinterpret_cast<uint32_t *>(rq_smem);                       // phase 8 (the class list is dead): position bitmap, prefix, sort buffers
     uint16_t *pref = reinterpret_cast<uint16_t *>(bm + nwp);
     uint32_t *key32 = reinterpret_cast<uint32_t *>(rq_smem + (((size_t)6 * nwp + 15) & ~(size_t)15));
-    int32_t *sid = reinterpret_cast<int32_t *>(key32 + 4 * R2_THREADS);
+    int32_t *sid = reinterpret_cast<int32_t *>(key32 + 4 * R2_H);
     int64_t *vbase_s = reinterpret_cast<int64_t *>(rq_smem + region);
     uint8_t *vs_s = reinterpret_cast<uint8_t *>(vbase_s + nvis);
     uint8_t *vlen_s = vs_s + nvis16;
@@ -996,8 +999,6 @@ __global__ void __launch_bounds__(R2_THREADS, 2) route_fast2_kernel(RoutingView 
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int64_t n_ids = rv.n_ids;
-    const int fshift = 32 - (31 - __clz(tbl * 4 - 1) + 1);
-    const uint32_t f2_off = (uint32_t)tbl >> 2;
     const bool vec_ok = (n_ids & 3) == 0;
     const int n4 = n_raw >> 2;
     const uint8_t *__restrict__ deleted = rv.deleted;
@@ -1018,25 +1019,31 @@ __global__ void __launch_bounds__(R2_THREADS, 2) route_fast2_kernel(RoutingView 
             for (int j = 0; j < 4; j++) if (id4[j] >= 0 && id4[j] < rv.n_deleted && deleted[id4[j]]) id4[j] = -2;
         }
     };
+    // Duplicate filter: tbl/2 32-bit words, each holding EIGHT 2-bit buckets of filter 1 (low half) and eight of filter 2 (high half).  An id
+    // picks the word and its filter-1 bucket from one multiplicative hash and its filter-2 bucket from another, so ONE shared atomic sets
+    // both "taken" bits and returns both old states, one predicated reduction sets the "taken twice" bits, and the classify pass tests
+    // both filters with one load.  (Two separate arrays -- route_fast_kernel -- need twice the atomics and loads for a slightly lower
+    // false-positive rate: 2.1 % vs 3.5 % of the positions at C2.)
     const uint32_t F_sa = (uint32_t)__cvta_generic_to_shared(F);
+    const int wshift = 32 - (31 - __clz(tbl >> 1));                             // tbl/2 words (a power of two)
+    auto filter_bits = [&](int32_t id, uint32_t &word) -> uint32_t {
+        const uint32_t h1 = (uint32_t)id * 0x9E3779B1u, h2 = (uint32_t)id * 0x85EBCA6Bu;
+        word = h1 >> wshift;
+        return (1u << (((h1 >> (wshift - 3)) & 7u) * 2u)) | (0x10000u << ((h2 >> 29) * 2u));
+    };
     auto filter_set = [&](int32_t id) {
-        const uint32_t h1 = ((uint32_t)id * 0x9E3779B1u) >> fshift, h2 = ((uint32_t)id * 0x85EBCA6Bu) >> fshift;
-        const uint32_t s1 = (h1 & 15u) * 2u, s2 = (h2 & 15u) * 2u;
-        const uint32_t a1 = F_sa + (h1 >> 4) * 4u, a2 = F_sa + (f2_off + (h2 >> 4)) * 4u;
-        // "taken" bit with the old value back; the "taken twice" bit only when it was taken already: a PREDICATED reduction (the C++ `if`
-        // around an atomic compiles to a divergent branch with convergence barriers, 6 extra instructions per id and filter)
-        uint32_t o1, o2;
-        asm volatile("atom.shared.or.b32 %0, [%1], %2;" : "=r"(o1) : "r"(a1), "r"(1u << s1) : "memory");
-        asm volatile("atom.shared.or.b32 %0, [%1], %2;" : "=r"(o2) : "r"(a2), "r"(1u << s2) : "memory");
-        asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p red.shared.or.b32 [%0], %1; }" ::"r"(a1), "r"(2u << s1), "r"((o1 >> s1) & 1u) : "memory");
-        asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p red.shared.or.b32 [%0], %1; }" ::"r"(a2), "r"(2u << s2), "r"((o2 >> s2) & 1u) : "memory");
+        uint32_t word;
+        const uint32_t bits = filter_bits(id, word), addr = F_sa + word * 4u;
+        uint32_t old;
+        asm volatile("atom.shared.or.b32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(bits) : "memory");
+        // (predicated: the C++ `if` around an atomic compiles to a divergent branch with convergence barriers)
+        asm volatile("{ .reg .pred p; setp.ne.u32 p, %1, 0; @p red.shared.or.b32 [%0], %1; }" ::"r"(addr), "r"((old & bits) << 1) : "memory");
     };
     auto filter_twice = [&](int32_t id) -> bool {                        // taken twice in BOTH filters: not provably a single occurrence
-        // both look-ups unconditionally: with 32 lanes some lane nearly always needs the second one, so a short-circuit only adds a branch
-        const uint32_t h1 = ((uint32_t)id * 0x9E3779B1u) >> fshift, h2 = ((uint32_t)id * 0x85EBCA6Bu) >> fshift;
-        return ((F[h1 >> 4] >> ((h1 & 15u) * 2u)) & (F[f2_off + (h2 >> 4)] >> ((h2 & 15u) * 2u)) & 2u) != 0;
+        uint32_t word;
+        const uint32_t bits = filter_bits(id, word);
+        return ((F[word] >> 1) & bits) == bits;
     };
-
     __shared__ int32_t s_q;
     for (;;) {
         __syncthreads();
@@ -1294,7 +1301,7 @@ __global__ void __launch_bounds__(R2_THREADS, 2) route_fast2_kernel(RoutingView 
         int my_e[2]; int32_t my_id[2]; uint32_t my_sc[2];
 #pragma unroll
         for (int u = 0; u < 2; u++) {
-            const int i = tid + u * R2_THREADS;
+            const int i = tid < R2_H ? tid + u * R2_H : m;
             my_e[u] = i < m ? (int)sel_pos[i] : -1;
             my_id[u] = i < m ? sel_id[i] : -1;
             my_sc[u] = i < m ? (uint32_t)sel_sc[i] : 0u;
@@ -1327,12 +1334,12 @@ __global__ void __launch_bounds__(R2_THREADS, 2) route_fast2_kernel(RoutingView 
                 sid[rank] = my_id[u];
             }
         }
-        if (sort_n == 2 * R2_THREADS) bitonic_sort32x2<2 * R2_THREADS>(a[0], a[1], tid, key32);
+        if (sort_n == 2 * R2_H) bitonic_sort32x2<2 * R2_H>(a[0], a[1], tid, key32);
         else bitonic_sort32x2<0>(a[0], a[1], tid, key32, sort_n);
         __syncthreads();
 #pragma unroll
         for (int u = 0; u < 2; u++) {
-            const int i = tid + u * R2_THREADS;
+            const int i = tid < R2_H ? tid + u * R2_H : want;
             if (i < want) { out_id[i] = sid[a[u] & ((1u << rb) - 1u)]; out_sc[i] = (int32_t)(a[u] >> (cb + rb)); }
         }
         if (tid == 0) { p.n_cand[q] = want; p.unique[q] = n_unique; p.raw_seen[q] = s_raw; }
@@ -1363,7 +1370,7 @@ bool route_fast_eligible(const RoutingView &rv, int probes, int64_t hard_cap, in
     // second-generation kernel (two CTAs per SM): B <= 1024 and a worklist of at least 1/8 of the positions
     Route2Layout L{};
     x.v2_smem = 0;
-    if (sort_n <= 2 * R2_THREADS && (int64_t)rv.TD * probes <= R2_THREADS && route2_layout(rv.TD, probes, (int)n_raw, tbl, L) &&
+    if (sort_n <= 2 * R2_H && (int64_t)rv.TD * probes <= R2_THREADS && route2_layout(rv.TD, probes, (int)n_raw, tbl, L) &&
         (L.wl_cap >= n_raw / 8 || L.wl_cap >= n_raw)) {
         x.v2_region = L.region; x.v2_cls_cap = L.cls_cap; x.v2_wl_cap = L.wl_cap; x.v2_smem = L.smem;
     }

@@ -68,15 +68,20 @@ int fspann_ctx_sync(fspann_ctx *ctx);
 int64_t fspann_ctx_launch_count(const fspann_ctx *ctx);
 
 /* Tuning / test switches: "route_general" = 1 forces the general Route kernel (sequential groups, exact HARD_CAP
- * semantics) even where the shared-memory fast path applies; "route_wl_extra" = n >= 0 clamps the fast path's dedicated
- * worklist to n entries (test hook for its overflow fallback), -1 = automatic; "tokengen_exact" = 1 runs the exact FP64 TokenGen
+ * semantics) even where the shared-memory fast path applies; "route_v1" = 1 keeps the fast path on its one-CTA-per-SM kernel (the
+ * default for refinementLimit <= 1024 is the two-CTA kernel, which hands the queries it cannot hold to the one-CTA kernel);
+ * "route_wl_extra" = n >= 0 clamps the fast path's dedicated worklist to n entries (test hook for the overflow fallbacks),
+ * -1 = automatic; "h2d_overlap" = n (default 2, 0 = off): the host-pointer search entries upload a batch of >= 4096 queries in n
+ * chunks on a copy stream so TokenGen + Route of a chunk overlap the PCIe copy of the next (with supplied codes: the whole query
+ * upload overlaps Route); "tokengen_exact" = 1 runs the exact FP64 TokenGen
  * kernel alone instead of a pre-filter + exact re-check; "tokengen_mode" = 0 (default) runs the pre-filter's contraction on the tensor
  * cores (tcgen05.mma on BF16-split operands, accumulator in TMEM) when the shape allows it, 2 = on the FP32 FMA pipe (the codes are
  * identical in every mode); "graphs" = 1 (default) lets a search of <= 64 queries replay its first pass (TokenGen .. counters and the
  * retry decision) as ONE captured CUDA graph from the third call with the same shape and buffers on (the second call captures; any upload,
  * key, option or buffer change drops the match), 0 = always launch kernel by kernel -- results are identical either way.  fspann_get_info:
  * "graph_captures" / "graph_replays" (how many such graphs were built / launched on this context), "last_tokengen_path" (1 exact, 2 FP32 pre-filter, 3 tensor-core pre-filter),
- * "last_route_path" (1 fast, 2 general), "route_treeified" (general path only: 1 if a bin of a query's bestScore map reached 9 entries in the
+ * "last_route_path" (1 fast, 2 general), "last_route_v2" (1: the two-CTA fast kernel ran), "route_overflowed" (queries of the last call it
+ * handed to the one-CTA kernel), (general path only: 1 if a bin of a query's bestScore map reached 9 entries in the
  * last call -- the JDK treeifies such a bin and its iteration order is not modelled), "sm_count", "build_treeified", "tokengen_rechecked" / "tokengen_overflow" (projections
  * the last TokenGen launch had to re-check exactly / whether its list overflowed and the exact kernel recomputed the batch). */
 int fspann_set_option(fspann_ctx *ctx, const char *name, int64_t value);
