@@ -1019,7 +1019,8 @@ __global__ void __launch_bounds__(R2_THREADS, 2) route_fast2_kernel(RoutingView 
             for (int j = 0; j < 4; j++) if (id4[j] >= 0 && id4[j] < rv.n_deleted && deleted[id4[j]]) id4[j] = -2;
         }
     };
-    // Duplicate filter: tbl/2 32-bit words, each holding EIGHT 2-bit buckets of filter 1 (low half) and eight of filter 2 (high half).  An id
+    // Duplicate filter: tbl/2 32-bit words, each holding EIGHT 2-bit buckets of filter 1 (low half: "taken" bits 0-7, "taken twice" bits 8-15)
+    // and eight of filter 2 (high half, same split).  An id
     // picks the word and its filter-1 bucket from one multiplicative hash and its filter-2 bucket from another, so ONE shared atomic sets
     // both "taken" bits and returns both old states, one predicated reduction sets the "taken twice" bits, and the classify pass tests
     // both filters with one load.  (Two separate arrays -- route_fast_kernel -- need twice the atomics and loads for a slightly lower
@@ -1029,7 +1030,7 @@ __global__ void __launch_bounds__(R2_THREADS, 2) route_fast2_kernel(RoutingView 
     auto filter_bits = [&](int32_t id, uint32_t &word) -> uint32_t {
         const uint32_t h1 = (uint32_t)id * 0x9E3779B1u, h2 = (uint32_t)id * 0x85EBCA6Bu;
         word = h1 >> wshift;
-        return (1u << (((h1 >> (wshift - 3)) & 7u) * 2u)) | (0x10000u << ((h2 >> 29) * 2u));
+        return (1u << ((h1 >> (wshift - 3)) & 7u)) | (0x10000u << (h2 >> 29));
     };
     auto filter_set = [&](int32_t id) {
         uint32_t word;
@@ -1037,12 +1038,12 @@ __global__ void __launch_bounds__(R2_THREADS, 2) route_fast2_kernel(RoutingView 
         uint32_t old;
         asm volatile("atom.shared.or.b32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(bits) : "memory");
         // (predicated: the C++ `if` around an atomic compiles to a divergent branch with convergence barriers)
-        asm volatile("{ .reg .pred p; setp.ne.u32 p, %1, 0; @p red.shared.or.b32 [%0], %1; }" ::"r"(addr), "r"((old & bits) << 1) : "memory");
+        asm volatile("{ .reg .pred p; setp.ne.u32 p, %1, 0; @p red.shared.or.b32 [%0], %1; }" ::"r"(addr), "r"((old & bits) << 8) : "memory");
     };
     auto filter_twice = [&](int32_t id) -> bool {                        // taken twice in BOTH filters: not provably a single occurrence
         uint32_t word;
         const uint32_t bits = filter_bits(id, word);
-        return ((F[word] >> 1) & bits) == bits;
+        return ((F[word] >> 8) & bits) == bits;
     };
     __shared__ int32_t s_q;
     for (;;) {
