@@ -82,12 +82,29 @@ def test_search_matches_oracle_sample_and_is_invariant_under_rotate_migrate(c2):
     g = O.GFunctions(cfg.dim, cfg.T, cfg.D, cfg.m, cfg.lam, c2["alpha"], c2["r"], c2["omega"])
     ix = O.Index(g, cfg.N, c2["mn"].shape[1], c2["mn"], c2["mx"], c2["rep"], c2["ids"])
     st = O.Store(cfg.dim, c2["iv"], c2["ct"], np.ones(cfg.N, dtype=np.int32), {1: c2["km"].derive(1)})
-    codes = O.tokengen_batch(q[:24], g)
-    assert np.array_equal(gpu.tokengen_batch(q[:24]), codes)
-    for i in range(24):
+    NS = 400                                                                                # oracle sample (the C port does ~190 queries/s per core)
+    codes = O.tokengen_batch(q[:NS], g)
+    assert np.array_equal(gpu.tokengen_batch(q[:NS]), codes)
+    for i in range(NS):
         ref = O.search(ix, st, q[i], codes[i], k, cfg.probes, cfg.hard_cap, cfg.B)
         assert np.array_equal(got["top_ids"][i], ref["top_ids"])
         assert np.array_equal(got["top_dist"][i].view(np.uint64), ref["top_dist"].view(np.uint64))
+        c = got["counters"][i]
+        assert (c[0], c[1], c[2], c[3], bool(c[4])) == (ref["cand_total"], ref["cand_kept"], ref["cand_decrypted"], ref["returned"], ref["retried"])
+    # a full 10k-query batch takes the chunked, overlapped upload of the host entry (>= 4096 queries): same answers as 2000 at a time,
+    # and as the plain single-copy upload
+    q10 = WL.query_vectors(cfg, 10000)
+    full = gpu.search_batch(q10, k, cfg.probes, cfg.hard_cap, cfg.B)
+    for b0 in (0, 4000, 8000):
+        part = gpu.search_batch(q10[b0:b0 + 2000], k, cfg.probes, cfg.hard_cap, cfg.B)
+        for key in ("top_ids", "n_ret", "counters"):
+            assert np.array_equal(part[key], full[key][b0:b0 + 2000]), key
+        assert np.array_equal(part["top_dist"].view(np.uint64), full["top_dist"][b0:b0 + 2000].view(np.uint64))
+    gpu.set_option("h2d_overlap", 0)
+    plain = gpu.search_batch(q10, k, cfg.probes, cfg.hard_cap, cfg.B)
+    gpu.set_option("h2d_overlap", 2)
+    assert np.array_equal(plain["top_ids"], full["top_ids"]) and np.array_equal(plain["counters"], full["counters"])
+    assert gpu.get_info("last_route_v2") == 1 and gpu.get_info("route_overflowed") == 0     # the two-CTA Route kernel held every query
     # config 5: Rotate -> v2, Migrate ids = 0 (mod 3) on the device with fresh IVs; then Rotate -> v3 and Migrate the touched set
     gpu.touched(clear=True)
     gpu.keys_set(2, c2["km"].derive(2))
@@ -132,3 +149,38 @@ def test_groundtruth_and_recall_at_full_size(c2):
         for pos in np.nonzero(hit)[0]:
             gi = int(np.nonzero(gt[i] == res["top_ids"][i][pos])[0][0])
             assert res["top_dist"][i][pos] == np.sqrt(d2[i][gi])
+
+
+def test_config3_shape_at_full_size_matches_oracle_sample():
+    """BASELINE configs[2] (GloVe-shape 1.2 M x 100, non-integer data: the FP64 distance path, 800-byte records) at full size: device
+    Setup, a 10k-query batch, oracle sample with counters."""
+    from fspann_query_system_b200.gpu import GpuContext
+    cfg = WL.CONFIGS["C3"]
+    base = WL.base_vectors(cfg)
+    alpha, r, omega = HS.build_gfunctions(base[:HS.MIN_SAMPLE_SIZE], cfg.m, cfg.lam, cfg.seed, cfg.T, cfg.D)
+    gpu = GpuContext(0)
+    try:
+        gpu.gfunctions_upload(cfg.dim, cfg.T, cfg.D, cfg.m, cfg.lam, alpha, r, omega)
+        mn, mx, rep, ids = gpu.routing_build(base, HS.staged_order(cfg.N))
+        km = HS.KeyManager(WL.MASTER_KEY)
+        iv = WL.record_ivs(cfg.N, cfg.base_seed + 5)
+        gpu.keys_set(1, km.derive(1))
+        ct = gpu.encrypt_batch(np.arange(cfg.N, dtype=np.int32), base, iv, 1)
+        gpu.store_upload(cfg.dim, iv, ct, np.ones(cfg.N, dtype=np.int32))
+        q = WL.query_vectors(cfg, 10000)
+        got = gpu.search_batch(q, cfg.k, cfg.probes, cfg.hard_cap, cfg.B)
+        assert (np.diff(got["top_dist"], axis=1)[got["n_ret"] == cfg.k] >= 0).all()
+        g = O.GFunctions(cfg.dim, cfg.T, cfg.D, cfg.m, cfg.lam, alpha, r, omega)
+        ix = O.Index(g, cfg.N, mn.shape[1], mn, mx, rep, ids)
+        st = O.Store(cfg.dim, iv, ct, np.ones(cfg.N, dtype=np.int32), {1: km.derive(1)})
+        sample = np.r_[0:100, 5000:5100, 9900:10000]
+        codes = O.tokengen_batch(q[sample], g)
+        for j, i in enumerate(sample):
+            ref = O.search(ix, st, q[i], codes[j], cfg.k, cfg.probes, cfg.hard_cap, cfg.B)
+            n = len(ref["top_ids"])
+            assert got["n_ret"][i] == n and np.array_equal(got["top_ids"][i, :n], ref["top_ids"])
+            assert np.array_equal(got["top_dist"][i, :n].view(np.uint64), ref["top_dist"].view(np.uint64))
+            c = got["counters"][i]
+            assert (c[0], c[1], c[2], c[3], bool(c[4])) == (ref["cand_total"], ref["cand_kept"], ref["cand_decrypted"], ref["returned"], ref["retried"])
+    finally:
+        gpu.close()
