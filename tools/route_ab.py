@@ -17,6 +17,9 @@ def main():
     name = sys.argv[1] if len(sys.argv) > 1 else "C2"
     cfg = getattr(WL, name)
     gpu = GpuContext(0)
+    for a in sys.argv[2:]:                                     # further library options: name=value
+        k_, v_ = a.split("=")
+        gpu.set_option(k_, int(v_))
     world, batches = bench.build_world(cfg, gpu, 3, 0, quiet=True)
     Q, k = batches[0].shape[0], cfg.k
     run = bench.DevRunner(gpu, torch, 0, Q, k)
