@@ -147,14 +147,26 @@ int do_route(fspann_ctx *ctx, int64_t Q, const uint64_t *d_codes, int probes, in
     if (!ctx->opt_route_general && route_fast_eligible(rv, probes, hard_cap, B, fx, fsmem)) {
         if (ctx->opt_route_wl_extra >= 0 && fx.wl_extra > ctx->opt_route_wl_extra) fx.wl_extra = ctx->opt_route_wl_extra & ~7;   // smem size kept
         if (ctx->opt_route_wl_extra >= 0 && fx.v2_wl_cap > ctx->opt_route_wl_extra) fx.v2_wl_cap = std::max(16, ctx->opt_route_wl_extra & ~15);
-        if (ctx->opt_route_v1) fx.v2_smem = 0;
+        if (ctx->opt_route_v1 && fx.v1_ok) fx.v2_smem = 0;
         ENSURE(ctx->s_route_ovf, sizeof(int32_t) * ((size_t)Q + 4));
         fx.ovf_n = (int32_t *)ctx->s_route_ovf.p; fx.ovf_list = fx.ovf_n + 4;
         ENSURE(ctx->s_vis_part, sizeof(int32_t) * (size_t)Q * rv.TD * probes);
         ENSURE(ctx->s_vis_score, (size_t)Q * rv.TD * probes);
         ENSURE(ctx->s_vis_n, (size_t)Q * rv.TD);
+        if (fx.v2_smem && fx.v2_big) { ENSURE(ctx->s_route_big, sizeof(unsigned long long) * (size_t)Q * B); fx.big_keys = (unsigned long long *)ctx->s_route_big.p; }
+        RouteParams pg = p;
+        int grid_g = 0;
+        if (fx.v2_smem && !fx.v1_ok) {                                      // the general kernel serves what the two-CTA kernel hands back
+            pg.scratch_ints = route_scratch_ints(pg.cap0, pg.max_nodes);
+            grid_g = std::min(route_grid(Q, ctx->sm_count), 64);           // few queries overflow: bound the scratch
+            ENSURE(ctx->s_route_scratch, sizeof(int32_t) * (size_t)pg.scratch_ints * grid_g);
+            ENSURE(ctx->s_overflow, sizeof(int32_t));
+            CK(cudaMemsetAsync(ctx->s_overflow.p, 0, sizeof(int32_t), ctx->stream));
+            pg.scratch = (int32_t *)ctx->s_route_scratch.p;
+            pg.chain_overflow = (int32_t *)ctx->s_overflow.p;
+        }
         LAUNCHED(launch_route_fast(ctx->stream, rv, p, fx, fsmem, ctx->sm_count, (int32_t *)ctx->s_vis_part.p, (uint8_t *)ctx->s_vis_score.p,
-                                   (uint8_t *)ctx->s_vis_n.p));
+                                   (uint8_t *)ctx->s_vis_n.p, &pg, grid_g));
         ctx->last_route_v2 = fx.v2_smem != 0;
         ctx->last_route_path = 1;
         return 0;
@@ -268,7 +280,7 @@ void fspann_ctx_destroy(fspann_ctx *ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->d_alpha_f, &ctx->d_alpha_norm, &ctx->d_alpha_tc, &ctx->s_vorder, &ctx->s_voff, &ctx->s_qfinite, &ctx->s_retry_out, &ctx->s_codes_in, &ctx->s_tg_work, &ctx->s_tg_list, &ctx->s_tg_qf, &ctx->s_tg_norm, &ctx->d_alpha, &ctx->d_r, &ctx->d_omega, &ctx->d_keys, &ctx->d_rep, &ctx->d_ids, &ctx->d_deleted, &ctx->d_rec,
                       &ctx->d_keyring, &ctx->d_hpow, &ctx->d_shoup, &ctx->s_rec_verdict, &ctx->s_qf32, &ctx->s_qu8, &ctx->s_f32_exact, &ctx->d_te0, &ctx->d_touched, &ctx->s_queries, &ctx->s_codes, &ctx->s_cand_ids,
-                      &ctx->s_cand_sc, &ctx->s_ncand, &ctx->s_raw, &ctx->s_uniq_cnt, &ctx->s_route_scratch, &ctx->s_overflow, &ctx->s_route_ovf, &ctx->s_cnt,
+                      &ctx->s_cand_sc, &ctx->s_ncand, &ctx->s_raw, &ctx->s_uniq_cnt, &ctx->s_route_scratch, &ctx->s_overflow, &ctx->s_route_ovf, &ctx->s_route_big, &ctx->s_cnt,
                       &ctx->s_flag, &ctx->s_fill, &ctx->s_uniq, &ctx->s_uoff, &ctx->s_pairs, &ctx->s_bsums, &ctx->s_totals, &ctx->s_dist, &ctx->s_verdict,
                       &ctx->s_topk_ids, &ctx->s_topk_dist, &ctx->s_topk_rank, &ctx->s_nret, &ctx->s_ndec, &ctx->s_counters, &ctx->s_stage_a, &ctx->s_stage_b,
                       &ctx->s_stage_c, &ctx->s_vis_part, &ctx->s_vis_score, &ctx->s_vis_n, &ctx->r_rows, &ctx->r_queries, &ctx->r_codes, &ctx->r_topk_ids, &ctx->r_topk_dist, &ctx->r_nret,

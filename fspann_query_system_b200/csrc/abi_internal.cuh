@@ -57,7 +57,7 @@ struct fspann_ctx {
     int opt_route_wl_extra = -1; // test hook: clamp the fast path's dedicated worklist (forces the no-worklist fallback when exceeded)
     int last_route_path = 0;     // 1 = shared-memory fast path, 2 = general path
     bool last_queries_finite = true;
-    DevBuf s_queries, s_codes, s_cand_ids, s_cand_sc, s_ncand, s_raw, s_uniq_cnt, s_route_scratch, s_overflow, s_route_ovf;
+    DevBuf s_queries, s_codes, s_cand_ids, s_cand_sc, s_ncand, s_raw, s_uniq_cnt, s_route_scratch, s_overflow, s_route_ovf, s_route_big;
     DevBuf s_rec_verdict, s_qf32, s_qu8, s_f32_exact, s_vorder, s_voff, s_qfinite, s_retry_out, s_codes_in;
     DevKeyRing ring_host{};
     int32_t *want_rank = nullptr;

@@ -68,6 +68,7 @@ struct RouteParams {
     int32_t *scratch;    // [grid][scratch_ints]
     int64_t scratch_ints;
     int32_t *chain_overflow;  // set when a bucket chain reached 9 (Java would treeify; order then unspecified)
+    const int32_t *qlist, *qlist_n;   // general kernel: serve these queries only (nullptr = all)
 };
 
 struct RouteFastExtra {
@@ -81,6 +82,9 @@ struct RouteFastExtra {
     // route_fast2_kernel (two CTAs per SM): 0 = not eligible
     size_t v2_smem;
     int v2_region, v2_cls_cap, v2_wl_cap;
+    int v2_big;                           // refinementLimit > 1024: the selected keys go to big_keys, route_sort_big_kernel orders them
+    int v1_ok, tbl1;                      // route_fast_kernel is eligible (non-binding HARD_CAP, state fits) with tbl1 table slots
+    unsigned long long *big_keys;         // [Q][B] (score | Java bucket | position)
     int32_t *ovf_n, *ovf_list;            // queries route_fast2_kernel hands to route_fast_kernel
     const int32_t *qlist, *qlist_n;       // route_fast_kernel: serve these queries only (nullptr = all)
 };
@@ -164,7 +168,7 @@ int launch_route(cudaStream_t s, const RoutingView &rv, const RouteParams &p, in
 int route_grid(int64_t Q, int sm_count);
 bool route_fast_eligible(const RoutingView &rv, int probes, int64_t hard_cap, int B, RouteFastExtra &x, size_t &smem);
 int launch_route_fast(cudaStream_t s, const RoutingView &rv, const RouteParams &p, RouteFastExtra x, size_t smem, int sm_count,
-                      int32_t *vis_part, uint8_t *vis_score, uint8_t *vis_n);
+                      int32_t *vis_part, uint8_t *vis_score, uint8_t *vis_n, const RouteParams *pg, int grid_g);
 int64_t route_scratch_ints(int32_t cap0, int32_t max_nodes);
 int launch_refine_group(cudaStream_t s, const StoreView &sv, const RefineParams &p);
 int launch_refine_verify(cudaStream_t s, const StoreView &sv, const RefineParams &p, int sm_count);

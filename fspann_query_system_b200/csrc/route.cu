@@ -105,7 +105,9 @@ __global__ void __launch_bounds__(RT_THREADS) route_kernel(RoutingView rv, Route
     sc.cl_id = sc.nnext + p.max_nodes;
     sc.cl_sc = sc.cl_id + p.max_nodes;
 
-    for (int64_t q = blockIdx.x; q < p.Q; q += gridDim.x) {
+    const int64_t n_q = p.qlist ? (int64_t)*p.qlist_n : p.Q;          // all queries, or the list the fast kernels could not hold
+    for (int64_t qi = blockIdx.x; qi < n_q; qi += gridDim.x) {
+        const int64_t q = p.qlist ? (int64_t)p.qlist[qi] : qi;
         const uint64_t *qcodes = p.codes + (size_t)q * TD * W;
         __syncthreads();
         // ---- 0. reset ----
@@ -916,7 +918,7 @@ static bool route2_layout(int TD, int probes, int n_raw, int tbl, Route2Layout &
     const int nbm = ((n_raw + 31) / 32 + 3) / 4 * 4;
     L.region = std::max(2 * tbl, 28672);
     L.cls_cap = std::min(n_raw, ((L.region - R2_SELBYTES) / 4) & ~7);
-    const size_t fixed = (size_t)L.region + sizeof(int64_t) * nvis + 2 * (size_t)nvis16 + 2 * sizeof(uint16_t) * (size_t)nvis16 + sizeof(uint32_t) * (size_t)nbm + 64;
+    const size_t fixed = (size_t)L.region + sizeof(int64_t) * nvis + 2 * (size_t)nvis16 + 3 * sizeof(uint16_t) * (size_t)nvis16 + sizeof(uint32_t) * (size_t)nbm + 64;
     const size_t limit = 114432;                                       // 2 x (dynamic + 1.2 KB static + 1 KB reserve) <= 228 KB per SM
     if (fixed + 9 * 1024 > limit) return false;
     int64_t cap = (int64_t)(limit - fixed) / 9;
@@ -964,7 +966,7 @@ __device__ __forceinline__ void bitonic_sort32x2(uint32_t &a0, uint32_t &a1, int
     }
 }
 
-template <bool HAS_DEL>
+template <bool HAS_DEL, bool BIG>
 __global__ void __launch_bounds__(R2_THREADS, 2) route_fast2_kernel(RoutingView rv, RouteParams p, RouteFastExtra x) {
     extern __shared__ __align__(16) unsigned char rq_smem[];
     const int TD = rv.TD, probes = p.probes, n_raw = x.n_raw, tbl = x.tbl, sort_n = x.sort_n, nvis = TD * probes;
@@ -988,14 +990,15 @@ __global__ void __launch_bounds__(R2_THREADS, 2) route_fast2_kernel(RoutingView 
     uint8_t *vlen_s = vs_s + nvis16;
     uint16_t *lowvis_s = reinterpret_cast<uint16_t *>(vlen_s + nvis16);
     uint16_t *inv_cnt = lowvis_s + nvis16;
-    uint32_t *inv_bm = reinterpret_cast<uint32_t *>(inv_cnt + nvis16);
+    uint16_t *rep_cnt = inv_cnt + nvis16;                                      // per visit: first occurrences of duplicated ids (HARD_CAP accounting)
+    uint32_t *inv_bm = reinterpret_cast<uint32_t *>(rep_cnt + nvis16);
     const int nbm = ((n_raw + 31) / 32 + 3) / 4 * 4;
     int32_t *wl_id = reinterpret_cast<int32_t *>(inv_bm + nbm);
     uint16_t *wl_pos = reinterpret_cast<uint16_t *>(wl_id + wl_cap);
     uint16_t *wl_next = wl_pos + wl_cap;
     uint8_t *wl_best = reinterpret_cast<uint8_t *>(wl_next + wl_cap);
     __shared__ int32_t s_hist[256];
-    __shared__ int32_t s_raw, s_uniq, s_m, s_ncls, s_nwl, s_nlow, s_pick[3], s_wsum[32];
+    __shared__ int32_t s_raw, s_uniq, s_m, s_ncls, s_nwl, s_nlow, s_pick[3], s_wsum[32], s_cut;
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int64_t n_ids = rv.n_ids;
@@ -1064,7 +1067,7 @@ __global__ void __launch_bounds__(R2_THREADS, 2) route_fast2_kernel(RoutingView 
         }
         for (int i = tid; i < tbl / 8; i += R2_THREADS) reinterpret_cast<uint4 *>(F)[i] = make_uint4(0, 0, 0, 0);
         for (int i = tid; i < nbm; i += R2_THREADS) inv_bm[i] = 0u;
-        for (int i = tid; i < nvis16 / 2; i += R2_THREADS) reinterpret_cast<uint32_t *>(inv_cnt)[i] = 0u;
+        for (int i = tid; i < nvis16; i += R2_THREADS) reinterpret_cast<uint32_t *>(inv_cnt)[i] = 0u;       // inv_cnt and rep_cnt
         if (tid < 256) s_hist[tid] = 0;
         if (tid == 0) { s_raw = 0; s_uniq = 0; s_m = 0; s_ncls = 0; s_nwl = 0; s_nlow = 0; }
         __syncthreads();
@@ -1133,10 +1136,6 @@ __global__ void __launch_bounds__(R2_THREADS, 2) route_fast2_kernel(RoutingView 
         }
         fits = __syncthreads_and(fits ? 1 : 0) != 0;
         const int n_inv = s_nwl;
-        if (fits && tid < nvis) {                                          // the singles of visit `tid` share its score
-            const int singles = (int)vlen_s[tid] - (int)inv_cnt[tid];
-            if (singles > 0) { atomicAdd(&s_hist[vs_s[tid]], singles); my_raw += singles; my_uniq += singles; }
-        }
         // ---- 4. exact path over the worklist (see route_fast_kernel; links and table entries are worklist slots) ----
         if (fits && n_inv > 0) {
             int tslots = 2 * n_inv <= 1024 ? 1024 : 1 << (32 - __clz(2 * n_inv - 1));
@@ -1171,8 +1170,24 @@ __global__ void __launch_bounds__(R2_THREADS, 2) route_fast2_kernel(RoutingView 
                 }
             }
             __syncthreads();
+        }
+        // ---- 4b. per-id statistics (+ HARD_CAP).  Pass 0 looks at every visit; it also counts, per visit, the ids that occur there FIRST
+        //      (singles + first occurrences of duplicated ids) = by how much that poll grows bestScore.  The reference polls a partition only
+        //      while bestScore.size() < HARD_CAP (PIS:657-659; the same test guards every table and division, PIS:624-628) and then adds it
+        //      whole, so the visits from the first one that finds the map full are never made: when there is such a visit, pass 1 repeats
+        //      the statistics over the visits before it (first occurrences and improvement counts do not depend on later visits; the
+        //      minimum score of an id does). ----
+        int cut_v = nvis;
+        for (int pass = 0; fits && pass < 2; pass++) {
+            const uint32_t cutoff = (uint32_t)cut_v * kBlock;
+            my_raw = 0; my_uniq = 0;
+            if (tid < cut_v) {                                             // the singles of visit `tid` share its score
+                const int singles = (int)vlen_s[tid] - (int)inv_cnt[tid];
+                if (singles > 0) { atomicAdd(&s_hist[vs_s[tid]], singles); my_raw += singles; my_uniq += singles; }
+            }
             for (int i = tid; i < n_inv; i += R2_THREADS) {
                 const uint32_t e = wl_pos[i];
+                if (e >= cutoff) { wl_best[i] = 255; continue; }
                 const uint32_t sc = vs_s[e >> 6];
                 uint32_t lk = wl_next[i];
                 while (!(lk & 0x8000u)) lk = wl_next[lk];
@@ -1180,7 +1195,8 @@ __global__ void __launch_bounds__(R2_THREADS, 2) route_fast2_kernel(RoutingView 
                 uint32_t first = 0xffffu, best = 255; bool low = true;
                 for (uint32_t y = head;;) {
                     const uint32_t ey = wl_pos[y], sy = vs_s[ey >> 6];
-                    first = min(first, ey); best = min(best, sy);
+                    first = min(first, ey);
+                    if (ey < cutoff) best = min(best, sy);
                     if (ey < e && sy <= sc) low = false;
                     const uint32_t ny = wl_next[y];
                     if (ny & 0x8000u) break;
@@ -1188,9 +1204,29 @@ __global__ void __launch_bounds__(R2_THREADS, 2) route_fast2_kernel(RoutingView 
                 }
                 my_raw += low;
                 const bool is_rep = first == e;
-                if (is_rep) { atomicAdd(&s_hist[best], 1); my_uniq++; }
+                if (is_rep) {
+                    atomicAdd(&s_hist[best], 1); my_uniq++;
+                    if (pass == 0) atomicAdd(reinterpret_cast<unsigned int *>(rep_cnt) + (e >> 7), 1u << (((e >> 6) & 1) * 16));
+                }
                 wl_best[i] = (uint8_t)(is_rep ? (RQ_DUP | best) : 255u);
             }
+            if (pass == 1 || p.hard_cap > (int64_t)n_raw - kBlock) break;      // the re-count is done / the cap cannot bind (block-uniform)
+            __syncthreads();
+            const int nu = tid < nvis ? (int)vlen_s[tid] - (int)inv_cnt[tid] + (int)rep_cnt[tid] : 0;
+            int tot;
+            const int ex = warp_excl_scan(nu, lane, tot);
+            if (lane == 31) s_wsum[tid >> 5] = ex + nu;
+            if (tid == 0) s_cut = nvis;
+            __syncthreads();
+            int before = ex;                                               // bestScore.size() when visit `tid` is about to be polled
+            for (int w = 0; w < (tid >> 5); w++) before += s_wsum[w];
+            if (tid < nvis && (int64_t)before >= p.hard_cap) atomicMin(&s_cut, tid);
+            __syncthreads();
+            cut_v = s_cut;
+            if (cut_v >= nvis) break;
+            if (tid < 256) s_hist[tid] = 0;
+            if (tid >= cut_v && tid < nvis) vlen_s[tid] = 0;                // the selection scan below skips the visits that were never made
+            __syncthreads();
         }
 #pragma unroll
         for (int o = 16; o; o >>= 1) { my_raw += __shfl_xor_sync(0xffffffffu, my_raw, o); my_uniq += __shfl_xor_sync(0xffffffffu, my_uniq, o); }
@@ -1211,10 +1247,12 @@ __global__ void __launch_bounds__(R2_THREADS, 2) route_fast2_kernel(RoutingView 
         const int sb = 32 - __clz(sstar);
         const int rb = sort_n <= 1 ? 0 : 32 - __clz(sort_n - 1);
         // what this kernel does not hold: more involved positions than worklist slots, a cut class beyond its list, keys wider than 32 bits
-        if (!fits || (need_levels && cls_n_expected > cls_cap) || sb + cb + rb > 32 || capF > 65536u) {
-            if (tid == 0) x.ovf_list[atomicAdd(x.ovf_n, 1)] = (int32_t)q;
+        if (!fits || (need_levels && cls_n_expected > cls_cap) || (!BIG && sb + cb + rb > 32) || capF > 65536u) {
+            if (tid == 0) { x.ovf_list[atomicAdd(x.ovf_n, 1)] = (int32_t)q; p.n_cand[q] = 0; }
             continue;
         }
+        // BIG (refinementLimit > 1024): the selected entries leave as 64-bit keys (score | Java bucket | position) and route_sort_big_kernel orders them
+        unsigned long long *big = BIG ? x.big_keys + (size_t)q * p.B : nullptr;
         // ---- 6. scan the positions that can hold a score <= s*: the visits with score <= s* (singles; ids re-read) and the worklist ----
         {
             bool low = false;
@@ -1243,7 +1281,9 @@ __global__ void __launch_bounds__(R2_THREADS, 2) route_fast2_kernel(RoutingView 
                 const bool below = sc < sstar || (sc == sstar && !need_levels && sc != 255u);
                 const bool incls = need_levels && sc == sstar && sc != 255u;
                 const int a = list_slot(&s_m, below, lane);
-                if (below && a < sort_n) { sel_id[a] = id; sel_pos[a] = (uint16_t)e; sel_sc[a] = (uint8_t)sc; }
+                if (BIG) {
+                    if (below && a < p.B) big[a] = ((unsigned long long)sc << 40) | ((unsigned long long)(java_hash_decimal(id) & (capF - 1u)) << 16) | (unsigned long long)e;
+                } else if (below && a < sort_n) { sel_id[a] = id; sel_pos[a] = (uint16_t)e; sel_sc[a] = (uint8_t)sc; }
                 const int c = list_slot(&s_ncls, incls, lane);
                 if (incls) { cls_pos[c] = (uint16_t)e; cls_hash[c] = (uint16_t)(java_hash_decimal(id) & 0xffffu); }
             }
@@ -1289,12 +1329,18 @@ __global__ void __launch_bounds__(R2_THREADS, 2) route_fast2_kernel(RoutingView 
                     take_it = (key2 >> sel_shift) <= prefix;
                 }
                 const int a = list_slot(&s_m, take_it, lane);
-                if (take_it && a < sort_n) {
+                if (BIG) {
+                    if (take_it && a < p.B) big[a] = ((unsigned long long)sstar << 40) | ((unsigned long long)((uint32_t)cls_hash[i] & (capF - 1u)) << 16) | (unsigned long long)e;
+                } else if (take_it && a < sort_n) {
                     sel_id[a] = __ldg(rv.ids + vbase_s[e >> 6] + (e & 63));    // the id at a position (single or first occurrence alike)
                     sel_pos[a] = (uint16_t)e; sel_sc[a] = (uint8_t)sstar;
                 }
             }
             __syncthreads();
+        }
+        if (BIG) {
+            if (tid == 0) { p.n_cand[q] = want; p.unique[q] = n_unique; p.raw_seen[q] = s_raw; }
+            continue;
         }
         // ---- 8. 32-bit keys (score | Java bucket | rank of the position among the selected), two per thread, key-only bitonic sort ----
         const int m = min(s_m, sort_n);
@@ -1347,59 +1393,170 @@ __global__ void __launch_bounds__(R2_THREADS, 2) route_fast2_kernel(RoutingView 
     }
 }
 
+// Orders the candidates route_fast2_kernel<.., BIG> selected: one CTA per query, E 64-bit keys (score | Java bucket | position) per thread,
+// element i = u * RS_THREADS + tid lives in register u of thread tid.  Bitonic network: strides >= RS_THREADS pair two registers of one
+// thread, strides 32..512 go through shared memory (consecutive lanes touch consecutive words: conflict-free), strides < 32 are warp
+// shuffles.  Then the id of every position is read back from the partition rows.
+constexpr int RS_THREADS = 1024;
+
+template <int E>
+__global__ void __launch_bounds__(RS_THREADS, 1) route_sort_big_kernel(RoutingView rv, RouteParams p, RouteFastExtra x) {
+    extern __shared__ __align__(16) unsigned char rs_smem[];
+    unsigned long long *sk = reinterpret_cast<unsigned long long *>(rs_smem);
+    const int tid = threadIdx.x, TD = rv.TD, probes = p.probes;
+    constexpr int n = E * RS_THREADS;
+    for (int64_t q = blockIdx.x; q < p.Q; q += gridDim.x) {
+        const int m = p.n_cand[q];
+        if (m <= 0) continue;                                            // empty, or handed to the fallback kernel (block-uniform)
+        const unsigned long long *src = x.big_keys + (size_t)q * p.B;
+        unsigned long long a[E];
+#pragma unroll
+        for (int u = 0; u < E; u++) { const int i = u * RS_THREADS + tid; a[u] = i < m ? src[i] : ~0ull; }
+#pragma unroll 1
+        for (int k = 2; k <= n; k <<= 1) {
+            // strides inside the thread: j = jl * RS_THREADS pairs registers u and u | jl
+#pragma unroll
+            for (int jl = E / 2; jl > 0; jl >>= 1) {
+                if (jl * RS_THREADS < k) {
+#pragma unroll
+                    for (int u = 0; u < E; u++) {
+                        if ((u & jl) == 0) {
+                            const bool asc = ((u * RS_THREADS + tid) & k) == 0;
+                            const unsigned long long lo = min(a[u], a[u | jl]), hi = max(a[u], a[u | jl]);
+                            a[u] = asc ? lo : hi; a[u | jl] = asc ? hi : lo;
+                        }
+                    }
+                }
+            }
+#pragma unroll 1
+            for (int j = min(k >> 1, RS_THREADS >> 1); j >= 32; j >>= 1) {  // partner in another warp: through shared memory
+                __syncthreads();
+#pragma unroll
+                for (int u = 0; u < E; u++) sk[u * RS_THREADS + tid] = a[u];
+                __syncthreads();
+                const bool lower = (tid & j) == 0;
+#pragma unroll
+                for (int u = 0; u < E; u++) {
+                    const unsigned long long b = sk[u * RS_THREADS + (tid ^ j)];
+                    const bool asc = ((u * RS_THREADS + tid) & k) == 0;
+                    a[u] = (lower == asc) ? min(a[u], b) : max(a[u], b);
+                }
+            }
+#pragma unroll 1
+            for (int j = min(k >> 1, 16); j > 0; j >>= 1) {                 // partner in the same warp
+                const bool lower = (tid & j) == 0;
+#pragma unroll
+                for (int u = 0; u < E; u++) {
+                    const unsigned long long b = __shfl_xor_sync(0xffffffffu, a[u], j);
+                    const bool asc = ((u * RS_THREADS + tid) & k) == 0;
+                    a[u] = (lower == asc) ? min(a[u], b) : max(a[u], b);
+                }
+            }
+        }
+        int32_t *out_id = p.cand_ids + (size_t)q * p.B, *out_sc = p.cand_scores + (size_t)q * p.B;
+#pragma unroll
+        for (int u = 0; u < E; u++) {
+            const int i = u * RS_THREADS + tid;
+            if (i < m) {
+                const uint32_t e = (uint32_t)(a[u] & 0xffffull), v = e >> 6;
+                const int g = (int)v / probes, jv = (int)v - g * probes;
+                const int64_t part = x.vis_part[(q * TD + g) * probes + jv];
+                out_id[i] = __ldg(rv.ids + (int64_t)g * rv.n_ids + part * kBlock + (e & 63u));
+                out_sc[i] = (int32_t)(a[u] >> 40);
+            }
+        }
+        __syncthreads();
+    }
+}
+
 bool route_fast_eligible(const RoutingView &rv, int probes, int64_t hard_cap, int B, RouteFastExtra &x, size_t &smem) {
+    x.v1_ok = 0; x.v2_smem = 0; x.v2_big = 0;
     if (probes < 1) return false;
     const int64_t n_raw = (int64_t)rv.TD * probes * kBlock;
     if (n_raw > 32000) return false;                         // positions and slots carry a 1-bit tag in 16 bits
-    if (n_raw - kBlock >= hard_cap) return false;          // the cap could bind: needs the sequential path
     if (rv.m * rv.lambda > 126) return false;               // scores are packed into 7 bits (see best_s encoding)
     if ((int64_t)rv.TD * probes > RQ_THREADS) return false;
-    int sort_n = 64; while (sort_n < B) sort_n <<= 1;
+    int sort_n = 64; while (sort_n < B && sort_n < (1 << 20)) sort_n <<= 1;
     int tbl = 1024; while (tbl < n_raw + n_raw / 4) tbl <<= 1;
     if (tbl > 32768) return false;
-    if (tbl < n_raw + sort_n) tbl <<= 1;                    // room for the class list and the selection list
-    if (tbl > 32768) return false;
-    const size_t limit = 227 * 1024 - 2048;
-    const size_t base = route_fast_smem(rv.TD, probes, (int)n_raw, tbl, sort_n, 0);
-    if (base > limit) return false;
-    // worklist of involved positions: wl_extra dedicated entries + the 6*sort_n that overlay skey / sid
-    int64_t wl_extra = std::max<int64_t>(0, n_raw - 6 * sort_n);
-    wl_extra = std::min<int64_t>(wl_extra, (int64_t)(limit - base) / 2);
-    wl_extra &= ~(int64_t)7;                                 // keeps skey 16-byte aligned
-    x.n_raw = (int)n_raw; x.tbl = tbl; x.sort_n = sort_n; x.wl_extra = (int)wl_extra;
-    smem = route_fast_smem(rv.TD, probes, (int)n_raw, tbl, sort_n, (int)wl_extra);
-    // second-generation kernel (two CTAs per SM): B <= 1024 and a worklist of at least 1/8 of the positions
+    x.n_raw = (int)n_raw; x.tbl = tbl; x.sort_n = sort_n; x.wl_extra = 0;
+    smem = 0;
+    // one-CTA kernel: needs a HARD_CAP that cannot bind (n_raw - 64 < cap: every poll of PIS:657-659 proceeds) and its whole state in shared memory
+    if (n_raw - kBlock < hard_cap) {
+        int tbl1 = tbl;
+        if (tbl1 < n_raw + sort_n) tbl1 <<= 1;              // room for the class list and the selection list
+        const size_t limit = 227 * 1024 - 2048;
+        if (tbl1 <= 32768 && route_fast_smem(rv.TD, probes, (int)n_raw, tbl1, sort_n, 0) <= limit) {
+            const size_t base = route_fast_smem(rv.TD, probes, (int)n_raw, tbl1, sort_n, 0);
+            // worklist of involved positions: wl_extra dedicated entries + the 6*sort_n that overlay skey / sid
+            int64_t wl_extra = std::max<int64_t>(0, n_raw - 6 * (int64_t)sort_n);
+            wl_extra = std::min<int64_t>(wl_extra, (int64_t)(limit - base) / 2);
+            wl_extra &= ~(int64_t)7;                         // keeps skey 16-byte aligned
+            x.v1_ok = 1; x.tbl1 = tbl1; x.wl_extra = (int)wl_extra;
+            smem = route_fast_smem(rv.TD, probes, (int)n_raw, tbl1, sort_n, (int)wl_extra);
+        }
+    }
+    // two-CTA kernel: any HARD_CAP; B <= 1024 sorted in the kernel, B <= 16384 by route_sort_big_kernel; a worklist of at least 1/8 of the positions
     Route2Layout L{};
-    x.v2_smem = 0;
-    if (sort_n <= 2 * R2_H && (int64_t)rv.TD * probes <= R2_THREADS && route2_layout(rv.TD, probes, (int)n_raw, tbl, L) &&
+    if (sort_n <= 16 * RS_THREADS && (int64_t)rv.TD * probes <= R2_THREADS && route2_layout(rv.TD, probes, (int)n_raw, tbl, L) &&
         (L.wl_cap >= n_raw / 8 || L.wl_cap >= n_raw)) {
         x.v2_region = L.region; x.v2_cls_cap = L.cls_cap; x.v2_wl_cap = L.wl_cap; x.v2_smem = L.smem;
+        x.v2_big = sort_n > 2 * R2_H;
     }
-    return true;
+    return x.v1_ok || x.v2_smem;
 }
 
 int configure_route_kernels() {   // per-device opt-in, see configure_tokengen_kernels
-    return opt_in_smem(route_fast_kernel) || opt_in_smem(route_fast2_kernel<false>) || opt_in_smem(route_fast2_kernel<true>) || opt_in_smem(route_kernel) ? -1 : 0;
+    return opt_in_smem(route_fast_kernel) || opt_in_smem(route_fast2_kernel<false, false>) || opt_in_smem(route_fast2_kernel<true, false>) ||
+           opt_in_smem(route_fast2_kernel<false, true>) || opt_in_smem(route_fast2_kernel<true, true>) || opt_in_smem(route_sort_big_kernel<1>) ||
+           opt_in_smem(route_sort_big_kernel<2>) || opt_in_smem(route_sort_big_kernel<4>) || opt_in_smem(route_sort_big_kernel<8>) ||
+           opt_in_smem(route_sort_big_kernel<16>) || opt_in_smem(route_kernel) ? -1 : 0;
 }
 
+// Fast path of Route.  x.v2_smem != 0: route_fast2_kernel (+ route_sort_big_kernel for B > 1024); the queries it hands back (x.ovf_list) go to
+// route_fast_kernel when that kernel is eligible (x.v1_ok), otherwise to the general kernel (`pg` = its parameters, scratch included).
 int launch_route_fast(cudaStream_t s, const RoutingView &rv, const RouteParams &p, RouteFastExtra x, size_t smem, int sm_count,
-                      int32_t *vis_part, uint8_t *vis_score, uint8_t *vis_n) {
+                      int32_t *vis_part, uint8_t *vis_score, uint8_t *vis_n, const RouteParams *pg, int grid_g) {
     if (p.Q <= 0) return 0;
     const int64_t nthreads = p.Q * rv.TD;
     route_probe_kernel<<<(unsigned)((nthreads + 127) / 128), 128, 0, s>>>(rv, p.Q, p.codes, p.probes, vis_part, vis_score, vis_n);
     x.vis_part = vis_part; x.vis_score = vis_score; x.vis_n = vis_n;
     const int grid = (int)std::min<int64_t>(p.Q, sm_count);
+    int launches = 1;
     if (x.v2_smem && x.ovf_n) {
-        // two CTAs per SM; the queries it cannot hold (worklist / class list / key width) come back in ovf_list for the one-CTA kernel
         if (cudaMemsetAsync(x.ovf_n, 0, 2 * sizeof(int32_t), s) != cudaSuccess) return -1;     // [0] overflow count, [1] next query
         const int grid2 = (int)std::min<int64_t>(p.Q, 2 * (int64_t)sm_count);
-        if (rv.deleted) route_fast2_kernel<true><<<grid2, R2_THREADS, x.v2_smem, s>>>(rv, p, x);
-        else route_fast2_kernel<false><<<grid2, R2_THREADS, x.v2_smem, s>>>(rv, p, x);
-        x.qlist = x.ovf_list; x.qlist_n = x.ovf_n;
-        route_fast_kernel<<<grid, RQ_THREADS, smem, s>>>(rv, p, x);
-        return cudaGetLastError() == cudaSuccess ? 3 : -1;
+        if (x.v2_big) {
+            if (rv.deleted) route_fast2_kernel<true, true><<<grid2, R2_THREADS, x.v2_smem, s>>>(rv, p, x);
+            else route_fast2_kernel<false, true><<<grid2, R2_THREADS, x.v2_smem, s>>>(rv, p, x);
+            const size_t ssm = sizeof(unsigned long long) * (size_t)x.sort_n;
+            switch (x.sort_n / RS_THREADS) {
+                case 2: route_sort_big_kernel<2><<<grid, RS_THREADS, ssm, s>>>(rv, p, x); break;
+                case 4: route_sort_big_kernel<4><<<grid, RS_THREADS, ssm, s>>>(rv, p, x); break;
+                case 8: route_sort_big_kernel<8><<<grid, RS_THREADS, ssm, s>>>(rv, p, x); break;
+                case 16: route_sort_big_kernel<16><<<grid, RS_THREADS, ssm, s>>>(rv, p, x); break;
+                default: return -1;
+            }
+            launches++;
+        } else {
+            if (rv.deleted) route_fast2_kernel<true, false><<<grid2, R2_THREADS, x.v2_smem, s>>>(rv, p, x);
+            else route_fast2_kernel<false, false><<<grid2, R2_THREADS, x.v2_smem, s>>>(rv, p, x);
+        }
+        launches += 2;
+        if (x.v1_ok) {
+            x.qlist = x.ovf_list; x.qlist_n = x.ovf_n; x.tbl = x.tbl1;
+            route_fast_kernel<<<grid, RQ_THREADS, smem, s>>>(rv, p, x);
+        } else {
+            if (!pg) return -1;
+            RouteParams g = *pg;
+            g.qlist = x.ovf_list; g.qlist_n = x.ovf_n;
+            const size_t gsm = sizeof(int32_t) * ((size_t)2 * rv.TD * p.probes + rv.TD);
+            route_kernel<<<grid_g, RT_THREADS, gsm, s>>>(rv, g);
+        }
+        return cudaGetLastError() == cudaSuccess ? launches : -1;
     }
-    x.qlist = nullptr; x.qlist_n = nullptr;
+    if (!x.v1_ok) return -1;
+    x.qlist = nullptr; x.qlist_n = nullptr; x.tbl = x.tbl1;
     route_fast_kernel<<<grid, RQ_THREADS, smem, s>>>(rv, p, x);
     return cudaGetLastError() == cudaSuccess ? 2 : -1;
 }

@@ -184,3 +184,32 @@ def test_config3_shape_at_full_size_matches_oracle_sample():
             assert (c[0], c[1], c[2], c[3], bool(c[4])) == (ref["cand_total"], ref["cand_kept"], ref["cand_decrypted"], ref["returned"], ref["retried"])
     finally:
         gpu.close()
+
+
+@pytest.mark.parametrize("probes,hard_cap,B", [(5, 24000, 1024), (5, 6000, 1024), (5, 12000, 4000), (6, 20000, 16000), (3, 2500, 1800), (5, 20000, 512),
+                                               (5, 20416, 1024), (5, 20417, 2000)])
+def test_route_fast_path_with_binding_cap_and_long_lists_at_full_size(c2, probes, hard_cap, B):
+    """The reference's own profiles (config_sift1m.json, sift1m_sub1.json, ...) use refinement limits of thousands and HARD_CAPs that bind.
+    At 1 M ids the duplication is low, so the two-CTA Route kernel holds (nearly) every query itself: binding caps through its visit cut,
+    B > 1024 through the separate sort kernel.  Ordered ids, scores and the raw / unique counters against the oracle."""
+    cfg, gpu = c2["cfg"], c2["gpu"]
+    NQ = 96
+    q = c2["queries"][:NQ]
+    g = O.GFunctions(cfg.dim, cfg.T, cfg.D, cfg.m, cfg.lam, c2["alpha"], c2["r"], c2["omega"])
+    ix = O.Index(g, cfg.N, c2["mn"].shape[1], c2["mn"], c2["mx"], c2["rep"], c2["ids"])
+    codes = O.tokengen_batch(q, g)
+    out = gpu.route_batch(codes, probes, hard_cap, B)
+    assert gpu.get_info("last_route_path") == 1 and gpu.get_info("last_route_v2") == 1
+    assert gpu.get_info("route_overflowed") <= NQ // 10
+    n_raw = cfg.T * cfg.D * probes * 64
+    bound = 0
+    for i in range(NQ):
+        ids, sc, raw, mc = O.route(ix, codes[i], probes, hard_cap)
+        n = min(B, len(ids))
+        assert (out["n_cand"][i], out["unique"][i], out["raw_seen"][i]) == (n, len(ids), raw), i
+        assert np.array_equal(out["cand_scores"][i, :n], sc[:n])
+        if mc < 9:
+            assert np.array_equal(out["cand_ids"][i, :n], ids[:n]), i
+        bound += len(ids) >= hard_cap
+    if hard_cap <= n_raw - 64 - 2000:
+        assert bound == NQ                                               # the cap really cut every query's visits short

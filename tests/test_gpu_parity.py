@@ -58,8 +58,12 @@ def test_route_candidates_ordered_bit_exact(wg, probes, hard_cap, B, general):
         assert ctx.get_info("last_route_path") == 2
     elif ctx.get_info("last_route_path") == 1:
         # fast path: the two-CTA kernel serves B <= 1024 unless forced off; queries it handed to the one-CTA kernel are counted
-        assert ctx.get_info("last_route_v2") == (1 if general == 0 and B <= 1024 else 0)
+        # (the one-CTA kernel needs a HARD_CAP that cannot bind and B small enough for its shared memory; forced, it yields to the two-CTA
+        #  kernel where it is not eligible)
+        assert ctx.get_info("last_route_v2") == 1 if general == 0 else ctx.get_info("last_route_v2") in (0, 1)
         assert 0 <= ctx.get_info("route_overflowed") <= codes.shape[0]
+        if general == 0 and w.g.T * w.g.D * probes * 64 <= 8192:       # short position lists fit the two-CTA kernel's worklist entirely
+            assert ctx.get_info("route_overflowed") == 0
     general = int(general == 1)
     worst_chain = 0
     for q in range(codes.shape[0]):
