@@ -153,7 +153,11 @@ int do_route(fspann_ctx *ctx, int64_t Q, const uint64_t *d_codes, int probes, in
         ENSURE(ctx->s_vis_part, sizeof(int32_t) * (size_t)Q * rv.TD * probes);
         ENSURE(ctx->s_vis_score, (size_t)Q * rv.TD * probes);
         ENSURE(ctx->s_vis_n, (size_t)Q * rv.TD);
-        if (fx.v2_smem && fx.v2_big) { ENSURE(ctx->s_route_big, sizeof(unsigned long long) * (size_t)Q * B); fx.big_keys = (unsigned long long *)ctx->s_route_big.p; }
+        if (fx.v2_smem && fx.v2_big) {
+            ENSURE(ctx->s_route_big, sizeof(unsigned long long) * (size_t)Q * B + sizeof(int32_t) * 8 * (size_t)Q);
+            fx.big_keys = (unsigned long long *)ctx->s_route_big.p;
+            fx.big_seg = (int32_t *)(fx.big_keys + (size_t)Q * B);
+        }
         RouteParams pg = p;
         int grid_g = 0;
         if (fx.v2_smem && !fx.v1_ok) {                                      // the general kernel serves what the two-CTA kernel hands back

@@ -85,6 +85,7 @@ struct RouteFastExtra {
     int v2_big;                           // refinementLimit > 1024: the selected keys go to big_keys, route_sort_big_kernel orders them
     int v1_ok, tbl1;                      // route_fast_kernel is eligible (non-binding HARD_CAP, state fits) with tbl1 table slots
     unsigned long long *big_keys;         // [Q][B] (score | Java bucket | position)
+    int32_t *big_seg;                     // [Q][5] segment starts of big_keys (segments are cut at score-class boundaries)
     int32_t *ovf_n, *ovf_list;            // queries route_fast2_kernel hands to route_fast_kernel
     const int32_t *qlist, *qlist_n;       // route_fast_kernel: serve these queries only (nullptr = all)
 };

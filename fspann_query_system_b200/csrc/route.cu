@@ -909,6 +909,8 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) route_fast_kernel(RoutingView r
 // =====================================================================================================================
 constexpr int R2_THREADS = 512;           // 16 warps per CTA, two CTAs per SM (768 threads = 48 warps per SM at 40 registers was measured slower: 2.00 vs 1.80 ms)
 constexpr int R2_H = 512;                 // the sort works on 2 x R2_H keys held by the first R2_H threads
+constexpr int RS_SEGMAX = 16384;          // keys one route_sort_big_kernel CTA orders (16 per thread)
+constexpr int RS_MAXSEG = 4;              // segments per query (n_raw <= 32000 needs at most 4 greedy segments of <= RS_SEGMAX)
 constexpr int R2_SELBYTES = 7168;          // sel_id int32[1024] + sel_pos uint16[1024] + sel_sc uint8[1024]
 
 struct Route2Layout { int region, cls_cap, wl_cap; size_t smem; };
@@ -919,7 +921,7 @@ static bool route2_layout(int TD, int probes, int n_raw, int tbl, Route2Layout &
     L.region = std::max(2 * tbl, 28672);
     L.cls_cap = std::min(n_raw, ((L.region - R2_SELBYTES) / 4) & ~7);
     const size_t fixed = (size_t)L.region + sizeof(int64_t) * nvis + 2 * (size_t)nvis16 + 3 * sizeof(uint16_t) * (size_t)nvis16 + sizeof(uint32_t) * (size_t)nbm + 64;
-    const size_t limit = 114432;                                       // 2 x (dynamic + 1.2 KB static + 1 KB reserve) <= 228 KB per SM
+    const size_t limit = 114176;                                       // 2 x (dynamic + 1.4 KB static + 1 KB reserve) <= 228 KB per SM
     if (fixed + 9 * 1024 > limit) return false;
     int64_t cap = (int64_t)(limit - fixed) / 9;
     cap = std::min<int64_t>(cap, n_raw);
@@ -930,6 +932,18 @@ static bool route2_layout(int TD, int probes, int n_raw, int tbl, Route2Layout &
     L.wl_cap = (int)cap;
     L.smem = fixed + 9 * (size_t)cap;
     return true;
+}
+
+// warp-aggregated slot allocation over a few counters: lanes with in == true and the same `which` share one shared atomic
+__device__ __forceinline__ int multi_slot(int32_t *counters, bool in, int which, int lane) {
+    const unsigned act = __ballot_sync(0xffffffffu, in);
+    if (!in) return -1;
+    const unsigned peers = __match_any_sync(act, which);
+    const int leader = __ffs(peers) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&counters[which], __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    return base + __popc(peers & ((1u << lane) - 1u));
 }
 
 // Bitonic sort of TWO 32-bit keys per thread (elements tid and tid + R2_H of threads tid < R2_H; the other threads only keep the barriers
@@ -999,6 +1013,8 @@ __global__ void __launch_bounds__(R2_THREADS, 2) route_fast2_kernel(RoutingView 
     uint8_t *wl_best = reinterpret_cast<uint8_t *>(wl_next + wl_cap);
     __shared__ int32_t s_hist[256];
     __shared__ int32_t s_raw, s_uniq, s_m, s_ncls, s_nwl, s_nlow, s_pick[3], s_wsum[32], s_cut;
+    __shared__ int32_t s_seg_start[RS_MAXSEG + 1], s_seg_cnt[RS_MAXSEG], s_seg_ok;
+    __shared__ uint8_t s_seg_of[128];
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int64_t n_ids = rv.n_ids;
@@ -1251,8 +1267,33 @@ __global__ void __launch_bounds__(R2_THREADS, 2) route_fast2_kernel(RoutingView 
             if (tid == 0) { x.ovf_list[atomicAdd(x.ovf_n, 1)] = (int32_t)q; p.n_cand[q] = 0; }
             continue;
         }
-        // BIG (refinementLimit > 1024): the selected entries leave as 64-bit keys (score | Java bucket | position) and route_sort_big_kernel orders them
+        // BIG (refinementLimit > 1024): the selected entries leave as 64-bit keys (score | Java bucket | position) and route_sort_big_kernel orders
+        // them.  The score is the leading key field, so the list is cut at score-class boundaries into <= RS_MAXSEG segments of <= RS_SEGMAX keys
+        // (greedy over the class histogram); every segment is sorted on its own and they concatenate in order.
         unsigned long long *big = BIG ? x.big_keys + (size_t)q * p.B : nullptr;
+        if (BIG) {
+            if (tid == 0) {
+                int seg = 0, fill = 0, ok = 1;
+                s_seg_start[0] = 0;
+                for (uint32_t c = 0; c <= sstar && c < 128u; c++) {
+                    const int nc = c < sstar ? s_hist[c] : want - cum;
+                    if (nc > RS_SEGMAX) ok = 0;
+                    if (fill + nc > RS_SEGMAX && fill > 0) {
+                        if (seg + 1 >= RS_MAXSEG) { ok = 0; } else { seg++; s_seg_start[seg] = s_seg_start[seg - 1] + fill; fill = 0; }
+                    }
+                    s_seg_of[c] = (uint8_t)seg;
+                    fill += nc;
+                }
+                for (int g2 = seg + 1; g2 <= RS_MAXSEG; g2++) s_seg_start[g2] = s_seg_start[seg] + fill;
+                for (int g2 = 0; g2 < RS_MAXSEG; g2++) s_seg_cnt[g2] = 0;
+                s_seg_ok = ok && sstar < 128u;
+            }
+            __syncthreads();
+            if (!s_seg_ok) {                                            // a single score class beyond one segment: the general kernel takes it
+                if (tid == 0) { x.ovf_list[atomicAdd(x.ovf_n, 1)] = (int32_t)q; p.n_cand[q] = 0; }
+                continue;
+            }
+        }
         // ---- 6. scan the positions that can hold a score <= s*: the visits with score <= s* (singles; ids re-read) and the worklist ----
         {
             bool low = false;
@@ -1282,7 +1323,12 @@ __global__ void __launch_bounds__(R2_THREADS, 2) route_fast2_kernel(RoutingView 
                 const bool incls = need_levels && sc == sstar && sc != 255u;
                 const int a = list_slot(&s_m, below, lane);
                 if (BIG) {
-                    if (below && a < p.B) big[a] = ((unsigned long long)sc << 40) | ((unsigned long long)(java_hash_decimal(id) & (capF - 1u)) << 16) | (unsigned long long)e;
+                    const int sg = below ? (int)s_seg_of[sc] : 0;
+                    const int off = multi_slot(s_seg_cnt, below, sg, lane);
+                    if (below) {
+                        const int slot = s_seg_start[sg] + off;
+                        if (slot < p.B) big[slot] = ((unsigned long long)sc << 40) | ((unsigned long long)(java_hash_decimal(id) & (capF - 1u)) << 16) | (unsigned long long)e;
+                    }
                 } else if (below && a < sort_n) { sel_id[a] = id; sel_pos[a] = (uint16_t)e; sel_sc[a] = (uint8_t)sc; }
                 const int c = list_slot(&s_ncls, incls, lane);
                 if (incls) { cls_pos[c] = (uint16_t)e; cls_hash[c] = (uint16_t)(java_hash_decimal(id) & 0xffffu); }
@@ -1330,7 +1376,12 @@ __global__ void __launch_bounds__(R2_THREADS, 2) route_fast2_kernel(RoutingView 
                 }
                 const int a = list_slot(&s_m, take_it, lane);
                 if (BIG) {
-                    if (take_it && a < p.B) big[a] = ((unsigned long long)sstar << 40) | ((unsigned long long)((uint32_t)cls_hash[i] & (capF - 1u)) << 16) | (unsigned long long)e;
+                    const int sg = s_seg_of[sstar];
+                    const int off = multi_slot(s_seg_cnt, take_it, sg, lane);
+                    if (take_it) {
+                        const int slot = s_seg_start[sg] + off;
+                        if (slot < p.B) big[slot] = ((unsigned long long)sstar << 40) | ((unsigned long long)((uint32_t)cls_hash[i] & (capF - 1u)) << 16) | (unsigned long long)e;
+                    }
                 } else if (take_it && a < sort_n) {
                     sel_id[a] = __ldg(rv.ids + vbase_s[e >> 6] + (e & 63));    // the id at a position (single or first occurrence alike)
                     sel_pos[a] = (uint16_t)e; sel_sc[a] = (uint8_t)sstar;
@@ -1339,6 +1390,7 @@ __global__ void __launch_bounds__(R2_THREADS, 2) route_fast2_kernel(RoutingView 
             __syncthreads();
         }
         if (BIG) {
+            if (tid <= RS_MAXSEG) x.big_seg[q * (RS_MAXSEG + 1) + tid] = s_seg_start[tid];
             if (tid == 0) { p.n_cand[q] = want; p.unique[q] = n_unique; p.raw_seen[q] = s_raw; }
             continue;
         }
@@ -1405,10 +1457,13 @@ __global__ void __launch_bounds__(RS_THREADS, 1) route_sort_big_kernel(RoutingVi
     unsigned long long *sk = reinterpret_cast<unsigned long long *>(rs_smem);
     const int tid = threadIdx.x, TD = rv.TD, probes = p.probes;
     constexpr int n = E * RS_THREADS;
-    for (int64_t q = blockIdx.x; q < p.Q; q += gridDim.x) {
-        const int m = p.n_cand[q];
-        if (m <= 0) continue;                                            // empty, or handed to the fallback kernel (block-uniform)
-        const unsigned long long *src = x.big_keys + (size_t)q * p.B;
+    for (int64_t w = blockIdx.x; w < p.Q * RS_MAXSEG; w += gridDim.x) {
+        const int sg = (int)(w / p.Q);                                   // segment-major: every CTA gets its share of the (usually only non-empty) first segments
+        const int64_t q = w - (int64_t)sg * p.Q;
+        if (p.n_cand[q] <= 0) continue;                                  // empty, or handed to the fallback kernel (block-uniform)
+        const int s0 = x.big_seg[q * (RS_MAXSEG + 1) + sg], m = x.big_seg[q * (RS_MAXSEG + 1) + sg + 1] - s0;
+        if (m <= 0) continue;
+        const unsigned long long *src = x.big_keys + (size_t)q * p.B + s0;
         unsigned long long a[E];
 #pragma unroll
         for (int u = 0; u < E; u++) { const int i = u * RS_THREADS + tid; a[u] = i < m ? src[i] : ~0ull; }
@@ -1453,7 +1508,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) route_sort_big_kernel(RoutingVi
                 }
             }
         }
-        int32_t *out_id = p.cand_ids + (size_t)q * p.B, *out_sc = p.cand_scores + (size_t)q * p.B;
+        int32_t *out_id = p.cand_ids + (size_t)q * p.B + s0, *out_sc = p.cand_scores + (size_t)q * p.B + s0;
 #pragma unroll
         for (int u = 0; u < E; u++) {
             const int i = u * RS_THREADS + tid;
@@ -1478,11 +1533,12 @@ bool route_fast_eligible(const RoutingView &rv, int probes, int64_t hard_cap, in
     if ((int64_t)rv.TD * probes > RQ_THREADS) return false;
     int sort_n = 64; while (sort_n < B && sort_n < (1 << 20)) sort_n <<= 1;
     int tbl = 1024; while (tbl < n_raw + n_raw / 4) tbl <<= 1;
-    if (tbl > 32768) return false;
+    const bool tbl_ok = tbl <= 32768;                        // the one-CTA kernel's table holds positions: it needs the full size
+    if (!tbl_ok) tbl = 32768;                                // the two-CTA kernel only sizes its filters with it
     x.n_raw = (int)n_raw; x.tbl = tbl; x.sort_n = sort_n; x.wl_extra = 0;
     smem = 0;
     // one-CTA kernel: needs a HARD_CAP that cannot bind (n_raw - 64 < cap: every poll of PIS:657-659 proceeds) and its whole state in shared memory
-    if (n_raw - kBlock < hard_cap) {
+    if (tbl_ok && n_raw - kBlock < hard_cap) {
         int tbl1 = tbl;
         if (tbl1 < n_raw + sort_n) tbl1 <<= 1;              // room for the class list and the selection list
         const size_t limit = 227 * 1024 - 2048;
@@ -1496,9 +1552,9 @@ bool route_fast_eligible(const RoutingView &rv, int probes, int64_t hard_cap, in
             smem = route_fast_smem(rv.TD, probes, (int)n_raw, tbl1, sort_n, (int)wl_extra);
         }
     }
-    // two-CTA kernel: any HARD_CAP; B <= 1024 sorted in the kernel, B <= 16384 by route_sort_big_kernel; a worklist of at least 1/8 of the positions
+    // two-CTA kernel: any HARD_CAP; B <= 1024 sorted in the kernel, B <= 32768 by route_sort_big_kernel (segments of <= 16384 keys); a worklist of at least 1/8 of the positions
     Route2Layout L{};
-    if (sort_n <= 16 * RS_THREADS && (int64_t)rv.TD * probes <= R2_THREADS && route2_layout(rv.TD, probes, (int)n_raw, tbl, L) &&
+    if (sort_n <= 2 * RS_SEGMAX && (int64_t)rv.TD * probes <= R2_THREADS && route2_layout(rv.TD, probes, (int)n_raw, tbl, L) &&
         (L.wl_cap >= n_raw / 8 || L.wl_cap >= n_raw)) {
         x.v2_region = L.region; x.v2_cls_cap = L.cls_cap; x.v2_wl_cap = L.wl_cap; x.v2_smem = L.smem;
         x.v2_big = sort_n > 2 * R2_H;
@@ -1529,8 +1585,9 @@ int launch_route_fast(cudaStream_t s, const RoutingView &rv, const RouteParams &
         if (x.v2_big) {
             if (rv.deleted) route_fast2_kernel<true, true><<<grid2, R2_THREADS, x.v2_smem, s>>>(rv, p, x);
             else route_fast2_kernel<false, true><<<grid2, R2_THREADS, x.v2_smem, s>>>(rv, p, x);
-            const size_t ssm = sizeof(unsigned long long) * (size_t)x.sort_n;
-            switch (x.sort_n / RS_THREADS) {
+            const int seg_n = std::min(x.sort_n, RS_SEGMAX);
+            const size_t ssm = sizeof(unsigned long long) * (size_t)seg_n;
+            switch (seg_n / RS_THREADS) {
                 case 2: route_sort_big_kernel<2><<<grid, RS_THREADS, ssm, s>>>(rv, p, x); break;
                 case 4: route_sort_big_kernel<4><<<grid, RS_THREADS, ssm, s>>>(rv, p, x); break;
                 case 8: route_sort_big_kernel<8><<<grid, RS_THREADS, ssm, s>>>(rv, p, x); break;
