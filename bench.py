@@ -240,6 +240,7 @@ def run_extra_config(name, cfg, torch, local_rank, steps, warmup, threads, log_f
         ok, cpu_qps = oracle_sample_check(cfg, world, gpu, batches[0], nq, threads)
         out = {"workload": f"{cfg.name}: N={cfg.N} d={cfg.dim} T={cfg.T} D={cfg.D} m={cfg.m} probes={cfg.probes} B={cfg.B} k={cfg.k} cap={cfg.hard_cap} Q={Q}",
                "queries_per_s": Q * steps / (ms * 1e-3), "ms_per_batch": ms / steps, "stage_ms": stage, "route_path": {1: "fast", 2: "general"}.get(gpu.get_info("last_route_path"), "?"),
+               "route_queries_handed_to_fallback": gpu.get_info("route_overflowed"), "hard_cap_binds": bool(cfg.hard_cap <= cfg.T * cfg.D * cfg.probes * 64 - 64),
                "refine_stage_frac_of_hbm": alg / (stage_ms * 1e-3) / 1e9 / peak if stage_ms > 0 else None,
                "reuse_factor": pairs / max(touched, 1), "mean_returned": float(res["n_ret"].mean()), "retried_queries": int(res["counters"][:, 4].sum()),
                "gpu_matches_oracle_on_sample": ok, "oracle_sample_queries": nq, "cpu_port_queries_per_s": cpu_qps, "cpu_threads": threads,
@@ -312,7 +313,7 @@ def main():
     ap.add_argument("--no-mixed", action="store_true", help="skip the config-5 Rotate + Migrate leg")
     ap.add_argument("--no-extras", action="store_true", help="skip the legs for BASELINE configs 1 / 3 / 4-shape and the published operating point")
     ap.add_argument("--no-sharded", action="store_true", help="skip the database-sharded and strong-scaling legs")
-    ap.add_argument("--extras", default="C1,C3,C4s,P6", help="which extra configs to run at N=1")
+    ap.add_argument("--extras", default="C1,C3,C4s,P6,SUB1", help="which extra configs to run at N=1")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

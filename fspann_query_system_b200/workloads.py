@@ -60,7 +60,10 @@ C4S = Config("C4s-deep4m", 4_000_000, 96, 10_000, 8, 8, 24, 2, 13, 5, 1024, 10, 
 # the reference's only published operating point (README.md:300, ART 2828 ms): profile SIFT_P6_BALANCED of config_sift1m.json:59-71 --
 # tables 6, probeOverride 6, refinementLimit 16000, maxGlobalCandidates 20000 -- queried at MAX_K = 100 like FSA.runQueries (FSA:634)
 P6 = Config("P6-sift1m-balanced", 1_000_000, 128, 1_000, 6, 8, 24, 2, 13, 6, 16_000, 100, 20_000, "sift", 1002, 2002, 4096)
-CONFIGS = {"C1": C1, "C2": C2, "C3": C3, "C4": C4, "C4s": C4S, "C5": C2, "P6": P6}
+# a profile of the reference whose HARD_CAP binds (sift1m_sub1.json, profile 2: tables 5, divisions 12, m 22, probeOverride 6, refinementLimit 6000,
+# maxGlobalCandidates 8000: 60 x 6 x 64 = 23 040 positions per query against a cap of 8 000), at full SIFT1M shape
+SUB1 = Config("SUB1-sift1m-sub1-p2", 1_000_000, 128, 1_000, 5, 12, 22, 2, 13, 6, 6_000, 100, 8_000, "sift", 1002, 2002, 4096)
+CONFIGS = {"C1": C1, "C2": C2, "C3": C3, "C4": C4, "C4s": C4S, "C5": C2, "P6": P6, "SUB1": SUB1}
 
 
 def _sift(n: int, dim: int, centres: int, seed: int, centre_seed: int) -> np.ndarray:
