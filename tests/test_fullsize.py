@@ -187,7 +187,7 @@ def test_config3_shape_at_full_size_matches_oracle_sample():
 
 
 @pytest.mark.parametrize("probes,hard_cap,B", [(5, 24000, 1024), (5, 6000, 1024), (5, 12000, 4000), (6, 20000, 16000), (3, 2500, 1800), (5, 20000, 512),
-                                               (5, 20416, 1024), (5, 20417, 2000), (7, 30000, 22000), (7, 20000, 20000)])
+                                               (5, 20416, 1024), (5, 20417, 2000), (7, 30000, 22000), (7, 20000, 20000), (5, 50000, 40000)])
 def test_route_fast_path_with_binding_cap_and_long_lists_at_full_size(c2, probes, hard_cap, B):
     """The reference's own profiles (config_sift1m.json, sift1m_sub1.json, ...) use refinement limits of thousands and HARD_CAPs that bind.
     At 1 M ids the duplication is low, so the two-CTA Route kernel holds (nearly) every query itself: binding caps through its visit cut,
