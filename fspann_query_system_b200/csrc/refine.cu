@@ -285,21 +285,25 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
 __device__ __forceinline__ uint32_t ror8(uint32_t x) { return __funnelshift_r(x, x, 8); }
 #define FSP_T0(s, k) lds32(__byte_perm((s), K0, 0x7604 | ((k) << 4)))
 #define FSP_T2(s, k) lds32(__byte_perm((s), K2, 0x7604 | ((k) << 4)))
+// second 64 KB block, same layout: column `lane` holds Te1[x] = ror8(Te0[x]), column 32+lane holds Te3[x] = ror8(Te2[x]): the rotate and one
+// XOR per state word and round leave the ALU pipe (which the decrypt kernel fills to 81 %) for twice the table space
+#define FSP_T1(s, k) lds32(__byte_perm((s), K1, 0x7604 | ((k) << 4)))
+#define FSP_T3(s, k) lds32(__byte_perm((s), K3, 0x7604 | ((k) << 4)))
 __device__ __forceinline__ void aes256_encrypt_fast(uint32_t K0, const uint32_t *rk, uint32_t s0, uint32_t s1, uint32_t s2, uint32_t s3,
                                                     uint32_t out[4]) {
-    const uint32_t K2 = K0 + 128u;
+    const uint32_t K2 = K0 + 128u, K1 = K0 + 0x10000u, K3 = K1 + 128u;
     s0 ^= rk[0]; s1 ^= rk[1]; s2 ^= rk[2]; s3 ^= rk[3];
 #pragma unroll
     for (int r = 1; r < 14; r++) {
-        // t_i = Te0[s_i.b3] ^ Te1[s_{i+1}.b2] ^ Te2[s_{i+2}.b1] ^ Te3[s_{i+3}.b0] ^ rk,  Te1 = ror8(Te0), Te3 = ror8(Te2)
-        const uint32_t a0 = FSP_T0(s0, 3), b0 = FSP_T0(s1, 2), c0 = FSP_T2(s2, 1), d0 = FSP_T2(s3, 0);
-        const uint32_t a1 = FSP_T0(s1, 3), b1 = FSP_T0(s2, 2), c1 = FSP_T2(s3, 1), d1 = FSP_T2(s0, 0);
-        const uint32_t a2 = FSP_T0(s2, 3), b2 = FSP_T0(s3, 2), c2 = FSP_T2(s0, 1), d2 = FSP_T2(s1, 0);
-        const uint32_t a3 = FSP_T0(s3, 3), b3 = FSP_T0(s0, 2), c3 = FSP_T2(s1, 1), d3 = FSP_T2(s2, 0);
-        s0 = a0 ^ c0 ^ rk[4 * r + 0] ^ ror8(b0 ^ d0);      // ror8 is linear: one rotate serves Te1 and Te3
-        s1 = a1 ^ c1 ^ rk[4 * r + 1] ^ ror8(b1 ^ d1);
-        s2 = a2 ^ c2 ^ rk[4 * r + 2] ^ ror8(b2 ^ d2);
-        s3 = a3 ^ c3 ^ rk[4 * r + 3] ^ ror8(b3 ^ d3);
+        // t_i = Te0[s_i.b3] ^ Te1[s_{i+1}.b2] ^ Te2[s_{i+2}.b1] ^ Te3[s_{i+3}.b0] ^ rk
+        const uint32_t a0 = FSP_T0(s0, 3), b0 = FSP_T1(s1, 2), c0 = FSP_T2(s2, 1), d0 = FSP_T3(s3, 0);
+        const uint32_t a1 = FSP_T0(s1, 3), b1 = FSP_T1(s2, 2), c1 = FSP_T2(s3, 1), d1 = FSP_T3(s0, 0);
+        const uint32_t a2 = FSP_T0(s2, 3), b2 = FSP_T1(s3, 2), c2 = FSP_T2(s0, 1), d2 = FSP_T3(s1, 0);
+        const uint32_t a3 = FSP_T0(s3, 3), b3 = FSP_T1(s0, 2), c3 = FSP_T2(s1, 1), d3 = FSP_T3(s2, 0);
+        s0 = a0 ^ b0 ^ c0 ^ d0 ^ rk[4 * r + 0];
+        s1 = a1 ^ b1 ^ c1 ^ d1 ^ rk[4 * r + 1];
+        s2 = a2 ^ b2 ^ c2 ^ d2 ^ rk[4 * r + 2];
+        s3 = a3 ^ b3 ^ c3 ^ d3 ^ rk[4 * r + 3];
     }
     // last round: S[x] is byte 3 and byte 0 of Te2[x] = (s, 3s, 2s, s) and bytes 2, 1 of Te0[x] = (2s, s, s, 3s)
 #define FSP_LAST(a, b, c, d) ((FSP_T2(a, 3) & 0xff000000u) | (FSP_T0(b, 2) & 0x00ff0000u) | (FSP_T0(c, 1) & 0x0000ff00u) | (FSP_T2(d, 0) & 0x000000ffu))
@@ -319,38 +323,38 @@ __device__ __forceinline__ void aes256_encrypt_fast(uint32_t K0, const uint32_t 
 struct CtrPre { uint32_t c0, d0, d1, d2, d3; };
 
 __device__ __forceinline__ CtrPre aes256_ctr_precompute(uint32_t K0, const uint32_t *rk, uint32_t iv0, uint32_t iv1, uint32_t iv2) {
-    const uint32_t K2 = K0 + 128u;
+    const uint32_t K2 = K0 + 128u, K1 = K0 + 0x10000u, K3 = K1 + 128u;
     const uint32_t s0 = iv0 ^ rk[0], s1 = iv1 ^ rk[1], s2 = iv2 ^ rk[2], s3 = rk[3];     // ctr bytes 1..3 are zero
     CtrPre o;
-    o.c0 = FSP_T0(s0, 3) ^ FSP_T2(s2, 1) ^ rk[4] ^ ror8(FSP_T0(s1, 2));               // + ror8(Te2[s3.b0]) per block
-    const uint32_t c1 = FSP_T0(s1, 3) ^ FSP_T2(s3, 1) ^ rk[5] ^ ror8(FSP_T0(s2, 2) ^ FSP_T2(s0, 0));
-    const uint32_t c2 = FSP_T0(s2, 3) ^ FSP_T2(s0, 1) ^ rk[6] ^ ror8(FSP_T0(s3, 2) ^ FSP_T2(s1, 0));
-    const uint32_t c3 = FSP_T0(s3, 3) ^ FSP_T2(s1, 1) ^ rk[7] ^ ror8(FSP_T0(s0, 2) ^ FSP_T2(s2, 0));
-    o.d0 = FSP_T2(c2, 1) ^ rk[8] ^ ror8(FSP_T0(c1, 2) ^ FSP_T2(c3, 0));               // + Te0[t0.b3]
-    o.d1 = FSP_T0(c1, 3) ^ FSP_T2(c3, 1) ^ rk[9] ^ ror8(FSP_T0(c2, 2));               // + ror8(Te2[t0.b0])
-    o.d2 = FSP_T0(c2, 3) ^ rk[10] ^ ror8(FSP_T0(c3, 2) ^ FSP_T2(c1, 0));              // + Te2[t0.b1]
-    o.d3 = FSP_T0(c3, 3) ^ FSP_T2(c1, 1) ^ rk[11] ^ ror8(FSP_T2(c2, 0));              // + ror8(Te0[t0.b2])
+    o.c0 = FSP_T0(s0, 3) ^ FSP_T2(s2, 1) ^ rk[4] ^ FSP_T1(s1, 2);                     // + Te3[s3.b0] per block
+    const uint32_t c1 = FSP_T0(s1, 3) ^ FSP_T2(s3, 1) ^ rk[5] ^ FSP_T1(s2, 2) ^ FSP_T3(s0, 0);
+    const uint32_t c2 = FSP_T0(s2, 3) ^ FSP_T2(s0, 1) ^ rk[6] ^ FSP_T1(s3, 2) ^ FSP_T3(s1, 0);
+    const uint32_t c3 = FSP_T0(s3, 3) ^ FSP_T2(s1, 1) ^ rk[7] ^ FSP_T1(s0, 2) ^ FSP_T3(s2, 0);
+    o.d0 = FSP_T2(c2, 1) ^ rk[8] ^ FSP_T1(c1, 2) ^ FSP_T3(c3, 0);                     // + Te0[t0.b3]
+    o.d1 = FSP_T0(c1, 3) ^ FSP_T2(c3, 1) ^ rk[9] ^ FSP_T1(c2, 2);                     // + Te3[t0.b0]
+    o.d2 = FSP_T0(c2, 3) ^ rk[10] ^ FSP_T1(c3, 2) ^ FSP_T3(c1, 0);                    // + Te2[t0.b1]
+    o.d3 = FSP_T0(c3, 3) ^ FSP_T2(c1, 1) ^ rk[11] ^ FSP_T3(c2, 0);                    // + Te1[t0.b2]
     return o;
 }
 
 // E_K(IV || ctr) for ctr < 256 given the record's CtrPre.
 __device__ __forceinline__ void aes256_ctr_block(uint32_t K0, const uint32_t *rk, const CtrPre &pre, uint32_t ctr, uint32_t out[4]) {
-    const uint32_t K2 = K0 + 128u;
-    const uint32_t t0 = pre.c0 ^ ror8(FSP_T2(ctr ^ rk[3], 0));
+    const uint32_t K2 = K0 + 128u, K1 = K0 + 0x10000u, K3 = K1 + 128u;
+    const uint32_t t0 = pre.c0 ^ FSP_T3(ctr ^ rk[3], 0);
     uint32_t s0 = pre.d0 ^ FSP_T0(t0, 3);
-    uint32_t s1 = pre.d1 ^ ror8(FSP_T2(t0, 0));
+    uint32_t s1 = pre.d1 ^ FSP_T3(t0, 0);
     uint32_t s2 = pre.d2 ^ FSP_T2(t0, 1);
-    uint32_t s3 = pre.d3 ^ ror8(FSP_T0(t0, 2));
+    uint32_t s3 = pre.d3 ^ FSP_T1(t0, 2);
 #pragma unroll
     for (int r = 3; r < 14; r++) {
-        const uint32_t a0 = FSP_T0(s0, 3), b0 = FSP_T0(s1, 2), c0 = FSP_T2(s2, 1), d0 = FSP_T2(s3, 0);
-        const uint32_t a1 = FSP_T0(s1, 3), b1 = FSP_T0(s2, 2), c1 = FSP_T2(s3, 1), d1 = FSP_T2(s0, 0);
-        const uint32_t a2 = FSP_T0(s2, 3), b2 = FSP_T0(s3, 2), c2 = FSP_T2(s0, 1), d2 = FSP_T2(s1, 0);
-        const uint32_t a3 = FSP_T0(s3, 3), b3 = FSP_T0(s0, 2), c3 = FSP_T2(s1, 1), d3 = FSP_T2(s2, 0);
-        s0 = a0 ^ c0 ^ rk[4 * r + 0] ^ ror8(b0 ^ d0);
-        s1 = a1 ^ c1 ^ rk[4 * r + 1] ^ ror8(b1 ^ d1);
-        s2 = a2 ^ c2 ^ rk[4 * r + 2] ^ ror8(b2 ^ d2);
-        s3 = a3 ^ c3 ^ rk[4 * r + 3] ^ ror8(b3 ^ d3);
+        const uint32_t a0 = FSP_T0(s0, 3), b0 = FSP_T1(s1, 2), c0 = FSP_T2(s2, 1), d0 = FSP_T3(s3, 0);
+        const uint32_t a1 = FSP_T0(s1, 3), b1 = FSP_T1(s2, 2), c1 = FSP_T2(s3, 1), d1 = FSP_T3(s0, 0);
+        const uint32_t a2 = FSP_T0(s2, 3), b2 = FSP_T1(s3, 2), c2 = FSP_T2(s0, 1), d2 = FSP_T3(s1, 0);
+        const uint32_t a3 = FSP_T0(s3, 3), b3 = FSP_T1(s0, 2), c3 = FSP_T2(s1, 1), d3 = FSP_T3(s2, 0);
+        s0 = a0 ^ b0 ^ c0 ^ d0 ^ rk[4 * r + 0];
+        s1 = a1 ^ b1 ^ c1 ^ d1 ^ rk[4 * r + 1];
+        s2 = a2 ^ b2 ^ c2 ^ d2 ^ rk[4 * r + 2];
+        s3 = a3 ^ b3 ^ c3 ^ d3 ^ rk[4 * r + 3];
     }
 #define FSP_LAST(a, b, c, d) ((FSP_T2(a, 3) & 0xff000000u) | (FSP_T0(b, 2) & 0x00ff0000u) | (FSP_T0(c, 1) & 0x0000ff00u) | (FSP_T2(d, 0) & 0x000000ffu))
     out[0] = FSP_LAST(s0, s1, s2, s3) ^ rk[56];
@@ -361,6 +365,8 @@ __device__ __forceinline__ void aes256_ctr_block(uint32_t K0, const uint32_t *rk
 }
 #undef FSP_T0
 #undef FSP_T2
+#undef FSP_T1
+#undef FSP_T3
 
 // AES-CTR decryption of record `id` by the whole warp (authentication already done by refine_verify_kernel).
 // Plaintext doubles -> pt_row[0..dim).  Returns true when every value is finite (warp-uniform).
@@ -937,15 +943,17 @@ __global__ void __launch_bounds__(RF_THREADS, 1) refine_decrypt_kernel(const __g
 
     for (int i = tid; i < 256 * 64; i += RF_THREADS) {
         const uint32_t t0 = sv.te0[i >> 6];
-        tab[i] = (i & 32) ? __funnelshift_r(t0, t0, 16) : t0;
+        const uint32_t v = (i & 32) ? __funnelshift_r(t0, t0, 16) : t0;    // Te0 | Te2
+        tab[i] = v;
+        tab[i + 256 * 64] = __funnelshift_r(v, v, 8);                      // Te1 | Te3 in the next 64 KB
     }
     const int nkeys = ring.n;
     __syncthreads();
 
     const AesFast te{base_sa + pad + (uint32_t)lane * 4u};
     unsigned char *rows_base = warp < lay.warps_a ? rf_smem + (size_t)warp * R * lay.row_bytes
-                                                  : rf_smem + pad + 0x10000u + (size_t)(warp - lay.warps_a) * R * lay.row_bytes;
-    unsigned char *u8_base = rf_smem + pad + 0x10000u + (size_t)(RF_WARPS - lay.warps_a) * R * lay.row_bytes + (size_t)warp * R * lay.u8_row_bytes;
+                                                  : rf_smem + pad + 0x20000u + (size_t)(warp - lay.warps_a) * R * lay.row_bytes;
+    unsigned char *u8_base = rf_smem + pad + 0x20000u + (size_t)(RF_WARPS - lay.warps_a) * R * lay.row_bytes + (size_t)warp * R * lay.u8_row_bytes;
     const bool use_u8 = p.queries_u8 != nullptr && (dim & 15) == 0 && p.f32_exact[1] != 0;
     const bool use_f32 = p.queries_f32 != nullptr && (dim & 3) == 0 && p.f32_exact[0] != 0;
     const int n_uniq = p.totals[1];
@@ -1073,7 +1081,7 @@ static bool decrypt_layout(int dim, int64_t rec_stride, DecryptLayout &lay) {
     lay.rec_bytes = ctr_fast ? (int)rec_stride : 0;          // TMA staging needs the in-place CTR path
     lay.row_bytes = lay.rec_bytes ? lay.rec_bytes + 16 : 8 * dim_pad + 16;   // + 16: the same column of different rows lands in different bank groups
     const int a_avail = 0x10000 - 2048;                       // region A: the window starts with <= 2 KB of reserved / static memory
-    const int b_avail = 227 * 1024 - 2 * 0x10000 - 64;
+    const int b_avail = 227 * 1024 - 3 * 0x10000 - 64;
     lay.u8_row_bytes = (dim & 15) == 0 ? dim + 16 : 0;       // byte rows (integer-valued data), 16-byte skew like the FP64 rows
     for (int rows = 8; rows >= 1; rows--) {
         const int per_warp = rows * lay.row_bytes;
@@ -1081,7 +1089,7 @@ static bool decrypt_layout(int dim, int64_t rec_stride, DecryptLayout &lay) {
         const int u8_total = RF_WARPS * rows * lay.u8_row_bytes;
         if (wb * per_warp + u8_total <= b_avail) {
             lay.rows = rows; lay.warps_a = wa;
-            lay.smem = (size_t)2 * 0x10000 + (size_t)wb * per_warp + (size_t)u8_total + 16;
+            lay.smem = (size_t)3 * 0x10000 + (size_t)wb * per_warp + (size_t)u8_total + 16;
             return true;
         }
     }
