@@ -239,7 +239,7 @@ int launch_refine_group(cudaStream_t s, const StoreView &sv, const RefineParams 
 constexpr int RF_THREADS = 768;    // one CTA per SM (the 64 KB-aligned AES table costs up to 128 KB of shared memory); 24 warps measured best of 16..32
 constexpr int RF_WARPS = RF_THREADS / 32;
 constexpr int DBG_THREADS = 256;
-constexpr int DBG_WARPS = DBG_THREADS / 32;
+[[maybe_unused]] constexpr int DBG_WARPS = DBG_THREADS / 32;
 
 struct TeSmem {
     const uint32_t *t;  // te_s + lane

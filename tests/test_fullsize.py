@@ -78,7 +78,7 @@ def test_search_matches_oracle_sample_and_is_invariant_under_rotate_migrate(c2):
     assert (got["n_ret"] == k).all() and (got["counters"][:, 5] == cfg.B).all()            # B candidates refined per query
     assert (got["counters"][:, 2] == cfg.B).all()                                           # all authenticated and decrypted
     assert (np.diff(got["top_dist"], axis=1) >= 0).all()                                    # sorted
-    # oracle spot check on 24 queries: ids exact, FP64 distances bit-exact
+    # oracle check on 400 queries: ids exact, FP64 distances bit-exact, counters equal
     g = O.GFunctions(cfg.dim, cfg.T, cfg.D, cfg.m, cfg.lam, c2["alpha"], c2["r"], c2["omega"])
     ix = O.Index(g, cfg.N, c2["mn"].shape[1], c2["mn"], c2["mx"], c2["rep"], c2["ids"])
     st = O.Store(cfg.dim, c2["iv"], c2["ct"], np.ones(cfg.N, dtype=np.int32), {1: c2["km"].derive(1)})
