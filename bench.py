@@ -66,7 +66,7 @@ def load_peaks():
 
 
 class ClockSampler:
-    """SM clock / throttle reasons sampled DURING the timed regions: NVML from a thread every 2 ms (the timed regions last tens of
+    """SM clock / throttle reasons sampled DURING the timed regions: NVML from a thread every 20 ms, started before the warm-up steps (more often perturbs the host-buffer leg: NVML queries contend with the driver; the timed regions last tens of
     milliseconds, too short for `nvidia-smi -lms`); falls back to one nvidia-smi query if NVML is unavailable."""
 
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
@@ -101,7 +101,7 @@ class ClockSampler:
                     self.mask |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(0.020)
 
     def start(self):
         if self.h is not None:
@@ -301,6 +301,7 @@ def world_cpu_only(cfg):
 
 
 def main():
+    sys.setswitchinterval(1e-4)     # the clock-sampling thread must hand the GIL back at once when a synchronous search call returns
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -393,11 +394,11 @@ def main():
         gpu.sync()
 
     # ---- value: inputs resident in HBM
+    sampler = ClockSampler(local_rank)
+    sampler.start()                                                       # started before the warm-up: NVML's first queries are slow and stall submissions
     for i in range(Wm):
         step_dev(i)
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     l0 = gpu.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -471,6 +472,17 @@ def main():
 
     # ---- e2e: host buffers through the public C-ABI call (pinned queries -> H2D -> search -> D2H results)
     h_q = [torch.from_numpy(b).pin_memory() for b in batches]
+    # pinned pages that were never a DMA source copy slower the first time (and some allocations sit on slower host memory: tools/pin_test.py):
+    # touch every buffer once, then record what one upload of each costs -- the timed region below still uploads every step's batch in full
+    scratch = torch.empty_like(d_batches[0])
+    h2d_ms = []
+    for rep in range(2):
+        h2d_ms = []
+        for hb in h_q:
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record(); scratch.copy_(hb, non_blocking=True); c1.record(); torch.cuda.synchronize()
+            h2d_ms.append(round(c0.elapsed_time(c1), 3))
+    del scratch
     h_ids = torch.empty((Q, k), dtype=torch.int32).pin_memory()
     h_dist = torch.empty((Q, k), dtype=torch.float64).pin_memory()
     h_nret = torch.empty((Q,), dtype=torch.int32).pin_memory()
@@ -479,15 +491,18 @@ def main():
     def step_host(i):
         gpu.search_batch_raw(Q, h_q[i % n_batches].data_ptr(), k, cfg.probes, cfg.hard_cap, cfg.B, 0, h_ids.data_ptr(), h_dist.data_ptr(),
                              h_nret.data_ptr(), h_cnt.data_ptr())
+    sampler.start()
     for i in range(Wm):
         step_host(i)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler.start()
     t_wall = time.perf_counter()
     f0.record(stream)
+    step_wall = []
     for i in range(K):
-        step_host(Wm + i)
+        t_s = time.perf_counter()
+        step_host(Wm + i)                                                 # returns synchronised: results are in the host buffers
+        step_wall.append((time.perf_counter() - t_s) * 1e3)
     f1.record(stream)
     barrier()
     e2e_ms = f0.elapsed_time(f1)
@@ -664,7 +679,8 @@ def main():
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                "clocks": clocks, "gpu_launches": launches,
                "e2e": {"value": e2e_val, "unit": "queries/s", "h2d_bytes_per_step": Q * dim * 8, "d2h_bytes_per_step": Q * k * 12 + Q * 4 + Q * 48,
-                       "ms_per_step": e2e_ms / K, "wall_ms_per_step": e2e_wall_ms / K, "result_checksum": checksum, "equals_device_path": e2e_same},
+                       "ms_per_step": e2e_ms / K, "wall_ms_per_step": e2e_wall_ms / K, "wall_ms_of_each_step": [round(v, 3) for v in step_wall], "h2d_ms_of_each_pinned_batch": h2d_ms, "result_checksum": checksum,
+                       "equals_device_path": e2e_same},
                "roofline": {"bound": "hbm", "kernel": "refine_decrypt_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                             "frac": achieved / peak if peak else None, "traffic": load_traffic(args.config == "C2" and not args.n and not args.q),
                             "traffic_unit": "bytes/launch (dram read+write, ncu; profiles/r2_decrypt_traffic.json)", "peak_source": peak_src,
