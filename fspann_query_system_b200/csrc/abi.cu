@@ -212,7 +212,7 @@ int do_refine(fspann_ctx *ctx, int64_t Q, const double *d_queries, const int32_t
     p.pairs = (uint32_t *)ctx->s_pairs.p; p.block_sums = (int32_t *)ctx->s_bsums.p; p.totals = (int32_t *)ctx->s_totals.p;
     p.dist = (double *)ctx->s_dist.p; p.verdict = (uint8_t *)ctx->s_verdict.p; p.touched = (uint32_t *)ctx->d_touched.p;
     p.rec_verdict = (uint8_t *)ctx->s_rec_verdict.p;
-    p.topk_ids = d_topk_ids; p.topk_dist = d_topk_dist; p.n_ret = d_nret; p.n_dec = d_ndec; p.topk_rank = ctx->want_rank;
+    p.topk_ids = d_topk_ids; p.topk_dist = d_topk_dist; p.n_ret = d_nret; p.n_dec = d_ndec; p.topk_rank = ctx->want_rank; p.rank_map = ctx->rank_map;
     ENSURE(ctx->s_qf32, sizeof(float) * (size_t)Q * sv.dim);
     ENSURE(ctx->s_qu8, (size_t)Q * sv.dim + 16);
     ENSURE(ctx->s_f32_exact, 4 * sizeof(int32_t));
@@ -286,7 +286,7 @@ void fspann_ctx_destroy(fspann_ctx *ctx) {
                       &ctx->d_keyring, &ctx->d_hpow, &ctx->d_shoup, &ctx->s_rec_verdict, &ctx->s_qf32, &ctx->s_qu8, &ctx->s_f32_exact, &ctx->d_te0, &ctx->d_touched, &ctx->s_queries, &ctx->s_codes, &ctx->s_cand_ids,
                       &ctx->s_cand_sc, &ctx->s_ncand, &ctx->s_raw, &ctx->s_uniq_cnt, &ctx->s_route_scratch, &ctx->s_overflow, &ctx->s_route_ovf, &ctx->s_route_big, &ctx->s_cnt,
                       &ctx->s_flag, &ctx->s_fill, &ctx->s_uniq, &ctx->s_uoff, &ctx->s_pairs, &ctx->s_bsums, &ctx->s_totals, &ctx->s_dist, &ctx->s_verdict,
-                      &ctx->s_topk_ids, &ctx->s_topk_dist, &ctx->s_topk_rank, &ctx->s_nret, &ctx->s_ndec, &ctx->s_counters, &ctx->s_stage_a, &ctx->s_stage_b,
+                      &ctx->s_topk_ids, &ctx->s_topk_dist, &ctx->s_topk_rank, &ctx->sh_c_ids, &ctx->sh_c_rank, &ctx->sh_c_n, &ctx->s_nret, &ctx->s_ndec, &ctx->s_counters, &ctx->s_stage_a, &ctx->s_stage_b,
                       &ctx->s_stage_c, &ctx->s_vis_part, &ctx->s_vis_score, &ctx->s_vis_n, &ctx->r_rows, &ctx->r_queries, &ctx->r_codes, &ctx->r_topk_ids, &ctx->r_topk_dist, &ctx->r_nret,
                       &ctx->r_counters, &ctx->t_cand_ids, &ctx->t_cand_sc, &ctx->t_ncand, &ctx->t_raw, &ctx->t_uniq_cnt, &ctx->t_ndec,
                       &ctx->g_base, &ctx->g_q, &ctx->g_dist, &ctx->g_ids, &ctx->g_d2, &ctx->g_flag, &ctx->g_res, &ctx->g_nret, &ctx->g_rec,
@@ -319,6 +319,7 @@ int fspann_set_option(fspann_ctx *ctx, const char *name, int64_t value) {
     if (!strcmp(name, "graphs")) { ctx->opt_graphs = value != 0; return FSPANN_OK; }
     if (!strcmp(name, "route_general")) { ctx->opt_route_general = value != 0; return FSPANN_OK; }
     if (!strcmp(name, "route_wl_extra")) { ctx->opt_route_wl_extra = (int)value; return FSPANN_OK; }
+    if (!strcmp(name, "shard_compact")) { ctx->opt_shard_compact = value != 0; return FSPANN_OK; }
     if (!strcmp(name, "route_v1")) { ctx->opt_route_v1 = value != 0; return FSPANN_OK; }
     if (!strcmp(name, "h2d_overlap")) { ctx->opt_h2d_overlap = (int)std::min<int64_t>(std::max<int64_t>(value, 0), 4); return FSPANN_OK; }
     if (!strcmp(name, "tokengen_exact")) { ctx->opt_tokengen_exact = value != 0; return FSPANN_OK; }

@@ -52,6 +52,7 @@ struct fspann_ctx {
     // scratch (grow only)
     DevBuf s_vis_part, s_vis_score, s_vis_n;
     int opt_route_general = 0;   // force the general (sequential, cap-exact) Route kernel
+    int opt_shard_compact = 1;   // sharded search: compact the gathered candidate lists to this shard's ids before Refine
     int opt_route_v1 = 0;        // use the one-CTA-per-SM fast Route kernel only (A/B switch)
     int last_route_v2 = 0;
     int opt_route_wl_extra = -1; // test hook: clamp the fast path's dedicated worklist (forces the no-worklist fallback when exceeded)
@@ -61,8 +62,9 @@ struct fspann_ctx {
     DevBuf s_rec_verdict, s_qf32, s_qu8, s_f32_exact, s_vorder, s_voff, s_qfinite, s_retry_out, s_codes_in;
     DevKeyRing ring_host{};
     int32_t *want_rank = nullptr;
+    const int32_t *rank_map = nullptr;   // set around do_refine by the sharded search (shard-compacted candidate lists)
     DevBuf s_cnt, s_flag, s_fill, s_uniq, s_uoff, s_pairs, s_bsums, s_totals, s_dist, s_verdict;
-    DevBuf s_topk_ids, s_topk_dist, s_topk_rank, s_nret, s_ndec, s_counters;
+    DevBuf s_topk_ids, s_topk_dist, s_topk_rank, s_nret, s_ndec, s_counters, sh_c_ids, sh_c_rank, sh_c_n;
     DevBuf s_stage_a, s_stage_b, s_stage_c;  // upload staging
     DevBuf g_base, g_q, g_dist, g_ids, g_d2, g_flag, g_res, g_nret, g_rec;  // ground truth / recall
     DevBuf b_codes, b_staged, b_scratch, b_ids, b_keys, b_rep, b_flag;  // device index build

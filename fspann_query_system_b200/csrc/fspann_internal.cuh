@@ -122,6 +122,7 @@ struct RefineParams {
     double *topk_dist;  // [Q][k]
     int32_t *n_ret, *n_dec;
     int32_t *topk_rank;  // [Q][k] candidate position of each result (for the cross-shard merge), or nullptr
+    const int32_t *rank_map;  // [Q][stride] original position of every (shard-compacted) candidate slot, or nullptr: positions are the slots
 };
 
 // Opt a kernel in to the device's full dynamic shared memory (opt-in limit minus the kernel's static shared memory) on the CURRENT
@@ -178,6 +179,8 @@ int launch_refine_decrypt(cudaStream_t s, const StoreView &sv, const RefineParam
 int launch_queries_to_f32(cudaStream_t s, const double *q, float *out, uint8_t *out8, int64_t Q, int dim, int32_t *exact, uint8_t *qfinite);
 int launch_retry_select(cudaStream_t s, int64_t Q, int k, const int32_t *n_ret, const int32_t *n_dec, const int32_t *exact, int32_t *rows, int32_t *out);
 int launch_refine_topk(cudaStream_t s, const RefineParams &p);
+int launch_shard_compact(cudaStream_t s, int64_t Q, int stride, const int32_t *cand, const int32_t *n_cand, int64_t id_lo, int64_t id_hi,
+                         int32_t *out_ids, int32_t *out_rank, int32_t *out_n);
 int launch_counters(cudaStream_t s, int64_t Q, const int32_t *raw, const int32_t *uniq, const int32_t *n_dec,
                     const int32_t *n_ret, const int32_t *n_cand, int32_t retried, int64_t *counters, const uint8_t *qfinite);
 int launch_gather_rows(cudaStream_t s, const void *src, void *dst, const int32_t *rows, int64_t n_rows, int64_t row_bytes, bool scatter);

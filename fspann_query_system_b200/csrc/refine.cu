@@ -1225,7 +1225,7 @@ __global__ void __launch_bounds__(TK_THREADS) refine_topk_kernel(RefineParams p)
             s_last_key = b; s_last_rank = br;
             p.topk_ids[(size_t)q * p.k + round] = p.cand_ids[(size_t)q * p.stride + br];
             p.topk_dist[(size_t)q * p.k + round] = __longlong_as_double((long long)b);
-            if (p.topk_rank) p.topk_rank[(size_t)q * p.k + round] = br;
+            if (p.topk_rank) p.topk_rank[(size_t)q * p.k + round] = p.rank_map ? p.rank_map[(size_t)q * p.stride + br] : br;
         }
         __syncthreads();
     }
@@ -1250,14 +1250,16 @@ __global__ void __launch_bounds__(TKW_WARPS * 32) refine_topk_warp_kernel(Refine
     const int n = p.n_cand[q];
     const double *dist = p.dist + (size_t)q * p.stride;
     const uint8_t *ver = p.verdict + (size_t)q * p.stride;
+    const int ne = (n + 31) >> 5;                                // entries per lane that can be live (warp-uniform): short lists (one shard of a
+                                                                 // sharded store, ragged lists) skip the rest of the unrolled loops
     uint8_t vv[E];
 #pragma unroll
-    for (int j = 0; j < E; j++) { const int r = lane + 32 * j; vv[j] = r < n ? ver[r] : (uint8_t)0xff; }
+    for (int j = 0; j < E; j++) { const int r = lane + 32 * j; vv[j] = (j < ne && r < n) ? ver[r] : (uint8_t)0xff; }
     unsigned long long key[E];
     int ndec = 0;
 #pragma unroll
     for (int j = 0; j < E; j++) {
-        const bool ok = vv[j] == FSPANN_V_OK;
+        const bool ok = j < ne && vv[j] == FSPANN_V_OK;
         key[j] = ok ? (unsigned long long)__double_as_longlong(dist[lane + 32 * j]) : ~0ull;     // dist >= +0.0: the bits order like the values
         ndec += ok;
     }
@@ -1267,7 +1269,7 @@ __global__ void __launch_bounds__(TKW_WARPS * 32) refine_topk_warp_kernel(Refine
     for (int round = 0; round < eff; round++) {
         unsigned long long best = ~0ull; int bj = 0;
 #pragma unroll
-        for (int j = 0; j < E; j++) if (key[j] < best) { best = key[j]; bj = j; }          // ties: the lower rank (smaller j) stays
+        for (int j = 0; j < E; j++) if (j < ne && key[j] < best) { best = key[j]; bj = j; }   // ties: the lower rank (smaller j) stays
         int best_r = lane + 32 * bj;
         unsigned long long b = best; int br = best_r;
 #pragma unroll
@@ -1278,10 +1280,10 @@ __global__ void __launch_bounds__(TKW_WARPS * 32) refine_topk_warp_kernel(Refine
         }
         if (br == best_r && b == best) {                              // the owner lane retires the entry and emits the result (QSI:298-316)
 #pragma unroll
-            for (int j = 0; j < E; j++) key[j] = (j == bj) ? ~0ull : key[j];
+            for (int j = 0; j < E; j++) if (j < ne) key[j] = (j == bj) ? ~0ull : key[j];
             p.topk_ids[(size_t)q * p.k + round] = p.cand_ids[(size_t)q * p.stride + br];
             p.topk_dist[(size_t)q * p.k + round] = __longlong_as_double((long long)b);
-            if (p.topk_rank) p.topk_rank[(size_t)q * p.k + round] = br;
+            if (p.topk_rank) p.topk_rank[(size_t)q * p.k + round] = p.rank_map ? p.rank_map[(size_t)q * p.stride + br] : br;
         }
     }
     for (int i = eff + lane; i < p.k; i += 32) {
@@ -1430,7 +1432,7 @@ __global__ void __launch_bounds__(TS_THREADS) refine_topk_select_kernel(RefinePa
             const int br = s_rank[i];
             p.topk_ids[(size_t)q * p.k + i] = p.cand_ids[(size_t)q * p.stride + br];
             p.topk_dist[(size_t)q * p.k + i] = __longlong_as_double((long long)s_key[i]);
-            if (p.topk_rank) p.topk_rank[(size_t)q * p.k + i] = br;
+            if (p.topk_rank) p.topk_rank[(size_t)q * p.k + i] = p.rank_map ? p.rank_map[(size_t)q * p.stride + br] : br;
         }
     }
     for (int i = eff + tid; i < p.k; i += TS_THREADS) {
@@ -1439,6 +1441,36 @@ __global__ void __launch_bounds__(TS_THREADS) refine_topk_select_kernel(RefinePa
         if (p.topk_rank) p.topk_rank[(size_t)q * p.k + i] = 0x7fffffff;
     }
     if (tid == 0) { p.n_ret[q] = eff; if (p.n_dec) p.n_dec[q] = total_ok; }
+}
+
+// Database-sharded search: keeps, per query, only the candidates whose id lies in this shard's range [id_lo, id_hi), in their original
+// order, with their original positions (rank_out) -- the grouping passes and the per-shard top-k then look at ~B/W slots per query instead
+// of scanning all B for the ones they own.  Ids outside every shard (negative, >= n_global) only ever produce "not found" verdicts, which
+// no output of the sharded search reports, so they are dropped too.  One warp per query, ordered (ballot) compaction.
+__global__ void shard_compact_kernel(int64_t Q, int stride, const int32_t *__restrict__ cand, const int32_t *__restrict__ n_cand, int64_t id_lo,
+                                     int64_t id_hi, int32_t *__restrict__ out_ids, int32_t *__restrict__ out_rank, int32_t *__restrict__ out_n) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (q >= Q) return;
+    const int n = n_cand[q];
+    const int32_t *src = cand + (size_t)q * stride;
+    int32_t *dst = out_ids + (size_t)q * stride, *dstr = out_rank + (size_t)q * stride;
+    int run = 0;
+    for (int r0 = 0; r0 < n; r0 += 32) {
+        const int r = r0 + lane;
+        const int32_t id = r < n ? src[r] : -1;
+        const bool own = r < n && (int64_t)id >= id_lo && (int64_t)id < id_hi;
+        const unsigned b = __ballot_sync(0xffffffffu, own);
+        if (own) { const int o = run + __popc(b & ((1u << lane) - 1u)); dst[o] = id; dstr[o] = r; }
+        run += __popc(b);
+    }
+    if (lane == 0) out_n[q] = run;
+}
+int launch_shard_compact(cudaStream_t s, int64_t Q, int stride, const int32_t *cand, const int32_t *n_cand, int64_t id_lo, int64_t id_hi,
+                         int32_t *out_ids, int32_t *out_rank, int32_t *out_n) {
+    if (Q <= 0) return 0;
+    shard_compact_kernel<<<(unsigned)((Q * 32 + 255) / 256), 256, 0, s>>>(Q, stride, cand, n_cand, id_lo, id_hi, out_ids, out_rank, out_n);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
 int launch_refine_topk(cudaStream_t s, const RefineParams &p) {

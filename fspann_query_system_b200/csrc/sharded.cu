@@ -122,9 +122,18 @@ int sharded_pass(fspann_ctx *ctx, int64_t Q, const double *d_queries, int k, int
     ENSURE(ctx->sh_loc_ids, tk_i); ENSURE(ctx->sh_loc_dist, tk_d); ENSURE(ctx->sh_loc_rank, tk_i); ENSURE(ctx->sh_loc_nret, qi); ENSURE(ctx->sh_ndec, qi);
     ctx->want_rank = (int32_t *)ctx->sh_loc_rank.p;
     if (main_pass) { rc = record_ev(ctx, 0); if (rc) return rc; rc = record_ev(ctx, 1); if (rc) return rc; rc = record_ev(ctx, 2); if (rc) return rc; }
-    rc = do_refine(ctx, Q, d_queries, cand_all, ncand_all, B, k, (int32_t *)ctx->sh_loc_ids.p, (double *)ctx->sh_loc_dist.p, (int32_t *)ctx->sh_loc_nret.p,
+    const int32_t *ref_cand = cand_all, *ref_n = ncand_all;
+    if (W > 1 && ctx->opt_shard_compact) {
+        // shard-local lists: this shard's candidates only, in order, with their positions in the full lists (the merge orders on those)
+        ENSURE(ctx->sh_c_ids, sizeof(int32_t) * (size_t)Q * B); ENSURE(ctx->sh_c_rank, sizeof(int32_t) * (size_t)Q * B); ENSURE(ctx->sh_c_n, qi);
+        LAUNCHED(launch_shard_compact(ctx->stream, Q, B, cand_all, ncand_all, ctx->sv.id_base, ctx->sv.id_base + ctx->sv.N, (int32_t *)ctx->sh_c_ids.p,
+                                      (int32_t *)ctx->sh_c_rank.p, (int32_t *)ctx->sh_c_n.p));
+        ref_cand = (const int32_t *)ctx->sh_c_ids.p; ref_n = (const int32_t *)ctx->sh_c_n.p;
+        ctx->rank_map = (const int32_t *)ctx->sh_c_rank.p;
+    }
+    rc = do_refine(ctx, Q, d_queries, ref_cand, ref_n, B, k, (int32_t *)ctx->sh_loc_ids.p, (double *)ctx->sh_loc_dist.p, (int32_t *)ctx->sh_loc_nret.p,
                    (int32_t *)ctx->sh_ndec.p, main_pass);
-    ctx->want_rank = nullptr;
+    ctx->want_rank = nullptr; ctx->rank_map = nullptr;
     if (rc) return rc;
     if (main_pass) { ctx->ev_valid = true; CK(cudaEventRecord(ctx->sh_ev[3], ctx->stream)); }
     // ---- 4. per-shard top-k of every rank + total decrypted count, then the global stable top-k
