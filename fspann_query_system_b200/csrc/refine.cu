@@ -1266,6 +1266,17 @@ __global__ void __launch_bounds__(TKW_WARPS * 32) refine_topk_warp_kernel(Refine
 #pragma unroll
     for (int o = 16; o; o >>= 1) ndec += __shfl_xor_sync(0xffffffffu, ndec, o);
     const int eff = min(p.k, ndec);
+    // The selected (distance, position) of round t is parked in lane t & 31 and written out 32 results at a time: an id look-up + three
+    // stores inside every round would put a dependent global load on the critical path of each of the k rounds.
+    unsigned long long my_b = 0ull; int my_br = 0;
+    auto flush = [&](int base, int cnt) {                             // results base .. base + cnt - 1 sit in lanes 0 .. cnt - 1
+        if (lane < cnt) {
+            const size_t o = (size_t)q * p.k + base + lane;
+            p.topk_ids[o] = p.cand_ids[(size_t)q * p.stride + my_br];    // QSI:298-316
+            p.topk_dist[o] = __longlong_as_double((long long)my_b);
+            if (p.topk_rank) p.topk_rank[o] = p.rank_map ? p.rank_map[(size_t)q * p.stride + my_br] : my_br;
+        }
+    };
     for (int round = 0; round < eff; round++) {
         unsigned long long best = ~0ull; int bj = 0;
 #pragma unroll
@@ -1278,14 +1289,14 @@ __global__ void __launch_bounds__(TKW_WARPS * 32) refine_topk_warp_kernel(Refine
             const int orr = __shfl_xor_sync(0xffffffffu, br, o);
             if (ok < b || (ok == b && orr < br)) { b = ok; br = orr; }
         }
-        if (br == best_r && b == best) {                              // the owner lane retires the entry and emits the result (QSI:298-316)
+        if (br == best_r && b == best) {                              // the owner lane retires the entry
 #pragma unroll
             for (int j = 0; j < E; j++) if (j < ne) key[j] = (j == bj) ? ~0ull : key[j];
-            p.topk_ids[(size_t)q * p.k + round] = p.cand_ids[(size_t)q * p.stride + br];
-            p.topk_dist[(size_t)q * p.k + round] = __longlong_as_double((long long)b);
-            if (p.topk_rank) p.topk_rank[(size_t)q * p.k + round] = p.rank_map ? p.rank_map[(size_t)q * p.stride + br] : br;
         }
+        if (lane == (round & 31)) { my_b = b; my_br = br; }
+        if ((round & 31) == 31) flush(round - 31, 32);
     }
+    if (eff & 31) flush(eff & ~31, eff & 31);
     for (int i = eff + lane; i < p.k; i += 32) {
         p.topk_ids[(size_t)q * p.k + i] = -1;
         p.topk_dist[(size_t)q * p.k + i] = __longlong_as_double(0x7ff8000000000000ll);
