@@ -1277,7 +1277,60 @@ __global__ void __launch_bounds__(TKW_WARPS * 32) refine_topk_warp_kernel(Refine
             if (p.topk_rank) p.topk_rank[o] = p.rank_map ? p.rank_map[(size_t)q * p.stride + my_br] : my_br;
         }
     };
-    for (int round = 0; round < eff; round++) {
+    // Small k: prune first.  Let T be the eff-th smallest of the 32 lane minima: at least eff entries are <= T, so every entry of the true
+    // top-eff is <= T as well.  Typically ~eff..2*eff of the up to 1024 entries survive; they are compacted (ordered ballots) into <= 64
+    // slots = two per lane, and the eff selection rounds then cost two compares + one warp reduction each instead of a scan of E entries.
+    bool pruned = false;
+    if (eff > 0 && eff <= 16) {
+        __shared__ unsigned long long s_pk[TKW_WARPS][64];
+        __shared__ int s_pr[TKW_WARPS][64];
+        const int w = threadIdx.x >> 5;
+        unsigned long long lmin = ~0ull;
+#pragma unroll
+        for (int j = 0; j < E; j++) if (j < ne) lmin = min(lmin, key[j]);
+        unsigned long long x = lmin;                              // bitonic sort of the lane minima across the warp
+#pragma unroll
+        for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+            for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+                const unsigned long long y = __shfl_xor_sync(0xffffffffu, x, jj);
+                const bool lower = (lane & jj) == 0, asc = (lane & kk) == 0;
+                x = (lower == asc) ? min(x, y) : max(x, y);
+            }
+        }
+        const unsigned long long T = __shfl_sync(0xffffffffu, x, eff - 1);
+        int run = 0;
+#pragma unroll
+        for (int j = 0; j < E; j++) {
+            if (j < ne) {
+                const bool keep = key[j] <= T && key[j] != ~0ull;
+                const unsigned bal = __ballot_sync(0xffffffffu, keep);
+                if (keep) { const int o = run + __popc(bal & ((1u << lane) - 1u)); if (o < 64) { s_pk[w][o] = key[j]; s_pr[w][o] = lane + 32 * j; } }
+                run += __popc(bal);
+            }
+        }
+        if (run <= 64) {                                          // warp-uniform
+            __syncwarp();
+            unsigned long long k0 = lane < run ? s_pk[w][lane] : ~0ull, k1 = lane + 32 < run ? s_pk[w][lane + 32] : ~0ull;
+            const int r0 = lane < run ? s_pr[w][lane] : 0x7fffffff, r1 = lane + 32 < run ? s_pr[w][lane + 32] : 0x7fffffff;
+            for (int round = 0; round < eff; round++) {
+                const bool first = k0 < k1 || (k0 == k1 && r0 < r1);
+                unsigned long long b = first ? k0 : k1; int br = first ? r0 : r1;
+                const unsigned long long mine = b; const int mine_r = br;
+#pragma unroll
+                for (int o = 16; o; o >>= 1) {
+                    const unsigned long long ok = __shfl_xor_sync(0xffffffffu, b, o);
+                    const int orr = __shfl_xor_sync(0xffffffffu, br, o);
+                    if (ok < b || (ok == b && orr < br)) { b = ok; br = orr; }
+                }
+                if (br == mine_r && b == mine) { if (first) k0 = ~0ull; else k1 = ~0ull; }
+                if (lane == (round & 31)) { my_b = b; my_br = br; }
+            }
+            flush(0, eff);
+            pruned = true;
+        }
+    }
+    for (int round = 0; !pruned && round < eff; round++) {
         unsigned long long best = ~0ull; int bj = 0;
 #pragma unroll
         for (int j = 0; j < E; j++) if (j < ne && key[j] < best) { best = key[j]; bj = j; }   // ties: the lower rank (smaller j) stays
@@ -1296,7 +1349,7 @@ __global__ void __launch_bounds__(TKW_WARPS * 32) refine_topk_warp_kernel(Refine
         if (lane == (round & 31)) { my_b = b; my_br = br; }
         if ((round & 31) == 31) flush(round - 31, 32);
     }
-    if (eff & 31) flush(eff & ~31, eff & 31);
+    if (!pruned && (eff & 31)) flush(eff & ~31, eff & 31);
     for (int i = eff + lane; i < p.k; i += 32) {
         p.topk_ids[(size_t)q * p.k + i] = -1;
         p.topk_dist[(size_t)q * p.k + i] = __longlong_as_double(0x7ff8000000000000ll);

@@ -116,18 +116,18 @@ def test_refine_verdicts_topk_bit_exact(wg):
         assert np.array_equal(out["top_dist"][q, :n].view(np.uint64), ref["top_dist"].view(np.uint64)), "distances must be bit-exact FP64"
 
 
-@pytest.mark.parametrize("k", [1, 10, 64, 300])
-def test_refine_long_lists_with_exact_distance_ties(wg, k):
+@pytest.mark.parametrize("B", [2500, 600], ids=["radix-select", "warp-kernel"])
+@pytest.mark.parametrize("k", [1, 10, 16, 17, 64, 300])
+def test_refine_long_lists_with_exact_distance_ties(wg, k, B):
     """Candidate lists beyond 1024 entries take the radix-select top-k.  Lists that name the same records several times give many
     EXACT distance ties, which the reference's stable sort (QSI:298) resolves by candidate order; ragged / empty lists included."""
     w, ctx = wg
     Q = min(12, w.queries.shape[0])
-    B = 2500
     rng = np.random.default_rng(17 + k)
     cand = np.full((Q, B), -1, dtype=np.int32)
     ncand = np.zeros(Q, dtype=np.int32)
     for q in range(Q):
-        n = [B, 1100, 0, 1025, 2499][q % 5]
+        n = [B, 1100, 0, 1025, 2499][q % 5] if B > 1024 else [B, 33, 0, 1, B - 1][q % 5]
         distinct = rng.choice(w.cfg.N, size=min(w.cfg.N, max(1, n // (1 + q % 4))), replace=False)
         lst = rng.choice(distinct, size=n, replace=True) if n else np.zeros(0, dtype=np.int64)
         cand[q, :n] = lst
