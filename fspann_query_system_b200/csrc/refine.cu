@@ -125,11 +125,18 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(int32_t *__res
 }
 __global__ void refine_fill_kernel(StoreView sv, RefineParams p) {
     const int64_t total = p.Q * (int64_t)p.stride;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        if (p.verdict[i] != 0xfe) continue;
-        const int32_t id = (int32_t)(p.cand_ids[i] - sv.id_base);
-        const int pos = p.cnt[id] + atomicAdd(&p.fill[id], 1);
-        p.pairs[pos] = (uint32_t)i;
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    // four slots per thread and iteration: the returning atomics (an L2 round trip each) of the four are in flight together
+    for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < total; i0 += 4 * step) {
+        int32_t id[4]; int base[4], off[4]; bool live[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { const int64_t i = i0 + u * step; live[u] = i < total && p.verdict[i] == 0xfe; }
+#pragma unroll
+        for (int u = 0; u < 4; u++) id[u] = live[u] ? (int32_t)(p.cand_ids[i0 + u * step] - sv.id_base) : 0;
+#pragma unroll
+        for (int u = 0; u < 4; u++) { base[u] = live[u] ? p.cnt[id[u]] : 0; off[u] = live[u] ? atomicAdd(&p.fill[id[u]], 1) : 0; }
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (live[u]) p.pairs[base[u] + off[u]] = (uint32_t)(i0 + u * step);
     }
 }
 
