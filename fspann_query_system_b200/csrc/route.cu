@@ -908,6 +908,7 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) route_fast_kernel(RoutingView r
 // Same results as route_fast_kernel bit for bit (same filters, same exact path, same selection keys).
 // =====================================================================================================================
 constexpr int R2_THREADS = 512;           // 16 warps per CTA, two CTAs per SM (768 threads = 48 warps per SM at 40 registers was measured slower: 2.00 vs 1.80 ms)
+constexpr int R2_U = 5;                   // 16-byte id slices a thread keeps in flight in the gather passes
 constexpr int R2_H = 512;                 // the sort works on 2 x R2_H keys held by the first R2_H threads
 constexpr int RS_SEGMAX = 16384;          // keys one route_sort_big_kernel CTA orders (16 per thread)
 constexpr int RS_MAXSEG = 4;              // segments per query (n_raw <= 32000 needs at most 4 greedy segments of <= RS_SEGMAX)
@@ -1087,17 +1088,17 @@ __global__ void __launch_bounds__(R2_THREADS, 2) route_fast2_kernel(RoutingView 
         if (tid < 256) s_hist[tid] = 0;
         if (tid == 0) { s_raw = 0; s_uniq = 0; s_m = 0; s_ncls = 0; s_nwl = 0; s_nlow = 0; }
         __syncthreads();
-        // ---- 2. gather ids (16-byte slices of the 256-byte partition rows, two in flight) and set the two 2-bit filters ----
-        for (int q0 = tid; q0 < n4; q0 += 2 * R2_THREADS) {
-            int32_t idv[2][4];
+        // ---- 2. gather ids (16-byte slices of the 256-byte partition rows, R2_U in flight) and set the two 2-bit filters ----
+        for (int q0 = tid; q0 < n4; q0 += R2_U * R2_THREADS) {
+            int32_t idv[R2_U][4];
 #pragma unroll
-            for (int u = 0; u < 2; u++) {
+            for (int u = 0; u < R2_U; u++) {
                 const int e = (q0 + u * R2_THREADS) << 2;
                 if (e < n_raw) gather4(e, idv[u]);
                 else { idv[u][0] = idv[u][1] = idv[u][2] = idv[u][3] = -1; }
             }
 #pragma unroll
-            for (int u = 0; u < 2; u++) {
+            for (int u = 0; u < R2_U; u++) {
                 if ((idv[u][0] | idv[u][1] | idv[u][2] | idv[u][3]) >= 0) {      // the common case: four live ids, no per-id test
 #pragma unroll
                     for (int j = 0; j < 4; j++) filter_set(idv[u][j]);
@@ -1111,16 +1112,16 @@ __global__ void __launch_bounds__(R2_THREADS, 2) route_fast2_kernel(RoutingView 
         // ---- 3. classify (ids re-read from L2): single, or involved -> bitmap + per-visit counter + worklist (slot: id, position) ----
         int my_raw = 0, my_uniq = 0;
         bool fits = true;
-        for (int q0 = tid; q0 < n4; q0 += 2 * R2_THREADS) {
-            int32_t idv[2][4];
+        for (int q0 = tid; q0 < n4; q0 += R2_U * R2_THREADS) {
+            int32_t idv[R2_U][4];
 #pragma unroll
-            for (int u = 0; u < 2; u++) {
+            for (int u = 0; u < R2_U; u++) {
                 const int e = (q0 + u * R2_THREADS) << 2;
                 if (e < n_raw) gather4(e, idv[u]);
                 else { idv[u][0] = idv[u][1] = idv[u][2] = idv[u][3] = -1; }
             }
 #pragma unroll
-            for (int u = 0; u < 2; u++) {
+            for (int u = 0; u < R2_U; u++) {
                 const int e = (q0 + u * R2_THREADS) << 2;
                 uint32_t invmask = 0; int dead = 0;
                 if ((idv[u][0] | idv[u][1] | idv[u][2] | idv[u][3]) >= 0) {
