@@ -338,12 +338,24 @@ __global__ void tokengen_recheck_kernel(RoutingView rv, const double *__restrict
         const double *v = queries + q * dim, *al = rv.alpha + ((size_t)g * m + j) * dim;
         double acc = 0.0;
         int i = 0;
-        for (; i + 8 <= dim; i += 8) {                                  // 16 independent loads in flight, strictly sequential adds
+        // strictly sequential adds (Coding:349-353), loads software-pipelined: the 16 loads of the next 8 terms are issued before the adds of the
+        // current 8, so a thread waits for one memory latency per 8 terms only while the pipeline fills (few threads have work: latency-bound)
+        if (dim >= 8) {
             double a[8], b[8];
 #pragma unroll
-            for (int u = 0; u < 8; u++) { a[u] = __ldg(v + i + u); b[u] = __ldg(al + i + u); }
+            for (int u = 0; u < 8; u++) { a[u] = __ldg(v + u); b[u] = __ldg(al + u); }
+            for (; i + 16 <= dim; i += 8) {
+                double a2[8], b2[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) { a2[u] = __ldg(v + i + 8 + u); b2[u] = __ldg(al + i + 8 + u); }
+#pragma unroll
+                for (int u = 0; u < 8; u++) acc = __dadd_rn(acc, __dmul_rn(a[u], b[u]));
+#pragma unroll
+                for (int u = 0; u < 8; u++) { a[u] = a2[u]; b[u] = b2[u]; }
+            }
 #pragma unroll
             for (int u = 0; u < 8; u++) acc = __dadd_rn(acc, __dmul_rn(a[u], b[u]));
+            i += 8;
         }
         for (; i < dim; i++) acc = __dadd_rn(acc, __dmul_rn(v[i], al[i]));
         const double y = __dadd_rn(acc, rv.r[(size_t)g * m + j]);
