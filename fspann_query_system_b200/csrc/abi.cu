@@ -148,6 +148,8 @@ int do_route(fspann_ctx *ctx, int64_t Q, const uint64_t *d_codes, int probes, in
         if (ctx->opt_route_wl_extra >= 0 && fx.wl_extra > ctx->opt_route_wl_extra) fx.wl_extra = ctx->opt_route_wl_extra & ~7;   // smem size kept
         if (ctx->opt_route_wl_extra >= 0 && fx.v2_wl_cap > ctx->opt_route_wl_extra) fx.v2_wl_cap = std::max(16, ctx->opt_route_wl_extra & ~15);
         if (ctx->opt_route_v1 && fx.v1_ok) fx.v2_smem = 0;
+        // at most one query per SM: the one-CTA kernel gives a single query 1024 threads and needs no overflow pass (latency of small batches)
+        if (fx.v1_ok && Q <= ctx->sm_count && ctx->opt_route_wl_extra < 0 && ctx->opt_route_small_v1) fx.v2_smem = 0;
         ENSURE(ctx->s_route_ovf, sizeof(int32_t) * ((size_t)Q + 4));
         fx.ovf_n = (int32_t *)ctx->s_route_ovf.p; fx.ovf_list = fx.ovf_n + 4;
         ENSURE(ctx->s_vis_part, sizeof(int32_t) * (size_t)Q * rv.TD * probes);
@@ -319,6 +321,7 @@ int fspann_set_option(fspann_ctx *ctx, const char *name, int64_t value) {
     if (!strcmp(name, "graphs")) { ctx->opt_graphs = value != 0; return FSPANN_OK; }
     if (!strcmp(name, "route_general")) { ctx->opt_route_general = value != 0; return FSPANN_OK; }
     if (!strcmp(name, "route_wl_extra")) { ctx->opt_route_wl_extra = (int)value; return FSPANN_OK; }
+    if (!strcmp(name, "route_small_v1")) { ctx->opt_route_small_v1 = value != 0; return FSPANN_OK; }
     if (!strcmp(name, "shard_compact")) { ctx->opt_shard_compact = value != 0; return FSPANN_OK; }
     if (!strcmp(name, "route_v1")) { ctx->opt_route_v1 = value != 0; return FSPANN_OK; }
     if (!strcmp(name, "h2d_overlap")) { ctx->opt_h2d_overlap = (int)std::min<int64_t>(std::max<int64_t>(value, 0), 4); return FSPANN_OK; }

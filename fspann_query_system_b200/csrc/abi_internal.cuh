@@ -53,6 +53,7 @@ struct fspann_ctx {
     DevBuf s_vis_part, s_vis_score, s_vis_n;
     int opt_route_general = 0;   // force the general (sequential, cap-exact) Route kernel
     int opt_shard_compact = 1;   // sharded search: compact the gathered candidate lists to this shard's ids before Refine
+    int opt_route_small_v1 = 1;  // batches of at most one query per SM take the one-CTA Route kernel (0: keep the two-CTA kernel, tests)
     int opt_route_v1 = 0;        // use the one-CTA-per-SM fast Route kernel only (A/B switch)
     int last_route_v2 = 0;
     int opt_route_wl_extra = -1; // test hook: clamp the fast path's dedicated worklist (forces the no-worklist fallback when exceeded)

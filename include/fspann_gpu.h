@@ -70,7 +70,8 @@ int64_t fspann_ctx_launch_count(const fspann_ctx *ctx);
 /* Tuning / test switches: "route_general" = 1 forces the general Route kernel (sequential groups, exact HARD_CAP
  * semantics) even where the shared-memory fast path applies; "route_v1" = 1 keeps the fast path on its one-CTA-per-SM kernel (the
  * default for refinementLimit <= 1024 is the two-CTA kernel, which hands the queries it cannot hold to the one-CTA kernel);
- * "route_wl_extra" = n >= 0 clamps the fast path's dedicated worklist to n entries (test hook for the overflow fallbacks),
+ * "route_small_v1" = 0 keeps batches of at most one query per SM on the two-CTA kernel too (by default they take the one-CTA kernel: lower
+ * latency, no overflow pass); "route_wl_extra" = n >= 0 clamps the fast path's dedicated worklist to n entries (test hook for the overflow fallbacks),
  * -1 = automatic; "h2d_overlap" = n (default 2, 0 = off): the host-pointer search entries upload a batch of >= 4096 queries in n
  * chunks on a copy stream so TokenGen + Route of a chunk overlap the PCIe copy of the next (with supplied codes: the whole query
  * upload overlaps Route); "tokengen_exact" = 1 runs the exact FP64 TokenGen

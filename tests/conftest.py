@@ -54,6 +54,7 @@ class World:
         from fspann_query_system_b200.gpu import GpuContext
         g, ix = self.g, self.ix
         ctx = GpuContext(0, debug=debug)
+        ctx.set_option("route_small_v1", 0)       # test batches are smaller than the SM count: keep Route on the two-CTA kernel (the default for real batches)
         ctx.routing_upload(g.dim, g.T, g.D, g.m, g.lam, g.alpha, g.r, g.omega, ix.min_key, ix.max_key, ix.rep, ix.ids)
         for v, k in self.store.keys.items():
             ctx.keys_set(v, k)

@@ -198,7 +198,11 @@ def test_route_fast_path_with_binding_cap_and_long_lists_at_full_size(c2, probes
     g = O.GFunctions(cfg.dim, cfg.T, cfg.D, cfg.m, cfg.lam, c2["alpha"], c2["r"], c2["omega"])
     ix = O.Index(g, cfg.N, c2["mn"].shape[1], c2["mn"], c2["mx"], c2["rep"], c2["ids"])
     codes = O.tokengen_batch(q, g)
-    out = gpu.route_batch(codes, probes, hard_cap, B)
+    gpu.set_option("route_small_v1", 0)                                  # 96 queries < SM count: keep them on the two-CTA kernel under test
+    try:
+        out = gpu.route_batch(codes, probes, hard_cap, B)
+    finally:
+        gpu.set_option("route_small_v1", 1)
     assert gpu.get_info("last_route_path") == 1 and gpu.get_info("last_route_v2") == 1
     assert gpu.get_info("route_overflowed") <= NQ // 10
     n_raw = cfg.T * cfg.D * probes * 64

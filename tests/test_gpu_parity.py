@@ -49,6 +49,7 @@ def test_route_candidates_ordered_bit_exact(wg, probes, hard_cap, B, general):
     B = min(B, 8192)
     ctx.set_option("route_general", int(general == 1))
     ctx.set_option("route_v1", int(general == 2))
+    ctx.set_option("route_small_v1", 0)         # (the fixture's setting) batches smaller than the SM count stay on the two-CTA kernel under test
     try:
         out = ctx.route_batch(codes, probes, hard_cap, B)
     finally:
@@ -308,3 +309,21 @@ def test_tokengen_prefilter_and_exact_kernel_agree_incl_boundary_vectors(wg):
     if g.dim <= 128 and g.W == 1:
         assert 3 in paths                                                # the tensor-core path did run for this shape
     assert np.array_equal(ctx.tokengen_batch(vecs[:7]), ref[:7]) and ctx.get_info("tokengen_overflow") == 0
+
+
+def test_small_batches_take_the_one_cta_route_kernel_with_identical_results(wg):
+    """Batches of at most one query per SM route on the one-CTA kernel by default (latency); same candidates as the two-CTA kernel."""
+    w, ctx = wg
+    codes = O.tokengen_batch(w.queries, w.g)
+    a = ctx.route_batch(codes, 5, 1 << 20, 64)
+    va = ctx.get_info("last_route_v2")
+    ctx.set_option("route_small_v1", 1)
+    try:
+        b = ctx.route_batch(codes, 5, 1 << 20, 64)
+        vb = ctx.get_info("last_route_v2")
+    finally:
+        ctx.set_option("route_small_v1", 0)
+    if ctx.get_info("last_route_path") == 1:
+        assert va == 1 and vb == 0
+    for key in ("cand_ids", "cand_scores", "n_cand", "unique", "raw_seen"):
+        assert np.array_equal(a[key], b[key]), key
