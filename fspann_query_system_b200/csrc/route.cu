@@ -1446,10 +1446,11 @@ __global__ void __launch_bounds__(R2_THREADS, 2) route_fast2_kernel(RoutingView 
     }
 }
 
-// Orders the candidates route_fast2_kernel<.., BIG> selected: one CTA per query, E 64-bit keys (score | Java bucket | position) per thread,
-// element i = u * RS_THREADS + tid lives in register u of thread tid.  Bitonic network: strides >= RS_THREADS pair two registers of one
-// thread, strides 32..512 go through shared memory (consecutive lanes touch consecutive words: conflict-free), strides < 32 are warp
-// shuffles.  Then the id of every position is read back from the partition rows.
+// Orders the candidates route_fast2_kernel<.., BIG> selected: one CTA per segment, E 64-bit keys (score | Java bucket | position) per thread,
+// thread tid OWNS the contiguous elements tid*E .. tid*E+E-1.  Bitonic network: strides below E pair two registers of one thread (50 of
+// the 105 stages at E = 16), strides E .. 16E are warp shuffles (thread distance 1 .. 16), only strides >= 32E go through shared memory
+// (15 stages; stored transposed, [u][tid], so consecutive lanes touch consecutive words).  Then the id of every position is read back
+// from the partition rows.
 constexpr int RS_THREADS = 1024;
 
 template <int E>
@@ -1467,52 +1468,50 @@ __global__ void __launch_bounds__(RS_THREADS, 1) route_sort_big_kernel(RoutingVi
         const unsigned long long *src = x.big_keys + (size_t)q * p.B + s0;
         unsigned long long a[E];
 #pragma unroll
-        for (int u = 0; u < E; u++) { const int i = u * RS_THREADS + tid; a[u] = i < m ? src[i] : ~0ull; }
+        for (int u = 0; u < E; u++) { const int i = tid * E + u; a[u] = i < m ? src[i] : ~0ull; }
 #pragma unroll 1
         for (int k = 2; k <= n; k <<= 1) {
-            // strides inside the thread: j = jl * RS_THREADS pairs registers u and u | jl
+            const bool asc_t = ((tid * E) & k) == 0;                     // direction of this thread's block once k >= E
+#pragma unroll 1
+            for (int j = k >> 1; j >= E; j >>= 1) {                      // partner in another thread, td threads away
+                const int td = j / E;
+                const bool lower = (tid & td) == 0;
+                if (td >= 32) {
+                    __syncthreads();
 #pragma unroll
-            for (int jl = E / 2; jl > 0; jl >>= 1) {
-                if (jl * RS_THREADS < k) {
+                    for (int u = 0; u < E; u++) sk[u * RS_THREADS + tid] = a[u];
+                    __syncthreads();
+#pragma unroll
+                    for (int u = 0; u < E; u++) {
+                        const unsigned long long b = sk[u * RS_THREADS + (tid ^ td)];
+                        a[u] = (lower == asc_t) ? min(a[u], b) : max(a[u], b);
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < E; u++) {
+                        const unsigned long long b = __shfl_xor_sync(0xffffffffu, a[u], td);
+                        a[u] = (lower == asc_t) ? min(a[u], b) : max(a[u], b);
+                    }
+                }
+            }
+#pragma unroll
+            for (int jl = E / 2; jl > 0; jl >>= 1) {                     // strides inside the thread's block: registers only
+                if (jl < k) {
 #pragma unroll
                     for (int u = 0; u < E; u++) {
                         if ((u & jl) == 0) {
-                            const bool asc = ((u * RS_THREADS + tid) & k) == 0;
+                            const bool asc = k >= E ? asc_t : ((u & k) == 0);
                             const unsigned long long lo = min(a[u], a[u | jl]), hi = max(a[u], a[u | jl]);
                             a[u] = asc ? lo : hi; a[u | jl] = asc ? hi : lo;
                         }
                     }
                 }
             }
-#pragma unroll 1
-            for (int j = min(k >> 1, RS_THREADS >> 1); j >= 32; j >>= 1) {  // partner in another warp: through shared memory
-                __syncthreads();
-#pragma unroll
-                for (int u = 0; u < E; u++) sk[u * RS_THREADS + tid] = a[u];
-                __syncthreads();
-                const bool lower = (tid & j) == 0;
-#pragma unroll
-                for (int u = 0; u < E; u++) {
-                    const unsigned long long b = sk[u * RS_THREADS + (tid ^ j)];
-                    const bool asc = ((u * RS_THREADS + tid) & k) == 0;
-                    a[u] = (lower == asc) ? min(a[u], b) : max(a[u], b);
-                }
-            }
-#pragma unroll 1
-            for (int j = min(k >> 1, 16); j > 0; j >>= 1) {                 // partner in the same warp
-                const bool lower = (tid & j) == 0;
-#pragma unroll
-                for (int u = 0; u < E; u++) {
-                    const unsigned long long b = __shfl_xor_sync(0xffffffffu, a[u], j);
-                    const bool asc = ((u * RS_THREADS + tid) & k) == 0;
-                    a[u] = (lower == asc) ? min(a[u], b) : max(a[u], b);
-                }
-            }
         }
         int32_t *out_id = p.cand_ids + (size_t)q * p.B + s0, *out_sc = p.cand_scores + (size_t)q * p.B + s0;
 #pragma unroll
         for (int u = 0; u < E; u++) {
-            const int i = u * RS_THREADS + tid;
+            const int i = tid * E + u;
             if (i < m) {
                 const uint32_t e = (uint32_t)(a[u] & 0xffffull), v = e >> 6;
                 const int g = (int)v / probes, jv = (int)v - g * probes;
