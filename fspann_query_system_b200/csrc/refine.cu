@@ -1399,10 +1399,50 @@ __global__ void __launch_bounds__(TS_THREADS) refine_topk_select_kernel(RefinePa
     const int eff = min(p.k, total_ok);
     __syncthreads();
 
+    // ---- 0. prune (k <= 256): with T = the eff-th smallest of the 256 per-thread minima at least eff keys are <= T, so the true top-eff is
+    //         among the keys <= T -- typically a few hundred of the thousands of candidates.  When they fit the sort buffer the radix
+    //         levels (eight passes over the whole list) are skipped: one ordered pass collects them and the sort below finishes. ----
+    bool pruned = false;
+    unsigned long long T = 0ull;
+    int n_sorted = eff;
+    if (eff > 0 && eff <= TS_THREADS) {
+        unsigned long long x = ~0ull;
+        for (int r = tid; r < n; r += TS_THREADS)
+            if (ver[r] == FSPANN_V_OK) x = min(x, (unsigned long long)__double_as_longlong(dist[r]));
+#pragma unroll 1
+        for (int kk = 2; kk <= TS_THREADS; kk <<= 1) {            // bitonic sort of the minima, one per thread
+#pragma unroll 1
+            for (int j = kk >> 1; j > 0; j >>= 1) {
+                unsigned long long y;
+                if (j >= 32) { __syncthreads(); s_key[tid] = x; __syncthreads(); y = s_key[tid ^ j]; }
+                else y = __shfl_xor_sync(0xffffffffu, x, j);
+                const bool lower = (tid & j) == 0, asc = (tid & kk) == 0;
+                x = (lower == asc) ? min(x, y) : max(x, y);
+            }
+        }
+        __syncthreads();
+        s_key[tid] = x;
+        if (tid == 0) s_cnt = 0;
+        __syncthreads();
+        T = s_key[eff - 1];
+        __syncthreads();
+        if (T != ~0ull) {
+            int c = 0;
+            for (int r = tid; r < n; r += TS_THREADS)
+                c += ver[r] == FSPANN_V_OK && (unsigned long long)__double_as_longlong(dist[r]) <= T;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            if (lane == 0) atomicAdd(&s_cnt, c);
+            __syncthreads();
+            const int S = s_cnt;
+            __syncthreads();
+            if (S <= TS_MAXK) { pruned = true; n_sorted = S; }
+        }
+    }
     if (eff > 0) {
         // ---- 1. radix select: prefix of the eff-th smallest key ----
-        unsigned long long prefix = 0ull;
-        int cum = 0, used = 0;
+        unsigned long long prefix = pruned ? T : 0ull;
+        int cum = 0, used = pruned ? 64 : 0;
         for (; used < 64; used += 8) {
             const int shift = 56 - used;
             s_hist[tid] = 0;
@@ -1446,7 +1486,7 @@ __global__ void __launch_bounds__(TS_THREADS) refine_topk_select_kernel(RefinePa
             if (cum + bin_n == eff) { used += 8; break; }      // the whole bin is selected: no finer split needed
         }
         const int pshift = 64 - used;                          // keys compare through their top `used` bits
-        const int need_tie = eff - cum;
+        const int need_tie = pruned ? 0x7fffffff : eff - cum;  // pruned: every key <= T is collected, the sort picks the first eff
         // ---- 2. ordered pass: below the prefix -> taken; equal -> taken in candidate order until need_tie ----
         int run_sel = 0, run_tie = 0;                          // block-uniform running counts
         for (int r0 = 0; r0 < n; r0 += TS_THREADS) {
@@ -1481,9 +1521,9 @@ __global__ void __launch_bounds__(TS_THREADS) refine_topk_select_kernel(RefinePa
             (void)less_before; (void)less_total;
             __syncthreads();
         }
-        // ---- 3. bitonic sort of the eff pairs on (key, rank) ----
-        int m = 1; while (m < eff) m <<= 1;
-        for (int i = eff + tid; i < m; i += TS_THREADS) { s_key[i] = ~0ull; s_rank[i] = 0x7fffffff; }
+        // ---- 3. bitonic sort of the collected pairs on (key, rank) ----
+        int m = 1; while (m < n_sorted) m <<= 1;
+        for (int i = n_sorted + tid; i < m; i += TS_THREADS) { s_key[i] = ~0ull; s_rank[i] = 0x7fffffff; }
         __syncthreads();
         for (int kk = 2; kk <= m; kk <<= 1) {
             for (int j = kk >> 1; j > 0; j >>= 1) {
