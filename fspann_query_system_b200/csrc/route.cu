@@ -1475,7 +1475,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) route_sort_big_kernel(RoutingVi
 #pragma unroll 1
             for (int j = k >> 1; j >= E; j >>= 1) {                      // partner in another thread, td threads away
                 const int td = j / E;
-                const bool lower = (tid & td) == 0;
+                const bool want_min = ((tid & td) == 0) == asc_t;        // this thread keeps the smaller key of the pair
                 if (td >= 32) {
                     __syncthreads();
 #pragma unroll
@@ -1484,13 +1484,13 @@ __global__ void __launch_bounds__(RS_THREADS, 1) route_sort_big_kernel(RoutingVi
 #pragma unroll
                     for (int u = 0; u < E; u++) {
                         const unsigned long long b = sk[u * RS_THREADS + (tid ^ td)];
-                        a[u] = (lower == asc_t) ? min(a[u], b) : max(a[u], b);
+                        a[u] = ((b < a[u]) == want_min) ? b : a[u];       // one 64-bit compare + select (min and max separately cost twice that)
                     }
                 } else {
 #pragma unroll
                     for (int u = 0; u < E; u++) {
                         const unsigned long long b = __shfl_xor_sync(0xffffffffu, a[u], td);
-                        a[u] = (lower == asc_t) ? min(a[u], b) : max(a[u], b);
+                        a[u] = ((b < a[u]) == want_min) ? b : a[u];
                     }
                 }
             }
@@ -1501,8 +1501,9 @@ __global__ void __launch_bounds__(RS_THREADS, 1) route_sort_big_kernel(RoutingVi
                     for (int u = 0; u < E; u++) {
                         if ((u & jl) == 0) {
                             const bool asc = k >= E ? asc_t : ((u & k) == 0);
-                            const unsigned long long lo = min(a[u], a[u | jl]), hi = max(a[u], a[u | jl]);
-                            a[u] = asc ? lo : hi; a[u | jl] = asc ? hi : lo;
+                            const bool sw = (a[u | jl] < a[u]) == asc;      // out of order for this direction: swap
+                            const unsigned long long t0 = a[u], t1 = a[u | jl];
+                            a[u] = sw ? t1 : t0; a[u | jl] = sw ? t0 : t1;
                         }
                     }
                 }
