@@ -342,9 +342,10 @@ int launch_route(cudaStream_t s, const RoutingView &rv, const RouteParams &p, in
 }
 
 // =====================================================================================================================
-// Fast path.  Used when (a) the HARD_CAP can never bind (T*D*probes*64 - 64 < hard_cap, so every poll of PIS:657-659
-// proceeds) and (b) the per-query working set fits in shared memory.  Then nothing in the algorithm is sequential any
-// more except the per-id improvement count, which is resolved per id from its (short) occurrence chain:
+// Fast path, first generation (one CTA per SM; today it serves the batches of at most one query per SM and the queries the two-CTA
+// kernel further down hands back).  Used when (a) the HARD_CAP can never bind (T*D*probes*64 - 64 < hard_cap, so every poll of
+// PIS:657-659 proceeds; route_fast2_kernel lifts this) and (b) the per-query working set fits in shared memory.  Then nothing in
+// the algorithm is sequential any more except the per-id improvement count, which is resolved per id from its (short) occurrence chain:
 //   kernel 1 (route_probe_kernel): one thread per (query, table, division): centre partition + probe order + scores;
 //   kernel 2 (route_fast_kernel) : one 1024-thread CTA per query, everything in shared memory:
 //        gather the <= T*D*probes*64 ids (coalesced 256-byte partition rows), insert them into an open-addressing table
