@@ -1064,17 +1064,47 @@ __global__ void __launch_bounds__(RF_THREADS, 1) refine_decrypt_kernel(const __g
                 for (int t = 0; t + 1 < gn; t++) i += (j >= __shfl_sync(0xffffffffu, my_end, g0 + t)) ? 1 : 0;
                 const int verdict = __shfl_sync(0xffffffffu, my_verdict, g0 + i);
                 const bool small = __shfl_sync(0xffffffffu, my_small ? 1 : 0, g0 + i) != 0;
-                if (j < offE) {
-                    const uint32_t pair = p.pairs[j];
-                    if (verdict == FSPANN_V_OK) {
-                        const uint32_t q = pair_query(p, pair);
-                        double d2;
-                        if (small) d2 = pair_dist2_bytes(p, dim, u8_base + (size_t)i * lay.u8_row_bytes, q);
-                        else d2 = pair_dist2(p, use_u8, use_f32, dim, reinterpret_cast<const double *>(rows_base + (size_t)i * lay.row_bytes + pt_off), q);
-                        p.dist[pair] = __dsqrt_rn(d2);
+                const bool live = j < offE;
+                const uint32_t pair = live ? p.pairs[j] : 0u;
+                const bool ok = live && verdict == FSPANN_V_OK;
+                const uint32_t q = ok ? pair_query(p, pair) : 0u;
+                // Byte path, cooperative form (dim <= 128): EIGHT lanes read one pair's 128-byte query row and record row 16 bytes each -- one
+                // coalesced line per pair instead of eight scattered 16-byte reads per lane (the kernel sits on the LSU; with two AES tables the
+                // extra shuffles made this slower, with four tables the ALU pipe has the room) -- four pairs per step, partial sums reduced over
+                // the 8 lanes, the pair's own lane picks its sum up.
+                if (dim <= 128 && __all_sync(0xffffffffu, !ok || small)) {
+                    uint32_t mine = 0;
+                    const int sub = lane & 7;
+#pragma unroll
+                    for (int st = 0; st < 8; st++) {
+                        const int src = st * 4 + (lane >> 3);
+                        const uint32_t q_s = __shfl_sync(0xffffffffu, q, src);
+                        const int i_s = __shfl_sync(0xffffffffu, i, src);
+                        const bool ok_s = __shfl_sync(0xffffffffu, ok ? 1 : 0, src) != 0;
+                        uint32_t part = 0;
+                        if (ok_s && sub * 16 < dim) {
+                            const uint4 qq = __ldg(reinterpret_cast<const uint4 *>(p.queries_u8 + (size_t)q_s * dim) + sub);
+                            const uint4 vv = *(reinterpret_cast<const uint4 *>(u8_base + (size_t)i_s * lay.u8_row_bytes) + sub);
+                            uint32_t d;
+                            d = __vabsdiffu4(qq.x, vv.x); part = __dp4a(d, d, part);
+                            d = __vabsdiffu4(qq.y, vv.y); part = __dp4a(d, d, part);
+                            d = __vabsdiffu4(qq.z, vv.z); part = __dp4a(d, d, part);
+                            d = __vabsdiffu4(qq.w, vv.w); part = __dp4a(d, d, part);
+                        }
+                        part += __shfl_xor_sync(0xffffffffu, part, 1);
+                        part += __shfl_xor_sync(0xffffffffu, part, 2);
+                        part += __shfl_xor_sync(0xffffffffu, part, 4);
+                        const uint32_t r = __shfl_sync(0xffffffffu, part, (lane & 3) * 8);
+                        if ((lane >> 2) == st) mine = r;
                     }
-                    p.verdict[pair] = (uint8_t)verdict;
+                    if (ok) p.dist[pair] = __dsqrt_rn((double)mine);
+                } else if (ok) {
+                    double d2;
+                    if (small) d2 = pair_dist2_bytes(p, dim, u8_base + (size_t)i * lay.u8_row_bytes, q);
+                    else d2 = pair_dist2(p, use_u8, use_f32, dim, reinterpret_cast<const double *>(rows_base + (size_t)i * lay.row_bytes + pt_off), q);
+                    p.dist[pair] = __dsqrt_rn(d2);
                 }
+                if (live) p.verdict[pair] = (uint8_t)verdict;
             }
             __syncwarp();
         }
